@@ -1,0 +1,188 @@
+/*
+ * oracle/ref_shim.c -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * A thin plain-pointer wrapper (ours, not reference code) around the REAL
+ * reference libswscale that oracle/build_ref.py compiles from /root/reference.
+ * It exists so Python (ctypes) can drive the reference without knowing the
+ * layouts of SwsContext/AVFrame, and so tests can read back the tables the
+ * reference computed (filters, yuv2rgb constants) to pin our own restatements.
+ *
+ * Reference entry points wrapped here:
+ *   sws_alloc_context/sws_init_context   libswscale/utils.c:1032,1884
+ *   sws_scale                            libswscale/swscale.c:1626
+ *   sws_scale_frame                      libswscale/swscale.c:1405
+ *   sws_setColorspaceDetails             libswscale/utils.c:849
+ */
+#include <stdint.h>
+#include <string.h>
+#include <time.h>
+
+#include "config.h"
+#include "libavutil/frame.h"
+#include "libavutil/imgutils.h"
+#include "libavutil/pixdesc.h"
+#include "libavutil/log.h"
+#include "libavutil/lfg.h"
+#include "libavutil/md5.h"
+#include "libswscale/swscale.h"
+#include "libswscale/swscale_internal.h"
+
+#define API __attribute__((visibility("default")))
+
+API int swsref_pix_fmt(const char *name) { return av_get_pix_fmt(name); }
+API void swsref_quiet(int level) { av_log_set_level(level); }
+
+/* opts: [0]=threads [1]=src_range [2]=dst_range [3]=src_h_chr_pos [4]=src_v_chr_pos
+ *       [5]=dst_h_chr_pos [6]=dst_v_chr_pos [7]=dither   (chr_pos: -513 = default) */
+API void *swsref_create(int sw, int sh, int sfmt, int dw, int dh, int dfmt,
+                        unsigned flags, const double *param, const int *opts)
+{
+    SwsContext *s = sws_alloc_context();
+    if (!s)
+        return NULL;
+    s->flags = flags;
+    s->src_w = sw; s->src_h = sh; s->src_format = sfmt;
+    s->dst_w = dw; s->dst_h = dh; s->dst_format = dfmt;
+    if (param) {
+        s->scaler_params[0] = param[0];
+        s->scaler_params[1] = param[1];
+    }
+    s->threads = 1;
+    if (opts) {
+        s->threads       = opts[0];
+        s->src_range     = opts[1];
+        s->dst_range     = opts[2];
+        s->src_h_chr_pos = opts[3];
+        s->src_v_chr_pos = opts[4];
+        s->dst_h_chr_pos = opts[5];
+        s->dst_v_chr_pos = opts[6];
+        s->dither        = opts[7];
+    }
+    if (sws_init_context(s, NULL, NULL) < 0) {
+        sws_freeContext(s);
+        return NULL;
+    }
+    return s;
+}
+
+API void swsref_free(void *ctx) { sws_freeContext(ctx); }
+
+API int swsref_set_colorspace(void *ctx, int src_cs, int src_range, int dst_cs,
+                              int dst_range, int brightness, int contrast, int saturation)
+{
+    return sws_setColorspaceDetails(ctx, sws_getCoefficients(src_cs), src_range,
+                                    sws_getCoefficients(dst_cs), dst_range,
+                                    brightness, contrast, saturation);
+}
+
+API int swsref_scale(void *ctx, const uint8_t *const src[4], const int src_stride[4],
+                     int y, int h, uint8_t *const dst[4], const int dst_stride[4])
+{
+    return sws_scale(ctx, src, src_stride, y, h, dst, dst_stride);
+}
+
+/* ---- refcounted frames so the threaded sws_scale_frame() path does no copies ---- */
+API void *swsref_frame_alloc(int w, int h, int fmt)
+{
+    AVFrame *f = av_frame_alloc();
+    if (!f)
+        return NULL;
+    f->width = w; f->height = h; f->format = fmt;
+    if (av_frame_get_buffer(f, 64) < 0) {
+        av_frame_free(&f);
+        return NULL;
+    }
+    return f;
+}
+API void swsref_frame_free(void *f) { AVFrame *fr = f; av_frame_free(&fr); }
+API uint8_t *swsref_frame_data(void *f, int p) { return ((AVFrame *)f)->data[p]; }
+API int swsref_frame_linesize(void *f, int p) { return ((AVFrame *)f)->linesize[p]; }
+API int swsref_scale_frame(void *ctx, void *dst, void *src)
+{
+    return sws_scale_frame(ctx, dst, src);
+}
+
+/* run `iters` conversions back to back; returns seconds (CLOCK_MONOTONIC) or <0 */
+API double swsref_bench_frame(void *ctx, void *dst, void *src, int iters)
+{
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int i = 0; i < iters; i++)
+        if (sws_scale_frame(ctx, dst, src) < 0)
+            return -1.0;
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+/* ---- introspection: what did the reference compute at init? ---- */
+static SwsInternal *first_ctx(void *ctx)
+{
+    SwsInternal *c = sws_internal(ctx);
+    if (c->nb_slice_ctx)
+        c = sws_internal(c->slice_ctx[0]);
+    return c;
+}
+
+/* which: 0=hLum 1=hChr 2=vLum 3=vChr; returns filterSize (0 if unscaled converter in use) */
+API int swsref_filter(void *ctx, int which, const int16_t **coef, const int32_t **pos, int *len)
+{
+    SwsInternal *c = first_ctx(ctx);
+    if (c->convert_unscaled || c->cascaded_context[0])
+        return 0;
+    switch (which) {
+    case 0: *coef = c->hLumFilter; *pos = c->hLumFilterPos; *len = c->opts.dst_w;  return c->hLumFilterSize;
+    case 1: *coef = c->hChrFilter; *pos = c->hChrFilterPos; *len = c->chrDstW;     return c->hChrFilterSize;
+    case 2: *coef = c->vLumFilter; *pos = c->vLumFilterPos; *len = c->opts.dst_h;  return c->vLumFilterSize;
+    case 3: *coef = c->vChrFilter; *pos = c->vChrFilterPos; *len = c->chrDstH;     return c->vChrFilterSize;
+    }
+    return -1;
+}
+
+/* out[0..5] = y_offset y_coeff v2r v2g u2g u2b; out[6]=unscaled? out[7]=cascaded?
+ * out[8..11] = chrSrcW chrSrcH chrDstW chrDstH; out[12]=srcBpc out[13]=dstBpc; out[14]=flags */
+API void swsref_info(void *ctx, int out[16])
+{
+    SwsInternal *c = first_ctx(ctx);
+    out[0] = c->yuv2rgb_y_offset;  out[1] = c->yuv2rgb_y_coeff;
+    out[2] = c->yuv2rgb_v2r_coeff; out[3] = c->yuv2rgb_v2g_coeff;
+    out[4] = c->yuv2rgb_u2g_coeff; out[5] = c->yuv2rgb_u2b_coeff;
+    out[6] = c->convert_unscaled != NULL;
+    out[7] = c->cascaded_context[0] != NULL;
+    out[8] = c->chrSrcW; out[9] = c->chrSrcH; out[10] = c->chrDstW; out[11] = c->chrDstH;
+    out[12] = c->srcBpc; out[13] = c->dstBpc; out[14] = c->opts.flags; out[15] = 0;
+}
+
+/* copy the rgb24/48 LUTs the reference built: y_table[2048]; rV/gU/bU as offsets into it */
+API int swsref_rgb_tables(void *ctx, uint8_t y_table[2048], int rV[1280], int gU[1280],
+                          int bU[1280], int gV[1280])
+{
+    SwsInternal *c = first_ctx(ctx);
+    if (!c->yuvTable || (c->dstFormatBpp != 24 && c->dstFormatBpp != 48))
+        return -1;
+    memcpy(y_table, c->yuvTable, 2048);
+    for (int i = 0; i < 1280; i++) {
+        rV[i] = (int)(c->table_rV[i] - (uint8_t *)c->yuvTable);
+        gU[i] = (int)(c->table_gU[i] - (uint8_t *)c->yuvTable);
+        bU[i] = (int)(c->table_bU[i] - (uint8_t *)c->yuvTable);
+        gV[i] = c->table_gV[i];
+    }
+    return 0;
+}
+
+/* the survey's synthetic-input recipe: av_lfg seeded, sequential fill */
+API void swsref_lfg_fill(uint8_t *buf, size_t n, unsigned seed, int bits)
+{
+    AVLFG r;
+    av_lfg_init(&r, seed);
+    if (bits <= 8) {
+        for (size_t i = 0; i < n; i++)
+            buf[i] = (uint8_t)av_lfg_get(&r);
+    } else {
+        uint16_t *p = (uint16_t *)buf;
+        unsigned mask = (1u << bits) - 1;
+        for (size_t i = 0; i < n / 2; i++)
+            p[i] = av_lfg_get(&r) & mask;
+    }
+}
+
+API void swsref_md5(uint8_t out[16], const uint8_t *buf, size_t n) { av_md5_sum(out, buf, n); }
