@@ -1,0 +1,834 @@
+/*
+ * sws_context.c -- host side of the B200 libswscale hot path (plain C).
+ *
+ * Mirrors the legacy API of the reference (libswscale/utils.c, swscale.c):
+ *   sws_alloc_context / sws_init_context / sws_getContext / sws_scale / ...
+ * Path selection (unscaled LUT converter vs. FIR pipeline), chroma geometry
+ * and flag fix-ups follow ff_sws_init_single_context() (utils.c:1137-1835);
+ * the per-line machinery it sets up is replaced by a device "plan" handed to
+ * the CUDA shim -- the B200 counterpart of ff_sws_init_swscale_<arch>()
+ * (swscale.c:697-714), installed at frame granularity like c->convert_unscaled
+ * (swscale_internal.h:99-101, swscale.c:1185).
+ */
+#include <errno.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "sws_internal.h"
+
+#define LIBSWSCALE_VERSION_MAJOR 10
+#define LIBSWSCALE_VERSION_MINOR 2
+#define LIBSWSCALE_VERSION_MICRO 100
+
+/* Minimal stand-in for libavutil's AVClass when built outside the librempeg tree
+ * (only class_name is meaningful); in-tree builds use the reference's options.c
+ * unchanged, see INTEGRATION.md. */
+struct AVClass {
+    const char *class_name;
+    const char *(*item_name)(void *ctx);
+    const void *option;
+    int version;
+};
+
+static const char *ctx_name(void *ctx) { (void)ctx; return "swscaler-b200"; }
+static const struct AVClass sws_b200_class = { "SWScaler", ctx_name, NULL, 0 };
+
+unsigned swscale_version(void)
+{
+    return (LIBSWSCALE_VERSION_MAJOR << 16) | (LIBSWSCALE_VERSION_MINOR << 8) | LIBSWSCALE_VERSION_MICRO;
+}
+const char *swscale_configuration(void) { return "b200-native sm_100a (no CPU fallback)"; }
+const char *swscale_license(void) { return "LGPL version 2.1 or later"; }
+const struct AVClass *sws_get_class(void) { return &sws_b200_class; }
+
+static void set_error(SwsInternal *c, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c->last_error, sizeof(c->last_error), fmt, ap);
+    va_end(ap);
+    if (c->opts.flags & SWS_PRINT_INFO)
+        fprintf(stderr, "[swscaler-b200] %s\n", c->last_error);
+}
+
+/* ------------------------------------------------------------ life cycle */
+
+SwsContext *sws_alloc_context(void)
+{
+    SwsInternal *c = calloc(1, sizeof(*c));
+    if (!c)
+        return NULL;
+    /* defaults of the reference's AVOption table (options.c:34-118) */
+    c->opts.av_class = &sws_b200_class;
+    c->opts.flags = SWS_BICUBIC;
+    c->opts.scaler_params[0] = SWS_PARAM_DEFAULT;
+    c->opts.scaler_params[1] = SWS_PARAM_DEFAULT;
+    c->opts.threads = 1;
+    c->opts.dither = SWS_DITHER_AUTO;
+    c->opts.alpha_blend = SWS_ALPHA_BLEND_NONE;
+    c->opts.src_w = c->opts.src_h = c->opts.dst_w = c->opts.dst_h = 16;
+    c->opts.src_v_chr_pos = c->opts.src_h_chr_pos = -513;
+    c->opts.dst_v_chr_pos = c->opts.dst_h_chr_pos = -513;
+    c->opts.intent = 1;
+    return &c->opts;
+}
+
+static void release_tables(SwsInternal *c)
+{
+    if (c->cuda)
+        ff_b200_cuda_destroy(c->cuda);
+    c->cuda = NULL;
+    ff_b200_free_fir(&c->h_lum);
+    ff_b200_free_fir(&c->h_chr);
+    ff_b200_free_fir(&c->v_lum);
+    ff_b200_free_fir(&c->v_chr);
+    c->initialized = 0;
+    c->planned = 0;
+}
+
+void sws_freeContext(SwsContext *sws)
+{
+    SwsInternal *c = sws_internal(sws);
+    if (!c)
+        return;
+    release_tables(c);
+    free(c);
+}
+
+void sws_free_context(SwsContext **pctx)
+{
+    if (!pctx || !*pctx)
+        return;
+    sws_freeContext(*pctx);
+    *pctx = NULL;
+}
+
+/* ------------------------------------------------------------ helpers */
+
+static int is_rgb(int fmt)
+{
+    const SwsPixDesc *d = ff_b200_pix_desc(fmt);
+    return d && (d->flags & SWSPF_RGB);
+}
+
+static int ceil_rshift(int a, int b) { return -((-a) >> b); }
+
+/* deprecated yuvj* ids -> plain id + full range (utils.c:773-809) */
+static int fold_jpeg_format(int *fmt)
+{
+    switch (*fmt) {
+    case AV_PIX_FMT_YUVJ420P: *fmt = AV_PIX_FMT_YUV420P; return 1;
+    case AV_PIX_FMT_YUVJ422P: *fmt = AV_PIX_FMT_YUV422P; return 1;
+    case AV_PIX_FMT_YUVJ444P: *fmt = AV_PIX_FMT_YUV444P; return 1;
+    }
+    return 0;
+}
+
+/* chroma siting -> position relative to the plane's own grid (utils.c:168-175) */
+static int local_chroma_pos(int sub, int pos)
+{
+    if (pos == -1 || pos <= -513)
+        pos = (128 << sub) - 128;
+    pos += 128;
+    return pos >> sub;
+}
+
+static int scaler_enum_to_flag(SwsScaler s, int fallback)
+{
+    switch (s) {
+    case SWS_SCALE_BILINEAR: return SWS_BILINEAR;
+    case SWS_SCALE_BICUBIC:  return SWS_BICUBIC;
+    case SWS_SCALE_POINT:    return SWS_POINT;
+    case SWS_SCALE_AREA:     return SWS_AREA;
+    case SWS_SCALE_GAUSSIAN: return SWS_GAUSS;
+    case SWS_SCALE_SINC:     return SWS_SINC;
+    case SWS_SCALE_LANCZOS:  return SWS_LANCZOS;
+    case SWS_SCALE_SPLINE:   return SWS_SPLINE;
+    default:                 return fallback;
+    }
+}
+
+/* limited<->full constants for the h-scaled lines (swscale.c:577-624) */
+static void solve_range(unsigned src_min, unsigned src_max, unsigned dst_min, unsigned dst_max,
+                        int src_shift, int mult_shift, uint32_t *coeff, int64_t *offset)
+{
+    const unsigned src_range = (uint16_t)(src_max - src_min);
+    const unsigned dst_range = (uint16_t)(dst_max - dst_min);
+    const int total = mult_shift + src_shift;
+    const uint64_t q = ((uint64_t)dst_range << total) / src_range;
+    *coeff  = (uint32_t)((q + (1ULL << src_shift) - 1) >> src_shift);
+    *offset = ((int64_t)dst_max << total) - ((int64_t)src_max << src_shift) * *coeff +
+              (1U << (mult_shift - 1));
+}
+
+static void plan_range_convert(SwsInternal *c)
+{
+    SwsCudaPlan *p = &c->plan;
+    p->range_mode = 0;
+    if (c->opts.src_range == c->opts.dst_range || is_rgb(c->opts.dst_format) || c->dst_bpc >= 32)
+        return;
+    {
+        const int bd = c->dst_bpc ? (c->dst_bpc < 16 ? c->dst_bpc : 16) : 8;
+        const int src_bits = bd <= 14 ? 15 : 19;
+        const int src_shift = src_bits - bd;
+        const int mult_shift = bd <= 14 ? 14 : 18;
+        const unsigned mpeg_min = 16U << (bd - 8), mpeg_lum = 235U << (bd - 8);
+        const unsigned mpeg_chr = 240U << (bd - 8), jpeg_max = (1U << bd) - 1;
+        if (c->opts.src_range) {   /* full -> limited */
+            solve_range(0, jpeg_max, mpeg_min, mpeg_lum, src_shift, mult_shift, &p->lum_rc_coeff, &p->lum_rc_offset);
+            solve_range(0, jpeg_max, mpeg_min, mpeg_chr, src_shift, mult_shift, &p->chr_rc_coeff, &p->chr_rc_offset);
+            p->range_mode = 2;
+        } else {                   /* limited -> full, clipped */
+            solve_range(mpeg_min, mpeg_lum, 0, jpeg_max, src_shift, mult_shift, &p->lum_rc_coeff, &p->lum_rc_offset);
+            solve_range(mpeg_min, mpeg_chr, 0, jpeg_max, src_shift, mult_shift, &p->chr_rc_coeff, &p->chr_rc_offset);
+            p->range_mode = 1;
+        }
+        if (bd <= 14) { /* the 15-bit kernels take uint16 coeff / int32 offset (swscale.c:166-216) */
+            p->lum_rc_coeff = (uint16_t)p->lum_rc_coeff;
+            p->chr_rc_coeff = (uint16_t)p->chr_rc_coeff;
+            p->lum_rc_offset = (int32_t)p->lum_rc_offset;
+            p->chr_rc_offset = (int32_t)p->chr_rc_offset;
+        }
+    }
+}
+
+static int plan_colorspace(SwsInternal *c)
+{
+    if (!is_rgb(c->opts.dst_format))
+        return 0;
+    return ff_b200_rgb_consts(&c->plan.rgb, c->src_colorspace, c->opts.src_range,
+                              c->brightness, c->contrast, c->saturation);
+}
+
+/* ------------------------------------------------------------ colourspace API */
+
+int sws_setColorspaceDetails(SwsContext *sws, const int inv_table[4], int srcRange,
+                             const int table[4], int dstRange,
+                             int brightness, int contrast, int saturation)
+{
+    SwsInternal *c = sws_internal(sws);
+    int changed;
+    if (!c || !inv_table || !table)
+        return AVERROR(EINVAL);
+
+    /* formats that are neither YUV nor gray carry no range (utils.c:844-880) */
+    if (is_rgb(sws->dst_format))
+        dstRange = 0;
+    if (is_rgb(sws->src_format))
+        srcRange = 0;
+
+    changed = !c->colorspace_set || sws->src_range != srcRange || sws->dst_range != dstRange ||
+              c->brightness != brightness || c->contrast != contrast || c->saturation != saturation ||
+              memcmp(c->src_colorspace, inv_table, sizeof(int) * 4) ||
+              memcmp(c->dst_colorspace, table, sizeof(int) * 4);
+
+    memmove(c->src_colorspace, inv_table, sizeof(int) * 4);
+    memmove(c->dst_colorspace, table, sizeof(int) * 4);
+    c->brightness = brightness;
+    c->contrast   = contrast;
+    c->saturation = saturation;
+    sws->src_range = srcRange;
+    sws->dst_range = dstRange;
+    c->colorspace_set = 1;
+
+    if (!changed || !c->initialized)
+        return 0;
+
+    if (!is_rgb(sws->dst_format) && !is_rgb(sws->src_format) &&
+        memcmp(c->dst_colorspace, c->src_colorspace, sizeof(int) * 4)) {
+        /* the reference cascades through an RGB intermediate here (utils.c:915-984) */
+        set_error(c, "YUV->YUV with differing matrices is not on the CUDA hot path");
+        return -1;
+    }
+    plan_range_convert(c);
+    if (plan_colorspace(c) < 0)
+        return -1;
+    return ff_b200_cuda_update_plan(c->cuda, &c->plan) < 0 ? -1 : 0;
+}
+
+int sws_getColorspaceDetails(SwsContext *sws, int **inv_table, int *srcRange,
+                             int **table, int *dstRange,
+                             int *brightness, int *contrast, int *saturation)
+{
+    SwsInternal *c = sws_internal(sws);
+    if (!c)
+        return -1;
+    *inv_table  = c->src_colorspace;
+    *table      = c->dst_colorspace;
+    *srcRange   = is_rgb(sws->src_format) ? 1 : sws->src_range;
+    *dstRange   = is_rgb(sws->dst_format) ? 1 : sws->dst_range;
+    *brightness = c->brightness;
+    *contrast   = c->contrast;
+    *saturation = c->saturation;
+    return 0;
+}
+
+/* ------------------------------------------------------------ init */
+
+static int dst_kind_of(int fmt, const SwsPixDesc *d)
+{
+    switch (fmt) {
+    case AV_PIX_FMT_RGB24:   return SWSC_DST_RGB24;
+    case AV_PIX_FMT_BGR24:   return SWSC_DST_BGR24;
+    case AV_PIX_FMT_RGBA:    return SWSC_DST_RGBA;
+    case AV_PIX_FMT_BGRA:    return SWSC_DST_BGRA;
+    case AV_PIX_FMT_ARGB:    return SWSC_DST_ARGB;
+    case AV_PIX_FMT_ABGR:    return SWSC_DST_ABGR;
+    case AV_PIX_FMT_RGB48LE: return SWSC_DST_RGB48;
+    case AV_PIX_FMT_BGR48LE: return SWSC_DST_BGR48;
+    case AV_PIX_FMT_NV12:    return SWSC_DST_NV12;
+    case AV_PIX_FMT_NV21:    return SWSC_DST_NV21;
+    }
+    if (d->flags & SWSPF_PLANAR)
+        return d->depth == 8 ? SWSC_DST_PLANAR8 : d->depth == 16 ? SWSC_DST_PLANAR16 : SWSC_DST_PLANARN;
+    return -1;
+}
+
+static int is_identity_bank(const SwsFirBank *b, int one)
+{
+    if (b->size != 1)
+        return 0;
+    for (int i = 0; i < b->len; i++)
+        if (b->coef[i] != one || b->pos[i] != i)
+            return 0;
+    return 1;
+}
+
+/* 1-tap bank: output i reads source sample i >> shift */
+static int nearest_bank(SwsFirBank *b, int len, int one, int shift)
+{
+    ff_b200_free_fir(b);
+    b->coef = malloc(sizeof(*b->coef) * (size_t)len);
+    b->pos  = malloc(sizeof(*b->pos) * (size_t)len);
+    if (!b->coef || !b->pos) {
+        ff_b200_free_fir(b);
+        return AVERROR(ENOMEM);
+    }
+    for (int i = 0; i < len; i++) {
+        b->coef[i] = (int16_t)one;
+        b->pos[i]  = i >> shift;
+    }
+    b->size = 1;
+    b->len  = len;
+    return 0;
+}
+
+static int init_single(SwsContext *sws, int with_device)
+{
+    SwsInternal *c = sws_internal(sws);
+    SwsCudaPlan *p = &c->plan;
+    const int srcW = sws->src_w, srcH = sws->src_h, dstW = sws->dst_w, dstH = sws->dst_h;
+    const SwsPixDesc *sd, *dd;
+    unsigned flags = sws->flags;
+    int scaler, lum_scaler, chr_scaler, unscaled, ret;
+    int64_t lum_xinc, lum_yinc, chr_xinc, chr_yinc;
+    SwsFirSpec spec;
+
+    if (!c->colorspace_set)
+        sws_setColorspaceDetails(sws, sws_getCoefficients(SWS_CS_DEFAULT), sws->src_range,
+                                 sws_getCoefficients(SWS_CS_DEFAULT), sws->dst_range, 0, 1 << 16, 1 << 16);
+
+    sd = ff_b200_pix_desc(sws->src_format);
+    dd = ff_b200_pix_desc(sws->dst_format);
+    if (!sd || !sd->as_input) {
+        set_error(c, "pixel format %d is not supported as input", sws->src_format);
+        return AVERROR(EINVAL);
+    }
+    if (!dd || !dd->as_output) {
+        set_error(c, "pixel format %d is not supported as output", sws->dst_format);
+        return AVERROR(EINVAL);
+    }
+
+    /* exactly one scaler; bicubic by default (utils.c:1196-1234) */
+    scaler = flags & (SWS_POINT | SWS_AREA | SWS_BILINEAR | SWS_FAST_BILINEAR | SWS_BICUBIC | SWS_X |
+                      SWS_GAUSS | SWS_LANCZOS | SWS_SINC | SWS_SPLINE | SWS_BICUBLIN);
+    if (!scaler) {
+        scaler = SWS_BICUBIC;
+        flags |= scaler;
+        sws->flags = flags;
+    } else if (scaler & (scaler - 1)) {
+        set_error(c, "exactly one scaler algorithm must be chosen, got %X", scaler);
+        return AVERROR(EINVAL);
+    }
+    if (scaler == SWS_FAST_BILINEAR) {
+        set_error(c, "SWS_FAST_BILINEAR is outside the CUDA hot path (SURVEY.md 2.2)");
+        return AVERROR(ENOTSUP);
+    }
+    lum_scaler = scaler_enum_to_flag(sws->scaler, scaler == SWS_BICUBLIN ? SWS_BICUBIC : scaler);
+    chr_scaler = scaler_enum_to_flag(sws->scaler_sub ? sws->scaler_sub : sws->scaler,
+                                     scaler == SWS_BICUBLIN ? SWS_BILINEAR : scaler);
+
+    if (srcW < 1 || srcH < 1 || dstW < 1 || dstH < 1) {
+        set_error(c, "%dx%d -> %dx%d is invalid scaling dimension", srcW, srcH, dstW, dstH);
+        return AVERROR(EINVAL);
+    }
+    if (sws->gamma_flag || (flags & SWS_SRC_V_CHR_DROP_MASK) ||
+        sws->dither == SWS_DITHER_ED || (flags & SWS_ERROR_DIFFUSION)) {
+        set_error(c, "gamma / chroma-drop / error-diffusion are outside the CUDA hot path");
+        return AVERROR(ENOTSUP);
+    }
+
+    unscaled = srcW == dstW && srcH == dstH;
+    lum_xinc = (((int64_t)srcW << 16) + (dstW >> 1)) / dstW;
+    lum_yinc = (((int64_t)srcH << 16) + (dstH >> 1)) / dstH;
+
+    c->chr_src_hsub = sd->log2_cw; c->chr_src_vsub = sd->log2_ch;
+    c->chr_dst_hsub = dd->log2_cw; c->chr_dst_vsub = dd->log2_ch;
+    c->dst_slice_align = 1 << c->chr_dst_vsub;
+
+    /* packed RGB shares one chroma pair between two pixels unless forced (utils.c:1270-1360) */
+    if (is_rgb(sws->dst_format) && !(flags & SWS_FULL_CHR_H_INT)) {
+        if (dstW & 1)
+            flags |= SWS_FULL_CHR_H_INT;
+        if (c->chr_src_hsub == 0 && c->chr_src_vsub == 0 && sws->dither != SWS_DITHER_BAYER)
+            flags |= SWS_FULL_CHR_H_INT;
+        sws->flags = flags;
+    }
+    if (is_rgb(sws->dst_format) && !(flags & SWS_FULL_CHR_H_INT))
+        c->chr_dst_hsub = 1;
+
+    c->chr_src_w = ceil_rshift(srcW, c->chr_src_hsub);
+    c->chr_src_h = ceil_rshift(srcH, c->chr_src_vsub);
+    c->chr_dst_w = ceil_rshift(dstW, c->chr_dst_hsub);
+    c->chr_dst_h = ceil_rshift(dstH, c->chr_dst_vsub);
+    c->src_bpc = sd->depth < 8 ? 8 : sd->depth;
+    c->dst_bpc = dd->depth < 8 ? 8 : dd->depth;
+
+    chr_xinc = (((int64_t)c->chr_src_w << 16) + (c->chr_dst_w >> 1)) / c->chr_dst_w;
+    chr_yinc = (((int64_t)c->chr_src_h << 16) + (c->chr_dst_h >> 1)) / c->chr_dst_h;
+    if (chr_xinc < 10 || chr_xinc > INT32_MAX || chr_yinc < 10 || chr_yinc > INT32_MAX ||
+        lum_xinc < 10 || lum_xinc > INT32_MAX || lum_yinc < 10 || lum_yinc > INT32_MAX)
+        return AVERROR_PATCHWELCOME;
+
+    /* which special converter would the reference install? (utils.c:1624-1637,
+     * swscale_unscaled.c:2392-2731) */
+    c->unscaled_lut = 0;
+    if (unscaled && (sws->src_range == sws->dst_range || is_rgb(sws->dst_format))) {
+        const int planar_yuv_pair = !is_rgb(sws->src_format) && !is_rgb(sws->dst_format);
+        if ((sws->src_format == AV_PIX_FMT_YUV420P || sws->src_format == AV_PIX_FMT_YUV422P) &&
+            is_rgb(sws->dst_format) && !(flags & SWS_ACCURATE_RND) &&
+            (sws->dither == SWS_DITHER_BAYER || sws->dither == SWS_DITHER_AUTO) && !(dstH & 1)) {
+            c->unscaled_lut = 1;        /* yuv2rgb_c_* nearest-chroma LUT converter (a13) */
+            c->dst_slice_align = 2;
+        } else if (planar_yuv_pair && c->chr_src_hsub == c->chr_dst_hsub &&
+                   c->chr_src_vsub == c->chr_dst_vsub && sd->depth != dd->depth &&
+                   !!(sd->flags & SWSPF_SEMI) == !!(dd->flags & SWSPF_SEMI)) {
+            /* planarCopyWrapper's dithered depth conversion is not restated yet */
+            set_error(c, "unscaled planar bit-depth conversion is not on the CUDA hot path yet");
+            return AVERROR(ENOTSUP);
+        }
+    }
+    if ((flags & SWS_FULL_CHR_H_INT) && is_rgb(sws->dst_format) && !c->unscaled_lut) {
+        set_error(c, "full-chroma RGB output (odd width / 4:4:4 source) is not on the CUDA hot path yet");
+        return AVERROR(ENOTSUP);
+    }
+
+    /* ---- FIR banks: horizontal 1<<14, vertical 1<<12 (utils.c:1681-1729) ---- */
+    memset(&spec, 0, sizeof(spec));
+    spec.flags = flags;
+    spec.param[0] = sws->scaler_params[0];
+    spec.param[1] = sws->scaler_params[1];
+
+    spec.one = 1 << 14;
+    spec.inc = lum_xinc; spec.src_len = srcW; spec.dst_len = dstW; spec.scaler = lum_scaler;
+    spec.src_pos = local_chroma_pos(0, 0); spec.dst_pos = local_chroma_pos(0, 0);
+    if ((ret = ff_b200_build_fir(&c->h_lum, &spec)) < 0)
+        goto fir_fail;
+    spec.inc = chr_xinc; spec.src_len = c->chr_src_w; spec.dst_len = c->chr_dst_w; spec.scaler = chr_scaler;
+    spec.src_pos = local_chroma_pos(c->chr_src_hsub, sws->src_h_chr_pos);
+    spec.dst_pos = local_chroma_pos(c->chr_dst_hsub, sws->dst_h_chr_pos);
+    if ((ret = ff_b200_build_fir(&c->h_chr, &spec)) < 0)
+        goto fir_fail;
+
+    spec.one = 1 << 12;
+    spec.inc = lum_yinc; spec.src_len = srcH; spec.dst_len = dstH; spec.scaler = lum_scaler;
+    spec.src_pos = local_chroma_pos(0, 0); spec.dst_pos = local_chroma_pos(0, 0);
+    if ((ret = ff_b200_build_fir(&c->v_lum, &spec)) < 0)
+        goto fir_fail;
+    spec.inc = chr_yinc; spec.src_len = c->chr_src_h; spec.dst_len = c->chr_dst_h; spec.scaler = chr_scaler;
+    spec.src_pos = local_chroma_pos(c->chr_src_vsub, sws->src_v_chr_pos);
+    spec.dst_pos = local_chroma_pos(c->chr_dst_vsub, sws->dst_v_chr_pos);
+    if ((ret = ff_b200_build_fir(&c->v_chr, &spec)) < 0)
+        goto fir_fail;
+
+    if (c->unscaled_lut) {
+        /* a13 samples chroma at column x>>1, row y>>vsub with no filtering and ignores
+         * chroma siting (yuv2rgb.c:137-236): express that as 1-tap banks so the same kernels
+         * serve it.  Arithmetic is identical: ((u<<7)*4096 + 2^18) >> 19 == u. */
+        if ((ret = nearest_bank(&c->h_chr, c->chr_dst_w, 1 << 14, 0)) < 0 ||
+            (ret = nearest_bank(&c->v_chr, c->chr_dst_h, 1 << 12, c->chr_src_vsub)) < 0)
+            goto fir_fail;
+    }
+
+    /* ---- device plan ---- */
+    memset(p, 0, sizeof(*p));
+    p->src_w = srcW; p->src_h = srcH; p->dst_w = dstW; p->dst_h = dstH;
+    p->chr_src_w = c->chr_src_w; p->chr_src_h = c->chr_src_h;
+    p->chr_dst_w = c->chr_dst_w; p->chr_dst_h = c->chr_dst_h;
+    p->chr_src_hsub = c->chr_src_hsub; p->chr_src_vsub = c->chr_src_vsub;
+    p->chr_dst_hsub = c->chr_dst_hsub; p->chr_dst_vsub = c->chr_dst_vsub;
+    p->src_layout = (sd->flags & SWSPF_SEMI) ? (sd->swap_uv ? SWSC_SRC_NV21 : SWSC_SRC_NV12) : SWSC_SRC_PLANAR;
+    p->dst_kind = dst_kind_of(sws->dst_format, dd);
+    p->src_bits = c->src_bpc;
+    p->dst_bits = c->dst_bpc;
+    p->has_chroma = 1;
+    p->unscaled_lut = c->unscaled_lut;
+    /* hScale selection (swscale.c:675-688) and its shift (swscale.c:69-159) */
+    p->inter_bits = c->dst_bpc > 14 ? 19 : 15;
+    if (c->src_bpc == 8)
+        p->h_shift = p->inter_bits == 15 ? 7 : 3;
+    else
+        p->h_shift = p->inter_bits == 15 ? c->src_bpc - 1 : c->src_bpc - 1 - 4;
+    /* 8-bit planar output of >8-bit sources is dithered (swscale.c:291-292,385-387,519-522) */
+    p->dither_bayer = c->src_bpc > 8;
+    plan_range_convert(c);
+    if ((ret = plan_colorspace(c)) < 0) {
+        set_error(c, "colourspace constants overflow the int32 kernel arithmetic");
+        return ret;
+    }
+    p->lum_identity = is_identity_bank(&c->h_lum, 1 << 14) && is_identity_bank(&c->v_lum, 1 << 12);
+    p->chr_h_identity = is_identity_bank(&c->h_chr, 1 << 14);
+
+    if (!with_device) {
+        c->planned = 1;
+        return 0;
+    }
+    ret = ff_b200_cuda_create(&c->cuda, p, &c->h_lum, &c->h_chr, &c->v_lum, &c->v_chr);
+    if (ret < 0) {
+        set_error(c, "CUDA initialisation failed (%d): no CPU fallback exists on this path", ret);
+        return ret;
+    }
+    c->dst_y = 0;
+    c->slice_dir = 0;
+    c->rows_received = 0;
+    c->initialized = 1;
+    return 0;
+
+fir_fail:
+    if (ret == SWS_B200_USE_CASCADE) {
+        set_error(c, "filter too long: the reference would cascade two contexts (utils.c:1803-1832)");
+        ret = AVERROR(ENOTSUP);
+    } else {
+        set_error(c, "filter construction failed (%d)", ret);
+    }
+    return ret;
+}
+
+int sws_init_context(SwsContext *sws, SwsFilter *srcFilter, SwsFilter *dstFilter)
+{
+    SwsInternal *c = sws_internal(sws);
+    int ret;
+    if (!c)
+        return AVERROR(EINVAL);
+    if (srcFilter || dstFilter) {
+        set_error(c, "SwsFilter pre/post filters are outside the CUDA hot path");
+        return AVERROR(ENOTSUP);
+    }
+    release_tables(c);
+    sws->src_range |= fold_jpeg_format(&sws->src_format);
+    sws->dst_range |= fold_jpeg_format(&sws->dst_format);
+    ret = init_single(sws, 1);
+    if (ret < 0)
+        release_tables(c);
+    return ret;
+}
+
+/* ------------------------------------------------------------ diagnostics
+ * Host-side planning without touching a device, so the table builders can be
+ * pinned against the reference on machines that have no GPU. */
+int sws_b200_plan_only(SwsContext *sws)
+{
+    SwsInternal *c = sws_internal(sws);
+    int ret;
+    if (!c)
+        return AVERROR(EINVAL);
+    release_tables(c);
+    sws->src_range |= fold_jpeg_format(&sws->src_format);
+    sws->dst_range |= fold_jpeg_format(&sws->dst_format);
+    ret = init_single(sws, 0);
+    if (ret < 0)
+        release_tables(c);
+    return ret;
+}
+
+int sws_b200_get_filter(SwsContext *sws, int which, const int16_t **coef, const int32_t **pos, int *len)
+{
+    SwsInternal *c = sws_internal(sws);
+    const SwsFirBank *b;
+    if (!c || (!c->planned && !c->initialized))
+        return AVERROR(EINVAL);
+    b = which == 0 ? &c->h_lum : which == 1 ? &c->h_chr : which == 2 ? &c->v_lum : which == 3 ? &c->v_chr : NULL;
+    if (!b || !b->coef)
+        return AVERROR(EINVAL);
+    *coef = b->coef;
+    *pos  = b->pos;
+    *len  = b->len;
+    return b->size;
+}
+
+int sws_b200_get_info(SwsContext *sws, int out[32])
+{
+    SwsInternal *c = sws_internal(sws);
+    const SwsCudaPlan *p;
+    if (!c || (!c->planned && !c->initialized))
+        return AVERROR(EINVAL);
+    p = &c->plan;
+    memset(out, 0, sizeof(int) * 32);
+    out[0] = p->rgb.y_offset; out[1] = p->rgb.y_coeff; out[2] = p->rgb.v2r; out[3] = p->rgb.v2g;
+    out[4] = p->rgb.u2g;      out[5] = p->rgb.u2b;     out[6] = c->unscaled_lut;
+    out[8] = c->chr_src_w;    out[9] = c->chr_src_h;   out[10] = c->chr_dst_w; out[11] = c->chr_dst_h;
+    out[12] = c->src_bpc;     out[13] = c->dst_bpc;    out[14] = (int)sws->flags;
+    out[15] = p->rgb.cy;      out[16] = p->rgb.yb;     out[17] = p->rgb.crv;   out[18] = p->rgb.cbu;
+    out[19] = p->rgb.cgu;     out[20] = p->rgb.cgv;    out[21] = p->rgb.base_r; out[22] = p->rgb.base_g;
+    out[23] = p->rgb.base_b;  out[24] = p->range_mode; out[25] = (int)p->lum_rc_coeff;
+    out[26] = (int)p->chr_rc_coeff; out[27] = p->lum_identity; out[28] = p->chr_h_identity;
+    out[29] = p->h_shift;     out[30] = p->inter_bits; out[31] = p->dst_kind;
+    return 0;
+}
+
+SwsContext *sws_getContext(int srcW, int srcH, enum AVPixelFormat srcFormat,
+                           int dstW, int dstH, enum AVPixelFormat dstFormat,
+                           int flags, SwsFilter *srcFilter,
+                           SwsFilter *dstFilter, const double *param)
+{
+    SwsContext *sws = sws_alloc_context();
+    if (!sws)
+        return NULL;
+    sws->flags = (unsigned)flags;
+    sws->src_w = srcW; sws->src_h = srcH; sws->src_format = srcFormat;
+    sws->dst_w = dstW; sws->dst_h = dstH; sws->dst_format = dstFormat;
+    for (int i = 0; param && i < SWS_NUM_SCALER_PARAMS; i++)
+        sws->scaler_params[i] = param[i];
+    if (sws_init_context(sws, srcFilter, dstFilter) < 0) {
+        if (flags & SWS_PRINT_INFO)
+            fprintf(stderr, "[swscaler-b200] sws_getContext failed: %s\n", sws_internal(sws)->last_error);
+        sws_freeContext(sws);
+        return NULL;
+    }
+    return sws;
+}
+
+SwsContext *sws_getCachedContext(SwsContext *prev, int srcW, int srcH,
+                                 enum AVPixelFormat srcFormat, int dstW, int dstH,
+                                 enum AVPixelFormat dstFormat, int flags,
+                                 SwsFilter *srcFilter, SwsFilter *dstFilter,
+                                 const double *param)
+{
+    static const double default_param[SWS_NUM_SCALER_PARAMS] = { SWS_PARAM_DEFAULT, SWS_PARAM_DEFAULT };
+    if (!param)
+        param = default_param;
+    if (prev && (prev->src_w != srcW || prev->src_h != srcH || prev->src_format != (int)srcFormat ||
+                 prev->dst_w != dstW || prev->dst_h != dstH || prev->dst_format != (int)dstFormat ||
+                 prev->flags != (unsigned)flags || prev->scaler_params[0] != param[0] ||
+                 prev->scaler_params[1] != param[1])) {
+        sws_freeContext(prev);
+        prev = NULL;
+    }
+    if (!prev)
+        return sws_getContext(srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags,
+                              srcFilter, dstFilter, param);
+    return prev;
+}
+
+/* ------------------------------------------------------------ sws_scale */
+
+/* last source rows (luma, chroma) output row y needs; mirrors swscale.c:412-425 */
+static void rows_needed(const SwsInternal *c, int y, int *last_lum, int *last_chr)
+{
+    const int vsub_mask = (1 << c->chr_dst_vsub) - 1;
+    int y2 = y | vsub_mask;
+    int first_l, first_c;
+    if (y2 > c->opts.dst_h - 1)
+        y2 = c->opts.dst_h - 1;
+    first_l = c->v_lum.pos[y2];
+    if (first_l < 1 - c->v_lum.size)
+        first_l = 1 - c->v_lum.size;
+    first_c = c->v_chr.pos[y >> c->chr_dst_vsub];
+    if (first_c < 1 - c->v_chr.size)
+        first_c = 1 - c->v_chr.size;
+    *last_lum = first_l + c->v_lum.size - 1;
+    if (*last_lum > c->opts.src_h - 1)
+        *last_lum = c->opts.src_h - 1;
+    *last_chr = first_c + c->v_chr.size - 1;
+    if (*last_chr > c->chr_src_h - 1)
+        *last_chr = c->chr_src_h - 1;
+}
+
+int sws_scale(SwsContext *sws, const uint8_t *const srcSlice[], const int srcStride[],
+              int srcSliceY, int srcSliceH, uint8_t *const dst[], const int dstStride[])
+{
+    SwsInternal *c = sws_internal(sws);
+    int macro_src, y0, y1, ret, avail_l, avail_c;
+
+    if (!c || !c->initialized)
+        return AVERROR(EINVAL);
+    if (!srcStride || !dstStride || !dst || !srcSlice) {
+        set_error(c, "one of the input parameters to sws_scale() is NULL");
+        return AVERROR(EINVAL);
+    }
+    macro_src = 1 << c->chr_src_vsub;
+    if ((srcSliceY & (macro_src - 1)) ||
+        ((srcSliceH & (macro_src - 1)) && srcSliceY + srcSliceH != sws->src_h) ||
+        srcSliceY + srcSliceH > sws->src_h || srcSliceY < 0 || srcSliceH < 0) {
+        set_error(c, "slice parameters %d, %d are invalid", srcSliceY, srcSliceH);
+        return AVERROR(EINVAL);
+    }
+    if (!srcSlice[0] || !dst[0]) {
+        set_error(c, "bad image pointers");
+        return AVERROR(EINVAL);
+    }
+    if (srcSliceH == 0)
+        return 0;
+
+    if (!c->slice_dir) {
+        if (srcSliceY != 0 && srcSliceY + srcSliceH != sws->src_h) {
+            set_error(c, "slices start in the middle");
+            return AVERROR(EINVAL);
+        }
+        if (srcSliceY != 0) {
+            set_error(c, "bottom-to-top slice order is not on the CUDA hot path");
+            return AVERROR(ENOTSUP);
+        }
+        c->slice_dir = 1;
+        c->dst_y = 0;
+    }
+    if (srcSliceY == 0)
+        c->dst_y = 0;
+
+    /* how far can the output advance with the rows received so far?  Same rule as the
+     * reference's enough_lines test (swscale.c:462-470). */
+    avail_l = srcSliceY + srcSliceH;
+    avail_c = ceil_rshift(srcSliceY + srcSliceH, c->chr_src_vsub);
+    y0 = c->dst_y;
+    if (c->unscaled_lut) {
+        /* the unscaled converter maps slice rows 1:1 (swscale.c:1161-1187) */
+        y0 = srcSliceY;
+        y1 = srcSliceY + srcSliceH;
+    } else {
+        for (y1 = y0; y1 < sws->dst_h; y1++) {
+            int ll, lc;
+            rows_needed(c, y1, &ll, &lc);
+            if (!(ll < avail_l && lc < avail_c))
+                break;
+        }
+    }
+
+    ret = ff_b200_cuda_scale_host(c->cuda, srcSlice, srcStride, srcSliceY, srcSliceH, 1,
+                                  dst, dstStride, y0, y1);
+    if (ret < 0) {
+        set_error(c, "CUDA conversion failed (%d)", ret);
+        return ret;
+    }
+    c->dst_y = y1;
+    if (srcSliceY + srcSliceH == sws->src_h)
+        c->slice_dir = 0;
+    return y1 - y0;
+}
+
+/* ------------------------------------------------------------ CUDA extension */
+
+int sws_cuda_scale_batch(SwsContext *sws, const uint8_t *const src[4], const int srcStride[4],
+                         const int64_t srcFrameStride[4], uint8_t *const dst[4],
+                         const int dstStride[4], const int64_t dstFrameStride[4], int nb_frames)
+{
+    SwsInternal *c = sws_internal(sws);
+    int ret;
+    if (!c || !c->initialized || !src || !dst || nb_frames < 1)
+        return AVERROR(EINVAL);
+    ret = ff_b200_cuda_launch(c->cuda, src, srcStride, srcFrameStride, dst, dstStride,
+                              dstFrameStride, nb_frames, 0, sws->dst_h);
+    return ret < 0 ? ret : sws->dst_h;
+}
+
+int sws_cuda_sync(SwsContext *sws)
+{
+    SwsInternal *c = sws_internal(sws);
+    return c && c->cuda ? ff_b200_cuda_sync(c->cuda) : AVERROR(EINVAL);
+}
+
+void *sws_cuda_stream(SwsContext *sws)
+{
+    SwsInternal *c = sws_internal(sws);
+    return c && c->cuda ? ff_b200_cuda_stream(c->cuda) : NULL;
+}
+
+long sws_cuda_launch_count(SwsContext *sws)
+{
+    SwsInternal *c = sws_internal(sws);
+    return c && c->cuda ? ff_b200_cuda_launch_count(c->cuda) : 0;
+}
+
+const char *sws_cuda_kernel_name(SwsContext *sws)
+{
+    SwsInternal *c = sws_internal(sws);
+    return c && c->cuda ? ff_b200_cuda_kernel_name(c->cuda) : "";
+}
+
+const char *sws_cuda_last_error(SwsContext *sws)
+{
+    SwsInternal *c = sws_internal(sws);
+    return c ? c->last_error : "";
+}
+
+/* ------------------------------------------------------------ SwsVector helpers
+ * (utils.c:1956-2248; only the subset callers of the legacy API use) */
+
+SwsVector *sws_allocVec(int length)
+{
+    SwsVector *v;
+    if (length <= 0 || length > (int)(INT32_MAX / sizeof(double)))
+        return NULL;
+    v = malloc(sizeof(*v));
+    if (!v)
+        return NULL;
+    v->length = length;
+    v->coeff = malloc(sizeof(double) * (size_t)length);
+    if (!v->coeff) {
+        free(v);
+        return NULL;
+    }
+    return v;
+}
+
+void sws_scaleVec(SwsVector *a, double scalar)
+{
+    for (int i = 0; i < a->length; i++)
+        a->coeff[i] *= scalar;
+}
+
+void sws_normalizeVec(SwsVector *a, double height)
+{
+    double sum = 0;
+    for (int i = 0; i < a->length; i++)
+        sum += a->coeff[i];
+    sws_scaleVec(a, height / sum);
+}
+
+SwsVector *sws_getGaussianVec(double variance, double quality)
+{
+    const int length = (int)(variance * quality + 0.5) | 1;
+    const double middle = (length - 1) * 0.5;
+    SwsVector *v;
+    if (variance < 0 || quality < 0)
+        return NULL;
+    v = sws_allocVec(length);
+    if (!v)
+        return NULL;
+    for (int i = 0; i < length; i++) {
+        double dist = i - middle;
+        v->coeff[i] = exp(-dist * dist / (2 * variance * variance)) / sqrt(2 * variance * M_PI);
+    }
+    sws_normalizeVec(v, 1.0);
+    return v;
+}
+
+void sws_freeVec(SwsVector *a)
+{
+    if (!a)
+        return;
+    free(a->coeff);
+    free(a);
+}

@@ -1,0 +1,739 @@
+/*
+ * sws_cuda.cu -- sm_100a kernels + the C-ABI shim of the B200 libswscale hot path.
+ *
+ * One fused kernel per output tile replaces the reference's per-line pipeline
+ *   lumToYV12/chrToYV12  -> hyScale/hcScale -> [lum/chrConvertRange]
+ *   -> yuv2plane1/X | yuv2nv12cX | yuv2packed1/2/X
+ * (libswscale/input.c:926-941, swscale.c:69-255, output.c:163-528,1115-1196,
+ *  1788-1939; scheduling in swscale.c:263-567 and vscale.c:41-171).
+ *
+ * Bit-exactness rules honoured here:
+ *  - the h-scaled lines are materialised exactly as the reference stores them
+ *    (int16 clipped to 15 bits, or int32 clipped to 19 bits) in shared memory;
+ *    H and V filters are never merged algebraically;
+ *  - all accumulations wrap in 32 bits exactly where the C code's `unsigned`
+ *    casts make them wrap; right shifts of signed values are arithmetic;
+ *  - the 8-bit RGB LUT chain is evaluated in closed form (sws_colorspace.c).
+ */
+#include <cuda_runtime.h>
+#include <climits>
+#include <type_traits>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <errno.h>
+
+#include "sws_internal.h"
+
+#define CUDA_OK(call)                                                           \
+    do {                                                                        \
+        cudaError_t e_ = (call);                                                \
+        if (e_ != cudaSuccess) {                                                \
+            fprintf(stderr, "[swscaler-b200] %s failed: %s (%s:%d)\n", #call,   \
+                    cudaGetErrorString(e_), __FILE__, __LINE__);                \
+            return AVERROR(EIO);                                                \
+        }                                                                       \
+    } while (0)
+
+/* ordered-dither rows for 8-bit planar output of >8-bit sources; same matrix as
+ * ff_dither_8x8_128 (reference swscale.c:42-52) */
+__constant__ uint8_t c_dither_8x8_128[8][8] = {
+    {  36, 68,  60, 92,  34, 66,  58, 90 },
+    { 100,  4, 124, 28,  98,  2, 122, 26 },
+    {  52, 84,  44, 76,  50, 82,  42, 74 },
+    { 116, 20, 108, 12, 114, 18, 106, 10 },
+    {  32, 64,  56, 88,  38, 70,  62, 94 },
+    {  96,  0, 120, 24, 102,  6, 126, 30 },
+    {  48, 80,  40, 72,  54, 86,  46, 78 },
+    { 112, 16, 104,  8, 118, 22, 110, 14 },
+};
+
+struct FrameArgs {
+    const uint8_t *src[4];
+    uint8_t *dst[4];
+    long long src_fstride[4];
+    long long dst_fstride[4];
+    int src_stride[4];
+    int dst_stride[4];
+    int y0, y1;          /* destination row range */
+    int tile_w, tile_h;  /* luma output tile */
+    int rows_l_cap, rows_c_cap; /* shared-memory row capacity */
+};
+
+__device__ __forceinline__ int clip_u8(int v) { return min(max(v, 0), 255); }
+__device__ __forceinline__ int clip_uintp2(int v, int bits) { return min(max(v, 0), (1 << bits) - 1); }
+__device__ __forceinline__ int clip_i16(int v) { return min(max(v, -32768), 32767); }
+
+template <bool SRC16>
+__device__ __forceinline__ int fetch(const uint8_t *row, int idx)
+{
+    if (SRC16)
+        return reinterpret_cast<const uint16_t *>(row)[idx];
+    return row[idx];
+}
+
+/* ------------------------------------------------------------------------
+ * Generic fused tile kernel: table-driven H FIR -> (range) -> V FIR -> pack.
+ *   SRC16   : source samples are 16-bit containers (9..16 bit depths)
+ *   INTER32 : h-scaled lines are 19-bit int32 (dst depth > 14) else 15-bit int16
+ * grid = (tiles_x, tiles_y, frames), block = 256 threads, dynamic smem.
+ * ------------------------------------------------------------------------ */
+template <bool SRC16, bool INTER32>
+__global__ void __launch_bounds__(256)
+sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_constant__ FrameArgs A)
+{
+    typedef typename std::conditional<INTER32, int32_t, int16_t>::type inter_t;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    const int f = blockIdx.z;
+    const uint8_t *src0 = A.src[0] + f * A.src_fstride[0];
+    const uint8_t *src1 = A.src[1] ? A.src[1] + f * A.src_fstride[1] : nullptr;
+    const uint8_t *src2 = A.src[2] ? A.src[2] + f * A.src_fstride[2] : nullptr;
+    uint8_t *dst0 = A.dst[0] + f * A.dst_fstride[0];
+    uint8_t *dst1 = A.dst[1] ? A.dst[1] + f * A.dst_fstride[1] : nullptr;
+    uint8_t *dst2 = A.dst[2] ? A.dst[2] + f * A.dst_fstride[2] : nullptr;
+
+    const int TW = A.tile_w, TH = A.tile_h;
+    const int x0 = blockIdx.x * TW;
+    const int ry0 = A.y0 + blockIdx.y * TH;
+    const int ry1 = min(ry0 + TH, A.y1);
+    const int tw = min(TW, P.dst_w - x0);            /* luma columns in this tile */
+    const int th = ry1 - ry0;
+
+    /* chroma output window of the tile */
+    const int hs = P.chr_dst_hsub, vs = P.chr_dst_vsub;
+    const int CW = TW >> hs;
+    const int cx0 = x0 >> hs;
+    const int cw = min(CW, P.chr_dst_w - cx0);
+    const int cy0 = ry0 >> vs;
+    const int cy1 = (ry1 == P.dst_h) ? P.chr_dst_h : (ry1 >> vs);
+    const int ch = cy1 - cy0;
+
+    inter_t *hb_l = reinterpret_cast<inter_t *>(smem_raw);
+    inter_t *hb_u = hb_l + (size_t)A.rows_l_cap * TW;
+    inter_t *hb_v = hb_u + (size_t)A.rows_c_cap * CW;
+
+    /* source row windows (positions are monotonic; take min/max defensively) */
+    int lo_l = INT_MAX, hi_l = 0, lo_c = INT_MAX, hi_c = 0;
+    for (int y = ry0; y < ry1; y++) {
+        int p = P.vl_pos[y];
+        lo_l = min(lo_l, p);
+        hi_l = max(hi_l, p + P.vl_size);
+    }
+    for (int y = cy0; y < cy1; y++) {
+        int p = P.vc_pos[y];
+        lo_c = min(lo_c, p);
+        hi_c = max(hi_c, p + P.vc_size);
+    }
+    lo_l = max(lo_l, 0); lo_c = max(lo_c, 0);
+    const int nl = min(hi_l - lo_l, A.rows_l_cap);
+    const int nc = (ch > 0) ? min(hi_c - lo_c, A.rows_c_cap) : 0;
+
+    const int h_max = INTER32 ? (1 << 19) - 1 : (1 << 15) - 1;
+    const int sh = P.h_shift;
+
+    /* ---- stage H, luma ---- */
+    {
+        const int fs = P.hl_size;
+        for (int idx = threadIdx.x; idx < nl * TW; idx += blockDim.x) {
+            const int r = idx / TW, x = idx - r * TW;
+            if (x >= tw)
+                continue;
+            const int sy = min(lo_l + r, P.src_h - 1);
+            const uint8_t *row = src0 + (size_t)sy * A.src_stride[0];
+            const int gx = x0 + x;
+            const int pos = P.hl_pos[gx];
+            const int16_t *co = P.hl_coef + (size_t)gx * fs;
+            int val = 0;
+            for (int j = 0; j < fs; j++)
+                val += fetch<SRC16>(row, min(pos + j, P.src_w - 1)) * (int)co[j];
+            val = min(val >> sh, h_max);
+            if (P.range_mode) {
+                if (!INTER32) {
+                    val = (val * (int)P.lum_rc_coeff + (int)P.lum_rc_offset) >> 14;
+                    if (P.range_mode == 1)
+                        val = min(val, (1 << 15) - 1);
+                    val = (int16_t)val;
+                } else {
+                    val = (int)(((long long)val * P.lum_rc_coeff + P.lum_rc_offset) >> 18);
+                    if (P.range_mode == 1)
+                        val = min(val, (1 << 19) - 1);
+                }
+            }
+            hb_l[idx] = (inter_t)val;
+        }
+    }
+    /* ---- stage H, chroma (input unpack of nv12/nv21 fused into the fetch) ---- */
+    if (P.has_chroma && ch > 0) {
+        const int fs = P.hc_size;
+        const int layout = P.src_layout;
+        for (int idx = threadIdx.x; idx < nc * CW; idx += blockDim.x) {
+            const int r = idx / CW, x = idx - r * CW;
+            if (x >= cw)
+                continue;
+            const int sy = min(lo_c + r, P.chr_src_h - 1);
+            const int gx = cx0 + x;
+            const int pos = P.hc_pos[gx];
+            const int16_t *co = P.hc_coef + (size_t)gx * fs;
+            int u = 0, v = 0;
+            if (layout == SWSC_SRC_PLANAR) {
+                const uint8_t *ru = src1 + (size_t)sy * A.src_stride[1];
+                const uint8_t *rv = src2 + (size_t)sy * A.src_stride[2];
+                for (int j = 0; j < fs; j++) {
+                    const int sx = min(pos + j, P.chr_src_w - 1);
+                    const int cj = co[j];
+                    u += fetch<SRC16>(ru, sx) * cj;
+                    v += fetch<SRC16>(rv, sx) * cj;
+                }
+            } else {
+                const uint8_t *ruv = src1 + (size_t)sy * A.src_stride[1];
+                const int uo = layout == SWSC_SRC_NV12 ? 0 : 1;
+                for (int j = 0; j < fs; j++) {
+                    const int sx = min(pos + j, P.chr_src_w - 1);
+                    const int cj = co[j];
+                    u += fetch<SRC16>(ruv, 2 * sx + uo) * cj;
+                    v += fetch<SRC16>(ruv, 2 * sx + 1 - uo) * cj;
+                }
+            }
+            u = min(u >> sh, h_max);
+            v = min(v >> sh, h_max);
+            if (P.range_mode) {
+                if (!INTER32) {
+                    u = (u * (int)P.chr_rc_coeff + (int)P.chr_rc_offset) >> 14;
+                    v = (v * (int)P.chr_rc_coeff + (int)P.chr_rc_offset) >> 14;
+                    if (P.range_mode == 1) {
+                        u = min(u, (1 << 15) - 1);
+                        v = min(v, (1 << 15) - 1);
+                    }
+                    u = (int16_t)u; v = (int16_t)v;
+                } else {
+                    u = (int)(((long long)u * P.chr_rc_coeff + P.chr_rc_offset) >> 18);
+                    v = (int)(((long long)v * P.chr_rc_coeff + P.chr_rc_offset) >> 18);
+                    if (P.range_mode == 1) {
+                        u = min(u, (1 << 19) - 1);
+                        v = min(v, (1 << 19) - 1);
+                    }
+                }
+            }
+            hb_u[idx] = (inter_t)u;
+            hb_v[idx] = (inter_t)v;
+        }
+    }
+    __syncthreads();
+
+    const int kind = P.dst_kind;
+    const int lfs = P.vl_size, cfs = P.vc_size;
+
+    /* ---- stage V + pack ---- */
+    if (kind >= SWSC_DST_RGB24) {
+        /* packed RGB: one chroma pair per two pixels (output.c:1788-1840 / 1115-1196) */
+        const int pw = tw >> 1;                       /* pairs in this tile (dst_w even here) */
+        const bool is16 = kind >= SWSC_DST_RGB48;
+        for (int idx = threadIdx.x; idx < th * (TW >> 1); idx += blockDim.x) {
+            const int ty = idx / (TW >> 1), i = idx - ty * (TW >> 1);
+            if (i >= pw)
+                continue;
+            const int y = ry0 + ty;
+            const int16_t *lf = P.vl_coef + (size_t)y * lfs;
+            const int16_t *cf = P.vc_coef + (size_t)y * cfs;   /* vs == 0 for RGB */
+            const int rl = max(P.vl_pos[y], 0) - lo_l;
+            const int rc = max(P.vc_pos[y], 0) - lo_c;
+            const inter_t *pl = hb_l + (size_t)rl * TW + 2 * i;
+            const inter_t *pu = hb_u + (size_t)rc * CW + i;
+            const inter_t *pv = hb_v + (size_t)rc * CW + i;
+            unsigned Y1 = 0, Y2 = 0, U = 0, V = 0;
+            for (int j = 0; j < lfs; j++) {
+                const int r = min(rl + j, nl - 1) - rl;
+                const unsigned c = (unsigned)(int)lf[j];
+                Y1 += (unsigned)(int)pl[(size_t)r * TW]     * c;
+                Y2 += (unsigned)(int)pl[(size_t)r * TW + 1] * c;
+            }
+            for (int j = 0; j < cfs; j++) {
+                const int r = min(rc + j, nc - 1) - rc;
+                const unsigned c = (unsigned)(int)cf[j];
+                U += (unsigned)(int)pu[(size_t)r * CW] * c;
+                V += (unsigned)(int)pv[(size_t)r * CW] * c;
+            }
+            if (!is16 || P.unscaled_lut) {
+                int y1v, y2v, uv, vv;
+                if (!INTER32) {
+                    /* yuv2packed2 (bilinear both ways) has no rounding bias (output.c:1861-1864) */
+                    unsigned bias = 1u << 18;
+                    if (lfs == 2 && cfs == 2) {
+                        const int l0 = lf[0], l1 = lf[1], c0 = cf[0], c1 = cf[1];
+                        if (l0 + l1 == 4096 && (unsigned)l1 <= 4096u &&
+                            c0 + c1 == 4096 && (unsigned)c1 <= 4096u)
+                            bias = 0;
+                    }
+                    y1v = (int)(Y1 + bias) >> 19; y2v = (int)(Y2 + bias) >> 19;
+                    uv  = (int)(U  + bias) >> 19; vv  = (int)(V  + bias) >> 19;
+                } else {
+                    /* unscaled LUT converter on a 16-bit destination: identity taps, 19-bit lines */
+                    y1v = (int)Y1 >> 23; y2v = (int)Y2 >> 23; uv = (int)U >> 23; vv = (int)V >> 23;
+                }
+                const int u8 = clip_u8(uv), v8 = clip_u8(vv);
+                const int oR = P.rgb.base_r + ((v8 * P.rgb.crv) >> 16);
+                const int oG = P.rgb.base_g + ((u8 * P.rgb.cgu) >> 16) + ((v8 * P.rgb.cgv) >> 16);
+                const int oB = P.rgb.base_b + ((u8 * P.rgb.cbu) >> 16);
+                const int cy = P.rgb.cy, yb = P.rgb.yb;
+                const int r1 = clip_u8((yb + (y1v + oR) * cy) >> 16);
+                const int g1 = clip_u8((yb + (y1v + oG) * cy) >> 16);
+                const int b1 = clip_u8((yb + (y1v + oB) * cy) >> 16);
+                const int r2 = clip_u8((yb + (y2v + oR) * cy) >> 16);
+                const int g2 = clip_u8((yb + (y2v + oG) * cy) >> 16);
+                const int b2 = clip_u8((yb + (y2v + oB) * cy) >> 16);
+                uint8_t *d = dst0 + (size_t)y * A.dst_stride[0];
+                const int gx = (x0 >> 1) + i;          /* pair index in the row */
+                switch (kind) {
+                case SWSC_DST_RGB24: d += 6 * gx;
+                    d[0] = r1; d[1] = g1; d[2] = b1; d[3] = r2; d[4] = g2; d[5] = b2; break;
+                case SWSC_DST_BGR24: d += 6 * gx;
+                    d[0] = b1; d[1] = g1; d[2] = r1; d[3] = b2; d[4] = g2; d[5] = r2; break;
+                case SWSC_DST_RGBA: d += 8 * gx;
+                    d[0] = r1; d[1] = g1; d[2] = b1; d[3] = 255; d[4] = r2; d[5] = g2; d[6] = b2; d[7] = 255; break;
+                case SWSC_DST_BGRA: d += 8 * gx;
+                    d[0] = b1; d[1] = g1; d[2] = r1; d[3] = 255; d[4] = b2; d[5] = g2; d[6] = r2; d[7] = 255; break;
+                case SWSC_DST_ARGB: d += 8 * gx;
+                    d[0] = 255; d[1] = r1; d[2] = g1; d[3] = b1; d[4] = 255; d[5] = r2; d[6] = g2; d[7] = b2; break;
+                case SWSC_DST_ABGR: d += 8 * gx;
+                    d[0] = 255; d[1] = b1; d[2] = g1; d[3] = r1; d[4] = 255; d[5] = b2; d[6] = g2; d[7] = r2; break;
+                case SWSC_DST_RGB48: { uint16_t *w = reinterpret_cast<uint16_t *>(d) + 6 * gx;
+                    w[0] = r1 * 257; w[1] = g1 * 257; w[2] = b1 * 257; w[3] = r2 * 257; w[4] = g2 * 257; w[5] = b2 * 257; break; }
+                case SWSC_DST_BGR48: { uint16_t *w = reinterpret_cast<uint16_t *>(d) + 6 * gx;
+                    w[0] = b1 * 257; w[1] = g1 * 257; w[2] = r1 * 257; w[3] = b2 * 257; w[4] = g2 * 257; w[5] = r2 * 257; break; }
+                }
+            } else {
+                /* 16-bit arithmetic path, wrapping exactly like the C template */
+                unsigned y1u = Y1 - 0x40000000u, y2u = Y2 - 0x40000000u;
+                unsigned uu = U - (128u << 23), vu = V - (128u << 23);
+                y1u = (unsigned)((int)y1u >> 14) + 0x10000u;
+                y2u = (unsigned)((int)y2u >> 14) + 0x10000u;
+                uu = (unsigned)((int)uu >> 14);
+                vu = (unsigned)((int)vu >> 14);
+                y1u -= (unsigned)P.rgb.y_offset; y2u -= (unsigned)P.rgb.y_offset;
+                y1u *= (unsigned)P.rgb.y_coeff;  y2u *= (unsigned)P.rgb.y_coeff;
+                y1u += (1u << 13) - (1u << 29);  y2u += (1u << 13) - (1u << 29);
+                const unsigned R = vu * (unsigned)P.rgb.v2r;
+                const unsigned G = vu * (unsigned)P.rgb.v2g + uu * (unsigned)P.rgb.u2g;
+                const unsigned B = uu * (unsigned)P.rgb.u2b;
+                const int r1 = clip_uintp2(((int)(R + y1u) >> 14) + (1 << 15), 16);
+                const int g1 = clip_uintp2(((int)(G + y1u) >> 14) + (1 << 15), 16);
+                const int b1 = clip_uintp2(((int)(B + y1u) >> 14) + (1 << 15), 16);
+                const int r2 = clip_uintp2(((int)(R + y2u) >> 14) + (1 << 15), 16);
+                const int g2 = clip_uintp2(((int)(G + y2u) >> 14) + (1 << 15), 16);
+                const int b2 = clip_uintp2(((int)(B + y2u) >> 14) + (1 << 15), 16);
+                uint16_t *w = reinterpret_cast<uint16_t *>(dst0 + (size_t)y * A.dst_stride[0]) + 6 * ((x0 >> 1) + i);
+                if (kind == SWSC_DST_RGB48) {
+                    w[0] = r1; w[1] = g1; w[2] = b1; w[3] = r2; w[4] = g2; w[5] = b2;
+                } else {
+                    w[0] = b1; w[1] = g1; w[2] = r1; w[3] = b2; w[4] = g2; w[5] = r2;
+                }
+            }
+        }
+    } else {
+        /* planar / semi-planar YUV (output.c:163-187,340-357,468-528; vscale.c:41-107) */
+        const int bits = P.dst_bits;
+        for (int idx = threadIdx.x; idx < th * TW; idx += blockDim.x) {
+            const int ty = idx / TW, x = idx - ty * TW;
+            if (x >= tw)
+                continue;
+            const int y = ry0 + ty;
+            const int16_t *lf = P.vl_coef + (size_t)y * lfs;
+            const int rl = max(P.vl_pos[y], 0) - lo_l;
+            const inter_t *pl = hb_l + (size_t)rl * TW + x;
+            unsigned acc = 0;
+            for (int j = 0; j < lfs; j++) {
+                const int r = min(rl + j, nl - 1) - rl;
+                acc += (unsigned)(int)pl[(size_t)r * TW] * (unsigned)(int)lf[j];
+            }
+            const int gx = x0 + x;
+            uint8_t *d = dst0 + (size_t)y * A.dst_stride[0];
+            if (kind == SWSC_DST_PLANAR8 || kind == SWSC_DST_NV12 || kind == SWSC_DST_NV21) {
+                const int dz = P.dither_bayer ? c_dither_8x8_128[y & 7][gx & 7] : 64;
+                d[gx] = clip_u8((int)(acc + ((unsigned)dz << 12)) >> 19);
+            } else if (kind == SWSC_DST_PLANARN) {
+                const int shift = 27 - bits;
+                reinterpret_cast<uint16_t *>(d)[gx] = clip_uintp2((int)(acc + (1u << (shift - 1))) >> shift, bits);
+            } else {
+                const int v = (int)(acc + (1u << 14) - 0x40000000u) >> 15;
+                reinterpret_cast<uint16_t *>(d)[gx] = 0x8000 + clip_i16(v);
+            }
+        }
+        if (P.has_chroma && ch > 0) {
+            for (int idx = threadIdx.x; idx < ch * CW; idx += blockDim.x) {
+                const int ty = idx / CW, x = idx - ty * CW;
+                if (x >= cw)
+                    continue;
+                const int y = cy0 + ty;
+                const int16_t *cf = P.vc_coef + (size_t)y * cfs;
+                const int rc = max(P.vc_pos[y], 0) - lo_c;
+                const inter_t *pu = hb_u + (size_t)rc * CW + x;
+                const inter_t *pv = hb_v + (size_t)rc * CW + x;
+                unsigned au = 0, av = 0;
+                for (int j = 0; j < cfs; j++) {
+                    const int r = min(rc + j, nc - 1) - rc;
+                    const unsigned c = (unsigned)(int)cf[j];
+                    au += (unsigned)(int)pu[(size_t)r * CW] * c;
+                    av += (unsigned)(int)pv[(size_t)r * CW] * c;
+                }
+                const int gx = cx0 + x;
+                if (kind == SWSC_DST_PLANAR8) {
+                    const int du = P.dither_bayer ? c_dither_8x8_128[y & 7][gx & 7] : 64;
+                    const int dv = P.dither_bayer ? c_dither_8x8_128[y & 7][(gx + 3) & 7] : 64;
+                    dst1[(size_t)y * A.dst_stride[1] + gx] = clip_u8((int)(au + ((unsigned)du << 12)) >> 19);
+                    dst2[(size_t)y * A.dst_stride[2] + gx] = clip_u8((int)(av + ((unsigned)dv << 12)) >> 19);
+                } else if (kind == SWSC_DST_NV12 || kind == SWSC_DST_NV21) {
+                    const int du = P.dither_bayer ? c_dither_8x8_128[y & 7][gx & 7] : 64;
+                    const int dv = P.dither_bayer ? c_dither_8x8_128[y & 7][(gx + 3) & 7] : 64;
+                    const int u8 = clip_u8((int)(au + ((unsigned)du << 12)) >> 19);
+                    const int v8 = clip_u8((int)(av + ((unsigned)dv << 12)) >> 19);
+                    uint8_t *d = dst1 + (size_t)y * A.dst_stride[1] + 2 * gx;
+                    d[0] = kind == SWSC_DST_NV12 ? u8 : v8;
+                    d[1] = kind == SWSC_DST_NV12 ? v8 : u8;
+                } else if (kind == SWSC_DST_PLANARN) {
+                    const int shift = 27 - bits;
+                    reinterpret_cast<uint16_t *>(dst1 + (size_t)y * A.dst_stride[1])[gx] =
+                        clip_uintp2((int)(au + (1u << (shift - 1))) >> shift, bits);
+                    reinterpret_cast<uint16_t *>(dst2 + (size_t)y * A.dst_stride[2])[gx] =
+                        clip_uintp2((int)(av + (1u << (shift - 1))) >> shift, bits);
+                } else {
+                    const int u = (int)(au + (1u << 14) - 0x40000000u) >> 15;
+                    const int v = (int)(av + (1u << 14) - 0x40000000u) >> 15;
+                    reinterpret_cast<uint16_t *>(dst1 + (size_t)y * A.dst_stride[1])[gx] = 0x8000 + clip_i16(u);
+                    reinterpret_cast<uint16_t *>(dst2 + (size_t)y * A.dst_stride[2])[gx] = 0x8000 + clip_i16(v);
+                }
+            }
+        }
+    }
+}
+
+/* ======================================================================== host side */
+
+struct SwsCudaState {
+    int device;
+    cudaStream_t stream;
+    SwsCudaPlan plan;
+    void *tables;            /* one allocation holding the four FIR banks */
+    /* host copies of the vertical banks for launch planning */
+    int32_t *h_vl_pos, *h_vc_pos;
+    /* staging frames for host-pointer sws_scale() */
+    uint8_t *d_src[4], *d_dst[4];
+    int d_src_stride[4], d_dst_stride[4];
+    int src_rows[4], dst_rows[4];
+    int src_rowbytes[4], dst_rowbytes[4];
+    long launches;
+    const char *kernel_name;
+    int tile_w, tile_h, rows_l_cap, rows_c_cap;
+    size_t smem_bytes;
+};
+
+extern "C" int sws_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" void *sws_cuda_host_alloc(size_t size)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, size, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void sws_cuda_host_free(void *ptr)
+{
+    if (ptr)
+        cudaFreeHost(ptr);
+}
+
+extern "C" int ff_b200_cuda_probe(void)
+{
+    int n = sws_cuda_device_count(), dev = 0;
+    if (n <= 0)
+        return AVERROR(ENOSYS);
+    if (cudaGetDevice(&dev) != cudaSuccess)
+        return AVERROR(ENOSYS);
+    return dev;
+}
+
+/* most h-scaled source rows any window of `th` consecutive output rows can need
+ * (tiles may start at any row when the legacy slice API is used) */
+static int max_rows_needed(const int32_t *pos, int fs, int n_out, int th)
+{
+    int worst = fs;
+    for (int y = 0; y < n_out; y++) {
+        int y1 = y + th < n_out ? y + th : n_out;
+        int lo = INT32_MAX, hi = 0;
+        for (int k = y; k < y1; k++) {
+            int p = pos[k] < 0 ? 0 : pos[k];
+            if (p < lo) lo = p;
+            if (pos[k] + fs > hi) hi = pos[k] + fs;
+        }
+        if (hi - lo > worst)
+            worst = hi - lo;
+    }
+    return worst;
+}
+
+static int plan_tiles(SwsCudaState *st)
+{
+    const SwsCudaPlan *p = &st->plan;
+    const int isz = p->inter_bits == 19 ? 4 : 2;
+    const int vs = p->chr_dst_vsub, hs = p->chr_dst_hsub;
+    const size_t budget = 96 * 1024;
+    int tw = 128;
+    while (tw > 32 && tw / 2 >= p->dst_w)
+        tw /= 2;
+    for (int th = 32; th >= (1 << vs); th >>= 1) {
+        int rl = max_rows_needed(st->h_vl_pos, p->vl_size, p->dst_h, th);
+        int cth = th >> vs ? th >> vs : 1;
+        int rc = max_rows_needed(st->h_vc_pos, p->vc_size, p->chr_dst_h, cth);
+        size_t need = ((size_t)rl * tw + 2 * (size_t)rc * (tw >> hs)) * isz;
+        if (need <= budget || th == (1 << vs)) {
+            if (need > 200 * 1024)
+                return AVERROR(ENOTSUP);
+            st->tile_w = tw; st->tile_h = th; st->rows_l_cap = rl; st->rows_c_cap = rc;
+            st->smem_bytes = need;
+            return 0;
+        }
+    }
+    return AVERROR(ENOTSUP);
+}
+
+typedef void (*generic_kernel_t)(const SwsCudaPlan, const FrameArgs);
+
+static generic_kernel_t pick_generic(const SwsCudaPlan *p)
+{
+    const bool src16 = p->src_bits > 8, i32 = p->inter_bits == 19;
+    if (src16)
+        return i32 ? sws_generic_tile_kernel<true, true> : sws_generic_tile_kernel<true, false>;
+    return i32 ? sws_generic_tile_kernel<false, true> : sws_generic_tile_kernel<false, false>;
+}
+
+extern "C" int ff_b200_cuda_create(SwsCudaState **out, SwsCudaPlan *plan,
+                                   const SwsFirBank *hl, const SwsFirBank *hc,
+                                   const SwsFirBank *vl, const SwsFirBank *vc)
+{
+    int dev = ff_b200_cuda_probe();
+    if (dev < 0)
+        return dev;
+    SwsCudaState *st = (SwsCudaState *)calloc(1, sizeof(*st));
+    if (!st)
+        return AVERROR(ENOMEM);
+    st->device = dev;
+    *out = st;
+    CUDA_OK(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
+
+    /* upload the four banks into one allocation: [coef|pos] x4, 16-byte aligned */
+    const SwsFirBank *banks[4] = { hl, hc, vl, vc };
+    size_t off[8], total = 0;
+    for (int i = 0; i < 4; i++) {
+        off[2 * i] = total;
+        total += (((size_t)banks[i]->len * banks[i]->size * sizeof(int16_t)) + 15) & ~(size_t)15;
+        off[2 * i + 1] = total;
+        total += (((size_t)banks[i]->len * sizeof(int32_t)) + 15) & ~(size_t)15;
+    }
+    CUDA_OK(cudaMalloc(&st->tables, total));
+    uint8_t *host = (uint8_t *)calloc(1, total);
+    if (!host)
+        return AVERROR(ENOMEM);
+    for (int i = 0; i < 4; i++) {
+        memcpy(host + off[2 * i], banks[i]->coef, (size_t)banks[i]->len * banks[i]->size * sizeof(int16_t));
+        memcpy(host + off[2 * i + 1], banks[i]->pos, (size_t)banks[i]->len * sizeof(int32_t));
+    }
+    cudaError_t e = cudaMemcpy(st->tables, host, total, cudaMemcpyHostToDevice);
+    free(host);
+    CUDA_OK(e);
+    uint8_t *t = (uint8_t *)st->tables;
+    plan->hl_coef = (const int16_t *)(t + off[0]); plan->hl_pos = (const int32_t *)(t + off[1]); plan->hl_size = hl->size;
+    plan->hc_coef = (const int16_t *)(t + off[2]); plan->hc_pos = (const int32_t *)(t + off[3]); plan->hc_size = hc->size;
+    plan->vl_coef = (const int16_t *)(t + off[4]); plan->vl_pos = (const int32_t *)(t + off[5]); plan->vl_size = vl->size;
+    plan->vc_coef = (const int16_t *)(t + off[6]); plan->vc_pos = (const int32_t *)(t + off[7]); plan->vc_size = vc->size;
+    st->plan = *plan;
+
+    st->h_vl_pos = (int32_t *)malloc(sizeof(int32_t) * vl->len);
+    st->h_vc_pos = (int32_t *)malloc(sizeof(int32_t) * vc->len);
+    if (!st->h_vl_pos || !st->h_vc_pos)
+        return AVERROR(ENOMEM);
+    memcpy(st->h_vl_pos, vl->pos, sizeof(int32_t) * vl->len);
+    memcpy(st->h_vc_pos, vc->pos, sizeof(int32_t) * vc->len);
+
+    int ret = plan_tiles(st);
+    if (ret < 0)
+        return ret;
+    st->kernel_name = "generic_tile";
+    CUDA_OK(cudaFuncSetAttribute((const void *)pick_generic(&st->plan),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem_bytes));
+    return 0;
+}
+
+extern "C" void ff_b200_cuda_destroy(SwsCudaState *st)
+{
+    if (!st)
+        return;
+    if (st->stream) {
+        cudaStreamSynchronize(st->stream);
+        cudaStreamDestroy(st->stream);
+    }
+    cudaFree(st->tables);
+    for (int i = 0; i < 4; i++) {
+        cudaFree(st->d_src[i]);
+        cudaFree(st->d_dst[i]);
+    }
+    free(st->h_vl_pos);
+    free(st->h_vc_pos);
+    free(st);
+}
+
+extern "C" int ff_b200_cuda_update_plan(SwsCudaState *st, const SwsCudaPlan *plan)
+{
+    /* keep the device table pointers, refresh the scalar constants */
+    SwsCudaPlan n = *plan;
+    n.hl_coef = st->plan.hl_coef; n.hl_pos = st->plan.hl_pos; n.hl_size = st->plan.hl_size;
+    n.hc_coef = st->plan.hc_coef; n.hc_pos = st->plan.hc_pos; n.hc_size = st->plan.hc_size;
+    n.vl_coef = st->plan.vl_coef; n.vl_pos = st->plan.vl_pos; n.vl_size = st->plan.vl_size;
+    n.vc_coef = st->plan.vc_coef; n.vc_pos = st->plan.vc_pos; n.vc_size = st->plan.vc_size;
+    st->plan = n;
+    return 0;
+}
+
+extern "C" int ff_b200_cuda_launch(SwsCudaState *st,
+                                   const uint8_t *const src[4], const int src_stride[4], const int64_t src_fstride[4],
+                                   uint8_t *const dst[4], const int dst_stride[4], const int64_t dst_fstride[4],
+                                   int nb_frames, int y0, int y1)
+{
+    if (y1 <= y0)
+        return 0;
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != st->device)
+        CUDA_OK(cudaSetDevice(st->device));
+    FrameArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 4; i++) {
+        a.src[i] = src[i]; a.dst[i] = dst[i];
+        a.src_stride[i] = src_stride[i]; a.dst_stride[i] = dst_stride[i];
+        a.src_fstride[i] = src_fstride ? src_fstride[i] : 0;
+        a.dst_fstride[i] = dst_fstride ? dst_fstride[i] : 0;
+    }
+    a.y0 = y0; a.y1 = y1;
+    a.tile_w = st->tile_w; a.tile_h = st->tile_h;
+    a.rows_l_cap = st->rows_l_cap; a.rows_c_cap = st->rows_c_cap;
+    dim3 grid((st->plan.dst_w + st->tile_w - 1) / st->tile_w,
+              (y1 - y0 + st->tile_h - 1) / st->tile_h, nb_frames);
+    pick_generic(&st->plan)<<<grid, 256, st->smem_bytes, st->stream>>>(st->plan, a);
+    CUDA_OK(cudaGetLastError());
+    st->launches++;
+    return 0;
+}
+
+static int ensure_staging(SwsCudaState *st)
+{
+    if (st->d_src[0])
+        return 0;
+    const SwsCudaPlan *p = &st->plan;
+    const int sb = p->src_bits > 8 ? 2 : 1;
+    /* source planes */
+    st->src_rows[0] = p->src_h; st->src_rowbytes[0] = p->src_w * sb;
+    if (p->src_layout == SWSC_SRC_PLANAR) {
+        st->src_rows[1] = st->src_rows[2] = p->chr_src_h;
+        st->src_rowbytes[1] = st->src_rowbytes[2] = p->chr_src_w * sb;
+    } else {
+        st->src_rows[1] = p->chr_src_h;
+        st->src_rowbytes[1] = p->chr_src_w * 2 * sb;
+    }
+    /* destination planes */
+    switch (p->dst_kind) {
+    case SWSC_DST_RGB24: case SWSC_DST_BGR24: st->dst_rowbytes[0] = p->dst_w * 3; break;
+    case SWSC_DST_RGBA: case SWSC_DST_BGRA: case SWSC_DST_ARGB: case SWSC_DST_ABGR:
+        st->dst_rowbytes[0] = p->dst_w * 4; break;
+    case SWSC_DST_RGB48: case SWSC_DST_BGR48: st->dst_rowbytes[0] = p->dst_w * 6; break;
+    default: {
+        const int db = p->dst_bits > 8 ? 2 : 1;
+        st->dst_rowbytes[0] = p->dst_w * db;
+        if (p->dst_kind == SWSC_DST_NV12 || p->dst_kind == SWSC_DST_NV21) {
+            st->dst_rows[1] = p->chr_dst_h; st->dst_rowbytes[1] = p->chr_dst_w * 2 * db;
+        } else {
+            st->dst_rows[1] = st->dst_rows[2] = p->chr_dst_h;
+            st->dst_rowbytes[1] = st->dst_rowbytes[2] = p->chr_dst_w * db;
+        }
+    } }
+    st->dst_rows[0] = p->dst_h;
+    for (int i = 0; i < 4; i++) {
+        if (st->src_rows[i]) {
+            st->d_src_stride[i] = (st->src_rowbytes[i] + 255) & ~255;
+            CUDA_OK(cudaMalloc(&st->d_src[i], (size_t)st->d_src_stride[i] * st->src_rows[i]));
+        }
+        if (st->dst_rows[i]) {
+            st->d_dst_stride[i] = (st->dst_rowbytes[i] + 255) & ~255;
+            CUDA_OK(cudaMalloc(&st->d_dst[i], (size_t)st->d_dst_stride[i] * st->dst_rows[i]));
+        }
+    }
+    return 0;
+}
+
+extern "C" int ff_b200_cuda_scale_host(SwsCudaState *st,
+                                       const uint8_t *const src[4], const int src_stride[4],
+                                       int src_y, int src_h, int upload,
+                                       uint8_t *const dst[4], const int dst_stride[4], int y0, int y1)
+{
+    const SwsCudaPlan *p = &st->plan;
+    int ret = ensure_staging(st);
+    if (ret < 0)
+        return ret;
+    if (upload) {
+        for (int i = 0; i < 3; i++) {
+            if (!st->src_rows[i])
+                continue;
+            if (!src[i])
+                return AVERROR(EINVAL);
+            const int vs = i ? p->chr_src_vsub : 0;
+            const int r0 = src_y >> vs;
+            int r1 = -((-(src_y + src_h)) >> vs);
+            if (r1 > st->src_rows[i])
+                r1 = st->src_rows[i];
+            /* slice pointers address the first row of the slice (swscale.h:566-576) */
+            CUDA_OK(cudaMemcpy2DAsync(st->d_src[i] + (size_t)r0 * st->d_src_stride[i], st->d_src_stride[i],
+                                      src[i], src_stride[i], st->src_rowbytes[i], r1 - r0,
+                                      cudaMemcpyHostToDevice, st->stream));
+        }
+    }
+    if (y1 > y0) {
+        int64_t zero[4] = { 0, 0, 0, 0 };
+        ret = ff_b200_cuda_launch(st, st->d_src, st->d_src_stride, zero, st->d_dst, st->d_dst_stride, zero, 1, y0, y1);
+        if (ret < 0)
+            return ret;
+        for (int i = 0; i < 3; i++) {
+            if (!st->dst_rows[i])
+                continue;
+            if (!dst[i])
+                return AVERROR(EINVAL);
+            const int vs = i ? p->chr_dst_vsub : 0;
+            const int r0 = y0 >> vs;
+            int r1 = (y1 == p->dst_h) ? st->dst_rows[i] : (y1 >> vs);
+            if (r1 <= r0)
+                continue;
+            CUDA_OK(cudaMemcpy2DAsync(dst[i] + (size_t)r0 * dst_stride[i], dst_stride[i],
+                                      st->d_dst[i] + (size_t)r0 * st->d_dst_stride[i], st->d_dst_stride[i],
+                                      st->dst_rowbytes[i], r1 - r0, cudaMemcpyDeviceToHost, st->stream));
+        }
+    }
+    CUDA_OK(cudaStreamSynchronize(st->stream));
+    return 0;
+}
+
+extern "C" int ff_b200_cuda_sync(SwsCudaState *st)
+{
+    CUDA_OK(cudaStreamSynchronize(st->stream));
+    return 0;
+}
+
+extern "C" void *ff_b200_cuda_stream(SwsCudaState *st) { return (void *)st->stream; }
+extern "C" long ff_b200_cuda_launch_count(SwsCudaState *st) { return st->launches; }
+extern "C" const char *ff_b200_cuda_kernel_name(SwsCudaState *st) { return st->kernel_name; }

@@ -1,0 +1,182 @@
+/*
+ * sws_internal.h -- private state of the B200 libswscale hot path.
+ *
+ * Plays the role of the reference's SwsInternal (libswscale/swscale_internal.h:337-706)
+ * but holds only what a frame-level GPU converter needs: geometry, the four
+ * FIR banks, colour constants and an opaque device state.  The per-line
+ * function pointers, ring-buffer slices and descriptor chains of the reference
+ * (swscale_internal.h:563-672, slice.c) have no equivalent: a whole frame is
+ * resident in HBM and one fused kernel replaces ff_swscale()'s line-pull loop.
+ */
+#ifndef SWS_B200_INTERNAL_H
+#define SWS_B200_INTERNAL_H
+
+#include <stdint.h>
+#include "swscale_b200.h"
+#include "swscale_b200_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ pixfmt */
+#define SWSPF_RGB     1   /* packed RGB family                        */
+#define SWSPF_PLANAR  2   /* one plane per component                  */
+#define SWSPF_SEMI    4   /* luma plane + interleaved chroma plane    */
+#define SWSPF_GRAY    8
+#define SWSPF_JPEG   16   /* deprecated yuvj*: implies full range     */
+
+typedef struct SwsPixDesc {
+    int fmt;
+    const char *name;
+    int flags;
+    int depth;        /* bits per component                         */
+    int log2_cw;      /* horizontal chroma shift                    */
+    int log2_ch;      /* vertical chroma shift                      */
+    int bpp;          /* bits per pixel (av_get_bits_per_pixel)     */
+    int nb_planes;
+    int swap_uv;      /* nv21                                        */
+    int as_input, as_output;
+} SwsPixDesc;
+
+const SwsPixDesc *ff_b200_pix_desc(int fmt);
+
+/* ------------------------------------------------------------------ filters */
+typedef struct SwsFirBank {
+    int16_t *coef;   /* [len][size]                               */
+    int32_t *pos;    /* [len] first source sample of each output  */
+    int size;        /* taps per output                           */
+    int len;         /* number of outputs                         */
+} SwsFirBank;
+
+typedef struct SwsFirSpec {
+    int64_t inc;           /* 16.16 source step per output sample                */
+    int src_len, dst_len;
+    int one;               /* fixed-point 1.0 of the stored coefficients         */
+    int scaler;            /* one SWS_* scaler flag                              */
+    unsigned flags;        /* full flag word (BITEXACT / ACCURATE_RND matter)    */
+    double param[2];
+    int src_pos, dst_pos;  /* chroma siting, 1/256 sample units, already local   */
+} SwsFirSpec;
+
+#define SWS_B200_USE_CASCADE (-12345)
+
+int  ff_b200_build_fir(SwsFirBank *out, const SwsFirSpec *spec);
+void ff_b200_free_fir(SwsFirBank *b);
+
+/* --------------------------------------------------------------- colourspace */
+typedef struct SwsRgbConsts {
+    /* closed form of the 8-bit LUT chain (reference yuv2rgb.c:680-703,901-914) */
+    int32_t cy;        /* luma slope, 16.16                                   */
+    int32_t yb;        /* LUT intercept incl. rounding: value(i)=(yb+i*cy)>>16 */
+    int32_t crv, cbu, cgu, cgv;         /* chroma slopes rescaled by cy        */
+    int32_t base_r, base_g, base_b;     /* LUT index bases (g: gU base + gV base) */
+    /* 16-bit arithmetic path (reference yuv2rgb.c:786-791, output.c:1115-1196) */
+    int32_t y_offset, y_coeff, v2r, v2g, u2g, u2b;
+} SwsRgbConsts;
+
+int ff_b200_rgb_consts(SwsRgbConsts *k, const int inv_table[4], int full_range,
+                       int brightness, int contrast, int saturation);
+
+/* ------------------------------------------------------------ device plan */
+enum {
+    SWSC_SRC_PLANAR = 0,   /* Y, U, V planes (or Y only for gray)     */
+    SWSC_SRC_NV12   = 1,   /* Y plane + interleaved UV                */
+    SWSC_SRC_NV21   = 2,   /* Y plane + interleaved VU                */
+};
+
+enum {
+    SWSC_DST_PLANAR8 = 0,
+    SWSC_DST_PLANARN,      /* 9..14 bit little-endian                  */
+    SWSC_DST_PLANAR16,
+    SWSC_DST_NV12,
+    SWSC_DST_NV21,
+    SWSC_DST_RGB24,
+    SWSC_DST_BGR24,
+    SWSC_DST_RGBA,
+    SWSC_DST_BGRA,
+    SWSC_DST_ARGB,
+    SWSC_DST_ABGR,
+    SWSC_DST_RGB48,
+    SWSC_DST_BGR48,
+};
+
+/* POD description of one conversion; passed by value to the kernels. */
+typedef struct SwsCudaPlan {
+    int src_w, src_h, dst_w, dst_h;
+    int chr_src_w, chr_src_h, chr_dst_w, chr_dst_h;
+    int chr_src_hsub, chr_src_vsub, chr_dst_hsub, chr_dst_vsub;
+    int src_layout, dst_kind;
+    int src_bits, dst_bits;      /* component depth                           */
+    int inter_bits;              /* 15 or 19: width of the h-scaled lines     */
+    int h_shift;                 /* right shift applied after the H FIR       */
+    int has_chroma;              /* 0 for gray sources/destinations           */
+    int unscaled_lut;            /* 1: reference would take convert_unscaled  */
+    int dither_bayer;            /* 1: ff_dither_8x8_128 rows, 0: constant 64 */
+    /* range conversion on the h-scaled lines (reference swscale.c:163-255,577-660) */
+    int range_mode;              /* 0 none, 1 to-jpeg, 2 from-jpeg            */
+    uint32_t lum_rc_coeff, chr_rc_coeff;
+    int64_t  lum_rc_offset, chr_rc_offset;
+    SwsRgbConsts rgb;
+    /* device pointers to the four FIR banks */
+    const int16_t *hl_coef, *hc_coef, *vl_coef, *vc_coef;
+    const int32_t *hl_pos,  *hc_pos,  *vl_pos,  *vc_pos;
+    int hl_size, hc_size, vl_size, vc_size;
+    /* fast-path eligibility, decided on the host at init */
+    int lum_identity;            /* h and v luma FIRs are the identity        */
+    int chr_h_identity;          /* horizontal chroma FIR is the identity     */
+} SwsCudaPlan;
+
+typedef struct SwsCudaState SwsCudaState;
+
+/* C-ABI shim implemented in sws_cuda.cu (the only translation unit that sees CUDA). */
+int  ff_b200_cuda_probe(void);    /* >=0: device ordinal in use, <0: AVERROR       */
+int  ff_b200_cuda_create(SwsCudaState **st, SwsCudaPlan *plan,
+                         const SwsFirBank *hl, const SwsFirBank *hc,
+                         const SwsFirBank *vl, const SwsFirBank *vc);
+void ff_b200_cuda_destroy(SwsCudaState *st);
+int  ff_b200_cuda_update_plan(SwsCudaState *st, const SwsCudaPlan *plan);
+/* device-resident frames; rows [y0,y1) of every frame; async on the context stream */
+int  ff_b200_cuda_launch(SwsCudaState *st,
+                         const uint8_t *const src[4], const int src_stride[4], const int64_t src_fstride[4],
+                         uint8_t *const dst[4], const int dst_stride[4], const int64_t dst_fstride[4],
+                         int nb_frames, int y0, int y1);
+/* host frame in, host rows [y0,y1) out; synchronous */
+int  ff_b200_cuda_scale_host(SwsCudaState *st,
+                             const uint8_t *const src[4], const int src_stride[4],
+                             int src_y, int src_h, int upload,
+                             uint8_t *const dst[4], const int dst_stride[4], int y0, int y1);
+int  ff_b200_cuda_sync(SwsCudaState *st);
+void *ff_b200_cuda_stream(SwsCudaState *st);
+long ff_b200_cuda_launch_count(SwsCudaState *st);
+const char *ff_b200_cuda_kernel_name(SwsCudaState *st);
+
+/* ----------------------------------------------------------------- context */
+typedef struct SwsInternal {
+    SwsContext opts;                 /* must be first (reference swscale_internal.h:79-82) */
+    int initialized;
+    int planned;                     /* tables built by sws_b200_plan_only() (no device) */
+    int src_colorspace[4], dst_colorspace[4];
+    int brightness, contrast, saturation;
+    int colorspace_set;
+    int chr_src_hsub, chr_src_vsub, chr_dst_hsub, chr_dst_vsub;
+    int chr_src_w, chr_src_h, chr_dst_w, chr_dst_h;
+    int src_bpc, dst_bpc;
+    int unscaled_lut;                /* reference would use c->convert_unscaled (a13) */
+    int dst_slice_align;
+    SwsFirBank h_lum, h_chr, v_lum, v_chr;
+    SwsCudaPlan plan;
+    SwsCudaState *cuda;
+    /* slice state of the legacy API (reference swscale.c:296-298,562-564) */
+    int dst_y;
+    int slice_dir;
+    int rows_received;
+    char last_error[256];
+} SwsInternal;
+
+static inline SwsInternal *sws_internal(const SwsContext *s) { return (SwsInternal *)s; }
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,158 @@
+"""GPU parity: sws_scale() through the C ABI of libswscale_b200.so versus the real
+reference C path (oracle/_ref), on identical seeded host frames.  Bit-exact or fail.
+
+Run with `pytest -m gpu` on the B200 box.
+"""
+import numpy as np
+import pytest
+
+from tests import sws_testlib as T
+from librempeg_b200 import swscale as S
+
+pytestmark = pytest.mark.gpu
+
+BX = S.BX
+
+
+def _check(**case):
+    got, want, name = T.run_case_both(**case)
+    diff = T.first_diff(got, want)
+    assert diff is None, "%r via %s: %s" % (case, name, diff)
+    return name
+
+
+# ---- the five BASELINE.json configurations (C1..C5; C5 is one frame of the batch) ----
+BASELINE_CASES = [
+    dict(sw=640, sh=480, sf="yuv420p", dw=640, dh=480, df="rgb24", flags=S.SWS_POINT | S.SWS_BITEXACT),
+    dict(sw=640, sh=480, sf="yuv420p", dw=640, dh=480, df="rgb24", flags=S.SWS_POINT | BX),
+    dict(sw=1920, sh=1080, sf="yuv420p", dw=1920, dh=1080, df="rgb24", flags=S.SWS_BICUBIC | BX),
+    dict(sw=3840, sh=2160, sf="yuv420p10le", dw=3840, dh=2160, df="rgb48le", flags=S.SWS_LANCZOS | BX),
+    dict(sw=7680, sh=4320, sf="nv12", dw=1920, dh=1080, df="yuv420p", flags=S.SWS_BICUBIC | BX),
+    dict(sw=3840, sh=2160, sf="yuv420p", dw=3840, dh=2160, df="rgb24", flags=S.SWS_BICUBIC | BX),
+    # default flags: the reference takes the unscaled LUT converter
+    dict(sw=1920, sh=1080, sf="yuv420p", dw=1920, dh=1080, df="rgb24", flags=S.SWS_BICUBIC),
+]
+
+
+@pytest.mark.parametrize("case", BASELINE_CASES, ids=lambda c: "%dx%d_%s_to_%dx%d_%s_%x" % (
+    c["sw"], c["sh"], c["sf"], c["dw"], c["dh"], c["df"], c["flags"]))
+@pytest.mark.parametrize("mode", ["noise", "extreme"])
+def test_baseline_configs(case, mode):
+    _check(mode=mode, seed=1234, **case)
+
+
+# ---- scaling ratios, scalers, odd sizes ----
+SCALERS = [S.SWS_POINT, S.SWS_BILINEAR, S.SWS_BICUBIC, S.SWS_AREA, S.SWS_GAUSS, S.SWS_SINC,
+           S.SWS_LANCZOS, S.SWS_SPLINE, S.SWS_X, S.SWS_BICUBLIN]
+
+
+@pytest.mark.parametrize("scaler", SCALERS)
+@pytest.mark.parametrize("geom", [(352, 288, 200, 100), (352, 288, 704, 576), (320, 240, 333, 251),
+                                  (642, 362, 320, 180)])
+def test_yuv420p_to_yuv420p_scalers(scaler, geom):
+    sw, sh, dw, dh = geom
+    _check(sw=sw, sh=sh, sf="yuv420p", dw=dw, dh=dh, df="yuv420p", flags=scaler | BX, seed=3)
+
+
+@pytest.mark.parametrize("scaler", [S.SWS_POINT, S.SWS_BILINEAR, S.SWS_BICUBIC, S.SWS_LANCZOS])
+@pytest.mark.parametrize("geom", [(352, 288, 200, 100), (352, 288, 704, 576), (320, 240, 334, 251),
+                                  (1920, 1080, 1280, 720)])
+@pytest.mark.parametrize("df", ["rgb24", "bgr24", "rgba", "bgra", "argb", "abgr", "rgb48le", "bgr48le"])
+def test_yuv420p_to_rgb_scaled(scaler, geom, df):
+    sw, sh, dw, dh = geom
+    _check(sw=sw, sh=sh, sf="yuv420p", dw=dw, dh=dh, df=df, flags=scaler | BX, seed=5)
+
+
+@pytest.mark.parametrize("sf", ["yuv420p", "yuv422p", "nv12", "nv21", "yuv420p10le", "yuv422p10le",
+                                "yuv420p9le", "yuv420p12le", "yuv420p14le", "yuv420p16le", "yuvj420p"])
+@pytest.mark.parametrize("df", ["rgb24", "rgb48le", "yuv420p", "yuv422p", "yuv444p", "nv12", "nv21",
+                                "yuv420p10le", "yuv444p12le", "yuv420p16le"])
+def test_format_matrix_scaled(sf, df):
+    _check(sw=322, sh=242, sf=sf, dw=400, dh=300, df=df, flags=S.SWS_BICUBIC | BX, seed=11)
+    _check(sw=322, sh=242, sf=sf, dw=160, dh=120, df=df, flags=S.SWS_BILINEAR | BX, seed=12)
+
+
+@pytest.mark.parametrize("sf,df", [("yuv420p", "rgb24"), ("yuv420p", "bgra"), ("yuv422p", "rgb24"),
+                                   ("yuv420p", "rgb48le"), ("yuv420p", "nv12"), ("nv12", "yuv420p"),
+                                   ("yuv420p", "yuv420p"), ("yuv420p10le", "yuv420p10le"),
+                                   ("yuv420p", "yuv422p"), ("yuv420p10le", "rgb48le"),
+                                   ("yuv420p10le", "rgb24")])
+@pytest.mark.parametrize("flags", [S.SWS_BICUBIC, S.SWS_BICUBIC | BX, S.SWS_POINT, S.SWS_BILINEAR | BX])
+def test_same_size(sf, df, flags):
+    _check(sw=642, sh=362, sf=sf, dw=642, dh=362, df=df, flags=flags, seed=21)
+
+
+def test_strided_buffers_and_padding_untouched():
+    """Padded strides on both sides; bytes outside the image must not be written."""
+    case = dict(sw=318, sh=200, sf="yuv420p", dw=318, dh=200, df="rgb24", flags=S.SWS_BICUBIC | BX)
+    src = T.Frame("yuv420p", 318, 200, pad=32).randomize(4)
+    want, _ = T.run_reference(src=src, dst_pad=64, **case)
+    got, _ = T.run_cuda(src=src, dst_pad=64, **case)
+    for g, w in zip(got.planes, want.planes):
+        assert np.array_equal(g, w)      # includes the (zero) padding columns
+
+
+@pytest.mark.parametrize("cs", [(1, 0, 1, 0), (5, 1, 5, 0), (9, 0, 9, 0), (7, 1, 7, 1)])
+@pytest.mark.parametrize("df", ["rgb24", "rgb48le"])
+def test_colorspace_details(cs, df):
+    """BT.709 / full range / BT.2020 / SMPTE240M through sws_setColorspaceDetails()."""
+    src_cs, src_range, dst_cs, dst_range = cs
+    colorspace = (src_cs, src_range, dst_cs, dst_range, 0, 1 << 16, 1 << 16)
+    _check(sw=320, sh=240, sf="yuv420p", dw=320, dh=240, df=df, flags=S.SWS_BICUBIC | BX,
+           seed=8, colorspace=colorspace)
+    _check(sw=320, sh=240, sf="yuv420p", dw=480, dh=360, df=df, flags=S.SWS_BICUBIC | BX,
+           seed=9, colorspace=colorspace)
+
+
+def test_brightness_contrast_saturation():
+    colorspace = (5, 0, 5, 0, 3000, int(1.2 * 65536), int(0.8 * 65536))
+    _check(sw=320, sh=240, sf="yuv420p", dw=320, dh=240, df="rgb24", flags=S.SWS_BICUBIC | BX,
+           seed=8, colorspace=colorspace)
+
+
+@pytest.mark.parametrize("ranges", [(0, 1), (1, 0)])
+@pytest.mark.parametrize("df", ["yuv420p", "yuv420p10le", "yuv420p16le"])
+def test_range_conversion(ranges, df):
+    """limited<->full conversion on the h-scaled lines (reference swscale.c:163-255)."""
+    _check(sw=320, sh=240, sf="yuv420p", dw=400, dh=300, df=df, flags=S.SWS_BICUBIC | BX, seed=13,
+           ctx_kwargs=dict(src_range=ranges[0], dst_range=ranges[1]))
+    _check(sw=320, sh=240, sf="yuv420p", dw=320, dh=240, df=df, flags=S.SWS_BICUBIC | BX, seed=14,
+           ctx_kwargs=dict(src_range=ranges[0], dst_range=ranges[1]))
+
+
+@pytest.mark.parametrize("chr_pos", [(0, 128, -513, -513), (0, 0, -513, -513), (128, 128, 0, 0)])
+def test_chroma_siting(chr_pos):
+    """left / top-left chroma siting makes the horizontal chroma FIR a half-sample shift (§3.3)."""
+    _check(sw=320, sh=240, sf="yuv420p", dw=320, dh=240, df="rgb24", flags=S.SWS_BICUBIC | BX,
+           seed=15, ctx_kwargs=dict(chr_pos=chr_pos))
+    _check(sw=320, sh=240, sf="yuv420p", dw=200, dh=150, df="yuv420p", flags=S.SWS_BICUBIC | BX,
+           seed=16, ctx_kwargs=dict(chr_pos=chr_pos))
+
+
+@pytest.mark.parametrize("case", [
+    dict(sw=640, sh=480, sf="yuv420p", dw=640, dh=480, df="rgb24", flags=S.SWS_BICUBIC | BX),
+    dict(sw=640, sh=480, sf="yuv420p", dw=320, dh=200, df="yuv420p", flags=S.SWS_BICUBIC | BX),
+    dict(sw=320, sh=240, sf="yuv420p", dw=640, dh=480, df="rgb24", flags=S.SWS_LANCZOS | BX),
+    dict(sw=640, sh=480, sf="yuv420p", dw=640, dh=480, df="rgb24", flags=S.SWS_BICUBIC),
+])
+@pytest.mark.parametrize("slice_h", [2, 16, 64, 200])
+def test_slices_top_down(case, slice_h):
+    """The legacy slice API: feed the source in horizontal bands (reference swscale.h:556-585)."""
+    sh = case["sh"]
+    slices = [(y, min(slice_h, sh - y)) for y in range(0, sh, slice_h)]
+    _check(seed=17, slices=slices, **case)
+
+
+def test_tiny_and_ragged_sizes():
+    for (sw, sh, dw, dh) in [(16, 16, 16, 16), (18, 10, 34, 22), (1920, 2, 1920, 2), (4, 1080, 4, 1080),
+                             (130, 66, 62, 30), (34, 34, 1280, 720)]:
+        _check(sw=sw, sh=sh, sf="yuv420p", dw=dw, dh=dh, df="rgb24", flags=S.SWS_BICUBIC | BX, seed=19)
+        _check(sw=sw, sh=sh, sf="yuv420p", dw=dw, dh=dh, df="yuv420p", flags=S.SWS_BICUBIC | BX, seed=20)
+
+
+def test_unsupported_fails_loudly():
+    """No silent CPU fallback: what the CUDA path does not implement must fail at init."""
+    with pytest.raises(RuntimeError):
+        S.SwsContext(320, 240, "yuv420p", 320, 240, "rgb24", S.SWS_FAST_BILINEAR)
+    with pytest.raises(RuntimeError):
+        S.SwsContext(320, 240, "yuv444p", 321, 240, "rgb24", S.SWS_BICUBIC | BX)  # full-chroma path
