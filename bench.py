@@ -1,0 +1,360 @@
+#!/usr/bin/env python3
+"""bench.py -- the libswscale hot-path benchmark (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (config.workload): 3840x2160 yuv420p -> rgb24, SWS_BICUBIC |
+SWS_BITEXACT | SWS_ACCURATE_RND -- BASELINE.json configs[4], the configuration
+the metric is quoted on; one 4K frame is 37.3 MB so it fits one GPU trivially.
+A step = one pass of the hot path over FRAMES_PER_GPU distinct synthetic frames
+(64 per GPU => 512 frames at 8 GPUs, the reference batch of configs[4]); frames
+are partitioned across ranks with no data-path collective (weak scaling).
+
+value   : Mpixels/s, whole job, frames already resident in HBM (one batched
+          launch per step through sws_cuda_scale_batch()).
+e2e     : Mpixels/s through the reference-facing call sws_scale() with HOST
+          (pinned) buffers -- H2D + kernel + D2H inside the timed region.
+roofline: algorithmic bytes (4.5 B/pixel) / average kernel
+          duration, against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline: the real reference C path (oracle/_ref) on the host cores, bounded sample.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H = 3840, 2160
+FRAMES_PER_GPU = 64          # 64 x 37.3 MB = 2.39 GB per step per GPU  (>> 126 MB L2)
+E2E_FRAMES = 16
+ALG_BYTES_PER_PIXEL = 4.5    # 1.5 B in (yuv420p) + 3 B out (rgb24)
+WORKLOAD = "3840x2160 yuv420p->rgb24 SWS_BICUBIC|SWS_BITEXACT|SWS_ACCURATE_RND"
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the path (oracle/_ref, built from the
+    unmodified /root/reference sources) with all host threads, on the same config."""
+    if rank != 0:
+        return
+    from oracle import refapi as R
+    if not R.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libswsref.so not built"}))
+        return
+    import numpy as np
+    cores = host_cores()
+    ctx = R.RefContext(W, H, "yuv420p", W, H, "rgb24", R.SWS_BICUBIC | R.BX, threads=cores)
+    src = R.RefFrame(W, H, "yuv420p")
+    dst = R.RefFrame(W, H, "rgb24")
+    rng = np.random.default_rng(1234)
+    for i, rows in enumerate((H, H // 2, H // 2)):
+        a, ls = src.plane(i, rows)
+        a[:] = rng.integers(0, 256, a.shape, dtype=np.uint8)
+    frames_per_step = 8          # bounded sample of the 64-frame step
+    L = R.lib()
+    for _ in range(max(args.warmup, 1)):
+        L.swsref_bench_frame(ctx.h, dst.f, src.f, 2)
+    t = 0.0
+    for _ in range(args.steps):
+        dt = L.swsref_bench_frame(ctx.h, dst.f, src.f, frames_per_step)
+        if dt < 0:
+            raise RuntimeError("reference sws_scale_frame failed")
+        t += dt
+    mpix = frames_per_step * args.steps * W * H / t / 1e6
+    line = {
+        "impl": "reference", "metric": "Mpixels/s", "value": mpix, "unit": "Mpixels/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": frames_per_step,
+                   "note": "reference C path (sws_scale_frame, slice-threaded) on host cores; "
+                           "bounded sample of the 64-frame step"},
+        "cpu_baseline": {"value": mpix, "unit": "Mpixels/s", "cores": cores, "kind": "reference",
+                         "sample": "%d frames x %d steps, threads=%d" % (frames_per_step, args.steps, cores)},
+        "e2e": {"value": mpix, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline_sample(seconds=12.0):
+    """rank 0, N=1: the reference on the host cores, ~10-30 s of CPU work."""
+    from oracle import refapi as R
+    if not R.available():
+        return None
+    import numpy as np
+    cores = host_cores()
+    out = {}
+    rng = np.random.default_rng(1234)
+    src = R.RefFrame(W, H, "yuv420p")
+    dst = R.RefFrame(W, H, "rgb24")
+    for i, rows in enumerate((H, H // 2, H // 2)):
+        a, ls = src.plane(i, rows)
+        a[:] = rng.integers(0, 256, a.shape, dtype=np.uint8)
+    L = R.lib()
+    for label, threads in (("threads_all", cores), ("threads_1", 1)):
+        ctx = R.RefContext(W, H, "yuv420p", W, H, "rgb24", R.SWS_BICUBIC | R.BX, threads=threads)
+        L.swsref_bench_frame(ctx.h, dst.f, src.f, 1)
+        n, t = 0, 0.0
+        budget = seconds * (0.7 if threads > 1 else 0.3)
+        while t < budget:
+            k = 4 if threads > 1 else 1
+            t += L.swsref_bench_frame(ctx.h, dst.f, src.f, k)
+            n += k
+        out[label] = (n * W * H / t / 1e6, n, t)
+        ctx.close()
+    return {"value": out["threads_all"][0], "unit": "Mpixels/s", "cores": cores, "kind": "reference",
+            "sample": "%d 4K frames in %.1f s with %d threads (sws_scale_frame, bitexact+accurate_rnd C path); "
+                      "1 thread: %.1f Mpixels/s" % (out["threads_all"][1], out["threads_all"][2], cores,
+                                                    out["threads_1"][0])}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_b200_arm(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    from librempeg_b200 import swscale as S
+
+    if not torch.cuda.is_available() or S.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    flags = S.SWS_BICUBIC | S.BX
+    ctx = S.SwsContext(W, H, "yuv420p", W, H, "rgb24", flags)
+    F = FRAMES_PER_GPU
+    ysz, csz, osz = W * H, (W // 2) * (H // 2), W * H * 3
+    # distinct synthetic frames, seed depends on the global frame index
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    src_y = torch.randint(0, 256, (F, ysz), dtype=torch.uint8, device=dev, generator=g)
+    src_u = torch.randint(0, 256, (F, csz), dtype=torch.uint8, device=dev, generator=g)
+    src_v = torch.randint(0, 256, (F, csz), dtype=torch.uint8, device=dev, generator=g)
+    dst = torch.zeros((F, osz), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def step():
+        r = ctx.scale_batch_device([src_y, src_u, src_v], [W, W // 2, W // 2], [ysz, csz, csz],
+                                   [dst], [W * 3], [osz], F)
+        if r < 0:
+            raise RuntimeError("sws_cuda_scale_batch failed: %d %s" % (r, ctx.last_error))
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # parity spot-check before any number is reported: frame 0 vs the oracle (rank 0)
+    parity = None
+    if rank == 0:
+        try:
+            from oracle import refapi as R
+            if R.available():
+                rc = R.RefContext(W, H, "yuv420p", W, H, "rgb24", R.SWS_BICUBIC | R.BX)
+                hy, hu, hv = src_y[0].cpu().numpy(), src_u[0].cpu().numpy(), src_v[0].cpu().numpy()
+                want = np.zeros(osz, np.uint8)
+                rc.scale([hy, hu, hv], [W, W // 2, W // 2], [want], [W * 3])
+                parity = bool(np.array_equal(want, dst[0].cpu().numpy()))
+                rc.close()
+                if not parity:
+                    raise AssertionError("bench: CUDA output differs from the reference; refusing to time")
+        except ImportError:
+            pass
+
+    sampler = ClockSampler(local_rank)
+    launches0 = ctx.launch_count
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    # ---- e2e: sws_scale() on pinned HOST frames, H2D + kernel + D2H timed ----
+    EF = E2E_FRAMES
+    h_y = torch.empty((EF, ysz), dtype=torch.uint8).pin_memory()
+    h_u = torch.empty((EF, csz), dtype=torch.uint8).pin_memory()
+    h_v = torch.empty((EF, csz), dtype=torch.uint8).pin_memory()
+    h_o = torch.empty((EF, osz), dtype=torch.uint8).pin_memory()
+    h_y.copy_(src_y[:EF]); h_u.copy_(src_u[:EF]); h_v.copy_(src_v[:EF])
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        for f in range(EF):
+            r = ctx.scale([h_y[f].data_ptr(), h_u[f].data_ptr(), h_v[f].data_ptr()], [W, W // 2, W // 2],
+                          [h_o[f].data_ptr()], [W * 3], 0, H)
+            if r != H:
+                raise RuntimeError("sws_scale failed: %d" % r)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_mpix = world * EF * e2e_steps * W * H / float(te.item()) / 1e6
+    if rank == 0 and parity is not None:
+        # the host path must give the same bytes as the device path
+        assert np.array_equal(h_o[0].numpy(), dst[0].cpu().numpy()), "host and device paths disagree"
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    step_ms = ms_max / args.steps
+    pixels_per_step = F * W * H
+    value = world * pixels_per_step / (step_ms * 1e-3) / 1e6
+    kernel_ms = ms / max(launches, 1)          # rank-0 kernel: one launch per step
+    bytes_per_launch = ALG_BYTES_PER_PIXEL * pixels_per_step * (args.steps / max(launches, 1))
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(ctx.kernel_name)
+    except Exception:
+        pass
+
+    line = {
+        "metric": "Mpixels/s", "value": value, "unit": "Mpixels/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F,
+                   "bytes_per_step_per_gpu": int(ALG_BYTES_PER_PIXEL * pixels_per_step),
+                   "l2_policy": "inputs larger than L2: %d distinct frames (%.2f GB) cycled every step"
+                                % (F, ALG_BYTES_PER_PIXEL * pixels_per_step / 1e9),
+                   "partition": "frames round-robin over ranks, no collective",
+                   "kernel": ctx.kernel_name, "parity_checked_vs_reference": parity},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "kernel": ctx.kernel_name, "kernel_ms": kernel_ms,
+                     "algorithmic_bytes_per_launch": bytes_per_launch},
+        "e2e": {"value": e2e_mpix, "unit": "Mpixels/s",
+                "h2d_bytes_per_step": int(EF * (ysz + 2 * csz)), "d2h_bytes_per_step": int(EF * osz),
+                "frames_per_step": EF, "call": "sws_scale() per frame, pinned host buffers"},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline_sample()
+        if cb:
+            line["cpu_baseline"] = cb
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+    else:
+        run_b200_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,6 +24,7 @@
 #include <errno.h>
 
 #include "sws_internal.h"
+#include "sws_fast420.cuh"
 
 #define CUDA_OK(call)                                                           \
     do {                                                                        \
@@ -423,6 +424,10 @@ struct SwsCudaState {
     int src_rowbytes[4], dst_rowbytes[4];
     long launches;
     const char *kernel_name;
+    /* fast420 path */
+    int fast_ok;
+    int4 *d_fast_rows;
+    int num_sms;
     int tile_w, tile_h, rows_l_cap, rows_c_cap;
     size_t smem_bytes;
 };
@@ -507,6 +512,150 @@ static int plan_tiles(SwsCudaState *st)
     return AVERROR(ENOTSUP);
 }
 
+
+/* ---------------------------------------------------------------- fast420 host side */
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode_tiled(void)
+{
+    static encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (encode_tiled_fn)p;
+    }
+    return fn;
+}
+
+static int make_map_3d(CUtensorMap *m, CUtensorMapDataType dt, const void *base, uint64_t d0, uint64_t d1,
+                       uint64_t d2, uint64_t stride1, uint64_t stride2, uint32_t b0, uint32_t b1)
+{
+    encode_tiled_fn enc = get_encode_tiled();
+    if (!enc)
+        return AVERROR(ENOSYS);
+    cuuint64_t dims[3] = { d0, d1, d2 };
+    cuuint64_t strides[2] = { stride1, stride2 };
+    cuuint32_t box[3] = { b0, b1, 1 };
+    cuuint32_t es[3] = { 1, 1, 1 };
+    CUresult r = enc(m, dt, 3, const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[swscaler-b200] cuTensorMapEncodeTiled failed: %d\n", (int)r);
+        return AVERROR(EIO);
+    }
+    return 0;
+}
+
+/* decide at init whether the conversion qualifies for the fast420 kernel and build its row table */
+static int fast420_setup(SwsCudaState *st, const SwsFirBank *vc)
+{
+    const SwsCudaPlan *p = &st->plan;
+    st->fast_ok = 0;
+    if (p->src_layout != SWSC_SRC_PLANAR || p->src_bits != 8 || p->inter_bits != 15)
+        return 0;
+    if (p->dst_kind != SWSC_DST_RGB24 && p->dst_kind != SWSC_DST_BGR24)
+        return 0;
+    if (!p->lum_identity || !p->chr_h_identity || p->chr_src_hsub != 1 || p->chr_dst_hsub != 1)
+        return 0;
+    if (vc->size > 4 || p->range_mode || (p->dst_w & 3) || !get_encode_tiled())
+        return 0;
+    if (max_rows_needed(vc->pos, vc->size > 4 ? vc->size : 4, vc->len, F420_TH) > F420_CROWS)
+        return 0;
+    int4 *rows = (int4 *)malloc(sizeof(int4) * vc->len);
+    if (!rows)
+        return AVERROR(ENOMEM);
+    for (int y = 0; y < vc->len; y++) {
+        uint32_t cl = 0, ch = 0;
+        for (int j = 0; j < vc->size; j++) {
+            const int c = vc->coef[(size_t)y * vc->size + j];
+            cl |= (uint32_t)(c & 0xFF) << (8 * j);
+            ch |= (uint32_t)((c >> 8) & 0xFF) << (8 * j);
+        }
+        int pos = vc->pos[y];
+        /* keep the 4-row window inside the plane: taps beyond vc->size are zero */
+        if (pos + 4 > p->chr_src_h && p->chr_src_h >= 4) {
+            const int shift = pos + 4 - p->chr_src_h;
+            if (shift * 8 < 32 && (cl >> (32 - 8 * shift)) == 0 && (ch >> (32 - 8 * shift)) == 0) {
+                cl <<= 8 * shift; ch <<= 8 * shift; pos -= shift;
+            }
+        }
+        rows[y] = make_int4(pos, (int)cl, (int)ch, 0);
+    }
+    /* the shift above must not break monotonicity of pos (the kernel's window only slides down) */
+    for (int y = 1; y < vc->len; y++)
+        if (rows[y].x < rows[y - 1].x) {
+            free(rows);
+            return 0;
+        }
+    cudaError_t e = cudaMalloc(&st->d_fast_rows, sizeof(int4) * vc->len);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(st->d_fast_rows, rows, sizeof(int4) * vc->len, cudaMemcpyHostToDevice);
+    free(rows);
+    CUDA_OK(e);
+    CUDA_OK(cudaFuncSetAttribute((const void *)sws_fast420_rgb8_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, F420_SMEM));
+    st->fast_ok = 1;
+    st->kernel_name = "fast420_rgb8_tma";
+    return 0;
+}
+
+static bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
+/* returns 1 if launched, 0 if the arguments do not qualify (caller falls back to the generic kernel) */
+static int fast420_launch(SwsCudaState *st, const uint8_t *const src[4], const int src_stride[4],
+                          const int64_t src_fstride[4], uint8_t *const dst[4], const int dst_stride[4],
+                          const int64_t dst_fstride[4], int nb_frames, int y0, int y1)
+{
+    const SwsCudaPlan *p = &st->plan;
+    if (!st->fast_ok || y0 != 0 || y1 != p->dst_h)
+        return 0;
+    for (int i = 0; i < 3; i++)
+        if (!aligned16(src[i]) || (src_stride[i] & 15) || src_stride[i] <= 0 ||
+            (nb_frames > 1 && (src_fstride[i] & 15 || src_fstride[i] <= 0)))
+            return 0;
+    if (!aligned16(dst[0]) || (dst_stride[0] & 15) || dst_stride[0] <= 0 ||
+        (nb_frames > 1 && (dst_fstride[0] & 15 || dst_fstride[0] <= 0)))
+        return 0;
+    CUtensorMap my, mu, mv, mo;
+    const uint64_t fs_y = nb_frames > 1 ? src_fstride[0] : (uint64_t)src_stride[0] * p->src_h;
+    const uint64_t fs_u = nb_frames > 1 ? src_fstride[1] : (uint64_t)src_stride[1] * p->chr_src_h;
+    const uint64_t fs_v = nb_frames > 1 ? src_fstride[2] : (uint64_t)src_stride[2] * p->chr_src_h;
+    const uint64_t fs_o = nb_frames > 1 ? dst_fstride[0] : (uint64_t)dst_stride[0] * p->dst_h;
+    int ret;
+    if ((ret = make_map_3d(&my, CU_TENSOR_MAP_DATA_TYPE_UINT8, src[0], p->src_w, p->src_h, nb_frames,
+                           src_stride[0], fs_y, F420_TW, F420_TH)) < 0 ||
+        (ret = make_map_3d(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT8, src[1], p->chr_src_w, p->chr_src_h, nb_frames,
+                           src_stride[1], fs_u, F420_TW / 2, F420_CROWS)) < 0 ||
+        (ret = make_map_3d(&mv, CU_TENSOR_MAP_DATA_TYPE_UINT8, src[2], p->chr_src_w, p->chr_src_h, nb_frames,
+                           src_stride[2], fs_v, F420_TW / 2, F420_CROWS)) < 0 ||
+        (ret = make_map_3d(&mo, CU_TENSOR_MAP_DATA_TYPE_UINT32, dst[0], (uint64_t)p->dst_w * 3 / 4, p->dst_h,
+                           nb_frames, dst_stride[0], fs_o, F420_TW * 3 / 4, F420_TH)) < 0)
+        return ret;
+    Fast420Args a;
+    a.tiles_x = (p->dst_w + F420_TW - 1) / F420_TW;
+    a.tiles_y = (p->dst_h + F420_TH - 1) / F420_TH;
+    a.frames = nb_frames;
+    a.dst_h = p->dst_h;
+    a.bgr = p->dst_kind == SWSC_DST_BGR24;
+    a.cy = p->rgb.cy; a.yb = p->rgb.yb;
+    a.crv = p->rgb.crv; a.cbu = p->rgb.cbu; a.cgu = p->rgb.cgu; a.cgv = p->rgb.cgv;
+    a.kr = p->rgb.base_r << 16; a.kg = p->rgb.base_g << 16; a.kb = p->rgb.base_b << 16;
+    a.rows = st->d_fast_rows;
+    const long long total = (long long)a.tiles_x * a.tiles_y * nb_frames;
+    const int grid = (int)(total < (long long)st->num_sms * 4 ? total : (long long)st->num_sms * 4);
+    sws_fast420_rgb8_kernel<<<grid, F420_THREADS, F420_SMEM, st->stream>>>(my, mu, mv, mo, a);
+    CUDA_OK(cudaGetLastError());
+    st->launches++;
+    return 1;
+}
+
 typedef void (*generic_kernel_t)(const SwsCudaPlan, const FrameArgs);
 
 static generic_kernel_t pick_generic(const SwsCudaPlan *p)
@@ -571,6 +720,10 @@ extern "C" int ff_b200_cuda_create(SwsCudaState **out, SwsCudaPlan *plan,
     st->kernel_name = "generic_tile";
     CUDA_OK(cudaFuncSetAttribute((const void *)pick_generic(&st->plan),
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem_bytes));
+    CUDA_OK(cudaDeviceGetAttribute(&st->num_sms, cudaDevAttrMultiProcessorCount, dev));
+    ret = fast420_setup(st, vc);
+    if (ret < 0)
+        return ret;
     return 0;
 }
 
@@ -583,6 +736,7 @@ extern "C" void ff_b200_cuda_destroy(SwsCudaState *st)
         cudaStreamDestroy(st->stream);
     }
     cudaFree(st->tables);
+    cudaFree(st->d_fast_rows);
     for (int i = 0; i < 4; i++) {
         cudaFree(st->d_src[i]);
         cudaFree(st->d_dst[i]);
@@ -614,6 +768,11 @@ extern "C" int ff_b200_cuda_launch(SwsCudaState *st,
     int cur = -1;
     if (cudaGetDevice(&cur) == cudaSuccess && cur != st->device)
         CUDA_OK(cudaSetDevice(st->device));
+    {
+        int r = fast420_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1);
+        if (r != 0)
+            return r < 0 ? r : 0;
+    }
     FrameArgs a;
     memset(&a, 0, sizeof(a));
     for (int i = 0; i < 4; i++) {

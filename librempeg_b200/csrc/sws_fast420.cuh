@@ -1,0 +1,256 @@
+/*
+ * sws_fast420.cuh -- the headline kernel: planar 8-bit 4:2:0 / 4:2:2 -> packed 8-bit RGB
+ * when the luma path is the identity and chroma is only filtered vertically
+ * (BASELINE configs C1, C2, C5 and the default-flags LUT converter).
+ *
+ * Fuses, per 256x32 output tile, what the reference runs per line as
+ *   hScale8To15_c (identity: x<<7)            libswscale/swscale.c:128-142
+ *   yuv2rgb24_X_c / _1_c (vertical chroma FIR) libswscale/output.c:1788-1939
+ *   yuv2rgb_write + LUTs (closed form)         libswscale/output.c:1697-1713, yuv2rgb.c:680-914
+ *
+ * Data movement: TMA (cp.async.bulk.tensor) loads the Y/U/V tiles into shared
+ * memory behind an mbarrier, double-buffered across the tiles of a persistent
+ * CTA; results are staged in shared memory and leave through one TMA tensor
+ * store per tile, so every HBM transaction is a full coalesced line.
+ *
+ * Arithmetic (exact): with identity H the 15-bit line is u<<7, so
+ *   U = (2^18 + sum_j (u_j<<7) c_j) >> 19 = (2048 + sum_j u_j c_j) >> 12.
+ * Split c_j = 256*ch_j + cl_j (cl_j in 0..255): S = 256*T + L, and
+ *   U = (T + ((L + 2048) >> 8)) >> 4                      -- two IDP.4A + two shifts.
+ * The four vertical taps of one chroma column live in one register (a sliding
+ * byte window advanced with one PRMT per column per source row).
+ */
+#pragma once
+
+#include <cuda.h>
+
+#define F420_TW 256          /* tile width  (luma pixels)  */
+#define F420_TH 32           /* tile height (luma rows)    */
+#define F420_CROWS 20        /* chroma source rows staged per tile */
+#define F420_THREADS 256
+#define F420_IN_BYTES (F420_TW * F420_TH + 2 * (F420_TW / 2) * F420_CROWS)   /* 13312 */
+#define F420_OUT_BYTES (F420_TW * 3 * F420_TH)                               /* 24576 */
+#define F420_STAGES 2
+#define F420_SMEM (F420_STAGES * F420_IN_BYTES + F420_OUT_BYTES)
+
+struct Fast420Args {
+    int tiles_x, tiles_y, frames;
+    int dst_h;
+    int bgr;                       /* 0: R,G,B byte order, 1: B,G,R */
+    int cy, yb;                    /* LUT closed form (sws_colorspace.c) */
+    int crv, cbu, cgu, cgv;
+    int kr, kg, kb;                /* index bases << 16 */
+    const int4 *rows;              /* per output row: {chroma pos, cl pack, ch pack, 0} */
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int x, int y, int z)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+        ::"l"(map), "r"(smem_u32(src)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+__device__ __forceinline__ int dp4a_uu(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+__device__ __forceinline__ int clamp_u8(int v)
+{
+    int d;
+    asm("min.relu.s32 %0, %1, 255;" : "=r"(d) : "r"(v));
+    return d;
+}
+
+__device__ __forceinline__ uint32_t clamp_u8x2(uint32_t v)
+{
+    uint32_t d;
+    asm("min.relu.s16x2 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(0x00FF00FFu));
+    return d;
+}
+
+__global__ void __launch_bounds__(F420_THREADS, 4)
+sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
+                        const __grid_constant__ CUtensorMap map_u,
+                        const __grid_constant__ CUtensorMap map_v,
+                        const __grid_constant__ CUtensorMap map_o,
+                        const __grid_constant__ Fast420Args A)
+{
+    /* carve-up: [stage0 in][stage1 in][out]; every TMA box starts 128-byte aligned */
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[F420_STAGES];
+    unsigned char *out_buf = smem_dyn + F420_STAGES * F420_IN_BYTES;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles_per_frame = A.tiles_x * A.tiles_y;
+    const int total = tiles_per_frame * A.frames;
+
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_u) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_o) : "memory");
+        for (int s = 0; s < F420_STAGES; s++)
+            mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int tile, int stage) {
+        const int f = tile / tiles_per_frame;
+        const int t = tile - f * tiles_per_frame;
+        const int ty = t / A.tiles_x, tx = t - ty * A.tiles_x;
+        const int y0 = ty * F420_TH;
+        const int c_lo = A.rows[y0].x;
+        unsigned char *b = smem_dyn + stage * F420_IN_BYTES;
+        mbar_expect_tx(&full_bar[stage], F420_IN_BYTES);
+        tma_load_3d(b, &map_y, &full_bar[stage], tx * F420_TW, y0, f);
+        tma_load_3d(b + F420_TW * F420_TH, &map_u, &full_bar[stage], tx * (F420_TW / 2), c_lo, f);
+        tma_load_3d(b + F420_TW * F420_TH + (F420_TW / 2) * F420_CROWS, &map_v, &full_bar[stage],
+                    tx * (F420_TW / 2), c_lo, f);
+    };
+
+    int tile = blockIdx.x;
+    if (tile < total && tid == 0)
+        issue(tile, 0);
+
+    const int cy = A.cy, yb = A.yb;
+    uint32_t phase_bits = 0;
+    int it = 0;
+
+    for (; tile < total; tile += gridDim.x, it++) {
+        const int stage = it & 1;
+        const int next = tile + gridDim.x;
+        if (tid == 0 && next < total)
+            issue(next, stage ^ 1);      /* buffer was released by the barrier that ended iteration it-1 */
+
+        const int f = tile / tiles_per_frame;
+        const int t = tile - f * tiles_per_frame;
+        const int ty = t / A.tiles_x, tx = t - ty * A.tiles_x;
+        const int y0 = ty * F420_TH;
+        const int c_lo = A.rows[y0].x;
+
+        mbar_wait(&full_bar[stage], (phase_bits >> stage) & 1);
+        phase_bits ^= 1u << stage;
+
+        const unsigned char *sy = smem_dyn + stage * F420_IN_BYTES;
+        const unsigned char *su = sy + F420_TW * F420_TH;
+        const unsigned char *sv = su + (F420_TW / 2) * F420_CROWS;
+
+        /* the previous tile's TMA store must have finished READING out_buf */
+        if (tid == 0)
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();
+
+        /* each warp converts 4 rows; each lane 8 pixels (4 chroma columns) */
+        uint32_t wu[4] = { 0, 0, 0, 0 }, wv[4] = { 0, 0, 0, 0 };
+        int wpos = -1000;                      /* chroma row (tile relative) of window byte 0 */
+#pragma unroll 1
+        for (int rr = 0; rr < F420_TH / 8; rr++) {
+            const int r = warp * (F420_TH / 8) + rr;
+            const int y = min(y0 + r, A.dst_h - 1);
+            const int4 row = A.rows[y];
+            const int pos = row.x - c_lo;
+            if (wpos + 4 <= pos || wpos > pos)
+                wpos = pos - 4;                /* (re)fill from scratch */
+            while (wpos < pos) {               /* slide the 4-row window down by one source row */
+                const int nr = min(wpos + 4, F420_CROWS - 1);
+                const uint32_t nu = *reinterpret_cast<const uint32_t *>(su + nr * (F420_TW / 2) + lane * 4);
+                const uint32_t nv = *reinterpret_cast<const uint32_t *>(sv + nr * (F420_TW / 2) + lane * 4);
+                wu[0] = prmt(wu[0], nu, 0x4321); wu[1] = prmt(wu[1], nu, 0x5321);
+                wu[2] = prmt(wu[2], nu, 0x6321); wu[3] = prmt(wu[3], nu, 0x7321);
+                wv[0] = prmt(wv[0], nv, 0x4321); wv[1] = prmt(wv[1], nv, 0x5321);
+                wv[2] = prmt(wv[2], nv, 0x6321); wv[3] = prmt(wv[3], nv, 0x7321);
+                wpos++;
+            }
+            const uint32_t clp = (uint32_t)row.y, chp = (uint32_t)row.z;
+            const uint2 yw = *reinterpret_cast<const uint2 *>(sy + r * F420_TW + lane * 8);
+            uint32_t h[12];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                int U = dp4a_uu(wu[c], clp, 2048) >> 8;
+                U = clamp_u8(dp4a_us(wu[c], chp, U) >> 4);
+                int V = dp4a_uu(wv[c], clp, 2048) >> 8;
+                V = clamp_u8(dp4a_us(wv[c], chp, V) >> 4);
+                const int pr = ((V * A.crv + A.kr) >> 16) * cy + yb;
+                const int pb = ((U * A.cbu + A.kb) >> 16) * cy + yb;
+                const int pg = (((U * A.cgu) >> 16) + ((V * A.cgv + A.kg) >> 16)) * cy + yb;
+                const uint32_t w = (c < 2) ? yw.x : yw.y;
+                const int ya = (w >> ((c & 1) * 16)) & 0xFF;
+                const int yc = (w >> ((c & 1) * 16 + 8)) & 0xFF;
+                const int p0 = A.bgr ? pb : pr, p2 = A.bgr ? pr : pb;
+                const uint32_t t0a = ya * cy + p0, t1a = ya * cy + pg, t2a = ya * cy + p2;
+                const uint32_t t0b = yc * cy + p0, t1b = yc * cy + pg, t2b = yc * cy + p2;
+                /* high halves are (t >> 16) as s16: pack pairs, clamp both lanes at once */
+                h[3 * c + 0] = clamp_u8x2(prmt(t0a, t1a, 0x7632));
+                h[3 * c + 1] = clamp_u8x2(prmt(t2a, t0b, 0x7632));
+                h[3 * c + 2] = clamp_u8x2(prmt(t1b, t2b, 0x7632));
+            }
+            uint2 *o = reinterpret_cast<uint2 *>(out_buf + r * (F420_TW * 3) + lane * 24);
+            o[0] = make_uint2(prmt(h[0], h[1], 0x6420), prmt(h[2], h[3], 0x6420));
+            o[1] = make_uint2(prmt(h[4], h[5], 0x6420), prmt(h[6], h[7], 0x6420));
+            o[2] = make_uint2(prmt(h[8], h[9], 0x6420), prmt(h[10], h[11], 0x6420));
+        }
+
+        /* publish the tile: generic-proxy writes -> async proxy, then one TMA store */
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_3d(&map_o, out_buf, tx * (F420_TW * 3 / 4), y0, f);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (tid == 0)
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
