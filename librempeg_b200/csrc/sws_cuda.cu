@@ -599,7 +599,9 @@ static int fast420_setup(SwsCudaState *st, const SwsFirBank *vc)
         e = cudaMemcpy(st->d_fast_rows, rows, sizeof(int4) * vc->len, cudaMemcpyHostToDevice);
     free(rows);
     CUDA_OK(e);
-    CUDA_OK(cudaFuncSetAttribute((const void *)sws_fast420_rgb8_kernel,
+    CUDA_OK(cudaFuncSetAttribute((const void *)sws_fast420_rgb8_kernel<false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, F420_SMEM));
+    CUDA_OK(cudaFuncSetAttribute((const void *)sws_fast420_rgb8_kernel<true>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, F420_SMEM));
     st->fast_ok = 1;
     st->kernel_name = "fast420_rgb8_tma";
@@ -650,7 +652,10 @@ static int fast420_launch(SwsCudaState *st, const uint8_t *const src[4], const i
     a.rows = st->d_fast_rows;
     const long long total = (long long)a.tiles_x * a.tiles_y * nb_frames;
     const int grid = (int)(total < (long long)st->num_sms * 4 ? total : (long long)st->num_sms * 4);
-    sws_fast420_rgb8_kernel<<<grid, F420_THREADS, F420_SMEM, st->stream>>>(my, mu, mv, mo, a);
+    if (a.bgr)
+        sws_fast420_rgb8_kernel<true><<<grid, F420_THREADS, F420_SMEM, st->stream>>>(my, mu, mv, mo, a);
+    else
+        sws_fast420_rgb8_kernel<false><<<grid, F420_THREADS, F420_SMEM, st->stream>>>(my, mu, mv, mo, a);
     CUDA_OK(cudaGetLastError());
     st->launches++;
     return 1;

@@ -120,6 +120,17 @@ __device__ __forceinline__ uint32_t clamp_u8x2(uint32_t v)
     return d;
 }
 
+/* 4x4 byte transpose of four row words (4 chroma columns each) into four column words
+ * whose byte j is row j: the vertical taps of one chroma column, ready for IDP.4A. */
+__device__ __forceinline__ void transpose4(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t (&w)[4])
+{
+    const uint32_t a = prmt(r0, r1, 0x5140), b = prmt(r2, r3, 0x5140);   /* cols 0,1 */
+    const uint32_t c = prmt(r0, r1, 0x7362), d = prmt(r2, r3, 0x7362);   /* cols 2,3 */
+    w[0] = prmt(a, b, 0x5410); w[1] = prmt(a, b, 0x7632);
+    w[2] = prmt(c, d, 0x5410); w[3] = prmt(c, d, 0x7632);
+}
+
+template <bool BGR>
 __global__ void __launch_bounds__(F420_THREADS, 4)
 sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
                         const __grid_constant__ CUtensorMap map_u,
@@ -132,7 +143,8 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
     __shared__ __align__(8) uint64_t full_bar[F420_STAGES];
     unsigned char *out_buf = smem_dyn + F420_STAGES * F420_IN_BYTES;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      /* warp-uniform for the compiler */
     const int tiles_per_frame = A.tiles_x * A.tiles_y;
     const int total = tiles_per_frame * A.frames;
 
@@ -166,6 +178,8 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
         issue(tile, 0);
 
     const int cy = A.cy, yb = A.yb;
+    const int crv = A.crv, cbu = A.cbu, cgu = A.cgu, cgv = A.cgv;
+    const int kr = A.kr, kg = A.kg, kb = A.kb;
     uint32_t phase_bits = 0;
     int it = 0;
 
@@ -181,41 +195,52 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
         const int y0 = ty * F420_TH;
         const int c_lo = A.rows[y0].x;
 
+        /* row metadata of this warp's four rows (same address in every lane: one broadcast load) */
+        const int r0 = warp * (F420_TH / 8);
+        int4 meta[F420_TH / 8];
+#pragma unroll
+        for (int rr = 0; rr < F420_TH / 8; rr++)
+            meta[rr] = __ldg(&A.rows[min(y0 + r0 + rr, A.dst_h - 1)]);
+
         mbar_wait(&full_bar[stage], (phase_bits >> stage) & 1);
         phase_bits ^= 1u << stage;
 
-        const unsigned char *sy = smem_dyn + stage * F420_IN_BYTES;
-        const unsigned char *su = sy + F420_TW * F420_TH;
+        const unsigned char *sy = smem_dyn + stage * F420_IN_BYTES + r0 * F420_TW + lane * 8;
+        const unsigned char *su = smem_dyn + stage * F420_IN_BYTES + F420_TW * F420_TH + lane * 4;
         const unsigned char *sv = su + (F420_TW / 2) * F420_CROWS;
+        unsigned char *so = out_buf + r0 * (F420_TW * 3) + lane * 24;
 
         /* the previous tile's TMA store must have finished READING out_buf */
         if (tid == 0)
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncthreads();
 
-        /* each warp converts 4 rows; each lane 8 pixels (4 chroma columns) */
-        uint32_t wu[4] = { 0, 0, 0, 0 }, wv[4] = { 0, 0, 0, 0 };
-        int wpos = -1000;                      /* chroma row (tile relative) of window byte 0 */
-#pragma unroll 1
+        uint32_t wu[4], wv[4];
+        int wpos = -64;                        /* chroma row (tile relative) held in window byte 0 */
+#pragma unroll
         for (int rr = 0; rr < F420_TH / 8; rr++) {
-            const int r = warp * (F420_TH / 8) + rr;
-            const int y = min(y0 + r, A.dst_h - 1);
-            const int4 row = A.rows[y];
-            const int pos = row.x - c_lo;
-            if (wpos + 4 <= pos || wpos > pos)
-                wpos = pos - 4;                /* (re)fill from scratch */
-            while (wpos < pos) {               /* slide the 4-row window down by one source row */
-                const int nr = min(wpos + 4, F420_CROWS - 1);
-                const uint32_t nu = *reinterpret_cast<const uint32_t *>(su + nr * (F420_TW / 2) + lane * 4);
-                const uint32_t nv = *reinterpret_cast<const uint32_t *>(sv + nr * (F420_TW / 2) + lane * 4);
-                wu[0] = prmt(wu[0], nu, 0x4321); wu[1] = prmt(wu[1], nu, 0x5321);
-                wu[2] = prmt(wu[2], nu, 0x6321); wu[3] = prmt(wu[3], nu, 0x7321);
-                wv[0] = prmt(wv[0], nv, 0x4321); wv[1] = prmt(wv[1], nv, 0x5321);
-                wv[2] = prmt(wv[2], nv, 0x6321); wv[3] = prmt(wv[3], nv, 0x7321);
-                wpos++;
+            const int pos = meta[rr].x - c_lo;
+            int d = pos - wpos;
+            if (d < 0 || d >= 4) {             /* (re)fill: transpose rows pos..pos+3 */
+                const unsigned char *pu = su + pos * (F420_TW / 2), *pv = sv + pos * (F420_TW / 2);
+                transpose4(*reinterpret_cast<const uint32_t *>(pu), *reinterpret_cast<const uint32_t *>(pu + 128),
+                           *reinterpret_cast<const uint32_t *>(pu + 256), *reinterpret_cast<const uint32_t *>(pu + 384), wu);
+                transpose4(*reinterpret_cast<const uint32_t *>(pv), *reinterpret_cast<const uint32_t *>(pv + 128),
+                           *reinterpret_cast<const uint32_t *>(pv + 256), *reinterpret_cast<const uint32_t *>(pv + 384), wv);
+            } else {
+#pragma unroll 1
+                for (int nr = wpos + 4; d > 0; d--, nr++) {   /* slide down one source row */
+                    const uint32_t nu = *reinterpret_cast<const uint32_t *>(su + nr * (F420_TW / 2));
+                    const uint32_t nv = *reinterpret_cast<const uint32_t *>(sv + nr * (F420_TW / 2));
+                    wu[0] = prmt(wu[0], nu, 0x4321); wu[1] = prmt(wu[1], nu, 0x5321);
+                    wu[2] = prmt(wu[2], nu, 0x6321); wu[3] = prmt(wu[3], nu, 0x7321);
+                    wv[0] = prmt(wv[0], nv, 0x4321); wv[1] = prmt(wv[1], nv, 0x5321);
+                    wv[2] = prmt(wv[2], nv, 0x6321); wv[3] = prmt(wv[3], nv, 0x7321);
+                }
             }
-            const uint32_t clp = (uint32_t)row.y, chp = (uint32_t)row.z;
-            const uint2 yw = *reinterpret_cast<const uint2 *>(sy + r * F420_TW + lane * 8);
+            wpos = pos;
+            const uint32_t clp = (uint32_t)meta[rr].y, chp = (uint32_t)meta[rr].z;
+            const uint2 yw = *reinterpret_cast<const uint2 *>(sy + rr * F420_TW);
             uint32_t h[12];
 #pragma unroll
             for (int c = 0; c < 4; c++) {
@@ -223,13 +248,13 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
                 U = clamp_u8(dp4a_us(wu[c], chp, U) >> 4);
                 int V = dp4a_uu(wv[c], clp, 2048) >> 8;
                 V = clamp_u8(dp4a_us(wv[c], chp, V) >> 4);
-                const int pr = ((V * A.crv + A.kr) >> 16) * cy + yb;
-                const int pb = ((U * A.cbu + A.kb) >> 16) * cy + yb;
-                const int pg = (((U * A.cgu) >> 16) + ((V * A.cgv + A.kg) >> 16)) * cy + yb;
+                const int pr = ((V * crv + kr) >> 16) * cy + yb;
+                const int pb = ((U * cbu + kb) >> 16) * cy + yb;
+                const int pg = (((U * cgu) >> 16) + ((V * cgv + kg) >> 16)) * cy + yb;
                 const uint32_t w = (c < 2) ? yw.x : yw.y;
-                const int ya = (w >> ((c & 1) * 16)) & 0xFF;
-                const int yc = (w >> ((c & 1) * 16 + 8)) & 0xFF;
-                const int p0 = A.bgr ? pb : pr, p2 = A.bgr ? pr : pb;
+                const int ya = prmt(w, 0u, 0x4440 + 2 * (c & 1));
+                const int yc = prmt(w, 0u, 0x4441 + 2 * (c & 1));
+                const int p0 = BGR ? pb : pr, p2 = BGR ? pr : pb;
                 const uint32_t t0a = ya * cy + p0, t1a = ya * cy + pg, t2a = ya * cy + p2;
                 const uint32_t t0b = yc * cy + p0, t1b = yc * cy + pg, t2b = yc * cy + p2;
                 /* high halves are (t >> 16) as s16: pack pairs, clamp both lanes at once */
@@ -237,7 +262,7 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
                 h[3 * c + 1] = clamp_u8x2(prmt(t2a, t0b, 0x7632));
                 h[3 * c + 2] = clamp_u8x2(prmt(t1b, t2b, 0x7632));
             }
-            uint2 *o = reinterpret_cast<uint2 *>(out_buf + r * (F420_TW * 3) + lane * 24);
+            uint2 *o = reinterpret_cast<uint2 *>(so + rr * (F420_TW * 3));
             o[0] = make_uint2(prmt(h[0], h[1], 0x6420), prmt(h[2], h[3], 0x6420));
             o[1] = make_uint2(prmt(h[4], h[5], 0x6420), prmt(h[6], h[7], 0x6420));
             o[2] = make_uint2(prmt(h[8], h[9], 0x6420), prmt(h[10], h[11], 0x6420));
