@@ -568,7 +568,8 @@ static int fast420_setup(SwsCudaState *st, const SwsFirBank *vc)
         return 0;
     if (max_rows_needed(vc->pos, vc->size > 4 ? vc->size : 4, vc->len, F420_TH) > F420_CROWS)
         return 0;
-    int4 *rows = (int4 *)malloc(sizeof(int4) * vc->len);
+    const int padded = ((vc->len + F420_TH - 1) / F420_TH + 1) * F420_TH;
+    int4 *rows = (int4 *)calloc(padded, sizeof(int4));
     if (!rows)
         return AVERROR(ENOMEM);
     for (int y = 0; y < vc->len; y++) {
@@ -586,17 +587,23 @@ static int fast420_setup(SwsCudaState *st, const SwsFirBank *vc)
                 cl <<= 8 * shift; ch <<= 8 * shift; pos -= shift;
             }
         }
-        rows[y] = make_int4(pos, (int)cl, (int)ch, 0);
+        rows[y] = make_int4(0, (int)cl, (int)ch, pos);
     }
-    /* the shift above must not break monotonicity of pos (the kernel's window only slides down) */
-    for (int y = 1; y < vc->len; y++)
-        if (rows[y].x < rows[y - 1].x) {
+    for (int y = vc->len; y < padded; y++)
+        rows[y] = rows[vc->len - 1];
+    /* the kernel's window only slides down: positions must be monotonic, and every tile must
+     * fit the staged chroma rows */
+    for (int y = 0; y < padded; y++) {
+        const int base = rows[y & ~(F420_TH - 1)].w;
+        rows[y].x = rows[y].w - base;
+        if ((y > 0 && rows[y].w < rows[y - 1].w) || rows[y].x < 0 || rows[y].x + 4 > F420_CROWS) {
             free(rows);
             return 0;
         }
-    cudaError_t e = cudaMalloc(&st->d_fast_rows, sizeof(int4) * vc->len);
+    }
+    cudaError_t e = cudaMalloc(&st->d_fast_rows, sizeof(int4) * padded);
     if (e == cudaSuccess)
-        e = cudaMemcpy(st->d_fast_rows, rows, sizeof(int4) * vc->len, cudaMemcpyHostToDevice);
+        e = cudaMemcpy(st->d_fast_rows, rows, sizeof(int4) * padded, cudaMemcpyHostToDevice);
     free(rows);
     CUDA_OK(e);
     CUDA_OK(cudaFuncSetAttribute((const void *)sws_fast420_rgb8_kernel<false>,
@@ -638,7 +645,7 @@ static int fast420_launch(SwsCudaState *st, const uint8_t *const src[4], const i
         (ret = make_map_3d(&mv, CU_TENSOR_MAP_DATA_TYPE_UINT8, src[2], p->chr_src_w, p->chr_src_h, nb_frames,
                            src_stride[2], fs_v, F420_TW / 2, F420_CROWS)) < 0 ||
         (ret = make_map_3d(&mo, CU_TENSOR_MAP_DATA_TYPE_UINT32, dst[0], (uint64_t)p->dst_w * 3 / 4, p->dst_h,
-                           nb_frames, dst_stride[0], fs_o, F420_TW * 3 / 4, F420_TH)) < 0)
+                           nb_frames, dst_stride[0], fs_o, F420_TW * 3 / 4, F420_TH / F420_CWARPS)) < 0)
         return ret;
     Fast420Args a;
     a.tiles_x = (p->dst_w + F420_TW - 1) / F420_TW;

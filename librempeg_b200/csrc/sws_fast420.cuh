@@ -27,8 +27,12 @@
 #define F420_TW 256          /* tile width  (luma pixels)  */
 #define F420_TH 32           /* tile height (luma rows)    */
 #define F420_CROWS 20        /* chroma source rows staged per tile */
-#define F420_THREADS 256
-#define F420_IN_BYTES (F420_TW * F420_TH + 2 * (F420_TW / 2) * F420_CROWS)   /* 13312 */
+#define F420_CWARPS 8        /* consumer warps, 4 rows each */
+#define F420_THREADS (32 * (F420_CWARPS + 1))   /* + one producer warp */
+#define F420_Y_BYTES (F420_TW * F420_TH)                                     /*  8192 */
+#define F420_C_BYTES ((F420_TW / 2) * F420_CROWS)                            /*  2560 */
+#define F420_META_BYTES (F420_TH * 16)                                       /*   512 */
+#define F420_IN_BYTES (F420_Y_BYTES + 2 * F420_C_BYTES + F420_META_BYTES)    /* 13824 */
 #define F420_OUT_BYTES (F420_TW * 3 * F420_TH)                               /* 24576 */
 #define F420_STAGES 2
 #define F420_SMEM (F420_STAGES * F420_IN_BYTES + F420_OUT_BYTES)
@@ -40,7 +44,9 @@ struct Fast420Args {
     int cy, yb;                    /* LUT closed form (sws_colorspace.c) */
     int crv, cbu, cgu, cgv;
     int kr, kg, kb;                /* index bases << 16 */
-    const int4 *rows;              /* per output row: {chroma pos, cl pack, ch pack, 0} */
+    /* per output row: {chroma row relative to the tile's first chroma row, cl pack, ch pack,
+     * absolute chroma row}; padded to a multiple of F420_TH rows */
+    const int4 *rows;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -76,6 +82,18 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int x, int y, int z)
@@ -138,10 +156,11 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
                         const __grid_constant__ CUtensorMap map_o,
                         const __grid_constant__ Fast420Args A)
 {
-    /* carve-up: [stage0 in][stage1 in][out]; every TMA box starts 128-byte aligned */
+    /* [stage0: Y | U | V | row meta][stage1 ...][out: 8 warps x 4 rows]; TMA boxes 128-byte aligned */
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[F420_STAGES];
-    unsigned char *out_buf = smem_dyn + F420_STAGES * F420_IN_BYTES;
+    __shared__ __align__(8) uint64_t empty_bar[F420_STAGES];
+    __shared__ __align__(16) int4 tile_info[F420_STAGES];     /* {x tile, first row, frame, -} */
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      /* warp-uniform for the compiler */
@@ -149,77 +168,75 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
     const int total = tiles_per_frame * A.frames;
 
     if (tid == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_u) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_o) : "memory");
-        for (int s = 0; s < F420_STAGES; s++)
+        for (int s = 0; s < F420_STAGES; s++) {
             mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], F420_CWARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    auto issue = [&](int tile, int stage) {
-        const int f = tile / tiles_per_frame;
-        const int t = tile - f * tiles_per_frame;
-        const int ty = t / A.tiles_x, tx = t - ty * A.tiles_x;
-        const int y0 = ty * F420_TH;
-        const int c_lo = A.rows[y0].x;
-        unsigned char *b = smem_dyn + stage * F420_IN_BYTES;
-        mbar_expect_tx(&full_bar[stage], F420_IN_BYTES);
-        tma_load_3d(b, &map_y, &full_bar[stage], tx * F420_TW, y0, f);
-        tma_load_3d(b + F420_TW * F420_TH, &map_u, &full_bar[stage], tx * (F420_TW / 2), c_lo, f);
-        tma_load_3d(b + F420_TW * F420_TH + (F420_TW / 2) * F420_CROWS, &map_v, &full_bar[stage],
-                    tx * (F420_TW / 2), c_lo, f);
-    };
+    if (warp == F420_CWARPS) {
+        /* ===== producer: one thread feeds the ring with TMA loads ===== */
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_u) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+            int i = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
+                const int stage = i % F420_STAGES, k = i / F420_STAGES;
+                if (k > 0)
+                    mbar_wait(&empty_bar[stage], (k - 1) & 1);   /* all 8 warps released the slot */
+                const int f = tile / tiles_per_frame;
+                const int t = tile - f * tiles_per_frame;
+                const int ty = t / A.tiles_x, tx = t - ty * A.tiles_x;
+                const int y0 = ty * F420_TH;
+                const int c_lo = __ldg(&A.rows[y0]).w;
+                unsigned char *b = smem_dyn + stage * F420_IN_BYTES;
+                tile_info[stage] = make_int4(tx, y0, f, 0);
+                mbar_expect_tx(&full_bar[stage], F420_IN_BYTES);
+                tma_load_3d(b, &map_y, &full_bar[stage], tx * F420_TW, y0, f);
+                tma_load_3d(b + F420_Y_BYTES, &map_u, &full_bar[stage], tx * (F420_TW / 2), c_lo, f);
+                tma_load_3d(b + F420_Y_BYTES + F420_C_BYTES, &map_v, &full_bar[stage], tx * (F420_TW / 2), c_lo, f);
+                bulk_load_1d(b + F420_Y_BYTES + 2 * F420_C_BYTES, A.rows + y0, F420_META_BYTES, &full_bar[stage]);
+            }
+        }
+        return;
+    }
 
-    int tile = blockIdx.x;
-    if (tile < total && tid == 0)
-        issue(tile, 0);
-
+    /* ===== consumers: each warp converts 4 rows of every tile, 8 pixels per lane ===== */
+    if (lane == 0)
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_o) : "memory");
     const int cy = A.cy, yb = A.yb;
     const int crv = A.crv, cbu = A.cbu, cgu = A.cgu, cgv = A.cgv;
     const int kr = A.kr, kg = A.kg, kb = A.kb;
-    uint32_t phase_bits = 0;
-    int it = 0;
+    const int r0 = warp * (F420_TH / F420_CWARPS);
+    unsigned char *so = smem_dyn + F420_STAGES * F420_IN_BYTES + r0 * (F420_TW * 3) + lane * 24;
+    unsigned char *so_warp = smem_dyn + F420_STAGES * F420_IN_BYTES + r0 * (F420_TW * 3);
 
-    for (; tile < total; tile += gridDim.x, it++) {
-        const int stage = it & 1;
-        const int next = tile + gridDim.x;
-        if (tid == 0 && next < total)
-            issue(next, stage ^ 1);      /* buffer was released by the barrier that ended iteration it-1 */
+    int i = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
+        const int stage = i % F420_STAGES;
+        const unsigned char *sb = smem_dyn + stage * F420_IN_BYTES;
+        mbar_wait(&full_bar[stage], (i / F420_STAGES) & 1);
 
-        const int f = tile / tiles_per_frame;
-        const int t = tile - f * tiles_per_frame;
-        const int ty = t / A.tiles_x, tx = t - ty * A.tiles_x;
-        const int y0 = ty * F420_TH;
-        const int c_lo = A.rows[y0].x;
+        const int4 ti = tile_info[stage];
+        const int4 *mrow = reinterpret_cast<const int4 *>(sb + F420_Y_BYTES + 2 * F420_C_BYTES) + r0;
+        const unsigned char *sy = sb + r0 * F420_TW + lane * 8;
+        const unsigned char *su = sb + F420_Y_BYTES + lane * 4;
+        const unsigned char *sv = su + F420_C_BYTES;
 
-        /* row metadata of this warp's four rows (same address in every lane: one broadcast load) */
-        const int r0 = warp * (F420_TH / 8);
-        int4 meta[F420_TH / 8];
-#pragma unroll
-        for (int rr = 0; rr < F420_TH / 8; rr++)
-            meta[rr] = __ldg(&A.rows[min(y0 + r0 + rr, A.dst_h - 1)]);
-
-        mbar_wait(&full_bar[stage], (phase_bits >> stage) & 1);
-        phase_bits ^= 1u << stage;
-
-        const unsigned char *sy = smem_dyn + stage * F420_IN_BYTES + r0 * F420_TW + lane * 8;
-        const unsigned char *su = smem_dyn + stage * F420_IN_BYTES + F420_TW * F420_TH + lane * 4;
-        const unsigned char *sv = su + (F420_TW / 2) * F420_CROWS;
-        unsigned char *so = out_buf + r0 * (F420_TW * 3) + lane * 24;
-
-        /* the previous tile's TMA store must have finished READING out_buf */
-        if (tid == 0)
+        /* this warp's previous TMA store must have finished READING its staging rows */
+        if (lane == 0)
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncthreads();
+        __syncwarp();
 
         uint32_t wu[4], wv[4];
         int wpos = -64;                        /* chroma row (tile relative) held in window byte 0 */
 #pragma unroll
-        for (int rr = 0; rr < F420_TH / 8; rr++) {
-            const int pos = meta[rr].x - c_lo;
+        for (int rr = 0; rr < F420_TH / F420_CWARPS; rr++) {
+            const int4 meta = mrow[rr];
+            const int pos = meta.x;
             int d = pos - wpos;
             if (d < 0 || d >= 4) {             /* (re)fill: transpose rows pos..pos+3 */
                 const unsigned char *pu = su + pos * (F420_TW / 2), *pv = sv + pos * (F420_TW / 2);
@@ -239,15 +256,14 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
                 }
             }
             wpos = pos;
-            const uint32_t clp = (uint32_t)meta[rr].y, chp = (uint32_t)meta[rr].z;
+            const uint32_t clp = (uint32_t)meta.y, chp = (uint32_t)meta.z;
             const uint2 yw = *reinterpret_cast<const uint2 *>(sy + rr * F420_TW);
             uint32_t h[12];
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                int U = dp4a_uu(wu[c], clp, 2048) >> 8;
-                U = clamp_u8(dp4a_us(wu[c], chp, U) >> 4);
-                int V = dp4a_uu(wv[c], clp, 2048) >> 8;
-                V = clamp_u8(dp4a_us(wv[c], chp, V) >> 4);
+                /* S + 2048 = 256*T + (L + 2048); both dot products are independent */
+                const int U = clamp_u8((dp4a_us(wu[c], chp, 0) * 256 + dp4a_uu(wu[c], clp, 2048)) >> 12);
+                const int V = clamp_u8((dp4a_us(wv[c], chp, 0) * 256 + dp4a_uu(wv[c], clp, 2048)) >> 12);
                 const int pr = ((V * crv + kr) >> 16) * cy + yb;
                 const int pb = ((U * cbu + kb) >> 16) * cy + yb;
                 const int pg = (((U * cgu) >> 16) + ((V * cgv + kg) >> 16)) * cy + yb;
@@ -268,14 +284,16 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
             o[2] = make_uint2(prmt(h[8], h[9], 0x6420), prmt(h[10], h[11], 0x6420));
         }
 
-        /* publish the tile: generic-proxy writes -> async proxy, then one TMA store */
+        /* publish this warp's 4 rows: generic-proxy writes -> async proxy, one TMA store per warp;
+         * the input slot is released at the same point (all lanes have finished reading it) */
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            tma_store_3d(&map_o, out_buf, tx * (F420_TW * 3 / 4), y0, f);
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&empty_bar[stage]);
+            tma_store_3d(&map_o, so_warp, ti.x * (F420_TW * 3 / 4), ti.y + r0, ti.z);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }
-    if (tid == 0)
+    if (lane == 0)
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }

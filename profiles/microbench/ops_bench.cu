@@ -68,6 +68,34 @@ __global__ void __launch_bounds__(1024) kmix(int *out, int b, int c, long long *
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+template <int OPA, int OPB>
+__global__ void __launch_bounds__(1024) kpair(int *out, int b, int c, long long *cycles)
+{
+    int acc[NACC];
+    for (int i = 0; i < NACC; i++) acc[i] = threadIdx.x + i;
+    __syncthreads();
+    long long t0 = clock64();
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < NACC; i += 2) { op<OPA>(acc[i], b, c); op<OPB>(acc[i + 1], b, c); }
+    }
+    long long t1 = clock64();
+    int s = 0;
+    for (int i = 0; i < NACC; i++) s ^= acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int OPA, int OPB>
+void runpair(const char *name, int *out, long long *cyc)
+{
+    kpair<OPA, OPB><<<148, 1024>>>(out, 3, 5, cyc); cudaDeviceSynchronize();
+    kpair<OPA, OPB><<<148, 1024>>>(out, 3, 5, cyc); cudaDeviceSynchronize();
+    long long h[148]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double avg = 0; for (int i = 0; i < 148; i++) avg += h[i]; avg /= 148;
+    printf("%-28s %7.3f warp-instr/clk/SM\n", name, 32.0 * ITERS * NACC / avg);
+}
+
 template <int OP>
 void run(const char *name, int *out, long long *cyc)
 {
@@ -115,5 +143,23 @@ int main()
         double avg = 0; for (int i = 0; i < 148; i++) avg += h[i]; avg /= 148;
         printf("%-28s %7.3f warp-instr/clk/SM\n", "IMAD+PRMT interleaved", 32.0 * ITERS * NACC / avg);
     }
+    runpair<0, 6>("IMAD + IDP4A", out, cyc);
+    runpair<2, 6>("PRMT + IDP4A", out, cyc);
+    runpair<0, 4>("IMAD + VIMNMX", out, cyc);
+    runpair<2, 4>("PRMT + VIMNMX", out, cyc);
+    runpair<0, 5>("IMAD + VIMNMX.S16x2", out, cyc);
+    runpair<2, 5>("PRMT + VIMNMX.S16x2", out, cyc);
+    runpair<2, 14>("PRMT + SHF", out, cyc);
+    runpair<0, 14>("IMAD + SHF", out, cyc);
+    runpair<0, 8>("IMAD + I2IP", out, cyc);
+    runpair<2, 8>("PRMT + I2IP", out, cyc);
+    runpair<0, 13>("IMAD + LOP3", out, cyc);
+    runpair<2, 13>("PRMT + LOP3", out, cyc);
+    runpair<0, 11>("IMAD + FFMA", out, cyc);
+    runpair<2, 11>("PRMT + FFMA", out, cyc);
+    runpair<6, 11>("IDP4A + FFMA", out, cyc);
+    runpair<0, 10>("IMAD + VIADDMNMX", out, cyc);
+    runpair<2, 10>("PRMT + VIADDMNMX", out, cyc);
+    runpair<0, 9>("IMAD + IMAD.HI", out, cyc);
     return 0;
 }
