@@ -183,6 +183,15 @@ def main():
         print(r.stderr[-6000:], file=sys.stderr)
         return 1
     print("built", so)
+    # the FATE input generator (tests/videogen.c): lets the suite check the reference's own
+    # golden CRCs (tests/ref/fate/filter-scalechroma, sws-yuv-range) on vsynth1
+    vg = os.path.join(OUT, "videogen")
+    r = subprocess.run(["gcc", "-O2", "-w", "-I", GEN, "-I", REF, os.path.join(REF, "tests", "videogen.c"),
+                        "-o", vg, "-lm"], capture_output=True, text=True)
+    if r.returncode != 0:
+        print(r.stderr[-3000:], file=sys.stderr)
+        return 1
+    print("built", vg)
     return 0
 
 

@@ -1,0 +1,629 @@
+"""oracle/sws_oracle.py -- CPU restatement (numpy) of the reference's legacy libswscale path.
+
+TEST INFRASTRUCTURE ONLY.  Imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline leg as a CHECKER; never by the product (librempeg_b200/).
+
+It restates, function by function, the reference algorithm for the hot path
+(hscale -> [range convert] -> vscale -> pixel pack) the way the reference
+computes it -- including the byte LUTs of yuv2rgb.c, which the product replaces
+by a closed form -- so that product and oracle share no code and no shortcuts.
+
+Pinning (tests/test_oracle_cpu.py):
+  * reference FATE golden CRCs  tests/ref/fate/filter-scalechroma (15 frames) and
+    tests/ref/fate/sws-yuv-range, on vsynth1 input made by the reference's tests/videogen.c;
+  * outputs of the real reference built by oracle/build_ref.py (oracle/_ref), live when
+    the .so is present and through the committed fixtures in tests/golden/.
+
+All file:line citations are relative to /root/reference/libswscale/.
+"""
+import math
+
+import numpy as np
+
+# ---- flags (swscale.h:131-208) ----
+SWS_FAST_BILINEAR = 1 << 0
+SWS_BILINEAR = 1 << 1
+SWS_BICUBIC = 1 << 2
+SWS_X = 1 << 3
+SWS_POINT = 1 << 4
+SWS_AREA = 1 << 5
+SWS_BICUBLIN = 1 << 6
+SWS_GAUSS = 1 << 7
+SWS_SINC = 1 << 8
+SWS_LANCZOS = 1 << 9
+SWS_SPLINE = 1 << 10
+SWS_FULL_CHR_H_INT = 1 << 13
+SWS_ACCURATE_RND = 1 << 18
+SWS_BITEXACT = 1 << 19
+BX = SWS_ACCURATE_RND | SWS_BITEXACT
+SWS_PARAM_DEFAULT = 123456
+SCALER_MASK = (SWS_POINT | SWS_AREA | SWS_BILINEAR | SWS_FAST_BILINEAR | SWS_BICUBIC | SWS_X |
+               SWS_GAUSS | SWS_LANCZOS | SWS_SINC | SWS_SPLINE | SWS_BICUBLIN)
+
+# yuv2rgb.c:47-59
+YUV2RGB_COEFFS = {
+    0: (104597, 132201, 25675, 53279), 1: (117489, 138438, 13975, 34925),
+    2: (104597, 132201, 25675, 53279), 3: (104597, 132201, 25675, 53279),
+    4: (104448, 132798, 24759, 53109), 5: (104597, 132201, 25675, 53279),
+    6: (104597, 132201, 25675, 53279), 7: (117579, 136230, 16907, 35559),
+    9: (110013, 140363, 12277, 42626), 10: (110013, 140363, 12277, 42626),
+}
+
+# swscale.c:42-52
+DITHER_8x8_128 = np.array([
+    [36, 68, 60, 92, 34, 66, 58, 90], [100, 4, 124, 28, 98, 2, 122, 26],
+    [52, 84, 44, 76, 50, 82, 42, 74], [116, 20, 108, 12, 114, 18, 106, 10],
+    [32, 64, 56, 88, 38, 70, 62, 94], [96, 0, 120, 24, 102, 6, 126, 30],
+    [48, 80, 40, 72, 54, 86, 46, 78], [112, 16, 104, 8, 118, 22, 110, 14]], np.int64)
+
+
+def _fmt(name):
+    """(kind, depth, log2_chroma_w, log2_chroma_h); kind in planar/semi/rgb8/rgb32/rgb16."""
+    if name in ("rgb24", "bgr24"):
+        return ("rgb8", 8, 0, 0)
+    if name in ("rgba", "bgra", "argb", "abgr"):
+        return ("rgb32", 8, 0, 0)
+    if name in ("rgb48le", "bgr48le"):
+        return ("rgb16", 16, 0, 0)
+    if name in ("nv12", "nv21"):
+        return ("semi", 8, 1, 1)
+    for key, (cw, ch) in {"420": (1, 1), "422": (1, 0), "444": (0, 0)}.items():
+        for pre in ("yuvj", "yuv"):
+            head = pre + key + "p"
+            if name.startswith(head):
+                rest = name[len(head):]
+                return ("planar", 8 if rest == "" else int(rest[:-2]), cw, ch)
+    raise ValueError("oracle: unsupported format " + name)
+
+
+def _cdiv_shift(a, s):
+    return -((-a) >> s)
+
+
+def _cdiv(a, b):
+    """C integer division (truncation toward zero) on Python ints."""
+    q = abs(a) // abs(b)
+    return q if (a >= 0) == (b >= 0) else -q
+
+
+def _rounded_div(a, b):
+    """ROUNDED_DIV, libavutil/common.h:58."""
+    return _cdiv(a + (b >> 1), b) if a >= 0 else _cdiv(a - (b >> 1), b)
+
+
+def _wrap32(x):
+    """Reinterpret int64 values as the int32 the C code would hold after unsigned wrap."""
+    return ((np.asarray(x, np.int64) + (1 << 31)) & 0xFFFFFFFF) - (1 << 31)
+
+
+# --------------------------------------------------------------------------- initFilter
+def _spline(a, b, c, d, dist):
+    """getSplineCoeff, utils.c:155-166."""
+    if dist <= 1.0:
+        return ((d * dist + c) * dist + b) * dist + a
+    return _spline(0.0, b + 2.0 * c + 3.0 * d, c + 3.0 * d, -b - 3.0 * c - 6.0 * d, dist - 1.0)
+
+
+def init_filter(x_inc, src_w, dst_w, one, scaler, flags, param, src_pos, dst_pos, filter_align=1):
+    """initFilter, utils.c:197-612 (srcFilter/dstFilter == NULL).  Returns (coef[dst_w][fs], pos[dst_w])
+    or None when the reference would ask for a cascade (RETCODE_USE_CASCADE)."""
+    ratio = src_w // dst_w
+    fone = 1 << (54 - min(int(math.log2(ratio | 1)), 8))
+    pos = [0] * dst_w
+
+    if abs(x_inc - 0x10000) < 10 and src_pos == dst_pos:                 # :219 unscaled
+        fs = 1
+        filt = [[fone] for _ in range(dst_w)]
+        pos = list(range(dst_w))
+    elif scaler == SWS_POINT:                                           # :229
+        fs = 1
+        x = ((dst_pos * x_inc) >> 8) - ((src_pos * 0x8000) >> 7)
+        filt = []
+        for i in range(dst_w):
+            pos[i] = (x - ((fs - 1) << 15) + (1 << 15)) >> 16
+            filt.append([fone])
+            x += x_inc
+    elif (x_inc <= (1 << 16) and scaler == SWS_AREA) or scaler == SWS_FAST_BILINEAR:   # :244
+        fs = 2
+        x = ((dst_pos * x_inc) >> 8) - ((src_pos * 0x8000) >> 7)
+        filt = []
+        for i in range(dst_w):
+            xx = (x - ((fs - 1) << 15) + (1 << 15)) >> 16
+            pos[i] = xx
+            row = []
+            for j in range(fs):
+                c = fone - abs(xx * (1 << 16) - x) * (fone >> 16)
+                row.append(max(c, 0))
+                xx += 1
+            filt.append(row)
+            x += x_inc
+    else:                                                               # :268 general
+        size_factor = {SWS_AREA: 1, SWS_BICUBIC: 4, SWS_BILINEAR: 2, SWS_GAUSS: 8, SWS_SINC: 20,
+                       SWS_SPLINE: 20, SWS_X: 8}.get(scaler, -1)
+        if scaler == SWS_LANCZOS:
+            size_factor = int(math.ceil(2 * param[0])) if param[0] != SWS_PARAM_DEFAULT else 6
+        assert 0 < size_factor <= 50
+        if x_inc <= 1 << 16:
+            fs = 1 + size_factor
+        else:
+            fs = 1 + (size_factor * src_w + dst_w - 1) // dst_w
+        fs = max(min(fs, src_w - 2), 1)
+        x = ((dst_pos * x_inc) >> 7) - ((src_pos * 0x10000) >> 7)
+        filt = []
+        for i in range(dst_w):
+            xx = _cdiv(x - (fs - 2) * (1 << 16), 1 << 17)
+            pos[i] = xx
+            row = []
+            for j in range(fs):
+                d = abs((xx * (1 << 17)) - x) << 13
+                if x_inc > 1 << 16:
+                    d = _cdiv(d * dst_w, src_w)
+                fd = d * (1.0 / (1 << 30))
+                if scaler == SWS_BICUBIC:
+                    B = int((param[0] if param[0] != SWS_PARAM_DEFAULT else 0) * (1 << 24))
+                    C = int((param[1] if param[1] != SWS_PARAM_DEFAULT else 0.6) * (1 << 24))
+                    if d >= 1 << 31:
+                        coeff = 0
+                    else:
+                        dd = (d * d) >> 30
+                        ddd = (dd * d) >> 30
+                        if d < 1 << 30:
+                            coeff = ((12 * (1 << 24) - 9 * B - 6 * C) * ddd +
+                                     (-18 * (1 << 24) + 12 * B + 6 * C) * dd +
+                                     (6 * (1 << 24) - 2 * B) * (1 << 30))
+                        else:
+                            coeff = ((-B - 6 * C) * ddd + (6 * B + 30 * C) * dd +
+                                     (-12 * B - 48 * C) * d + (8 * B + 24 * C) * (1 << 30))
+                    coeff = _cdiv(coeff, (1 << 54) // fone)
+                elif scaler == SWS_X:
+                    A = param[0] if param[0] != SWS_PARAM_DEFAULT else 1.0
+                    c = math.cos(fd * math.pi) if fd < 1.0 else -1.0
+                    c = -math.pow(-c, A) if c < 0.0 else math.pow(c, A)
+                    coeff = int((c * 0.5 + 0.5) * fone)
+                elif scaler == SWS_AREA:
+                    d2 = d - (1 << 29)
+                    if d2 * x_inc < -(1 << (29 + 16)):
+                        coeff = 1 << (30 + 16)
+                    elif d2 * x_inc < (1 << (29 + 16)):
+                        coeff = -d2 * x_inc + (1 << (29 + 16))
+                    else:
+                        coeff = 0
+                    coeff *= fone >> (30 + 16)
+                elif scaler == SWS_GAUSS:
+                    p = param[0] if param[0] != SWS_PARAM_DEFAULT else 3.0
+                    coeff = int(math.pow(2.0, -p * fd * fd) * fone)
+                elif scaler == SWS_SINC:
+                    coeff = int((math.sin(fd * math.pi) / (fd * math.pi) if d else 1.0) * fone)
+                elif scaler == SWS_LANCZOS:
+                    p = param[0] if param[0] != SWS_PARAM_DEFAULT else 3.0
+                    coeff = int((math.sin(fd * math.pi) * math.sin(fd * math.pi / p) /
+                                 (fd * fd * math.pi * math.pi / p) if d else 1.0) * fone)
+                    if fd > p:
+                        coeff = 0
+                elif scaler == SWS_BILINEAR:
+                    coeff = max((1 << 30) - d, 0) * (fone >> 30)
+                elif scaler == SWS_SPLINE:
+                    p = -2.196152422706632
+                    coeff = int(_spline(1.0, 0.0, p, -p - 1.0, fd) * fone)
+                else:
+                    raise AssertionError("bad scaler")
+                row.append(coeff)
+                xx += 1
+            filt.append(row)
+            x += 2 * x_inc
+
+    # :417-457 reduce: shift near-zero taps out on the left, count them on the right
+    f2 = fs
+    cutoff = 0.002 * fone
+    min_fs = 0
+    for i in range(dst_w - 1, -1, -1):
+        row = filt[i]
+        acc = 0
+        for _ in range(f2):
+            acc += abs(row[0])
+            if acc > cutoff:
+                break
+            if i < dst_w - 1 and pos[i] >= pos[i + 1]:
+                break
+            row.pop(0)
+            row.append(0)
+            pos[i] += 1
+        acc = 0
+        keep = f2
+        for j in range(f2 - 1, 0, -1):
+            acc += abs(row[j])
+            if acc > cutoff:
+                break
+            keep -= 1
+        min_fs = max(min_fs, keep)
+    assert min_fs > 0
+    fs = (min_fs + (filter_align - 1)) & ~(filter_align - 1)
+    if fs >= 256 * 16 // 16:                                            # :492 (generic APCK_SIZE == 16)
+        return None
+    # :504-515 copy/truncate, zero the alignment padding under BITEXACT
+    out = []
+    for i in range(dst_w):
+        row = [(filt[i][j] if j < f2 else 0) for j in range(fs)]
+        if flags & SWS_BITEXACT:
+            for j in range(min_fs, fs):
+                row[j] = 0
+        out.append(row)
+    # :520-560 fold taps outside the image onto the border
+    for i in range(dst_w):
+        row = out[i]
+        if pos[i] < 0:
+            for j in range(1, fs):
+                left = max(j + pos[i], 0)
+                row[left] += row[j]
+                row[j] = 0
+            pos[i] = 0
+        if pos[i] + fs > src_w:
+            shift = pos[i] + min(fs - src_w, 0)
+            acc = 0
+            for j in range(fs - 1, -1, -1):
+                if pos[i] + j >= src_w:
+                    acc += row[j]
+                    row[j] = 0
+            for j in range(fs - 1, -1, -1):
+                row[j] = 0 if j < shift else row[j - shift]
+            pos[i] -= shift
+            row[src_w - 1 - pos[i]] += acc
+        assert 0 <= pos[i] < src_w
+    # :569-588 normalise with error diffusion
+    coef = np.zeros((dst_w, fs), np.int16)
+    for i in range(dst_w):
+        total = sum(out[i])
+        total = _cdiv(total + one // 2, one)
+        if not total:
+            total = 1
+        err = 0
+        for j in range(fs):
+            v = out[i][j] + err
+            iv = _rounded_div(v, total)
+            coef[i, j] = iv
+            err = v - iv * total
+    return coef, np.array(pos, np.int32)
+
+
+# --------------------------------------------------------------------------- yuv2rgb tables
+def _round_i16(f):
+    """roundToInt16, yuv2rgb.c:705-715 (as the int16_t the caller stores)."""
+    r = (f + (1 << 15)) >> 16
+    if r < -0x7FFF:
+        return -0x8000
+    if r > 0x7FFF:
+        return 0x7FFF
+    return r
+
+
+def yuv2rgb_tables(inv_table, full_range, brightness, contrast, saturation):
+    """ff_yuv2rgb_c_init_tables for bpp 24/48 (yuv2rgb.c:717-914) + fill_table/fill_gv_table (:680-703).
+    Returns dict with the byte LUT, the four index tables and the six 16-bit path coefficients."""
+    crv, cbu, cgu, cgv = inv_table[0], inv_table[1], -inv_table[2], -inv_table[3]
+    cy, oy = 1 << 16, 0
+    if not full_range:
+        cy = (cy * 255) // 219
+        oy = 16 << 16
+    else:
+        crv = _cdiv(crv * 224, 255); cbu = _cdiv(cbu * 224, 255)
+        cgu = _cdiv(cgu * 224, 255); cgv = _cdiv(cgv * 224, 255)
+    cy = (cy * contrast) >> 16
+    crv = (crv * contrast * saturation) >> 32
+    cbu = (cbu * contrast * saturation) >> 32
+    cgu = (cgu * contrast * saturation) >> 32
+    cgv = (cgv * contrast * saturation) >> 32
+    oy -= 256 * brightness
+    t = {"y_coeff": _round_i16(cy * (1 << 13)), "y_offset": _round_i16(oy * (1 << 9)),
+         "v2r": _round_i16(crv * (1 << 13)), "v2g": _round_i16(cgv * (1 << 13)),
+         "u2g": _round_i16(cgu * (1 << 13)), "u2b": _round_i16(cbu * (1 << 13))}
+    div = max(cy, 1)
+    crv = _cdiv(crv * (1 << 16) + 0x8000, div); cbu = _cdiv(cbu * (1 << 16) + 0x8000, div)
+    cgu = _cdiv(cgu * (1 << 16) + 0x8000, div); cgv = _cdiv(cgv * (1 << 16) + 0x8000, div)
+    headroom = 512
+    yoffs = (384 if full_range else 326) + headroom
+    size = 1024 + 2 * headroom
+    y_table = np.zeros(size, np.uint8)
+    yb = -(384 << 16) - headroom * cy - oy
+    for i in range(size):
+        y_table[i] = min(max((yb + 0x8000) >> 16, 0), 255)
+        yb += cy
+
+    def fill(inc, base):                       # fill_table: pointer into y_table -> index
+        start = base - (inc >> 9)
+        return np.array([start + ((min(max(i - 512, 0), 255) * inc) >> 16) for i in range(1280)], np.int64)
+
+    t["y_table"] = y_table
+    t["rV"] = fill(crv, yoffs)
+    t["gU"] = fill(cgu, yoffs)
+    t["bU"] = fill(cbu, yoffs)
+    off = -(cgv >> 9)                          # fill_gv_table
+    t["gV"] = np.array([off + ((min(max(i - 512, 0), 255) * cgv) >> 16) for i in range(1280)], np.int64)
+    return t
+
+
+# --------------------------------------------------------------------------- the context
+class OracleContext:
+    """Geometry and path selection of ff_sws_init_single_context (utils.c:1137-1835) for the
+    formats the hot path covers, then whole-frame conversion with the per-line kernels of
+    swscale.c / output.c restated on numpy arrays."""
+
+    def __init__(self, sw, sh, sfmt, dw, dh, dfmt, flags, param=None, src_range=0, dst_range=0,
+                 chr_pos=(-513, -513, -513, -513), dither=1, colorspace=None):
+        self.sw, self.sh, self.dw, self.dh = sw, sh, dw, dh
+        param = list(param) if param is not None else [SWS_PARAM_DEFAULT, SWS_PARAM_DEFAULT]
+        if sfmt.startswith("yuvj"):                                   # handle_jpeg, utils.c:773
+            sfmt, src_range = "yuv" + sfmt[4:], 1
+        if dfmt.startswith("yuvj"):
+            dfmt, dst_range = "yuv" + dfmt[4:], 1
+        self.sfmt, self.dfmt = sfmt, dfmt
+        self.skind, self.sdepth, shs, svs = _fmt(sfmt)
+        self.dkind, self.ddepth, dhs, dvs = _fmt(dfmt)
+        dst_rgb = self.dkind.startswith("rgb")
+        self.src_range, self.dst_range = src_range, (0 if dst_rgb else dst_range)
+        scaler = flags & SCALER_MASK
+        if not scaler:                                                # :1209
+            scaler = SWS_BICUBIC
+            flags |= scaler
+        assert scaler & (scaler - 1) == 0 and scaler != SWS_FAST_BILINEAR
+        lum_scaler = SWS_BICUBIC if scaler == SWS_BICUBLIN else scaler
+        chr_scaler = SWS_BILINEAR if scaler == SWS_BICUBLIN else scaler
+        unscaled = sw == dw and sh == dh
+        if dst_rgb and not (flags & SWS_FULL_CHR_H_INT):              # :1270-1286
+            if dw & 1 or (shs == 0 and svs == 0 and dither != 2):
+                flags |= SWS_FULL_CHR_H_INT
+        if dst_rgb and not (flags & SWS_FULL_CHR_H_INT):              # :1359
+            dhs = 1
+        self.flags = flags
+        self.shs, self.svs, self.dhs, self.dvs = shs, svs, dhs, dvs
+        self.csw, self.csh = _cdiv_shift(sw, shs), _cdiv_shift(sh, svs)
+        self.cdw, self.cdh = _cdiv_shift(dw, dhs), _cdiv_shift(dh, dvs)
+        self.src_bpc, self.dst_bpc = max(self.sdepth, 8), max(self.ddepth, 8)
+        lum_xinc = ((sw << 16) + (dw >> 1)) // dw
+        lum_yinc = ((sh << 16) + (dh >> 1)) // dh
+        chr_xinc = ((self.csw << 16) + (self.cdw >> 1)) // self.cdw
+        chr_yinc = ((self.csh << 16) + (self.cdh >> 1)) // self.cdh
+        cs = colorspace or (5, src_range, 5, dst_range, 0, 1 << 16, 1 << 16)
+        self.rgb = None
+        if dst_rgb:
+            self.rgb = yuv2rgb_tables(YUV2RGB_COEFFS[cs[0]], cs[1] if colorspace else src_range,
+                                      cs[4], cs[5], cs[6])
+            if colorspace:
+                self.src_range = cs[1]
+
+        # unscaled special converters, swscale_unscaled.c:2392-2731 (only the ones that differ)
+        self.unscaled_lut = False
+        if unscaled and (self.src_range == self.dst_range or dst_rgb):
+            if sfmt in ("yuv420p", "yuv422p") and dst_rgb and not (flags & SWS_ACCURATE_RND) \
+                    and dither in (1, 2) and not (dh & 1):
+                self.unscaled_lut = True                               # yuv2rgb_c_* (yuv2rgb.c:137-236)
+                return
+            if (not dst_rgb and self.skind in ("planar", "semi") and self.dkind in ("planar", "semi")
+                    and (shs, svs) == (dhs, dvs) and (self.skind == "semi") == (self.dkind == "semi")
+                    and self.sdepth != self.ddepth):
+                raise NotImplementedError("planarCopyWrapper depth conversion is not restated")
+        if dst_rgb and flags & SWS_FULL_CHR_H_INT:
+            raise NotImplementedError("full-chroma RGB output is not restated")
+
+        def lpos(sub, pos):                                            # get_local_pos, utils.c:168
+            if pos == -1 or pos <= -513:
+                pos = (128 << sub) - 128
+            return (pos + 128) >> sub
+
+        shp, svp, dhp, dvp = chr_pos
+        self.h_lum = init_filter(lum_xinc, sw, dw, 1 << 14, lum_scaler, flags, param, lpos(0, 0), lpos(0, 0))
+        self.h_chr = init_filter(chr_xinc, self.csw, self.cdw, 1 << 14, chr_scaler, flags, param,
+                                 lpos(shs, shp), lpos(dhs, dhp))
+        self.v_lum = init_filter(lum_yinc, sh, dh, 1 << 12, lum_scaler, flags, param, lpos(0, 0), lpos(0, 0))
+        self.v_chr = init_filter(chr_yinc, self.csh, self.cdh, 1 << 12, chr_scaler, flags, param,
+                                 lpos(svs, svp), lpos(dvs, dvp))
+        if None in (self.h_lum, self.h_chr, self.v_lum, self.v_chr):
+            raise NotImplementedError("cascaded contexts are not restated")
+
+    # ---- stage 0: planes as integer sample arrays (input.c:926-941 for nv12/nv21)
+    def _unpack(self, planes):
+        dt = np.uint8 if self.sdepth == 8 else np.dtype("<u2")
+        lum = np.ascontiguousarray(planes[0]).view(dt)[:self.sh, :self.sw].astype(np.int64)
+        if self.skind == "semi":
+            uv = np.ascontiguousarray(planes[1]).view(dt)[:self.csh, :2 * self.csw].astype(np.int64)
+            a, b = uv[:, 0::2], uv[:, 1::2]
+            u, v = (a, b) if self.sfmt == "nv12" else (b, a)
+        else:
+            u = np.ascontiguousarray(planes[1]).view(dt)[:self.csh, :self.csw].astype(np.int64)
+            v = np.ascontiguousarray(planes[2]).view(dt)[:self.csh, :self.csw].astype(np.int64)
+        return lum, u, v
+
+    # ---- stage H: hScale8To15_c / hScale16To15_c / hScale8To19_c / hScale16To19_c (swscale.c:69-159)
+    def _hscale(self, src, bank):
+        coef, pos = bank
+        inter19 = self.dst_bpc > 14
+        if self.src_bpc == 8:
+            sh = 3 if inter19 else 7
+        else:
+            sh = self.sdepth - 1 - 4 if inter19 else self.sdepth - 1
+        acc = np.zeros((src.shape[0], len(pos)), np.int64)
+        for j in range(coef.shape[1]):
+            idx = np.minimum(pos.astype(np.int64) + j, src.shape[1] - 1)
+            acc += src[:, idx] * coef[:, j].astype(np.int64)[None, :]
+        acc = _wrap32(acc) >> sh
+        out = np.minimum(acc, (1 << 19) - 1 if inter19 else (1 << 15) - 1)
+        return out if inter19 else out.astype(np.int16).astype(np.int64)
+
+    # ---- range conversion on the h-scaled lines (swscale.c:163-255, constants :577-624)
+    def _range(self, lum, u, v):
+        if self.src_range == self.dst_range or self.dkind.startswith("rgb"):
+            return lum, u, v
+        bd = min(self.dst_bpc, 16)
+        src_bits = 15 if bd <= 14 else 19
+        src_shift, mult_shift = src_bits - bd, (14 if bd <= 14 else 18)
+        mpeg_min, mpeg_lum, mpeg_chr, jpeg_max = 16 << (bd - 8), 235 << (bd - 8), 240 << (bd - 8), (1 << bd) - 1
+
+        def solve(smin, smax, dmin, dmax):
+            total = mult_shift + src_shift
+            coeff = _cdiv_shift(((dmax - dmin) << total) // (smax - smin), src_shift)
+            offset = (dmax << total) - (smax << src_shift) * coeff + (1 << (mult_shift - 1))
+            return coeff, offset
+
+        if self.src_range:
+            lc, lo = solve(0, jpeg_max, mpeg_min, mpeg_lum)
+            cc, co = solve(0, jpeg_max, mpeg_min, mpeg_chr)
+        else:
+            lc, lo = solve(mpeg_min, mpeg_lum, 0, jpeg_max)
+            cc, co = solve(mpeg_min, mpeg_chr, 0, jpeg_max)
+        to_jpeg = not self.src_range
+        if bd <= 14:
+            lc &= 0xFFFF; cc &= 0xFFFF
+            lo = int(_wrap32(lo)); co = int(_wrap32(co))
+
+            def conv(x, c, o):
+                y = _wrap32(x * c + o) >> 14
+                if to_jpeg:
+                    y = np.minimum(y, (1 << 15) - 1)
+                return y.astype(np.int16).astype(np.int64)
+        else:
+            def conv(x, c, o):
+                y = (x * c + o) >> 18
+                y = _wrap32(y)
+                if to_jpeg:
+                    y = np.minimum(y, (1 << 19) - 1)
+                return y
+        return conv(lum, lc, lo), conv(u, cc, co), conv(v, cc, co)
+
+    @staticmethod
+    def _vsum(lines, bank, rows=None):
+        """sum_j lines[pos[y]+j] * filter[y][j] for every output row, as 32-bit wrapped values."""
+        coef, pos = bank
+        n = len(pos) if rows is None else rows
+        acc = np.zeros((n, lines.shape[1]), np.int64)
+        for j in range(coef.shape[1]):
+            idx = np.clip(pos[:n].astype(np.int64) + j, 0, lines.shape[0] - 1)
+            acc += lines[idx] * coef[:n, j].astype(np.int64)[:, None]
+        return acc
+
+    # ---- the conversion
+    def scale(self, planes):
+        lum, u, v = self._unpack(planes)
+        if self.unscaled_lut:
+            return self._unscaled_lut(lum, u, v)
+        hl = self._hscale(lum, self.h_lum)
+        hu = self._hscale(u, self.h_chr)
+        hv = self._hscale(v, self.h_chr)
+        hl, hu, hv = self._range(hl, hu, hv)
+        if self.dkind in ("planar", "semi"):
+            return self._planar_out(hl, hu, hv)
+        if self.dkind == "rgb16":
+            return self._rgb16_out(hl, hu, hv)
+        return self._rgb8_out(hl, hu, hv)
+
+    # yuv2planeX_8_c / yuv2planeX_10_c / yuv2planeX_16_c / yuv2nv12cX_c (output.c:163-187,340-357,468-528)
+    def _planar_out(self, hl, hu, hv):
+        bits = self.ddepth
+        yl = self._vsum(hl, self.v_lum)
+        yu = self._vsum(hu, self.v_chr)
+        yv = self._vsum(hv, self.v_chr)
+
+        def dither_plane(shape, offset):
+            h, w = shape
+            if self.src_bpc > 8:                      # swscale.c:291-292,519-522
+                return DITHER_8x8_128[(np.arange(h) & 7)[:, None], ((np.arange(w) + offset) & 7)[None, :]]
+            return np.full(shape, 64, np.int64)
+
+        def out(acc, offset):
+            if bits == 8:
+                val = _wrap32(acc + (dither_plane(acc.shape, offset) << 12)) >> 19
+                return np.clip(val, 0, 255).astype(np.uint8)
+            if bits < 16:
+                shift = 11 + 16 - bits
+                val = _wrap32(acc + (1 << (shift - 1))) >> shift
+                return np.clip(val, 0, (1 << bits) - 1).astype("<u2")
+            val = _wrap32(acc + (1 << 14) - 0x40000000) >> 15
+            return (0x8000 + np.clip(val, -32768, 32767)).astype("<u2")
+
+        py, pu, pv = out(yl, 0), out(yu, 0), out(yv, 3)
+        if self.dkind == "semi":
+            uv = np.zeros((pu.shape[0], pu.shape[1] * 2), pu.dtype)
+            a, b = (pu, pv) if self.dfmt == "nv12" else (pv, pu)
+            uv[:, 0::2], uv[:, 1::2] = a, b
+            return [py.view(np.uint8), uv.view(np.uint8)]
+        return [py.view(np.uint8).reshape(py.shape[0], -1), pu.view(np.uint8).reshape(pu.shape[0], -1),
+                pv.view(np.uint8).reshape(pv.shape[0], -1)]
+
+    # yuv2rgb_X_c_template / _2_c_template + yuv2rgb_write (output.c:1662-1880); chooser vscale.c:135-169
+    def _rgb8_out(self, hl, hu, hv):
+        lcoef, _ = self.v_lum
+        ccoef, _ = self.v_chr
+        n = self.dh
+        Y = self._vsum(hl, self.v_lum)
+        U = self._vsum(hu, self.v_chr, n)
+        V = self._vsum(hv, self.v_chr, n)
+        bias = np.full((n, 1), 1 << 18, np.int64)
+        if lcoef.shape[1] == 2 and ccoef.shape[1] == 2:        # yuv2packed2: no rounding bias
+            l0, l1 = lcoef[:n, 0].astype(np.int64), lcoef[:n, 1].astype(np.int64)
+            c0, c1 = ccoef[:n, 0].astype(np.int64), ccoef[:n, 1].astype(np.int64)
+            two = (l0 + l1 == 4096) & (l1 >= 0) & (l1 <= 4096) & (c0 + c1 == 4096) & (c1 >= 0) & (c1 <= 4096)
+            bias[two, 0] = 0
+        Y = _wrap32(Y + bias) >> 19
+        U = _wrap32(U + bias) >> 19
+        V = _wrap32(V + bias) >> 19
+        return [self._write_rgb8(Y, U, V)]
+
+    def _write_rgb8(self, Y, U, V):
+        t = self.rgb
+        pairs = self.dw >> 1 if self.unscaled_lut else (self.dw + 1) >> 1
+        U, V = U[:, :pairs], V[:, :pairs]
+        r_idx = t["rV"][V + 512]
+        g_idx = t["gU"][U + 512] + t["gV"][V + 512]
+        b_idx = t["bU"][U + 512]
+        rows = Y.shape[0]
+        px = pairs * 2
+        Yp = Y[:, :px]
+        rep = lambda a: np.repeat(a, 2, axis=1)[:, :px]
+        R = t["y_table"][Yp + rep(r_idx)]
+        G = t["y_table"][Yp + rep(g_idx)]
+        B = t["y_table"][Yp + rep(b_idx)]
+        order = {"rgb24": (R, G, B), "bgr24": (B, G, R), "rgba": (R, G, B, None), "bgra": (B, G, R, None),
+                 "argb": (None, R, G, B), "abgr": (None, B, G, R),
+                 "rgb48le": (R, G, B), "bgr48le": (B, G, R)}[self.dfmt]
+        bpp = len(order) * (2 if self.dkind == "rgb16" else 1)
+        out = np.zeros((rows, self.dw * bpp), np.uint8)
+        for k, comp in enumerate(order):
+            val = np.full((rows, px), 255, np.uint8) if comp is None else comp
+            if self.dkind == "rgb16":                 # PUTRGB48 (yuv2rgb.c:107-115): byte replicated
+                out[:, 2 * k:px * bpp:bpp] = val
+                out[:, 2 * k + 1:px * bpp:bpp] = val
+            else:
+                out[:, k:px * bpp:bpp] = val
+        return out
+
+    # yuv2rgba64_X_c_template, hasAlpha=0, eightbytes=0 (output.c:1115-1196)
+    def _rgb16_out(self, hl, hu, hv):
+        t = self.rgb
+        n = self.dh
+        Y = _wrap32(self._vsum(hl, self.v_lum) - 0x40000000)
+        U = _wrap32(self._vsum(hu, self.v_chr, n) - (128 << 23))
+        V = _wrap32(self._vsum(hv, self.v_chr, n) - (128 << 23))
+        Y = (Y >> 14) + 0x10000
+        U = U >> 14
+        V = V >> 14
+        Y = _wrap32(_wrap32((Y - t["y_offset"]) * t["y_coeff"]) + (1 << 13) - (1 << 29))
+        R = _wrap32(V * t["v2r"])
+        G = _wrap32(V * t["v2g"] + U * t["u2g"])
+        B = _wrap32(U * t["u2b"])
+        pairs = (self.dw + 1) >> 1
+        rep = lambda a: np.repeat(a[:, :pairs], 2, axis=1)[:, :self.dw]
+        comp = lambda c: np.clip((_wrap32(rep(c) + Y[:, :self.dw]) >> 14) + (1 << 15), 0, 65535).astype("<u2")
+        r, g, b = comp(R), comp(G), comp(B)
+        out = np.zeros((n, self.dw * 3), "<u2")
+        a, c = (r, b) if self.dfmt == "rgb48le" else (b, r)
+        out[:, 0::3], out[:, 1::3], out[:, 2::3] = a, g, c
+        return [out.view(np.uint8).reshape(n, -1)]
+
+    # yuv2rgb_c_24_rgb & friends: nearest chroma, byte LUTs (yuv2rgb.c:68-236,520-559)
+    def _unscaled_lut(self, lum, u, v):
+        rows = np.arange(self.dh) >> self.svs
+        U = np.repeat(u[rows], 1, axis=0)
+        V = v[rows]
+        return [self._write_rgb8(lum, U, V)]
+
+
+def convert(sw, sh, sfmt, dw, dh, dfmt, flags, planes, **kw):
+    return OracleContext(sw, sh, sfmt, dw, dh, dfmt, flags, **kw).scale(planes)

@@ -1,0 +1,93 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/golden_md5.json from the REAL reference (oracle/_ref/libswsref.so,
+built from /root/reference by oracle/build_ref.py).  Run in the build container:
+
+    python tests/golden/make_golden.py
+
+Inputs are produced by tests/sws_testlib.det_values (splitmix64 of the sample index), so
+they can be regenerated bit-for-bit anywhere; only the md5 of every output plane is stored.
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from tests import sws_testlib as T  # noqa: E402
+from oracle import refapi as R      # noqa: E402
+
+BX = R.BX
+
+
+def cases():
+    out = []
+    # the five BASELINE.json configurations at full size ("large": skipped by the CPU suite)
+    out += [
+        dict(sw=640, sh=480, sf="yuv420p", dw=640, dh=480, df="rgb24", flags=R.SWS_POINT | R.SWS_BITEXACT),
+        dict(sw=640, sh=480, sf="yuv420p", dw=640, dh=480, df="rgb24", flags=R.SWS_POINT | BX),
+        dict(sw=1920, sh=1080, sf="yuv420p", dw=1920, dh=1080, df="rgb24", flags=R.SWS_BICUBIC | BX, large=1),
+        dict(sw=3840, sh=2160, sf="yuv420p10le", dw=3840, dh=2160, df="rgb48le", flags=R.SWS_LANCZOS | BX, large=1),
+        dict(sw=7680, sh=4320, sf="nv12", dw=1920, dh=1080, df="yuv420p", flags=R.SWS_BICUBIC | BX, large=1),
+        dict(sw=3840, sh=2160, sf="yuv420p", dw=3840, dh=2160, df="rgb24", flags=R.SWS_BICUBIC | BX, large=1),
+        dict(sw=3840, sh=2160, sf="yuv420p", dw=3840, dh=2160, df="rgb24", flags=R.SWS_BICUBIC, large=1),
+        dict(sw=1920, sh=1080, sf="yuv420p", dw=3840, dh=2160, df="rgb24", flags=R.SWS_BICUBIC | BX, large=1),
+    ]
+    # small cases across formats / scalers / options
+    scalers = [R.SWS_POINT, R.SWS_BILINEAR, R.SWS_BICUBIC, R.SWS_AREA, R.SWS_GAUSS, R.SWS_SINC,
+               R.SWS_LANCZOS, R.SWS_SPLINE, R.SWS_X, R.SWS_BICUBLIN]
+    for i, sc in enumerate(scalers):
+        out.append(dict(sw=352, sh=288, sf="yuv420p", dw=200, dh=100, df="yuv420p", flags=sc | BX))
+        out.append(dict(sw=176, sh=144, sf="yuv420p", dw=352, dh=288, df="rgb24", flags=sc | BX))
+    for sf in ["yuv420p", "yuv422p", "nv12", "nv21", "yuv420p10le", "yuv422p10le", "yuv420p9le",
+               "yuv420p12le", "yuv420p14le", "yuv420p16le", "yuvj420p"]:
+        for df in ["rgb24", "bgr24", "rgba", "bgra", "argb", "abgr", "rgb48le", "bgr48le", "yuv420p",
+                   "yuv422p", "yuv444p", "nv12", "nv21", "yuv420p10le", "yuv444p12le", "yuv420p16le"]:
+            out.append(dict(sw=162, sh=122, sf=sf, dw=200, dh=150, df=df, flags=R.SWS_BICUBIC | BX))
+    for sf, df in [("yuv420p", "rgb24"), ("yuv420p", "bgra"), ("yuv422p", "rgb24"), ("yuv420p", "rgb48le"),
+                   ("yuv420p", "nv12"), ("nv12", "yuv420p"), ("yuv420p10le", "rgb48le")]:
+        for fl in [R.SWS_BICUBIC, R.SWS_BICUBIC | BX, R.SWS_POINT]:
+            out.append(dict(sw=322, sh=182, sf=sf, dw=322, dh=182, df=df, flags=fl))
+    for cs in [(1, 0, 1, 0), (5, 1, 5, 0), (9, 0, 9, 0), (7, 1, 7, 1)]:
+        out.append(dict(sw=160, sh=120, sf="yuv420p", dw=160, dh=120, df="rgb24", flags=R.SWS_BICUBIC | BX,
+                        colorspace=list(cs) + [0, 1 << 16, 1 << 16]))
+    out.append(dict(sw=160, sh=120, sf="yuv420p", dw=160, dh=120, df="rgb24", flags=R.SWS_BICUBIC | BX,
+                    colorspace=[5, 0, 5, 0, 3000, 78643, 52428]))
+    for rng in [(0, 1), (1, 0)]:
+        for df in ["yuv420p", "yuv420p10le", "yuv420p16le"]:
+            out.append(dict(sw=160, sh=120, sf="yuv420p", dw=200, dh=150, df=df, flags=R.SWS_BICUBIC | BX,
+                            ctx_kwargs=dict(src_range=rng[0], dst_range=rng[1])))
+    for pos in [(0, 128, -513, -513), (0, 0, -513, -513), (128, 128, 0, 0)]:
+        out.append(dict(sw=160, sh=120, sf="yuv420p", dw=160, dh=120, df="rgb24", flags=R.SWS_BICUBIC | BX,
+                        ctx_kwargs=dict(chr_pos=list(pos))))
+        out.append(dict(sw=160, sh=120, sf="yuv420p", dw=100, dh=74, df="yuv420p", flags=R.SWS_BICUBIC | BX,
+                        ctx_kwargs=dict(chr_pos=list(pos))))
+    for (sw, sh, dw, dh) in [(16, 16, 16, 16), (18, 10, 34, 22), (1920, 2, 1920, 2), (4, 1080, 4, 1080),
+                             (130, 66, 62, 30), (34, 34, 1280, 720)]:
+        out.append(dict(sw=sw, sh=sh, sf="yuv420p", dw=dw, dh=dh, df="rgb24", flags=R.SWS_BICUBIC | BX))
+        out.append(dict(sw=sw, sh=sh, sf="yuv420p", dw=dw, dh=dh, df="yuv420p", flags=R.SWS_BICUBIC | BX))
+    for i, c in enumerate(out):
+        c.setdefault("seed", 100 + i)
+        c.setdefault("mode", "extreme" if i % 7 == 3 else "noise")
+    return out
+
+
+def main():
+    res = []
+    for c in cases():
+        kw = {k: v for k, v in c.items() if k not in ("large", "seed", "mode")}
+        if "ctx_kwargs" in kw and "chr_pos" in kw["ctx_kwargs"]:
+            kw["ctx_kwargs"] = dict(kw["ctx_kwargs"], chr_pos=tuple(kw["ctx_kwargs"]["chr_pos"]))
+        src = T.Frame(c["sf"], c["sw"], c["sh"]).randomize(c["seed"], c["mode"])
+        want, _ = T.run_reference(src=src, **kw)
+        c["md5"] = T.md5_planes(want.valid())
+        res.append(c)
+        print(c["sw"], c["sh"], c["sf"], "->", c["dw"], c["dh"], c["df"], hex(c["flags"]), c["md5"][0])
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_md5.json"), "w") as f:
+        json.dump({"generator": "tests/golden/make_golden.py", "oracle": "oracle/_ref/libswsref.so (real reference C path)",
+                   "cases": res}, f, indent=0)
+    print(len(res), "cases written")
+
+
+if __name__ == "__main__":
+    main()

@@ -51,6 +51,19 @@ def depth_of(fmt):
     return 8
 
 
+def det_values(seed, n, bits):
+    """Deterministic pseudo-random samples (splitmix64 of the index): identical on every
+    machine and numpy version, so golden md5s in tests/golden/ stay valid forever."""
+    with np.errstate(over="ignore"):
+        z = np.arange(n, dtype=np.uint64) + np.uint64((seed * 0x9E3779B97F4A7C15 + 0x1234567) & 0xFFFFFFFFFFFFFFFF)
+        z ^= z >> np.uint64(30)
+        z *= np.uint64(0xBF58476D1CE4E5B9)
+        z ^= z >> np.uint64(27)
+        z *= np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+    return (z & np.uint64((1 << bits) - 1))
+
+
 class Frame:
     """Planes as 2-D uint8 arrays [rows, stride] with row_bytes valid bytes per row."""
 
@@ -69,12 +82,12 @@ class Frame:
     def randomize(self, seed, mode="noise"):
         rng = np.random.default_rng(seed)
         d = depth_of(self.fmt)
-        for (rows, rb), a in zip(self.layout, self.planes):
+        for pi, ((rows, rb), a) in enumerate(zip(self.layout, self.planes)):
             if mode == "noise":
                 if d == 8:
-                    a[:, :rb] = rng.integers(0, 256, (rows, rb), dtype=np.uint8)
+                    a[:, :rb] = det_values(seed * 4 + pi, rows * rb, 8).astype(np.uint8).reshape(rows, rb)
                 else:
-                    v = rng.integers(0, 1 << d, (rows, rb // 2), dtype=np.uint16)
+                    v = det_values(seed * 4 + pi, rows * (rb // 2), d).astype(np.uint16).reshape(rows, rb // 2)
                     a[:, :rb] = v.view(np.uint8).reshape(rows, rb)
             elif mode == "smooth":
                 n = rb if d == 8 else rb // 2
@@ -153,6 +166,21 @@ def _subs(fmt):
         if k + "p" in fmt:
             return k
     return "444"
+
+
+def run_oracle(sw, sh, sf, dw, dh, df, flags, src, param=None, ctx_kwargs=None, colorspace=None, **_):
+    """The numpy restatement (oracle/sws_oracle.py) on the same frame; returns tight planes."""
+    from oracle import sws_oracle as O
+    kw = dict(ctx_kwargs or {})
+    c = O.OracleContext(sw, sh, sf, dw, dh, df, flags, param=param, colorspace=colorspace, **kw)
+    out = c.scale(src.valid())
+    lay = plane_layout(df, dw, dh)
+    return [np.ascontiguousarray(o).view(np.uint8).reshape(rows, -1)[:, :rb] for o, (rows, rb) in zip(out, lay)]
+
+
+def md5_planes(planes):
+    import hashlib
+    return [hashlib.md5(np.ascontiguousarray(p).tobytes()).hexdigest() for p in planes]
 
 
 def run_case_both(sw, sh, sf, dw, dh, df, flags, seed=1, mode="noise", src_pad=0, dst_pad=0, **kw):

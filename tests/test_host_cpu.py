@@ -1,0 +1,196 @@
+"""CPU suite, part 2: the host side of the product (no GPU, no compute calls).
+
+ * the C-ABI library loads and exports every symbol include/*.h declares;
+ * the host-built FIR banks and colour constants equal the oracle's (numpy restatement, and the
+   real reference when present);
+ * the closed-form RGB LUT evaluation used by the kernels equals the reference's byte LUTs;
+ * no device => context creation fails loudly (no CPU fallback); the product never touches oracle/.
+"""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests import sws_testlib as T
+from librempeg_b200 import swscale as S
+from oracle import sws_oracle as O
+from oracle import refapi as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = set()
+    for h in os.listdir(os.path.join(ROOT, "include")):
+        txt = open(os.path.join(ROOT, "include", h)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        for m in re.finditer(r"\b((?:sws|swscale)_[A-Za-z0-9_]+)\s*\(", txt):
+            names.add(m.group(1))
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(S.SO_PATH, mode=os.RTLD_LOCAL)
+    decl = _declared_symbols()
+    assert len(decl) >= 30
+    missing = [n for n in decl if not hasattr(lib, n)]
+    assert not missing, "declared in include/*.h but not exported: %s" % missing
+
+
+def test_public_struct_layout_matches_reference_abi():
+    """Field order of the public SwsContext is ABI (reference swscale.h:222-315)."""
+    c = S.lib().sws_alloc_context()
+    s = c.contents
+    assert s.flags == S.SWS_BICUBIC and s.threads == 1 and s.dither == 1
+    assert s.scaler_params[0] == 123456 and s.src_h_chr_pos == -513 and s.dst_v_chr_pos == -513
+    assert (s.src_w, s.src_h, s.dst_w, s.dst_h) == (16, 16, 16, 16) and s.intent == 1
+    S.lib().sws_freeContext(c)
+    assert ctypes.sizeof(S.SwsContextStruct) == 120
+    assert S.SwsContextStruct.src_w.offset == 56 and S.SwsContextStruct.backends.offset == 116
+
+
+def test_version_and_queries():
+    L = S.lib()
+    L.swscale_version.restype = ctypes.c_uint
+    assert L.swscale_version() >> 16 == 10          # LIBSWSCALE_VERSION_MAJOR, version_major.h:27
+    assert L.sws_isSupportedInput(S.PIX_FMT["yuv420p"]) and L.sws_isSupportedOutput(S.PIX_FMT["rgb24"])
+    assert not L.sws_isSupportedInput(S.PIX_FMT["rgb24"])    # RGB input is a "next" row
+    assert not L.sws_isSupportedOutput(9999)
+    co = L.sws_getCoefficients(1)
+    assert [co[i] for i in range(4)] == [117489, 138438, 13975, 34925]
+    assert [L.sws_getCoefficients(8)[i] for i in range(4)] == [104597, 132201, 25675, 53279]
+
+
+GEOMS = [
+    (640, 480, "yuv420p", 640, 480, "rgb24", S.SWS_POINT | S.BX),
+    (1920, 1080, "yuv420p", 1920, 1080, "rgb24", S.SWS_BICUBIC | S.BX),
+    (3840, 2160, "yuv420p10le", 3840, 2160, "rgb48le", S.SWS_LANCZOS | S.BX),
+    (7680, 4320, "nv12", 1920, 1080, "yuv420p", S.SWS_BICUBIC | S.BX),
+    (1920, 1080, "yuv420p", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
+    (1280, 720, "yuv420p", 854, 480, "yuv420p", S.SWS_LANCZOS | S.BX),
+    (1280, 720, "yuv420p", 1000, 700, "yuv420p", S.SWS_SPLINE | S.BX),
+    (1280, 720, "yuv420p", 333, 211, "yuv420p", S.SWS_GAUSS | S.BX),
+    (1280, 720, "yuv420p", 1921, 1081, "yuv420p", S.SWS_SINC | S.BX),
+    (1280, 720, "yuv420p", 640, 360, "yuv420p", S.SWS_AREA | S.BX),
+    (640, 360, "yuv420p", 1280, 720, "yuv420p", S.SWS_AREA | S.BX),
+    (640, 360, "yuv420p", 1280, 720, "rgb24", S.SWS_BILINEAR),
+    (640, 360, "yuv420p", 1280, 720, "yuv420p", S.SWS_X | S.BX),
+    (640, 360, "yuv420p", 17, 9, "yuv420p", S.SWS_BICUBIC | S.BX),
+    (64, 36, "yuv420p", 1280, 720, "yuv420p", S.SWS_BICUBLIN),
+    (640, 360, "yuv422p", 1280, 720, "yuv444p", S.SWS_POINT),
+    (640, 360, "yuv420p", 640, 360, "rgb24", S.SWS_BICUBIC),
+]
+
+
+@pytest.mark.parametrize("g", GEOMS, ids=lambda g: "%dx%d_%s_%dx%d_%s_%x" % g)
+def test_host_fir_banks_match_oracle(g):
+    """ff_b200_build_fir (sws_filter.c) vs initFilter restated in numpy vs the real reference."""
+    sw, sh, sf, dw, dh, df, fl = g
+    mine = S.SwsContext(sw, sh, sf, dw, dh, df, fl, plan_only=True)
+    info = mine.info()
+    orc = O.OracleContext(sw, sh, sf, dw, dh, df, fl)
+    assert bool(info["unscaled"]) == orc.unscaled_lut
+    ref = R.RefContext(sw, sh, sf, dw, dh, df, fl) if R.available() else None
+    if ref:
+        ri = ref.info()
+        for k in ("y_offset", "y_coeff", "v2r", "v2g", "u2g", "u2b", "unscaled", "chrSrcW", "chrSrcH",
+                  "chrDstW", "chrDstH", "srcBpc", "dstBpc"):
+            assert ri[k] == info[k], k
+    if orc.unscaled_lut:
+        return
+    for which, bank in enumerate((orc.h_lum, orc.h_chr, orc.v_lum, orc.v_chr)):
+        co, po = mine.filter(which)
+        assert np.array_equal(co, bank[0]) and np.array_equal(po, bank[1]), "bank %d vs numpy oracle" % which
+        if ref:
+            rc, rp = ref.filter(which)
+            assert np.array_equal(co, rc) and np.array_equal(po, rp), "bank %d vs reference" % which
+
+
+@pytest.mark.parametrize("cs", [(5, 0, 0, 1 << 16, 1 << 16), (1, 0, 0, 1 << 16, 1 << 16), (5, 1, 0, 1 << 16, 1 << 16),
+                                (9, 1, 0, 1 << 16, 1 << 16), (7, 0, 0, 1 << 16, 1 << 16),
+                                (5, 0, 3000, 78643, 52428), (1, 1, -2000, 60000, 70000)])
+def test_rgb_closed_form_equals_reference_luts(cs):
+    """The kernels evaluate r = clip_u8((yb + (Y + base_r + ((V8*crv)>>16))*cy) >> 16) instead of reading
+    y_table[...] through table_rV (yuv2rgb.c:680-703,901-914).  Check every (Y, U8, V8) the LUT index can see."""
+    csp, full, br, co, sa = cs
+    mine = S.SwsContext(64, 64, "yuv420p", 64, 64, "rgb24", S.SWS_BICUBIC | S.BX, plan_only=True)
+    assert mine.set_colorspace(csp, full, csp, 0, br, co, sa) == 0
+    mine.close()
+    # plan_only contexts apply the colourspace at (re)planning time
+    mine = S.SwsContext(64, 64, "yuv420p", 64, 64, "rgb24", S.SWS_BICUBIC | S.BX, plan_only=True,
+                        src_range=full)
+    L = S.lib()
+    L.sws_setColorspaceDetails(mine.p, L.sws_getCoefficients(csp), full, L.sws_getCoefficients(csp), 0, br, co, sa)
+    assert L.sws_b200_plan_only(mine.p) == 0
+    k = mine.info()
+    t = O.yuv2rgb_tables(O.YUV2RGB_COEFFS[csp], full, br, co, sa)
+    for key in ("y_offset", "y_coeff", "v2r", "v2g", "u2g", "u2b"):
+        assert k[key] == t[key], key
+    Y = np.arange(-40, 300, dtype=np.int64)[:, None]
+    C8 = np.arange(256, dtype=np.int64)[None, :]
+
+    def closed(idx):
+        return np.clip((k["yb"] + idx * k["cy"]) >> 16, 0, 255)
+
+    r = closed(Y + k["base_r"] + ((C8 * k["crv"]) >> 16))
+    b = closed(Y + k["base_b"] + ((C8 * k["cbu"]) >> 16))
+    assert np.array_equal(r, t["y_table"][Y + t["rV"][C8 + 512]])
+    assert np.array_equal(b, t["y_table"][Y + t["bU"][C8 + 512]])
+    for u8 in range(0, 256, 5):
+        g = closed(Y + k["base_g"] + ((u8 * k["cgu"]) >> 16) + ((C8 * k["cgv"]) >> 16))
+        assert np.array_equal(g, t["y_table"][Y + t["gU"][u8 + 512] + t["gV"][C8 + 512]])
+    if R.available():
+        ref = R.RefContext(64, 64, "yuv420p", 64, 64, "rgb24", S.SWS_BICUBIC | S.BX, src_range=full)
+        ref.set_colorspace(csp, full, csp, 0, br, co, sa)
+        y_table, rV, gU, bU, gV = ref.rgb_tables()
+        assert np.array_equal(y_table, t["y_table"])
+        assert np.array_equal(rV, t["rV"]) and np.array_equal(gU, t["gU"])
+        assert np.array_equal(bU, t["bU"]) and np.array_equal(gV, t["gV"])
+
+
+def test_no_device_means_loud_failure_not_cpu_fallback():
+    """On a machine without CUDA, sws_init_context must fail; nothing converts on the CPU."""
+    if S.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(RuntimeError):
+        S.SwsContext(64, 64, "yuv420p", 64, 64, "rgb24", S.SWS_BICUBIC)
+    L = S.lib()
+    assert not L.sws_getContext(64, 64, 0, 64, 64, 2, S.SWS_BICUBIC, None, None, None)
+
+
+def test_init_rejects_what_the_hot_path_does_not_cover():
+    for kw in (dict(src_fmt="yuv420p", dst_fmt="rgb24", flags=S.SWS_FAST_BILINEAR),
+               dict(src_fmt="yuv420p", dst_fmt="rgb24", flags=S.SWS_BICUBIC | S.SWS_BILINEAR),
+               dict(src_fmt="yuv444p", dst_fmt="rgb24", flags=S.SWS_BICUBIC | S.BX)):
+        with pytest.raises(RuntimeError):
+            S.SwsContext(64, 64, kw["src_fmt"], 64, 64, kw["dst_fmt"], kw["flags"], plan_only=True)
+    with pytest.raises(RuntimeError):
+        S.SwsContext(0, 64, "yuv420p", 64, 64, "rgb24", S.SWS_BICUBIC, plan_only=True)
+    with pytest.raises(RuntimeError):   # odd width forces the (not yet covered) full-chroma path
+        S.SwsContext(64, 64, "yuv420p", 65, 64, "rgb24", S.SWS_BICUBIC | S.BX, plan_only=True)
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under librempeg_b200/ may import, link or mention it."""
+    bad = []
+    for dp, _, files in os.walk(os.path.join(ROOT, "librempeg_b200")):
+        for f in files:
+            if f.endswith((".py", ".c", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                if re.search(r"\boracle\b|libswsref|refapi", txt):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad
+    out = os.popen("ldd %s" % S.SO_PATH).read()
+    assert "swsref" not in out and "avutil" not in out
+
+
+def test_partition_round_robin():
+    from librempeg_b200 import partition as P
+    assert P.frames_for_rank(512, 3, 8) == list(range(3, 512, 8))
+    assert sum(P.frames_per_rank(513, 8)) == 513 and P.frames_per_rank(512, 8) == [64] * 8
+    allf = sorted(sum((P.frames_for_rank(37, r, 4) for r in range(4)), []))
+    assert allf == list(range(37))
+    with pytest.raises(ValueError):
+        P.frames_for_rank(8, 8, 8)
