@@ -158,7 +158,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.002)
 
     def summary(self):
         s = sorted(self.samples)
