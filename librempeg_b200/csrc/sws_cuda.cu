@@ -21,6 +21,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <errno.h>
 
 #include "sws_internal.h"
@@ -426,6 +427,9 @@ struct SwsCudaState {
     const char *kernel_name;
     /* fast420 path */
     int fast_ok;
+    int e2e_mode, e2e_bands; /* how sws_scale() moves page-locked host frames (see scale_host)  */
+    cudaStream_t s_in, s_out;
+    cudaEvent_t ev_in[16], ev_k[16];
     int4 *d_fast_rows;
     int num_sms;
     int tile_w, tile_h, rows_l_cap, rows_c_cap;
@@ -611,6 +615,13 @@ static int fast420_setup(SwsCudaState *st, const SwsFirBank *vc)
     CUDA_OK(cudaFuncSetAttribute((const void *)sws_fast420_rgb8_kernel<true>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, F420_SMEM));
     st->fast_ok = 1;
+    {
+        const char *e = getenv("SWS_B200_E2E_MODE"), *b = getenv("SWS_B200_E2E_BANDS");
+        st->e2e_mode = e ? atoi(e) : 3;
+        st->e2e_bands = b ? atoi(b) : 4;
+        if (st->e2e_bands < 1) st->e2e_bands = 1;
+        if (st->e2e_bands > 16) st->e2e_bands = 16;
+    }
     st->kernel_name = "fast420_rgb8_tma";
     return 0;
 }
@@ -620,10 +631,11 @@ static bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 /* returns 1 if launched, 0 if the arguments do not qualify (caller falls back to the generic kernel) */
 static int fast420_launch(SwsCudaState *st, const uint8_t *const src[4], const int src_stride[4],
                           const int64_t src_fstride[4], uint8_t *const dst[4], const int dst_stride[4],
-                          const int64_t dst_fstride[4], int nb_frames, int y0, int y1)
+                          const int64_t dst_fstride[4], int nb_frames, int y0, int y1, cudaStream_t stream)
 {
     const SwsCudaPlan *p = &st->plan;
-    if (!st->fast_ok || y0 != 0 || y1 != p->dst_h)
+    /* row ranges must start on a tile row; the end is clipped by the store tensor map */
+    if (!st->fast_ok || (y0 % F420_TH) || y1 <= y0 || y1 > p->dst_h)
         return 0;
     for (int i = 0; i < 3; i++)
         if (!aligned16(src[i]) || (src_stride[i] & 15) || src_stride[i] <= 0 ||
@@ -644,12 +656,13 @@ static int fast420_launch(SwsCudaState *st, const uint8_t *const src[4], const i
                            src_stride[1], fs_u, F420_TW / 2, F420_CROWS)) < 0 ||
         (ret = make_map_3d(&mv, CU_TENSOR_MAP_DATA_TYPE_UINT8, src[2], p->chr_src_w, p->chr_src_h, nb_frames,
                            src_stride[2], fs_v, F420_TW / 2, F420_CROWS)) < 0 ||
-        (ret = make_map_3d(&mo, CU_TENSOR_MAP_DATA_TYPE_UINT32, dst[0], (uint64_t)p->dst_w * 3 / 4, p->dst_h,
+        (ret = make_map_3d(&mo, CU_TENSOR_MAP_DATA_TYPE_UINT32, dst[0], (uint64_t)p->dst_w * 3 / 4, y1,
                            nb_frames, dst_stride[0], fs_o, F420_TW * 3 / 4, F420_TH / F420_CWARPS)) < 0)
         return ret;
     Fast420Args a;
     a.tiles_x = (p->dst_w + F420_TW - 1) / F420_TW;
-    a.tiles_y = (p->dst_h + F420_TH - 1) / F420_TH;
+    a.tiles_y = (y1 - y0 + F420_TH - 1) / F420_TH;
+    a.ty_first = y0 / F420_TH;
     a.frames = nb_frames;
     a.dst_h = p->dst_h;
     a.bgr = p->dst_kind == SWSC_DST_BGR24;
@@ -660,9 +673,9 @@ static int fast420_launch(SwsCudaState *st, const uint8_t *const src[4], const i
     const long long total = (long long)a.tiles_x * a.tiles_y * nb_frames;
     const int grid = (int)(total < (long long)st->num_sms * 4 ? total : (long long)st->num_sms * 4);
     if (a.bgr)
-        sws_fast420_rgb8_kernel<true><<<grid, F420_THREADS, F420_SMEM, st->stream>>>(my, mu, mv, mo, a);
+        sws_fast420_rgb8_kernel<true><<<grid, F420_THREADS, F420_SMEM, stream>>>(my, mu, mv, mo, a);
     else
-        sws_fast420_rgb8_kernel<false><<<grid, F420_THREADS, F420_SMEM, st->stream>>>(my, mu, mv, mo, a);
+        sws_fast420_rgb8_kernel<false><<<grid, F420_THREADS, F420_SMEM, stream>>>(my, mu, mv, mo, a);
     CUDA_OK(cudaGetLastError());
     st->launches++;
     return 1;
@@ -749,6 +762,14 @@ extern "C" void ff_b200_cuda_destroy(SwsCudaState *st)
     }
     cudaFree(st->tables);
     cudaFree(st->d_fast_rows);
+    if (st->s_in) {
+        cudaStreamDestroy(st->s_in);
+        cudaStreamDestroy(st->s_out);
+        for (int k = 0; k < 16; k++) {
+            cudaEventDestroy(st->ev_in[k]);
+            cudaEventDestroy(st->ev_k[k]);
+        }
+    }
     for (int i = 0; i < 4; i++) {
         cudaFree(st->d_src[i]);
         cudaFree(st->d_dst[i]);
@@ -781,7 +802,7 @@ extern "C" int ff_b200_cuda_launch(SwsCudaState *st,
     if (cudaGetDevice(&cur) == cudaSuccess && cur != st->device)
         CUDA_OK(cudaSetDevice(st->device));
     {
-        int r = fast420_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1);
+        int r = fast420_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);
         if (r != 0)
             return r < 0 ? r : 0;
     }
@@ -838,14 +859,101 @@ static int ensure_staging(SwsCudaState *st)
     st->dst_rows[0] = p->dst_h;
     for (int i = 0; i < 4; i++) {
         if (st->src_rows[i]) {
-            st->d_src_stride[i] = (st->src_rowbytes[i] + 255) & ~255;
+            st->d_src_stride[i] = (st->src_rowbytes[i] + 15) & ~15;
             CUDA_OK(cudaMalloc(&st->d_src[i], (size_t)st->d_src_stride[i] * st->src_rows[i]));
         }
         if (st->dst_rows[i]) {
-            st->d_dst_stride[i] = (st->dst_rowbytes[i] + 255) & ~255;
+            st->d_dst_stride[i] = (st->dst_rowbytes[i] + 15) & ~15;
             CUDA_OK(cudaMalloc(&st->d_dst[i], (size_t)st->d_dst_stride[i] * st->dst_rows[i]));
         }
     }
+    return 0;
+}
+
+
+
+/* rows x rowbytes copy; one contiguous DMA when both pitches equal the row size */
+static cudaError_t copy_rows_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t rowbytes,
+                                   size_t rows, cudaMemcpyKind kind, cudaStream_t s)
+{
+    if (dpitch == rowbytes && spitch == rowbytes)
+        return cudaMemcpyAsync(dst, src, rowbytes * rows, kind, s);
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, rowbytes, rows, kind, s);
+}
+
+/* One synchronous host-frame conversion as a pipeline of row bands:
+ *   stream s_in : H2D of band k+1        (copy engine)
+ *   st->stream  : kernel on band k       (SMs)
+ *   stream s_out: D2H of band k-1        (second copy engine)   [or the kernel stores to the host frame]
+ * PCIe is full duplex, so the frame costs ~max(H2D, D2H) instead of their sum.
+ * Returns 0 when done, 1 if the caller should fall back to the serial path, <0 on error. */
+#define E2E_MAX_BANDS 16
+static int pipelined_host_frame(SwsCudaState *st, const uint8_t *const src[4], const int src_stride[4],
+                                uint8_t *const dst[4], const int dst_stride[4], uint8_t *const ddst[4],
+                                bool store_to_host)
+{
+    const SwsCudaPlan *p = &st->plan;
+    int ret = ensure_staging(st);
+    if (ret < 0)
+        return ret;
+    if (!st->s_in) {
+        CUDA_OK(cudaStreamCreateWithFlags(&st->s_in, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&st->s_out, cudaStreamNonBlocking));
+        for (int k = 0; k < E2E_MAX_BANDS; k++) {
+            CUDA_OK(cudaEventCreateWithFlags(&st->ev_in[k], cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&st->ev_k[k], cudaEventDisableTiming));
+        }
+    }
+    int bands = st->e2e_bands;
+    int band_h = ((p->dst_h + bands - 1) / bands + F420_TH - 1) / F420_TH * F420_TH;
+    if (band_h < F420_TH)
+        band_h = F420_TH;
+    int64_t zero[4] = { 0, 0, 0, 0 };
+    int cup = 0;                                   /* chroma source rows uploaded so far */
+    int k = 0;
+    for (int y0 = 0; y0 < p->dst_h; y0 += band_h, k++) {
+        const int y1 = y0 + band_h < p->dst_h ? y0 + band_h : p->dst_h;
+        /* identity luma: source rows == destination rows */
+        CUDA_OK(copy_rows_async(st->d_src[0] + (size_t)y0 * st->d_src_stride[0], st->d_src_stride[0],
+                                  src[0] + (size_t)y0 * src_stride[0], src_stride[0], st->src_rowbytes[0],
+                                  y1 - y0, cudaMemcpyHostToDevice, st->s_in));
+        int chi = y1 == p->dst_h ? p->chr_src_h : st->h_vc_pos[y1 - 1] + 4;
+        if (chi > p->chr_src_h)
+            chi = p->chr_src_h;
+        if (chi > cup) {
+            for (int i = 1; i < 3; i++)
+                CUDA_OK(copy_rows_async(st->d_src[i] + (size_t)cup * st->d_src_stride[i], st->d_src_stride[i],
+                                          src[i] + (size_t)cup * src_stride[i], src_stride[i],
+                                          st->src_rowbytes[i], chi - cup, cudaMemcpyHostToDevice, st->s_in));
+            cup = chi;
+        }
+        CUDA_OK(cudaEventRecord(st->ev_in[k], st->s_in));
+        CUDA_OK(cudaStreamWaitEvent(st->stream, st->ev_in[k], 0));
+        int r;
+        if (store_to_host)
+            r = fast420_launch(st, st->d_src, st->d_src_stride, zero, ddst, dst_stride, zero, 1, y0, y1, st->stream);
+        else
+            r = fast420_launch(st, st->d_src, st->d_src_stride, zero, st->d_dst, st->d_dst_stride, zero, 1, y0, y1,
+                               st->stream);
+        if (r < 0)
+            return r;
+        if (r == 0) {                              /* cannot happen for staging buffers; be safe */
+            cudaStreamSynchronize(st->s_in);
+            cudaStreamSynchronize(st->stream);
+            return 1;
+        }
+        if (!store_to_host) {
+            CUDA_OK(cudaEventRecord(st->ev_k[k], st->stream));
+            CUDA_OK(cudaStreamWaitEvent(st->s_out, st->ev_k[k], 0));
+            CUDA_OK(copy_rows_async(dst[0] + (size_t)y0 * dst_stride[0], dst_stride[0],
+                                      st->d_dst[0] + (size_t)y0 * st->d_dst_stride[0], st->d_dst_stride[0],
+                                      st->dst_rowbytes[0], y1 - y0, cudaMemcpyDeviceToHost, st->s_out));
+        }
+    }
+    if (store_to_host)
+        CUDA_OK(cudaStreamSynchronize(st->stream));
+    else
+        CUDA_OK(cudaStreamSynchronize(st->s_out));
     return 0;
 }
 
@@ -855,7 +963,52 @@ extern "C" int ff_b200_cuda_scale_host(SwsCudaState *st,
                                        uint8_t *const dst[4], const int dst_stride[4], int y0, int y1)
 {
     const SwsCudaPlan *p = &st->plan;
-    int ret = ensure_staging(st);
+    int ret;
+
+    /* Page-locked caller frames (cudaHostAlloc / cudaHostRegister, e.g. sws_cuda_host_alloc) let a
+     * single synchronous sws_scale() overlap PCIe traffic in both directions.  e2e_mode:
+     *   0  serial   : H2D, kernel, D2H back to back (also the path for pageable frames)
+     *   1  zero-copy: the TMA kernel reads and writes the host frames directly
+     *   2  chunked  : row bands pipelined over three streams (H2D | kernel | D2H)
+     *   3  chunked H2D + kernel writing the host destination directly */
+    if (st->fast_ok && st->e2e_mode && src_y == 0 && src_h == p->src_h && y0 == 0 && y1 == p->dst_h) {
+        const uint8_t *dsrc[4] = { nullptr, nullptr, nullptr, nullptr };
+        uint8_t *ddst[4] = { nullptr, nullptr, nullptr, nullptr };
+        bool ok = true;
+        for (int i = 0; i < 3 && ok; i++) {
+            cudaPointerAttributes at;
+            if (!src[i] || cudaPointerGetAttributes(&at, src[i]) != cudaSuccess ||
+                at.type != cudaMemoryTypeHost || !at.devicePointer)
+                ok = false;
+            else
+                dsrc[i] = (const uint8_t *)at.devicePointer;
+        }
+        if (ok) {
+            cudaPointerAttributes at;
+            if (!dst[0] || cudaPointerGetAttributes(&at, dst[0]) != cudaSuccess ||
+                at.type != cudaMemoryTypeHost || !at.devicePointer)
+                ok = false;
+            else
+                ddst[0] = (uint8_t *)at.devicePointer;
+        }
+        cudaGetLastError();   /* pageable pointers make cudaPointerGetAttributes report an error */
+        if (ok && st->e2e_mode == 1) {
+            int r = fast420_launch(st, dsrc, src_stride, nullptr, ddst, dst_stride, nullptr, 1, 0, p->dst_h, st->stream);
+            if (r < 0)
+                return r;
+            if (r == 1) {
+                CUDA_OK(cudaStreamSynchronize(st->stream));
+                return 0;
+            }
+        } else if (ok && (st->e2e_mode == 2 || st->e2e_mode == 3)) {
+            int r = pipelined_host_frame(st, src, src_stride, dst, dst_stride, ddst,
+                                         st->e2e_mode == 3 && aligned16(ddst[0]) && !(dst_stride[0] & 15));
+            if (r <= 0)
+                return r;
+        }
+    }
+
+    ret = ensure_staging(st);
     if (ret < 0)
         return ret;
     if (upload) {
@@ -870,7 +1023,7 @@ extern "C" int ff_b200_cuda_scale_host(SwsCudaState *st,
             if (r1 > st->src_rows[i])
                 r1 = st->src_rows[i];
             /* slice pointers address the first row of the slice (swscale.h:566-576) */
-            CUDA_OK(cudaMemcpy2DAsync(st->d_src[i] + (size_t)r0 * st->d_src_stride[i], st->d_src_stride[i],
+            CUDA_OK(copy_rows_async(st->d_src[i] + (size_t)r0 * st->d_src_stride[i], st->d_src_stride[i],
                                       src[i], src_stride[i], st->src_rowbytes[i], r1 - r0,
                                       cudaMemcpyHostToDevice, st->stream));
         }
@@ -890,7 +1043,7 @@ extern "C" int ff_b200_cuda_scale_host(SwsCudaState *st,
             int r1 = (y1 == p->dst_h) ? st->dst_rows[i] : (y1 >> vs);
             if (r1 <= r0)
                 continue;
-            CUDA_OK(cudaMemcpy2DAsync(dst[i] + (size_t)r0 * dst_stride[i], dst_stride[i],
+            CUDA_OK(copy_rows_async(dst[i] + (size_t)r0 * dst_stride[i], dst_stride[i],
                                       st->d_dst[i] + (size_t)r0 * st->d_dst_stride[i], st->d_dst_stride[i],
                                       st->dst_rowbytes[i], r1 - r0, cudaMemcpyDeviceToHost, st->stream));
         }

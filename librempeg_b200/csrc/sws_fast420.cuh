@@ -39,6 +39,7 @@
 
 struct Fast420Args {
     int tiles_x, tiles_y, frames;
+    int ty_first;                  /* first tile row of this launch (row-range launches) */
     int dst_h;
     int bgr;                       /* 0: R,G,B byte order, 1: B,G,R */
     int cy, yb;                    /* LUT closed form (sws_colorspace.c) */
@@ -190,7 +191,7 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
                 const int f = tile / tiles_per_frame;
                 const int t = tile - f * tiles_per_frame;
                 const int ty = t / A.tiles_x, tx = t - ty * A.tiles_x;
-                const int y0 = ty * F420_TH;
+                const int y0 = (A.ty_first + ty) * F420_TH;
                 const int c_lo = __ldg(&A.rows[y0]).w;
                 unsigned char *b = smem_dyn + stage * F420_IN_BYTES;
                 tile_info[stage] = make_int4(tx, y0, f, 0);

@@ -253,5 +253,28 @@ class SwsContext:
         return {v: out[k] for k, v in keys.items()}
 
 
+class PinnedBuffer:
+    """Page-locked host memory from sws_cuda_host_alloc(), viewed as a numpy uint8 array."""
+
+    def __init__(self, nbytes):
+        self._L = lib()
+        self.ptr = self._L.sws_cuda_host_alloc(nbytes)
+        if not self.ptr:
+            raise MemoryError("sws_cuda_host_alloc(%d) failed" % nbytes)
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr))
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            self._L.sws_cuda_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def device_count():
     return lib().sws_cuda_device_count()

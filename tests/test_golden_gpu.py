@@ -134,3 +134,27 @@ def test_gray_ramp_property_full_size():
     t = O.yuv2rgb_tables(O.YUV2RGB_COEFFS[5], 0, 0, 1 << 16, 1 << 16)
     lut = t["y_table"][np.arange(256) + t["rV"][128 + 512]]
     assert np.array_equal(rgb[..., 0], lut[src.planes[0][:, :w]])
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("geom", [(3840, 2160), (1920, 1080), (640, 480), (1280, 722)])
+def test_pinned_host_frames_all_transfer_modes(mode, geom, monkeypatch):
+    """sws_scale() on page-locked frames: serial, zero-copy, banded H2D|kernel|D2H and banded with direct
+    host stores must all give the bytes of the pageable path (which the goldens pin to the reference)."""
+    w, h = geom
+    monkeypatch.setenv("SWS_B200_E2E_MODE", mode)
+    monkeypatch.setenv("SWS_B200_E2E_BANDS", "5")
+    ctx = S.SwsContext(w, h, "yuv420p", w, h, "rgb24", S.SWS_BICUBIC | S.BX)
+    src = T.Frame("yuv420p", w, h).randomize(31)
+    want = T.Frame("rgb24", w, h, fill=0)
+    assert ctx.scale(src.planes, src.strides, want.planes, want.strides, 0, h) == h
+    ysz, csz, osz = w * h, (w // 2) * (h // 2), w * h * 3
+    bufs = [S.PinnedBuffer(ysz), S.PinnedBuffer(csz), S.PinnedBuffer(csz), S.PinnedBuffer(osz)]
+    for b, pl, (rows, rb) in zip(bufs, src.planes, src.layout):
+        b.array[:] = pl[:, :rb].reshape(-1)
+    bufs[3].array[:] = 0
+    for _ in range(2):
+        assert ctx.scale([b.ptr for b in bufs[:3]], [w, w // 2, w // 2], [bufs[3].ptr], [w * 3], 0, h) == h
+    assert np.array_equal(bufs[3].array.reshape(h, w * 3), want.valid()[0])
+    for b in bufs:
+        b.close()
