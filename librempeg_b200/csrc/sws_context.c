@@ -421,11 +421,6 @@ static int init_single(SwsContext *sws, int with_device)
             return AVERROR(ENOTSUP);
         }
     }
-    if ((flags & SWS_FULL_CHR_H_INT) && is_rgb(sws->dst_format) && !c->unscaled_lut) {
-        set_error(c, "full-chroma RGB output (odd width / 4:4:4 source) is not on the CUDA hot path yet");
-        return AVERROR(ENOTSUP);
-    }
-
     /* ---- FIR banks: horizontal 1<<14, vertical 1<<12 (utils.c:1681-1729) ---- */
     memset(&spec, 0, sizeof(spec));
     spec.flags = flags;
@@ -476,6 +471,7 @@ static int init_single(SwsContext *sws, int with_device)
     p->dst_bits = c->dst_bpc;
     p->has_chroma = 1;
     p->unscaled_lut = c->unscaled_lut;
+    p->full_chr = is_rgb(sws->dst_format) && (flags & SWS_FULL_CHR_H_INT) && !c->unscaled_lut;
     /* hScale selection (swscale.c:675-688) and its shift (swscale.c:69-159) */
     p->inter_bits = c->dst_bpc > 14 ? 19 : 15;
     if (c->src_bpc == 8)

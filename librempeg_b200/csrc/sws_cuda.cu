@@ -227,7 +227,77 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
     const int lfs = P.vl_size, cfs = P.vc_size;
 
     /* ---- stage V + pack ---- */
-    if (kind >= SWSC_DST_RGB24) {
+    if (kind >= SWSC_DST_RGB24 && P.full_chr) {
+        /* packed RGB with full horizontal chroma (odd width / 4:4:4 source): every pixel has its own
+         * U,V and the colour step is arithmetic, not LUT based: yuv2rgb_full_{X,1,2}_c_template +
+         * yuv2rgb_write_full (output.c:1998-2051,2160-2330), yuv2rgba64_full_X_c_template (:1373-1430) */
+        const bool is16 = kind >= SWSC_DST_RGB48;
+        for (int idx = threadIdx.x; idx < th * TW; idx += blockDim.x) {
+            const int ty = idx / TW, x = idx - ty * TW;
+            if (x >= tw)
+                continue;
+            const int y = ry0 + ty;
+            const int16_t *lf = P.vl_coef + (size_t)y * lfs;
+            const int16_t *cf = P.vc_coef + (size_t)y * cfs;
+            const int rl = max(P.vl_pos[y], 0) - lo_l;
+            const int rc = max(P.vc_pos[y], 0) - lo_c;
+            const inter_t *pl = hb_l + (size_t)rl * TW + x;
+            const inter_t *pu = hb_u + (size_t)rc * CW + x;
+            const inter_t *pv = hb_v + (size_t)rc * CW + x;
+            unsigned Yv = 0, U = 0, V = 0;
+            for (int j = 0; j < lfs; j++)
+                Yv += (unsigned)(int)pl[(size_t)(min(rl + j, nl - 1) - rl) * TW] * (unsigned)(int)lf[j];
+            for (int j = 0; j < cfs; j++) {
+                const int r = min(rc + j, nc - 1) - rc;
+                const unsigned c = (unsigned)(int)cf[j];
+                U += (unsigned)(int)pu[(size_t)r * CW] * c;
+                V += (unsigned)(int)pv[(size_t)r * CW] * c;
+            }
+            const int gx = x0 + x;
+            uint8_t *d = dst0 + (size_t)y * A.dst_stride[0];
+            if (!is16) {
+                /* rounding bias 1<<9, dropped by the 2-tap fast paths exactly as vscale.c:135-163 picks them */
+                unsigned lb = 1u << 9, cb = 1u << 9;
+                if (cfs == 2) {
+                    const int c0 = cf[0], c1 = cf[1];
+                    const bool cok = c0 + c1 == 4096 && (unsigned)c1 <= 4096u;
+                    if (lfs == 1 && cok)
+                        cb = 0;
+                    else if (lfs == 2 && cok && lf[0] + lf[1] == 4096 && (unsigned)(int)lf[1] <= 4096u)
+                        lb = cb = 0;
+                }
+                int Yi = (int)(Yv + lb) >> 10;
+                const int Ui = (int)(U + cb - (128u << 19)) >> 10;
+                const int Vi = (int)(V + cb - (128u << 19)) >> 10;
+                unsigned Yu = (unsigned)(Yi - P.rgb.y_offset) * (unsigned)P.rgb.y_coeff + (1u << 21);
+                int R = (int)(Yu + (unsigned)Vi * (unsigned)P.rgb.v2r);
+                int G = (int)(Yu + (unsigned)Vi * (unsigned)P.rgb.v2g + (unsigned)Ui * (unsigned)P.rgb.u2g);
+                int B = (int)(Yu + (unsigned)Ui * (unsigned)P.rgb.u2b);
+                R = clip_uintp2(R, 30) >> 22; G = clip_uintp2(G, 30) >> 22; B = clip_uintp2(B, 30) >> 22;
+                switch (kind) {
+                case SWSC_DST_RGB24: d += 3 * gx; d[0] = R; d[1] = G; d[2] = B; break;
+                case SWSC_DST_BGR24: d += 3 * gx; d[0] = B; d[1] = G; d[2] = R; break;
+                case SWSC_DST_RGBA: d += 4 * gx; d[0] = R; d[1] = G; d[2] = B; d[3] = 255; break;
+                case SWSC_DST_BGRA: d += 4 * gx; d[0] = B; d[1] = G; d[2] = R; d[3] = 255; break;
+                case SWSC_DST_ARGB: d += 4 * gx; d[0] = 255; d[1] = R; d[2] = G; d[3] = B; break;
+                case SWSC_DST_ABGR: d += 4 * gx; d[0] = 255; d[1] = B; d[2] = G; d[3] = R; break;
+                }
+            } else {
+                int Yi = ((int)(Yv - 0x40000000u) >> 14) + 0x10000;
+                const int Ui = (int)(U - (128u << 23)) >> 14;
+                const int Vi = (int)(V - (128u << 23)) >> 14;
+                const unsigned Yu = (unsigned)(Yi - P.rgb.y_offset) * (unsigned)P.rgb.y_coeff + (1u << 13) - (1u << 29);
+                const unsigned R = (unsigned)Vi * (unsigned)P.rgb.v2r;
+                const unsigned G = (unsigned)Vi * (unsigned)P.rgb.v2g + (unsigned)Ui * (unsigned)P.rgb.u2g;
+                const unsigned B = (unsigned)Ui * (unsigned)P.rgb.u2b;
+                const int r = clip_uintp2(((int)(R + Yu) >> 14) + (1 << 15), 16);
+                const int g = clip_uintp2(((int)(G + Yu) >> 14) + (1 << 15), 16);
+                const int b = clip_uintp2(((int)(B + Yu) >> 14) + (1 << 15), 16);
+                uint16_t *w = reinterpret_cast<uint16_t *>(d) + 3 * gx;
+                w[0] = kind == SWSC_DST_RGB48 ? r : b; w[1] = g; w[2] = kind == SWSC_DST_RGB48 ? b : r;
+            }
+        }
+    } else if (kind >= SWSC_DST_RGB24) {
         /* packed RGB: one chroma pair per two pixels (output.c:1788-1840 / 1115-1196) */
         const int pw = tw >> 1;                       /* pairs in this tile (dst_w even here) */
         const bool is16 = kind >= SWSC_DST_RGB48;

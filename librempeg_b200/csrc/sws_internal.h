@@ -112,6 +112,7 @@ typedef struct SwsCudaPlan {
     int h_shift;                 /* right shift applied after the H FIR       */
     int has_chroma;              /* 0 for gray sources/destinations           */
     int unscaled_lut;            /* 1: reference would take convert_unscaled  */
+    int full_chr;                /* 1: SWS_FULL_CHR_H_INT packed RGB (per-pixel chroma, arithmetic) */
     int dither_bayer;            /* 1: ff_dither_8x8_128 rows, 0: constant 64 */
     /* range conversion on the h-scaled lines (reference swscale.c:163-255,577-660) */
     int range_mode;              /* 0 none, 1 to-jpeg, 2 from-jpeg            */

@@ -401,8 +401,7 @@ class OracleContext:
                     and (shs, svs) == (dhs, dvs) and (self.skind == "semi") == (self.dkind == "semi")
                     and self.sdepth != self.ddepth):
                 raise NotImplementedError("planarCopyWrapper depth conversion is not restated")
-        if dst_rgb and flags & SWS_FULL_CHR_H_INT:
-            raise NotImplementedError("full-chroma RGB output is not restated")
+        self.full_chr = bool(dst_rgb and flags & SWS_FULL_CHR_H_INT)
 
         def lpos(sub, pos):                                            # get_local_pos, utils.c:168
             if pos == -1 or pos <= -513:
@@ -510,9 +509,60 @@ class OracleContext:
         hl, hu, hv = self._range(hl, hu, hv)
         if self.dkind in ("planar", "semi"):
             return self._planar_out(hl, hu, hv)
+        if self.full_chr:
+            return self._rgb_full_out(hl, hu, hv)
         if self.dkind == "rgb16":
             return self._rgb16_out(hl, hu, hv)
         return self._rgb8_out(hl, hu, hv)
+
+    # yuv2rgb_full_{X,1,2}_c_template + yuv2rgb_write_full (output.c:1998-2051,2160-2330);
+    # yuv2rgba64_full_X_c_template (output.c:1373-1430); chooser vscale.c:135-163
+    def _rgb_full_out(self, hl, hu, hv):
+        t = self.rgb
+        n, w = self.dh, self.dw
+        lcoef, ccoef = self.v_lum[0], self.v_chr[0]
+        Y = self._vsum(hl, self.v_lum)[:, :w]
+        U = self._vsum(hu, self.v_chr, n)[:, :w]
+        V = self._vsum(hv, self.v_chr, n)[:, :w]
+        if self.dkind == "rgb16":
+            Y = (_wrap32(Y - 0x40000000) >> 14) + 0x10000
+            U = _wrap32(U - (128 << 23)) >> 14
+            V = _wrap32(V - (128 << 23)) >> 14
+            Y = _wrap32(_wrap32((Y - t["y_offset"]) * t["y_coeff"]) + (1 << 13) - (1 << 29))
+            R = _wrap32(V * t["v2r"]); G = _wrap32(V * t["v2g"] + U * t["u2g"]); B = _wrap32(U * t["u2b"])
+            comp = lambda c: np.clip((_wrap32(c + Y) >> 14) + (1 << 15), 0, 65535).astype("<u2")
+            r, g, b = comp(R), comp(G), comp(B)
+            out = np.zeros((n, w * 3), "<u2")
+            a, c = (r, b) if self.dfmt == "rgb48le" else (b, r)
+            out[:, 0::3], out[:, 1::3], out[:, 2::3] = a, g, c
+            return [out.view(np.uint8).reshape(n, -1)]
+        lb = np.full((n, 1), 1 << 9, np.int64)
+        cb = np.full((n, 1), 1 << 9, np.int64)
+        if ccoef.shape[1] == 2:
+            c0, c1 = ccoef[:n, 0].astype(np.int64), ccoef[:n, 1].astype(np.int64)
+            cok = (c0 + c1 == 4096) & (c1 >= 0) & (c1 <= 4096)
+            if lcoef.shape[1] == 1:
+                cb[cok, 0] = 0
+            elif lcoef.shape[1] == 2:
+                l0, l1 = lcoef[:n, 0].astype(np.int64), lcoef[:n, 1].astype(np.int64)
+                both = cok & (l0 + l1 == 4096) & (l1 >= 0) & (l1 <= 4096)
+                lb[both, 0] = 0
+                cb[both, 0] = 0
+        Y = _wrap32(Y + lb) >> 10
+        U = _wrap32(U + cb - (128 << 19)) >> 10
+        V = _wrap32(V + cb - (128 << 19)) >> 10
+        Y = _wrap32(_wrap32((Y - t["y_offset"]) * t["y_coeff"]) + (1 << 21))
+        clip30 = lambda x: np.clip(_wrap32(x), 0, (1 << 30) - 1) >> 22
+        R = clip30(Y + V * t["v2r"]).astype(np.uint8)
+        G = clip30(Y + V * t["v2g"] + U * t["u2g"]).astype(np.uint8)
+        B = clip30(Y + U * t["u2b"]).astype(np.uint8)
+        order = {"rgb24": (R, G, B), "bgr24": (B, G, R), "rgba": (R, G, B, None), "bgra": (B, G, R, None),
+                 "argb": (None, R, G, B), "abgr": (None, B, G, R)}[self.dfmt]
+        bpp = len(order)
+        out = np.zeros((n, w * bpp), np.uint8)
+        for k, comp in enumerate(order):
+            out[:, k::bpp] = 255 if comp is None else comp
+        return [out]
 
     # yuv2planeX_8_c / yuv2planeX_10_c / yuv2planeX_16_c / yuv2nv12cX_c (output.c:163-187,340-357,468-528)
     def _planar_out(self, hl, hu, hv):

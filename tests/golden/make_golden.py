@@ -66,6 +66,12 @@ def cases():
                              (130, 66, 62, 30), (34, 34, 1280, 720)]:
         out.append(dict(sw=sw, sh=sh, sf="yuv420p", dw=dw, dh=dh, df="rgb24", flags=R.SWS_BICUBIC | BX))
         out.append(dict(sw=sw, sh=sh, sf="yuv420p", dw=dw, dh=dh, df="yuv420p", flags=R.SWS_BICUBIC | BX))
+    # full-chroma RGB (odd width, 4:4:4 sources, explicit flag)
+    for sf in ["yuv444p", "yuv420p", "yuv444p10le"]:
+        for df in ["rgb24", "bgra", "argb", "rgb48le"]:
+            out.append(dict(sw=162, sh=122, sf=sf, dw=201, dh=150, df=df, flags=R.SWS_BICUBIC | BX))
+            out.append(dict(sw=162, sh=122, sf=sf, dw=162, dh=160, df=df,
+                            flags=R.SWS_BILINEAR | BX | R.SWS_FULL_CHR_H_INT))
     for i, c in enumerate(out):
         c.setdefault("seed", 100 + i)
         c.setdefault("mode", "extreme" if i % 7 == 3 else "noise")

@@ -163,13 +163,17 @@ def test_no_device_means_loud_failure_not_cpu_fallback():
 def test_init_rejects_what_the_hot_path_does_not_cover():
     for kw in (dict(src_fmt="yuv420p", dst_fmt="rgb24", flags=S.SWS_FAST_BILINEAR),
                dict(src_fmt="yuv420p", dst_fmt="rgb24", flags=S.SWS_BICUBIC | S.SWS_BILINEAR),
-               dict(src_fmt="yuv444p", dst_fmt="rgb24", flags=S.SWS_BICUBIC | S.BX)):
+               dict(src_fmt="yuv420p10le", dst_fmt="yuv420p", flags=S.SWS_BICUBIC | S.BX),   # planarCopyWrapper
+               dict(src_fmt="yuv420p", dst_fmt="rgb24", flags=S.SWS_BICUBIC | (1 << 16))):    # chroma drop
         with pytest.raises(RuntimeError):
             S.SwsContext(64, 64, kw["src_fmt"], 64, 64, kw["dst_fmt"], kw["flags"], plan_only=True)
     with pytest.raises(RuntimeError):
         S.SwsContext(0, 64, "yuv420p", 64, 64, "rgb24", S.SWS_BICUBIC, plan_only=True)
-    with pytest.raises(RuntimeError):   # odd width forces the (not yet covered) full-chroma path
-        S.SwsContext(64, 64, "yuv420p", 65, 64, "rgb24", S.SWS_BICUBIC | S.BX, plan_only=True)
+    # odd width / 4:4:4 sources force full-chroma interpolation (utils.c:1270-1286): covered
+    c = S.SwsContext(64, 64, "yuv420p", 65, 64, "rgb24", S.SWS_BICUBIC | S.BX, plan_only=True)
+    assert c.fields.flags & S.SWS_FULL_CHR_H_INT
+    c = S.SwsContext(64, 64, "yuv444p", 64, 64, "rgb24", S.SWS_BICUBIC | S.BX, plan_only=True)
+    assert c.fields.flags & S.SWS_FULL_CHR_H_INT
 
 
 def test_product_never_touches_the_oracle():

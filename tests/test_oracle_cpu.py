@@ -112,7 +112,7 @@ def test_numpy_oracle_matches_golden_fixture(case):
 
 
 @pytest.mark.skipif(not R.available(), reason="oracle/_ref/libswsref.so not built")
-@pytest.mark.parametrize("idx", range(0, 246, 9))
+@pytest.mark.parametrize("idx", range(0, 270, 9))
 def test_golden_fixture_still_matches_real_reference(idx):
     """Guards the fixtures themselves: regenerate a sample of them from the live reference."""
     case = _golden_cases(False)[idx]

@@ -155,4 +155,18 @@ def test_unsupported_fails_loudly():
     with pytest.raises(RuntimeError):
         S.SwsContext(320, 240, "yuv420p", 320, 240, "rgb24", S.SWS_FAST_BILINEAR)
     with pytest.raises(RuntimeError):
-        S.SwsContext(320, 240, "yuv444p", 321, 240, "rgb24", S.SWS_BICUBIC | BX)  # full-chroma path
+        S.SwsContext(320, 240, "yuv420p10le", 320, 240, "yuv420p", S.SWS_BICUBIC | BX)  # planarCopyWrapper
+
+
+@pytest.mark.parametrize("sf", ["yuv444p", "yuv420p", "yuv422p", "yuv444p10le", "yuv420p12le", "nv12"])
+@pytest.mark.parametrize("df", ["rgb24", "bgr24", "rgba", "bgra", "argb", "abgr", "rgb48le", "bgr48le"])
+@pytest.mark.parametrize("geom,flags", [((322, 242, 323, 242), S.SWS_BICUBIC | BX),
+                                        ((322, 242, 401, 301), S.SWS_BILINEAR | BX),
+                                        ((322, 242, 161, 121), S.SWS_LANCZOS | BX),
+                                        ((322, 242, 322, 300), S.SWS_BILINEAR | BX | S.SWS_FULL_CHR_H_INT),
+                                        ((322, 242, 322, 242), S.SWS_POINT | BX | S.SWS_FULL_CHR_H_INT)])
+def test_full_chroma_rgb(sf, df, geom, flags):
+    """SWS_FULL_CHR_H_INT (forced by odd widths and 4:4:4 sources, utils.c:1270-1286): per-pixel chroma and
+    the arithmetic colour step of yuv2rgb_write_full (output.c:1998-2051) incl. the bias-free 2-tap variants."""
+    sw, sh, dw, dh = geom
+    _check(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags, seed=41)

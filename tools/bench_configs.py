@@ -1,0 +1,82 @@
+#!/usr/bin/env python3
+"""Device-resident throughput of every BASELINE.json configuration (not the headline bench line;
+bench.py reports the metric configuration).  For each config: frames resident in HBM, one batched
+launch per step through sws_cuda_scale_batch(), CUDA events on the library stream.
+
+    python tools/bench_configs.py [--frames 16] [--steps 10]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+from librempeg_b200 import swscale as S  # noqa: E402
+from tests import sws_testlib as T  # noqa: E402
+
+CONFIGS = [
+    ("C1 640x480 yuv420p->rgb24 point", 640, 480, "yuv420p", 640, 480, "rgb24", S.SWS_POINT | S.BX),
+    ("C2 1080p yuv420p->rgb24 bicubic", 1920, 1080, "yuv420p", 1920, 1080, "rgb24", S.SWS_BICUBIC | S.BX),
+    ("C3 4K yuv420p10le->rgb48le lanczos", 3840, 2160, "yuv420p10le", 3840, 2160, "rgb48le", S.SWS_LANCZOS | S.BX),
+    ("C4 8K nv12->1080p yuv420p bicubic", 7680, 4320, "nv12", 1920, 1080, "yuv420p", S.SWS_BICUBIC | S.BX),
+    ("C5 4K yuv420p->rgb24 bicubic", 3840, 2160, "yuv420p", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
+    ("C5' 4K yuv420p->rgb24 default flags (LUT path)", 3840, 2160, "yuv420p", 3840, 2160, "rgb24", S.SWS_BICUBIC),
+    ("X1 1080p->4K yuv420p->rgb24 bicubic", 1920, 1080, "yuv420p", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
+    ("X2 4K->1080p yuv420p->yuv420p bicubic", 3840, 2160, "yuv420p", 1920, 1080, "yuv420p", S.SWS_BICUBIC | S.BX),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    peak = 6449.4
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    for (name, sw, sh, sf, dw, dh, df, flags) in CONFIGS:
+        if args.only and args.only not in name:
+            continue
+        ctx = S.SwsContext(sw, sh, sf, dw, dh, df, flags)
+        sl, dl = T.plane_layout(sf, sw, sh), T.plane_layout(df, dw, dh)
+        F = args.frames
+        src = [torch.randint(0, 256, (F, rows * rb), dtype=torch.uint8, device=dev) for rows, rb in sl]
+        if "10le" in sf:   # keep 10-bit samples in range
+            for t in src:
+                v = t.view(torch.int16)
+                v &= 0x3FF
+        dst = [torch.zeros((F, rows * rb), dtype=torch.uint8, device=dev) for rows, rb in dl]
+        sstr, dstr = [rb for _, rb in sl], [rb for _, rb in dl]
+        sfs, dfs = [rows * rb for rows, rb in sl], [rows * rb for rows, rb in dl]
+        stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+        def step():
+            r = ctx.scale_batch_device(src, sstr, sfs, dst, dstr, dfs, F)
+            assert r == dh, ctx.last_error
+        for _ in range(3):
+            step()
+        ctx.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        by = (sum(sfs) + sum(dfs)) * F
+        gbs = by / (ms * 1e-3) / 1e9
+        print("%-48s %-18s %8.3f ms/%d frames  in %8.1f Mpix/s  out %8.1f Mpix/s  %7.1f GB/s = %5.1f%% of %.0f"
+              % (name, ctx.kernel_name, ms, F, F * sw * sh / ms / 1e3, F * dw * dh / ms / 1e3, gbs, 100 * gbs / peak, peak))
+        ctx.close()
+
+
+if __name__ == "__main__":
+    main()
