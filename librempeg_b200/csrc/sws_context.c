@@ -95,6 +95,9 @@ void sws_freeContext(SwsContext *sws)
     if (!c)
         return;
     release_tables(c);
+    if (c->dyn)
+        sws_freeContext(c->dyn);
+    free(c->dyn_key);
     free(c);
 }
 

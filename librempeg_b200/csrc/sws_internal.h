@@ -172,6 +172,11 @@ typedef struct SwsInternal {
     int dst_y;
     int slice_dir;
     int rows_received;
+    /* AVFrame entry points (sws_frame.c) */
+    SwsContext *dyn;                 /* inner legacy context of the dynamic sws_scale_frame() mode */
+    void *dyn_key;                   /* description it was planned for */
+    const void *frame_src, *frame_dst;   /* sws_frame_start() .. sws_frame_end() */
+    int frame_rows_sent, frame_uploaded;
     char last_error[256];
 } SwsInternal;
 

@@ -186,3 +186,47 @@ API void swsref_lfg_fill(uint8_t *buf, size_t n, unsigned seed, int bits)
 }
 
 API void swsref_md5(uint8_t out[16], const uint8_t *buf, size_t n) { av_md5_sum(out, buf, n); }
+
+/* ---- AVFrame ABI facts and the dynamic (frame-described) mode of sws_scale_frame() ---- */
+#include <stddef.h>
+API void swsref_frame_offsets(int out[24])
+{
+    int i = 0;
+    out[i++] = offsetof(AVFrame, data);           out[i++] = offsetof(AVFrame, linesize);
+    out[i++] = offsetof(AVFrame, extended_data);  out[i++] = offsetof(AVFrame, width);
+    out[i++] = offsetof(AVFrame, height);         out[i++] = offsetof(AVFrame, nb_samples);
+    out[i++] = offsetof(AVFrame, format);         out[i++] = offsetof(AVFrame, pict_type);
+    out[i++] = offsetof(AVFrame, sample_aspect_ratio); out[i++] = offsetof(AVFrame, pts);
+    out[i++] = offsetof(AVFrame, pkt_dts);        out[i++] = offsetof(AVFrame, time_base);
+    out[i++] = offsetof(AVFrame, quality);        out[i++] = offsetof(AVFrame, opaque);
+    out[i++] = offsetof(AVFrame, repeat_pict);    out[i++] = offsetof(AVFrame, sample_rate);
+    out[i++] = offsetof(AVFrame, buf);            out[i++] = offsetof(AVFrame, flags);
+    out[i++] = offsetof(AVFrame, color_range);    out[i++] = offsetof(AVFrame, color_primaries);
+    out[i++] = offsetof(AVFrame, color_trc);      out[i++] = offsetof(AVFrame, colorspace);
+    out[i++] = offsetof(AVFrame, chroma_location); out[i++] = offsetof(AVFrame, hw_frames_ctx);
+}
+
+/* props: [0..2] = src color_range, colorspace, chroma_location; [3..5] = dst */
+API int swsref_scale_frame_dynamic(unsigned flags, int threads, void *dst, void *src, const int props[6])
+{
+    AVFrame *s = src, *d = dst;
+    SwsContext *c = sws_alloc_context();
+    int ret;
+    if (!c)
+        return AVERROR(ENOMEM);
+    c->flags = flags;
+    c->threads = threads;
+    s->color_range = props[0]; s->colorspace = props[1]; s->chroma_location = props[2];
+    d->color_range = props[3]; d->colorspace = props[4]; d->chroma_location = props[5];
+    ret = sws_scale_frame(c, d, s);
+    sws_free_context(&c);
+    return ret;
+}
+
+API int swsref_is_noop(void *dst, void *src, const int props[6])
+{
+    AVFrame *s = src, *d = dst;
+    s->color_range = props[0]; s->colorspace = props[1]; s->chroma_location = props[2];
+    d->color_range = props[3]; d->colorspace = props[4]; d->chroma_location = props[5];
+    return sws_is_noop(d, s);
+}
