@@ -26,6 +26,7 @@
 
 #include "sws_internal.h"
 #include "sws_fast420.cuh"
+#include "sws_fast420_16.cuh"
 
 #define CUDA_OK(call)                                                           \
     do {                                                                        \
@@ -497,6 +498,8 @@ struct SwsCudaState {
     const char *kernel_name;
     /* fast420 path */
     int fast_ok;
+    int fast16_ok, fast16_taps;
+    Fast16Row *d_fast16_rows;
     int e2e_mode, e2e_bands; /* how sws_scale() moves page-locked host frames (see scale_host)  */
     cudaStream_t s_in, s_out;
     cudaEvent_t ev_in[16], ev_k[16];
@@ -751,6 +754,124 @@ static int fast420_launch(SwsCudaState *st, const uint8_t *const src[4], const i
     return 1;
 }
 
+
+/* ---------------------------------------------------------------- fast420 16-bit host side */
+
+typedef void (*fast16_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                                const Fast16Args);
+
+static fast16_kernel_t pick_fast16(int taps, bool bgr)
+{
+    switch (taps) {
+    case 4:  return bgr ? sws_fast420_rgb16_kernel<4, true> : sws_fast420_rgb16_kernel<4, false>;
+    case 6:  return bgr ? sws_fast420_rgb16_kernel<6, true> : sws_fast420_rgb16_kernel<6, false>;
+    default: return bgr ? sws_fast420_rgb16_kernel<8, true> : sws_fast420_rgb16_kernel<8, false>;
+    }
+}
+
+static int fast16_setup(SwsCudaState *st, const SwsFirBank *vc)
+{
+    const SwsCudaPlan *p = &st->plan;
+    st->fast16_ok = 0;
+    if (p->src_layout != SWSC_SRC_PLANAR || p->src_bits <= 8 || p->src_bits > 16 || p->inter_bits != 19)
+        return 0;
+    if (p->dst_kind != SWSC_DST_RGB48 && p->dst_kind != SWSC_DST_BGR48)
+        return 0;
+    if (!p->lum_identity || !p->chr_h_identity || p->chr_src_hsub != 1 || p->chr_dst_hsub != 1)
+        return 0;
+    if (vc->size > 8 || p->range_mode || p->full_chr || p->unscaled_lut || (p->dst_w & 1) || !get_encode_tiled())
+        return 0;
+    const int taps = vc->size <= 4 ? 4 : vc->size <= 6 ? 6 : 8;
+    const int padded = ((vc->len + F16_TH - 1) / F16_TH + 1) * F16_TH;
+    Fast16Row *rows = (Fast16Row *)calloc(padded, sizeof(Fast16Row));
+    if (!rows)
+        return AVERROR(ENOMEM);
+    for (int y = 0; y < padded; y++) {
+        const int yy = y < vc->len ? y : vc->len - 1;
+        int c[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+        for (int j = 0; j < vc->size; j++)
+            c[j] = vc->coef[(size_t)yy * vc->size + j];
+        rows[y].pos_abs = vc->pos[yy];
+        rows[y].c01 = (c[0] & 0xFFFF) | (c[1] << 16);
+        rows[y].c23 = (c[2] & 0xFFFF) | (c[3] << 16);
+        rows[y].c45 = (c[4] & 0xFFFF) | (c[5] << 16);
+        rows[y].c67 = (c[6] & 0xFFFF) | (c[7] << 16);
+    }
+    for (int y = 0; y < padded; y++) {
+        const int base = rows[y & ~(F16_TH - 1)].pos_abs;
+        rows[y].pos_rel = rows[y].pos_abs - base;
+        if ((y > 0 && rows[y].pos_abs < rows[y - 1].pos_abs) || rows[y].pos_rel < 0 ||
+            rows[y].pos_rel + taps > F16_CROWS) {
+            free(rows);
+            return 0;
+        }
+    }
+    cudaError_t e = cudaMalloc(&st->d_fast16_rows, sizeof(Fast16Row) * padded);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(st->d_fast16_rows, rows, sizeof(Fast16Row) * padded, cudaMemcpyHostToDevice);
+    free(rows);
+    CUDA_OK(e);
+    CUDA_OK(cudaFuncSetAttribute((const void *)pick_fast16(taps, false),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
+    CUDA_OK(cudaFuncSetAttribute((const void *)pick_fast16(taps, true),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
+    st->fast16_ok = 1;
+    st->fast16_taps = taps;
+    st->kernel_name = "fast420_rgb16_tma";
+    return 0;
+}
+
+static int fast16_launch(SwsCudaState *st, const uint8_t *const src[4], const int src_stride[4],
+                         const int64_t src_fstride[4], uint8_t *const dst[4], const int dst_stride[4],
+                         const int64_t dst_fstride[4], int nb_frames, int y0, int y1, cudaStream_t stream)
+{
+    const SwsCudaPlan *p = &st->plan;
+    if (!st->fast16_ok || (y0 % F16_TH) || y1 <= y0 || y1 > p->dst_h)
+        return 0;
+    for (int i = 0; i < 3; i++)
+        if (!aligned16(src[i]) || (src_stride[i] & 15) || src_stride[i] <= 0 ||
+            (nb_frames > 1 && (src_fstride[i] & 15 || src_fstride[i] <= 0)))
+            return 0;
+    if (!aligned16(dst[0]) || (dst_stride[0] & 15) || dst_stride[0] <= 0 ||
+        (nb_frames > 1 && (dst_fstride[0] & 15 || dst_fstride[0] <= 0)))
+        return 0;
+    CUtensorMap my, mu, mv, mo;
+    const uint64_t fs_y = nb_frames > 1 ? src_fstride[0] : (uint64_t)src_stride[0] * p->src_h;
+    const uint64_t fs_u = nb_frames > 1 ? src_fstride[1] : (uint64_t)src_stride[1] * p->chr_src_h;
+    const uint64_t fs_v = nb_frames > 1 ? src_fstride[2] : (uint64_t)src_stride[2] * p->chr_src_h;
+    const uint64_t fs_o = nb_frames > 1 ? dst_fstride[0] : (uint64_t)dst_stride[0] * p->dst_h;
+    int ret;
+    if ((ret = make_map_3d(&my, CU_TENSOR_MAP_DATA_TYPE_UINT16, src[0], p->src_w, p->src_h, nb_frames,
+                           src_stride[0], fs_y, F16_TW, F16_TH)) < 0 ||
+        (ret = make_map_3d(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT16, src[1], p->chr_src_w, p->chr_src_h, nb_frames,
+                           src_stride[1], fs_u, F16_TW / 2, F16_CROWS)) < 0 ||
+        (ret = make_map_3d(&mv, CU_TENSOR_MAP_DATA_TYPE_UINT16, src[2], p->chr_src_w, p->chr_src_h, nb_frames,
+                           src_stride[2], fs_v, F16_TW / 2, F16_CROWS)) < 0 ||
+        (ret = make_map_3d(&mo, CU_TENSOR_MAP_DATA_TYPE_UINT32, dst[0], (uint64_t)p->dst_w * 3 / 2, y1,
+                           nb_frames, dst_stride[0], fs_o, F16_TW * 6 / 4, F16_TH / F420_CWARPS)) < 0)
+        return ret;
+    Fast16Args a;
+    memset(&a, 0, sizeof(a));
+    a.tiles_x = (p->dst_w + F16_TW - 1) / F16_TW;
+    a.tiles_y = (y1 - y0 + F16_TH - 1) / F16_TH;
+    a.ty_first = y0 / F16_TH;
+    a.frames = nb_frames;
+    a.dst_h = p->dst_h;
+    a.s19 = 19 - p->src_bits;
+    a.bgr = p->dst_kind == SWSC_DST_BGR48;
+    a.ycoef = (unsigned)p->rgb.y_coeff;
+    a.kconst = (1u << 13) - (1u << 29) - (unsigned)p->rgb.y_offset * (unsigned)p->rgb.y_coeff;
+    a.v2r = (unsigned)p->rgb.v2r; a.v2g = (unsigned)p->rgb.v2g;
+    a.u2g = (unsigned)p->rgb.u2g; a.u2b = (unsigned)p->rgb.u2b;
+    a.rows = st->d_fast16_rows;
+    const long long total = (long long)a.tiles_x * a.tiles_y * nb_frames;
+    const int grid = (int)(total < (long long)st->num_sms * 4 ? total : (long long)st->num_sms * 4);
+    pick_fast16(st->fast16_taps, a.bgr)<<<grid, F420_THREADS, F16_SMEM, stream>>>(my, mu, mv, mo, a);
+    CUDA_OK(cudaGetLastError());
+    st->launches++;
+    return 1;
+}
+
 typedef void (*generic_kernel_t)(const SwsCudaPlan, const FrameArgs);
 
 static generic_kernel_t pick_generic(const SwsCudaPlan *p)
@@ -819,6 +940,9 @@ extern "C" int ff_b200_cuda_create(SwsCudaState **out, SwsCudaPlan *plan,
     ret = fast420_setup(st, vc);
     if (ret < 0)
         return ret;
+    ret = fast16_setup(st, vc);
+    if (ret < 0)
+        return ret;
     return 0;
 }
 
@@ -832,6 +956,7 @@ extern "C" void ff_b200_cuda_destroy(SwsCudaState *st)
     }
     cudaFree(st->tables);
     cudaFree(st->d_fast_rows);
+    cudaFree(st->d_fast16_rows);
     if (st->s_in) {
         cudaStreamDestroy(st->s_in);
         cudaStreamDestroy(st->s_out);
@@ -873,6 +998,9 @@ extern "C" int ff_b200_cuda_launch(SwsCudaState *st,
         CUDA_OK(cudaSetDevice(st->device));
     {
         int r = fast420_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);
+        if (r != 0)
+            return r < 0 ? r : 0;
+        r = fast16_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);
         if (r != 0)
             return r < 0 ? r : 0;
     }
