@@ -75,6 +75,8 @@ __device__ __forceinline__ int fetch(const uint8_t *row, int idx)
     return row[idx];
 }
 
+#include "sws_scale8.cuh"
+
 /* ------------------------------------------------------------------------
  * Generic fused tile kernel: table-driven H FIR -> (range) -> V FIR -> pack.
  *   SRC16   : source samples are 16-bit containers (9..16 bit depths)
@@ -498,6 +500,12 @@ struct SwsCudaState {
     const char *kernel_name;
     /* fast420 path */
     int fast_ok;
+    int s8_ok, s8_fs4, s8_tile_h, s8_nl_cap, s8_nc_cap, s8_seg_l, s8_seg_c;
+    size_t s8_smem;
+    void *s8_tables;
+    int *s8_hl_pos, *s8_hc_pos;
+    uint32_t *s8_hl_cl, *s8_hl_ch, *s8_hc_cl, *s8_hc_ch;
+    S8VRow *s8_vl, *s8_vc;
     int fast16_ok, fast16_taps;
     Fast16Row *d_fast16_rows;
     int e2e_mode, e2e_bands; /* how sws_scale() moves page-locked host frames (see scale_host)  */
@@ -872,6 +880,212 @@ static int fast16_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     return 1;
 }
 
+
+/* ---------------------------------------------------------------- scale8 host side */
+
+typedef void (*scale8_kernel_t)(const Scale8Args);
+static scale8_kernel_t pick_scale8(int fs4)
+{
+    return fs4 == 1 ? sws_scale8_kernel<1> : fs4 == 2 ? sws_scale8_kernel<2> : sws_scale8_kernel<4>;
+}
+
+/* pack one horizontal bank: per output, fs4 words of low bytes and fs4 words of high bytes */
+static void s8_pack_h(const SwsFirBank *b, int fs4, uint32_t *cl, uint32_t *ch)
+{
+    for (int x = 0; x < b->len; x++)
+        for (int k = 0; k < fs4; k++) {
+            uint32_t l = 0, h = 0;
+            for (int t = 0; t < 4; t++) {
+                const int j = 4 * k + t;
+                const int c = j < b->size ? b->coef[(size_t)x * b->size + j] : 0;
+                l |= (uint32_t)(c & 0xFF) << (8 * t);
+                h |= (uint32_t)((c >> 8) & 0xFF) << (8 * t);
+            }
+            cl[(size_t)x * fs4 + k] = l;
+            ch[(size_t)x * fs4 + k] = h;
+        }
+}
+
+/* vertical bank: even first row, leading zero tap when the true first row is odd */
+static int s8_pack_v(const SwsFirBank *b, S8VRow *rows)
+{
+    for (int y = 0; y < b->len; y++) {
+        const int par = b->pos[y] & 1;
+        const int n = b->size + par;
+        S8VRow *r = &rows[y];
+        memset(r, 0, sizeof(*r));
+        r->pos_even = b->pos[y] - par;
+        r->n4 = (n + 3) / 4;
+        if (r->n4 > S8_VF4 || b->pos[y] < 0)
+            return -1;
+        for (int j = 0; j < b->size; j++) {
+            const int c = b->coef[(size_t)y * b->size + j];
+            const int t = j + par;
+            r->cl[t >> 2] |= (uint32_t)(c & 0xFF) << (8 * (t & 3));
+            r->ch[t >> 2] |= (uint32_t)((c >> 8) & 0xFF) << (8 * (t & 3));
+        }
+    }
+    return 0;
+}
+
+/* rows of transposed h-scaled lines any window of th output rows needs; == 2 (mod 4) for bank spread */
+static int s8_rows_cap(const S8VRow *rows, int n, int th)
+{
+    int worst = 4;
+    for (int y = 0; y < n; y++) {
+        const int y1 = y + th < n ? y + th : n;
+        int lo = INT32_MAX, hi = 0;
+        for (int k = y; k < y1; k++) {
+            if (rows[k].pos_even < lo) lo = rows[k].pos_even;
+            if (rows[k].pos_even + 4 * rows[k].n4 > hi) hi = rows[k].pos_even + 4 * rows[k].n4;
+        }
+        if (hi - lo > worst) worst = hi - lo;
+    }
+    while ((worst & 3) != 2)
+        worst++;
+    return worst;
+}
+
+static int s8_seg_bytes(const SwsFirBank *b, int fs4, int tile_cols)
+{
+    int worst = 16;
+    for (int x0 = 0; x0 < b->len; x0 += tile_cols) {
+        const int x1 = x0 + tile_cols - 1 < b->len - 1 ? x0 + tile_cols - 1 : b->len - 1;
+        const int a0 = b->pos[x0] & ~15;
+        int need = 0;
+        for (int x = x0; x <= x1; x++) {      /* positions are monotonic, but be safe */
+            if (b->pos[x] < b->pos[x0])
+                return -1;
+            const int e = ((b->pos[x] - a0) & ~3) + 4 * fs4 + 4;
+            if (e > need) need = e;
+        }
+        need = (need + 15) & ~15;
+        if (need > worst) worst = need;
+    }
+    return worst;
+}
+
+static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank *hc,
+                        const SwsFirBank *vl, const SwsFirBank *vc)
+{
+    const SwsCudaPlan *p = &st->plan;
+    st->s8_ok = 0;
+    if (p->src_bits != 8 || p->inter_bits != 15 || p->range_mode)
+        return 0;
+    if (p->dst_kind != SWSC_DST_PLANAR8 && p->dst_kind != SWSC_DST_NV12 && p->dst_kind != SWSC_DST_NV21)
+        return 0;
+    if (hl->size > 16 || hc->size > 16 || vl->size > 16 || vc->size > 16)
+        return 0;
+    if (hl->size > p->src_w || hc->size > p->chr_src_w || p->chr_dst_hsub > 1 || p->chr_dst_vsub > 1)
+        return 0;
+    const int fs = hl->size > hc->size ? hl->size : hc->size;
+    const int fs4 = fs <= 4 ? 1 : fs <= 8 ? 2 : 4;
+    const int cw = S8_TW >> p->chr_dst_hsub;
+
+    S8VRow *hvl = (S8VRow *)malloc(sizeof(S8VRow) * vl->len);
+    S8VRow *hvc = (S8VRow *)malloc(sizeof(S8VRow) * vc->len);
+    int ret = 0;
+    if (!hvl || !hvc || s8_pack_v(vl, hvl) < 0 || s8_pack_v(vc, hvc) < 0)
+        ret = 1;
+    const int seg_l = ret ? -1 : s8_seg_bytes(hl, fs4, S8_TW);
+    const int seg_c = ret ? -1 : s8_seg_bytes(hc, fs4, cw);
+    if (seg_l < 0 || seg_c < 0)
+        ret = 1;
+    int th = 0, nl_cap = 0, nc_cap = 0;
+    size_t smem = 0;
+    if (!ret) {
+        ret = 1;
+        for (th = 32; th >= 2; th >>= 1) {
+            const int cth = th >> p->chr_dst_vsub ? th >> p->chr_dst_vsub : 1;
+            nl_cap = s8_rows_cap(hvl, vl->len, th);
+            nc_cap = s8_rows_cap(hvc, vc->len, cth);
+            const int stage = S8_CH * (seg_l > 2 * seg_c ? seg_l : 2 * seg_c);
+            smem = ((size_t)S8_TW * nl_cap + 2 * (size_t)cw * nc_cap) * 2 + stage;
+            if (smem <= 100 * 1024) {
+                ret = 0;
+                break;
+            }
+        }
+    }
+    if (ret) {
+        free(hvl); free(hvc);
+        return 0;                     /* not eligible: the generic kernel handles it */
+    }
+    /* one device allocation: positions, packed H taps, V rows */
+    size_t off = 0, o_hlp, o_hcp, o_hlcl, o_hlch, o_hccl, o_hcch, o_vl, o_vc;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+    o_hlp = take(sizeof(int) * hl->len); o_hcp = take(sizeof(int) * hc->len);
+    o_hlcl = take(4 * (size_t)hl->len * fs4); o_hlch = take(4 * (size_t)hl->len * fs4);
+    o_hccl = take(4 * (size_t)hc->len * fs4); o_hcch = take(4 * (size_t)hc->len * fs4);
+    o_vl = take(sizeof(S8VRow) * vl->len); o_vc = take(sizeof(S8VRow) * vc->len);
+    uint8_t *host = (uint8_t *)calloc(1, off);
+    if (!host) {
+        free(hvl); free(hvc);
+        return AVERROR(ENOMEM);
+    }
+    memcpy(host + o_hlp, hl->pos, sizeof(int) * hl->len);
+    memcpy(host + o_hcp, hc->pos, sizeof(int) * hc->len);
+    s8_pack_h(hl, fs4, (uint32_t *)(host + o_hlcl), (uint32_t *)(host + o_hlch));
+    s8_pack_h(hc, fs4, (uint32_t *)(host + o_hccl), (uint32_t *)(host + o_hcch));
+    memcpy(host + o_vl, hvl, sizeof(S8VRow) * vl->len);
+    memcpy(host + o_vc, hvc, sizeof(S8VRow) * vc->len);
+    free(hvl); free(hvc);
+    cudaError_t e = cudaMalloc(&st->s8_tables, off);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(st->s8_tables, host, off, cudaMemcpyHostToDevice);
+    free(host);
+    CUDA_OK(e);
+    uint8_t *t = (uint8_t *)st->s8_tables;
+    st->s8_hl_pos = (int *)(t + o_hlp); st->s8_hc_pos = (int *)(t + o_hcp);
+    st->s8_hl_cl = (uint32_t *)(t + o_hlcl); st->s8_hl_ch = (uint32_t *)(t + o_hlch);
+    st->s8_hc_cl = (uint32_t *)(t + o_hccl); st->s8_hc_ch = (uint32_t *)(t + o_hcch);
+    st->s8_vl = (S8VRow *)(t + o_vl); st->s8_vc = (S8VRow *)(t + o_vc);
+    st->s8_fs4 = fs4; st->s8_tile_h = th; st->s8_nl_cap = nl_cap; st->s8_nc_cap = nc_cap;
+    st->s8_seg_l = seg_l; st->s8_seg_c = seg_c; st->s8_smem = smem;
+    CUDA_OK(cudaFuncSetAttribute((const void *)pick_scale8(fs4), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    st->s8_ok = 1;
+    if (!st->fast_ok && !st->fast16_ok)
+        st->kernel_name = "scale8_dp4a";
+    return 0;
+}
+
+static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const int src_stride[4],
+                         const int64_t src_fstride[4], uint8_t *const dst[4], const int dst_stride[4],
+                         const int64_t dst_fstride[4], int nb_frames, int y0, int y1, cudaStream_t stream)
+{
+    const SwsCudaPlan *p = &st->plan;
+    if (!st->s8_ok)
+        return 0;
+    const int nsrc = p->src_layout == SWSC_SRC_PLANAR ? 3 : 2;
+    for (int i = 0; i < nsrc; i++)
+        if (!src[i] || !aligned16(src[i]) || (src_stride[i] & 15) || src_stride[i] < 16 ||
+            (nb_frames > 1 && (src_fstride[i] & 15)))
+            return 0;
+    Scale8Args a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 3; i++) {
+        a.src[i] = src[i]; a.dst[i] = dst[i];
+        a.src_stride[i] = src_stride[i]; a.dst_stride[i] = dst_stride[i];
+        a.src_fstride[i] = src_fstride ? src_fstride[i] : 0;
+        a.dst_fstride[i] = dst_fstride ? dst_fstride[i] : 0;
+    }
+    a.src_w = p->src_w; a.src_h = p->src_h; a.chr_src_w = p->chr_src_w; a.chr_src_h = p->chr_src_h;
+    a.dst_w = p->dst_w; a.dst_h = p->dst_h; a.chr_dst_w = p->chr_dst_w; a.chr_dst_h = p->chr_dst_h;
+    a.hs = p->chr_dst_hsub; a.vs = p->chr_dst_vsub;
+    a.src_layout = p->src_layout; a.dst_kind = p->dst_kind;
+    a.y0 = y0; a.y1 = y1; a.tile_h = st->s8_tile_h;
+    a.nl_cap = st->s8_nl_cap; a.nc_cap = st->s8_nc_cap; a.seg_l = st->s8_seg_l; a.seg_c = st->s8_seg_c;
+    a.hl_pos = st->s8_hl_pos; a.hc_pos = st->s8_hc_pos;
+    a.hl_cl = st->s8_hl_cl; a.hl_ch = st->s8_hl_ch; a.hc_cl = st->s8_hc_cl; a.hc_ch = st->s8_hc_ch;
+    a.vl = st->s8_vl; a.vc = st->s8_vc;
+    dim3 grid((p->dst_w + S8_TW - 1) / S8_TW, (y1 - y0 + st->s8_tile_h - 1) / st->s8_tile_h, nb_frames);
+    pick_scale8(st->s8_fs4)<<<grid, 256, st->s8_smem, stream>>>(a);
+    CUDA_OK(cudaGetLastError());
+    st->launches++;
+    return 1;
+}
+
 typedef void (*generic_kernel_t)(const SwsCudaPlan, const FrameArgs);
 
 static generic_kernel_t pick_generic(const SwsCudaPlan *p)
@@ -943,6 +1157,9 @@ extern "C" int ff_b200_cuda_create(SwsCudaState **out, SwsCudaPlan *plan,
     ret = fast16_setup(st, vc);
     if (ret < 0)
         return ret;
+    ret = scale8_setup(st, hl, hc, vl, vc);
+    if (ret < 0)
+        return ret;
     return 0;
 }
 
@@ -957,6 +1174,7 @@ extern "C" void ff_b200_cuda_destroy(SwsCudaState *st)
     cudaFree(st->tables);
     cudaFree(st->d_fast_rows);
     cudaFree(st->d_fast16_rows);
+    cudaFree(st->s8_tables);
     if (st->s_in) {
         cudaStreamDestroy(st->s_in);
         cudaStreamDestroy(st->s_out);
@@ -1001,6 +1219,9 @@ extern "C" int ff_b200_cuda_launch(SwsCudaState *st,
         if (r != 0)
             return r < 0 ? r : 0;
         r = fast16_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);
+        if (r != 0)
+            return r < 0 ? r : 0;
+        r = scale8_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);
         if (r != 0)
             return r < 0 ? r : 0;
     }
