@@ -991,6 +991,8 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     const int seg_c = ret ? -1 : s8_seg_bytes(hc, fs4, cw);
     if (seg_l < 0 || seg_c < 0)
         ret = 1;
+    else if (S8_CH * (seg_l >> 4) > S8_PRE * 256 || 2 * S8_CH * (seg_c >> 4) > S8_PRE * 256)
+        ret = 1;                      /* a staging pass must fit the per-thread prefetch registers */
     int th = 0, nl_cap = 0, nc_cap = 0;
     size_t smem = 0;
     if (!ret) {

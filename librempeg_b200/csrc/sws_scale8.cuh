@@ -20,7 +20,8 @@
 #pragma once
 
 #define S8_TW 128
-#define S8_CH 8          /* source rows staged per pass */
+#define S8_CH 16         /* source rows staged per pass */
+#define S8_PRE 4         /* 16-byte loads a thread keeps in flight for the next pass */
 #define S8_VF4 5         /* vertical taps: up to 5 groups of 4 (16 taps + parity pad) */
 
 struct S8VRow {          /* per destination row, 48 bytes */
@@ -180,16 +181,36 @@ sws_scale8_kernel(const __grid_constant__ Scale8Args A)
         }
         const int nchunk = A.seg_l >> 4;
         const int last16 = (A.src_stride[0] - 16) & ~15;
+        const int per_pass = S8_CH * nchunk;
+        uint4 pre[S8_PRE];
+        /* software pipeline: the loads of pass k+1 are in flight while pass k is filtered */
+        auto fetch = [&](int r) {
+#pragma unroll
+            for (int q = 0; q < S8_PRE; q++) {
+                const int i = tid + q * 256;
+                if (i < per_pass) {
+                    const int row = i / nchunk, c = i - row * nchunk;
+                    const int sr = min(lo_l + r + row, A.src_h - 1);
+                    pre[q] = __ldg(reinterpret_cast<const uint4 *>(src0 + (size_t)sr * A.src_stride[0] +
+                                                                    min(a0 + 16 * c, last16)));
+                }
+            }
+        };
+        if (nl > 0)
+            fetch(0);
         for (int r = 0; r < nl; r += S8_CH) {
             __syncthreads();
-            for (int i = tid; i < S8_CH * nchunk; i += 256) {
-                const int row = i / nchunk, c = i - row * nchunk;
-                const int sr = min(lo_l + r + row, A.src_h - 1);
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src0 + (size_t)sr * A.src_stride[0] +
-                                                                       min(a0 + 16 * c, last16)));
-                *reinterpret_cast<uint4 *>(stage + row * A.seg_l + 16 * c) = v;
+#pragma unroll
+            for (int q = 0; q < S8_PRE; q++) {
+                const int i = tid + q * 256;
+                if (i < per_pass) {
+                    const int row = i / nchunk, c = i - row * nchunk;
+                    *reinterpret_cast<uint4 *>(stage + row * A.seg_l + 16 * c) = pre[q];
+                }
             }
             __syncthreads();
+            if (r + S8_CH < nl)
+                fetch(r + S8_CH);
             for (int rr = g; rr < S8_CH && r + rr < nl; rr += 2) {
                 const int val = s8_hfir<FS4>(stage + rr * A.seg_l + (off & ~3), sh, cl, chh);
                 if (x < tw)
@@ -214,35 +235,57 @@ sws_scale8_kernel(const __grid_constant__ Scale8Args A)
         int16_t *hb = pl ? hb_v : hb_u;
         const bool planar = A.src_layout == SWSC_SRC_PLANAR;
         const int uo = A.src_layout == SWSC_SRC_NV21 ? 1 : 0;     /* nv21: V first */
+        const int nchunk = planar ? A.seg_c >> 4 : A.seg_c >> 3;
+        const int per_pass = (planar ? 2 : 1) * S8_CH * nchunk;
+        const int last16 = (A.src_stride[1] - 16) & ~15;
+        uint4 pre[S8_PRE];
+        auto fetch = [&](int r) {
+#pragma unroll
+            for (int q = 0; q < S8_PRE; q++) {
+                const int i = tid + q * 256;
+                if (i < per_pass) {
+                    if (planar) {
+                        const int p = i / (S8_CH * nchunk), j = i - p * (S8_CH * nchunk);
+                        const int row = j / nchunk, c = j - row * nchunk;
+                        const int sr = min(lo_c + r + row, A.chr_src_h - 1);
+                        const uint8_t *base = p ? src2 + (size_t)sr * A.src_stride[2]
+                                                : src1 + (size_t)sr * A.src_stride[1];
+                        pre[q] = __ldg(reinterpret_cast<const uint4 *>(base + min(a0 + 16 * c, last16)));
+                    } else {
+                        const int row = i / nchunk, c = i - row * nchunk;
+                        const int sr = min(lo_c + r + row, A.chr_src_h - 1);
+                        pre[q] = __ldg(reinterpret_cast<const uint4 *>(src1 + (size_t)sr * A.src_stride[1] +
+                                                                        min(2 * a0 + 16 * c, last16)));
+                    }
+                }
+            }
+        };
+        if (nc > 0)
+            fetch(0);
         for (int r = 0; r < nc; r += S8_CH) {
             __syncthreads();
-            if (planar) {
-                const int nchunk = A.seg_c >> 4;
-                const int last16 = (A.src_stride[1] - 16) & ~15;
-                for (int i = tid; i < 2 * S8_CH * nchunk; i += 256) {
-                    const int p = i / (S8_CH * nchunk), j = i - p * (S8_CH * nchunk);
-                    const int row = j / nchunk, c = j - row * nchunk;
-                    const int sr = min(lo_c + r + row, A.chr_src_h - 1);
-                    const uint8_t *base = p ? src2 + (size_t)sr * A.src_stride[2] : src1 + (size_t)sr * A.src_stride[1];
-                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base + min(a0 + 16 * c, last16)));
-                    *reinterpret_cast<uint4 *>(stage + (p * S8_CH + row) * A.seg_c + 16 * c) = v;
-                }
-            } else {
-                /* nv12 / nv21: 16 interleaved bytes -> 8 U + 8 V (input.c:926-941) */
-                const int nchunk = A.seg_c >> 3;
-                const int last16 = (A.src_stride[1] - 16) & ~15;
-                for (int i = tid; i < S8_CH * nchunk; i += 256) {
-                    const int row = i / nchunk, c = i - row * nchunk;
-                    const int sr = min(lo_c + r + row, A.chr_src_h - 1);
-                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src1 + (size_t)sr * A.src_stride[1] +
-                                                                           min(2 * a0 + 16 * c, last16)));
-                    const uint2 e = make_uint2(prmt(v.x, v.y, 0x6420), prmt(v.z, v.w, 0x6420));
-                    const uint2 o = make_uint2(prmt(v.x, v.y, 0x7531), prmt(v.z, v.w, 0x7531));
-                    *reinterpret_cast<uint2 *>(stage + (uo * S8_CH + row) * A.seg_c + 8 * c) = e;
-                    *reinterpret_cast<uint2 *>(stage + ((1 - uo) * S8_CH + row) * A.seg_c + 8 * c) = o;
+#pragma unroll
+            for (int q = 0; q < S8_PRE; q++) {
+                const int i = tid + q * 256;
+                if (i < per_pass) {
+                    const uint4 v = pre[q];
+                    if (planar) {
+                        const int p = i / (S8_CH * nchunk), j = i - p * (S8_CH * nchunk);
+                        const int row = j / nchunk, c = j - row * nchunk;
+                        *reinterpret_cast<uint4 *>(stage + (p * S8_CH + row) * A.seg_c + 16 * c) = v;
+                    } else {
+                        /* nv12 / nv21: 16 interleaved bytes -> 8 U + 8 V (input.c:926-941) */
+                        const int row = i / nchunk, c = i - row * nchunk;
+                        const uint2 e = make_uint2(prmt(v.x, v.y, 0x6420), prmt(v.z, v.w, 0x6420));
+                        const uint2 o = make_uint2(prmt(v.x, v.y, 0x7531), prmt(v.z, v.w, 0x7531));
+                        *reinterpret_cast<uint2 *>(stage + (uo * S8_CH + row) * A.seg_c + 8 * c) = e;
+                        *reinterpret_cast<uint2 *>(stage + ((1 - uo) * S8_CH + row) * A.seg_c + 8 * c) = o;
+                    }
                 }
             }
             __syncthreads();
+            if (r + S8_CH < nc)
+                fetch(r + S8_CH);
             for (int rr = g; rr < S8_CH && r + rr < nc; rr += ngroups) {
                 const int val = s8_hfir<FS4>(stage + (pl * S8_CH + rr) * A.seg_c + (off & ~3), sh, cl, chh);
                 if (x < cw)
