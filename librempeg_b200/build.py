@@ -53,8 +53,9 @@ def build_native(force=False, verbose=False):
         src = os.path.join(CSRC, s)
         obj = os.path.join(CSRC, s[:-3] + ".o")
         if force or _newer(obj, [src] + headers):
+            extra = os.environ.get("SWS_B200_NVCC_DEFS", "").split()
             log += _run(["nvcc"] + NVCC_ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-                                                "-Xptxas", "-v"] + inc + ["-c", src, "-o", obj])
+                                                "-Xptxas", "-v"] + extra + inc + ["-c", src, "-o", obj])
         objs.append(obj)
     if force or _newer(SO_PATH, objs):
         log += _run(["nvcc"] + NVCC_ARCH + ["-shared", "-o", SO_PATH] + objs +

@@ -638,19 +638,56 @@ static int make_map_3d(CUtensorMap *m, CUtensorMapDataType dt, const void *base,
     return 0;
 }
 
+typedef void (*fast420_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                                 const Fast420Args);
+
+static int fast420_fmt(int dst_kind)
+{
+    switch (dst_kind) {
+    case SWSC_DST_RGB24: return F420_RGB24;
+    case SWSC_DST_BGR24: return F420_BGR24;
+    case SWSC_DST_RGBA:  return F420_RGBA;
+    case SWSC_DST_BGRA:  return F420_BGRA;
+    case SWSC_DST_ARGB:  return F420_ARGB;
+    default:             return F420_ABGR;
+    }
+}
+
+template <int FMT>
+static fast420_kernel_t pick_fast420_src(int layout)
+{
+    return layout == SWSC_SRC_PLANAR ? sws_fast420_rgb8_kernel<FMT, F420_PLANAR>
+         : layout == SWSC_SRC_NV12   ? sws_fast420_rgb8_kernel<FMT, F420_NV12>
+                                     : sws_fast420_rgb8_kernel<FMT, F420_NV21>;
+}
+
+static fast420_kernel_t pick_fast420(int fmt, int layout)
+{
+    switch (fmt) {
+    case F420_RGB24: return pick_fast420_src<F420_RGB24>(layout);
+    case F420_BGR24: return pick_fast420_src<F420_BGR24>(layout);
+    case F420_RGBA:  return pick_fast420_src<F420_RGBA>(layout);
+    case F420_BGRA:  return pick_fast420_src<F420_BGRA>(layout);
+    case F420_ARGB:  return pick_fast420_src<F420_ARGB>(layout);
+    default:         return pick_fast420_src<F420_ABGR>(layout);
+    }
+}
+
 /* decide at init whether the conversion qualifies for the fast420 kernel and build its row table */
 static int fast420_setup(SwsCudaState *st, const SwsFirBank *vc)
 {
     const SwsCudaPlan *p = &st->plan;
     st->fast_ok = 0;
-    if (p->src_layout != SWSC_SRC_PLANAR || p->src_bits != 8 || p->inter_bits != 15)
+    if (p->src_bits != 8 || p->inter_bits != 15)
         return 0;
-    if (p->dst_kind != SWSC_DST_RGB24 && p->dst_kind != SWSC_DST_BGR24)
+    if (p->dst_kind < SWSC_DST_RGB24 || p->dst_kind > SWSC_DST_ABGR || p->full_chr)
         return 0;
     if (!p->lum_identity || !p->chr_h_identity || p->chr_src_hsub != 1 || p->chr_dst_hsub != 1)
         return 0;
-    if (vc->size > 4 || p->range_mode || (p->dst_w & 3) || !get_encode_tiled())
+    if (vc->size > 4 || p->range_mode || !get_encode_tiled())
         return 0;
+    if ((p->dst_kind == SWSC_DST_RGB24 || p->dst_kind == SWSC_DST_BGR24) && (p->dst_w & 3))
+        return 0;                     /* the store tensor map counts 32-bit words */
     if (max_rows_needed(vc->pos, vc->size > 4 ? vc->size : 4, vc->len, F420_TH) > F420_CROWS)
         return 0;
     const int padded = ((vc->len + F420_TH - 1) / F420_TH + 1) * F420_TH;
@@ -691,10 +728,11 @@ static int fast420_setup(SwsCudaState *st, const SwsFirBank *vc)
         e = cudaMemcpy(st->d_fast_rows, rows, sizeof(int4) * padded, cudaMemcpyHostToDevice);
     free(rows);
     CUDA_OK(e);
-    CUDA_OK(cudaFuncSetAttribute((const void *)sws_fast420_rgb8_kernel<false>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, F420_SMEM));
-    CUDA_OK(cudaFuncSetAttribute((const void *)sws_fast420_rgb8_kernel<true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, F420_SMEM));
+    {
+        const int fmt = fast420_fmt(p->dst_kind);
+        CUDA_OK(cudaFuncSetAttribute((const void *)pick_fast420(fmt, p->src_layout),
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, F420_SMEM(fmt >= F420_RGBA ? 4 : 3)));
+    }
     st->fast_ok = 1;
     {
         const char *e = getenv("SWS_B200_E2E_MODE"), *b = getenv("SWS_B200_E2E_BANDS");
@@ -718,8 +756,11 @@ static int fast420_launch(SwsCudaState *st, const uint8_t *const src[4], const i
     /* row ranges must start on a tile row; the end is clipped by the store tensor map */
     if (!st->fast_ok || (y0 % F420_TH) || y1 <= y0 || y1 > p->dst_h)
         return 0;
-    for (int i = 0; i < 3; i++)
-        if (!aligned16(src[i]) || (src_stride[i] & 15) || src_stride[i] <= 0 ||
+    const bool planar = p->src_layout == SWSC_SRC_PLANAR;
+    const int fmt = fast420_fmt(p->dst_kind);
+    const int bpp = fmt >= F420_RGBA ? 4 : 3;
+    for (int i = 0; i < (planar ? 3 : 2); i++)
+        if (!src[i] || !aligned16(src[i]) || (src_stride[i] & 15) || src_stride[i] <= 0 ||
             (nb_frames > 1 && (src_fstride[i] & 15 || src_fstride[i] <= 0)))
             return 0;
     if (!aligned16(dst[0]) || (dst_stride[0] & 15) || dst_stride[0] <= 0 ||
@@ -728,17 +769,27 @@ static int fast420_launch(SwsCudaState *st, const uint8_t *const src[4], const i
     CUtensorMap my, mu, mv, mo;
     const uint64_t fs_y = nb_frames > 1 ? src_fstride[0] : (uint64_t)src_stride[0] * p->src_h;
     const uint64_t fs_u = nb_frames > 1 ? src_fstride[1] : (uint64_t)src_stride[1] * p->chr_src_h;
-    const uint64_t fs_v = nb_frames > 1 ? src_fstride[2] : (uint64_t)src_stride[2] * p->chr_src_h;
     const uint64_t fs_o = nb_frames > 1 ? dst_fstride[0] : (uint64_t)dst_stride[0] * p->dst_h;
     int ret;
     if ((ret = make_map_3d(&my, CU_TENSOR_MAP_DATA_TYPE_UINT8, src[0], p->src_w, p->src_h, nb_frames,
-                           src_stride[0], fs_y, F420_TW, F420_TH)) < 0 ||
-        (ret = make_map_3d(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT8, src[1], p->chr_src_w, p->chr_src_h, nb_frames,
-                           src_stride[1], fs_u, F420_TW / 2, F420_CROWS)) < 0 ||
-        (ret = make_map_3d(&mv, CU_TENSOR_MAP_DATA_TYPE_UINT8, src[2], p->chr_src_w, p->chr_src_h, nb_frames,
-                           src_stride[2], fs_v, F420_TW / 2, F420_CROWS)) < 0 ||
-        (ret = make_map_3d(&mo, CU_TENSOR_MAP_DATA_TYPE_UINT32, dst[0], (uint64_t)p->dst_w * 3 / 4, y1,
-                           nb_frames, dst_stride[0], fs_o, F420_TW * 3 / 4, F420_TH / F420_CWARPS)) < 0)
+                           src_stride[0], fs_y, F420_TW, F420_TH)) < 0)
+        return ret;
+    if (planar) {
+        const uint64_t fs_v = nb_frames > 1 ? src_fstride[2] : (uint64_t)src_stride[2] * p->chr_src_h;
+        if ((ret = make_map_3d(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT8, src[1], p->chr_src_w, p->chr_src_h, nb_frames,
+                               src_stride[1], fs_u, F420_TW / 2, F420_CROWS)) < 0 ||
+            (ret = make_map_3d(&mv, CU_TENSOR_MAP_DATA_TYPE_UINT8, src[2], p->chr_src_w, p->chr_src_h, nb_frames,
+                               src_stride[2], fs_v, F420_TW / 2, F420_CROWS)) < 0)
+            return ret;
+    } else {
+        /* interleaved UV plane: 2 bytes per chroma sample, one 256-byte box row per tile row */
+        if ((ret = make_map_3d(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT8, src[1], 2 * (uint64_t)p->chr_src_w,
+                               p->chr_src_h, nb_frames, src_stride[1], fs_u, F420_TW, F420_CROWS)) < 0)
+            return ret;
+        mv = mu;
+    }
+    if ((ret = make_map_3d(&mo, CU_TENSOR_MAP_DATA_TYPE_UINT32, dst[0], (uint64_t)p->dst_w * bpp / 4, y1,
+                           nb_frames, dst_stride[0], fs_o, F420_TW * bpp / 4, F420_TH / F420_CWARPS)) < 0)
         return ret;
     Fast420Args a;
     a.tiles_x = (p->dst_w + F420_TW - 1) / F420_TW;
@@ -746,17 +797,14 @@ static int fast420_launch(SwsCudaState *st, const uint8_t *const src[4], const i
     a.ty_first = y0 / F420_TH;
     a.frames = nb_frames;
     a.dst_h = p->dst_h;
-    a.bgr = p->dst_kind == SWSC_DST_BGR24;
     a.cy = p->rgb.cy; a.yb = p->rgb.yb;
     a.crv = p->rgb.crv; a.cbu = p->rgb.cbu; a.cgu = p->rgb.cgu; a.cgv = p->rgb.cgv;
     a.kr = p->rgb.base_r << 16; a.kg = p->rgb.base_g << 16; a.kb = p->rgb.base_b << 16;
     a.rows = st->d_fast_rows;
     const long long total = (long long)a.tiles_x * a.tiles_y * nb_frames;
-    const int grid = (int)(total < (long long)st->num_sms * 4 ? total : (long long)st->num_sms * 4);
-    if (a.bgr)
-        sws_fast420_rgb8_kernel<true><<<grid, F420_THREADS, F420_SMEM, stream>>>(my, mu, mv, mo, a);
-    else
-        sws_fast420_rgb8_kernel<false><<<grid, F420_THREADS, F420_SMEM, stream>>>(my, mu, mv, mo, a);
+    const int grid = (int)(total < (long long)st->num_sms * F420_CTAS_PER_SM ? total : (long long)st->num_sms * F420_CTAS_PER_SM);
+    pick_fast420(fmt, p->src_layout)<<<grid, F420_THREADS, F420_SMEM(bpp), stream>>>(my, mu, mv, mo, a);
+    st->kernel_name = "fast420_rgb8_tma";     /* the name always reports the last kernel launched */
     CUDA_OK(cudaGetLastError());
     st->launches++;
     return 1;
@@ -873,8 +921,9 @@ static int fast16_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.u2g = (unsigned)p->rgb.u2g; a.u2b = (unsigned)p->rgb.u2b;
     a.rows = st->d_fast16_rows;
     const long long total = (long long)a.tiles_x * a.tiles_y * nb_frames;
-    const int grid = (int)(total < (long long)st->num_sms * 4 ? total : (long long)st->num_sms * 4);
+    const int grid = (int)(total < (long long)st->num_sms * F420_CTAS_PER_SM ? total : (long long)st->num_sms * F420_CTAS_PER_SM);
     pick_fast16(st->fast16_taps, a.bgr)<<<grid, F420_THREADS, F16_SMEM, stream>>>(my, mu, mv, mo, a);
+    st->kernel_name = "fast420_rgb16_tma";
     CUDA_OK(cudaGetLastError());
     st->launches++;
     return 1;
@@ -1083,6 +1132,7 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.vl = st->s8_vl; a.vc = st->s8_vc;
     dim3 grid((p->dst_w + S8_TW - 1) / S8_TW, (y1 - y0 + st->s8_tile_h - 1) / st->s8_tile_h, nb_frames);
     pick_scale8(st->s8_fs4)<<<grid, 256, st->s8_smem, stream>>>(a);
+    st->kernel_name = "scale8_dp4a";
     CUDA_OK(cudaGetLastError());
     st->launches++;
     return 1;
@@ -1241,6 +1291,7 @@ extern "C" int ff_b200_cuda_launch(SwsCudaState *st,
     dim3 grid((st->plan.dst_w + st->tile_w - 1) / st->tile_w,
               (y1 - y0 + st->tile_h - 1) / st->tile_h, nb_frames);
     pick_generic(&st->plan)<<<grid, 256, st->smem_bytes, st->stream>>>(st->plan, a);
+    st->kernel_name = "generic_tile";
     CUDA_OK(cudaGetLastError());
     st->launches++;
     return 0;

@@ -33,15 +33,23 @@
 #define F420_C_BYTES ((F420_TW / 2) * F420_CROWS)                            /*  2560 */
 #define F420_META_BYTES (F420_TH * 16)                                       /*   512 */
 #define F420_IN_BYTES (F420_Y_BYTES + 2 * F420_C_BYTES + F420_META_BYTES)    /* 13824 */
-#define F420_OUT_BYTES (F420_TW * 3 * F420_TH)                               /* 24576 */
-#define F420_STAGES 2
-#define F420_SMEM (F420_STAGES * F420_IN_BYTES + F420_OUT_BYTES)
+#define F420_OUT_BYTES(bpp) (F420_TW * (bpp) * F420_TH)                      /* 24576 / 32768 */
+#ifndef F420_STAGES
+#define F420_STAGES 3          /* input ring depth (measured: 3 stages x 3 CTAs/SM beats 2 x 4 by 1.3 %) */
+#endif
+#ifndef F420_CTAS_PER_SM
+#define F420_CTAS_PER_SM 3
+#endif
+#define F420_SMEM(bpp) (F420_STAGES * F420_IN_BYTES + F420_OUT_BYTES(bpp))
+
+/* destination byte orders and source chroma layouts the kernel is instantiated for */
+enum { F420_RGB24 = 0, F420_BGR24, F420_RGBA, F420_BGRA, F420_ARGB, F420_ABGR };
+enum { F420_PLANAR = 0, F420_NV12, F420_NV21 };
 
 struct Fast420Args {
     int tiles_x, tiles_y, frames;
     int ty_first;                  /* first tile row of this launch (row-range launches) */
     int dst_h;
-    int bgr;                       /* 0: R,G,B byte order, 1: B,G,R */
     int cy, yb;                    /* LUT closed form (sws_colorspace.c) */
     int crv, cbu, cgu, cgv;
     int kr, kg, kb;                /* index bases << 16 */
@@ -71,7 +79,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
+#ifdef F420_WAIT_HINT
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+#endif
         "@p bra DONE;\n"
         "bra WAIT_LOOP;\n"
         "DONE:\n"
@@ -149,15 +161,16 @@ __device__ __forceinline__ void transpose4(uint32_t r0, uint32_t r1, uint32_t r2
     w[2] = prmt(c, d, 0x5410); w[3] = prmt(c, d, 0x7632);
 }
 
-template <bool BGR>
-__global__ void __launch_bounds__(F420_THREADS, 4)
+template <int FMT, int SRC>
+__global__ void __launch_bounds__(F420_THREADS, F420_CTAS_PER_SM)
 sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
                         const __grid_constant__ CUtensorMap map_u,
                         const __grid_constant__ CUtensorMap map_v,
                         const __grid_constant__ CUtensorMap map_o,
                         const __grid_constant__ Fast420Args A)
 {
-    /* [stage0: Y | U | V | row meta][stage1 ...][out: 8 warps x 4 rows]; TMA boxes 128-byte aligned */
+    constexpr int BPP = FMT >= F420_RGBA ? 4 : 3;
+    /* [stage: Y | U | V (or interleaved UV) | row meta] x STAGES, then [out: 8 warps x 4 rows] */
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[F420_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[F420_STAGES];
@@ -182,7 +195,8 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_u) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+            if (SRC == F420_PLANAR)
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
             int i = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
                 const int stage = i % F420_STAGES, k = i / F420_STAGES;
@@ -197,8 +211,12 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
                 tile_info[stage] = make_int4(tx, y0, f, 0);
                 mbar_expect_tx(&full_bar[stage], F420_IN_BYTES);
                 tma_load_3d(b, &map_y, &full_bar[stage], tx * F420_TW, y0, f);
-                tma_load_3d(b + F420_Y_BYTES, &map_u, &full_bar[stage], tx * (F420_TW / 2), c_lo, f);
-                tma_load_3d(b + F420_Y_BYTES + F420_C_BYTES, &map_v, &full_bar[stage], tx * (F420_TW / 2), c_lo, f);
+                if (SRC == F420_PLANAR) {
+                    tma_load_3d(b + F420_Y_BYTES, &map_u, &full_bar[stage], tx * (F420_TW / 2), c_lo, f);
+                    tma_load_3d(b + F420_Y_BYTES + F420_C_BYTES, &map_v, &full_bar[stage], tx * (F420_TW / 2), c_lo, f);
+                } else {   /* nv12 / nv21: one box of interleaved UV rows, same bytes */
+                    tma_load_3d(b + F420_Y_BYTES, &map_u, &full_bar[stage], tx * F420_TW, c_lo, f);
+                }
                 bulk_load_1d(b + F420_Y_BYTES + 2 * F420_C_BYTES, A.rows + y0, F420_META_BYTES, &full_bar[stage]);
             }
         }
@@ -212,8 +230,11 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
     const int crv = A.crv, cbu = A.cbu, cgu = A.cgu, cgv = A.cgv;
     const int kr = A.kr, kg = A.kg, kb = A.kb;
     const int r0 = warp * (F420_TH / F420_CWARPS);
-    unsigned char *so = smem_dyn + F420_STAGES * F420_IN_BYTES + r0 * (F420_TW * 3) + lane * 24;
-    unsigned char *so_warp = smem_dyn + F420_STAGES * F420_IN_BYTES + r0 * (F420_TW * 3);
+    unsigned char *so_warp = smem_dyn + F420_STAGES * F420_IN_BYTES + r0 * (F420_TW * BPP);
+    unsigned char *so = so_warp + lane * (8 * BPP);
+    /* chroma rows: planar = 128-byte U row + 128-byte V row (one word each per lane);
+     * semi-planar = one 256-byte UV row (two words per lane) */
+    constexpr int CSTRIDE = SRC == F420_PLANAR ? F420_TW / 2 : F420_TW;
 
     int i = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
@@ -224,15 +245,16 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
         const int4 ti = tile_info[stage];
         const int4 *mrow = reinterpret_cast<const int4 *>(sb + F420_Y_BYTES + 2 * F420_C_BYTES) + r0;
         const unsigned char *sy = sb + r0 * F420_TW + lane * 8;
-        const unsigned char *su = sb + F420_Y_BYTES + lane * 4;
-        const unsigned char *sv = su + F420_C_BYTES;
+        const unsigned char *sp = sb + F420_Y_BYTES + (SRC == F420_PLANAR ? lane * 4 : lane * 8);
+        const unsigned char *sq = SRC == F420_PLANAR ? sp + F420_C_BYTES : sp + 4;
 
         /* this warp's previous TMA store must have finished READING its staging rows */
         if (lane == 0)
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
 
-        uint32_t wu[4], wv[4];
+        /* P/Q: byte j of P[k] = source row j of byte lane k of the first / second chroma word */
+        uint32_t P[4], Q[4];
         int wpos = -64;                        /* chroma row (tile relative) held in window byte 0 */
 #pragma unroll
         for (int rr = 0; rr < F420_TH / F420_CWARPS; rr++) {
@@ -240,49 +262,85 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
             const int pos = meta.x;
             int d = pos - wpos;
             if (d < 0 || d >= 4) {             /* (re)fill: transpose rows pos..pos+3 */
-                const unsigned char *pu = su + pos * (F420_TW / 2), *pv = sv + pos * (F420_TW / 2);
-                transpose4(*reinterpret_cast<const uint32_t *>(pu), *reinterpret_cast<const uint32_t *>(pu + 128),
-                           *reinterpret_cast<const uint32_t *>(pu + 256), *reinterpret_cast<const uint32_t *>(pu + 384), wu);
-                transpose4(*reinterpret_cast<const uint32_t *>(pv), *reinterpret_cast<const uint32_t *>(pv + 128),
-                           *reinterpret_cast<const uint32_t *>(pv + 256), *reinterpret_cast<const uint32_t *>(pv + 384), wv);
+                const unsigned char *pp = sp + pos * CSTRIDE, *pq = sq + pos * CSTRIDE;
+                transpose4(*reinterpret_cast<const uint32_t *>(pp), *reinterpret_cast<const uint32_t *>(pp + CSTRIDE),
+                           *reinterpret_cast<const uint32_t *>(pp + 2 * CSTRIDE),
+                           *reinterpret_cast<const uint32_t *>(pp + 3 * CSTRIDE), P);
+                transpose4(*reinterpret_cast<const uint32_t *>(pq), *reinterpret_cast<const uint32_t *>(pq + CSTRIDE),
+                           *reinterpret_cast<const uint32_t *>(pq + 2 * CSTRIDE),
+                           *reinterpret_cast<const uint32_t *>(pq + 3 * CSTRIDE), Q);
             } else {
 #pragma unroll 1
                 for (int nr = wpos + 4; d > 0; d--, nr++) {   /* slide down one source row */
-                    const uint32_t nu = *reinterpret_cast<const uint32_t *>(su + nr * (F420_TW / 2));
-                    const uint32_t nv = *reinterpret_cast<const uint32_t *>(sv + nr * (F420_TW / 2));
-                    wu[0] = prmt(wu[0], nu, 0x4321); wu[1] = prmt(wu[1], nu, 0x5321);
-                    wu[2] = prmt(wu[2], nu, 0x6321); wu[3] = prmt(wu[3], nu, 0x7321);
-                    wv[0] = prmt(wv[0], nv, 0x4321); wv[1] = prmt(wv[1], nv, 0x5321);
-                    wv[2] = prmt(wv[2], nv, 0x6321); wv[3] = prmt(wv[3], nv, 0x7321);
+                    const uint32_t np = *reinterpret_cast<const uint32_t *>(sp + nr * CSTRIDE);
+                    const uint32_t nq = *reinterpret_cast<const uint32_t *>(sq + nr * CSTRIDE);
+                    P[0] = prmt(P[0], np, 0x4321); P[1] = prmt(P[1], np, 0x5321);
+                    P[2] = prmt(P[2], np, 0x6321); P[3] = prmt(P[3], np, 0x7321);
+                    Q[0] = prmt(Q[0], nq, 0x4321); Q[1] = prmt(Q[1], nq, 0x5321);
+                    Q[2] = prmt(Q[2], nq, 0x6321); Q[3] = prmt(Q[3], nq, 0x7321);
                 }
             }
             wpos = pos;
             const uint32_t clp = (uint32_t)meta.y, chp = (uint32_t)meta.z;
             const uint2 yw = *reinterpret_cast<const uint2 *>(sy + rr * F420_TW);
-            uint32_t h[12];
+            uint32_t h[BPP == 3 ? 12 : 16];
 #pragma unroll
             for (int c = 0; c < 4; c++) {
+                /* which window registers hold U and V of chroma column c */
+                const uint32_t wU = SRC == F420_PLANAR ? P[c]
+                                  : SRC == F420_NV12 ? (c < 2 ? P[2 * c] : Q[2 * c - 4])
+                                                     : (c < 2 ? P[2 * c + 1] : Q[2 * c - 3]);
+                const uint32_t wV = SRC == F420_PLANAR ? Q[c]
+                                  : SRC == F420_NV12 ? (c < 2 ? P[2 * c + 1] : Q[2 * c - 3])
+                                                     : (c < 2 ? P[2 * c] : Q[2 * c - 4]);
                 /* S + 2048 = 256*T + (L + 2048); both dot products are independent */
-                const int U = clamp_u8((dp4a_us(wu[c], chp, 0) * 256 + dp4a_uu(wu[c], clp, 2048)) >> 12);
-                const int V = clamp_u8((dp4a_us(wv[c], chp, 0) * 256 + dp4a_uu(wv[c], clp, 2048)) >> 12);
+                const int U = clamp_u8((dp4a_us(wU, chp, 0) * 256 + dp4a_uu(wU, clp, 2048)) >> 12);
+                const int V = clamp_u8((dp4a_us(wV, chp, 0) * 256 + dp4a_uu(wV, clp, 2048)) >> 12);
                 const int pr = ((V * crv + kr) >> 16) * cy + yb;
                 const int pb = ((U * cbu + kb) >> 16) * cy + yb;
                 const int pg = (((U * cgu) >> 16) + ((V * cgv + kg) >> 16)) * cy + yb;
                 const uint32_t w = (c < 2) ? yw.x : yw.y;
                 const int ya = prmt(w, 0u, 0x4440 + 2 * (c & 1));
                 const int yc = prmt(w, 0u, 0x4441 + 2 * (c & 1));
-                const int p0 = BGR ? pb : pr, p2 = BGR ? pr : pb;
-                const uint32_t t0a = ya * cy + p0, t1a = ya * cy + pg, t2a = ya * cy + p2;
-                const uint32_t t0b = yc * cy + p0, t1b = yc * cy + pg, t2b = yc * cy + p2;
+                const uint32_t tRa = ya * cy + pr, tGa = ya * cy + pg, tBa = ya * cy + pb;
+                const uint32_t tRb = yc * cy + pr, tGb = yc * cy + pg, tBb = yc * cy + pb;
                 /* high halves are (t >> 16) as s16: pack pairs, clamp both lanes at once */
-                h[3 * c + 0] = clamp_u8x2(prmt(t0a, t1a, 0x7632));
-                h[3 * c + 1] = clamp_u8x2(prmt(t2a, t0b, 0x7632));
-                h[3 * c + 2] = clamp_u8x2(prmt(t1b, t2b, 0x7632));
+                constexpr uint32_t FF = 0x00FF0000u;          /* high half = 255: the opaque alpha */
+                if (FMT == F420_RGB24) {
+                    h[3 * c + 0] = clamp_u8x2(prmt(tRa, tGa, 0x7632));
+                    h[3 * c + 1] = clamp_u8x2(prmt(tBa, tRb, 0x7632));
+                    h[3 * c + 2] = clamp_u8x2(prmt(tGb, tBb, 0x7632));
+                } else if (FMT == F420_BGR24) {
+                    h[3 * c + 0] = clamp_u8x2(prmt(tBa, tGa, 0x7632));
+                    h[3 * c + 1] = clamp_u8x2(prmt(tRa, tBb, 0x7632));
+                    h[3 * c + 2] = clamp_u8x2(prmt(tGb, tRb, 0x7632));
+                } else if (FMT == F420_RGBA) {
+                    h[4 * c + 0] = clamp_u8x2(prmt(tRa, tGa, 0x7632)); h[4 * c + 1] = clamp_u8x2(prmt(tBa, FF, 0x7632));
+                    h[4 * c + 2] = clamp_u8x2(prmt(tRb, tGb, 0x7632)); h[4 * c + 3] = clamp_u8x2(prmt(tBb, FF, 0x7632));
+                } else if (FMT == F420_BGRA) {
+                    h[4 * c + 0] = clamp_u8x2(prmt(tBa, tGa, 0x7632)); h[4 * c + 1] = clamp_u8x2(prmt(tRa, FF, 0x7632));
+                    h[4 * c + 2] = clamp_u8x2(prmt(tBb, tGb, 0x7632)); h[4 * c + 3] = clamp_u8x2(prmt(tRb, FF, 0x7632));
+                } else if (FMT == F420_ARGB) {
+                    h[4 * c + 0] = clamp_u8x2(prmt(FF, tRa, 0x7632)); h[4 * c + 1] = clamp_u8x2(prmt(tGa, tBa, 0x7632));
+                    h[4 * c + 2] = clamp_u8x2(prmt(FF, tRb, 0x7632)); h[4 * c + 3] = clamp_u8x2(prmt(tGb, tBb, 0x7632));
+                } else {
+                    h[4 * c + 0] = clamp_u8x2(prmt(FF, tBa, 0x7632)); h[4 * c + 1] = clamp_u8x2(prmt(tGa, tRa, 0x7632));
+                    h[4 * c + 2] = clamp_u8x2(prmt(FF, tBb, 0x7632)); h[4 * c + 3] = clamp_u8x2(prmt(tGb, tRb, 0x7632));
+                }
             }
-            uint2 *o = reinterpret_cast<uint2 *>(so + rr * (F420_TW * 3));
-            o[0] = make_uint2(prmt(h[0], h[1], 0x6420), prmt(h[2], h[3], 0x6420));
-            o[1] = make_uint2(prmt(h[4], h[5], 0x6420), prmt(h[6], h[7], 0x6420));
-            o[2] = make_uint2(prmt(h[8], h[9], 0x6420), prmt(h[10], h[11], 0x6420));
+            /* every h[] holds two bytes (at bits 0 and 16): gather four of them per output word */
+            if (BPP == 3) {
+                uint2 *o = reinterpret_cast<uint2 *>(so + rr * (F420_TW * 3));
+                o[0] = make_uint2(prmt(h[0], h[1], 0x6420), prmt(h[2], h[3], 0x6420));
+                o[1] = make_uint2(prmt(h[4], h[5], 0x6420), prmt(h[6], h[7], 0x6420));
+                o[2] = make_uint2(prmt(h[8], h[9], 0x6420), prmt(h[10], h[11], 0x6420));
+            } else {
+                uint4 *o = reinterpret_cast<uint4 *>(so + rr * (F420_TW * 4));
+                o[0] = make_uint4(prmt(h[0], h[1], 0x6420), prmt(h[2], h[3], 0x6420),
+                                  prmt(h[4], h[5], 0x6420), prmt(h[6], h[7], 0x6420));
+                o[1] = make_uint4(prmt(h[8], h[9], 0x6420), prmt(h[10], h[11], 0x6420),
+                                  prmt(h[12], h[13], 0x6420), prmt(h[14], h[15], 0x6420));
+            }
         }
 
         /* publish this warp's 4 rows: generic-proxy writes -> async proxy, one TMA store per warp;
@@ -291,7 +349,7 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
         __syncwarp();
         if (lane == 0) {
             mbar_arrive(&empty_bar[stage]);
-            tma_store_3d(&map_o, so_warp, ti.x * (F420_TW * 3 / 4), ti.y + r0, ti.z);
+            tma_store_3d(&map_o, so_warp, ti.x * (F420_TW * BPP / 4), ti.y + r0, ti.z);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }

@@ -50,7 +50,7 @@ __device__ __forceinline__ uint32_t pack_sat_s16(int hi, int lo)
 }
 
 template <int TAPS, bool BGR>
-__global__ void __launch_bounds__(F420_THREADS, 4)
+__global__ void __launch_bounds__(F420_THREADS, F420_CTAS_PER_SM)
 sws_fast420_rgb16_kernel(const __grid_constant__ CUtensorMap map_y,
                          const __grid_constant__ CUtensorMap map_u,
                          const __grid_constant__ CUtensorMap map_v,

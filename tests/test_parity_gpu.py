@@ -170,3 +170,17 @@ def test_full_chroma_rgb(sf, df, geom, flags):
     the arithmetic colour step of yuv2rgb_write_full (output.c:1998-2051) incl. the bias-free 2-tap variants."""
     sw, sh, dw, dh = geom
     _check(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags, seed=41)
+
+
+# ---- every instantiation of the same-size 8-bit 4:2:0 kernel (3 chroma layouts x 6 byte orders) ----
+@pytest.mark.parametrize("sf", ["yuv420p", "nv12", "nv21"])
+@pytest.mark.parametrize("df", ["rgb24", "bgr24", "rgba", "bgra", "argb", "abgr"])
+@pytest.mark.parametrize("geom,flags", [((644, 366), S.SWS_BICUBIC | BX),          # ragged right/bottom tiles
+                                        ((256, 34), S.SWS_BILINEAR | BX),
+                                        ((1280, 720), S.SWS_POINT | BX),
+                                        ((648, 360), S.SWS_BICUBIC)])
+def test_fast420_instantiations(sf, df, geom, flags):
+    w, h = geom
+    for mode in ("noise", "extreme"):
+        name = _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=flags, seed=77, mode=mode)
+        assert name.startswith("fast420"), name

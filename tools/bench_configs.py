@@ -24,6 +24,9 @@ CONFIGS = [
     ("C4 8K nv12->1080p yuv420p bicubic", 7680, 4320, "nv12", 1920, 1080, "yuv420p", S.SWS_BICUBIC | S.BX),
     ("C5 4K yuv420p->rgb24 bicubic", 3840, 2160, "yuv420p", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
     ("C5' 4K yuv420p->rgb24 default flags (LUT path)", 3840, 2160, "yuv420p", 3840, 2160, "rgb24", S.SWS_BICUBIC),
+    ("C5a 4K yuv420p->rgba bicubic", 3840, 2160, "yuv420p", 3840, 2160, "rgba", S.SWS_BICUBIC | S.BX),
+    ("C5n 4K nv12->rgb24 bicubic", 3840, 2160, "nv12", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
+    ("C5b 4K nv12->bgra bicubic", 3840, 2160, "nv12", 3840, 2160, "bgra", S.SWS_BICUBIC | S.BX),
     ("X1 1080p->4K yuv420p->rgb24 bicubic", 1920, 1080, "yuv420p", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
     ("X2 4K->1080p yuv420p->yuv420p bicubic", 3840, 2160, "yuv420p", 1920, 1080, "yuv420p", S.SWS_BICUBIC | S.BX),
 ]
