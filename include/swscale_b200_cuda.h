@@ -59,10 +59,13 @@ void  sws_cuda_host_free(void *ptr);
  * but skip the device upload.  sws_b200_get_filter(): which = 0 hLum, 1 hChr,
  * 2 vLum, 3 vChr; returns the tap count, coef is [len][taps] int16, pos [len]
  * (the tables of reference swscale_internal.h:437-448).  sws_b200_get_info():
- * out[0..5] = yuv2rgb y_offset,y_coeff,v2r,v2g,u2g,u2b (yuv2rgb.c:786-791), ... */
+ * out[0..5] = yuv2rgb y_offset,y_coeff,v2r,v2g,u2g,u2b (yuv2rgb.c:786-791), ...
+ * sws_b200_get_rgb2yuv(): {ry,gy,by,ru,gu,bu,rv,gv,bv}, the C entries of the reference's
+ * input_rgb2yuv_table (swscale_internal.h:467-476, utils.c:614-706); RGB sources only. */
 int sws_b200_plan_only(SwsContext *c);
 int sws_b200_get_filter(SwsContext *c, int which, const int16_t **coef, const int32_t **pos, int *len);
 int sws_b200_get_info(SwsContext *c, int out[32]);
+int sws_b200_get_rgb2yuv(SwsContext *c, int out[9]);
 
 #ifdef __cplusplus
 }

@@ -123,3 +123,49 @@ int ff_b200_rgb_consts(SwsRgbConsts *k, const int inv_table[4], int full_range,
     k->base_g = yoffs - (int32_t)(cgu >> 9) - (int32_t)(cgv >> 9);
     return 0;
 }
+
+/* ---------------------------------------------------------------- RGB -> YUV
+ * Nine 15-bit coefficients {ry,gy,by, ru,gu,bu, rv,gv,bv} for packed-RGB sources, derived from
+ * the DESTINATION matrix exactly as the reference does (fill_rgb2yuv_table, utils.c:614-706):
+ * the luma weights follow from inverting {crv,cbu,cgu,cgv}; always limited range (the full-range
+ * case is handled by the range conversion of the h-scaled lines).  BT.601 uses the classic
+ * rounded constants instead of the derived ones (utils.c:692-702). */
+static int64_t rounded_div(int64_t a, int64_t b)
+{
+    return (a >= 0 ? a + (b >> 1) : a - (b >> 1)) / b;
+}
+
+void ff_b200_rgb2yuv_table(int32_t out[9], const int table[4])
+{
+    const int64_t one = 65536, sh = 1 << 15;
+    const int64_t vr = table[0], ub = table[1], ug = -table[2], vg = -table[3];
+    const int64_t cy = one * 255 / 219;
+    const int64_t w = rounded_div(one * one * ug, ub);
+    const int64_t v = rounded_div(one * one * vg, vr);
+    const int64_t z = one * one - w - v;
+    const int64_t Cy = rounded_div(cy * z, one);
+    const int64_t Cu = rounded_div(ub * z, one);
+    const int64_t Cv = rounded_div(vr * z, one);
+
+    out[0] = (int32_t)-rounded_div(sh * v, Cy);
+    out[1] = (int32_t) rounded_div(sh * one * one, Cy);
+    out[2] = (int32_t)-rounded_div(sh * w, Cy);
+    out[3] = (int32_t) rounded_div(sh * v, Cu);
+    out[4] = (int32_t)-rounded_div(sh * one * one, Cu);
+    out[5] = (int32_t) rounded_div(sh * (z + w), Cu);
+    out[6] = (int32_t) rounded_div(sh * (v + z), Cv);
+    out[7] = (int32_t)-rounded_div(sh * one * one, Cv);
+    out[8] = (int32_t) rounded_div(sh * w, Cv);
+
+    if (!memcmp(table, yuv2rgb_coeffs[SWS_CS_DEFAULT], sizeof(yuv2rgb_coeffs[0]))) {
+        out[0] =  (int)(0.299 * 219 / 255 * (1 << 15) + 0.5);
+        out[1] =  (int)(0.587 * 219 / 255 * (1 << 15) + 0.5);
+        out[2] =  (int)(0.114 * 219 / 255 * (1 << 15) + 0.5);
+        out[3] = -(int)(0.169 * 224 / 255 * (1 << 15) + 0.5);
+        out[4] = -(int)(0.331 * 224 / 255 * (1 << 15) + 0.5);
+        out[5] =  (int)(0.500 * 224 / 255 * (1 << 15) + 0.5);
+        out[6] =  (int)(0.500 * 224 / 255 * (1 << 15) + 0.5);
+        out[7] = -(int)(0.419 * 224 / 255 * (1 << 15) + 0.5);
+        out[8] = -(int)(0.081 * 224 / 255 * (1 << 15) + 0.5);
+    }
+}

@@ -200,6 +200,8 @@ static void plan_range_convert(SwsInternal *c)
 
 static int plan_colorspace(SwsInternal *c)
 {
+    if (is_rgb(c->opts.src_format))
+        ff_b200_rgb2yuv_table(c->plan.rgb2yuv, c->dst_colorspace);
     if (!is_rgb(c->opts.dst_format))
         return 0;
     return ff_b200_rgb_consts(&c->plan.rgb, c->src_colorspace, c->opts.src_range,
@@ -392,6 +394,11 @@ static int init_single(SwsContext *sws, int with_device)
     }
     if (is_rgb(sws->dst_format) && !(flags & SWS_FULL_CHR_H_INT))
         c->chr_dst_hsub = 1;
+    /* packed RGB sources: chroma is read from horizontally summed pixel pairs unless the caller
+     * asks for full chroma input or the output needs the resolution (utils.c:1367-1390) */
+    if (is_rgb(sws->src_format) && !(srcW & 1) && !(flags & SWS_FULL_CHR_H_INP) &&
+        (dstW >> c->chr_dst_hsub) <= (srcW >> 1))
+        c->chr_src_hsub = 1;
 
     c->chr_src_w = ceil_rshift(srcW, c->chr_src_hsub);
     c->chr_src_h = ceil_rshift(srcH, c->chr_src_vsub);
@@ -399,6 +406,8 @@ static int init_single(SwsContext *sws, int with_device)
     c->chr_dst_h = ceil_rshift(dstH, c->chr_dst_vsub);
     c->src_bpc = sd->depth < 8 ? 8 : sd->depth;
     c->dst_bpc = dd->depth < 8 ? 8 : dd->depth;
+    if (is_rgb(sws->src_format))
+        c->src_bpc = 16;          /* the RGB readers emit 14-bit samples in 16-bit lines (utils.c:1407-1408) */
 
     chr_xinc = (((int64_t)c->chr_src_w << 16) + (c->chr_dst_w >> 1)) / c->chr_dst_w;
     chr_yinc = (((int64_t)c->chr_src_h << 16) + (c->chr_dst_h >> 1)) / c->chr_dst_h;
@@ -409,8 +418,21 @@ static int init_single(SwsContext *sws, int with_device)
     /* which special converter would the reference install? (utils.c:1624-1637,
      * swscale_unscaled.c:2392-2731) */
     c->unscaled_lut = 0;
+    c->special = SWSC_SPECIAL_NONE;
     if (unscaled && (sws->src_range == sws->dst_range || is_rgb(sws->dst_format))) {
         const int planar_yuv_pair = !is_rgb(sws->src_format) && !is_rgb(sws->dst_format);
+        if (is_rgb(sws->src_format) && is_rgb(sws->dst_format) && sd->depth == 8 && dd->depth == 8) {
+            /* rgbToRgbWrapper (findRgbConvFn, swscale_unscaled.c:1843-2060,2463-2466) and
+             * packedCopyWrapper for identical formats (:2689-2707).  With SWS_BITEXACT the reference
+             * refuses 24 -> rgba/bgra and lets the scaler do it (:1992-1996). */
+            const int s32 = sd->bpp == 32, d32 = dd->bpp == 32;
+            if (sws->src_format == sws->dst_format || s32 || !d32 || !(flags & SWS_BITEXACT) ||
+                sws->dst_format == AV_PIX_FMT_ARGB || sws->dst_format == AV_PIX_FMT_ABGR)
+                c->special = SWSC_SPECIAL_SHUFFLE;
+        }
+        if (sws->src_format == AV_PIX_FMT_BGR24 && sws->dst_format == AV_PIX_FMT_YUV420P &&
+            !(flags & SWS_ACCURATE_RND) && !(dstW & 1))
+            c->special = SWSC_SPECIAL_BGR24_YV12;     /* swscale_unscaled.c:2062-2077,2453-2457 */
         if ((sws->src_format == AV_PIX_FMT_YUV420P || sws->src_format == AV_PIX_FMT_YUV422P) &&
             is_rgb(sws->dst_format) && !(flags & SWS_ACCURATE_RND) &&
             (sws->dither == SWS_DITHER_BAYER || sws->dither == SWS_DITHER_AUTO) && !(dstH & 1)) {
@@ -423,6 +445,10 @@ static int init_single(SwsContext *sws, int with_device)
             set_error(c, "unscaled planar bit-depth conversion is not on the CUDA hot path yet");
             return AVERROR(ENOTSUP);
         }
+    }
+    if (!c->special && is_rgb(sws->src_format) && sd->bpp == 32 && is_rgb(sws->dst_format) && dd->bpp == 32) {
+        set_error(c, "carrying an alpha plane through the scaler is not on the CUDA hot path");
+        return AVERROR(ENOTSUP);
     }
     /* ---- FIR banks: horizontal 1<<14, vertical 1<<12 (utils.c:1681-1729) ---- */
     memset(&spec, 0, sizeof(spec));
@@ -474,15 +500,54 @@ static int init_single(SwsContext *sws, int with_device)
     p->dst_bits = c->dst_bpc;
     p->has_chroma = 1;
     p->unscaled_lut = c->unscaled_lut;
+    p->special = c->special;
     p->full_chr = is_rgb(sws->dst_format) && (flags & SWS_FULL_CHR_H_INT) && !c->unscaled_lut;
     /* hScale selection (swscale.c:675-688) and its shift (swscale.c:69-159) */
     p->inter_bits = c->dst_bpc > 14 ? 19 : 15;
-    if (c->src_bpc == 8)
+    if (is_rgb(sws->src_format))
+        p->h_shift = p->inter_bits == 15 ? 13 : 9;         /* swscale.c:80-81,108-109 */
+    else if (c->src_bpc == 8)
         p->h_shift = p->inter_bits == 15 ? 7 : 3;
     else
         p->h_shift = p->inter_bits == 15 ? c->src_bpc - 1 : c->src_bpc - 1 - 4;
-    /* 8-bit planar output of >8-bit sources is dithered (swscale.c:291-292,385-387,519-522) */
-    p->dither_bayer = c->src_bpc > 8;
+    /* 8-bit planar output of >8-bit sources is dithered (swscale.c:291-292,385-387,519-522);
+     * packed 8-bit RGB is neither isNBPS nor is16BPS, so it is not */
+    p->dither_bayer = sd->depth > 8;
+    if (is_rgb(sws->src_format)) {
+        static const struct { int fmt, bpp, r, g, b; } order[] = {
+            { AV_PIX_FMT_RGB24, 3, 0, 1, 2 }, { AV_PIX_FMT_BGR24, 3, 2, 1, 0 },
+            { AV_PIX_FMT_RGBA,  4, 0, 1, 2 }, { AV_PIX_FMT_BGRA,  4, 2, 1, 0 },
+            { AV_PIX_FMT_ARGB,  4, 1, 2, 3 }, { AV_PIX_FMT_ABGR,  4, 3, 2, 1 },
+        };
+        p->src_layout = SWSC_SRC_RGB;
+        p->src_bits = 8;
+        for (size_t i = 0; i < sizeof(order) / sizeof(order[0]); i++)
+            if (order[i].fmt == sws->src_format) {
+                p->src_bpp = order[i].bpp;
+                p->src_ro = order[i].r; p->src_go = order[i].g; p->src_bo = order[i].b;
+            }
+        if (!p->src_bpp) {
+            set_error(c, "RGB source format %d is not on the CUDA hot path", sws->src_format);
+            return AVERROR(ENOTSUP);
+        }
+        p->src_rgb_half = c->chr_src_hsub;
+        if (c->special == SWSC_SPECIAL_SHUFFLE) {
+            /* destination byte k <- source byte of the same component; a missing alpha becomes 255 */
+            int so[4] = { -1, -1, -1, -1 }, dorder[4] = { 4, 4, 4, 4 };   /* component (r,g,b,a) -> byte */
+            so[0] = p->src_ro; so[1] = p->src_go; so[2] = p->src_bo;
+            if (p->src_bpp == 4)
+                so[3] = 6 - p->src_ro - p->src_go - p->src_bo;
+            p->dst_bpp = dd->bpp / 8;
+            for (size_t i = 0; i < sizeof(order) / sizeof(order[0]); i++)
+                if (order[i].fmt == sws->dst_format) {
+                    dorder[order[i].r] = 0; dorder[order[i].g] = 1; dorder[order[i].b] = 2;
+                    if (order[i].bpp == 4)
+                        dorder[6 - order[i].r - order[i].g - order[i].b] = 3;
+                }
+            for (int k = 0; k < 4; k++)
+                p->shuf_map[k] = dorder[k] < 4 && so[dorder[k]] >= 0 ? so[dorder[k]] : 4;
+        }
+    }
     plan_range_convert(c);
     if ((ret = plan_colorspace(c)) < 0) {
         set_error(c, "colourspace constants overflow the int32 kernel arithmetic");
@@ -566,6 +631,16 @@ int sws_b200_get_filter(SwsContext *sws, int which, const int16_t **coef, const 
     *pos  = b->pos;
     *len  = b->len;
     return b->size;
+}
+
+int sws_b200_get_rgb2yuv(SwsContext *sws, int out[9])
+{
+    SwsInternal *c = sws_internal(sws);
+    if (!c || (!c->planned && !c->initialized) || c->plan.src_layout != SWSC_SRC_RGB)
+        return AVERROR(EINVAL);
+    for (int i = 0; i < 9; i++)
+        out[i] = c->plan.rgb2yuv[i];
+    return 0;
 }
 
 int sws_b200_get_info(SwsContext *sws, int out[32])
@@ -702,8 +777,8 @@ int sws_scale(SwsContext *sws, const uint8_t *const srcSlice[], const int srcStr
     avail_l = srcSliceY + srcSliceH;
     avail_c = ceil_rshift(srcSliceY + srcSliceH, c->chr_src_vsub);
     y0 = c->dst_y;
-    if (c->unscaled_lut) {
-        /* the unscaled converter maps slice rows 1:1 (swscale.c:1161-1187) */
+    if (c->unscaled_lut || c->special) {
+        /* the unscaled converters map slice rows 1:1 (swscale.c:1161-1187) */
         y0 = srcSliceY;
         y1 = srcSliceY + srcSliceH;
     } else {

@@ -75,7 +75,158 @@ __device__ __forceinline__ int fetch(const uint8_t *row, int idx)
     return row[idx];
 }
 
+/* Packed 8-bit RGB readers: one 14-bit luma or chroma sample (8-bit value << 6) from pixel x of a
+ * row, restating rgb24ToY_c / rgb24ToUV_c / rgb24ToUV_half_c (reference input.c:1068-1180) for
+ * 3-byte pixels and the rgb16_32To{Y,UV,UV_half}_c_template instances for 4-byte pixels
+ * (input.c:264-345,391-394: coefficients << 8, unsigned rounding constant, logical shift).  Both
+ * store into int16 lines that the horizontal scaler reads back as uint16 (swscale.c:99-125). */
+__device__ __forceinline__ int rgb_luma14(const SwsCudaPlan &P, const uint8_t *row, int x)
+{
+    const uint8_t *px = row + x * P.src_bpp;
+    const int r = px[P.src_ro], g = px[P.src_go], b = px[P.src_bo];
+    const int s = P.rgb2yuv[0] * r + P.rgb2yuv[1] * g + P.rgb2yuv[2] * b;
+    if (P.src_bpp == 3)
+        return (uint16_t)((s + (32 << 14) + (1 << 8)) >> 9);
+    return (uint16_t)(((unsigned)s * 256u + (32u << 22) + (1u << 16)) >> 17);
+}
+
+__device__ __forceinline__ void rgb_chroma14(const SwsCudaPlan &P, const uint8_t *row, int x, int &u, int &v)
+{
+    int r, g, b;
+    if (P.src_rgb_half) {
+        const uint8_t *px = row + 2 * x * P.src_bpp, *qx = px + P.src_bpp;
+        r = px[P.src_ro] + qx[P.src_ro]; g = px[P.src_go] + qx[P.src_go]; b = px[P.src_bo] + qx[P.src_bo];
+    } else {
+        const uint8_t *px = row + x * P.src_bpp;
+        r = px[P.src_ro]; g = px[P.src_go]; b = px[P.src_bo];
+    }
+    const int su = P.rgb2yuv[3] * r + P.rgb2yuv[4] * g + P.rgb2yuv[5] * b;
+    const int sv = P.rgb2yuv[6] * r + P.rgb2yuv[7] * g + P.rgb2yuv[8] * b;
+    if (P.src_bpp == 3) {
+        if (P.src_rgb_half) {
+            u = (uint16_t)((su + (256 << 15) + (1 << 9)) >> 10);
+            v = (uint16_t)((sv + (256 << 15) + (1 << 9)) >> 10);
+        } else {
+            u = (uint16_t)((su + (256 << 14) + (1 << 8)) >> 9);
+            v = (uint16_t)((sv + (256 << 14) + (1 << 8)) >> 9);
+        }
+    } else if (P.src_rgb_half) {
+        u = (uint16_t)(((unsigned)su * 256u + (256u << 23) + (1u << 17)) >> 18);
+        v = (uint16_t)(((unsigned)sv * 256u + (256u << 23) + (1u << 17)) >> 18);
+    } else {
+        u = (uint16_t)(((unsigned)su * 256u + (256u << 22) + (1u << 16)) >> 17);
+        v = (uint16_t)(((unsigned)sv * 256u + (256u << 22) + (1u << 16)) >> 17);
+    }
+}
+
 #include "sws_scale8.cuh"
+
+
+/* ------------------------------------------------------------------------
+ * Unscaled special converters (reference swscale_unscaled.c), pure HBM-bound byte work.
+ * ------------------------------------------------------------------------ */
+struct ShuffleArgs {
+    const uint8_t *src;
+    uint8_t *dst;
+    long long src_fstride, dst_fstride;
+    int src_stride, dst_stride;
+    int w, y0;
+    int map[4];            /* destination byte k of a pixel <- source byte map[k]; 4 = constant 255 */
+};
+
+#define SHUF_PX 1024       /* pixels of one row per block */
+
+/* rgbToRgbWrapper / packedCopyWrapper between 8-bit packed RGB layouts (swscale_unscaled.c:2001-2060):
+ * a byte permutation per pixel; alpha is carried when both sides have it, 255 when only the
+ * destination has it.  Rows are staged through shared memory so that global loads and stores are
+ * whole words whenever the row addresses allow it. */
+template <int SBPP, int DBPP>
+__global__ void __launch_bounds__(256)
+sws_rgb_shuffle_kernel(const __grid_constant__ ShuffleArgs A)
+{
+    __shared__ __align__(16) uint32_t sm[SHUF_PX * SBPP / 4];
+    uint8_t *sb = reinterpret_cast<uint8_t *>(sm);
+    const int x0 = blockIdx.x * SHUF_PX;
+    const int y = A.y0 + blockIdx.y;
+    const int n = min(SHUF_PX, A.w - x0);
+    const uint8_t *s = A.src + blockIdx.z * A.src_fstride + (size_t)y * A.src_stride + (size_t)x0 * SBPP;
+    uint8_t *d = A.dst + blockIdx.z * A.dst_fstride + (size_t)y * A.dst_stride + (size_t)x0 * DBPP;
+    const int nin = n * SBPP, nout = n * DBPP;
+
+    if (((uintptr_t)s & 3) == 0) {
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(s);
+        for (int i = threadIdx.x; i < (nin >> 2); i += blockDim.x)
+            sm[i] = __ldg(sw + i);
+        for (int i = (nin & ~3) + threadIdx.x; i < nin; i += blockDim.x)
+            sb[i] = s[i];
+    } else {
+        for (int i = threadIdx.x; i < nin; i += blockDim.x)
+            sb[i] = s[i];
+    }
+    __syncthreads();
+
+    auto out_byte = [&](int ob) -> uint32_t {
+        const int px = ob / DBPP, k = ob - px * DBPP;
+        const int m = A.map[k];
+        return m == 4 ? 255u : sb[px * SBPP + m];
+    };
+    if (((uintptr_t)d & 3) == 0) {
+        uint32_t *dw = reinterpret_cast<uint32_t *>(d);
+        for (int i = threadIdx.x; i < (nout >> 2); i += blockDim.x) {
+            const int ob = 4 * i;
+            dw[i] = out_byte(ob) | out_byte(ob + 1) << 8 | out_byte(ob + 2) << 16 | out_byte(ob + 3) << 24;
+        }
+        for (int i = (nout & ~3) + threadIdx.x; i < nout; i += blockDim.x)
+            d[i] = (uint8_t)out_byte(i);
+    } else {
+        for (int i = threadIdx.x; i < nout; i += blockDim.x)
+            d[i] = (uint8_t)out_byte(i);
+    }
+}
+
+struct Bgr24Yv12Args {
+    const uint8_t *src;
+    uint8_t *dst[3];
+    long long src_fstride, dst_fstride[3];
+    int src_stride, dst_stride[3];
+    int cw;                /* chroma width = width >> 1 */
+    int y0, h;             /* slice rows [y0, y0 + h) */
+    int ry, gy, by, ru, gu, bu, rv, gv, bv;
+};
+
+/* bgr24ToYv12Wrapper -> ff_rgb24toyv12_c (rgb2rgb_template.c:580-641): per 2x2 block four luma
+ * samples ((ry*r+gy*g+by*b) >> 15) + 16 and one chroma pair from the truncated box average of the
+ * four pixels; an odd last row is paired with itself.  One thread per chroma sample. */
+__global__ void __launch_bounds__(256)
+sws_bgr24_to_yv12_kernel(const __grid_constant__ Bgr24Yv12Args A)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pr = blockIdx.y;                       /* row pair inside the slice */
+    if (i >= A.cw)
+        return;
+    const int ya = 2 * pr, yb = min(2 * pr + 1, A.h - 1);
+    const uint8_t *s = A.src + blockIdx.z * A.src_fstride;
+    const uint8_t *s1 = s + (size_t)(A.y0 + ya) * A.src_stride + 6 * i;
+    const uint8_t *s2 = s + (size_t)(A.y0 + yb) * A.src_stride + 6 * i;
+    uint8_t *d0 = A.dst[0] + blockIdx.z * A.dst_fstride[0];
+    uint8_t *y1p = d0 + (size_t)(A.y0 + ya) * A.dst_stride[0] + 2 * i;
+    uint8_t *y2p = d0 + (size_t)(A.y0 + yb) * A.dst_stride[0] + 2 * i;
+    const unsigned b11 = s1[0], g11 = s1[1], r11 = s1[2], b12 = s1[3], g12 = s1[4], r12 = s1[5];
+    const unsigned b21 = s2[0], g21 = s2[1], r21 = s2[2], b22 = s2[3], g22 = s2[4], r22 = s2[5];
+    auto luma = [&](unsigned r, unsigned g, unsigned b) {
+        return (uint8_t)(((A.ry * (int)r + A.gy * (int)g + A.by * (int)b) >> 15) + 16);
+    };
+    y1p[0] = luma(r11, g11, b11); y1p[1] = luma(r12, g12, b12);
+    if (yb != ya) {                                  /* an odd last row is its own partner */
+        y2p[0] = luma(r21, g21, b21); y2p[1] = luma(r22, g22, b22);
+    }
+    const int bx = (b11 + b12 + b21 + b22) >> 2, gx = (g11 + g12 + g21 + g22) >> 2, rx = (r11 + r12 + r21 + r22) >> 2;
+    const size_t crow = (size_t)((A.y0 >> 1) + pr);
+    (A.dst[1] + blockIdx.z * A.dst_fstride[1])[crow * A.dst_stride[1] + i] =
+        (uint8_t)(((A.ru * rx + A.gu * gx + A.bu * bx) >> 15) + 128);
+    (A.dst[2] + blockIdx.z * A.dst_fstride[2])[crow * A.dst_stride[2] + i] =
+        (uint8_t)(((A.rv * rx + A.gv * gx + A.bv * bx) >> 15) + 128);
+}
 
 /* ------------------------------------------------------------------------
  * Generic fused tile kernel: table-driven H FIR -> (range) -> V FIR -> pack.
@@ -150,8 +301,13 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
             const int pos = P.hl_pos[gx];
             const int16_t *co = P.hl_coef + (size_t)gx * fs;
             int val = 0;
-            for (int j = 0; j < fs; j++)
-                val += fetch<SRC16>(row, min(pos + j, P.src_w - 1)) * (int)co[j];
+            if (P.src_layout == SWSC_SRC_RGB) {
+                for (int j = 0; j < fs; j++)
+                    val += rgb_luma14(P, row, min(pos + j, P.src_w - 1)) * (int)co[j];
+            } else {
+                for (int j = 0; j < fs; j++)
+                    val += fetch<SRC16>(row, min(pos + j, P.src_w - 1)) * (int)co[j];
+            }
             val = min(val >> sh, h_max);
             if (P.range_mode) {
                 if (!INTER32) {
@@ -189,6 +345,14 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
                     const int cj = co[j];
                     u += fetch<SRC16>(ru, sx) * cj;
                     v += fetch<SRC16>(rv, sx) * cj;
+                }
+            } else if (layout == SWSC_SRC_RGB) {
+                const uint8_t *row = src0 + (size_t)sy * A.src_stride[0];
+                for (int j = 0; j < fs; j++) {
+                    int uu, vv;
+                    rgb_chroma14(P, row, min(pos + j, P.chr_src_w - 1), uu, vv);
+                    u += uu * (int)co[j];
+                    v += vv * (int)co[j];
                 }
             } else {
                 const uint8_t *ruv = src1 + (size_t)sy * A.src_stride[1];
@@ -678,7 +842,7 @@ static int fast420_setup(SwsCudaState *st, const SwsFirBank *vc)
 {
     const SwsCudaPlan *p = &st->plan;
     st->fast_ok = 0;
-    if (p->src_bits != 8 || p->inter_bits != 15)
+    if (p->src_bits != 8 || p->inter_bits != 15 || p->src_layout > SWSC_SRC_NV21)
         return 0;
     if (p->dst_kind < SWSC_DST_RGB24 || p->dst_kind > SWSC_DST_ABGR || p->full_chr)
         return 0;
@@ -1019,7 +1183,7 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
 {
     const SwsCudaPlan *p = &st->plan;
     st->s8_ok = 0;
-    if (p->src_bits != 8 || p->inter_bits != 15 || p->range_mode)
+    if (p->src_bits != 8 || p->inter_bits != 15 || p->range_mode || p->src_layout > SWSC_SRC_NV21)
         return 0;
     if (p->dst_kind != SWSC_DST_PLANAR8 && p->dst_kind != SWSC_DST_NV12 && p->dst_kind != SWSC_DST_NV21)
         return 0;
@@ -1256,6 +1420,58 @@ extern "C" int ff_b200_cuda_update_plan(SwsCudaState *st, const SwsCudaPlan *pla
     return 0;
 }
 
+/* whole-frame special converters; returns 1 if launched */
+static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const int src_stride[4],
+                          const int64_t src_fstride[4], uint8_t *const dst[4], const int dst_stride[4],
+                          const int64_t dst_fstride[4], int nb_frames, int y0, int y1, cudaStream_t stream)
+{
+    const SwsCudaPlan *p = &st->plan;
+    if (p->special == SWSC_SPECIAL_SHUFFLE) {
+        ShuffleArgs a;
+        a.src = src[0]; a.dst = dst[0];
+        a.src_fstride = src_fstride ? src_fstride[0] : 0;
+        a.dst_fstride = dst_fstride ? dst_fstride[0] : 0;
+        a.src_stride = src_stride[0]; a.dst_stride = dst_stride[0];
+        a.w = p->src_w; a.y0 = y0;
+        for (int k = 0; k < 4; k++)
+            a.map[k] = p->shuf_map[k];
+        dim3 grid((p->src_w + SHUF_PX - 1) / SHUF_PX, y1 - y0, nb_frames);
+        if (p->src_bpp == 3 && p->dst_bpp == 3)
+            sws_rgb_shuffle_kernel<3, 3><<<grid, 256, 0, stream>>>(a);
+        else if (p->src_bpp == 3)
+            sws_rgb_shuffle_kernel<3, 4><<<grid, 256, 0, stream>>>(a);
+        else if (p->dst_bpp == 3)
+            sws_rgb_shuffle_kernel<4, 3><<<grid, 256, 0, stream>>>(a);
+        else
+            sws_rgb_shuffle_kernel<4, 4><<<grid, 256, 0, stream>>>(a);
+        st->kernel_name = "rgb_shuffle";
+    } else if (p->special == SWSC_SPECIAL_BGR24_YV12) {
+        Bgr24Yv12Args a;
+        a.src = src[0];
+        a.src_fstride = src_fstride ? src_fstride[0] : 0;
+        a.src_stride = src_stride[0];
+        for (int i = 0; i < 3; i++) {
+            if (!dst[i])
+                return AVERROR(EINVAL);
+            a.dst[i] = dst[i];
+            a.dst_fstride[i] = dst_fstride ? dst_fstride[i] : 0;
+            a.dst_stride[i] = dst_stride[i];
+        }
+        a.cw = p->src_w >> 1; a.y0 = y0; a.h = y1 - y0;
+        a.ry = p->rgb2yuv[0]; a.gy = p->rgb2yuv[1]; a.by = p->rgb2yuv[2];
+        a.ru = p->rgb2yuv[3]; a.gu = p->rgb2yuv[4]; a.bu = p->rgb2yuv[5];
+        a.rv = p->rgb2yuv[6]; a.gv = p->rgb2yuv[7]; a.bv = p->rgb2yuv[8];
+        dim3 grid((a.cw + 255) / 256, (a.h + 1) / 2, nb_frames);
+        sws_bgr24_to_yv12_kernel<<<grid, 256, 0, stream>>>(a);
+        st->kernel_name = "bgr24_to_yv12";
+    } else {
+        return 0;
+    }
+    CUDA_OK(cudaGetLastError());
+    st->launches++;
+    return 1;
+}
+
 extern "C" int ff_b200_cuda_launch(SwsCudaState *st,
                                    const uint8_t *const src[4], const int src_stride[4], const int64_t src_fstride[4],
                                    uint8_t *const dst[4], const int dst_stride[4], const int64_t dst_fstride[4],
@@ -1267,7 +1483,10 @@ extern "C" int ff_b200_cuda_launch(SwsCudaState *st,
     if (cudaGetDevice(&cur) == cudaSuccess && cur != st->device)
         CUDA_OK(cudaSetDevice(st->device));
     {
-        int r = fast420_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);
+        int r = special_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);
+        if (r != 0)
+            return r < 0 ? r : 0;
+        r = fast420_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);
         if (r != 0)
             return r < 0 ? r : 0;
         r = fast16_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);
@@ -1305,7 +1524,9 @@ static int ensure_staging(SwsCudaState *st)
     const int sb = p->src_bits > 8 ? 2 : 1;
     /* source planes */
     st->src_rows[0] = p->src_h; st->src_rowbytes[0] = p->src_w * sb;
-    if (p->src_layout == SWSC_SRC_PLANAR) {
+    if (p->src_layout == SWSC_SRC_RGB) {
+        st->src_rowbytes[0] = p->src_w * p->src_bpp;
+    } else if (p->src_layout == SWSC_SRC_PLANAR) {
         st->src_rows[1] = st->src_rows[2] = p->chr_src_h;
         st->src_rowbytes[1] = st->src_rowbytes[2] = p->chr_src_w * sb;
     } else {
@@ -1393,7 +1614,7 @@ static int pipelined_host_frame(SwsCudaState *st, const uint8_t *const src[4], c
         if (chi > p->chr_src_h)
             chi = p->chr_src_h;
         if (chi > cup) {
-            for (int i = 1; i < 3; i++)
+            for (int i = 1; i < 3 && st->src_rows[i]; i++)     /* U and V planes, or the one UV plane */
                 CUDA_OK(copy_rows_async(st->d_src[i] + (size_t)cup * st->d_src_stride[i], st->d_src_stride[i],
                                           src[i] + (size_t)cup * src_stride[i], src_stride[i],
                                           st->src_rowbytes[i], chi - cup, cudaMemcpyHostToDevice, st->s_in));
@@ -1447,7 +1668,8 @@ extern "C" int ff_b200_cuda_scale_host(SwsCudaState *st,
         const uint8_t *dsrc[4] = { nullptr, nullptr, nullptr, nullptr };
         uint8_t *ddst[4] = { nullptr, nullptr, nullptr, nullptr };
         bool ok = true;
-        for (int i = 0; i < 3 && ok; i++) {
+        const int nb_src = p->src_layout == SWSC_SRC_PLANAR ? 3 : 2;
+        for (int i = 0; i < nb_src && ok; i++) {
             cudaPointerAttributes at;
             if (!src[i] || cudaPointerGetAttributes(&at, src[i]) != cudaSuccess ||
                 at.type != cudaMemoryTypeHost || !at.devicePointer)

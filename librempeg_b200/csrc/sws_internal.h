@@ -77,12 +77,14 @@ typedef struct SwsRgbConsts {
 
 int ff_b200_rgb_consts(SwsRgbConsts *k, const int inv_table[4], int full_range,
                        int brightness, int contrast, int saturation);
+void ff_b200_rgb2yuv_table(int32_t out[9], const int table[4]);
 
 /* ------------------------------------------------------------ device plan */
 enum {
     SWSC_SRC_PLANAR = 0,   /* Y, U, V planes (or Y only for gray)     */
     SWSC_SRC_NV12   = 1,   /* Y plane + interleaved UV                */
     SWSC_SRC_NV21   = 2,   /* Y plane + interleaved VU                */
+    SWSC_SRC_RGB    = 3,   /* one packed plane of 8-bit R,G,B[,A] pixels */
 };
 
 enum {
@@ -101,6 +103,13 @@ enum {
     SWSC_DST_BGR48,
 };
 
+/* unscaled converters the reference installs instead of the scaler (swscale_unscaled.c) */
+enum {
+    SWSC_SPECIAL_NONE = 0,
+    SWSC_SPECIAL_SHUFFLE,        /* rgbToRgbWrapper / packedCopyWrapper between 8-bit packed RGB layouts */
+    SWSC_SPECIAL_BGR24_YV12,     /* bgr24ToYv12Wrapper: 2x2 box chroma, truncating 15-bit matrix */
+};
+
 /* POD description of one conversion; passed by value to the kernels. */
 typedef struct SwsCudaPlan {
     int src_w, src_h, dst_w, dst_h;
@@ -112,6 +121,9 @@ typedef struct SwsCudaPlan {
     int h_shift;                 /* right shift applied after the H FIR       */
     int has_chroma;              /* 0 for gray sources/destinations           */
     int unscaled_lut;            /* 1: reference would take convert_unscaled  */
+    int special;                 /* whole-frame special converter, SWSC_SPECIAL_* */
+    int shuf_map[4];             /* SHUFFLE: source byte of every destination byte, 4 = constant 255 */
+    int dst_bpp;                 /* SHUFFLE: destination pixel stride in bytes */
     int full_chr;                /* 1: SWS_FULL_CHR_H_INT packed RGB (per-pixel chroma, arithmetic) */
     int dither_bayer;            /* 1: ff_dither_8x8_128 rows, 0: constant 64 */
     /* range conversion on the h-scaled lines (reference swscale.c:163-255,577-660) */
@@ -119,6 +131,10 @@ typedef struct SwsCudaPlan {
     uint32_t lum_rc_coeff, chr_rc_coeff;
     int64_t  lum_rc_offset, chr_rc_offset;
     SwsRgbConsts rgb;
+    /* packed-RGB sources (reference input.c:264-345,1068-1180): pixel stride, byte offsets of R,G,B,
+     * chroma taken from horizontally summed pixel pairs (the *_half readers), and the 15-bit matrix */
+    int src_bpp, src_ro, src_go, src_bo, src_rgb_half;
+    int32_t rgb2yuv[9];
     /* device pointers to the four FIR banks */
     const int16_t *hl_coef, *hc_coef, *vl_coef, *vc_coef;
     const int32_t *hl_pos,  *hc_pos,  *vl_pos,  *vc_pos;
@@ -164,6 +180,7 @@ typedef struct SwsInternal {
     int chr_src_w, chr_src_h, chr_dst_w, chr_dst_h;
     int src_bpc, dst_bpc;
     int unscaled_lut;                /* reference would use c->convert_unscaled (a13) */
+    int special;                     /* SWSC_SPECIAL_*: rows map 1:1 like the unscaled LUT converter */
     int dst_slice_align;
     SwsFirBank h_lum, h_chr, v_lum, v_chr;
     SwsCudaPlan plan;

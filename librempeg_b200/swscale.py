@@ -38,6 +38,7 @@ SWS_LANCZOS = 1 << 9
 SWS_SPLINE = 1 << 10
 SWS_PRINT_INFO = 1 << 12
 SWS_FULL_CHR_H_INT = 1 << 13
+SWS_FULL_CHR_H_INP = 1 << 14
 SWS_ACCURATE_RND = 1 << 18
 SWS_BITEXACT = 1 << 19
 BX = SWS_ACCURATE_RND | SWS_BITEXACT
@@ -106,6 +107,8 @@ def lib():
     L.sws_b200_plan_only.argtypes = [ctxp]
     L.sws_b200_get_filter.restype = C.c_int
     L.sws_b200_get_filter.argtypes = [ctxp, C.c_int, P(P(C.c_int16)), P(P(C.c_int32)), P(C.c_int)]
+    L.sws_b200_get_rgb2yuv.restype = C.c_int
+    L.sws_b200_get_rgb2yuv.argtypes = [ctxp, P(C.c_int)]
     L.sws_b200_get_info.restype = C.c_int
     L.sws_b200_get_info.argtypes = [ctxp, P(C.c_int)]
     _lib = L
@@ -239,6 +242,12 @@ class SwsContext:
         co = np.ctypeslib.as_array(coef, shape=(n.value * fs,)).copy().reshape(n.value, fs)
         po = np.ctypeslib.as_array(pos, shape=(n.value,)).copy()
         return co, po
+
+    def rgb2yuv(self):
+        out = (C.c_int * 9)()
+        if self._L.sws_b200_get_rgb2yuv(self.p, out) < 0:
+            return None
+        return list(out)
 
     def info(self):
         out = (C.c_int * 32)()

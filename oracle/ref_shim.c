@@ -152,6 +152,14 @@ API void swsref_info(void *ctx, int out[16])
     out[12] = c->srcBpc; out[13] = c->dstBpc; out[14] = c->opts.flags; out[15] = 0;
 }
 
+/* the C entries of input_rgb2yuv_table: ry gy by ru gu bu rv gv bv */
+API void swsref_rgb2yuv(void *ctx, int out[9])
+{
+    SwsInternal *c = first_ctx(ctx);
+    for (int i = 0; i < 9; i++)
+        out[i] = c->input_rgb2yuv_table[i];
+}
+
 /* copy the rgb24/48 LUTs the reference built: y_table[2048]; rV/gU/bU as offsets into it */
 API int swsref_rgb_tables(void *ctx, uint8_t y_table[2048], int rV[1280], int gU[1280],
                           int bU[1280], int gV[1280])

@@ -25,6 +25,7 @@ SWS_SINC = 1 << 8
 SWS_LANCZOS = 1 << 9
 SWS_SPLINE = 1 << 10
 SWS_FULL_CHR_H_INT = 1 << 13
+SWS_FULL_CHR_H_INP = 1 << 14
 SWS_ACCURATE_RND = 1 << 18
 SWS_BITEXACT = 1 << 19
 BX = SWS_ACCURATE_RND | SWS_BITEXACT
@@ -65,6 +66,8 @@ def lib():
         L.swsref_filter.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.POINTER(C.c_int16)),
                                     C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int)]
         L.swsref_info.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        if hasattr(L, "swsref_rgb2yuv"):
+            L.swsref_rgb2yuv.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         L.swsref_rgb_tables.restype = C.c_int
         L.swsref_rgb_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.swsref_lfg_fill.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_int]
@@ -154,6 +157,11 @@ class RefContext:
         keys = ["y_offset", "y_coeff", "v2r", "v2g", "u2g", "u2b", "unscaled", "cascaded",
                 "chrSrcW", "chrSrcH", "chrDstW", "chrDstH", "srcBpc", "dstBpc", "flags"]
         return dict(zip(keys, list(out)))
+
+    def rgb2yuv(self):
+        out = (C.c_int * 9)()
+        lib().swsref_rgb2yuv(self.h, out)
+        return list(out)
 
     def rgb_tables(self):
         y = np.zeros(2048, np.uint8)

@@ -33,6 +33,7 @@ SWS_SINC = 1 << 8
 SWS_LANCZOS = 1 << 9
 SWS_SPLINE = 1 << 10
 SWS_FULL_CHR_H_INT = 1 << 13
+SWS_FULL_CHR_H_INP = 1 << 14
 SWS_ACCURATE_RND = 1 << 18
 SWS_BITEXACT = 1 << 19
 BX = SWS_ACCURATE_RND | SWS_BITEXACT
@@ -342,6 +343,26 @@ def yuv2rgb_tables(inv_table, full_range, brightness, contrast, saturation):
 
 
 # --------------------------------------------------------------------------- the context
+def rgb2yuv_table(table):
+    """fill_rgb2yuv_table (utils.c:614-706): {ry,gy,by,ru,gu,bu,rv,gv,bv} at 15 bits from the
+    destination matrix, always limited range; BT.601 takes the classic rounded constants."""
+    one, sh = 65536, 1 << 15
+    vr, ub, ug, vg = table[0], table[1], -table[2], -table[3]
+    cy = _cdiv(one * 255, 219)
+    w = _rounded_div(one * one * ug, ub)
+    v = _rounded_div(one * one * vg, vr)
+    z = one * one - w - v
+    Cy, Cu, Cv = _rounded_div(cy * z, one), _rounded_div(ub * z, one), _rounded_div(vr * z, one)
+    out = [-_rounded_div(sh * v, Cy), _rounded_div(sh * one * one, Cy), -_rounded_div(sh * w, Cy),
+           _rounded_div(sh * v, Cu), -_rounded_div(sh * one * one, Cu), _rounded_div(sh * (z + w), Cu),
+           _rounded_div(sh * (v + z), Cv), -_rounded_div(sh * one * one, Cv), _rounded_div(sh * w, Cv)]
+    if tuple(table) == YUV2RGB_COEFFS[5]:
+        f = lambda k, span: int(k * span / 255 * (1 << 15) + 0.5)      # noqa: E731
+        out = [f(0.299, 219), f(0.587, 219), f(0.114, 219), -f(0.169, 224), -f(0.331, 224), f(0.500, 224),
+               f(0.500, 224), -f(0.419, 224), -f(0.081, 224)]
+    return out
+
+
 class OracleContext:
     """Geometry and path selection of ff_sws_init_single_context (utils.c:1137-1835) for the
     formats the hot path covers, then whole-frame conversion with the per-line kernels of
@@ -359,7 +380,12 @@ class OracleContext:
         self.skind, self.sdepth, shs, svs = _fmt(sfmt)
         self.dkind, self.ddepth, dhs, dvs = _fmt(dfmt)
         dst_rgb = self.dkind.startswith("rgb")
-        self.src_range, self.dst_range = src_range, (0 if dst_rgb else dst_range)
+        src_rgb = self.skind.startswith("rgb")
+        if self.skind == "rgb16":
+            raise NotImplementedError("16-bit RGB sources are not restated")
+        # formats that are neither YUV nor gray carry no range, utils.c:844-880
+        self.src_range, self.dst_range = (0 if src_rgb else src_range), (0 if dst_rgb else dst_range)
+        src_range = self.src_range
         scaler = flags & SCALER_MASK
         if not scaler:                                                # :1209
             scaler = SWS_BICUBIC
@@ -373,11 +399,16 @@ class OracleContext:
                 flags |= SWS_FULL_CHR_H_INT
         if dst_rgb and not (flags & SWS_FULL_CHR_H_INT):              # :1359
             dhs = 1
+        # packed RGB sources: chroma from summed pixel pairs (the *_half readers), utils.c:1367-1390
+        if src_rgb and not (sw & 1) and not (flags & SWS_FULL_CHR_H_INP) and (dw >> dhs) <= (sw >> 1):
+            shs = 1
         self.flags = flags
         self.shs, self.svs, self.dhs, self.dvs = shs, svs, dhs, dvs
         self.csw, self.csh = _cdiv_shift(sw, shs), _cdiv_shift(sh, svs)
         self.cdw, self.cdh = _cdiv_shift(dw, dhs), _cdiv_shift(dh, dvs)
         self.src_bpc, self.dst_bpc = max(self.sdepth, 8), max(self.ddepth, 8)
+        if src_rgb:
+            self.src_bpc = 16                                          # utils.c:1407-1408
         lum_xinc = ((sw << 16) + (dw >> 1)) // dw
         lum_yinc = ((sh << 16) + (dh >> 1)) // dh
         chr_xinc = ((self.csw << 16) + (self.cdw >> 1)) // self.cdw
@@ -387,12 +418,25 @@ class OracleContext:
         if dst_rgb:
             self.rgb = yuv2rgb_tables(YUV2RGB_COEFFS[cs[0]], cs[1] if colorspace else src_range,
                                       cs[4], cs[5], cs[6])
-            if colorspace:
+            if colorspace and not src_rgb:
                 self.src_range = cs[1]
+        if src_rgb:
+            self.rgb2yuv = rgb2yuv_table(YUV2RGB_COEFFS[cs[2]])
 
         # unscaled special converters, swscale_unscaled.c:2392-2731 (only the ones that differ)
         self.unscaled_lut = False
+        self.special = None
         if unscaled and (self.src_range == self.dst_range or dst_rgb):
+            if src_rgb and dst_rgb and self.dkind != "rgb16":
+                # rgbToRgbWrapper (findRgbConvFn, swscale_unscaled.c:1843-2060,2463-2466), packedCopyWrapper
+                # for identical formats; with SWS_BITEXACT 24 -> rgba/bgra is left to the scaler (:1992-1996)
+                s32, d32 = self.skind == "rgb32", self.dkind == "rgb32"
+                if sfmt == dfmt or s32 or not d32 or not (flags & SWS_BITEXACT) or dfmt in ("argb", "abgr"):
+                    self.special = "shuffle"
+                    return
+            if sfmt == "bgr24" and dfmt == "yuv420p" and not (flags & SWS_ACCURATE_RND) and not (dw & 1):
+                self.special = "bgr24_yv12"                            # swscale_unscaled.c:2062-2077,2453-2457
+                return
             if sfmt in ("yuv420p", "yuv422p") and dst_rgb and not (flags & SWS_ACCURATE_RND) \
                     and dither in (1, 2) and not (dh & 1):
                 self.unscaled_lut = True                               # yuv2rgb_c_* (yuv2rgb.c:137-236)
@@ -401,6 +445,8 @@ class OracleContext:
                     and (shs, svs) == (dhs, dvs) and (self.skind == "semi") == (self.dkind == "semi")
                     and self.sdepth != self.ddepth):
                 raise NotImplementedError("planarCopyWrapper depth conversion is not restated")
+        if self.skind == "rgb32" and self.dkind == "rgb32":
+            raise NotImplementedError("the alpha plane (alpToYV12 -> yuv2packedX with alpha) is not restated")
         self.full_chr = bool(dst_rgb and flags & SWS_FULL_CHR_H_INT)
 
         def lpos(sub, pos):                                            # get_local_pos, utils.c:168
@@ -420,6 +466,8 @@ class OracleContext:
 
     # ---- stage 0: planes as integer sample arrays (input.c:926-941 for nv12/nv21)
     def _unpack(self, planes):
+        if self.skind.startswith("rgb"):
+            return self._unpack_rgb(planes[0])
         dt = np.uint8 if self.sdepth == 8 else np.dtype("<u2")
         lum = np.ascontiguousarray(planes[0]).view(dt)[:self.sh, :self.sw].astype(np.int64)
         if self.skind == "semi":
@@ -431,11 +479,44 @@ class OracleContext:
             v = np.ascontiguousarray(planes[2]).view(dt)[:self.csh, :self.csw].astype(np.int64)
         return lum, u, v
 
+    # packed 8-bit RGB readers: rgb24ToY_c / rgb24ToUV_c / rgb24ToUV_half_c (input.c:1068-1180) for
+    # 3-byte pixels, the rgb16_32To{Y,UV,UV_half}_c_template instances (input.c:264-345,391-394) for
+    # 4-byte pixels (coefficients << 8, unsigned rounding term, logical shift); int16 lines that the
+    # horizontal scaler reads back as uint16
+    def _unpack_rgb(self, plane):
+        bpp = 3 if self.skind == "rgb8" else 4
+        ro, go, bo = {"rgb24": (0, 1, 2), "bgr24": (2, 1, 0), "rgba": (0, 1, 2), "bgra": (2, 1, 0),
+                      "argb": (1, 2, 3), "abgr": (3, 2, 1)}[self.sfmt]
+        px = np.ascontiguousarray(plane)[:self.sh, :self.sw * bpp].astype(np.int64).reshape(self.sh, self.sw, bpp)
+        r, g, b = px[:, :, ro], px[:, :, go], px[:, :, bo]
+        ry, gy, by, ru, gu, bu, rv, gv, bv = self.rgb2yuv
+        half = self.shs == 1
+
+        def store(x):                       # int16 store, uint16 load
+            return np.asarray(x, np.int64) & 0xFFFF
+
+        if bpp == 3:
+            lum = store(_wrap32(ry * r + gy * g + by * b + (32 << 14) + (1 << 8)) >> 9)
+        else:
+            lum = store(((ry * r + gy * g + by * b) * 256 + (32 << 22) + (1 << 16) & 0xFFFFFFFF) >> 17)
+        if half:
+            r, g, b = r[:, 0::2] + r[:, 1::2], g[:, 0::2] + g[:, 1::2], b[:, 0::2] + b[:, 1::2]
+        su, sv = ru * r + gu * g + bu * b, rv * r + gv * g + bv * b
+        if bpp == 3:
+            rnd, sh = ((256 << 15) + (1 << 9), 10) if half else ((256 << 14) + (1 << 8), 9)
+            u, v = store(_wrap32(su + rnd) >> sh), store(_wrap32(sv + rnd) >> sh)
+        else:
+            rnd, sh = ((256 << 23) + (1 << 17), 18) if half else ((256 << 22) + (1 << 16), 17)
+            u, v = store((su * 256 + rnd & 0xFFFFFFFF) >> sh), store((sv * 256 + rnd & 0xFFFFFFFF) >> sh)
+        return lum, u, v
+
     # ---- stage H: hScale8To15_c / hScale16To15_c / hScale8To19_c / hScale16To19_c (swscale.c:69-159)
     def _hscale(self, src, bank):
         coef, pos = bank
         inter19 = self.dst_bpc > 14
-        if self.src_bpc == 8:
+        if self.skind.startswith("rgb"):
+            sh = 9 if inter19 else 13                                  # swscale.c:80-81,108-109
+        elif self.src_bpc == 8:
             sh = 3 if inter19 else 7
         else:
             sh = self.sdepth - 1 - 4 if inter19 else self.sdepth - 1
@@ -499,7 +580,39 @@ class OracleContext:
         return acc
 
     # ---- the conversion
+    _ORDER = {"rgb24": "rgb", "bgr24": "bgr", "rgba": "rgba", "bgra": "bgra", "argb": "argb", "abgr": "abgr"}
+
+    def _shuffle(self, plane):
+        """Byte permutation per pixel; alpha carried when both sides have it, else 255."""
+        so, do = self._ORDER[self.sfmt], self._ORDER[self.dfmt]
+        px = np.ascontiguousarray(plane)[:self.sh, :self.sw * len(so)].reshape(self.sh, self.sw, len(so))
+        out = np.empty((self.sh, self.sw, len(do)), np.uint8)
+        for k, comp in enumerate(do):
+            out[:, :, k] = px[:, :, so.index(comp)] if comp in so else 255
+        return [out.reshape(self.sh, -1)]
+
+    def _bgr24_yv12(self, plane):
+        """ff_rgb24toyv12_c (rgb2rgb_template.c:580-641): truncating 15-bit matrix, 2x2 box chroma,
+        an odd last row is its own partner."""
+        px = np.ascontiguousarray(plane)[:self.sh, :self.sw * 3].astype(np.int64).reshape(self.sh, self.sw, 3)
+        b, g, r = px[:, :, 0], px[:, :, 1], px[:, :, 2]
+        ry, gy, by, ru, gu, bu, rv, gv, bv = self.rgb2yuv
+        Y = (((ry * r + gy * g + by * b) >> 15) + 16) & 0xFF
+        ra = np.arange(0, self.sh, 2)
+        rb = np.minimum(ra + 1, self.sh - 1)
+
+        def box(c):
+            return (c[ra][:, 0::2] + c[ra][:, 1::2] + c[rb][:, 0::2] + c[rb][:, 1::2]) >> 2
+        rx, gx, bx = box(r), box(g), box(b)
+        U = (((ru * rx + gu * gx + bu * bx) >> 15) + 128) & 0xFF
+        V = (((rv * rx + gv * gx + bv * bx) >> 15) + 128) & 0xFF
+        return [Y.astype(np.uint8), U.astype(np.uint8), V.astype(np.uint8)]
+
     def scale(self, planes):
+        if self.special == "shuffle":
+            return self._shuffle(planes[0])
+        if self.special == "bgr24_yv12":
+            return self._bgr24_yv12(planes[0])
         lum, u, v = self._unpack(planes)
         if self.unscaled_lut:
             return self._unscaled_lut(lum, u, v)
@@ -573,7 +686,7 @@ class OracleContext:
 
         def dither_plane(shape, offset):
             h, w = shape
-            if self.src_bpc > 8:                      # swscale.c:291-292,519-522
+            if self.sdepth > 8:                       # isNBPS||is16BPS source, swscale.c:291-292,519-522
                 return DITHER_8x8_128[(np.arange(h) & 7)[:, None], ((np.arange(w) + offset) & 7)[None, :]]
             return np.full(shape, 64, np.int64)
 

@@ -72,6 +72,22 @@ def cases():
             out.append(dict(sw=162, sh=122, sf=sf, dw=201, dh=150, df=df, flags=R.SWS_BICUBIC | BX))
             out.append(dict(sw=162, sh=122, sf=sf, dw=162, dh=160, df=df,
                             flags=R.SWS_BILINEAR | BX | R.SWS_FULL_CHR_H_INT))
+    # packed 8-bit RGB sources: pair-summed and full-resolution chroma readers,
+    # 3- and 4-byte pixels, planar / semi-planar / high-depth / full-range / RGB destinations
+    for sf in ["rgb24", "bgr24", "rgba", "bgra", "argb", "abgr"]:
+        for df in ["yuv420p", "yuv444p", "nv12", "yuv420p10le", "yuv444p16le", "yuvj420p", "rgb24"]:
+            out.append(dict(sw=162, sh=122, sf=sf, dw=162, dh=122, df=df, flags=R.SWS_BICUBIC | BX))
+            out.append(dict(sw=162, sh=122, sf=sf, dw=100, dh=75, df=df, flags=R.SWS_BILINEAR | BX))
+        out.append(dict(sw=163, sh=121, sf=sf, dw=163, dh=121, df="yuv420p", flags=R.SWS_BICUBIC | BX))
+        out.append(dict(sw=162, sh=122, sf=sf, dw=200, dh=150, df="yuv422p", flags=R.SWS_LANCZOS | BX))
+        out.append(dict(sw=162, sh=122, sf=sf, dw=120, dh=122, df="yuv420p",
+                        flags=R.SWS_BICUBIC | BX | R.SWS_FULL_CHR_H_INP))
+        out.append(dict(sw=162, sh=122, sf=sf, dw=162, dh=122, df="yuv420p", flags=R.SWS_POINT))
+    for cs in [1, 7, 9]:
+        out.append(dict(sw=160, sh=120, sf="rgb24", dw=160, dh=120, df="yuv420p", flags=R.SWS_BICUBIC | BX,
+                        colorspace=[cs, 0, cs, 0, 0, 1 << 16, 1 << 16]))
+    out.append(dict(sw=1920, sh=1080, sf="rgb24", dw=1920, dh=1080, df="yuv420p", flags=R.SWS_BICUBIC | BX, large=1))
+    out.append(dict(sw=3840, sh=2160, sf="bgra", dw=1920, dh=1080, df="nv12", flags=R.SWS_BICUBIC | BX, large=1))
     for i, c in enumerate(out):
         c.setdefault("seed", 100 + i)
         c.setdefault("mode", "extreme" if i % 7 == 3 else "noise")

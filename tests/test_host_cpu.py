@@ -56,7 +56,8 @@ def test_version_and_queries():
     L.swscale_version.restype = ctypes.c_uint
     assert L.swscale_version() >> 16 == 10          # LIBSWSCALE_VERSION_MAJOR, version_major.h:27
     assert L.sws_isSupportedInput(S.PIX_FMT["yuv420p"]) and L.sws_isSupportedOutput(S.PIX_FMT["rgb24"])
-    assert not L.sws_isSupportedInput(S.PIX_FMT["rgb24"])    # RGB input is a "next" row
+    assert L.sws_isSupportedInput(S.PIX_FMT["rgb24"])        # packed 8-bit RGB input
+    assert not L.sws_isSupportedInput(S.PIX_FMT["rgb48le"])  # 16-bit RGB is output-only
     assert not L.sws_isSupportedOutput(9999)
     co = L.sws_getCoefficients(1)
     assert [co[i] for i in range(4)] == [117489, 138438, 13975, 34925]
@@ -148,6 +149,42 @@ def test_rgb_closed_form_equals_reference_luts(cs):
         assert np.array_equal(y_table, t["y_table"])
         assert np.array_equal(rV, t["rV"]) and np.array_equal(gU, t["gU"])
         assert np.array_equal(bU, t["bU"]) and np.array_equal(gV, t["gV"])
+
+
+@pytest.mark.parametrize("cs", [0, 1, 4, 5, 7, 9])
+@pytest.mark.parametrize("sf", ["rgb24", "bgra"])
+def test_rgb2yuv_matrix_matches_oracle_and_reference(cs, sf):
+    """ff_b200_rgb2yuv_table (sws_colorspace.c) vs fill_rgb2yuv_table restated in numpy vs the real
+    reference (utils.c:614-706), for every matrix sws_getCoefficients() knows."""
+    mine = S.SwsContext(64, 64, sf, 64, 64, "yuv420p", S.SWS_BICUBIC | S.BX, plan_only=True)
+    L = S.lib()
+    L.sws_setColorspaceDetails(mine.p, L.sws_getCoefficients(cs), 0, L.sws_getCoefficients(cs), 0, 0, 1 << 16, 1 << 16)
+    assert L.sws_b200_plan_only(mine.p) == 0
+    got = mine.rgb2yuv()
+    assert got == O.rgb2yuv_table(O.YUV2RGB_COEFFS.get(cs, O.YUV2RGB_COEFFS[5]))
+    info = mine.info()
+    assert info["h_shift"] == 13 and info["srcBpc"] == 16 and info["chrSrcW"] == 32
+    if R.available() and hasattr(R.lib(), "swsref_rgb2yuv"):
+        ref = R.RefContext(64, 64, sf, 64, 64, "yuv420p", S.SWS_BICUBIC | S.BX)
+        ref.set_colorspace(cs, 0, cs, 0, 0, 1 << 16, 1 << 16)
+        assert ref.rgb2yuv() == got
+        ri = ref.info()
+        assert ri["srcBpc"] == 16 and ri["chrSrcW"] == 32
+    # a YUV source has no such matrix
+    yuv = S.SwsContext(64, 64, "yuv420p", 64, 64, "rgb24", S.SWS_BICUBIC | S.BX, plan_only=True)
+    assert yuv.rgb2yuv() is None
+
+
+def test_rgb_source_chroma_reader_selection():
+    """*_half readers only when the source width is even, SWS_FULL_CHR_H_INP is absent and the chroma
+    output is at most half the source width (utils.c:1367-1390)."""
+    for (sw, dw, df, flags, want) in [(64, 64, "yuv420p", 0, 32), (64, 64, "yuv444p", 0, 64),
+                                      (65, 65, "yuv420p", 0, 65), (64, 64, "yuv420p", S.SWS_FULL_CHR_H_INP, 64),
+                                      (64, 32, "yuv444p", 0, 32), (64, 200, "yuv420p", 0, 64)]:
+        mine = S.SwsContext(sw, 48, "rgb24", dw, 48, df, S.SWS_BICUBIC | S.BX | flags, plan_only=True)
+        assert mine.info()["chrSrcW"] == want, (sw, dw, df, flags)
+        if R.available():
+            assert R.RefContext(sw, 48, "rgb24", dw, 48, df, S.SWS_BICUBIC | S.BX | flags).info()["chrSrcW"] == want
 
 
 def test_no_device_means_loud_failure_not_cpu_fallback():

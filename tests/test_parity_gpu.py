@@ -184,3 +184,60 @@ def test_fast420_instantiations(sf, df, geom, flags):
     for mode in ("noise", "extreme"):
         name = _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=flags, seed=77, mode=mode)
         assert name.startswith("fast420"), name
+
+
+# ---- packed 8-bit RGB sources: rgb24ToY/UV[_half] and the 32-bit template readers (input.c:264-345,1068-1180) ----
+RGB_SRC = ["rgb24", "bgr24", "rgba", "bgra", "argb", "abgr"]
+
+
+@pytest.mark.parametrize("sf", RGB_SRC)
+@pytest.mark.parametrize("df", ["yuv420p", "yuv422p", "yuv444p", "nv12", "nv21", "yuv420p10le", "yuv444p16le",
+                                "yuvj420p", "rgb24", "bgr24", "rgb48le"])
+@pytest.mark.parametrize("geom,flags", [((322, 182, 322, 182), S.SWS_BICUBIC | BX),
+                                        ((323, 181, 323, 181), S.SWS_BICUBIC | BX),
+                                        ((322, 182, 160, 90), S.SWS_BILINEAR | BX),
+                                        ((322, 182, 500, 300), S.SWS_LANCZOS | BX),
+                                        ((322, 182, 200, 182), S.SWS_BICUBIC | BX | S.SWS_FULL_CHR_H_INP),
+                                        ((322, 182, 322, 182), S.SWS_POINT)])
+def test_rgb_sources(sf, df, geom, flags):
+    sw, sh, dw, dh = geom
+    for mode in ("noise", "extreme"):
+        _check(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags, seed=91, mode=mode)
+
+
+@pytest.mark.parametrize("cs", [1, 7, 9])
+@pytest.mark.parametrize("sf", ["rgb24", "abgr"])
+def test_rgb_sources_other_matrices(cs, sf):
+    _check(sw=322, sh=182, sf=sf, dw=322, dh=182, df="yuv420p", flags=S.SWS_BICUBIC | BX, seed=93,
+           colorspace=(cs, 0, cs, 0, 0, 1 << 16, 1 << 16))
+
+
+@pytest.mark.parametrize("case", [dict(sw=1920, sh=1080, sf="rgb24", dw=1920, dh=1080, df="yuv420p"),
+                                  dict(sw=3840, sh=2160, sf="bgra", dw=1920, dh=1080, df="nv12"),
+                                  dict(sw=1280, sh=720, sf="rgba", dw=1920, dh=1080, df="yuv420p10le")],
+                         ids=lambda c: "%s_%d_to_%s_%d" % (c["sf"], c["sw"], c["df"], c["dw"]))
+def test_rgb_sources_full_size(case):
+    _check(flags=S.SWS_BICUBIC | BX, seed=95, **case)
+
+
+# ---- unscaled special converters for packed RGB (swscale_unscaled.c:1843-2077,2453-2466) ----
+@pytest.mark.parametrize("sf", RGB_SRC)
+@pytest.mark.parametrize("df", RGB_SRC)
+@pytest.mark.parametrize("geom,flags", [((322, 182), S.SWS_BICUBIC | BX), ((323, 181), S.SWS_BICUBIC),
+                                        ((1030, 64), S.SWS_POINT), ((2050, 31), S.SWS_BICUBIC | S.SWS_BITEXACT)])
+def test_rgb_to_rgb_unscaled(sf, df, geom, flags):
+    """Byte shuffles (alpha carried or set to 255); with SWS_BITEXACT 24-bit -> rgba/bgra goes through the
+    scaler instead, exactly as findRgbConvFn decides."""
+    w, h = geom
+    name = _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=flags, seed=97, src_pad=5, dst_pad=3)
+    via_scaler = flags & S.SWS_BITEXACT and sf in ("rgb24", "bgr24") and df in ("rgba", "bgra")
+    assert name == ("generic_tile" if via_scaler else "rgb_shuffle"), name
+
+
+@pytest.mark.parametrize("geom", [(322, 182), (322, 181), (1920, 1080), (2, 2), (2, 1)])
+@pytest.mark.parametrize("flags", [S.SWS_BICUBIC, S.SWS_POINT | S.SWS_BITEXACT])
+def test_bgr24_to_yuv420p_unscaled_box_converter(geom, flags):
+    w, h = geom
+    for mode in ("noise", "extreme"):
+        name = _check(sw=w, sh=h, sf="bgr24", dw=w, dh=h, df="yuv420p", flags=flags, seed=99, mode=mode)
+        assert name == "bgr24_to_yv12", name
