@@ -27,6 +27,10 @@ CONFIGS = [
     ("C5a 4K yuv420p->rgba bicubic", 3840, 2160, "yuv420p", 3840, 2160, "rgba", S.SWS_BICUBIC | S.BX),
     ("C5n 4K nv12->rgb24 bicubic", 3840, 2160, "nv12", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
     ("C5b 4K nv12->bgra bicubic", 3840, 2160, "nv12", 3840, 2160, "bgra", S.SWS_BICUBIC | S.BX),
+    ("E1 4K rgb24->yuv420p bicubic", 3840, 2160, "rgb24", 3840, 2160, "yuv420p", S.SWS_BICUBIC | S.BX),
+    ("E2 4K bgra->1080p nv12 bicubic", 3840, 2160, "bgra", 1920, 1080, "nv12", S.SWS_BICUBIC | S.BX),
+    ("E3 4K bgr24->yuv420p default flags (box converter)", 3840, 2160, "bgr24", 3840, 2160, "yuv420p", S.SWS_BICUBIC),
+    ("E4 4K rgba->bgra shuffle", 3840, 2160, "rgba", 3840, 2160, "bgra", S.SWS_BICUBIC | S.BX),
     ("X1 1080p->4K yuv420p->rgb24 bicubic", 1920, 1080, "yuv420p", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
     ("X2 4K->1080p yuv420p->yuv420p bicubic", 3840, 2160, "yuv420p", 1920, 1080, "yuv420p", S.SWS_BICUBIC | S.BX),
 ]
