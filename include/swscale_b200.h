@@ -241,6 +241,12 @@ int sws_isSupportedOutput(enum AVPixelFormat pix_fmt);
 int sws_isSupportedEndiannessConversion(enum AVPixelFormat pix_fmt);
 int sws_test_format(enum AVPixelFormat format, int output);
 int sws_test_hw_format(enum AVPixelFormat format);
+/* colour-property queries: reference swscale.h:363,374,385 / format.c:627-656.  The arguments are
+ * libavutil's AVColorSpace / AVColorPrimaries / AVColorTransferCharacteristic values (ints here;
+ * include/swscale_b200_frame.h names the AVColorSpace ones). */
+int sws_test_colorspace(int colorspace, int output);
+int sws_test_primaries(int primaries, int output);
+int sws_test_transfer(int trc, int output);
 
 /* ---- SwsVector helpers: reference swscale.h:699-717 / utils.c:1956-2248 ---- */
 SwsVector *sws_allocVec(int length);
@@ -248,6 +254,15 @@ SwsVector *sws_getGaussianVec(double variance, double quality);
 void sws_scaleVec(SwsVector *a, double scalar);
 void sws_normalizeVec(SwsVector *a, double height);
 void sws_freeVec(SwsVector *a);
+/* SwsFilter builder: reference swscale.h:719-723 / utils.c:2155-2248.  sws_init_context() on this
+ * path rejects non-NULL filters with AVERROR(ENOTSUP); the builder itself is complete. */
+SwsFilter *sws_getDefaultFilter(float lumaGBlur, float chromaGBlur, float lumaSharpen, float chromaSharpen,
+                                float chromaHShift, float chromaVShift, int verbose);
+void sws_freeFilter(SwsFilter *filter);
+
+/* ---- palette helpers: reference swscale.h:753,765 / swscale_unscaled.c:2733-2760 ---- */
+void sws_convertPalette8ToPacked32(const uint8_t *src, uint8_t *dst, int num_pixels, const uint8_t *palette);
+void sws_convertPalette8ToPacked24(const uint8_t *src, uint8_t *dst, int num_pixels, const uint8_t *palette);
 
 #ifdef __cplusplus
 }

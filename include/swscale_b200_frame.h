@@ -77,6 +77,8 @@ int sws_frame_setup(SwsContext *ctx, const AVFrame *dst, const AVFrame *src);
 
 /* reference swscale.h:415 / format.c:693 */
 int sws_is_noop(const AVFrame *dst, const AVFrame *src);
+/* reference swscale.h:392 / format.c:680-691: format, colour properties, range and siting all supported */
+int sws_test_frame(const AVFrame *frame, int output);
 
 /* reference swscale.h:439 / swscale.c:1405.  dst must carry buffers (the frame-pool allocator of the
  * reference lives in libavutil); returns >= 0 or a negative AVERROR. */

@@ -120,6 +120,7 @@ __device__ __forceinline__ void rgb_chroma14(const SwsCudaPlan &P, const uint8_t
 }
 
 #include "sws_scale8.cuh"
+#include "sws_tile15.cuh"
 
 
 /* ------------------------------------------------------------------------
@@ -671,6 +672,10 @@ struct SwsCudaState {
     uint32_t *s8_hl_cl, *s8_hl_ch, *s8_hc_cl, *s8_hc_ch;
     S8VRow *s8_vl, *s8_vc;
     int fast16_ok, fast16_taps;
+    /* tile15 path */
+    int t15_ok, t15_srck, t15_ht, t15_outk, t15_tile_h, t15_nl_cap, t15_nc_cap, t15_seg_l, t15_seg_c, t15_srl, t15_src;
+    size_t t15_smem;
+    unsigned disabled;       /* SWS_B200_DISABLE: bit set of kernels switched off for A/B runs */
     Fast16Row *d_fast16_rows;
     int e2e_mode, e2e_bands; /* how sws_scale() moves page-locked host frames (see scale_host)  */
     cudaStream_t s_in, s_out;
@@ -761,6 +766,9 @@ static int plan_tiles(SwsCudaState *st)
     return AVERROR(ENOTSUP);
 }
 
+
+static int tile15_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank *hc,
+                        const SwsFirBank *vl, const SwsFirBank *vc);
 
 /* ---------------------------------------------------------------- fast420 host side */
 
@@ -918,7 +926,7 @@ static int fast420_launch(SwsCudaState *st, const uint8_t *const src[4], const i
 {
     const SwsCudaPlan *p = &st->plan;
     /* row ranges must start on a tile row; the end is clipped by the store tensor map */
-    if (!st->fast_ok || (y0 % F420_TH) || y1 <= y0 || y1 > p->dst_h)
+    if (!st->fast_ok || (st->disabled & 1) || (y0 % F420_TH) || y1 <= y0 || y1 > p->dst_h)
         return 0;
     const bool planar = p->src_layout == SWSC_SRC_PLANAR;
     const int fmt = fast420_fmt(p->dst_kind);
@@ -1046,7 +1054,7 @@ static int fast16_launch(SwsCudaState *st, const uint8_t *const src[4], const in
                          const int64_t dst_fstride[4], int nb_frames, int y0, int y1, cudaStream_t stream)
 {
     const SwsCudaPlan *p = &st->plan;
-    if (!st->fast16_ok || (y0 % F16_TH) || y1 <= y0 || y1 > p->dst_h)
+    if (!st->fast16_ok || (st->disabled & 2) || (y0 % F16_TH) || y1 <= y0 || y1 > p->dst_h)
         return 0;
     for (int i = 0; i < 3; i++)
         if (!aligned16(src[i]) || (src_stride[i] & 15) || src_stride[i] <= 0 ||
@@ -1270,7 +1278,7 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
                          const int64_t dst_fstride[4], int nb_frames, int y0, int y1, cudaStream_t stream)
 {
     const SwsCudaPlan *p = &st->plan;
-    if (!st->s8_ok)
+    if (!st->s8_ok || (st->disabled & 4))
         return 0;
     const int nsrc = p->src_layout == SWSC_SRC_PLANAR ? 3 : 2;
     for (int i = 0; i < nsrc; i++)
@@ -1376,6 +1384,20 @@ extern "C" int ff_b200_cuda_create(SwsCudaState **out, SwsCudaPlan *plan,
     ret = scale8_setup(st, hl, hc, vl, vc);
     if (ret < 0)
         return ret;
+    ret = tile15_setup(st, hl, hc, vl, vc);
+    if (ret < 0)
+        return ret;
+    {
+        /* SWS_B200_DISABLE=fast420,fast16,scale8,tile15: force the next kernel in the dispatch order (A/B runs, tests) */
+        const char *d = getenv("SWS_B200_DISABLE");
+        st->disabled = 0;
+        if (d) {
+            if (strstr(d, "fast420")) st->disabled |= 1;
+            if (strstr(d, "fast16"))  st->disabled |= 2;
+            if (strstr(d, "scale8"))  st->disabled |= 4;
+            if (strstr(d, "tile15"))  st->disabled |= 16;
+        }
+    }
     return 0;
 }
 
@@ -1418,6 +1440,151 @@ extern "C" int ff_b200_cuda_update_plan(SwsCudaState *st, const SwsCudaPlan *pla
     n.vc_coef = st->plan.vc_coef; n.vc_pos = st->plan.vc_pos; n.vc_size = st->plan.vc_size;
     st->plan = n;
     return 0;
+}
+
+/* ---------------------------------------------------------------- tile15 host side */
+
+typedef void (*tile15_kernel_t)(const SwsCudaPlan, const Tile15Args);
+
+template <int SRCK, int HT>
+static tile15_kernel_t pick_tile15_out(int outk)
+{
+    return outk == T15_OUT_PLANAR8 ? sws_tile15_kernel<SRCK, HT, T15_OUT_PLANAR8>
+         : outk == T15_OUT_PLANARN ? sws_tile15_kernel<SRCK, HT, T15_OUT_PLANARN>
+                                   : sws_tile15_kernel<SRCK, HT, T15_OUT_RGB8>;
+}
+
+template <int SRCK>
+static tile15_kernel_t pick_tile15_ht(int ht, int outk)
+{
+    return ht == 4 ? pick_tile15_out<SRCK, 4>(outk) : ht == 8 ? pick_tile15_out<SRCK, 8>(outk)
+                                                              : pick_tile15_out<SRCK, 16>(outk);
+}
+
+static tile15_kernel_t pick_tile15(int srck, int ht, int outk)
+{
+    return srck == T15_SRC_U8 ? pick_tile15_ht<T15_SRC_U8>(ht, outk)
+         : srck == T15_SRC_U16 ? pick_tile15_ht<T15_SRC_U16>(ht, outk)
+                               : pick_tile15_ht<T15_SRC_RGB>(ht, outk);
+}
+
+/* positions non-decreasing and every tap inside [0, src_len): what initFilter guarantees */
+static bool bank_regular(const SwsFirBank *b, int src_len)
+{
+    for (int i = 0; i < b->len; i++) {
+        if (b->pos[i] < 0 || b->pos[i] + b->size > src_len)
+            return false;
+        if (i && b->pos[i] < b->pos[i - 1])
+            return false;
+    }
+    return true;
+}
+
+/* widest source span (in samples) any tile of `tw` output columns reads */
+static int bank_span(const SwsFirBank *b, int tw)
+{
+    int worst = 0;
+    for (int x0 = 0; x0 < b->len; x0 += tw) {
+        const int x1 = x0 + tw - 1 < b->len - 1 ? x0 + tw - 1 : b->len - 1;
+        const int span = b->pos[x1] + b->size - b->pos[x0];
+        if (span > worst)
+            worst = span;
+    }
+    return worst;
+}
+
+static int tile15_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank *hc,
+                        const SwsFirBank *vl, const SwsFirBank *vc)
+{
+    const SwsCudaPlan *p = &st->plan;
+    st->t15_ok = 0;
+    if (p->inter_bits != 15 || p->full_chr || p->special || !p->has_chroma)
+        return 0;
+    int outk;
+    if (p->dst_kind == SWSC_DST_PLANAR8 || p->dst_kind == SWSC_DST_NV12 || p->dst_kind == SWSC_DST_NV21)
+        outk = T15_OUT_PLANAR8;
+    else if (p->dst_kind == SWSC_DST_PLANARN)
+        outk = T15_OUT_PLANARN;
+    else if (p->dst_kind >= SWSC_DST_RGB24 && p->dst_kind <= SWSC_DST_ABGR && p->chr_dst_hsub == 1)
+        outk = T15_OUT_RGB8;
+    else
+        return 0;
+    const int srck = p->src_layout == SWSC_SRC_RGB ? T15_SRC_RGB : p->src_bits == 8 ? T15_SRC_U8 : T15_SRC_U16;
+    if (srck == T15_SRC_U16 && p->src_layout != SWSC_SRC_PLANAR)
+        return 0;
+    const int fs = hl->size > hc->size ? hl->size : hc->size;
+    if (fs > 16)
+        return 0;
+    if (!bank_regular(hl, p->src_w) || !bank_regular(hc, p->chr_src_w) ||
+        !bank_regular(vl, p->src_h) || !bank_regular(vc, p->chr_src_h))
+        return 0;
+    const int ht = fs <= 4 ? 4 : fs <= 8 ? 8 : 16;
+    const int cw = T15_TW >> p->chr_dst_hsub;
+    const int seg_l = (bank_span(hl, T15_TW) + 7) & ~7;
+    const int seg_c = (bank_span(hc, cw) + 7) & ~7;
+    const size_t ss = srck == T15_SRC_U8 ? 1 : 2;
+    const int vs = p->chr_dst_vsub;
+    const size_t budget = 72 * 1024;               /* three CTAs per SM */
+    int found = 0;
+    for (int th = 32; th >= (1 << vs) && !found; th >>= 1) {
+        const int rl = max_rows_needed(st->h_vl_pos, p->vl_size, p->dst_h, th);
+        const int cth = th >> vs ? th >> vs : 1;
+        const int rc = max_rows_needed(st->h_vc_pos, p->vc_size, p->chr_dst_h, cth);
+        const size_t lines = ((size_t)rl * T15_TW + 2 * (size_t)rc * cw) * 2;
+        /* stage whole tiles when they fit, else as many rows per pass as the budget allows (>= 4) */
+        for (int div = 1; div <= 64 && !found; div *= 2) {
+            int srl = (rl + div - 1) / div, src = (rc + div - 1) / div;
+            if (div > 1 && (srl < 4 || src < 4)) {
+                srl = srl < 4 ? (rl < 4 ? rl : 4) : srl;
+                src = src < 4 ? (rc < 4 ? rc : 4) : src;
+            }
+            size_t stage = ((size_t)srl * seg_l + 2 * (size_t)src * seg_c) * ss;
+            if (stage < T15_OUT_BYTES)
+                stage = T15_OUT_BYTES;
+            stage = (stage + 15) & ~(size_t)15;
+            if (lines + stage <= budget || (th == (1 << vs) && div == 64 && lines + stage <= 200 * 1024)) {
+                st->t15_tile_h = th; st->t15_nl_cap = rl; st->t15_nc_cap = rc;
+                st->t15_srl = srl; st->t15_src = src;
+                st->t15_smem = lines + stage;
+                found = 1;
+            }
+        }
+    }
+    if (!found)
+        return 0;
+    st->t15_srck = srck; st->t15_ht = ht; st->t15_outk = outk;
+    st->t15_seg_l = seg_l; st->t15_seg_c = seg_c;
+    CUDA_OK(cudaFuncSetAttribute((const void *)pick_tile15(srck, ht, outk),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->t15_smem));
+    st->t15_ok = 1;
+    return 0;
+}
+
+static int tile15_launch(SwsCudaState *st, const uint8_t *const src[4], const int src_stride[4],
+                         const int64_t src_fstride[4], uint8_t *const dst[4], const int dst_stride[4],
+                         const int64_t dst_fstride[4], int nb_frames, int y0, int y1, cudaStream_t stream)
+{
+    if (!st->t15_ok || (st->disabled & 16))
+        return 0;
+    const SwsCudaPlan *p = &st->plan;
+    Tile15Args a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 3; i++) {
+        a.src[i] = src[i]; a.dst[i] = dst[i];
+        a.src_stride[i] = src_stride[i]; a.dst_stride[i] = dst_stride[i];
+        a.src_fstride[i] = src_fstride ? src_fstride[i] : 0;
+        a.dst_fstride[i] = dst_fstride ? dst_fstride[i] : 0;
+    }
+    a.y0 = y0; a.y1 = y1; a.tile_h = st->t15_tile_h;
+    a.nl_cap = st->t15_nl_cap; a.nc_cap = st->t15_nc_cap;
+    a.seg_l = st->t15_seg_l; a.seg_c = st->t15_seg_c;
+    a.srl = st->t15_srl; a.src_rows = st->t15_src;
+    dim3 grid((p->dst_w + T15_TW - 1) / T15_TW, (y1 - y0 + a.tile_h - 1) / a.tile_h, nb_frames);
+    pick_tile15(st->t15_srck, st->t15_ht, st->t15_outk)<<<grid, 256, st->t15_smem, stream>>>(*p, a);
+    st->kernel_name = "tile15";
+    CUDA_OK(cudaGetLastError());
+    st->launches++;
+    return 1;
 }
 
 /* whole-frame special converters; returns 1 if launched */
@@ -1493,6 +1660,9 @@ extern "C" int ff_b200_cuda_launch(SwsCudaState *st,
         if (r != 0)
             return r < 0 ? r : 0;
         r = scale8_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);
+        if (r != 0)
+            return r < 0 ? r : 0;
+        r = tile15_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);
         if (r != 0)
             return r < 0 ? r : 0;
     }
@@ -1664,7 +1834,7 @@ extern "C" int ff_b200_cuda_scale_host(SwsCudaState *st,
      *   1  zero-copy: the TMA kernel reads and writes the host frames directly
      *   2  chunked  : row bands pipelined over three streams (H2D | kernel | D2H)
      *   3  chunked H2D + kernel writing the host destination directly */
-    if (st->fast_ok && st->e2e_mode && src_y == 0 && src_h == p->src_h && y0 == 0 && y1 == p->dst_h) {
+    if (st->fast_ok && !(st->disabled & 1) && st->e2e_mode && src_y == 0 && src_h == p->src_h && y0 == 0 && y1 == p->dst_h) {
         const uint8_t *dsrc[4] = { nullptr, nullptr, nullptr, nullptr };
         uint8_t *ddst[4] = { nullptr, nullptr, nullptr, nullptr };
         bool ok = true;

@@ -238,3 +238,17 @@ API int swsref_is_noop(void *dst, void *src, const int props[6])
     d->color_range = props[3]; d->colorspace = props[4]; d->chroma_location = props[5];
     return sws_is_noop(d, s);
 }
+
+/* lumH of sws_getDefaultFilter(): pins our SwsFilter builder; returns the vector length */
+API int swsref_default_filter(float lgb, float cgb, float ls, float cs, float chs, float cvs, double out[64])
+{
+    SwsFilter *f = sws_getDefaultFilter(lgb, cgb, ls, cs, chs, cvs, 0);
+    int n;
+    if (!f)
+        return -1;
+    n = f->lumH->length;
+    for (int i = 0; i < n && i < 64; i++)
+        out[i] = f->lumH->coeff[i];
+    sws_freeFilter(f);
+    return n;
+}

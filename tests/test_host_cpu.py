@@ -235,3 +235,58 @@ def test_partition_round_robin():
     assert allf == list(range(37))
     with pytest.raises(ValueError):
         P.frames_for_rank(8, 8, 8)
+
+
+def test_reference_export_list_is_complete():
+    """the reference's libswscale exports exactly these 40 symbols (libswscale.v)."""
+    want = """sws_alloc_context sws_free_context sws_init_context sws_freeContext sws_getContext
+    sws_getCachedContext sws_scale sws_scale_frame sws_frame_setup sws_frame_start sws_frame_end sws_send_slice
+    sws_receive_slice sws_receive_slice_alignment sws_is_noop sws_test_format sws_test_hw_format
+    sws_test_colorspace sws_test_primaries sws_test_transfer sws_test_frame sws_isSupportedInput
+    sws_isSupportedOutput sws_isSupportedEndiannessConversion sws_setColorspaceDetails sws_getColorspaceDetails
+    sws_getCoefficients sws_get_class sws_allocVec sws_getGaussianVec sws_scaleVec sws_normalizeVec sws_freeVec
+    sws_getDefaultFilter sws_freeFilter sws_convertPalette8ToPacked24 sws_convertPalette8ToPacked32
+    swscale_version swscale_configuration swscale_license""".split()
+    assert len(want) == 40
+    L = S.lib()
+    missing = [s for s in want if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_colour_property_queries_and_default_filter():
+    L = S.lib()
+    assert [L.sws_test_colorspace(c, 0) for c in range(12)] == [1, 1, 1, 0, 1, 1, 1, 1, 0, 1, 0, 0]
+    assert [L.sws_test_primaries(p, 0) for p in (0, 1, 2, 3, 4, 12, 22, 23, 256, 257)] == [0, 1, 1, 0, 1, 1, 1, 0, 1, 0]
+    assert [L.sws_test_transfer(t, 1) for t in (0, 1, 2, 3, 8, 9, 10, 13, 16, 18, 19)] == [0, 1, 1, 0, 1, 0, 0, 1, 1, 1, 0]
+
+    class Vec(ctypes.Structure):
+        _fields_ = [("coeff", ctypes.POINTER(ctypes.c_double)), ("length", ctypes.c_int)]
+
+    class Filt(ctypes.Structure):
+        _fields_ = [(n, ctypes.POINTER(Vec)) for n in ("lumH", "lumV", "chrH", "chrV")]
+
+    L.sws_getDefaultFilter.restype = ctypes.POINTER(Filt)
+    L.sws_getDefaultFilter.argtypes = [ctypes.c_float] * 6 + [ctypes.c_int]
+    L.sws_freeFilter.argtypes = [ctypes.POINTER(Filt)]
+    f = L.sws_getDefaultFilter(2.0, 0.0, 0.5, 0.0, 1.0, 0.0, 0)
+    lum = f.contents.lumH.contents
+    co = [lum.coeff[i] for i in range(lum.length)]
+    assert lum.length == 7 and abs(sum(co) - 1.0) < 1e-12 and co[3] == max(co) and co[0] < 0   # blur, then unsharp
+    chr_h = f.contents.chrH.contents
+    assert [chr_h.coeff[i] for i in range(chr_h.length)] == [1.0, 0.0, 0.0]                      # identity shifted left
+    assert f.contents.chrV.contents.length == 1
+    if R.available():
+        RL = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libswsref.so"))
+        if hasattr(RL, "swsref_default_filter"):
+            out = (ctypes.c_double * 64)()
+            n = RL.swsref_default_filter(ctypes.c_float(2.0), ctypes.c_float(0.0), ctypes.c_float(0.5),
+                                         ctypes.c_float(0.0), ctypes.c_float(1.0), ctypes.c_float(0.0), out)
+            assert n == 7 and [out[i] for i in range(7)] == co
+    L.sws_freeFilter(f)
+    # the CUDA path refuses to run with one (no silent ignore)
+    pal = (ctypes.c_uint8 * 1024)(*([10, 20, 30, 40] * 256))
+    src = (ctypes.c_uint8 * 4)(0, 1, 2, 3)
+    d24, d32 = (ctypes.c_uint8 * 12)(), (ctypes.c_uint8 * 16)()
+    L.sws_convertPalette8ToPacked24(src, d24, 4, pal)
+    L.sws_convertPalette8ToPacked32(src, d32, 4, pal)
+    assert list(d24) == [10, 20, 30] * 4 and list(d32) == [10, 20, 30, 40] * 4

@@ -241,3 +241,22 @@ def test_bgr24_to_yuv420p_unscaled_box_converter(geom, flags):
     for mode in ("noise", "extreme"):
         name = _check(sw=w, sh=h, sf="bgr24", dw=w, dh=h, df="yuv420p", flags=flags, seed=99, mode=mode)
         assert name == "bgr24_to_yv12", name
+
+
+# ---- dispatch order: every conversion must give the same bytes whichever kernel serves it ----
+@pytest.mark.parametrize("case", [
+    dict(sw=644, sh=366, sf="yuv420p", dw=644, dh=366, df="rgb24", flags=S.SWS_BICUBIC | BX),      # fast420
+    dict(sw=644, sh=366, sf="yuv420p10le", dw=644, dh=366, df="rgb48le", flags=S.SWS_LANCZOS | BX),  # fast16
+    dict(sw=1280, sh=720, sf="nv12", dw=640, dh=360, df="yuv420p", flags=S.SWS_BICUBIC | BX),        # scale8
+    dict(sw=640, sh=360, sf="yuv420p", dw=1280, dh=720, df="bgra", flags=S.SWS_BICUBIC | BX),        # tile15
+    dict(sw=644, sh=366, sf="rgb24", dw=644, dh=366, df="yuv420p", flags=S.SWS_BICUBIC | BX),        # tile15
+    dict(sw=644, sh=366, sf="yuv420p10le", dw=320, dh=180, df="yuv420p", flags=S.SWS_BILINEAR | BX),  # tile15
+], ids=lambda c: "%s_%d_to_%s_%d" % (c["sf"], c["sw"], c["df"], c["dw"]))
+def test_kernel_fallback_chain_is_bit_identical(case, monkeypatch):
+    first = _check(seed=111, **case)
+    seen = [first]
+    for off in ("fast420,fast16,scale8", "fast420,fast16,scale8,tile15"):
+        monkeypatch.setenv("SWS_B200_DISABLE", off)
+        seen.append(_check(seed=111, **case))
+    assert seen[-1] == "generic_tile", seen
+    assert first != "generic_tile", seen
