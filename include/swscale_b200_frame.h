@@ -71,8 +71,42 @@ typedef struct AVFrame {
 } AVFrame;
 #endif /* AVUTIL_FRAME_H */
 
+#ifndef AVUTIL_HWCONTEXT_H
+/* What an AV_PIX_FMT_CUDA frame carries (reference libavutil/buffer.h:82-95, hwcontext.h:27-44,63-101,
+ * 118-221): frame->hw_frames_ctx is an AVBufferRef whose data points at an AVHWFramesContext;
+ * data[]/linesize[] of the frame are device pointers / pitches in the layout of sw_format. */
+typedef struct AVBufferRef {
+    void *buffer;
+    uint8_t *data;
+    size_t size;
+} AVBufferRef;
+enum AVHWDeviceType { AV_HWDEVICE_TYPE_NONE = 0, AV_HWDEVICE_TYPE_VDPAU = 1, AV_HWDEVICE_TYPE_CUDA = 2 };
+typedef struct AVHWDeviceContext {
+    const void *av_class;
+    int type;                        /* enum AVHWDeviceType */
+    void *hwctx;
+} AVHWDeviceContext;
+typedef struct AVHWFramesContext {
+    const void *av_class;
+    AVBufferRef *device_ref;         /* -> AVHWDeviceContext */
+    AVHWDeviceContext *device_ctx;
+    void *hwctx;
+    void (*free)(struct AVHWFramesContext *ctx);
+    void *user_opaque;
+    void *pool;
+    int initial_pool_size;
+    int format;                      /* AV_PIX_FMT_CUDA */
+    int sw_format;                   /* layout of the device planes */
+    int width, height;
+} AVHWFramesContext;
+#endif /* AVUTIL_HWCONTEXT_H */
+
 /* reference swscale.h:405 / swscale.c:1500.  Dynamic mode: (re)plans the conversion described by the
- * two frames (format, size, color_range, colorspace, chroma_location) with the context's flags. */
+ * two frames (format, size, color_range, colorspace, chroma_location) with the context's flags.
+ * Hardware frames: the reference accepts Vulkan frames only (swscale.c:1511-1538); this library
+ * accepts AV_PIX_FMT_CUDA frames instead under the same rules -- both frames
+ * carry a frames context, both are allocated, both live on the same CUDA device -- and converts
+ * them in place in device memory, no PCIe transfer. */
 int sws_frame_setup(SwsContext *ctx, const AVFrame *dst, const AVFrame *src);
 
 /* reference swscale.h:415 / format.c:693 */

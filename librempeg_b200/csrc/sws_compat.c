@@ -54,10 +54,14 @@ int sws_test_frame(const AVFrame *frame, int output)
 {
     if (!frame || frame->width <= 0 || frame->height <= 0)
         return 0;
-    /* hardware frames are not accepted (sws_test_hw_format: only AV_PIX_FMT_NONE) */
-    if (frame->hw_frames_ctx)
-        return 0;
-    return sws_test_format(frame->format, output) &&
+    int format = frame->format;
+    if (frame->hw_frames_ctx) {          /* ff_fmt_from_frame: test the software layout of a hardware frame */
+        const AVHWFramesContext *fc = (const AVHWFramesContext *)((const AVBufferRef *)frame->hw_frames_ctx)->data;
+        if (!fc || !sws_test_hw_format(frame->format))
+            return 0;
+        format = fc->sw_format;
+    }
+    return sws_test_format(format, output) &&
            sws_test_colorspace(frame->colorspace, output) &&
            sws_test_primaries(frame->color_primaries, output) &&
            sws_test_transfer(frame->color_trc, output) &&

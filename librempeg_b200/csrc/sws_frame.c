@@ -16,16 +16,33 @@
 
 #include "sws_internal.h"
 #include "swscale_b200_frame.h"
+#include "swscale_b200_cuda.h"
 
 typedef struct FrameDesc {
     int format, width, height, range, csp, loc;
+    int hw;                 /* 1: AV_PIX_FMT_CUDA frame, `format` is its sw_format */
 } FrameDesc;
+
+static const AVHWFramesContext *frames_ctx(const AVFrame *f)
+{
+    const AVBufferRef *ref = f->hw_frames_ctx;
+    return ref ? (const AVHWFramesContext *)ref->data : NULL;
+}
 
 /* sanitize_fmt + the fields ff_fmt_from_frame keeps (format.c:305-339,345-380) */
 static int describe(FrameDesc *d, const AVFrame *f)
 {
-    const SwsPixDesc *pd = ff_b200_pix_desc(f->format);
+    const SwsPixDesc *pd;
     d->format = f->format;
+    d->hw = 0;
+    if (f->format == AV_PIX_FMT_CUDA) {          /* ff_fmt_from_frame: hw frames describe their sw_format */
+        const AVHWFramesContext *fc = frames_ctx(f);
+        if (!fc || fc->format != AV_PIX_FMT_CUDA)
+            return AVERROR(EINVAL);
+        d->format = fc->sw_format;
+        d->hw = 1;
+    }
+    pd = ff_b200_pix_desc(d->format);
     d->width  = f->width;
     d->height = f->height;
     d->range  = f->color_range;
@@ -93,8 +110,22 @@ int sws_frame_setup(SwsContext *ctx, const AVFrame *dst, const AVFrame *src)
         return AVERROR(EINVAL);
     if (c->initialized)
         return AVERROR(EINVAL);                 /* legacy contexts use sws_frame_start() & co. */
-    if (src->hw_frames_ctx || dst->hw_frames_ctx)
-        return AVERROR(ENOTSUP);                /* use sws_cuda_scale_batch() for device frames */
+    /* if a single frame has a frames context, then both need one (swscale.c:1511-1538) */
+    if (!!src->hw_frames_ctx != !!dst->hw_frames_ctx)
+        return AVERROR(ENOTSUP);
+    if (src->hw_frames_ctx) {
+        const AVHWFramesContext *sf = frames_ctx(src), *df = frames_ctx(dst);
+        if (!src->data[0] || !dst->data[0])
+            return AVERROR(EINVAL);             /* hardware frames must already be allocated */
+        if (!sf || !df || !sf->device_ref || !df->device_ref ||
+            sf->device_ref->data != df->device_ref->data)
+            return AVERROR(EINVAL);             /* both frames must live on the same device */
+        if (((const AVHWDeviceContext *)sf->device_ref->data)->type != AV_HWDEVICE_TYPE_CUDA ||
+            src->format != AV_PIX_FMT_CUDA || dst->format != AV_PIX_FMT_CUDA)
+            return AVERROR(ENOTSUP);            /* only CUDA devices are supported */
+    } else if (src->format == AV_PIX_FMT_CUDA || dst->format == AV_PIX_FMT_CUDA) {
+        return AVERROR(EINVAL);
+    }
     if ((src->flags | dst->flags) & AV_FRAME_FLAG_INTERLACED)
         return AVERROR(ENOTSUP);
     if (src->width < 1 || src->height < 1 || dst->width < 1 || dst->height < 1)
@@ -205,6 +236,16 @@ int sws_scale_frame(SwsContext *ctx, AVFrame *dst, const AVFrame *src)
         return 0;
     if (!dst->data[0])
         return AVERROR(ENOTSUP);   /* buffer allocation needs libavutil's frame pool (swscale.c:1437-1467) */
+    if (src->format == AV_PIX_FMT_CUDA) {
+        /* device-resident planes: one launch on the context stream, complete on return */
+        ret = sws_cuda_scale_batch(c->dyn, (const uint8_t *const *)src->data, src->linesize, NULL,
+                                   dst->data, dst->linesize, NULL, 1);
+        if (ret >= 0)
+            ret = sws_cuda_sync(c->dyn);
+        if (ret < 0)
+            memcpy(c->last_error, sws_internal(c->dyn)->last_error, sizeof(c->last_error));
+        return ret < 0 ? ret : 0;
+    }
     ret = sws_scale(c->dyn, (const uint8_t *const *)src->data, src->linesize, 0, src->height,
                     dst->data, dst->linesize);
     if (ret < 0)

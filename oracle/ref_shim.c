@@ -19,6 +19,8 @@
 
 #include "config.h"
 #include "libavutil/frame.h"
+#include "libavutil/buffer.h"
+#include "libavutil/hwcontext.h"
 #include "libavutil/imgutils.h"
 #include "libavutil/pixdesc.h"
 #include "libavutil/log.h"
@@ -251,4 +253,18 @@ API int swsref_default_filter(float lgb, float cgb, float ls, float cs, float ch
         out[i] = f->lumH->coeff[i];
     sws_freeFilter(f);
     return n;
+}
+
+/* ABI facts of the structures an AV_PIX_FMT_CUDA frame carries (include/swscale_b200_frame.h mirrors them) */
+API void swsref_hw_offsets(int out[16])
+{
+    int i = 0;
+    out[i++] = offsetof(AVBufferRef, data);             out[i++] = offsetof(AVBufferRef, size);
+    out[i++] = offsetof(AVHWDeviceContext, type);       out[i++] = offsetof(AVHWDeviceContext, hwctx);
+    out[i++] = offsetof(AVHWFramesContext, device_ref); out[i++] = offsetof(AVHWFramesContext, device_ctx);
+    out[i++] = offsetof(AVHWFramesContext, hwctx);      out[i++] = offsetof(AVHWFramesContext, pool);
+    out[i++] = offsetof(AVHWFramesContext, initial_pool_size);
+    out[i++] = offsetof(AVHWFramesContext, format);     out[i++] = offsetof(AVHWFramesContext, sw_format);
+    out[i++] = offsetof(AVHWFramesContext, width);      out[i++] = offsetof(AVHWFramesContext, height);
+    out[i++] = AV_HWDEVICE_TYPE_CUDA;                   out[i++] = AV_PIX_FMT_CUDA;
 }

@@ -31,6 +31,37 @@ class AVFrame(C.Structure):
     ]
 
 
+class AVBufferRef(C.Structure):
+    _fields_ = [("buffer", C.c_void_p), ("data", C.c_void_p), ("size", C.c_size_t)]
+
+
+class AVHWDeviceContext(C.Structure):
+    _fields_ = [("av_class", C.c_void_p), ("type", C.c_int), ("hwctx", C.c_void_p)]
+
+
+class AVHWFramesContext(C.Structure):
+    _fields_ = [("av_class", C.c_void_p), ("device_ref", C.POINTER(AVBufferRef)), ("device_ctx", C.c_void_p),
+                ("hwctx", C.c_void_p), ("free", C.c_void_p), ("user_opaque", C.c_void_p), ("pool", C.c_void_p),
+                ("initial_pool_size", C.c_int), ("format", C.c_int), ("sw_format", C.c_int),
+                ("width", C.c_int), ("height", C.c_int)]
+
+
+AV_PIX_FMT_CUDA = 117
+
+
+class CudaFramesCtx:
+    """What libavutil's hwcontext_cuda would hand out: device ctx + frames ctx behind AVBufferRefs."""
+
+    def __init__(self, sw_format, w, h, dev_type=2, device=None):
+        self.dev = device or AVHWDeviceContext(None, dev_type, None)
+        self.dev_ref = AVBufferRef(None, C.addressof(self.dev), C.sizeof(self.dev))
+        self.fc = AVHWFramesContext()
+        self.fc.device_ref = C.pointer(self.dev_ref)
+        self.fc.format, self.fc.sw_format = AV_PIX_FMT_CUDA, S.pix_fmt(sw_format)
+        self.fc.width, self.fc.height = w, h
+        self.ref = AVBufferRef(None, C.addressof(self.fc), C.sizeof(self.fc))
+
+
 def _bind():
     L = S.lib()
     P = C.POINTER
@@ -74,6 +105,53 @@ def test_avframe_mirror_matches_reference_layout():
              "chroma_location", "hw_frames_ctx"]
     for n, off in zip(names, out):
         assert getattr(AVFrame, n).offset == off, n
+
+
+@pytest.mark.skipif(not R.available() or not hasattr(R.lib(), "swsref_hw_offsets"),
+                    reason="oracle/_ref/libswsref.so not built")
+def test_hw_context_mirrors_match_reference_layout():
+    out = (C.c_int * 16)()
+    R.lib().swsref_hw_offsets(out)
+    got = [AVBufferRef.data.offset, AVBufferRef.size.offset, AVHWDeviceContext.type.offset,
+           AVHWDeviceContext.hwctx.offset, AVHWFramesContext.device_ref.offset, AVHWFramesContext.device_ctx.offset,
+           AVHWFramesContext.hwctx.offset, AVHWFramesContext.pool.offset, AVHWFramesContext.initial_pool_size.offset,
+           AVHWFramesContext.format.offset, AVHWFramesContext.sw_format.offset, AVHWFramesContext.width.offset,
+           AVHWFramesContext.height.offset, 2, AV_PIX_FMT_CUDA]
+    assert got == list(out)[:15]
+
+
+def test_hw_frame_rules_without_a_device():
+    """sws_frame_setup's hardware-frame checks (swscale.c:1511-1538) are host logic: mixed hw/sw frames,
+    unallocated frames, different devices and non-CUDA devices are refused before any device work."""
+    L = _bind()
+    assert L.sws_test_hw_format(AV_PIX_FMT_CUDA) == 1 and L.sws_test_hw_format(-1) == 1
+    assert L.sws_test_hw_format(S.pix_fmt("yuv420p")) == 0
+    a, b = T.Frame("yuv420p", 64, 48), T.Frame("rgb24", 64, 48)
+    fa, fb = make_avframe(a, "yuv420p"), make_avframe(b, "rgb24")
+    ca, cb = CudaFramesCtx("yuv420p", 64, 48), CudaFramesCtx("rgb24", 64, 48)
+    L.sws_test_frame.argtypes = [C.POINTER(AVFrame), C.c_int]
+    assert L.sws_test_frame(C.byref(fa), 0) == 0                         # primaries/transfer 0 are reserved values
+    fa.color_primaries = fa.color_trc = 2                                # what av_frame_alloc() sets: unspecified
+    assert L.sws_test_frame(C.byref(fa), 0) == 1
+    ctx = L.sws_alloc_context()
+    try:
+        fa.format, fa.hw_frames_ctx = AV_PIX_FMT_CUDA, C.addressof(ca.ref)
+        assert L.sws_test_frame(C.byref(fa), 0) == 1                     # judged by its sw_format
+        assert L.sws_frame_setup(ctx, C.byref(fb), C.byref(fa)) == -95   # ENOTSUP: only one side is a hw frame
+        fb.format, fb.hw_frames_ctx = AV_PIX_FMT_CUDA, C.addressof(cb.ref)
+        assert L.sws_frame_setup(ctx, C.byref(fb), C.byref(fa)) == -22   # EINVAL: different devices
+        cb2 = CudaFramesCtx("rgb24", 64, 48, device=ca.dev)
+        cb2.fc.device_ref = ca.fc.device_ref
+        fb.hw_frames_ctx = C.addressof(cb2.ref)
+        d0 = fb.data[0]
+        fb.data[0] = None
+        assert L.sws_frame_setup(ctx, C.byref(fb), C.byref(fa)) == -22   # EINVAL: not allocated
+        fb.data[0] = d0
+        ca.dev.type = 11                                                  # AV_HWDEVICE_TYPE_VULKAN
+        assert L.sws_frame_setup(ctx, C.byref(fb), C.byref(fa)) == -95   # ENOTSUP: not a CUDA device
+        assert L.sws_is_noop(C.byref(fa), C.byref(fa)) == 1 and L.sws_is_noop(C.byref(fb), C.byref(fa)) == 0
+    finally:
+        S.lib().sws_freeContext(ctx)
 
 
 def test_sws_is_noop():
@@ -179,3 +257,47 @@ def test_legacy_frame_slice_api(geom):
     fd2 = make_avframe(dst2, df)
     assert L.sws_scale_frame(c.p, C.byref(fd2), C.byref(fs)) >= 0
     assert T.first_diff(dst2.valid(), want.valid()) is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", [("yuv420p", 1280, 720, "rgb24", 1280, 720, S.SWS_BICUBIC | S.BX),
+                                  ("nv12", 1280, 720, "bgra", 1280, 720, S.SWS_BICUBIC | S.BX),
+                                  ("yuv420p", 640, 360, "rgb24", 1280, 720, S.SWS_BICUBIC | S.BX),
+                                  ("rgb24", 1280, 720, "yuv420p", 1280, 720, S.SWS_BICUBIC | S.BX),
+                                  ("nv12", 1920, 1080, "yuv420p", 640, 360, S.SWS_BICUBIC | S.BX)])
+def test_scale_frame_cuda_hw_frames(geom):
+    """AV_PIX_FMT_CUDA frames (device pointers in data[], sw_format in the frames
+    context) convert in place in device memory and equal the host-frame result of the same call."""
+    torch = pytest.importorskip("torch")
+    sf, sw, sh, df, dw, dh, flags = geom
+    L = _bind()
+    src = T.Frame(sf, sw, sh).randomize(71)
+    want = T.Frame(df, dw, dh, fill=0)
+    props, dprops = (1, 1, 1), (0, 1, 0)        # same matrix on both sides (YUV->YUV matrix changes cascade)
+    fs, fd = make_avframe(src, sf, props), make_avframe(want, df, dprops)
+    ctx = L.sws_alloc_context()
+    ctx.contents.flags = flags
+    try:
+        assert L.sws_scale_frame(ctx, C.byref(fd), C.byref(fs)) >= 0
+
+        dev = torch.device("cuda", 0)
+        d_src = [torch.from_numpy(np.ascontiguousarray(p)).to(dev) for p in src.planes]
+        d_dst = [torch.zeros(p.shape, dtype=torch.uint8, device=dev) for p in want.planes]
+        cs, cd = CudaFramesCtx(sf, sw, sh), CudaFramesCtx(df, dw, dh)
+        cd.fc.device_ref = cs.fc.device_ref
+        hs, hd = make_avframe(src, sf, props), make_avframe(want, df, dprops)
+        for f, planes, fc in ((hs, d_src, cs), (hd, d_dst, cd)):
+            for i in range(8):
+                f.data[i] = planes[i].data_ptr() if i < len(planes) else None
+            f.format, f.hw_frames_ctx = AV_PIX_FMT_CUDA, C.addressof(fc.ref)
+        torch.cuda.synchronize()
+        ctx2 = L.sws_alloc_context()
+        ctx2.contents.flags = flags
+        try:
+            assert L.sws_scale_frame(ctx2, C.byref(hd), C.byref(hs)) >= 0
+        finally:
+            S.lib().sws_freeContext(ctx2)
+        for got, w, (rows, rb) in zip(d_dst, want.planes, want.layout):
+            assert np.array_equal(got.cpu().numpy()[:rows, :rb], w[:rows, :rb])
+    finally:
+        S.lib().sws_freeContext(ctx)
