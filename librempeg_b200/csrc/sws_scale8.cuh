@@ -88,7 +88,7 @@ __device__ __forceinline__ int s8_hfir(const unsigned char *srow, int sh, const 
         acc_h = dp4a_us(v, ch[k], acc_h);
         w0 = w1;
     }
-    return min((acc_h * 256 + acc_l) >> 7, (1 << 15) - 1);
+    return min(((acc_h << 8) + acc_l) >> 7, (1 << 15) - 1);
 }
 
 /* vertical FIR for one column (transposed 15-bit lines), result before the >> 19 */
@@ -119,6 +119,16 @@ __device__ __forceinline__ S8VRow s8_load_vrow(const S8VRow *p)
     return r;
 }
 
+
+/*
+ * Kernel shape.  One CTA = 128 x TH outputs, 256 threads, three CTAs per SM.
+ *  staging: 16 source rows per pass; warp w brings in rows 2w and 2w+1 (16-byte loads, one row segment
+ *           per warp instruction), held in registers while the previous pass is being filtered.
+ *  H:       thread = (output column, row group).  A thread filters PAIRS of vertically adjacent rows
+ *           and stores both 15-bit results with one 32-bit shared-memory store into the transposed
+ *           line buffer (column stride is an odd number of words: conflict-free for H stores and V loads).
+ *  V:       warp = output row, lane = columns lane + 32k.
+ */
 template <int FS4>
 __global__ void __launch_bounds__(256, 3)
 sws_scale8_kernel(const __grid_constant__ Scale8Args A)
@@ -139,34 +149,40 @@ sws_scale8_kernel(const __grid_constant__ Scale8Args A)
     const int ry0 = A.y0 + blockIdx.y * TH;
     const int ry1 = min(ry0 + TH, A.y1);
     const int tw = min(S8_TW, A.dst_w - x0), th = ry1 - ry0;
-    const int CW = S8_TW >> A.hs;
+    const int cs = 7 - A.hs;                 /* log2 of the chroma tile width */
+    const int CW = 1 << cs;
     const int cx0 = x0 >> A.hs;
     const int cw = min(CW, A.chr_dst_w - cx0);
     const int cy0 = ry0 >> A.vs;
     const int cy1 = (ry1 == A.dst_h) ? A.chr_dst_h : (ry1 >> A.vs);
     const int ch = cy1 - cy0;
+    const int lstride_w = A.nl_cap >> 1, cstride_w = A.nc_cap >> 1;   /* odd by construction */
 
-    int16_t *hb_l = reinterpret_cast<int16_t *>(smem_raw);
-    int16_t *hb_u = hb_l + (size_t)S8_TW * A.nl_cap;
-    int16_t *hb_v = hb_u + (size_t)CW * A.nc_cap;
-    unsigned char *stage = reinterpret_cast<unsigned char *>(hb_v + (size_t)CW * A.nc_cap);
+    uint32_t *hb_l = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *hb_u = hb_l + S8_TW * lstride_w;
+    uint32_t *hb_v = hb_u + CW * cstride_w;
+    unsigned char *stage = reinterpret_cast<unsigned char *>(hb_v + CW * cstride_w);
 
-    /* source row windows of the tile (first rows are even by construction) */
+    /* source row windows of the tile (first rows are even by construction): lane = output row */
     int lo_l = INT_MAX, hi_l = 0, lo_c = INT_MAX, hi_c = 0;
-    for (int y = ry0; y < ry1; y++) {
-        const int2 pn = __ldg(reinterpret_cast<const int2 *>(A.vl + y));
-        lo_l = min(lo_l, pn.x);
-        hi_l = max(hi_l, pn.x + 4 * pn.y);
+    if (ry0 + lane < ry1) {
+        const int2 pn = __ldg(reinterpret_cast<const int2 *>(A.vl + ry0 + lane));
+        lo_l = pn.x;
+        hi_l = pn.x + 4 * pn.y;
     }
-    for (int y = cy0; y < cy1; y++) {
-        const int2 pn = __ldg(reinterpret_cast<const int2 *>(A.vc + y));
-        lo_c = min(lo_c, pn.x);
-        hi_c = max(hi_c, pn.x + 4 * pn.y);
+    if (cy0 + lane < cy1) {
+        const int2 pn = __ldg(reinterpret_cast<const int2 *>(A.vc + cy0 + lane));
+        lo_c = pn.x;
+        hi_c = pn.x + 4 * pn.y;
     }
+    lo_l = __reduce_min_sync(0xffffffffu, lo_l);
+    hi_l = __reduce_max_sync(0xffffffffu, hi_l);
+    lo_c = __reduce_min_sync(0xffffffffu, lo_c);
+    hi_c = __reduce_max_sync(0xffffffffu, hi_c);
     const int nl = min(min(hi_l, A.src_h) - lo_l, A.nl_cap);
     const int nc = ch > 0 ? min(min(hi_c, A.chr_src_h) - lo_c, A.nc_cap) : 0;
 
-    /* ================= stage H, luma: thread = (column, row parity) ================= */
+    /* ================= stage H, luma: thread = (column, row group of 8) ================= */
     {
         const int x = tid & (S8_TW - 1), g = tid >> 7;
         const int gx = min(x0 + x, A.dst_w - 1);
@@ -179,49 +195,50 @@ sws_scale8_kernel(const __grid_constant__ Scale8Args A)
             cl[k] = __ldg(A.hl_cl + (size_t)gx * FS4 + k);
             chh[k] = __ldg(A.hl_ch + (size_t)gx * FS4 + k);
         }
-        const int nchunk = A.seg_l >> 4;
+        const int seg = A.seg_l, nchunk = seg >> 4;
         const int last16 = (A.src_stride[0] - 16) & ~15;
-        const int per_pass = S8_CH * nchunk;
-        uint4 pre[S8_PRE];
-        /* software pipeline: the loads of pass k+1 are in flight while pass k is filtered */
+        const int go0 = min(a0 + 16 * lane, last16), go1 = min(a0 + 16 * lane + 512, last16);
+        const bool v0 = lane < nchunk, v1 = lane + 32 < nchunk;
+        uint4 pre[4];
         auto fetch = [&](int r) {
 #pragma unroll
-            for (int q = 0; q < S8_PRE; q++) {
-                const int i = tid + q * 256;
-                if (i < per_pass) {
-                    const int row = i / nchunk, c = i - row * nchunk;
-                    const int sr = min(lo_l + r + row, A.src_h - 1);
-                    pre[q] = __ldg(reinterpret_cast<const uint4 *>(src0 + (size_t)sr * A.src_stride[0] +
-                                                                    min(a0 + 16 * c, last16)));
-                }
+            for (int j = 0; j < 2; j++) {
+                const int sr = min(lo_l + r + 2 * warp + j, A.src_h - 1);
+                const uint8_t *rp = src0 + (size_t)sr * A.src_stride[0];
+                if (v0) pre[2 * j] = __ldg(reinterpret_cast<const uint4 *>(rp + go0));
+                if (v1) pre[2 * j + 1] = __ldg(reinterpret_cast<const uint4 *>(rp + go1));
             }
         };
+        unsigned char *sd = stage + 2 * warp * seg + 16 * lane;
+        const unsigned char *sp = stage + 8 * g * seg + (off & ~3);
+        uint32_t *hp = hb_l + x * lstride_w + 4 * g;
         if (nl > 0)
             fetch(0);
         for (int r = 0; r < nl; r += S8_CH) {
             __syncthreads();
 #pragma unroll
-            for (int q = 0; q < S8_PRE; q++) {
-                const int i = tid + q * 256;
-                if (i < per_pass) {
-                    const int row = i / nchunk, c = i - row * nchunk;
-                    *reinterpret_cast<uint4 *>(stage + row * A.seg_l + 16 * c) = pre[q];
-                }
+            for (int j = 0; j < 2; j++) {
+                if (v0) *reinterpret_cast<uint4 *>(sd + j * seg) = pre[2 * j];
+                if (v1) *reinterpret_cast<uint4 *>(sd + j * seg + 512) = pre[2 * j + 1];
             }
             __syncthreads();
             if (r + S8_CH < nl)
                 fetch(r + S8_CH);
-            for (int rr = g; rr < S8_CH && r + rr < nl; rr += 2) {
-                const int val = s8_hfir<FS4>(stage + rr * A.seg_l + (off & ~3), sh, cl, chh);
-                if (x < tw)
-                    hb_l[(size_t)x * A.nl_cap + r + rr] = (int16_t)val;
+            const int left = nl - r - 8 * g;         /* rows of this group still inside the window */
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                if (2 * m < left) {
+                    const int va = s8_hfir<FS4>(sp + (2 * m) * seg, sh, cl, chh);
+                    const int vb = s8_hfir<FS4>(sp + (2 * m + 1) * seg, sh, cl, chh);
+                    hp[(r >> 1) + m] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
+                }
             }
         }
     }
-    /* ================= stage H, chroma: thread = (column, plane, row parity) ================= */
+    /* ================= stage H, chroma: thread = (column, plane, row group) ================= */
     if (ch > 0) {
-        const int x = tid & (CW - 1), pl = (tid / CW) & 1, g = tid / (2 * CW);
-        const int ngroups = 256 / (2 * CW);
+        const int x = tid & (CW - 1), pl = (tid >> cs) & 1, g = tid >> (cs + 1);
+        const int npair = A.hs ? 4 : 8;          /* row pairs per thread and pass */
         const int gx = min(cx0 + x, A.chr_dst_w - 1);
         const int a0 = __ldg(A.hc_pos + cx0) & ~15;
         const int off = __ldg(A.hc_pos + gx) - a0;
@@ -232,64 +249,75 @@ sws_scale8_kernel(const __grid_constant__ Scale8Args A)
             cl[k] = __ldg(A.hc_cl + (size_t)gx * FS4 + k);
             chh[k] = __ldg(A.hc_ch + (size_t)gx * FS4 + k);
         }
-        int16_t *hb = pl ? hb_v : hb_u;
+        const int seg = A.seg_c;
         const bool planar = A.src_layout == SWSC_SRC_PLANAR;
         const int uo = A.src_layout == SWSC_SRC_NV21 ? 1 : 0;     /* nv21: V first */
-        const int nchunk = planar ? A.seg_c >> 4 : A.seg_c >> 3;
-        const int per_pass = (planar ? 2 : 1) * S8_CH * nchunk;
         const int last16 = (A.src_stride[1] - 16) & ~15;
-        uint4 pre[S8_PRE];
+        /* planar: slot q = (plane q>>1, row 2w + (q&1)), chunk = lane;  nv12: slot q = (row 2w + (q>>1), chunk lane + 32(q&1)) */
+        const int nchunk = planar ? seg >> 4 : seg >> 3;
+        const int go0 = planar ? min(a0 + 16 * lane, last16) : min(2 * a0 + 16 * lane, last16);
+        const int go1 = planar ? go0 : min(2 * a0 + 16 * lane + 512, last16);
+        const bool v0 = lane < nchunk, v1 = planar ? v0 : lane + 32 < nchunk;
+        uint4 pre[4];
         auto fetch = [&](int r) {
 #pragma unroll
-            for (int q = 0; q < S8_PRE; q++) {
-                const int i = tid + q * 256;
-                if (i < per_pass) {
-                    if (planar) {
-                        const int p = i / (S8_CH * nchunk), j = i - p * (S8_CH * nchunk);
-                        const int row = j / nchunk, c = j - row * nchunk;
-                        const int sr = min(lo_c + r + row, A.chr_src_h - 1);
-                        const uint8_t *base = p ? src2 + (size_t)sr * A.src_stride[2]
-                                                : src1 + (size_t)sr * A.src_stride[1];
-                        pre[q] = __ldg(reinterpret_cast<const uint4 *>(base + min(a0 + 16 * c, last16)));
-                    } else {
-                        const int row = i / nchunk, c = i - row * nchunk;
-                        const int sr = min(lo_c + r + row, A.chr_src_h - 1);
-                        pre[q] = __ldg(reinterpret_cast<const uint4 *>(src1 + (size_t)sr * A.src_stride[1] +
-                                                                        min(2 * a0 + 16 * c, last16)));
+            for (int j = 0; j < 2; j++) {
+                const int sr = min(lo_c + r + 2 * warp + j, A.chr_src_h - 1);
+                if (planar) {
+                    if (v0) {
+                        pre[j] = __ldg(reinterpret_cast<const uint4 *>(src1 + (size_t)sr * A.src_stride[1] + go0));
+                        pre[2 + j] = __ldg(reinterpret_cast<const uint4 *>(src2 + (size_t)sr * A.src_stride[2] + go0));
                     }
+                } else {
+                    const uint8_t *rp = src1 + (size_t)sr * A.src_stride[1];
+                    if (v0) pre[2 * j] = __ldg(reinterpret_cast<const uint4 *>(rp + go0));
+                    if (v1) pre[2 * j + 1] = __ldg(reinterpret_cast<const uint4 *>(rp + go1));
                 }
             }
         };
+        const unsigned char *sp = stage + (pl * S8_CH + 2 * npair * g) * seg + (off & ~3);
+        uint32_t *hp = (pl ? hb_v : hb_u) + x * cstride_w + npair * g;
         if (nc > 0)
             fetch(0);
         for (int r = 0; r < nc; r += S8_CH) {
             __syncthreads();
+            if (planar) {
+                unsigned char *sd = stage + 2 * warp * seg + 16 * lane;
+                if (v0) {
 #pragma unroll
-            for (int q = 0; q < S8_PRE; q++) {
-                const int i = tid + q * 256;
-                if (i < per_pass) {
-                    const uint4 v = pre[q];
-                    if (planar) {
-                        const int p = i / (S8_CH * nchunk), j = i - p * (S8_CH * nchunk);
-                        const int row = j / nchunk, c = j - row * nchunk;
-                        *reinterpret_cast<uint4 *>(stage + (p * S8_CH + row) * A.seg_c + 16 * c) = v;
-                    } else {
-                        /* nv12 / nv21: 16 interleaved bytes -> 8 U + 8 V (input.c:926-941) */
-                        const int row = i / nchunk, c = i - row * nchunk;
-                        const uint2 e = make_uint2(prmt(v.x, v.y, 0x6420), prmt(v.z, v.w, 0x6420));
-                        const uint2 o = make_uint2(prmt(v.x, v.y, 0x7531), prmt(v.z, v.w, 0x7531));
-                        *reinterpret_cast<uint2 *>(stage + (uo * S8_CH + row) * A.seg_c + 8 * c) = e;
-                        *reinterpret_cast<uint2 *>(stage + ((1 - uo) * S8_CH + row) * A.seg_c + 8 * c) = o;
+                    for (int j = 0; j < 2; j++) {
+                        *reinterpret_cast<uint4 *>(sd + j * seg) = pre[j];
+                        *reinterpret_cast<uint4 *>(sd + (S8_CH + j) * seg) = pre[2 + j];
+                    }
+                }
+            } else {
+                /* nv12 / nv21: 16 interleaved bytes -> 8 U + 8 V (input.c:926-941) */
+                unsigned char *se = stage + (uo * S8_CH + 2 * warp) * seg + 8 * lane;
+                unsigned char *so = stage + ((1 - uo) * S8_CH + 2 * warp) * seg + 8 * lane;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if ((q & 1) ? v1 : v0) {
+                        const uint4 v = pre[q];
+                        const int o = (q >> 1) * seg + 256 * (q & 1);
+                        *reinterpret_cast<uint2 *>(se + o) = make_uint2(prmt(v.x, v.y, 0x6420), prmt(v.z, v.w, 0x6420));
+                        *reinterpret_cast<uint2 *>(so + o) = make_uint2(prmt(v.x, v.y, 0x7531), prmt(v.z, v.w, 0x7531));
                     }
                 }
             }
             __syncthreads();
             if (r + S8_CH < nc)
                 fetch(r + S8_CH);
-            for (int rr = g; rr < S8_CH && r + rr < nc; rr += ngroups) {
-                const int val = s8_hfir<FS4>(stage + (pl * S8_CH + rr) * A.seg_c + (off & ~3), sh, cl, chh);
-                if (x < cw)
-                    hb[(size_t)x * A.nc_cap + r + rr] = (int16_t)val;
+            const int left = nc - r - 2 * npair * g;
+            for (int mm = 0; mm < npair; mm += 4) {
+#pragma unroll
+                for (int m4 = 0; m4 < 4; m4++) {
+                    const int m = mm + m4;
+                    if (2 * m < left) {
+                        const int va = s8_hfir<FS4>(sp + (2 * m) * seg, sh, cl, chh);
+                        const int vb = s8_hfir<FS4>(sp + (2 * m + 1) * seg, sh, cl, chh);
+                        hp[(r >> 1) + m] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
+                    }
+                }
             }
         }
     }
@@ -299,37 +327,30 @@ sws_scale8_kernel(const __grid_constant__ Scale8Args A)
     for (int ty = warp; ty < th; ty += 8) {
         const int y = ry0 + ty;
         const S8VRow vr = s8_load_vrow(A.vl + y);
-        const int p2 = (vr.pos_even - lo_l) >> 1;
-        uint8_t *d = dst0 + (size_t)y * A.dst_stride[0] + x0;
+        const uint32_t *hp = hb_l + lane * lstride_w + ((vr.pos_even - lo_l) >> 1);
+        uint8_t *d = dst0 + (size_t)y * A.dst_stride[0] + x0 + lane;
 #pragma unroll
         for (int c = 0; c < S8_TW / 32; c++) {
-            const int col = lane + 32 * c;
-            const uint32_t *hp = reinterpret_cast<const uint32_t *>(hb_l + (size_t)col * A.nl_cap) + p2;
-            const int v = clip_u8(s8_vfir(hp, vr) >> 19);
-            if (col < tw)
-                d[col] = (uint8_t)v;
+            const int v = clip_u8(s8_vfir(hp + 32 * c * lstride_w, vr) >> 19);
+            if (lane + 32 * c < tw)
+                d[32 * c] = (uint8_t)v;
         }
     }
     /* ================= stage V, chroma: task = (plane, row) ================= */
     if (ch > 0) {
         const bool semi = A.dst_kind == SWSC_DST_NV12 || A.dst_kind == SWSC_DST_NV21;
+        const int first = A.dst_kind == SWSC_DST_NV21 ? 1 : 0;   /* nv12: U first */
         for (int task = warp; task < 2 * ch; task += 8) {
             const int pl = task & 1, y = cy0 + (task >> 1);
             const S8VRow vr = s8_load_vrow(A.vc + y);
-            const int p2 = (vr.pos_even - lo_c) >> 1;
-            const int16_t *hb = pl ? hb_v : hb_u;
-            for (int col = lane; col < CW; col += 32) {
-                const uint32_t *hp = reinterpret_cast<const uint32_t *>(hb + (size_t)col * A.nc_cap) + p2;
-                const int v = clip_u8(s8_vfir(hp, vr) >> 19);
-                if (col < cw) {
-                    if (!semi) {
-                        uint8_t *d = (pl ? dst2 : dst1) + (size_t)y * A.dst_stride[pl ? 2 : 1];
-                        d[cx0 + col] = (uint8_t)v;
-                    } else {
-                        const int first = A.dst_kind == SWSC_DST_NV12 ? 0 : 1;   /* nv12: U first */
-                        dst1[(size_t)y * A.dst_stride[1] + 2 * (cx0 + col) + (pl ^ first)] = (uint8_t)v;
-                    }
-                }
+            const uint32_t *hp = (pl ? hb_v : hb_u) + lane * cstride_w + ((vr.pos_even - lo_c) >> 1);
+            uint8_t *d = semi ? dst1 + (size_t)y * A.dst_stride[1] + 2 * (cx0 + lane) + (pl ^ first)
+                              : (pl ? dst2 : dst1) + (size_t)y * A.dst_stride[pl ? 2 : 1] + cx0 + lane;
+            const int dstep = semi ? 64 : 32;
+            for (int c = 0; 32 * c < CW; c++) {
+                const int v = clip_u8(s8_vfir(hp + 32 * c * cstride_w, vr) >> 19);
+                if (lane + 32 * c < cw)
+                    d[dstep * c] = (uint8_t)v;
             }
         }
     }
