@@ -665,7 +665,7 @@ struct SwsCudaState {
     const char *kernel_name;
     /* fast420 path */
     int fast_ok;
-    int s8_ok, s8_fs4, s8_tile_h, s8_nl_cap, s8_nc_cap, s8_seg_l, s8_seg_c;
+    int s8_ok, s8_fs4, s8_tile_h, s8_nl_cap, s8_nc_cap, s8_seg_l, s8_seg_c, s8_slot;
     size_t s8_smem;
     void *s8_tables;
     int *s8_hl_pos, *s8_hc_pos;
@@ -1104,7 +1104,7 @@ static int fast16_launch(SwsCudaState *st, const uint8_t *const src[4], const in
 
 /* ---------------------------------------------------------------- scale8 host side */
 
-typedef void (*scale8_kernel_t)(const Scale8Args);
+typedef void (*scale8_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Scale8Args);
 static scale8_kernel_t pick_scale8(int fs4)
 {
     return fs4 == 1 ? sws_scale8_kernel<1> : fs4 == 2 ? sws_scale8_kernel<2> : sws_scale8_kernel<4>;
@@ -1212,9 +1212,9 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     const int seg_c = ret ? -1 : s8_seg_bytes(hc, fs4, cw);
     if (seg_l < 0 || seg_c < 0)
         ret = 1;
-    else if (S8_CH * (seg_l >> 4) > S8_PRE * 256 || 2 * S8_CH * (seg_c >> 4) > S8_PRE * 256)
-        ret = 1;                      /* a staging pass must fit the per-thread prefetch registers */
-    int th = 0, nl_cap = 0, nc_cap = 0;
+    else if (seg_l > 1024 || seg_c > 512 || !get_encode_tiled())
+        ret = 1;                      /* one ring-slot row is one TMA box row of at most 256 32-bit elements */
+    int th = 0, nl_cap = 0, nc_cap = 0, slot = 0;
     size_t smem = 0;
     if (!ret) {
         ret = 1;
@@ -1222,8 +1222,8 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
             const int cth = th >> p->chr_dst_vsub ? th >> p->chr_dst_vsub : 1;
             nl_cap = s8_rows_cap(hvl, vl->len, th);
             nc_cap = s8_rows_cap(hvc, vc->len, cth);
-            const int stage = S8_CH * (seg_l > 2 * seg_c ? seg_l : 2 * seg_c);
-            smem = ((size_t)S8_TW * nl_cap + 2 * (size_t)cw * nc_cap) * 2 + stage;
+            slot = (S8_ROWS * (seg_l > 2 * seg_c ? seg_l : 2 * seg_c) + 127) & ~127;
+            smem = ((size_t)S8_TW * nl_cap + 2 * (size_t)cw * nc_cap) * 2 + (size_t)S8_STAGES * slot;
             if (smem <= 100 * 1024) {
                 ret = 0;
                 break;
@@ -1264,7 +1264,7 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     st->s8_hc_cl = (uint32_t *)(t + o_hccl); st->s8_hc_ch = (uint32_t *)(t + o_hcch);
     st->s8_vl = (S8VRow *)(t + o_vl); st->s8_vc = (S8VRow *)(t + o_vc);
     st->s8_fs4 = fs4; st->s8_tile_h = th; st->s8_nl_cap = nl_cap; st->s8_nc_cap = nc_cap;
-    st->s8_seg_l = seg_l; st->s8_seg_c = seg_c; st->s8_smem = smem;
+    st->s8_seg_l = seg_l; st->s8_seg_c = seg_c; st->s8_smem = smem; st->s8_slot = slot;
     CUDA_OK(cudaFuncSetAttribute((const void *)pick_scale8(fs4), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
     st->s8_ok = 1;
@@ -1285,12 +1285,31 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
         if (!src[i] || !aligned16(src[i]) || (src_stride[i] & 15) || src_stride[i] < 16 ||
             (nb_frames > 1 && (src_fstride[i] & 15)))
             return 0;
+    /* source planes as 32-bit-element tensors {row words, rows, frames}: a ring slot is one 8-row box */
+    CUtensorMap my, mu, mv;
+    const bool planar = p->src_layout == SWSC_SRC_PLANAR;
+    const uint64_t fs_y = nb_frames > 1 ? src_fstride[0] : (uint64_t)src_stride[0] * p->src_h;
+    const uint64_t fs_u = nb_frames > 1 ? src_fstride[1] : (uint64_t)src_stride[1] * p->chr_src_h;
+    const uint64_t cbytes = planar ? (uint64_t)p->chr_src_w : 2 * (uint64_t)p->chr_src_w;
+    int ret;
+    if ((ret = make_map_3d(&my, CU_TENSOR_MAP_DATA_TYPE_UINT32, src[0], ((uint64_t)p->src_w + 3) / 4, p->src_h,
+                           nb_frames, src_stride[0], fs_y, st->s8_seg_l / 4, S8_ROWS)) < 0 ||
+        (ret = make_map_3d(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT32, src[1], (cbytes + 3) / 4, p->chr_src_h,
+                           nb_frames, src_stride[1], fs_u, (planar ? st->s8_seg_c : 2 * st->s8_seg_c) / 4,
+                           S8_ROWS)) < 0)
+        return ret;
+    mv = mu;
+    if (planar) {
+        const uint64_t fs_v = nb_frames > 1 ? src_fstride[2] : (uint64_t)src_stride[2] * p->chr_src_h;
+        if ((ret = make_map_3d(&mv, CU_TENSOR_MAP_DATA_TYPE_UINT32, src[2], (cbytes + 3) / 4, p->chr_src_h,
+                               nb_frames, src_stride[2], fs_v, st->s8_seg_c / 4, S8_ROWS)) < 0)
+            return ret;
+    }
     Scale8Args a;
     memset(&a, 0, sizeof(a));
     for (int i = 0; i < 3; i++) {
-        a.src[i] = src[i]; a.dst[i] = dst[i];
-        a.src_stride[i] = src_stride[i]; a.dst_stride[i] = dst_stride[i];
-        a.src_fstride[i] = src_fstride ? src_fstride[i] : 0;
+        a.dst[i] = dst[i];
+        a.dst_stride[i] = dst_stride[i];
         a.dst_fstride[i] = dst_fstride ? dst_fstride[i] : 0;
     }
     a.src_w = p->src_w; a.src_h = p->src_h; a.chr_src_w = p->chr_src_w; a.chr_src_h = p->chr_src_h;
@@ -1299,11 +1318,12 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.src_layout = p->src_layout; a.dst_kind = p->dst_kind;
     a.y0 = y0; a.y1 = y1; a.tile_h = st->s8_tile_h;
     a.nl_cap = st->s8_nl_cap; a.nc_cap = st->s8_nc_cap; a.seg_l = st->s8_seg_l; a.seg_c = st->s8_seg_c;
+    a.slot_bytes = st->s8_slot;
     a.hl_pos = st->s8_hl_pos; a.hc_pos = st->s8_hc_pos;
     a.hl_cl = st->s8_hl_cl; a.hl_ch = st->s8_hl_ch; a.hc_cl = st->s8_hc_cl; a.hc_ch = st->s8_hc_ch;
     a.vl = st->s8_vl; a.vc = st->s8_vc;
     dim3 grid((p->dst_w + S8_TW - 1) / S8_TW, (y1 - y0 + st->s8_tile_h - 1) / st->s8_tile_h, nb_frames);
-    pick_scale8(st->s8_fs4)<<<grid, 256, st->s8_smem, stream>>>(a);
+    pick_scale8(st->s8_fs4)<<<grid, 256, st->s8_smem, stream>>>(my, mu, mv, a);
     st->kernel_name = "scale8_dp4a";
     CUDA_OK(cudaGetLastError());
     st->launches++;

@@ -20,8 +20,8 @@
 #pragma once
 
 #define S8_TW 128
-#define S8_CH 16         /* source rows staged per pass */
-#define S8_PRE 4         /* 16-byte loads a thread keeps in flight for the next pass */
+#define S8_ROWS 8        /* source rows per ring slot (one TMA box) */
+#define S8_STAGES 3      /* ring depth */
 #define S8_VF4 5         /* vertical taps: up to 5 groups of 4 (16 taps + parity pad) */
 
 struct S8VRow {          /* per destination row, 48 bytes */
@@ -32,16 +32,16 @@ struct S8VRow {          /* per destination row, 48 bytes */
 };
 
 struct Scale8Args {
-    const uint8_t *src[3];
     uint8_t *dst[3];
-    long long src_fstride[3], dst_fstride[3];
-    int src_stride[3], dst_stride[3];
+    long long dst_fstride[3];
+    int dst_stride[3];
     int src_w, src_h, chr_src_w, chr_src_h, dst_w, dst_h, chr_dst_w, chr_dst_h;
     int hs, vs;
     int src_layout, dst_kind;
     int y0, y1, tile_h;
     int nl_cap, nc_cap;
-    int seg_l, seg_c;
+    int seg_l, seg_c;        /* staged bytes per luma row / chroma samples per chroma row */
+    int slot_bytes;          /* one ring slot: max(8 luma rows, 8 rows of both chroma planes), 128-byte multiple */
     const int *hl_pos, *hc_pos;
     const uint32_t *hl_cl, *hl_ch, *hc_cl, *hc_ch;
     const S8VRow *vl, *vc;
@@ -120,26 +120,56 @@ __device__ __forceinline__ S8VRow s8_load_vrow(const S8VRow *p)
 }
 
 
+
+/* horizontal FIR of one staged row of interleaved chroma (nv12 / nv21) for one output column: the
+ * de-interleave of nv12ToUV_c (input.c:926-941) is two byte permutes per four taps */
+template <int FS4>
+__device__ __forceinline__ void s8_hfir_uv(const unsigned char *srow, int sh, const uint32_t (&cl)[FS4],
+                                           const uint32_t (&ch)[FS4], int &even, int &odd)
+{
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(srow);
+    uint32_t w0 = wp[0];
+    int el = 0, eh = 0, ol = 0, oh = 0;
+#pragma unroll
+    for (int k = 0; k < FS4; k++) {
+        const uint32_t w1 = wp[2 * k + 1], w2 = wp[2 * k + 2];
+        const uint32_t s0 = __funnelshift_r(w0, w1, sh), s1 = __funnelshift_r(w1, w2, sh);
+        const uint32_t e = prmt(s0, s1, 0x6420), o = prmt(s0, s1, 0x7531);
+        el = dp4a_uu(e, cl[k], el);
+        eh = dp4a_us(e, ch[k], eh);
+        ol = dp4a_uu(o, cl[k], ol);
+        oh = dp4a_us(o, ch[k], oh);
+        w0 = w2;
+    }
+    even = min(((eh << 8) + el) >> 7, (1 << 15) - 1);
+    odd = min(((oh << 8) + ol) >> 7, (1 << 15) - 1);
+}
+
 /*
  * Kernel shape.  One CTA = 128 x TH outputs, 256 threads, three CTAs per SM.
- *  staging: 16 source rows per pass; warp w brings in rows 2w and 2w+1 (16-byte loads, one row segment
- *           per warp instruction), held in registers while the previous pass is being filtered.
+ *  staging: the source rows a tile needs stream through a 3-slot shared-memory ring, 8 rows per slot,
+ *           one TMA tensor load (cp.async.bulk.tensor) per plane and slot issued by thread 0 two
+ *           slots ahead; full/empty mbarriers, no CTA-wide barrier while filtering.  Rows and columns
+ *           outside the image are zero-filled by TMA; only zero taps ever read them.  The luma slots
+ *           of a tile are followed by its chroma slots in the same ring.
  *  H:       thread = (output column, row group).  A thread filters PAIRS of vertically adjacent rows
  *           and stores both 15-bit results with one 32-bit shared-memory store into the transposed
- *           line buffer (column stride is an odd number of words: conflict-free for H stores and V loads).
+ *           line buffer (column stride is an odd number of words: conflict-free for H stores and V
+ *           loads).  Chroma: one thread filters U and V of its column (interleaved nv12 rows are
+ *           de-interleaved on the fly).
  *  V:       warp = output row, lane = columns lane + 32k.
  */
 template <int FS4>
 __global__ void __launch_bounds__(256, 3)
-sws_scale8_kernel(const __grid_constant__ Scale8Args A)
+sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_u,
+                  const __grid_constant__ CUtensorMap map_v, const __grid_constant__ Scale8Args A)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[S8_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[S8_STAGES];
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int f = blockIdx.z;
-    const uint8_t *src0 = A.src[0] + f * A.src_fstride[0];
-    const uint8_t *src1 = A.src[1] + f * A.src_fstride[1];
-    const uint8_t *src2 = A.src[2] ? A.src[2] + f * A.src_fstride[2] : nullptr;
     uint8_t *dst0 = A.dst[0] + f * A.dst_fstride[0];
     uint8_t *dst1 = A.dst[1] + f * A.dst_fstride[1];
     uint8_t *dst2 = A.dst[2] ? A.dst[2] + f * A.dst_fstride[2] : nullptr;
@@ -157,11 +187,21 @@ sws_scale8_kernel(const __grid_constant__ Scale8Args A)
     const int cy1 = (ry1 == A.dst_h) ? A.chr_dst_h : (ry1 >> A.vs);
     const int ch = cy1 - cy0;
     const int lstride_w = A.nl_cap >> 1, cstride_w = A.nc_cap >> 1;   /* odd by construction */
+    const int slot = A.slot_bytes;
 
-    uint32_t *hb_l = reinterpret_cast<uint32_t *>(smem_raw);
+    unsigned char *ring = smem_raw;
+    uint32_t *hb_l = reinterpret_cast<uint32_t *>(smem_raw + S8_STAGES * slot);
     uint32_t *hb_u = hb_l + S8_TW * lstride_w;
     uint32_t *hb_v = hb_u + CW * cstride_w;
-    unsigned char *stage = reinterpret_cast<unsigned char *>(hb_v + CW * cstride_w);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < S8_STAGES; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
 
     /* source row windows of the tile (first rows are even by construction): lane = output row */
     int lo_l = INT_MAX, hi_l = 0, lo_c = INT_MAX, hi_c = 0;
@@ -181,13 +221,58 @@ sws_scale8_kernel(const __grid_constant__ Scale8Args A)
     hi_c = __reduce_max_sync(0xffffffffu, hi_c);
     const int nl = min(min(hi_l, A.src_h) - lo_l, A.nl_cap);
     const int nc = ch > 0 ? min(min(hi_c, A.chr_src_h) - lo_c, A.nc_cap) : 0;
+    const int npl = (nl + S8_ROWS - 1) / S8_ROWS, npc = (nc + S8_ROWS - 1) / S8_ROWS;
+    const int np = npl + npc;
 
-    /* ================= stage H, luma: thread = (column, row group of 8) ================= */
+    const int a0l = __ldg(A.hl_pos + x0) & ~15;
+    const int a0c = ch > 0 ? __ldg(A.hc_pos + cx0) & ~15 : 0;
+    const bool planar = A.src_layout == SWSC_SRC_PLANAR;
+
+    /* thread 0: fill ring slot q % S8_STAGES with pass q */
+    auto issue = [&](int q) {
+        const int b = q % S8_STAGES;
+        unsigned char *d = ring + b * slot;
+        if (q < npl) {
+            mbar_expect_tx(&full_bar[b], S8_ROWS * A.seg_l);
+            tma_load_3d(d, &map_y, &full_bar[b], a0l >> 2, lo_l + S8_ROWS * q, f);
+        } else {
+            const int row = lo_c + S8_ROWS * (q - npl);
+            mbar_expect_tx(&full_bar[b], 2 * S8_ROWS * A.seg_c);
+            if (planar) {
+                tma_load_3d(d, &map_u, &full_bar[b], a0c >> 2, row, f);
+                tma_load_3d(d + S8_ROWS * A.seg_c, &map_v, &full_bar[b], a0c >> 2, row, f);
+            } else {
+                tma_load_3d(d, &map_u, &full_bar[b], a0c >> 1, row, f);
+            }
+        }
+    };
+    __syncthreads();
+    if (tid == 0) {
+        for (int q = 0; q < min(np, S8_STAGES - 1); q++)
+            issue(q);
+    }
+    /* before pass q is filtered, thread 0 refills the slot that pass q - 1 used */
+    auto advance = [&](int q) {
+        if (tid == 0 && q + S8_STAGES - 1 < np) {
+            const int qn = q + S8_STAGES - 1;
+            if (qn >= S8_STAGES)
+                mbar_wait(&empty_bar[qn % S8_STAGES], (qn / S8_STAGES - 1) & 1);
+            issue(qn);
+        }
+        __syncwarp();
+        mbar_wait(&full_bar[q % S8_STAGES], (q / S8_STAGES) & 1);
+    };
+    auto release = [&](int q) {
+        __syncwarp();
+        if (lane == 0)
+            mbar_arrive(&empty_bar[q % S8_STAGES]);
+    };
+
+    /* ================= stage H, luma: thread = (column, group of 4 rows) ================= */
     {
         const int x = tid & (S8_TW - 1), g = tid >> 7;
         const int gx = min(x0 + x, A.dst_w - 1);
-        const int a0 = __ldg(A.hl_pos + x0) & ~15;
-        const int off = __ldg(A.hl_pos + gx) - a0;
+        const int off = __ldg(A.hl_pos + gx) - a0l;
         const int sh = (off & 3) * 8;
         uint32_t cl[FS4], chh[FS4];
 #pragma unroll
@@ -195,54 +280,30 @@ sws_scale8_kernel(const __grid_constant__ Scale8Args A)
             cl[k] = __ldg(A.hl_cl + (size_t)gx * FS4 + k);
             chh[k] = __ldg(A.hl_ch + (size_t)gx * FS4 + k);
         }
-        const int seg = A.seg_l, nchunk = seg >> 4;
-        const int last16 = (A.src_stride[0] - 16) & ~15;
-        const int go0 = min(a0 + 16 * lane, last16), go1 = min(a0 + 16 * lane + 512, last16);
-        const bool v0 = lane < nchunk, v1 = lane + 32 < nchunk;
-        uint4 pre[4];
-        auto fetch = [&](int r) {
+        const int seg = A.seg_l;
+        const int so = 4 * g * seg + (off & ~3);
+        uint32_t *hp = hb_l + x * lstride_w + 2 * g;
+        for (int q = 0; q < npl; q++) {
+            advance(q);
+            const unsigned char *sp = ring + (q % S8_STAGES) * slot + so;
+            const int left = nl - S8_ROWS * q - 4 * g;        /* rows of this group still inside the window */
 #pragma unroll
-            for (int j = 0; j < 2; j++) {
-                const int sr = min(lo_l + r + 2 * warp + j, A.src_h - 1);
-                const uint8_t *rp = src0 + (size_t)sr * A.src_stride[0];
-                if (v0) pre[2 * j] = __ldg(reinterpret_cast<const uint4 *>(rp + go0));
-                if (v1) pre[2 * j + 1] = __ldg(reinterpret_cast<const uint4 *>(rp + go1));
-            }
-        };
-        unsigned char *sd = stage + 2 * warp * seg + 16 * lane;
-        const unsigned char *sp = stage + 8 * g * seg + (off & ~3);
-        uint32_t *hp = hb_l + x * lstride_w + 4 * g;
-        if (nl > 0)
-            fetch(0);
-        for (int r = 0; r < nl; r += S8_CH) {
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                if (v0) *reinterpret_cast<uint4 *>(sd + j * seg) = pre[2 * j];
-                if (v1) *reinterpret_cast<uint4 *>(sd + j * seg + 512) = pre[2 * j + 1];
-            }
-            __syncthreads();
-            if (r + S8_CH < nl)
-                fetch(r + S8_CH);
-            const int left = nl - r - 8 * g;         /* rows of this group still inside the window */
-#pragma unroll
-            for (int m = 0; m < 4; m++) {
+            for (int m = 0; m < 2; m++) {
                 if (2 * m < left) {
                     const int va = s8_hfir<FS4>(sp + (2 * m) * seg, sh, cl, chh);
                     const int vb = s8_hfir<FS4>(sp + (2 * m + 1) * seg, sh, cl, chh);
-                    hp[(r >> 1) + m] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
+                    hp[4 * q + m] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
                 }
             }
+            release(q);
         }
     }
-    /* ================= stage H, chroma: thread = (column, plane, row group) ================= */
-    if (ch > 0) {
-        const int x = tid & (CW - 1), pl = (tid >> cs) & 1, g = tid >> (cs + 1);
-        const int npair = A.hs ? 4 : 8;          /* row pairs per thread and pass */
+    /* ================= stage H, chroma: thread = (column, row group), both planes ================= */
+    if (npc > 0) {
+        const int x = tid & (CW - 1), g = tid >> cs;
+        const int npair = A.hs ? 1 : 2;          /* row pairs per thread and pass */
         const int gx = min(cx0 + x, A.chr_dst_w - 1);
-        const int a0 = __ldg(A.hc_pos + cx0) & ~15;
-        const int off = __ldg(A.hc_pos + gx) - a0;
-        const int sh = (off & 3) * 8;
+        const int off = __ldg(A.hc_pos + gx) - a0c;
         uint32_t cl[FS4], chh[FS4];
 #pragma unroll
         for (int k = 0; k < FS4; k++) {
@@ -250,75 +311,40 @@ sws_scale8_kernel(const __grid_constant__ Scale8Args A)
             chh[k] = __ldg(A.hc_ch + (size_t)gx * FS4 + k);
         }
         const int seg = A.seg_c;
-        const bool planar = A.src_layout == SWSC_SRC_PLANAR;
-        const int uo = A.src_layout == SWSC_SRC_NV21 ? 1 : 0;     /* nv21: V first */
-        const int last16 = (A.src_stride[1] - 16) & ~15;
-        /* planar: slot q = (plane q>>1, row 2w + (q&1)), chunk = lane;  nv12: slot q = (row 2w + (q>>1), chunk lane + 32(q&1)) */
-        const int nchunk = planar ? seg >> 4 : seg >> 3;
-        const int go0 = planar ? min(a0 + 16 * lane, last16) : min(2 * a0 + 16 * lane, last16);
-        const int go1 = planar ? go0 : min(2 * a0 + 16 * lane + 512, last16);
-        const bool v0 = lane < nchunk, v1 = planar ? v0 : lane + 32 < nchunk;
-        uint4 pre[4];
-        auto fetch = [&](int r) {
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                const int sr = min(lo_c + r + 2 * warp + j, A.chr_src_h - 1);
-                if (planar) {
-                    if (v0) {
-                        pre[j] = __ldg(reinterpret_cast<const uint4 *>(src1 + (size_t)sr * A.src_stride[1] + go0));
-                        pre[2 + j] = __ldg(reinterpret_cast<const uint4 *>(src2 + (size_t)sr * A.src_stride[2] + go0));
+        const bool vfirst = A.src_layout == SWSC_SRC_NV21;
+        uint32_t *hpu = hb_u + x * cstride_w + npair * g;
+        uint32_t *hpv = hb_v + x * cstride_w + npair * g;
+        for (int qc = 0; qc < npc; qc++) {
+            const int q = npl + qc;
+            advance(q);
+            const unsigned char *sb = ring + (q % S8_STAGES) * slot;
+            const int left = nc - S8_ROWS * qc - 2 * npair * g;
+            for (int m = 0; m < npair; m++) {
+                if (2 * m < left) {
+                    const int row = 2 * npair * g + 2 * m;
+                    int ua, ub, va, vb;
+                    if (planar) {
+                        const unsigned char *sp = sb + row * seg + (off & ~3);
+                        const int sh = (off & 3) * 8;
+                        ua = s8_hfir<FS4>(sp, sh, cl, chh);
+                        ub = s8_hfir<FS4>(sp + seg, sh, cl, chh);
+                        va = s8_hfir<FS4>(sp + S8_ROWS * seg, sh, cl, chh);
+                        vb = s8_hfir<FS4>(sp + (S8_ROWS + 1) * seg, sh, cl, chh);
+                    } else {
+                        const unsigned char *sp = sb + row * 2 * seg + ((2 * off) & ~3);
+                        const int sh = (off & 1) * 16;
+                        s8_hfir_uv<FS4>(sp, sh, cl, chh, ua, va);
+                        s8_hfir_uv<FS4>(sp + 2 * seg, sh, cl, chh, ub, vb);
+                        if (vfirst) {
+                            int t = ua; ua = va; va = t;
+                            t = ub; ub = vb; vb = t;
+                        }
                     }
-                } else {
-                    const uint8_t *rp = src1 + (size_t)sr * A.src_stride[1];
-                    if (v0) pre[2 * j] = __ldg(reinterpret_cast<const uint4 *>(rp + go0));
-                    if (v1) pre[2 * j + 1] = __ldg(reinterpret_cast<const uint4 *>(rp + go1));
+                    hpu[4 * qc + m] = prmt((uint32_t)ua, (uint32_t)ub, 0x5410);
+                    hpv[4 * qc + m] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
                 }
             }
-        };
-        const unsigned char *sp = stage + (pl * S8_CH + 2 * npair * g) * seg + (off & ~3);
-        uint32_t *hp = (pl ? hb_v : hb_u) + x * cstride_w + npair * g;
-        if (nc > 0)
-            fetch(0);
-        for (int r = 0; r < nc; r += S8_CH) {
-            __syncthreads();
-            if (planar) {
-                unsigned char *sd = stage + 2 * warp * seg + 16 * lane;
-                if (v0) {
-#pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        *reinterpret_cast<uint4 *>(sd + j * seg) = pre[j];
-                        *reinterpret_cast<uint4 *>(sd + (S8_CH + j) * seg) = pre[2 + j];
-                    }
-                }
-            } else {
-                /* nv12 / nv21: 16 interleaved bytes -> 8 U + 8 V (input.c:926-941) */
-                unsigned char *se = stage + (uo * S8_CH + 2 * warp) * seg + 8 * lane;
-                unsigned char *so = stage + ((1 - uo) * S8_CH + 2 * warp) * seg + 8 * lane;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if ((q & 1) ? v1 : v0) {
-                        const uint4 v = pre[q];
-                        const int o = (q >> 1) * seg + 256 * (q & 1);
-                        *reinterpret_cast<uint2 *>(se + o) = make_uint2(prmt(v.x, v.y, 0x6420), prmt(v.z, v.w, 0x6420));
-                        *reinterpret_cast<uint2 *>(so + o) = make_uint2(prmt(v.x, v.y, 0x7531), prmt(v.z, v.w, 0x7531));
-                    }
-                }
-            }
-            __syncthreads();
-            if (r + S8_CH < nc)
-                fetch(r + S8_CH);
-            const int left = nc - r - 2 * npair * g;
-            for (int mm = 0; mm < npair; mm += 4) {
-#pragma unroll
-                for (int m4 = 0; m4 < 4; m4++) {
-                    const int m = mm + m4;
-                    if (2 * m < left) {
-                        const int va = s8_hfir<FS4>(sp + (2 * m) * seg, sh, cl, chh);
-                        const int vb = s8_hfir<FS4>(sp + (2 * m + 1) * seg, sh, cl, chh);
-                        hp[(r >> 1) + m] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
-                    }
-                }
-            }
+            release(q);
         }
     }
     __syncthreads();
