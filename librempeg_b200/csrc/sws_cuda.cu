@@ -1268,6 +1268,9 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     CUDA_OK(cudaFuncSetAttribute((const void *)pick_scale8(fs4), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
     st->s8_ok = 1;
+    if (getenv("SWS_B200_DEBUG"))
+        fprintf(stderr, "[swscaler-b200] scale8: fs4=%d tile_h=%d nl_cap=%d nc_cap=%d seg_l=%d seg_c=%d slot=%d smem=%zu\n",
+                fs4, th, nl_cap, nc_cap, seg_l, seg_c, slot, smem);
     if (!st->fast_ok && !st->fast16_ok)
         st->kernel_name = "scale8_dp4a";
     return 0;
@@ -1323,7 +1326,7 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.hl_cl = st->s8_hl_cl; a.hl_ch = st->s8_hl_ch; a.hc_cl = st->s8_hc_cl; a.hc_ch = st->s8_hc_ch;
     a.vl = st->s8_vl; a.vc = st->s8_vc;
     dim3 grid((p->dst_w + S8_TW - 1) / S8_TW, (y1 - y0 + st->s8_tile_h - 1) / st->s8_tile_h, nb_frames);
-    pick_scale8(st->s8_fs4)<<<grid, 256, st->s8_smem, stream>>>(my, mu, mv, a);
+    pick_scale8(st->s8_fs4)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
     st->kernel_name = "scale8_dp4a";
     CUDA_OK(cudaGetLastError());
     st->launches++;

@@ -20,8 +20,13 @@
 #pragma once
 
 #define S8_TW 128
-#define S8_ROWS 8        /* source rows per ring slot (one TMA box) */
-#define S8_STAGES 3      /* ring depth */
+#ifndef S8_ROWS
+#define S8_ROWS 16       /* source rows per ring slot (one TMA box): 8 or 16 */
+#endif
+#ifndef S8_STAGES
+#define S8_STAGES 2      /* ring depth */
+#endif
+#define S8_THREADS 288   /* 8 filtering warps + 1 TMA producer warp */
 #define S8_VF4 5         /* vertical taps: up to 5 groups of 4 (16 taps + parity pad) */
 
 struct S8VRow {          /* per destination row, 48 bytes */
@@ -121,6 +126,39 @@ __device__ __forceinline__ S8VRow s8_load_vrow(const S8VRow *p)
 
 
 
+/* mbarrier / TMA helpers on raw shared-window addresses (computed once per kernel) */
+__device__ __forceinline__ void s8_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "S8_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra S8_DONE;\n"
+        "bra S8_WAIT;\n"
+        "S8_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void s8_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void s8_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void s8_tma_load(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y, int z)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void s8_tma_prefetch(const CUtensorMap *map, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(map), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
 /* horizontal FIR of one staged row of interleaved chroma (nv12 / nv21) for one output column: the
  * de-interleave of nv12ToUV_c (input.c:926-941) is two byte permutes per four taps */
 template <int FS4>
@@ -146,12 +184,12 @@ __device__ __forceinline__ void s8_hfir_uv(const unsigned char *srow, int sh, co
 }
 
 /*
- * Kernel shape.  One CTA = 128 x TH outputs, 256 threads, three CTAs per SM.
- *  staging: the source rows a tile needs stream through a 3-slot shared-memory ring, 8 rows per slot,
- *           one TMA tensor load (cp.async.bulk.tensor) per plane and slot issued by thread 0 two
- *           slots ahead; full/empty mbarriers, no CTA-wide barrier while filtering.  Rows and columns
- *           outside the image are zero-filled by TMA; only zero taps ever read them.  The luma slots
- *           of a tile are followed by its chroma slots in the same ring.
+ * Kernel shape.  One CTA = 128 x TH outputs, 8 filtering warps + 1 producer warp, three CTAs per SM.
+ *  staging: the source rows a tile needs stream through a shared-memory ring of S8_STAGES slots,
+ *           S8_ROWS rows per slot, one TMA tensor load (cp.async.bulk.tensor) per plane and slot
+ *           issued by the producer warp; full/empty mbarriers, no CTA-wide barrier while filtering.
+ *           Rows and columns outside the image are zero-filled by TMA; only zero taps ever read
+ *           them.  The luma slots of a tile are followed by its chroma slots in the same ring.
  *  H:       thread = (output column, row group).  A thread filters PAIRS of vertically adjacent rows
  *           and stores both 15-bit results with one 32-bit shared-memory store into the transposed
  *           line buffer (column stride is an odd number of words: conflict-free for H stores and V
@@ -160,39 +198,28 @@ __device__ __forceinline__ void s8_hfir_uv(const unsigned char *srow, int sh, co
  *  V:       warp = output row, lane = columns lane + 32k.
  */
 template <int FS4>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(S8_THREADS, 3)
 sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_u,
                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ Scale8Args A)
 {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[S8_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[S8_STAGES];
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int f = blockIdx.z;
-    uint8_t *dst0 = A.dst[0] + f * A.dst_fstride[0];
-    uint8_t *dst1 = A.dst[1] + f * A.dst_fstride[1];
-    uint8_t *dst2 = A.dst[2] ? A.dst[2] + f * A.dst_fstride[2] : nullptr;
 
     const int TH = A.tile_h;
     const int x0 = blockIdx.x * S8_TW;
     const int ry0 = A.y0 + blockIdx.y * TH;
     const int ry1 = min(ry0 + TH, A.y1);
-    const int tw = min(S8_TW, A.dst_w - x0), th = ry1 - ry0;
     const int cs = 7 - A.hs;                 /* log2 of the chroma tile width */
     const int CW = 1 << cs;
     const int cx0 = x0 >> A.hs;
-    const int cw = min(CW, A.chr_dst_w - cx0);
     const int cy0 = ry0 >> A.vs;
     const int cy1 = (ry1 == A.dst_h) ? A.chr_dst_h : (ry1 >> A.vs);
     const int ch = cy1 - cy0;
-    const int lstride_w = A.nl_cap >> 1, cstride_w = A.nc_cap >> 1;   /* odd by construction */
     const int slot = A.slot_bytes;
-
-    unsigned char *ring = smem_raw;
-    uint32_t *hb_l = reinterpret_cast<uint32_t *>(smem_raw + S8_STAGES * slot);
-    uint32_t *hb_u = hb_l + S8_TW * lstride_w;
-    uint32_t *hb_v = hb_u + CW * cstride_w;
 
     if (tid == 0) {
 #pragma unroll
@@ -222,54 +249,71 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     const int nl = min(min(hi_l, A.src_h) - lo_l, A.nl_cap);
     const int nc = ch > 0 ? min(min(hi_c, A.chr_src_h) - lo_c, A.nc_cap) : 0;
     const int npl = (nl + S8_ROWS - 1) / S8_ROWS, npc = (nc + S8_ROWS - 1) / S8_ROWS;
-    const int np = npl + npc;
 
     const int a0l = __ldg(A.hl_pos + x0) & ~15;
     const int a0c = ch > 0 ? __ldg(A.hc_pos + cx0) & ~15 : 0;
     const bool planar = A.src_layout == SWSC_SRC_PLANAR;
+    const uint32_t ring_a = smem_u32(smem_raw), full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+    __syncthreads();
 
-    /* thread 0: fill ring slot q % S8_STAGES with pass q */
-    auto issue = [&](int q) {
-        const int b = q % S8_STAGES;
-        unsigned char *d = ring + b * slot;
-        if (q < npl) {
-            mbar_expect_tx(&full_bar[b], S8_ROWS * A.seg_l);
-            tma_load_3d(d, &map_y, &full_bar[b], a0l >> 2, lo_l + S8_ROWS * q, f);
-        } else {
-            const int row = lo_c + S8_ROWS * (q - npl);
-            mbar_expect_tx(&full_bar[b], 2 * S8_ROWS * A.seg_c);
-            if (planar) {
-                tma_load_3d(d, &map_u, &full_bar[b], a0c >> 2, row, f);
-                tma_load_3d(d + S8_ROWS * A.seg_c, &map_v, &full_bar[b], a0c >> 2, row, f);
-            } else {
-                tma_load_3d(d, &map_u, &full_bar[b], a0c >> 1, row, f);
+    if (warp == 8) {
+        /* ===== producer: one thread keeps the ring full ===== */
+        if (lane == 0) {
+            int b = 0;
+            uint32_t par = 1;              /* parity of the previous use of slot b */
+            for (int q = 0; q < npl + npc; q++) {
+                if (q >= S8_STAGES)
+                    s8_wait(empty_a + 8 * b, par);          /* all 8 warps released the slot */
+                const uint32_t d = ring_a + b * slot, bar = full_a + 8 * b;
+                if (q < npl) {
+                    s8_expect_tx(bar, S8_ROWS * A.seg_l);
+                    s8_tma_load(d, &map_y, bar, a0l >> 2, lo_l + S8_ROWS * q, f);
+                } else {
+                    const int row = lo_c + S8_ROWS * (q - npl);
+                    s8_expect_tx(bar, 2 * S8_ROWS * A.seg_c);
+                    if (planar) {
+                        s8_tma_load(d, &map_u, bar, a0c >> 2, row, f);
+                        s8_tma_load(d + S8_ROWS * A.seg_c, &map_v, bar, a0c >> 2, row, f);
+                    } else {
+                        s8_tma_load(d, &map_u, bar, a0c >> 1, row, f);
+                    }
+                }
+                if (++b == S8_STAGES) {
+                    b = 0;
+                    par ^= 1;
+                }
             }
         }
-    };
-    __syncthreads();
-    if (tid == 0) {
-        for (int q = 0; q < min(np, S8_STAGES - 1); q++)
-            issue(q);
+        return;
     }
-    /* before pass q is filtered, thread 0 refills the slot that pass q - 1 used */
-    auto advance = [&](int q) {
-        if (tid == 0 && q + S8_STAGES - 1 < np) {
-            const int qn = q + S8_STAGES - 1;
-            if (qn >= S8_STAGES)
-                mbar_wait(&empty_bar[qn % S8_STAGES], (qn / S8_STAGES - 1) & 1);
-            issue(qn);
-        }
-        __syncwarp();
-        mbar_wait(&full_bar[q % S8_STAGES], (q / S8_STAGES) & 1);
-    };
-    auto release = [&](int q) {
+
+    uint8_t *dst0 = A.dst[0] + f * A.dst_fstride[0];
+    uint8_t *dst1 = A.dst[1] + f * A.dst_fstride[1];
+    uint8_t *dst2 = A.dst[2] ? A.dst[2] + f * A.dst_fstride[2] : nullptr;
+    const int tw = min(S8_TW, A.dst_w - x0), th = ry1 - ry0;
+    const int cw = min(CW, A.chr_dst_w - cx0);
+    const int lstride_w = A.nl_cap >> 1, cstride_w = A.nc_cap >> 1;   /* odd by construction */
+    const unsigned char *ring = smem_raw;
+    uint32_t *hb_l = reinterpret_cast<uint32_t *>(smem_raw + S8_STAGES * slot);
+    uint32_t *hb_u = hb_l + S8_TW * lstride_w;
+    uint32_t *hb_v = hb_u + CW * cstride_w;
+
+    /* ring position of the pass being filtered: slot sb, parity sphase */
+    int sb = 0;
+    uint32_t sphase = 0;
+    auto release = [&]() {
         __syncwarp();
         if (lane == 0)
-            mbar_arrive(&empty_bar[q % S8_STAGES]);
+            s8_arrive(empty_a + 8 * sb);
+        if (++sb == S8_STAGES) {
+            sb = 0;
+            sphase ^= 1;
+        }
     };
 
-    /* ================= stage H, luma: thread = (column, group of 4 rows) ================= */
+    /* ================= stage H, luma: thread = (column, half of the slot's rows) ================= */
     {
+        constexpr int NP = S8_ROWS / 4;          /* row pairs per thread and pass */
         const int x = tid & (S8_TW - 1), g = tid >> 7;
         const int gx = min(x0 + x, A.dst_w - 1);
         const int off = __ldg(A.hl_pos + gx) - a0l;
@@ -281,27 +325,29 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             chh[k] = __ldg(A.hl_ch + (size_t)gx * FS4 + k);
         }
         const int seg = A.seg_l;
-        const int so = 4 * g * seg + (off & ~3);
-        uint32_t *hp = hb_l + x * lstride_w + 2 * g;
+        const int so = 2 * NP * g * seg + (off & ~3);
+        uint32_t *hp = hb_l + x * lstride_w + NP * g;
+        int left = nl - 2 * NP * g;              /* rows of this thread's group still inside the window */
         for (int q = 0; q < npl; q++) {
-            advance(q);
-            const unsigned char *sp = ring + (q % S8_STAGES) * slot + so;
-            const int left = nl - S8_ROWS * q - 4 * g;        /* rows of this group still inside the window */
+            s8_wait(full_a + 8 * sb, sphase);
+            const unsigned char *sp = ring + sb * slot + so;
 #pragma unroll
-            for (int m = 0; m < 2; m++) {
+            for (int m = 0; m < NP; m++) {
                 if (2 * m < left) {
                     const int va = s8_hfir<FS4>(sp + (2 * m) * seg, sh, cl, chh);
                     const int vb = s8_hfir<FS4>(sp + (2 * m + 1) * seg, sh, cl, chh);
-                    hp[4 * q + m] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
+                    hp[m] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
                 }
             }
-            release(q);
+            hp += S8_ROWS / 2;
+            left -= S8_ROWS;
+            release();
         }
     }
     /* ================= stage H, chroma: thread = (column, row group), both planes ================= */
     if (npc > 0) {
         const int x = tid & (CW - 1), g = tid >> cs;
-        const int npair = A.hs ? 1 : 2;          /* row pairs per thread and pass */
+        const int npair = A.hs ? S8_ROWS / 8 : S8_ROWS / 4;          /* row pairs per thread and pass */
         const int gx = min(cx0 + x, A.chr_dst_w - 1);
         const int off = __ldg(A.hc_pos + gx) - a0c;
         uint32_t cl[FS4], chh[FS4];
@@ -314,25 +360,22 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
         const bool vfirst = A.src_layout == SWSC_SRC_NV21;
         uint32_t *hpu = hb_u + x * cstride_w + npair * g;
         uint32_t *hpv = hb_v + x * cstride_w + npair * g;
+        const int rowbytes = planar ? seg : 2 * seg;
+        const int so = 2 * npair * g * rowbytes + (planar ? (off & ~3) : ((2 * off) & ~3));
+        const int sh = planar ? (off & 3) * 8 : (off & 1) * 16;
+        int left = nc - 2 * npair * g;
         for (int qc = 0; qc < npc; qc++) {
-            const int q = npl + qc;
-            advance(q);
-            const unsigned char *sb = ring + (q % S8_STAGES) * slot;
-            const int left = nc - S8_ROWS * qc - 2 * npair * g;
+            s8_wait(full_a + 8 * sb, sphase);
+            const unsigned char *sp = ring + sb * slot + so;
             for (int m = 0; m < npair; m++) {
                 if (2 * m < left) {
-                    const int row = 2 * npair * g + 2 * m;
                     int ua, ub, va, vb;
                     if (planar) {
-                        const unsigned char *sp = sb + row * seg + (off & ~3);
-                        const int sh = (off & 3) * 8;
                         ua = s8_hfir<FS4>(sp, sh, cl, chh);
                         ub = s8_hfir<FS4>(sp + seg, sh, cl, chh);
                         va = s8_hfir<FS4>(sp + S8_ROWS * seg, sh, cl, chh);
                         vb = s8_hfir<FS4>(sp + (S8_ROWS + 1) * seg, sh, cl, chh);
                     } else {
-                        const unsigned char *sp = sb + row * 2 * seg + ((2 * off) & ~3);
-                        const int sh = (off & 1) * 16;
                         s8_hfir_uv<FS4>(sp, sh, cl, chh, ua, va);
                         s8_hfir_uv<FS4>(sp + 2 * seg, sh, cl, chh, ub, vb);
                         if (vfirst) {
@@ -340,14 +383,18 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                             t = ub; ub = vb; vb = t;
                         }
                     }
-                    hpu[4 * qc + m] = prmt((uint32_t)ua, (uint32_t)ub, 0x5410);
-                    hpv[4 * qc + m] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
+                    hpu[m] = prmt((uint32_t)ua, (uint32_t)ub, 0x5410);
+                    hpv[m] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
                 }
+                sp += 2 * rowbytes;
             }
-            release(q);
+            hpu += S8_ROWS / 2;
+            hpv += S8_ROWS / 2;
+            left -= S8_ROWS;
+            release();
         }
     }
-    __syncthreads();
+    asm volatile("bar.sync 1, 256;" ::: "memory");      /* the 8 filtering warps: all h-scaled lines are in place */
 
     /* ================= stage V, luma: warp = row, lane = columns lane, lane+32, ... ================= */
     for (int ty = warp; ty < th; ty += 8) {
