@@ -665,7 +665,7 @@ struct SwsCudaState {
     const char *kernel_name;
     /* fast420 path */
     int fast_ok;
-    int s8_ok, s8_fs4, s8_tile_h, s8_nl_cap, s8_nc_cap, s8_seg_l, s8_seg_c, s8_slot;
+    int s8_ok, s8_fs4, s8_tile_h, s8_nl_cap, s8_nc_cap, s8_seg_l, s8_seg_c, s8_slot, s8_vl_n4, s8_vc_n4;
     size_t s8_smem;
     void *s8_tables;
     int *s8_hl_pos, *s8_hc_pos;
@@ -1152,13 +1152,15 @@ static int s8_pack_v(const SwsFirBank *b, S8VRow *rows)
 /* rows of transposed h-scaled lines any window of th output rows needs; == 2 (mod 4) for bank spread */
 static int s8_rows_cap(const S8VRow *rows, int n, int th)
 {
-    int worst = 4;
+    int worst = 4, n4 = 0;
+    for (int y = 0; y < n; y++)            /* the kernel reads the bank's largest group count for every row */
+        if (rows[y].n4 > n4) n4 = rows[y].n4;
     for (int y = 0; y < n; y++) {
         const int y1 = y + th < n ? y + th : n;
         int lo = INT32_MAX, hi = 0;
         for (int k = y; k < y1; k++) {
             if (rows[k].pos_even < lo) lo = rows[k].pos_even;
-            if (rows[k].pos_even + 4 * rows[k].n4 > hi) hi = rows[k].pos_even + 4 * rows[k].n4;
+            if (rows[k].pos_even + 4 * n4 > hi) hi = rows[k].pos_even + 4 * n4;
         }
         if (hi - lo > worst) worst = hi - lo;
     }
@@ -1250,6 +1252,11 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     memcpy(host + o_hcp, hc->pos, sizeof(int) * hc->len);
     s8_pack_h(hl, fs4, (uint32_t *)(host + o_hlcl), (uint32_t *)(host + o_hlch));
     s8_pack_h(hc, fs4, (uint32_t *)(host + o_hccl), (uint32_t *)(host + o_hcch));
+    st->s8_vl_n4 = st->s8_vc_n4 = 0;
+    for (int y = 0; y < vl->len; y++)
+        if (hvl[y].n4 > st->s8_vl_n4) st->s8_vl_n4 = hvl[y].n4;
+    for (int y = 0; y < vc->len; y++)
+        if (hvc[y].n4 > st->s8_vc_n4) st->s8_vc_n4 = hvc[y].n4;
     memcpy(host + o_vl, hvl, sizeof(S8VRow) * vl->len);
     memcpy(host + o_vc, hvc, sizeof(S8VRow) * vc->len);
     free(hvl); free(hvc);
@@ -1322,6 +1329,7 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.y0 = y0; a.y1 = y1; a.tile_h = st->s8_tile_h;
     a.nl_cap = st->s8_nl_cap; a.nc_cap = st->s8_nc_cap; a.seg_l = st->s8_seg_l; a.seg_c = st->s8_seg_c;
     a.slot_bytes = st->s8_slot;
+    a.vl_n4 = st->s8_vl_n4; a.vc_n4 = st->s8_vc_n4;
     a.hl_pos = st->s8_hl_pos; a.hc_pos = st->s8_hc_pos;
     a.hl_cl = st->s8_hl_cl; a.hl_ch = st->s8_hl_ch; a.hc_cl = st->s8_hc_cl; a.hc_ch = st->s8_hc_ch;
     a.vl = st->s8_vl; a.vc = st->s8_vc;

@@ -45,6 +45,7 @@ struct Scale8Args {
     int src_layout, dst_kind;
     int y0, y1, tile_h;
     int nl_cap, nc_cap;
+    int vl_n4, vc_n4;        /* vertical tap groups of four in use (max over rows) */
     int seg_l, seg_c;        /* staged bytes per luma row / chroma samples per chroma row */
     int slot_bytes;          /* one ring slot: max(8 luma rows, 8 rows of both chroma planes), 128-byte multiple */
     const int *hl_pos, *hc_pos;
@@ -96,13 +97,14 @@ __device__ __forceinline__ int s8_hfir(const unsigned char *srow, int sh, const 
     return min(((acc_h << 8) + acc_l) >> 7, (1 << 15) - 1);
 }
 
-/* vertical FIR for one column (transposed 15-bit lines), result before the >> 19 */
-__device__ __forceinline__ int s8_vfir(const uint32_t *hp, const S8VRow &vr)
+/* vertical FIR for one column (transposed 15-bit lines), result before the >> 19; n4 = tap groups in
+ * use by any row of the bank (kernel argument, warp-uniform), rows with fewer have zero taps there */
+__device__ __forceinline__ int s8_vfir(const uint32_t *hp, const S8VRow &vr, int n4)
 {
     int acc_l = 64 << 12, acc_h = 0;       /* dither 64 for 8-bit sources (swscale.c:54-56,385-387) */
 #pragma unroll
     for (int k = 0; k < S8_VF4; k++) {
-        if (k < vr.n4) {
+        if (k < n4) {
             const uint32_t w0 = hp[2 * k], w1 = hp[2 * k + 1];
             acc_l = dp2a_lo_su(w0, vr.cl[k], acc_l);
             acc_h = dp2a_lo_ss(w0, vr.ch[k], acc_h);
@@ -110,7 +112,7 @@ __device__ __forceinline__ int s8_vfir(const uint32_t *hp, const S8VRow &vr)
             acc_h = dp2a_hi_ss(w1, vr.ch[k], acc_h);
         }
     }
-    return acc_h * 256 + acc_l;
+    return (acc_h << 8) + acc_l;
 }
 
 __device__ __forceinline__ S8VRow s8_load_vrow(const S8VRow *p)
@@ -397,34 +399,50 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     asm volatile("bar.sync 1, 256;" ::: "memory");      /* the 8 filtering warps: all h-scaled lines are in place */
 
     /* ================= stage V, luma: warp = row, lane = columns lane, lane+32, ... ================= */
-    for (int ty = warp; ty < th; ty += 8) {
-        const int y = ry0 + ty;
-        const S8VRow vr = s8_load_vrow(A.vl + y);
-        const uint32_t *hp = hb_l + lane * lstride_w + ((vr.pos_even - lo_l) >> 1);
-        uint8_t *d = dst0 + (size_t)y * A.dst_stride[0] + x0 + lane;
+    {
+        const int n4 = A.vl_n4;
+        S8VRow vr;
+        if (warp < th)
+            vr = s8_load_vrow(A.vl + ry0 + warp);
+        for (int ty = warp; ty < th; ty += 8) {
+            const int y = ry0 + ty;
+            S8VRow nx;
+            if (ty + 8 < th)
+                nx = s8_load_vrow(A.vl + y + 8);        /* next row's taps are in flight while this row is filtered */
+            const uint32_t *hp = hb_l + lane * lstride_w + ((vr.pos_even - lo_l) >> 1);
+            uint8_t *d = dst0 + (size_t)y * A.dst_stride[0] + x0 + lane;
 #pragma unroll
-        for (int c = 0; c < S8_TW / 32; c++) {
-            const int v = clip_u8(s8_vfir(hp + 32 * c * lstride_w, vr) >> 19);
-            if (lane + 32 * c < tw)
-                d[32 * c] = (uint8_t)v;
+            for (int c = 0; c < S8_TW / 32; c++) {
+                const int v = clip_u8(s8_vfir(hp + 32 * c * lstride_w, vr, n4) >> 19);
+                if (lane + 32 * c < tw)
+                    d[32 * c] = (uint8_t)v;
+            }
+            vr = nx;
         }
     }
     /* ================= stage V, chroma: task = (plane, row) ================= */
     if (ch > 0) {
+        const int n4 = A.vc_n4;
         const bool semi = A.dst_kind == SWSC_DST_NV12 || A.dst_kind == SWSC_DST_NV21;
         const int first = A.dst_kind == SWSC_DST_NV21 ? 1 : 0;   /* nv12: U first */
+        S8VRow vr;
+        if (warp < 2 * ch)
+            vr = s8_load_vrow(A.vc + cy0 + (warp >> 1));
         for (int task = warp; task < 2 * ch; task += 8) {
             const int pl = task & 1, y = cy0 + (task >> 1);
-            const S8VRow vr = s8_load_vrow(A.vc + y);
+            S8VRow nx;
+            if (task + 8 < 2 * ch)
+                nx = s8_load_vrow(A.vc + y + 4);
             const uint32_t *hp = (pl ? hb_v : hb_u) + lane * cstride_w + ((vr.pos_even - lo_c) >> 1);
             uint8_t *d = semi ? dst1 + (size_t)y * A.dst_stride[1] + 2 * (cx0 + lane) + (pl ^ first)
                               : (pl ? dst2 : dst1) + (size_t)y * A.dst_stride[pl ? 2 : 1] + cx0 + lane;
             const int dstep = semi ? 64 : 32;
             for (int c = 0; 32 * c < CW; c++) {
-                const int v = clip_u8(s8_vfir(hp + 32 * c * cstride_w, vr) >> 19);
+                const int v = clip_u8(s8_vfir(hp + 32 * c * cstride_w, vr, n4) >> 19);
                 if (lane + 32 * c < cw)
                     d[dstep * c] = (uint8_t)v;
             }
+            vr = nx;
         }
     }
 }
