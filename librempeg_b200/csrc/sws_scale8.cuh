@@ -97,22 +97,34 @@ __device__ __forceinline__ int s8_hfir(const unsigned char *srow, int sh, const 
     return min(((acc_h << 8) + acc_l) >> 7, (1 << 15) - 1);
 }
 
-/* vertical FIR for one column (transposed 15-bit lines), result before the >> 19; n4 = tap groups in
- * use by any row of the bank (kernel argument, warp-uniform), rows with fewer have zero taps there */
-__device__ __forceinline__ int s8_vfir(const uint32_t *hp, const S8VRow &vr, int n4)
+/* vertical FIR for NC columns (transposed 15-bit lines, cstep words apart), results before the >> 19;
+ * n4 = tap groups in use by any row of the bank (kernel argument, warp-uniform), rows with fewer have
+ * zero taps there.  Columns are the inner loop: 2 NC independent accumulator chains. */
+template <int NC>
+__device__ __forceinline__ void s8_vfir(const uint32_t *hp, int cstep, const S8VRow &vr, int n4, int (&out)[NC])
 {
-    int acc_l = 64 << 12, acc_h = 0;       /* dither 64 for 8-bit sources (swscale.c:54-56,385-387) */
+    int acc_l[NC], acc_h[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        acc_l[c] = 64 << 12;                /* dither 64 for 8-bit sources (swscale.c:54-56,385-387) */
+        acc_h[c] = 0;
+    }
 #pragma unroll
     for (int k = 0; k < S8_VF4; k++) {
         if (k < n4) {
-            const uint32_t w0 = hp[2 * k], w1 = hp[2 * k + 1];
-            acc_l = dp2a_lo_su(w0, vr.cl[k], acc_l);
-            acc_h = dp2a_lo_ss(w0, vr.ch[k], acc_h);
-            acc_l = dp2a_hi_su(w1, vr.cl[k], acc_l);
-            acc_h = dp2a_hi_ss(w1, vr.ch[k], acc_h);
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const uint32_t w0 = hp[c * cstep + 2 * k], w1 = hp[c * cstep + 2 * k + 1];
+                acc_l[c] = dp2a_lo_su(w0, vr.cl[k], acc_l[c]);
+                acc_h[c] = dp2a_lo_ss(w0, vr.ch[k], acc_h[c]);
+                acc_l[c] = dp2a_hi_su(w1, vr.cl[k], acc_l[c]);
+                acc_h[c] = dp2a_hi_ss(w1, vr.ch[k], acc_h[c]);
+            }
         }
     }
-    return (acc_h << 8) + acc_l;
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+        out[c] = clip_u8(((acc_h[c] << 8) + acc_l[c]) >> 19);
 }
 
 __device__ __forceinline__ S8VRow s8_load_vrow(const S8VRow *p)
@@ -411,12 +423,12 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 nx = s8_load_vrow(A.vl + y + 8);        /* next row's taps are in flight while this row is filtered */
             const uint32_t *hp = hb_l + lane * lstride_w + ((vr.pos_even - lo_l) >> 1);
             uint8_t *d = dst0 + (size_t)y * A.dst_stride[0] + x0 + lane;
+            int v[S8_TW / 32];
+            s8_vfir<S8_TW / 32>(hp, 32 * lstride_w, vr, n4, v);
 #pragma unroll
-            for (int c = 0; c < S8_TW / 32; c++) {
-                const int v = clip_u8(s8_vfir(hp + 32 * c * lstride_w, vr, n4) >> 19);
+            for (int c = 0; c < S8_TW / 32; c++)
                 if (lane + 32 * c < tw)
-                    d[32 * c] = (uint8_t)v;
-            }
+                    d[32 * c] = (uint8_t)v[c];
             vr = nx;
         }
     }
@@ -437,10 +449,13 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             uint8_t *d = semi ? dst1 + (size_t)y * A.dst_stride[1] + 2 * (cx0 + lane) + (pl ^ first)
                               : (pl ? dst2 : dst1) + (size_t)y * A.dst_stride[pl ? 2 : 1] + cx0 + lane;
             const int dstep = semi ? 64 : 32;
-            for (int c = 0; 32 * c < CW; c++) {
-                const int v = clip_u8(s8_vfir(hp + 32 * c * cstride_w, vr, n4) >> 19);
+            for (int c = 0; 32 * c < CW; c += 2) {
+                int v[2];
+                s8_vfir<2>(hp + 32 * c * cstride_w, 32 * cstride_w, vr, n4, v);
                 if (lane + 32 * c < cw)
-                    d[dstep * c] = (uint8_t)v;
+                    d[dstep * c] = (uint8_t)v[0];
+                if (lane + 32 * c + 32 < cw)
+                    d[dstep * (c + 1)] = (uint8_t)v[1];
             }
             vr = nx;
         }
