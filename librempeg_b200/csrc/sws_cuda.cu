@@ -1105,9 +1105,11 @@ static int fast16_launch(SwsCudaState *st, const uint8_t *const src[4], const in
 /* ---------------------------------------------------------------- scale8 host side */
 
 typedef void (*scale8_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Scale8Args);
-static scale8_kernel_t pick_scale8(int fs4)
+static scale8_kernel_t pick_scale8(int fs4, bool rgb)
 {
-    return fs4 == 1 ? sws_scale8_kernel<1> : fs4 == 2 ? sws_scale8_kernel<2> : sws_scale8_kernel<4>;
+    if (rgb)
+        return fs4 == 1 ? sws_scale8_kernel<1, true> : fs4 == 2 ? sws_scale8_kernel<2, true> : sws_scale8_kernel<4, true>;
+    return fs4 == 1 ? sws_scale8_kernel<1, false> : fs4 == 2 ? sws_scale8_kernel<2, false> : sws_scale8_kernel<4, false>;
 }
 
 /* pack one horizontal bank: per output, fs4 words of low bytes and fs4 words of high bytes */
@@ -1159,8 +1161,9 @@ static int s8_rows_cap(const S8VRow *rows, int n, int th)
         const int y1 = y + th < n ? y + th : n;
         int lo = INT32_MAX, hi = 0;
         for (int k = y; k < y1; k++) {
-            if (rows[k].pos_even < lo) lo = rows[k].pos_even;
-            if (rows[k].pos_even + 4 * n4 > hi) hi = rows[k].pos_even + 4 * n4;
+            const int pe = rows[k].pos_even & ~1;
+            if (pe < lo) lo = pe;
+            if (pe + 4 * n4 > hi) hi = pe + 4 * n4;
         }
         if (hi - lo > worst) worst = hi - lo;
     }
@@ -1195,7 +1198,12 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     st->s8_ok = 0;
     if (p->src_bits != 8 || p->inter_bits != 15 || p->range_mode || p->src_layout > SWSC_SRC_NV21)
         return 0;
-    if (p->dst_kind != SWSC_DST_PLANAR8 && p->dst_kind != SWSC_DST_NV12 && p->dst_kind != SWSC_DST_NV21)
+    /* destinations: 8-bit planar / semi-planar YUV, or packed 8-bit RGB with one chroma sample per pixel pair */
+    const bool rgb = p->dst_kind >= SWSC_DST_RGB24 && p->dst_kind <= SWSC_DST_ABGR;
+    if (rgb && (p->chr_dst_hsub != 1 || p->chr_dst_vsub != 0 || p->full_chr || p->special || p->unscaled_lut ||
+                !p->has_chroma))
+        return 0;
+    if (!rgb && p->dst_kind != SWSC_DST_PLANAR8 && p->dst_kind != SWSC_DST_NV12 && p->dst_kind != SWSC_DST_NV21)
         return 0;
     if (hl->size > 16 || hc->size > 16 || vl->size > 16 || vc->size > 16)
         return 0;
@@ -1210,6 +1218,15 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     int ret = 0;
     if (!hvl || !hvc || s8_pack_v(vl, hvl) < 0 || s8_pack_v(vc, hvc) < 0)
         ret = 1;
+    if (!ret && rgb && vl->size == 2 && vc->size == 2) {
+        /* rows the reference hands to yuv2packed2 (both filters 2-tap bilinear) round without a bias
+         * (vscale.c:148-163, output.c:1861-1864): flagged in bit 0 of the even first row */
+        for (int y = 0; y < vl->len && y < vc->len; y++) {
+            const int l0 = vl->coef[2 * y], l1 = vl->coef[2 * y + 1], c0 = vc->coef[2 * y], c1 = vc->coef[2 * y + 1];
+            if (l0 + l1 == 4096 && (unsigned)l1 <= 4096u && c0 + c1 == 4096 && (unsigned)c1 <= 4096u)
+                hvl[y].pos_even |= 1;
+        }
+    }
     const int seg_l = ret ? -1 : s8_seg_bytes(hl, fs4, S8_TW);
     const int seg_c = ret ? -1 : s8_seg_bytes(hc, fs4, cw);
     if (seg_l < 0 || seg_c < 0)
@@ -1220,17 +1237,22 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     size_t smem = 0;
     if (!ret) {
         ret = 1;
-        for (th = 32; th >= 2; th >>= 1) {
-            const int cth = th >> p->chr_dst_vsub ? th >> p->chr_dst_vsub : 1;
-            nl_cap = s8_rows_cap(hvl, vl->len, th);
-            nc_cap = s8_rows_cap(hvc, vc->len, cth);
-            slot = (S8_ROWS * (seg_l > 2 * seg_c ? seg_l : 2 * seg_c) + 127) & ~127;
-            smem = ((size_t)S8_TW * nl_cap + 2 * (size_t)cw * nc_cap) * 2 + (size_t)S8_STAGES * slot;
-            if (smem <= 100 * 1024) {
-                ret = 0;
-                break;
+        /* largest tile that still leaves three CTAs per SM (about 74 KB each); failing that, two */
+        const size_t budget[2] = { 74 * 1024 + 512, 100 * 1024 };
+        for (int pass = 0; pass < 2 && ret; pass++)
+            for (th = 32; th >= 2; th >>= 1) {
+                const int cth = th >> p->chr_dst_vsub ? th >> p->chr_dst_vsub : 1;
+                nl_cap = s8_rows_cap(hvl, vl->len, th);
+                nc_cap = s8_rows_cap(hvc, vc->len, cth);
+                slot = (S8_ROWS * (seg_l > 2 * seg_c ? seg_l : 2 * seg_c) + 127) & ~127;
+                if (rgb && S8_STAGES * slot < 8 * 512)
+                    slot = 8 * 512 / S8_STAGES;       /* the idle ring stages the packed RGB rows of the 8 warps */
+                smem = ((size_t)S8_TW * nl_cap + 2 * (size_t)cw * nc_cap) * 2 + (size_t)S8_STAGES * slot;
+                if (smem <= budget[pass]) {
+                    ret = 0;
+                    break;
+                }
             }
-        }
     }
     if (ret) {
         free(hvl); free(hvc);
@@ -1272,7 +1294,7 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     st->s8_vl = (S8VRow *)(t + o_vl); st->s8_vc = (S8VRow *)(t + o_vc);
     st->s8_fs4 = fs4; st->s8_tile_h = th; st->s8_nl_cap = nl_cap; st->s8_nc_cap = nc_cap;
     st->s8_seg_l = seg_l; st->s8_seg_c = seg_c; st->s8_smem = smem; st->s8_slot = slot;
-    CUDA_OK(cudaFuncSetAttribute((const void *)pick_scale8(fs4), cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_OK(cudaFuncSetAttribute((const void *)pick_scale8(fs4, rgb), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
     st->s8_ok = 1;
     if (getenv("SWS_B200_DEBUG"))
@@ -1330,11 +1352,14 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.nl_cap = st->s8_nl_cap; a.nc_cap = st->s8_nc_cap; a.seg_l = st->s8_seg_l; a.seg_c = st->s8_seg_c;
     a.slot_bytes = st->s8_slot;
     a.vl_n4 = st->s8_vl_n4; a.vc_n4 = st->s8_vc_n4;
+    a.cy = p->rgb.cy; a.yb = p->rgb.yb; a.base_r = p->rgb.base_r; a.base_g = p->rgb.base_g; a.base_b = p->rgb.base_b;
+    a.crv = p->rgb.crv; a.cgu = p->rgb.cgu; a.cgv = p->rgb.cgv; a.cbu = p->rgb.cbu;
+    const bool rgb = p->dst_kind >= SWSC_DST_RGB24 && p->dst_kind <= SWSC_DST_ABGR;
     a.hl_pos = st->s8_hl_pos; a.hc_pos = st->s8_hc_pos;
     a.hl_cl = st->s8_hl_cl; a.hl_ch = st->s8_hl_ch; a.hc_cl = st->s8_hc_cl; a.hc_ch = st->s8_hc_ch;
     a.vl = st->s8_vl; a.vc = st->s8_vc;
     dim3 grid((p->dst_w + S8_TW - 1) / S8_TW, (y1 - y0 + st->s8_tile_h - 1) / st->s8_tile_h, nb_frames);
-    pick_scale8(st->s8_fs4)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
+    pick_scale8(st->s8_fs4, rgb)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
     st->kernel_name = "scale8_dp4a";
     CUDA_OK(cudaGetLastError());
     st->launches++;

@@ -30,7 +30,8 @@
 #define S8_VF4 5         /* vertical taps: up to 5 groups of 4 (16 taps + parity pad) */
 
 struct S8VRow {          /* per destination row, 48 bytes */
-    int pos_even;        /* first source row, rounded down to even */
+    int pos_even;        /* first source row, rounded down to even; luma bank, RGB output: bit 0 = this row takes
+                            the bias-free yuv2packed2 rounding (vscale.c:148-163, output.c:1861-1864) */
     int n4;              /* groups of four taps in use */
     uint32_t cl[S8_VF4]; /* low bytes of the taps, four per word */
     uint32_t ch[S8_VF4]; /* high (signed) bytes */
@@ -45,6 +46,7 @@ struct Scale8Args {
     int src_layout, dst_kind;
     int y0, y1, tile_h;
     int nl_cap, nc_cap;
+    int cy, yb, base_r, base_g, base_b, crv, cgu, cgv, cbu;   /* packed RGB output: closed-form LUT constants */
     int vl_n4, vc_n4;        /* vertical tap groups of four in use (max over rows) */
     int seg_l, seg_c;        /* staged bytes per luma row / chroma samples per chroma row */
     int slot_bytes;          /* one ring slot: max(8 luma rows, 8 rows of both chroma planes), 128-byte multiple */
@@ -97,16 +99,17 @@ __device__ __forceinline__ int s8_hfir(const unsigned char *srow, int sh, const 
     return min(((acc_h << 8) + acc_l) >> 7, (1 << 15) - 1);
 }
 
-/* vertical FIR for NC columns (transposed 15-bit lines, cstep words apart), results before the >> 19;
- * n4 = tap groups in use by any row of the bank (kernel argument, warp-uniform), rows with fewer have
- * zero taps there.  Columns are the inner loop: 2 NC independent accumulator chains. */
+/* vertical FIR for NC columns (transposed 15-bit lines, cstep words apart): bias + sum of taps, before
+ * the >> 19; n4 = tap groups in use by any row of the bank (kernel argument, warp-uniform), rows with
+ * fewer have zero taps there.  Columns are the inner loop: 2 NC independent accumulator chains. */
 template <int NC>
-__device__ __forceinline__ void s8_vfir(const uint32_t *hp, int cstep, const S8VRow &vr, int n4, int (&out)[NC])
+__device__ __forceinline__ void s8_vsum(const uint32_t *hp, int cstep, const S8VRow &vr, int n4, int bias,
+                                        int (&out)[NC])
 {
     int acc_l[NC], acc_h[NC];
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-        acc_l[c] = 64 << 12;                /* dither 64 for 8-bit sources (swscale.c:54-56,385-387) */
+        acc_l[c] = bias;
         acc_h[c] = 0;
     }
 #pragma unroll
@@ -124,7 +127,17 @@ __device__ __forceinline__ void s8_vfir(const uint32_t *hp, int cstep, const S8V
     }
 #pragma unroll
     for (int c = 0; c < NC; c++)
-        out[c] = clip_u8(((acc_h[c] << 8) + acc_l[c]) >> 19);
+        out[c] = (acc_h[c] << 8) + acc_l[c];
+}
+
+/* planar 8-bit output: dither 64 for 8-bit sources (swscale.c:54-56,385-387), clip */
+template <int NC>
+__device__ __forceinline__ void s8_vfir(const uint32_t *hp, int cstep, const S8VRow &vr, int n4, int (&out)[NC])
+{
+    s8_vsum<NC>(hp, cstep, vr, n4, 64 << 12, out);
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+        out[c] = clip_u8(out[c] >> 19);
 }
 
 __device__ __forceinline__ S8VRow s8_load_vrow(const S8VRow *p)
@@ -211,7 +224,7 @@ __device__ __forceinline__ void s8_hfir_uv(const unsigned char *srow, int sh, co
  *           de-interleaved on the fly).
  *  V:       warp = output row, lane = columns lane + 32k.
  */
-template <int FS4>
+template <int FS4, bool RGB>
 __global__ void __launch_bounds__(S8_THREADS, 3)
 sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_u,
                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ Scale8Args A)
@@ -248,8 +261,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     int lo_l = INT_MAX, hi_l = 0, lo_c = INT_MAX, hi_c = 0;
     if (ry0 + lane < ry1) {
         const int2 pn = __ldg(reinterpret_cast<const int2 *>(A.vl + ry0 + lane));
-        lo_l = pn.x;
-        hi_l = pn.x + 4 * pn.y;
+        lo_l = pn.x & ~1;
+        hi_l = lo_l + 4 * pn.y;
     }
     if (cy0 + lane < cy1) {
         const int2 pn = __ldg(reinterpret_cast<const int2 *>(A.vc + cy0 + lane));
@@ -340,7 +353,10 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
         }
         const int seg = A.seg_l;
         const int so = 2 * NP * g * seg + (off & ~3);
-        uint32_t *hp = hb_l + x * lstride_w + NP * g;
+        /* RGB output: even columns in slots 0..63, odd columns in 64..127, so that a lane of the V stage
+         * finds both pixels of its pair at a conflict-free stride */
+        const int lslot = RGB ? (x >> 1) + 64 * (x & 1) : x;
+        uint32_t *hp = hb_l + lslot * lstride_w + NP * g;
         int left = nl - 2 * NP * g;              /* rows of this thread's group still inside the window */
         for (int q = 0; q < npl; q++) {
             s8_wait(full_a + 8 * sb, sphase);
@@ -409,6 +425,88 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
         }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");      /* the 8 filtering warps: all h-scaled lines are in place */
+
+    if (RGB) {
+        /* ============ stage V + yuv2rgb, packed RGB with one chroma sample per pixel pair: warp = row,
+         * lane = pairs lane and lane + 32 (yuv2rgb_X/_1/_2_c_template + yuv2rgb_write, output.c:1662-1939;
+         * the byte LUTs in closed form as in the other RGB kernels) ============ */
+        const int kind = A.dst_kind;
+        const int bpp = kind >= SWSC_DST_RGBA ? 4 : 3;
+        unsigned char *orow = smem_raw + warp * 512;          /* the ring is idle now: 512 B of row staging per warp */
+        const int cy = A.cy, yb = A.yb;
+        S8VRow vl, vc;
+        if (warp < th) {
+            vl = s8_load_vrow(A.vl + ry0 + warp);
+            vc = s8_load_vrow(A.vc + ry0 + warp);
+        }
+        for (int ty = warp; ty < th; ty += 8) {
+            const int y = ry0 + ty;
+            S8VRow nl_, nc_;
+            if (ty + 8 < th) {
+                nl_ = s8_load_vrow(A.vl + y + 8);
+                nc_ = s8_load_vrow(A.vc + y + 8);
+            }
+            const int bias = (vl.pos_even & 1) ? 0 : 1 << 18;
+            int Y[4], U[2], V[2];
+            s8_vsum<4>(hb_l + lane * lstride_w + (((vl.pos_even & ~1) - lo_l) >> 1), 32 * lstride_w, vl, A.vl_n4, bias, Y);
+            s8_vsum<2>(hb_u + lane * cstride_w + ((vc.pos_even - lo_c) >> 1), 32 * cstride_w, vc, A.vc_n4, bias, U);
+            s8_vsum<2>(hb_v + lane * cstride_w + ((vc.pos_even - lo_c) >> 1), 32 * cstride_w, vc, A.vc_n4, bias, V);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int y1v = Y[k] >> 19, y2v = Y[k + 2] >> 19;
+                const int u8 = clamp_u8(U[k] >> 19), v8 = clamp_u8(V[k] >> 19);
+                const int pR = (A.base_r + ((v8 * A.crv) >> 16)) * cy + yb;
+                const int pG = (A.base_g + ((u8 * A.cgu) >> 16) + ((v8 * A.cgv) >> 16)) * cy + yb;
+                const int pB = (A.base_b + ((u8 * A.cbu) >> 16)) * cy + yb;
+                const uint32_t tRa = y1v * cy + pR, tGa = y1v * cy + pG, tBa = y1v * cy + pB;
+                const uint32_t tRb = y2v * cy + pR, tGb = y2v * cy + pG, tBb = y2v * cy + pB;
+                constexpr uint32_t FF = 0x00FF0000u;
+                const int p = lane + 32 * k;
+                if (bpp == 3) {
+                    uint32_t h0, h1, h2;
+                    if (kind == SWSC_DST_RGB24) {
+                        h0 = clamp_u8x2(prmt(tRa, tGa, 0x7632)); h1 = clamp_u8x2(prmt(tBa, tRb, 0x7632));
+                        h2 = clamp_u8x2(prmt(tGb, tBb, 0x7632));
+                    } else {
+                        h0 = clamp_u8x2(prmt(tBa, tGa, 0x7632)); h1 = clamp_u8x2(prmt(tRa, tBb, 0x7632));
+                        h2 = clamp_u8x2(prmt(tGb, tRb, 0x7632));
+                    }
+                    uint16_t *o = reinterpret_cast<uint16_t *>(orow + 6 * p);
+                    o[0] = (uint16_t)prmt(h0, 0u, 0x4420); o[1] = (uint16_t)prmt(h1, 0u, 0x4420);
+                    o[2] = (uint16_t)prmt(h2, 0u, 0x4420);
+                } else {
+                    uint32_t a0, a1, b0, b1;
+                    if (kind == SWSC_DST_RGBA) {
+                        a0 = prmt(tRa, tGa, 0x7632); a1 = prmt(tBa, FF, 0x7632); b0 = prmt(tRb, tGb, 0x7632); b1 = prmt(tBb, FF, 0x7632);
+                    } else if (kind == SWSC_DST_BGRA) {
+                        a0 = prmt(tBa, tGa, 0x7632); a1 = prmt(tRa, FF, 0x7632); b0 = prmt(tBb, tGb, 0x7632); b1 = prmt(tRb, FF, 0x7632);
+                    } else if (kind == SWSC_DST_ARGB) {
+                        a0 = prmt(FF, tRa, 0x7632); a1 = prmt(tGa, tBa, 0x7632); b0 = prmt(FF, tRb, 0x7632); b1 = prmt(tGb, tBb, 0x7632);
+                    } else {
+                        a0 = prmt(FF, tBa, 0x7632); a1 = prmt(tGa, tRa, 0x7632); b0 = prmt(FF, tBb, 0x7632); b1 = prmt(tGb, tRb, 0x7632);
+                    }
+                    a0 = clamp_u8x2(a0); a1 = clamp_u8x2(a1); b0 = clamp_u8x2(b0); b1 = clamp_u8x2(b1);
+                    *reinterpret_cast<uint2 *>(orow + 8 * p) = make_uint2(prmt(a0, a1, 0x6420), prmt(b0, b1, 0x6420));
+                }
+            }
+            __syncwarp();
+            /* copy the finished row out: 16-byte stores when the destination row allows it */
+            uint8_t *d = dst0 + (size_t)y * A.dst_stride[0] + (size_t)x0 * bpp;
+            const int nbytes = tw * bpp;
+            int done = 0;
+            if (((uintptr_t)d & 15) == 0) {
+                for (int i = lane; i < (nbytes >> 4); i += 32)
+                    reinterpret_cast<uint4 *>(d)[i] = reinterpret_cast<const uint4 *>(orow)[i];
+                done = nbytes & ~15;
+            }
+            for (int i = done + lane; i < nbytes; i += 32)
+                d[i] = orow[i];
+            vl = nl_;
+            vc = nc_;
+        }
+        return;
+    }
 
     /* ================= stage V, luma: warp = row, lane = columns lane, lane+32, ... ================= */
     {
