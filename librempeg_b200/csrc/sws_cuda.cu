@@ -185,6 +185,61 @@ sws_rgb_shuffle_kernel(const __grid_constant__ ShuffleArgs A)
     }
 }
 
+/* The same permutation for 16-byte aligned rows: a thread owns 16 pixels (three or four 16-byte
+ * loads and stores).  Per group of four pixels every destination word is gathered from at most three
+ * consecutive source words with two byte permutes; the selectors only depend on the byte map and
+ * are prepared on the host (ShuffleVecArgs). */
+struct ShuffleVecArgs {
+    const uint8_t *src;
+    uint8_t *dst;
+    long long src_fstride, dst_fstride;
+    int src_stride, dst_stride;
+    int w, y0, rows;
+    int chunks;            /* 16-pixel chunks per row, the last one may be partial */
+    uint32_t sel1[4], sel2[4], keep[4], fill[4];   /* per destination word of a four-pixel group */
+    int map[4];
+};
+
+template <int SBPP, int DBPP>
+__global__ void __launch_bounds__(256)
+sws_rgb_shuffle_vec_kernel(const __grid_constant__ ShuffleVecArgs A)
+{
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int row = (int)(idx / A.chunks), c = (int)(idx - (long long)row * A.chunks);
+    if (row >= A.rows)
+        return;
+    const uint8_t *s = A.src + blockIdx.z * A.src_fstride + (size_t)(A.y0 + row) * A.src_stride + (size_t)c * 16 * SBPP;
+    uint8_t *d = A.dst + blockIdx.z * A.dst_fstride + (size_t)(A.y0 + row) * A.dst_stride + (size_t)c * 16 * DBPP;
+    const int n = min(16, A.w - 16 * c);
+    if (n < 16) {                       /* partial last chunk of a row: byte by byte */
+        for (int px = 0; px < n; px++)
+#pragma unroll
+            for (int k = 0; k < DBPP; k++) {
+                const int m = A.map[k];
+                d[px * DBPP + k] = m == 4 ? 255 : s[px * SBPP + m];
+            }
+        return;
+    }
+    uint32_t w[4 * SBPP + 2], o[4 * DBPP];
+#pragma unroll
+    for (int i = 0; i < SBPP; i++) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(s) + i);
+        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+    }
+    w[4 * SBPP] = w[4 * SBPP + 1] = 0;
+#pragma unroll
+    for (int g = 0; g < 4; g++)
+#pragma unroll
+        for (int j = 0; j < DBPP; j++) {
+            const int lo = g * SBPP + ((4 * j) / DBPP * SBPP) / 4;
+            const uint32_t t = prmt(w[lo], w[lo + 1], A.sel1[j]);
+            o[g * DBPP + j] = (prmt(t, w[lo + 2], A.sel2[j]) & A.keep[j]) | A.fill[j];
+        }
+#pragma unroll
+    for (int i = 0; i < DBPP; i++)
+        __stcs(reinterpret_cast<uint4 *>(d) + i, make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+}
+
 struct Bgr24Yv12Args {
     const uint8_t *src;
     uint8_t *dst[3];
@@ -227,6 +282,57 @@ sws_bgr24_to_yv12_kernel(const __grid_constant__ Bgr24Yv12Args A)
         (uint8_t)(((A.ru * rx + A.gu * gx + A.bu * bx) >> 15) + 128);
     (A.dst[2] + blockIdx.z * A.dst_fstride[2])[crow * A.dst_stride[2] + i] =
         (uint8_t)(((A.rv * rx + A.gv * gx + A.bv * bx) >> 15) + 128);
+}
+
+/* The same converter for 16-byte aligned rows: a thread owns 16 pixels of a row pair (three 16-byte
+ * loads per row, one 16-byte luma store per row, 8 bytes of U and of V). */
+__global__ void __launch_bounds__(256)
+sws_bgr24_to_yv12_vec_kernel(const __grid_constant__ Bgr24Yv12Args A, int chunks, int pairs)
+{
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int pr = (int)(idx / chunks), c = (int)(idx - (long long)pr * chunks);
+    if (pr >= pairs)
+        return;
+    const int ya = 2 * pr, yb = min(2 * pr + 1, A.h - 1);
+    const uint8_t *s = A.src + blockIdx.z * A.src_fstride + (size_t)c * 48;
+    uint32_t w[2][12];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(s + (size_t)(A.y0 + (r ? yb : ya)) * A.src_stride);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const uint4 v = __ldcs(q + i);
+            w[r][4 * i] = v.x; w[r][4 * i + 1] = v.y; w[r][4 * i + 2] = v.z; w[r][4 * i + 3] = v.w;
+        }
+    }
+    auto byte_at = [&](int r, int k) -> int { return (int)((w[r][k >> 2] >> (8 * (k & 3))) & 0xFFu); };
+    uint32_t yw[2][4] = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 } }, uw[2] = { 0, 0 }, vw[2] = { 0, 0 };
+#pragma unroll
+    for (int p2 = 0; p2 < 8; p2++) {                 /* pixel pairs = chroma samples */
+        int bs = 0, gs = 0, rs = 0;
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int px = 2 * p2 + q;
+                const int b = byte_at(r, 3 * px), g = byte_at(r, 3 * px + 1), rr = byte_at(r, 3 * px + 2);
+                bs += b; gs += g; rs += rr;
+                const uint32_t yv = (uint32_t)(((A.ry * rr + A.gy * g + A.by * b) >> 15) + 16) & 0xFFu;
+                yw[r][px >> 2] |= yv << (8 * (px & 3));
+            }
+        bs >>= 2; gs >>= 2; rs >>= 2;
+        const uint32_t u = (uint32_t)(((A.ru * rs + A.gu * gs + A.bu * bs) >> 15) + 128) & 0xFFu;
+        const uint32_t v = (uint32_t)(((A.rv * rs + A.gv * gs + A.bv * bs) >> 15) + 128) & 0xFFu;
+        uw[p2 >> 2] |= u << (8 * (p2 & 3));
+        vw[p2 >> 2] |= v << (8 * (p2 & 3));
+    }
+    uint8_t *d0 = A.dst[0] + blockIdx.z * A.dst_fstride[0] + (size_t)c * 16;
+    __stcs(reinterpret_cast<uint4 *>(d0 + (size_t)(A.y0 + ya) * A.dst_stride[0]), make_uint4(yw[0][0], yw[0][1], yw[0][2], yw[0][3]));
+    if (yb != ya)                                    /* an odd last row is its own partner */
+        __stcs(reinterpret_cast<uint4 *>(d0 + (size_t)(A.y0 + yb) * A.dst_stride[0]), make_uint4(yw[1][0], yw[1][1], yw[1][2], yw[1][3]));
+    const size_t crow = (size_t)((A.y0 >> 1) + pr);
+    __stcs(reinterpret_cast<uint2 *>(A.dst[1] + blockIdx.z * A.dst_fstride[1] + crow * A.dst_stride[1] + (size_t)c * 8), make_uint2(uw[0], uw[1]));
+    __stcs(reinterpret_cast<uint2 *>(A.dst[2] + blockIdx.z * A.dst_fstride[2] + crow * A.dst_stride[2] + (size_t)c * 8), make_uint2(vw[0], vw[1]));
 }
 
 /* ------------------------------------------------------------------------
@@ -1658,6 +1764,52 @@ static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const i
         a.w = p->src_w; a.y0 = y0;
         for (int k = 0; k < 4; k++)
             a.map[k] = p->shuf_map[k];
+        const bool vec = aligned16(src[0]) && aligned16(dst[0]) && !(src_stride[0] & 15) && !(dst_stride[0] & 15) &&
+                         src_stride[0] > 0 && dst_stride[0] > 0 && !(a.src_fstride & 15) && !(a.dst_fstride & 15);
+        if (vec) {
+            ShuffleVecArgs v;
+            memset(&v, 0, sizeof(v));
+            v.src = a.src; v.dst = a.dst; v.src_fstride = a.src_fstride; v.dst_fstride = a.dst_fstride;
+            v.src_stride = a.src_stride; v.dst_stride = a.dst_stride;
+            v.w = a.w; v.y0 = y0; v.rows = y1 - y0; v.chunks = (a.w + 15) / 16;
+            const int sb = p->src_bpp, db = p->dst_bpp;
+            for (int j = 0; j < db; j++) {
+                const int lo = ((4 * j) / db * sb) / 4;
+                uint32_t s1 = 0, s2 = 0, keep = 0, fill = 0;
+                for (int b = 0; b < 4; b++) {
+                    const int ob = 4 * j + b, px = ob / db, m = p->shuf_map[ob % db];
+                    v.map[ob % db] = m;
+                    if (m == 4) {
+                        fill |= 0xFFu << (8 * b);
+                        s2 |= (uint32_t)b << (4 * b);
+                        continue;
+                    }
+                    const int ib = px * sb + m, wi = ib / 4 - lo, bi = ib % 4;
+                    keep |= 0xFFu << (8 * b);
+                    if (wi <= 1) {
+                        s1 |= (uint32_t)(wi * 4 + bi) << (4 * b);
+                        s2 |= (uint32_t)b << (4 * b);
+                    } else {
+                        s2 |= (uint32_t)(4 + bi) << (4 * b);
+                    }
+                }
+                v.sel1[j] = s1; v.sel2[j] = s2; v.keep[j] = keep; v.fill[j] = fill;
+            }
+            const long long work = (long long)v.chunks * v.rows;
+            dim3 vgrid((unsigned)((work + 255) / 256), 1, nb_frames);
+            if (sb == 3 && db == 3)
+                sws_rgb_shuffle_vec_kernel<3, 3><<<vgrid, 256, 0, stream>>>(v);
+            else if (sb == 3)
+                sws_rgb_shuffle_vec_kernel<3, 4><<<vgrid, 256, 0, stream>>>(v);
+            else if (db == 3)
+                sws_rgb_shuffle_vec_kernel<4, 3><<<vgrid, 256, 0, stream>>>(v);
+            else
+                sws_rgb_shuffle_vec_kernel<4, 4><<<vgrid, 256, 0, stream>>>(v);
+            st->kernel_name = "rgb_shuffle";
+            CUDA_OK(cudaGetLastError());
+            st->launches++;
+            return 1;
+        }
         dim3 grid((p->src_w + SHUF_PX - 1) / SHUF_PX, y1 - y0, nb_frames);
         if (p->src_bpp == 3 && p->dst_bpp == 3)
             sws_rgb_shuffle_kernel<3, 3><<<grid, 256, 0, stream>>>(a);
@@ -1684,8 +1836,19 @@ static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const i
         a.ry = p->rgb2yuv[0]; a.gy = p->rgb2yuv[1]; a.by = p->rgb2yuv[2];
         a.ru = p->rgb2yuv[3]; a.gu = p->rgb2yuv[4]; a.bu = p->rgb2yuv[5];
         a.rv = p->rgb2yuv[6]; a.gv = p->rgb2yuv[7]; a.bv = p->rgb2yuv[8];
-        dim3 grid((a.cw + 255) / 256, (a.h + 1) / 2, nb_frames);
-        sws_bgr24_to_yv12_kernel<<<grid, 256, 0, stream>>>(a);
+        bool vec = !(p->src_w & 15) && aligned16(src[0]) && !(src_stride[0] & 15) && !(a.src_fstride & 15) &&
+                   aligned16(dst[0]) && !(dst_stride[0] & 15) && !(a.dst_fstride[0] & 15);
+        for (int i = 1; i < 3; i++)
+            vec = vec && !((uintptr_t)dst[i] & 7) && !(dst_stride[i] & 7) && !(a.dst_fstride[i] & 7);
+        if (vec) {
+            const int chunks = p->src_w / 16, pairs = (a.h + 1) / 2;
+            const long long work = (long long)chunks * pairs;
+            dim3 vgrid((unsigned)((work + 255) / 256), 1, nb_frames);
+            sws_bgr24_to_yv12_vec_kernel<<<vgrid, 256, 0, stream>>>(a, chunks, pairs);
+        } else {
+            dim3 grid((a.cw + 255) / 256, (a.h + 1) / 2, nb_frames);
+            sws_bgr24_to_yv12_kernel<<<grid, 256, 0, stream>>>(a);
+        }
         st->kernel_name = "bgr24_to_yv12";
     } else {
         return 0;

@@ -3,7 +3,11 @@
 bench.py reports the metric configuration).  For each config: frames resident in HBM, one batched
 launch per step through sws_cuda_scale_batch(), CUDA events on the library stream.
 
-    python tools/bench_configs.py [--frames 16] [--steps 10]
+    python tools/bench_configs.py [--frames 0] [--steps 20]
+
+--frames 0 (default) sizes every batch to about --gbytes of algorithmic traffic (at least 16 frames,
+at most 1024), so that every configuration is measured in steady state on a working set far larger
+than the 126 MB L2; --frames N forces N frames per launch.
 """
 import argparse
 import json
@@ -38,8 +42,9 @@ CONFIGS = [
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=16)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--frames", type=int, default=0)
+    ap.add_argument("--gbytes", type=float, default=1.5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--only", default="")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -54,6 +59,9 @@ def main():
         ctx = S.SwsContext(sw, sh, sf, dw, dh, df, flags)
         sl, dl = T.plane_layout(sf, sw, sh), T.plane_layout(df, dw, dh)
         F = args.frames
+        if F <= 0:
+            per_frame = sum(rows * rb for rows, rb in sl) + sum(rows * rb for rows, rb in dl)
+            F = max(16, min(1024, int(args.gbytes * 1e9 / per_frame)))
         src = [torch.randint(0, 256, (F, rows * rb), dtype=torch.uint8, device=dev) for rows, rb in sl]
         if "10le" in sf:   # keep 10-bit samples in range
             for t in src:

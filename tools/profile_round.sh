@@ -5,7 +5,8 @@ set -u
 TAG=${1:-r01}
 OUT=gpurun_out
 mkdir -p $OUT
-python tools/bench_configs.py --frames 16 --steps 10 > $OUT/configs_$TAG.txt 2>&1
+python tools/bench_configs.py > $OUT/configs_$TAG.txt 2>&1
+python tools/bench_configs.py --frames 16 > $OUT/configs_16frames_$TAG.txt 2>&1
 python bench.py --steps 20 --warmup 3 > $OUT/bench_${TAG}_n1.json 2> $OUT/bench_${TAG}_n1.err
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_${TAG}_reference_arm.json 2>> $OUT/bench_${TAG}_n1.err
 # launch list of the bench command (per-launch durations are cold/serialised: only the SHARE matters)
