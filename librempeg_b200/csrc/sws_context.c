@@ -555,6 +555,7 @@ static int init_single(SwsContext *sws, int with_device)
     }
     p->lum_identity = is_identity_bank(&c->h_lum, 1 << 14) && is_identity_bank(&c->v_lum, 1 << 12);
     p->chr_h_identity = is_identity_bank(&c->h_chr, 1 << 14);
+    p->chr_v_identity = is_identity_bank(&c->v_chr, 1 << 12);
 
     if (!with_device) {
         c->planned = 1;

@@ -335,6 +335,82 @@ sws_bgr24_to_yv12_vec_kernel(const __grid_constant__ Bgr24Yv12Args A, int chunks
     __stcs(reinterpret_cast<uint2 *>(A.dst[2] + blockIdx.z * A.dst_fstride[2] + crow * A.dst_stride[2] + (size_t)c * 8), make_uint2(vw[0], vw[1]));
 }
 
+/* 8-bit YUV -> 8-bit YUV of the same geometry with identity filters (planarToNv12Wrapper,
+ * nv12ToPlanarWrapper, planar copies: swscale_unscaled.c:147-215): the scaler arithmetic collapses to
+ * ((x << 7) * 4096 + (64 << 12)) >> 19 == x, so the conversion is a copy with chroma (de)interleaving.
+ * 16-byte aligned planes; blockIdx.y selects the luma or the chroma half of the work. */
+struct Copy8Args {
+    const uint8_t *src[3];
+    uint8_t *dst[3];
+    long long src_fstride[3], dst_fstride[3];
+    int src_stride[3], dst_stride[3];
+    int w, cw, y0, rows, cy0, crows;
+    int lchunks, cchunks;          /* 16-byte luma chunks / 16-sample chroma chunks per row */
+    int src_layout, dst_kind;
+};
+
+__global__ void __launch_bounds__(256)
+sws_copy8_kernel(const __grid_constant__ Copy8Args A)
+{
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int f = blockIdx.z;
+    if (blockIdx.y == 0) {
+        const int row = (int)(idx / A.lchunks), c = (int)(idx - (long long)row * A.lchunks);
+        if (row >= A.rows)
+            return;
+        const uint8_t *s = A.src[0] + f * A.src_fstride[0] + (size_t)(A.y0 + row) * A.src_stride[0] + 16 * (size_t)c;
+        uint8_t *d = A.dst[0] + f * A.dst_fstride[0] + (size_t)(A.y0 + row) * A.dst_stride[0] + 16 * (size_t)c;
+        const int n = min(16, A.w - 16 * c);
+        if (n == 16)
+            __stcs(reinterpret_cast<uint4 *>(d), __ldcs(reinterpret_cast<const uint4 *>(s)));
+        else
+            for (int i = 0; i < n; i++)
+                d[i] = s[i];
+        return;
+    }
+    const int row = (int)(idx / A.cchunks), c = (int)(idx - (long long)row * A.cchunks);
+    if (row >= A.crows)
+        return;
+    const int y = A.cy0 + row, n = min(16, A.cw - 16 * c);
+    const bool splanar = A.src_layout == SWSC_SRC_PLANAR, dplanar = A.dst_kind == SWSC_DST_PLANAR8;
+    const int sswap = A.src_layout == SWSC_SRC_NV21, dswap = A.dst_kind == SWSC_DST_NV21;
+    const uint8_t *s1 = A.src[1] + f * A.src_fstride[1] + (size_t)y * A.src_stride[1];
+    const uint8_t *s2 = splanar ? A.src[2] + f * A.src_fstride[2] + (size_t)y * A.src_stride[2] : nullptr;
+    uint8_t *d1 = A.dst[1] + f * A.dst_fstride[1] + (size_t)y * A.dst_stride[1];
+    uint8_t *d2 = dplanar ? A.dst[2] + f * A.dst_fstride[2] + (size_t)y * A.dst_stride[2] : nullptr;
+    if (n < 16) {                       /* partial last chunk of a chroma row */
+        for (int i = 0; i < n; i++) {
+            const int x = 16 * c + i;
+            const uint8_t u = splanar ? s1[x] : s1[2 * x + sswap], v = splanar ? s2[x] : s1[2 * x + 1 - sswap];
+            if (dplanar) {
+                d1[x] = u; d2[x] = v;
+            } else {
+                d1[2 * x + dswap] = u; d1[2 * x + 1 - dswap] = v;
+            }
+        }
+        return;
+    }
+    uint4 u, v;
+    if (splanar) {
+        u = __ldcs(reinterpret_cast<const uint4 *>(s1) + c);
+        v = __ldcs(reinterpret_cast<const uint4 *>(s2) + c);
+    } else {
+        const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(s1) + 2 * c), b = __ldcs(reinterpret_cast<const uint4 *>(s1) + 2 * c + 1);
+        const uint4 e = make_uint4(prmt(a.x, a.y, 0x6420), prmt(a.z, a.w, 0x6420), prmt(b.x, b.y, 0x6420), prmt(b.z, b.w, 0x6420));
+        const uint4 o = make_uint4(prmt(a.x, a.y, 0x7531), prmt(a.z, a.w, 0x7531), prmt(b.x, b.y, 0x7531), prmt(b.z, b.w, 0x7531));
+        u = sswap ? o : e;
+        v = sswap ? e : o;
+    }
+    if (dplanar) {
+        __stcs(reinterpret_cast<uint4 *>(d1) + c, u);
+        __stcs(reinterpret_cast<uint4 *>(d2) + c, v);
+    } else {
+        const uint4 e = dswap ? v : u, o = dswap ? u : v;
+        __stcs(reinterpret_cast<uint4 *>(d1) + 2 * c, make_uint4(prmt(e.x, o.x, 0x5140), prmt(e.x, o.x, 0x7362), prmt(e.y, o.y, 0x5140), prmt(e.y, o.y, 0x7362)));
+        __stcs(reinterpret_cast<uint4 *>(d1) + 2 * c + 1, make_uint4(prmt(e.z, o.z, 0x5140), prmt(e.z, o.z, 0x7362), prmt(e.w, o.w, 0x5140), prmt(e.w, o.w, 0x7362)));
+    }
+}
+
 /* ------------------------------------------------------------------------
  * Generic fused tile kernel: table-driven H FIR -> (range) -> V FIR -> pack.
  *   SRC16   : source samples are 16-bit containers (9..16 bit depths)
@@ -1557,6 +1633,7 @@ extern "C" int ff_b200_cuda_create(SwsCudaState **out, SwsCudaPlan *plan,
             if (strstr(d, "fast420")) st->disabled |= 1;
             if (strstr(d, "fast16"))  st->disabled |= 2;
             if (strstr(d, "scale8"))  st->disabled |= 4;
+            if (strstr(d, "copy8"))   st->disabled |= 32;
             if (strstr(d, "tile15"))  st->disabled |= 16;
         }
     }
@@ -1755,6 +1832,43 @@ static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const i
                           const int64_t dst_fstride[4], int nb_frames, int y0, int y1, cudaStream_t stream)
 {
     const SwsCudaPlan *p = &st->plan;
+    if (!p->special && p->src_bits == 8 && p->src_layout <= SWSC_SRC_NV21 && p->has_chroma && !p->range_mode &&
+        !p->dither_bayer && p->lum_identity && p->chr_h_identity && p->chr_v_identity &&
+        (p->dst_kind == SWSC_DST_PLANAR8 || p->dst_kind == SWSC_DST_NV12 || p->dst_kind == SWSC_DST_NV21) &&
+        p->src_w == p->dst_w && p->src_h == p->dst_h && p->chr_src_w == p->chr_dst_w && p->chr_src_h == p->chr_dst_h &&
+        !(st->disabled & 32)) {
+        const int nsrc = p->src_layout == SWSC_SRC_PLANAR ? 3 : 2, ndst = p->dst_kind == SWSC_DST_PLANAR8 ? 3 : 2;
+        bool ok = true;
+        for (int i = 0; i < nsrc; i++)
+            ok = ok && src[i] && aligned16(src[i]) && !(src_stride[i] & 15) && src_stride[i] > 0 &&
+                 !(nb_frames > 1 && (src_fstride[i] & 15));
+        for (int i = 0; i < ndst; i++)
+            ok = ok && dst[i] && aligned16(dst[i]) && !(dst_stride[i] & 15) && dst_stride[i] > 0 &&
+                 !(nb_frames > 1 && (dst_fstride[i] & 15));
+        if (ok) {
+            Copy8Args a;
+            memset(&a, 0, sizeof(a));
+            for (int i = 0; i < 3; i++) {
+                a.src[i] = src[i]; a.dst[i] = dst[i];
+                a.src_stride[i] = src_stride[i]; a.dst_stride[i] = dst_stride[i];
+                a.src_fstride[i] = src_fstride ? src_fstride[i] : 0;
+                a.dst_fstride[i] = dst_fstride ? dst_fstride[i] : 0;
+            }
+            a.w = p->dst_w; a.cw = p->chr_dst_w; a.y0 = y0; a.rows = y1 - y0;
+            a.cy0 = y0 >> p->chr_dst_vsub;
+            a.crows = (y1 == p->dst_h ? p->chr_dst_h : y1 >> p->chr_dst_vsub) - a.cy0;
+            a.lchunks = (a.w + 15) / 16; a.cchunks = (a.cw + 15) / 16;
+            a.src_layout = p->src_layout; a.dst_kind = p->dst_kind;
+            const long long lw = (long long)a.lchunks * a.rows, cwk = (long long)a.cchunks * a.crows;
+            const long long mx = lw > cwk ? lw : cwk;
+            dim3 grid((unsigned)((mx + 255) / 256), 2, nb_frames);
+            sws_copy8_kernel<<<grid, 256, 0, stream>>>(a);
+            st->kernel_name = "copy8";
+            CUDA_OK(cudaGetLastError());
+            st->launches++;
+            return 1;
+        }
+    }
     if (p->special == SWSC_SPECIAL_SHUFFLE) {
         ShuffleArgs a;
         a.src = src[0]; a.dst = dst[0];

@@ -142,6 +142,7 @@ typedef struct SwsCudaPlan {
     /* fast-path eligibility, decided on the host at init */
     int lum_identity;            /* h and v luma FIRs are the identity        */
     int chr_h_identity;          /* horizontal chroma FIR is the identity     */
+    int chr_v_identity;          /* vertical chroma FIR is the identity       */
 } SwsCudaPlan;
 
 typedef struct SwsCudaState SwsCudaState;

@@ -35,6 +35,8 @@ CONFIGS = [
     ("E2 4K bgra->1080p nv12 bicubic", 3840, 2160, "bgra", 1920, 1080, "nv12", S.SWS_BICUBIC | S.BX),
     ("E3 4K bgr24->yuv420p default flags (box converter)", 3840, 2160, "bgr24", 3840, 2160, "yuv420p", S.SWS_BICUBIC),
     ("E4 4K rgba->bgra shuffle", 3840, 2160, "rgba", 3840, 2160, "bgra", S.SWS_BICUBIC | S.BX),
+    ("U1 4K nv12->yuv420p (de-interleave copy)", 3840, 2160, "nv12", 3840, 2160, "yuv420p", S.SWS_BICUBIC | S.BX),
+    ("U2 4K yuv420p->nv12 (interleave copy)", 3840, 2160, "yuv420p", 3840, 2160, "nv12", S.SWS_BICUBIC | S.BX),
     ("X1 1080p->4K yuv420p->rgb24 bicubic", 1920, 1080, "yuv420p", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
     ("X2 4K->1080p yuv420p->yuv420p bicubic", 3840, 2160, "yuv420p", 1920, 1080, "yuv420p", S.SWS_BICUBIC | S.BX),
 ]
