@@ -260,3 +260,32 @@ def test_kernel_fallback_chain_is_bit_identical(case, monkeypatch):
         seen.append(_check(seed=111, **case))
     assert seen[-1] == "generic_tile", seen
     assert first != "generic_tile", seen
+
+
+# ---- identity 8-bit yuv -> yuv conversions: the copy / (de)interleave kernel (swscale_unscaled.c:147-215) ----
+@pytest.mark.parametrize("sf,df", [("nv12", "yuv420p"), ("yuv420p", "nv12"), ("nv21", "nv12"), ("yuv420p", "nv21"),
+                                   ("nv21", "yuv420p"), ("yuv420p", "yuv420p"), ("yuv422p", "yuv422p")])
+@pytest.mark.parametrize("geom", [(644, 366), (34, 18), (1920, 1080), (322, 243)])
+def test_copy8_kernel(sf, df, geom):
+    w, h = geom
+    for mode in ("noise", "extreme"):
+        name = _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=S.SWS_BICUBIC | BX, seed=91, mode=mode)
+        assert name == "copy8", name
+    slices = [(y, min(32, h - y)) for y in range(0, h, 32)]
+    _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=S.SWS_BILINEAR, seed=92, slices=slices)
+
+
+# ---- the dot-product scaling kernel with packed RGB output (yuv2rgb_X/_1/_2 rounding, output.c:1662-1939) ----
+@pytest.mark.parametrize("sf", ["yuv420p", "nv12", "nv21", "yuv422p", "yuv444p"])
+@pytest.mark.parametrize("df", ["rgb24", "bgr24", "rgba", "bgra", "argb", "abgr"])
+@pytest.mark.parametrize("geom,flags", [((320, 180, 640, 360), S.SWS_BICUBIC | BX),
+                                        ((640, 360, 320, 180), S.SWS_BILINEAR | BX),      # 2-tap rows: yuv2packed2
+                                        ((322, 242, 400, 300), S.SWS_BILINEAR | BX),
+                                        ((1280, 720, 642, 362), S.SWS_LANCZOS | BX),       # 13 taps
+                                        ((322, 242, 644, 242), S.SWS_POINT | BX)])
+def test_scale8_rgb_output(sf, df, geom, flags):
+    sw, sh, dw, dh = geom
+    for mode in ("noise", "extreme"):
+        name = _check(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags, seed=93, mode=mode)
+        if sf != "yuv444p":           # 4:4:4 sources force full-chroma RGB: another kernel
+            assert name.startswith("scale8"), name
