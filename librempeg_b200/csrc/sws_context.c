@@ -433,6 +433,17 @@ static int init_single(SwsContext *sws, int with_device)
         if (sws->src_format == AV_PIX_FMT_BGR24 && sws->dst_format == AV_PIX_FMT_YUV420P &&
             !(flags & SWS_ACCURATE_RND) && !(dstW & 1))
             c->special = SWSC_SPECIAL_BGR24_YV12;     /* swscale_unscaled.c:2062-2077,2453-2457 */
+        if (planar_yuv_pair && sd->depth == 8 && dd->depth == 8) {
+            /* planarToNv12Wrapper, nv12ToPlanarWrapper and the plain plane copy (swscale_unscaled.c:147-215,
+             * 2405-2420,2675-2700): chosen at init and, like every convert_unscaled hook, kept even if
+             * sws_setColorspaceDetails() later makes the ranges differ (utils.c:849-905) */
+            const int ssemi = !!(sd->flags & SWSPF_SEMI), dsemi = !!(dd->flags & SWSPF_SEMI);
+            const int s420 = sd->log2_cw == 1 && sd->log2_ch == 1, d420 = dd->log2_cw == 1 && dd->log2_ch == 1;
+            if ((s420 && d420 && ssemi != dsemi) ||
+                (sd->log2_cw == dd->log2_cw && sd->log2_ch == dd->log2_ch && ssemi == dsemi &&
+                 sd->swap_uv == dd->swap_uv))
+                c->special = SWSC_SPECIAL_COPY8;
+        }
         if ((sws->src_format == AV_PIX_FMT_YUV420P || sws->src_format == AV_PIX_FMT_YUV422P) &&
             is_rgb(sws->dst_format) && !(flags & SWS_ACCURATE_RND) &&
             (sws->dither == SWS_DITHER_BAYER || sws->dither == SWS_DITHER_AUTO) && !(dstH & 1)) {

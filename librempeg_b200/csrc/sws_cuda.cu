@@ -40,7 +40,7 @@
 
 /* ordered-dither rows for 8-bit planar output of >8-bit sources; same matrix as
  * ff_dither_8x8_128 (reference swscale.c:42-52) */
-__constant__ uint8_t c_dither_8x8_128[8][8] = {
+__constant__ __align__(8) uint8_t c_dither_8x8_128[8][8] = {
     {  36, 68,  60, 92,  34, 66,  58, 90 },
     { 100,  4, 124, 28,  98,  2, 122, 26 },
     {  52, 84,  44, 76,  50, 82,  42, 74 },
@@ -121,6 +121,7 @@ __device__ __forceinline__ void rgb_chroma14(const SwsCudaPlan &P, const uint8_t
 
 #include "sws_scale8.cuh"
 #include "sws_tile15.cuh"
+#include "sws_rgb420.cuh"
 
 
 /* ------------------------------------------------------------------------
@@ -347,6 +348,7 @@ struct Copy8Args {
     int w, cw, y0, rows, cy0, crows;
     int lchunks, cchunks;          /* 16-byte luma chunks / 16-sample chroma chunks per row */
     int src_layout, dst_kind;
+    int vec;                       /* every plane and stride is 16-byte aligned */
 };
 
 __global__ void __launch_bounds__(256)
@@ -361,7 +363,7 @@ sws_copy8_kernel(const __grid_constant__ Copy8Args A)
         const uint8_t *s = A.src[0] + f * A.src_fstride[0] + (size_t)(A.y0 + row) * A.src_stride[0] + 16 * (size_t)c;
         uint8_t *d = A.dst[0] + f * A.dst_fstride[0] + (size_t)(A.y0 + row) * A.dst_stride[0] + 16 * (size_t)c;
         const int n = min(16, A.w - 16 * c);
-        if (n == 16)
+        if (n == 16 && A.vec)
             __stcs(reinterpret_cast<uint4 *>(d), __ldcs(reinterpret_cast<const uint4 *>(s)));
         else
             for (int i = 0; i < n; i++)
@@ -378,7 +380,7 @@ sws_copy8_kernel(const __grid_constant__ Copy8Args A)
     const uint8_t *s2 = splanar ? A.src[2] + f * A.src_fstride[2] + (size_t)y * A.src_stride[2] : nullptr;
     uint8_t *d1 = A.dst[1] + f * A.dst_fstride[1] + (size_t)y * A.dst_stride[1];
     uint8_t *d2 = dplanar ? A.dst[2] + f * A.dst_fstride[2] + (size_t)y * A.dst_stride[2] : nullptr;
-    if (n < 16) {                       /* partial last chunk of a chroma row */
+    if (n < 16 || !A.vec) {             /* partial last chunk of a chroma row, or unaligned planes */
         for (int i = 0; i < n; i++) {
             const int x = 16 * c + i;
             const uint8_t u = splanar ? s1[x] : s1[2 * x + sswap], v = splanar ? s2[x] : s1[2 * x + 1 - sswap];
@@ -847,6 +849,7 @@ struct SwsCudaState {
     const char *kernel_name;
     /* fast420 path */
     int fast_ok;
+    int r420_ok, r420_cr;
     int s8_ok, s8_fs4, s8_tile_h, s8_nl_cap, s8_nc_cap, s8_seg_l, s8_seg_c, s8_slot, s8_vl_n4, s8_vc_n4;
     size_t s8_smem;
     void *s8_tables;
@@ -951,6 +954,7 @@ static int plan_tiles(SwsCudaState *st)
 
 static int tile15_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank *hc,
                         const SwsFirBank *vl, const SwsFirBank *vc);
+static int rgb420_setup(SwsCudaState *st, const SwsFirBank *vc);
 
 /* ---------------------------------------------------------------- fast420 host side */
 
@@ -1492,7 +1496,7 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
                          const int64_t dst_fstride[4], int nb_frames, int y0, int y1, cudaStream_t stream)
 {
     const SwsCudaPlan *p = &st->plan;
-    if (!st->s8_ok || (st->disabled & 4))
+    if (!st->s8_ok || (st->disabled & 4) || p->range_mode)
         return 0;
     const int nsrc = p->src_layout == SWSC_SRC_PLANAR ? 3 : 2;
     for (int i = 0; i < nsrc; i++)
@@ -1622,6 +1626,9 @@ extern "C" int ff_b200_cuda_create(SwsCudaState **out, SwsCudaPlan *plan,
     ret = scale8_setup(st, hl, hc, vl, vc);
     if (ret < 0)
         return ret;
+    ret = rgb420_setup(st, vc);
+    if (ret < 0)
+        return ret;
     ret = tile15_setup(st, hl, hc, vl, vc);
     if (ret < 0)
         return ret;
@@ -1634,6 +1641,7 @@ extern "C" int ff_b200_cuda_create(SwsCudaState **out, SwsCudaPlan *plan,
             if (strstr(d, "fast16"))  st->disabled |= 2;
             if (strstr(d, "scale8"))  st->disabled |= 4;
             if (strstr(d, "copy8"))   st->disabled |= 32;
+            if (strstr(d, "rgb420"))  st->disabled |= 64;
             if (strstr(d, "tile15"))  st->disabled |= 16;
         }
     }
@@ -1826,26 +1834,123 @@ static int tile15_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     return 1;
 }
 
+/* ---------------------------------------------------------------- rgb420 host side */
+
+static int rgb420_setup(SwsCudaState *st, const SwsFirBank *vc)
+{
+    const SwsCudaPlan *p = &st->plan;
+    st->r420_ok = 0;
+    if (p->src_layout != SWSC_SRC_RGB || !p->src_rgb_half || p->special || p->range_mode || p->dither_bayer ||
+        p->inter_bits != 15 || !p->lum_identity || !p->chr_h_identity || !p->has_chroma)
+        return 0;
+    if (p->dst_kind != SWSC_DST_PLANAR8 && p->dst_kind != SWSC_DST_NV12 && p->dst_kind != SWSC_DST_NV21)
+        return 0;
+    if (p->chr_dst_hsub != 1 || p->chr_dst_vsub != 1 || p->src_w != p->dst_w || p->src_h != p->dst_h ||
+        (p->src_w & 15) || p->chr_src_w != p->chr_dst_w || p->chr_src_h != p->src_h || p->h_shift != 13)
+        return 0;
+    if (vc->size > 16 || !bank_regular(vc, p->chr_src_h))
+        return 0;
+    for (int i = 0; i < 9; i++)
+        if (p->rgb2yuv[i] < -32768 || p->rgb2yuv[i] > 32767)
+            return 0;
+    /* chroma rows per tile: as many as keep the source-row window (and the luma rows) inside the line buffer */
+    int cr;
+    for (cr = 32; cr >= 1; cr--) {
+        int worst = 0;
+        for (int c0 = 0; c0 < vc->len; c0 += cr) {
+            const int c1 = c0 + cr < vc->len ? c0 + cr : vc->len;
+            const int n = vc->pos[c1 - 1] + vc->size - vc->pos[c0];
+            if (n > worst) worst = n;
+        }
+        if (worst <= R420_MAXROWS)
+            break;
+    }
+    if (cr < 4)
+        return 0;
+    st->r420_cr = cr;
+    st->r420_ok = 1;
+    return 0;
+}
+
+static int rgb420_launch(SwsCudaState *st, const uint8_t *const src[4], const int src_stride[4],
+                         const int64_t src_fstride[4], uint8_t *const dst[4], const int dst_stride[4],
+                         const int64_t dst_fstride[4], int nb_frames, int y0, int y1, cudaStream_t stream)
+{
+    const SwsCudaPlan *p = &st->plan;
+    /* range conversion can be switched on after init by sws_setColorspaceDetails(): another kernel's job */
+    if (!st->r420_ok || (st->disabled & 64) || p->range_mode || (y0 & 1) || (y1 != p->dst_h && (y1 & 1)))
+        return 0;
+    const int ndst = p->dst_kind == SWSC_DST_PLANAR8 ? 3 : 2;
+    if (!src[0] || !aligned16(src[0]) || (src_stride[0] & 15) || src_stride[0] <= 0 ||
+        (nb_frames > 1 && (src_fstride[0] & 15)))
+        return 0;
+    for (int i = 0; i < ndst; i++)
+        if (!dst[i] || !aligned16(dst[i]) || (dst_stride[i] & 15) || dst_stride[i] <= 0 ||
+            (nb_frames > 1 && (dst_fstride[i] & 15)))
+            return 0;
+    Rgb420Args a;
+    memset(&a, 0, sizeof(a));
+    a.src = src[0]; a.src_stride = src_stride[0]; a.src_fstride = src_fstride ? src_fstride[0] : 0;
+    for (int i = 0; i < 3; i++) {
+        a.dst[i] = dst[i]; a.dst_stride[i] = dst_stride[i];
+        a.dst_fstride[i] = dst_fstride ? dst_fstride[i] : 0;
+    }
+    a.w = p->dst_w;
+    a.cy_begin = y0 >> 1;
+    a.cy_end = y1 == p->dst_h ? p->chr_dst_h : y1 >> 1;
+    a.y_end = y1;
+    a.cr = st->r420_cr;
+    a.vc_size = p->vc_size; a.vc_coef = p->vc_coef; a.vc_pos = p->vc_pos;
+    a.dst_kind = p->dst_kind;
+    /* matrix rows as 16-bit pairs in the byte order of a pixel word (unused bytes get a zero coefficient) */
+    int ky[4] = { 0, 0, 0, 0 }, ku[4] = { 0, 0, 0, 0 }, kv[4] = { 0, 0, 0, 0 };
+    ky[p->src_ro] = p->rgb2yuv[0]; ky[p->src_go] = p->rgb2yuv[1]; ky[p->src_bo] = p->rgb2yuv[2];
+    ku[p->src_ro] = p->rgb2yuv[3]; ku[p->src_go] = p->rgb2yuv[4]; ku[p->src_bo] = p->rgb2yuv[5];
+    kv[p->src_ro] = p->rgb2yuv[6]; kv[p->src_go] = p->rgb2yuv[7]; kv[p->src_bo] = p->rgb2yuv[8];
+    auto pair = [](int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); };
+    a.ylo = pair(ky[0], ky[1]); a.yhi = pair(ky[2], ky[3]);
+    a.ulo = pair(ku[0], ku[1]); a.uhi = pair(ku[2], ku[3]);
+    a.vlo = pair(kv[0], kv[1]); a.vhi = pair(kv[2], kv[3]);
+    if (a.cy_end <= a.cy_begin)
+        return 0;
+    dim3 grid((p->dst_w + R420_TW - 1) / R420_TW, (a.cy_end - a.cy_begin + a.cr - 1) / a.cr, nb_frames);
+    if (p->src_bpp == 3)
+        sws_rgb420_kernel<3><<<grid, 256, 0, stream>>>(a);
+    else
+        sws_rgb420_kernel<4><<<grid, 256, 0, stream>>>(a);
+    st->kernel_name = "rgb420";
+    CUDA_OK(cudaGetLastError());
+    st->launches++;
+    return 1;
+}
+
 /* whole-frame special converters; returns 1 if launched */
 static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const int src_stride[4],
                           const int64_t src_fstride[4], uint8_t *const dst[4], const int dst_stride[4],
                           const int64_t dst_fstride[4], int nb_frames, int y0, int y1, cudaStream_t stream)
 {
     const SwsCudaPlan *p = &st->plan;
-    if (!p->special && p->src_bits == 8 && p->src_layout <= SWSC_SRC_NV21 && p->has_chroma && !p->range_mode &&
-        !p->dither_bayer && p->lum_identity && p->chr_h_identity && p->chr_v_identity &&
-        (p->dst_kind == SWSC_DST_PLANAR8 || p->dst_kind == SWSC_DST_NV12 || p->dst_kind == SWSC_DST_NV21) &&
-        p->src_w == p->dst_w && p->src_h == p->dst_h && p->chr_src_w == p->chr_dst_w && p->chr_src_h == p->chr_dst_h &&
-        !(st->disabled & 32)) {
+    /* identity 8-bit yuv -> yuv: the reference's copy wrappers (chosen at init, range changes after init
+     * do not unseat them) and every conversion whose four filters are the identity without range conversion */
+    if (p->special == SWSC_SPECIAL_COPY8 ||
+        (!p->special && p->src_bits == 8 && p->src_layout <= SWSC_SRC_NV21 && p->has_chroma && !p->range_mode &&
+         !p->dither_bayer && p->lum_identity && p->chr_h_identity && p->chr_v_identity &&
+         (p->dst_kind == SWSC_DST_PLANAR8 || p->dst_kind == SWSC_DST_NV12 || p->dst_kind == SWSC_DST_NV21) &&
+         p->src_w == p->dst_w && p->src_h == p->dst_h && p->chr_src_w == p->chr_dst_w && p->chr_src_h == p->chr_dst_h &&
+         !(st->disabled & 32))) {
         const int nsrc = p->src_layout == SWSC_SRC_PLANAR ? 3 : 2, ndst = p->dst_kind == SWSC_DST_PLANAR8 ? 3 : 2;
-        bool ok = true;
-        for (int i = 0; i < nsrc; i++)
-            ok = ok && src[i] && aligned16(src[i]) && !(src_stride[i] & 15) && src_stride[i] > 0 &&
-                 !(nb_frames > 1 && (src_fstride[i] & 15));
-        for (int i = 0; i < ndst; i++)
-            ok = ok && dst[i] && aligned16(dst[i]) && !(dst_stride[i] & 15) && dst_stride[i] > 0 &&
-                 !(nb_frames > 1 && (dst_fstride[i] & 15));
-        if (ok) {
+        bool vec = true, ok = true;
+        for (int i = 0; i < nsrc; i++) {
+            ok = ok && src[i];
+            vec = vec && aligned16(src[i]) && !(src_stride[i] & 15) && !(nb_frames > 1 && (src_fstride[i] & 15));
+        }
+        for (int i = 0; i < ndst; i++) {
+            ok = ok && dst[i];
+            vec = vec && aligned16(dst[i]) && !(dst_stride[i] & 15) && !(nb_frames > 1 && (dst_fstride[i] & 15));
+        }
+        if (!ok)
+            return AVERROR(EINVAL);
+        {
             Copy8Args a;
             memset(&a, 0, sizeof(a));
             for (int i = 0; i < 3; i++) {
@@ -1859,6 +1964,7 @@ static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const i
             a.crows = (y1 == p->dst_h ? p->chr_dst_h : y1 >> p->chr_dst_vsub) - a.cy0;
             a.lchunks = (a.w + 15) / 16; a.cchunks = (a.cw + 15) / 16;
             a.src_layout = p->src_layout; a.dst_kind = p->dst_kind;
+            a.vec = vec;
             const long long lw = (long long)a.lchunks * a.rows, cwk = (long long)a.cchunks * a.crows;
             const long long mx = lw > cwk ? lw : cwk;
             dim3 grid((unsigned)((mx + 255) / 256), 2, nb_frames);
@@ -1990,6 +2096,9 @@ extern "C" int ff_b200_cuda_launch(SwsCudaState *st,
         if (r != 0)
             return r < 0 ? r : 0;
         r = fast16_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);
+        if (r != 0)
+            return r < 0 ? r : 0;
+        r = rgb420_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);
         if (r != 0)
             return r < 0 ? r : 0;
         r = scale8_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);

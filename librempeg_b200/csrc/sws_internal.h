@@ -108,6 +108,7 @@ enum {
     SWSC_SPECIAL_NONE = 0,
     SWSC_SPECIAL_SHUFFLE,        /* rgbToRgbWrapper / packedCopyWrapper between 8-bit packed RGB layouts */
     SWSC_SPECIAL_BGR24_YV12,     /* bgr24ToYv12Wrapper: 2x2 box chroma, truncating 15-bit matrix */
+    SWSC_SPECIAL_COPY8,          /* planarCopyWrapper / planarToNv12Wrapper / nv12ToPlanarWrapper, 8-bit */
 };
 
 /* POD description of one conversion; passed by value to the kernels. */

@@ -289,3 +289,42 @@ def test_scale8_rgb_output(sf, df, geom, flags):
         name = _check(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags, seed=93, mode=mode)
         if sf != "yuv444p":           # 4:4:4 sources force full-chroma RGB: another kernel
             assert name.startswith("scale8"), name
+
+
+# ---- packed RGB -> 4:2:0 of the same size: the fused reader + vertical-chroma kernel ----
+@pytest.mark.parametrize("sf", RGB_SRC)
+@pytest.mark.parametrize("df", ["yuv420p", "nv12", "nv21"])
+@pytest.mark.parametrize("geom,flags", [((640, 360), S.SWS_BICUBIC | BX), ((1920, 1080), S.SWS_BILINEAR | BX),
+                                        ((144, 37), S.SWS_LANCZOS | BX), ((320, 182), S.SWS_BICUBIC),
+                                        ((656, 366), S.SWS_AREA | BX), ((48, 10), S.SWS_POINT | BX)])
+def test_rgb420_kernel(sf, df, geom, flags):
+    w, h = geom
+    if sf == "bgr24" and df == "yuv420p" and not (flags & S.SWS_ACCURATE_RND):
+        pytest.skip("bgr24ToYv12Wrapper special converter, covered elsewhere")
+    for mode in ("noise", "extreme"):
+        name = _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=flags, seed=95, mode=mode)
+        assert name == "rgb420", name
+    slices = [(y, min(34, h - y)) for y in range(0, h, 34)]
+    _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=flags, seed=96, slices=slices)
+
+
+def test_rgb420_colorspace():
+    """BT.709 limited-range destination matrix through the fused RGB reader (a full-range destination
+    adds range conversion: test_range_switched_on_after_init)."""
+    colorspace = (1, 0, 1, 0, 0, 1 << 16, 1 << 16)
+    for sf in ("rgb24", "bgra"):
+        name = _check(sw=640, sh=360, sf=sf, dw=640, dh=360, df="yuv420p", flags=S.SWS_BICUBIC | BX, seed=97,
+                      colorspace=colorspace)
+        assert name == "rgb420", name
+
+
+@pytest.mark.parametrize("ranges", [(0, 1), (1, 0)])
+@pytest.mark.parametrize("case", [dict(sw=640, sh=360, sf="yuv420p", dw=320, dh=180, df="yuv420p"),
+                                  dict(sw=640, sh=360, sf="nv12", dw=640, dh=360, df="yuv420p"),
+                                  dict(sw=640, sh=360, sf="rgb24", dw=640, dh=360, df="yuv420p"),
+                                  dict(sw=640, sh=360, sf="bgra", dw=640, dh=360, df="nv12")])
+def test_range_switched_on_after_init(case, ranges):
+    """sws_setColorspaceDetails() after init turns range conversion on: the kernels chosen at init that
+    do not implement it must step aside (reference swscale.c:626-660, utils.c:849-1005)."""
+    colorspace = (5, ranges[0], 5, ranges[1], 0, 1 << 16, 1 << 16)
+    _check(flags=S.SWS_BICUBIC | BX, seed=98, colorspace=colorspace, **case)
