@@ -1836,6 +1836,29 @@ static int tile15_launch(SwsCudaState *st, const uint8_t *const src[4], const in
 
 /* ---------------------------------------------------------------- rgb420 host side */
 
+/* the rgb420 kernel keeps 16-bit matrix coefficients and drops the readers' uint16 wrap and the 15-bit clip:
+ * admit only matrices whose 14-bit samples stay in [0, 16384) for every input (luma: one pixel, bias
+ * (32 << 14) + (1 << 8), >> 9; chroma: a pixel pair, bias (256 << 15) + (1 << 9), >> 10).  Checked at init and
+ * at every launch (sws_setColorspaceDetails() may replace the matrix). */
+static bool rgb420_matrix_ok(const SwsCudaPlan *p)
+{
+    for (int i = 0; i < 9; i++)
+        if (p->rgb2yuv[i] < -32768 || p->rgb2yuv[i] > 32767)
+            return false;
+    for (int r = 0; r < 3; r++) {
+        long long lo = 0, hi = 0;
+        for (int k = 0; k < 3; k++) {
+            const long long c = p->rgb2yuv[3 * r + k];
+            (c < 0 ? lo : hi) += c * (r ? 510 : 255);
+        }
+        const long long bias = r ? (256LL << 15) + (1 << 9) : (32LL << 14) + (1 << 8);
+        const int sh = r ? 10 : 9;
+        if (bias + lo < 0 || ((bias + hi) >> sh) >= 16384)
+            return false;
+    }
+    return true;
+}
+
 static int rgb420_setup(SwsCudaState *st, const SwsFirBank *vc)
 {
     const SwsCudaPlan *p = &st->plan;
@@ -1850,9 +1873,8 @@ static int rgb420_setup(SwsCudaState *st, const SwsFirBank *vc)
         return 0;
     if (vc->size > 16 || !bank_regular(vc, p->chr_src_h))
         return 0;
-    for (int i = 0; i < 9; i++)
-        if (p->rgb2yuv[i] < -32768 || p->rgb2yuv[i] > 32767)
-            return 0;
+    if (!rgb420_matrix_ok(p))
+        return 0;
     /* chroma rows per tile: as many as keep the source-row window (and the luma rows) inside the line buffer */
     int cr;
     for (cr = 32; cr >= 1; cr--) {
@@ -1878,7 +1900,8 @@ static int rgb420_launch(SwsCudaState *st, const uint8_t *const src[4], const in
 {
     const SwsCudaPlan *p = &st->plan;
     /* range conversion can be switched on after init by sws_setColorspaceDetails(): another kernel's job */
-    if (!st->r420_ok || (st->disabled & 64) || p->range_mode || (y0 & 1) || (y1 != p->dst_h && (y1 & 1)))
+    if (!st->r420_ok || (st->disabled & 64) || p->range_mode || (y0 & 1) || (y1 != p->dst_h && (y1 & 1)) ||
+        !rgb420_matrix_ok(p))
         return 0;
     const int ndst = p->dst_kind == SWSC_DST_PLANAR8 ? 3 : 2;
     if (!src[0] || !aligned16(src[0]) || (src_stride[0] & 15) || src_stride[0] <= 0 ||

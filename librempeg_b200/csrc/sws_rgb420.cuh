@@ -12,6 +12,10 @@
  *   Y14 = (ry r + gy g + by b + (32 << 14) + (1 << 8)) >> 9               (the 32-bit readers' unsigned
  *   U14 = (ru (r0+r1) + gu (g0+g1) + bu (b0+b1) + (256 << 15) + (1 << 9)) >> 10   form is the same number)
  *   line15 = min(2 * x14, 32767);  Y = clip_u8((line15 + 64) >> 7);  U = clip_u8((sum_j c_j line15_j + (64 << 12)) >> 19)
+ * The host admits only matrices for which 0 <= x14 < 16384 for every input (true for every colourspace
+ * libswscale can produce; checked, not assumed), so the uint16 wrap and the clip at 32767 cannot trigger and
+ *   Y = min(255, (sY + 16384) >> 15)          with sY the biased luma dot product (floor of floor = floor),
+ *   U = clip_u8((sum_j c_j U14_j + (64 << 11)) >> 18)     with the 14-bit samples kept in shared memory.
  * A pixel is one 32-bit word (3-byte pixels are cut out of the row with funnel shifts), so the matrix
  * row is two IDP.2A with the 16-bit coefficients arranged per byte order on the host.
  *
@@ -60,70 +64,78 @@ sws_rgb420_kernel(const __grid_constant__ Rgb420Args A)
     const uint8_t *src = A.src + f * A.src_fstride + (size_t)x0 * BPP;
     uint8_t *dy = A.dst[0] + f * A.dst_fstride[0] + x0;
 
-    /* ---------------- phase 1: item = (source row, 16-pixel chunk) ---------------- */
+    /* ---------------- phase 1: item = (source row, 16-pixel chunk) ----------------
+     * the loads of both rounds of a full tile are issued before anything is computed */
     const int items = (r1 - r0) * 8;
-    for (int it = tid; it < items; it += 256) {
-        const int row = r0 + (it >> 3), k = it & 7;
-        if (k >= nchunk)
-            continue;
-        const uint4 *q = reinterpret_cast<const uint4 *>(src + (size_t)row * A.src_stride + (size_t)k * 16 * BPP);
-        uint32_t px[16];
-        if (BPP == 4) {
+    constexpr int NW = BPP == 4 ? 16 : 12;
+    uint32_t w[2][NW];
+    for (int base = 0; base < items; base += 512) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint4 v = __ldg(q + i);
-                px[4 * i] = v.x; px[4 * i + 1] = v.y; px[4 * i + 2] = v.z; px[4 * i + 3] = v.w;
-            }
-        } else {
-            uint32_t w[12];
+        for (int rd = 0; rd < 2; rd++) {
+            const int it = base + rd * 256 + tid;
+            const int row = r0 + (it >> 3), k = it & 7;
+            if (it < items && k < nchunk) {
+                const uint4 *q = reinterpret_cast<const uint4 *>(src + (size_t)row * A.src_stride + (size_t)k * 16 * BPP);
 #pragma unroll
-            for (int i = 0; i < 3; i++) {
-                const uint4 v = __ldg(q + i);
-                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-            }
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-                px[4 * g] = w[3 * g];
-                px[4 * g + 1] = __funnelshift_r(w[3 * g], w[3 * g + 1], 24);
-                px[4 * g + 2] = __funnelshift_r(w[3 * g + 1], w[3 * g + 2], 16);
-                px[4 * g + 3] = w[3 * g + 2] >> 8;
-            }
-        }
-        if (row >= ly0 && row < ly1) {
-            uint32_t yo[4];
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int s = dp2a_hi_su(A.yhi, px[i], dp2a_lo_su(A.ylo, px[i], (32 << 14) + (1 << 8)));
-                const int l15 = min((int)((uint32_t)(s >> 9) & 0xFFFFu) * 2, 32767);
-                const uint32_t yv = (uint32_t)clip_u8((l15 + 64) >> 7);
-                if ((i & 3) == 0)
-                    yo[i >> 2] = yv;
-                else
-                    yo[i >> 2] |= yv << (8 * (i & 3));
-            }
-            __stcs(reinterpret_cast<uint4 *>(dy + (size_t)row * A.dst_stride[0] + 16 * k), make_uint4(yo[0], yo[1], yo[2], yo[3]));
-        }
-        if (row >= lo_c && row < hi_c) {
-            uint32_t uo[4], vo[4];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const uint32_t a = px[2 * i], b = px[2 * i + 1];
-                int su = dp2a_hi_su(A.uhi, a, dp2a_lo_su(A.ulo, a, (256 << 15) + (1 << 9)));
-                su = dp2a_hi_su(A.uhi, b, dp2a_lo_su(A.ulo, b, su));
-                int sv = dp2a_hi_su(A.vhi, a, dp2a_lo_su(A.vlo, a, (256 << 15) + (1 << 9)));
-                sv = dp2a_hi_su(A.vhi, b, dp2a_lo_su(A.vlo, b, sv));
-                const uint32_t u15 = (uint32_t)min((int)((uint32_t)(su >> 10) & 0xFFFFu) * 2, 32767);
-                const uint32_t v15 = (uint32_t)min((int)((uint32_t)(sv >> 10) & 0xFFFFu) * 2, 32767);
-                if (i & 1) {
-                    uo[i >> 1] |= u15 << 16;
-                    vo[i >> 1] |= v15 << 16;
-                } else {
-                    uo[i >> 1] = u15;
-                    vo[i >> 1] = v15;
+                for (int i = 0; i < NW / 4; i++) {
+                    const uint4 v = __ldg(q + i);
+                    w[rd][4 * i] = v.x; w[rd][4 * i + 1] = v.y; w[rd][4 * i + 2] = v.z; w[rd][4 * i + 3] = v.w;
                 }
             }
-            *reinterpret_cast<uint4 *>(&s_u[row - lo_c][8 * k]) = make_uint4(uo[0], uo[1], uo[2], uo[3]);
-            *reinterpret_cast<uint4 *>(&s_v[row - lo_c][8 * k]) = make_uint4(vo[0], vo[1], vo[2], vo[3]);
+        }
+#pragma unroll
+        for (int rd = 0; rd < 2; rd++) {
+            const int it = base + rd * 256 + tid;
+            const int row = r0 + (it >> 3), k = it & 7;
+            if (it >= items || k >= nchunk)
+                continue;
+            uint32_t px[16];
+            if (BPP == 4) {
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    px[i] = w[rd][i];
+            } else {
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    px[4 * g] = w[rd][3 * g];
+                    px[4 * g + 1] = __funnelshift_r(w[rd][3 * g], w[rd][3 * g + 1], 24);
+                    px[4 * g + 2] = __funnelshift_r(w[rd][3 * g + 1], w[rd][3 * g + 2], 16);
+                    px[4 * g + 3] = w[rd][3 * g + 2] >> 8;
+                }
+            }
+            if (row >= ly0 && row < ly1) {
+                uint32_t yo[4];
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    uint32_t y4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int sy = dp2a_hi_su(A.yhi, px[i + j], dp2a_lo_su(A.ylo, px[i + j], (32 << 14) + (1 << 8) + 16384));
+                        y4[j] = (uint32_t)min(sy >> 15, 255);
+                    }
+                    yo[i >> 2] = prmt(prmt(y4[0], y4[1], 0x0040), prmt(y4[2], y4[3], 0x0040), 0x5410);
+                }
+                __stcs(reinterpret_cast<uint4 *>(dy + (size_t)row * A.dst_stride[0] + 16 * k), make_uint4(yo[0], yo[1], yo[2], yo[3]));
+            }
+            if (row >= lo_c && row < hi_c) {
+                uint32_t uo[4], vo[4];
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                    int su[2], sv[2];
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const uint32_t a = px[2 * (i + j)], b = px[2 * (i + j) + 1];
+                        su[j] = dp2a_hi_su(A.uhi, a, dp2a_lo_su(A.ulo, a, (256 << 15) + (1 << 9)));
+                        su[j] = dp2a_hi_su(A.uhi, b, dp2a_lo_su(A.ulo, b, su[j]));
+                        sv[j] = dp2a_hi_su(A.vhi, a, dp2a_lo_su(A.vlo, a, (256 << 15) + (1 << 9)));
+                        sv[j] = dp2a_hi_su(A.vhi, b, dp2a_lo_su(A.vlo, b, sv[j]));
+                    }
+                    uo[i >> 1] = prmt((uint32_t)(su[0] >> 10), (uint32_t)(su[1] >> 10), 0x5410);
+                    vo[i >> 1] = prmt((uint32_t)(sv[0] >> 10), (uint32_t)(sv[1] >> 10), 0x5410);
+                }
+                *reinterpret_cast<uint4 *>(&s_u[row - lo_c][8 * k]) = make_uint4(uo[0], uo[1], uo[2], uo[3]);
+                *reinterpret_cast<uint4 *>(&s_v[row - lo_c][8 * k]) = make_uint4(vo[0], vo[1], vo[2], vo[3]);
+            }
         }
     }
     __syncthreads();
@@ -140,7 +152,7 @@ sws_rgb420_kernel(const __grid_constant__ Rgb420Args A)
         unsigned au[8], av[8];
 #pragma unroll
         for (int i = 0; i < 8; i++)
-            au[i] = av[i] = 64u << 12;
+            au[i] = av[i] = 64u << 11;
         for (int j = 0; j < fs; j++) {
             const unsigned c = (unsigned)(int)__ldg(cf + j);
             const uint4 u = *reinterpret_cast<const uint4 *>(&s_u[pos + j][8 * g]);
@@ -153,8 +165,8 @@ sws_rgb420_kernel(const __grid_constant__ Rgb420Args A)
         uint32_t ub[8], vb[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            ub[i] = (uint32_t)clip_u8((int)au[i] >> 19);
-            vb[i] = (uint32_t)clip_u8((int)av[i] >> 19);
+            ub[i] = (uint32_t)clip_u8((int)au[i] >> 18);
+            vb[i] = (uint32_t)clip_u8((int)av[i] >> 18);
         }
         const int cx = (x0 >> 1) + 8 * g;
         if (A.dst_kind == SWSC_DST_PLANAR8) {

@@ -13,13 +13,18 @@ python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_${TAG}_refere
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
 # full captures of the dominant kernel of every BASELINE configuration
-cap() {  # name, kernel regex, config filter, frames
+cap() {  # name, kernel regex, config filter, frames, pixels per launch (thread-instructions per pixel in the summary)
     ncu --set full --clock-control none --import-source on -k regex:$2 -s 3 -c 1 -f -o $OUT/$1_$TAG \
         python tools/bench_configs.py --only "$3" --frames $4 --steps 1 > $OUT/$1_$TAG.log 2>&1
+    # the reports are 10+ MB each and gpurun brings back at most 64 MiB: summarise here, keep the text
+    python profiles/ncu_summarize.py $OUT/$1_$TAG.ncu-rep $5 > $OUT/$1_${TAG}_ncu_summary.txt 2>&1
+    rm -f $OUT/$1_$TAG.ncu-rep
 }
-cap fast420 sws_fast420_rgb8 "C5 4K" 64
-cap fast16  sws_fast420_rgb16 "C3 4K" 16
-cap scale8  sws_scale8 "C4 8K" 16
-cap generic_rgbsrc sws_generic_tile "E1 4K" 4
-cap generic_upscale sws_generic_tile "X1 1080p" 4
+cap fast420 sws_fast420_rgb8 "C5 4K" 64 $((3840*2160*64))
+cap fast16  sws_fast420_rgb16 "C3 4K" 16 $((3840*2160*16))
+cap scale8  sws_scale8 "C4 8K" 16 $((7680*4320*16))
+cap scale8_rgb sws_scale8 "X1 1080p" 16 $((3840*2160*16))
+cap rgb420 sws_rgb420 "E1 4K" 16 $((3840*2160*16))
+cap tile15_rgbsrc sws_tile15 "E2 4K" 4 $((3840*2160*4))
+cap copy8 sws_copy8 "U1 4K" 16 $((3840*2160*16))
 ls -la $OUT
