@@ -302,6 +302,43 @@ static int is_identity_bank(const SwsFirBank *b, int one)
     return 1;
 }
 
+/* ff_hyscale_fast_c / ff_hcscale_fast_c (hscale_fast_bilinear.c:23-55) as a 2-tap bank for the 8 -> 15 bit
+ * horizontal stage, which computes min((sum src * coef) >> 7, 32767):
+ *   luma    dst = (src[xx] << 7) + (src[xx+1] - src[xx]) * xalpha = src[xx] * (128 - xalpha) + src[xx+1] * xalpha
+ *   chroma  dst = src[xx] * (xalpha ^ 127) + src[xx+1] * xalpha                       (the taps sum to 127)
+ * with xx = xpos >> 16, xalpha = (xpos & 0xFFFF) >> 9, unsigned xpos += xInc; outputs whose
+ * (i * xInc) >> 16 reaches the last source sample are src[srcW-1] * 128.  Coefficients are the weights
+ * times 128, so the >> 7 is exact and the clip (<= 255 * 128) never triggers. */
+static int fast_bilinear_bank(SwsFirBank *b, int dst_len, int src_len, unsigned x_inc, int chroma)
+{
+    if (src_len < 2)
+        return AVERROR(EINVAL);
+    ff_b200_free_fir(b);
+    b->coef = malloc(sizeof(*b->coef) * (size_t)dst_len * 2);
+    b->pos  = malloc(sizeof(*b->pos) * (size_t)dst_len);
+    if (!b->coef || !b->pos) {
+        ff_b200_free_fir(b);
+        return AVERROR(ENOMEM);
+    }
+    b->size = 2;
+    b->len  = dst_len;
+    unsigned xpos = 0;
+    for (int i = 0; i < dst_len; i++) {
+        const unsigned xx = xpos >> 16, xalpha = (xpos & 0xFFFF) >> 9;
+        if ((((int64_t)i * x_inc) >> 16) >= src_len - 1) {
+            b->pos[i] = src_len - 2;
+            b->coef[2 * i] = 0;
+            b->coef[2 * i + 1] = 128 * 128;
+        } else {
+            b->pos[i] = (int)xx;
+            b->coef[2 * i] = (int16_t)((chroma ? (xalpha ^ 127) : 128 - xalpha) * 128);
+            b->coef[2 * i + 1] = (int16_t)(xalpha * 128);
+        }
+        xpos += x_inc;
+    }
+    return 0;
+}
+
 /* 1-tap bank: output i reads source sample i >> shift */
 static int nearest_bank(SwsFirBank *b, int len, int one, int shift)
 {
@@ -358,9 +395,10 @@ static int init_single(SwsContext *sws, int with_device)
         set_error(c, "exactly one scaler algorithm must be chosen, got %X", scaler);
         return AVERROR(EINVAL);
     }
-    if (scaler == SWS_FAST_BILINEAR) {
-        set_error(c, "SWS_FAST_BILINEAR is outside the CUDA hot path (SURVEY.md 2.2)");
-        return AVERROR(ENOTSUP);
+    if (scaler == SWS_FAST_BILINEAR && (srcW < 8 || dstW <= 8)) {
+        scaler = SWS_BILINEAR;                         /* utils.c:1224-1230 */
+        flags ^= SWS_FAST_BILINEAR | SWS_BILINEAR;
+        sws->flags = flags;
     }
     lum_scaler = scaler_enum_to_flag(sws->scaler, scaler == SWS_BICUBLIN ? SWS_BICUBIC : scaler);
     chr_scaler = scaler_enum_to_flag(sws->scaler_sub ? sws->scaler_sub : sws->scaler,
@@ -388,7 +426,8 @@ static int init_single(SwsContext *sws, int with_device)
     if (is_rgb(sws->dst_format) && !(flags & SWS_FULL_CHR_H_INT)) {
         if (dstW & 1)
             flags |= SWS_FULL_CHR_H_INT;
-        if (c->chr_src_hsub == 0 && c->chr_src_vsub == 0 && sws->dither != SWS_DITHER_BAYER)
+        if (c->chr_src_hsub == 0 && c->chr_src_vsub == 0 && sws->dither != SWS_DITHER_BAYER &&
+            !(flags & SWS_FAST_BILINEAR))                      /* utils.c:1278-1285 */
             flags |= SWS_FULL_CHR_H_INT;
         sws->flags = flags;
     }
@@ -397,7 +436,7 @@ static int init_single(SwsContext *sws, int with_device)
     /* packed RGB sources: chroma is read from horizontally summed pixel pairs unless the caller
      * asks for full chroma input or the output needs the resolution (utils.c:1367-1390) */
     if (is_rgb(sws->src_format) && !(srcW & 1) && !(flags & SWS_FULL_CHR_H_INP) &&
-        (dstW >> c->chr_dst_hsub) <= (srcW >> 1))
+        ((dstW >> c->chr_dst_hsub) <= (srcW >> 1) || (flags & SWS_FAST_BILINEAR)))
         c->chr_src_hsub = 1;
 
     c->chr_src_w = ceil_rshift(srcW, c->chr_src_hsub);
@@ -489,6 +528,16 @@ static int init_single(SwsContext *sws, int with_device)
     if ((ret = ff_b200_build_fir(&c->v_chr, &spec)) < 0)
         goto fir_fail;
 
+    if ((flags & SWS_FAST_BILINEAR) && c->src_bpc == 8 && c->dst_bpc <= 14) {
+        /* ff_hyscale_fast_c / ff_hcscale_fast_c replace the horizontal FIR (swscale.c:675-681,
+         * hscale_fast_bilinear.c:23-55): the same numbers as a 2-tap bank */
+        /* a luma step of exactly 1.0 makes xalpha 0 everywhere: the identity bank already says that.  Not so
+         * for chroma, whose left weight is xalpha ^ 127 = 127 (the samples come out as 127/128 of the source) */
+        if (lum_xinc != 0x10000 && (ret = fast_bilinear_bank(&c->h_lum, dstW, srcW, (unsigned)lum_xinc, 0)) < 0)
+            goto fir_fail;
+        if ((ret = fast_bilinear_bank(&c->h_chr, c->chr_dst_w, c->chr_src_w, (unsigned)chr_xinc, 1)) < 0)
+            goto fir_fail;
+    }
     if (c->unscaled_lut) {
         /* a13 samples chroma at column x>>1, row y>>vsub with no filtering and ignores
          * chroma siting (yuv2rgb.c:137-236): express that as 1-tap banks so the same kernels

@@ -166,8 +166,9 @@ static int generate(Taps *t, const SwsFirSpec *s, int64_t fone)
             t->w[i]   = fone;
             x += inc;
         }
-    } else if (inc <= (1 << 16) && s->scaler == SWS_AREA) {
-        /* area upscale degenerates to 2-tap linear interpolation */
+    } else if ((inc <= (1 << 16) && s->scaler == SWS_AREA) || s->scaler == SWS_FAST_BILINEAR) {
+        /* area upscale degenerates to 2-tap linear interpolation; SWS_FAST_BILINEAR takes the same
+         * branch for every ratio (utils.c:244-245) */
         int64_t x = ((s->dst_pos * inc) >> 8) - ((s->src_pos * 0x8000LL) >> 7);
         width = 2;
         t->w = malloc(sizeof(*t->w) * (size_t)n * 2);

@@ -390,17 +390,21 @@ class OracleContext:
         if not scaler:                                                # :1209
             scaler = SWS_BICUBIC
             flags |= scaler
-        assert scaler & (scaler - 1) == 0 and scaler != SWS_FAST_BILINEAR
+        assert scaler & (scaler - 1) == 0
+        if scaler == SWS_FAST_BILINEAR and (sw < 8 or dw <= 8):       # :1224-1230
+            scaler = SWS_BILINEAR
+            flags ^= SWS_FAST_BILINEAR | SWS_BILINEAR
         lum_scaler = SWS_BICUBIC if scaler == SWS_BICUBLIN else scaler
         chr_scaler = SWS_BILINEAR if scaler == SWS_BICUBLIN else scaler
         unscaled = sw == dw and sh == dh
         if dst_rgb and not (flags & SWS_FULL_CHR_H_INT):              # :1270-1286
-            if dw & 1 or (shs == 0 and svs == 0 and dither != 2):
+            if dw & 1 or (shs == 0 and svs == 0 and dither != 2 and not flags & SWS_FAST_BILINEAR):
                 flags |= SWS_FULL_CHR_H_INT
         if dst_rgb and not (flags & SWS_FULL_CHR_H_INT):              # :1359
             dhs = 1
         # packed RGB sources: chroma from summed pixel pairs (the *_half readers), utils.c:1367-1390
-        if src_rgb and not (sw & 1) and not (flags & SWS_FULL_CHR_H_INP) and (dw >> dhs) <= (sw >> 1):
+        if src_rgb and not (sw & 1) and not (flags & SWS_FULL_CHR_H_INP) and \
+                ((dw >> dhs) <= (sw >> 1) or flags & SWS_FAST_BILINEAR):
             shs = 1
         self.flags = flags
         self.shs, self.svs, self.dhs, self.dvs = shs, svs, dhs, dvs
@@ -463,6 +467,10 @@ class OracleContext:
                                  lpos(svs, svp), lpos(dvs, dvp))
         if None in (self.h_lum, self.h_chr, self.v_lum, self.v_chr):
             raise NotImplementedError("cascaded contexts are not restated")
+        # SWS_FAST_BILINEAR on 8-bit sources with <= 14-bit destinations: hyscale_fast / hcscale_fast
+        # replace the horizontal FIR (swscale.c:675-681, hscale.c:54,188)
+        self.fast_h = bool(flags & SWS_FAST_BILINEAR) and self.src_bpc == 8 and self.dst_bpc <= 14
+        self.lum_xinc, self.chr_xinc = lum_xinc, chr_xinc
 
     # ---- stage 0: planes as integer sample arrays (input.c:926-941 for nv12/nv21)
     def _unpack(self, planes):
@@ -527,6 +535,24 @@ class OracleContext:
         acc = _wrap32(acc) >> sh
         out = np.minimum(acc, (1 << 19) - 1 if inter19 else (1 << 15) - 1)
         return out if inter19 else out.astype(np.int16).astype(np.int64)
+
+    # ---- ff_hyscale_fast_c / ff_hcscale_fast_c (hscale_fast_bilinear.c:23-55): 16.16 stepping, 7-bit
+    # blend factor; the chroma variant weighs the left sample with (xalpha ^ 127), i.e. the taps sum to 127
+    @staticmethod
+    def _hscale_fast(src, dst_w, x_inc, chroma):
+        src_w = src.shape[1]
+        i = np.arange(dst_w, dtype=np.int64)
+        xpos = (i * x_inc) & 0xFFFFFFFF                                # unsigned int xpos
+        xx = xpos >> 16
+        xa = (xpos & 0xFFFF) >> 9
+        left, right = src[:, np.minimum(xx, src_w - 1)], src[:, np.minimum(xx + 1, src_w - 1)]
+        if chroma:
+            out = left * (xa ^ 127)[None, :] + right * xa[None, :]
+        else:
+            out = (left << 7) + (right - left) * xa[None, :]
+        tail = ((i * x_inc) >> 16) >= src_w - 1                         # the fix-up loop at the right edge
+        out[:, tail] = src[:, src_w - 1:src_w] * 128
+        return out.astype(np.int16).astype(np.int64)
 
     # ---- range conversion on the h-scaled lines (swscale.c:163-255, constants :577-624)
     def _range(self, lum, u, v):
@@ -616,9 +642,14 @@ class OracleContext:
         lum, u, v = self._unpack(planes)
         if self.unscaled_lut:
             return self._unscaled_lut(lum, u, v)
-        hl = self._hscale(lum, self.h_lum)
-        hu = self._hscale(u, self.h_chr)
-        hv = self._hscale(v, self.h_chr)
+        if self.fast_h:
+            hl = self._hscale_fast(lum, self.dw, self.lum_xinc, False)
+            hu = self._hscale_fast(u, self.cdw, self.chr_xinc, True)
+            hv = self._hscale_fast(v, self.cdw, self.chr_xinc, True)
+        else:
+            hl = self._hscale(lum, self.h_lum)
+            hu = self._hscale(u, self.h_chr)
+            hv = self._hscale(v, self.h_chr)
         hl, hu, hv = self._range(hl, hu, hv)
         if self.dkind in ("planar", "semi"):
             return self._planar_out(hl, hu, hv)

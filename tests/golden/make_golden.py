@@ -88,6 +88,18 @@ def cases():
                         colorspace=[cs, 0, cs, 0, 0, 1 << 16, 1 << 16]))
     out.append(dict(sw=1920, sh=1080, sf="rgb24", dw=1920, dh=1080, df="yuv420p", flags=R.SWS_BICUBIC | BX, large=1))
     out.append(dict(sw=3840, sh=2160, sf="bgra", dw=1920, dh=1080, df="nv12", flags=R.SWS_BICUBIC | BX, large=1))
+    # SWS_FAST_BILINEAR (appended last so that earlier seeds stay put): hyscale_fast / hcscale_fast on 8-bit
+    # sources with <= 14-bit destinations, the 2-tap initFilter banks elsewhere, the srcW < 8 fallback
+    FB = R.SWS_FAST_BILINEAR
+    for sf, df, g in [("yuv420p", "yuv420p", (352, 288, 200, 100)), ("yuv420p", "rgb24", (176, 144, 352, 288)),
+                      ("nv12", "bgra", (162, 122, 200, 150)), ("yuv422p", "nv12", (162, 122, 100, 75)),
+                      ("yuv420p", "yuv420p10le", (162, 122, 200, 150)), ("yuv420p", "yuv420p16le", (162, 122, 200, 150)),
+                      ("yuv420p10le", "yuv420p", (162, 122, 200, 150)), ("yuv420p10le", "rgb48le", (162, 122, 100, 75)),
+                      ("rgb24", "yuv420p", (162, 122, 200, 150)), ("bgra", "nv12", (162, 122, 100, 75)),
+                      ("yuv420p", "rgb24", (6, 16, 40, 30)), ("yuv420p", "yuv420p", (40, 30, 8, 6)),
+                      ("yuv420p", "rgb24", (162, 122, 162, 200)), ("yuv420p", "yuv444p", (162, 122, 323, 122))]:
+        out.append(dict(sw=g[0], sh=g[1], sf=sf, dw=g[2], dh=g[3], df=df, flags=FB | BX))
+        out.append(dict(sw=g[0], sh=g[1], sf=sf, dw=g[2], dh=g[3], df=df, flags=FB))
     for i, c in enumerate(out):
         c.setdefault("seed", 100 + i)
         c.setdefault("mode", "extreme" if i % 7 == 3 else "noise")

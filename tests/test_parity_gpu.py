@@ -153,7 +153,7 @@ def test_tiny_and_ragged_sizes():
 def test_unsupported_fails_loudly():
     """No silent CPU fallback: what the CUDA path does not implement must fail at init."""
     with pytest.raises(RuntimeError):
-        S.SwsContext(320, 240, "yuv420p", 320, 240, "rgb24", S.SWS_FAST_BILINEAR)
+        S.SwsContext(320, 240, "yuv420p", 320, 240, "rgb24", S.SWS_BICUBIC | (1 << 16))          # vertical chroma drop
     with pytest.raises(RuntimeError):
         S.SwsContext(320, 240, "yuv420p10le", 320, 240, "yuv420p", S.SWS_BICUBIC | BX)  # planarCopyWrapper
 
@@ -328,3 +328,17 @@ def test_range_switched_on_after_init(case, ranges):
     do not implement it must step aside (reference swscale.c:626-660, utils.c:849-1005)."""
     colorspace = (5, ranges[0], 5, ranges[1], 0, 1 << 16, 1 << 16)
     _check(flags=S.SWS_BICUBIC | BX, seed=98, colorspace=colorspace, **case)
+
+
+# ---- SWS_FAST_BILINEAR: ff_hyscale_fast_c / ff_hcscale_fast_c as 2-tap banks (hscale_fast_bilinear.c:23-55) ----
+@pytest.mark.parametrize("sf,df", [("yuv420p", "yuv420p"), ("yuv420p", "rgb24"), ("nv12", "bgra"), ("yuv422p", "nv12"),
+                                   ("yuv420p", "yuv420p10le"), ("yuv420p", "yuv420p16le"), ("yuv420p10le", "yuv420p"),
+                                   ("yuv420p10le", "rgb48le"), ("rgb24", "yuv420p"), ("bgra", "nv12"),
+                                   ("yuv444p", "rgb24"), ("nv21", "yuv444p")])
+@pytest.mark.parametrize("geom", [(352, 288, 200, 100), (176, 144, 352, 288), (322, 242, 333, 251), (6, 16, 40, 30),
+                                  (640, 360, 640, 200), (640, 360, 1280, 360), (1920, 1080, 1280, 720)])
+@pytest.mark.parametrize("extra", [0, BX])
+def test_fast_bilinear(sf, df, geom, extra):
+    sw, sh, dw, dh = geom
+    for mode in ("noise", "extreme"):
+        _check(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=S.SWS_FAST_BILINEAR | extra, seed=99, mode=mode)
