@@ -171,6 +171,8 @@ static void plan_range_convert(SwsInternal *c)
 {
     SwsCudaPlan *p = &c->plan;
     p->range_mode = 0;
+    p->src_full_range = c->opts.src_range;
+    p->dither_none = c->opts.dither == SWS_DITHER_NONE;
     if (c->opts.src_range == c->opts.dst_range || is_rgb(c->opts.dst_format) || c->dst_bpc >= 32)
         return;
     {
@@ -490,10 +492,12 @@ static int init_single(SwsContext *sws, int with_device)
             c->dst_slice_align = 2;
         } else if (planar_yuv_pair && c->chr_src_hsub == c->chr_dst_hsub &&
                    c->chr_src_vsub == c->chr_dst_vsub && sd->depth != dd->depth &&
-                   !!(sd->flags & SWSPF_SEMI) == !!(dd->flags & SWSPF_SEMI)) {
-            /* planarCopyWrapper's dithered depth conversion is not restated yet */
-            set_error(c, "unscaled planar bit-depth conversion is not on the CUDA hot path yet");
-            return AVERROR(ENOTSUP);
+                   !(sd->flags & SWSPF_SEMI) && !(dd->flags & SWSPF_SEMI)) {
+            /* planarCopyWrapper between depths (swscale_unscaled.c:2220-2384): ordered dither down,
+             * bit replication (full-range luma) or plain shift up */
+            c->special = SWSC_SPECIAL_DEPTHCOPY;
+            if (sws->dither != SWS_DITHER_NONE)
+                c->dst_slice_align = 8 << c->chr_dst_vsub;      /* :2694-2696: the dither rows count from the slice */
         }
     }
     if (!c->special && is_rgb(sws->src_format) && sd->bpp == 32 && is_rgb(sws->dst_format) && dd->bpp == 32) {

@@ -413,6 +413,133 @@ sws_copy8_kernel(const __grid_constant__ Copy8Args A)
     }
 }
 
+/* planarCopyWrapper between planar YUV depths (swscale_unscaled.c:2160-2218,2249-2346), little-endian:
+ *   down, dither none:        t = (v + (1 << (shift - 1))) >> shift;  out = t - (t >> dst_depth)
+ *   down, chroma / MPEG luma: t = (v + d) >> shift;                   out = t - (t >> dst_depth)
+ *   down, full-range luma:    out = (v - (v >> dst_depth) + d) >> shift
+ *   up,   chroma / MPEG luma: out = v << shift
+ *   up,   full-range luma:    out = (v << shift) | (v >> (2 * src_depth - dst_depth))
+ * d = ordered-dither matrix of level `shift` (1..8), row = plane row & 7, column = x & 7.  The matrices are
+ * periodic tiles (2x2 for levels 1-2, 4x4 for 3-4, 8x8 above; level 7 repeats level 6, level 8 is
+ * ff_dither_8x8_128); the host expands them once into constant memory. */
+__constant__ __align__(8) uint8_t c_depth_dither[8][8][8];
+
+static const uint8_t depth_tile_1[2][2] = { { 0, 1 }, { 1, 0 } };
+static const uint8_t depth_tile_2[2][2] = { { 1, 2 }, { 3, 0 } };
+static const uint8_t depth_tile_3[4][4] = { { 2, 4, 3, 5 }, { 6, 0, 7, 1 }, { 3, 5, 2, 4 }, { 7, 1, 6, 0 } };
+static const uint8_t depth_tile_4[4][4] = { { 4, 8, 7, 11 }, { 12, 0, 15, 3 }, { 6, 10, 5, 9 }, { 14, 2, 13, 1 } };
+static const uint8_t depth_tile_5[8][8] = {
+    { 9, 17, 15, 23, 8, 16, 14, 22 }, { 25, 1, 31, 7, 24, 0, 30, 6 }, { 13, 21, 11, 19, 12, 20, 10, 18 },
+    { 29, 5, 27, 3, 28, 4, 26, 2 },   { 8, 16, 14, 22, 9, 17, 15, 23 }, { 24, 0, 30, 6, 25, 1, 31, 7 },
+    { 12, 20, 10, 18, 13, 21, 11, 19 }, { 28, 4, 26, 2, 29, 5, 27, 3 } };
+static const uint8_t depth_tile_6[8][8] = {
+    { 18, 34, 30, 46, 17, 33, 29, 45 }, { 50, 2, 62, 14, 49, 1, 61, 13 }, { 26, 42, 22, 38, 25, 41, 21, 37 },
+    { 58, 10, 54, 6, 57, 9, 53, 5 },    { 16, 32, 28, 44, 19, 35, 31, 47 }, { 48, 0, 60, 12, 51, 3, 63, 15 },
+    { 24, 40, 20, 36, 27, 43, 23, 39 }, { 56, 8, 52, 4, 59, 11, 55, 7 } };
+static const uint8_t depth_tile_8[8][8] = {            /* == ff_dither_8x8_128 */
+    { 36, 68, 60, 92, 34, 66, 58, 90 },   { 100, 4, 124, 28, 98, 2, 122, 26 }, { 52, 84, 44, 76, 50, 82, 42, 74 },
+    { 116, 20, 108, 12, 114, 18, 106, 10 }, { 32, 64, 56, 88, 38, 70, 62, 94 }, { 96, 0, 120, 24, 102, 6, 126, 30 },
+    { 48, 80, 40, 72, 54, 86, 46, 78 },   { 112, 16, 104, 8, 118, 22, 110, 14 } };
+
+static cudaError_t upload_depth_dither(void)
+{
+    uint8_t t[8][8][8];
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++) {
+            t[0][y][x] = depth_tile_1[y & 1][x & 1];
+            t[1][y][x] = depth_tile_2[y & 1][x & 1];
+            t[2][y][x] = depth_tile_3[y & 3][x & 3];
+            t[3][y][x] = depth_tile_4[y & 3][x & 3];
+            t[4][y][x] = depth_tile_5[y][x];
+            t[5][y][x] = t[6][y][x] = depth_tile_6[y][x];
+            t[7][y][x] = depth_tile_8[y][x];
+        }
+    return cudaMemcpyToSymbol(c_depth_dither, t, sizeof(t));
+}
+
+struct DepthCopyArgs {
+    const uint8_t *src[3];
+    uint8_t *dst[3];
+    long long src_fstride[3], dst_fstride[3];
+    int src_stride[3], dst_stride[3];
+    int w[3], y0[3], rows[3];      /* per plane: width, first row, row count of this launch */
+    int chunks[3];                 /* 8-sample chunks per row */
+    int src_depth, dst_depth;
+    int luma_shiftonly;            /* limited-range source: luma is shifted like chroma */
+    int dither_none;
+    int vec;                       /* planes and strides allow 8/16-byte accesses */
+};
+
+template <typename SrcT, typename DstT>
+__global__ void __launch_bounds__(256)
+sws_depthcopy_kernel(const __grid_constant__ DepthCopyArgs A)
+{
+    const int plane = blockIdx.y;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int row = (int)(idx / A.chunks[plane]), c = (int)(idx - (long long)row * A.chunks[plane]);
+    if (row >= A.rows[plane])
+        return;
+    const int y = A.y0[plane] + row;
+    const SrcT *s = reinterpret_cast<const SrcT *>(A.src[plane] + blockIdx.z * A.src_fstride[plane] + (size_t)y * A.src_stride[plane]) + 8 * c;
+    DstT *d = reinterpret_cast<DstT *>(A.dst[plane] + blockIdx.z * A.dst_fstride[plane] + (size_t)y * A.dst_stride[plane]) + 8 * c;
+    const int n = min(8, A.w[plane] - 8 * c);
+    const bool shiftonly = plane != 0 || A.luma_shiftonly;
+    const int sd = A.src_depth, dd = A.dst_depth;
+    unsigned v[8], o[8];
+    if (n == 8 && A.vec) {
+        if (sizeof(SrcT) == 1) {
+            const uint2 q = __ldcs(reinterpret_cast<const uint2 *>(s));
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                v[i] = ((i < 4 ? q.x : q.y) >> (8 * (i & 3))) & 0xFFu;
+        } else {
+            const uint4 q = __ldcs(reinterpret_cast<const uint4 *>(s));
+            const unsigned w4[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                v[i] = (w4[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            v[i] = i < n ? s[i] : 0;
+    }
+    if (sd > dd) {
+        const int shift = sd - dd;
+        const uint2 dq = *reinterpret_cast<const uint2 *>(c_depth_dither[shift - 1][row & 7]);   /* rows count from the slice */
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const unsigned dz = ((i < 4 ? dq.x : dq.y) >> (8 * (i & 3))) & 0xFFu;
+            if (A.dither_none) {
+                const unsigned t = (v[i] + (1u << (shift - 1))) >> shift;
+                o[i] = t - (t >> dd);
+            } else if (shiftonly) {
+                const unsigned t = (v[i] + dz) >> shift;
+                o[i] = t - (t >> dd);
+            } else {
+                o[i] = (v[i] - (v[i] >> dd) + dz) >> shift;
+            }
+        }
+    } else {
+        const int shift = dd - sd, rep = 2 * sd - dd;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            o[i] = shiftonly ? v[i] << shift : (v[i] << shift) | (v[i] >> rep);
+    }
+    if (n == 8 && A.vec) {
+        if (sizeof(DstT) == 1) {
+            __stcs(reinterpret_cast<uint2 *>(d), make_uint2((o[0] & 0xFF) | (o[1] & 0xFF) << 8 | (o[2] & 0xFF) << 16 | o[3] << 24,
+                                                            (o[4] & 0xFF) | (o[5] & 0xFF) << 8 | (o[6] & 0xFF) << 16 | o[7] << 24));
+        } else {
+            __stcs(reinterpret_cast<uint4 *>(d), make_uint4((o[0] & 0xFFFF) | o[1] << 16, (o[2] & 0xFFFF) | o[3] << 16,
+                                                            (o[4] & 0xFFFF) | o[5] << 16, (o[6] & 0xFFFF) | o[7] << 16));
+        }
+    } else {
+        for (int i = 0; i < n; i++)
+            d[i] = (DstT)o[i];
+    }
+}
+
 /* ------------------------------------------------------------------------
  * Generic fused tile kernel: table-driven H FIR -> (range) -> V FIR -> pack.
  *   SRC16   : source samples are 16-bit containers (9..16 bit depths)
@@ -1575,6 +1702,8 @@ extern "C" int ff_b200_cuda_create(SwsCudaState **out, SwsCudaPlan *plan,
     st->device = dev;
     *out = st;
     CUDA_OK(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
+    if (plan->special == SWSC_SPECIAL_DEPTHCOPY)
+        CUDA_OK(upload_depth_dither());
 
     /* upload the four banks into one allocation: [coef|pos] x4, 16-byte aligned */
     const SwsFirBank *banks[4] = { hl, hc, vl, vc };
@@ -1997,6 +2126,46 @@ static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const i
             st->launches++;
             return 1;
         }
+    }
+    if (p->special == SWSC_SPECIAL_DEPTHCOPY) {
+        DepthCopyArgs a;
+        memset(&a, 0, sizeof(a));
+        const int sb = p->src_bits > 8 ? 2 : 1, db = p->dst_bits > 8 ? 2 : 1;
+        bool vec = true;
+        long long mx = 0;
+        for (int i = 0; i < 3; i++) {
+            if (!src[i] || !dst[i])
+                return AVERROR(EINVAL);
+            a.src[i] = src[i]; a.dst[i] = dst[i];
+            a.src_stride[i] = src_stride[i]; a.dst_stride[i] = dst_stride[i];
+            a.src_fstride[i] = src_fstride ? src_fstride[i] : 0;
+            a.dst_fstride[i] = dst_fstride ? dst_fstride[i] : 0;
+            vec = vec && aligned16(src[i]) && aligned16(dst[i]) && !(src_stride[i] & 15) && !(dst_stride[i] & 15) &&
+                  !(a.src_fstride[i] & 15) && !(a.dst_fstride[i] & 15);
+            a.w[i] = i ? p->chr_dst_w : p->dst_w;
+            a.y0[i] = i ? (y0 + (1 << p->chr_dst_vsub) - 1) >> p->chr_dst_vsub : y0;       /* AV_CEIL_RSHIFT, :2229-2230 */
+            const int yend = i ? (y1 == p->dst_h ? p->chr_dst_h : (y1 + (1 << p->chr_dst_vsub) - 1) >> p->chr_dst_vsub) : y1;
+            a.rows[i] = yend - a.y0[i];
+            a.chunks[i] = (a.w[i] + 7) / 8;
+            const long long work = (long long)a.chunks[i] * a.rows[i];
+            if (work > mx) mx = work;
+        }
+        (void)sb; (void)db;
+        a.src_depth = p->src_bits; a.dst_depth = p->dst_bits;
+        a.luma_shiftonly = !p->src_full_range;
+        a.dither_none = p->dither_none;
+        a.vec = vec;
+        dim3 grid((unsigned)((mx + 255) / 256), 3, nb_frames);
+        if (p->src_bits == 8)
+            sws_depthcopy_kernel<uint8_t, uint16_t><<<grid, 256, 0, stream>>>(a);
+        else if (p->dst_bits == 8)
+            sws_depthcopy_kernel<uint16_t, uint8_t><<<grid, 256, 0, stream>>>(a);
+        else
+            sws_depthcopy_kernel<uint16_t, uint16_t><<<grid, 256, 0, stream>>>(a);
+        st->kernel_name = "depthcopy";
+        CUDA_OK(cudaGetLastError());
+        st->launches++;
+        return 1;
     }
     if (p->special == SWSC_SPECIAL_SHUFFLE) {
         ShuffleArgs a;

@@ -109,6 +109,7 @@ enum {
     SWSC_SPECIAL_SHUFFLE,        /* rgbToRgbWrapper / packedCopyWrapper between 8-bit packed RGB layouts */
     SWSC_SPECIAL_BGR24_YV12,     /* bgr24ToYv12Wrapper: 2x2 box chroma, truncating 15-bit matrix */
     SWSC_SPECIAL_COPY8,          /* planarCopyWrapper / planarToNv12Wrapper / nv12ToPlanarWrapper, 8-bit */
+    SWSC_SPECIAL_DEPTHCOPY,      /* planarCopyWrapper between planar YUV depths (dithered down, replicated up) */
 };
 
 /* POD description of one conversion; passed by value to the kernels. */
@@ -129,6 +130,8 @@ typedef struct SwsCudaPlan {
     int dither_bayer;            /* 1: ff_dither_8x8_128 rows, 0: constant 64 */
     /* range conversion on the h-scaled lines (reference swscale.c:163-255,577-660) */
     int range_mode;              /* 0 none, 1 to-jpeg, 2 from-jpeg            */
+    int src_full_range;          /* sws->src_range, read by the depth-copy converter at call time */
+    int dither_none;             /* sws->dither == SWS_DITHER_NONE            */
     uint32_t lum_rc_coeff, chr_rc_coeff;
     int64_t  lum_rc_offset, chr_rc_offset;
     SwsRgbConsts rgb;

@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(S8_THREADS, 3)
 sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_u,
                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ Scale8Args A)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char s8_smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[S8_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[S8_STAGES];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -280,7 +280,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     const int a0l = __ldg(A.hl_pos + x0) & ~15;
     const int a0c = ch > 0 ? __ldg(A.hc_pos + cx0) & ~15 : 0;
     const bool planar = A.src_layout == SWSC_SRC_PLANAR;
-    const uint32_t ring_a = smem_u32(smem_raw), full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+    const uint32_t ring_a = smem_u32(s8_smem_raw), full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
     __syncthreads();
 
     if (warp == 8) {
@@ -320,8 +320,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     const int tw = min(S8_TW, A.dst_w - x0), th = ry1 - ry0;
     const int cw = min(CW, A.chr_dst_w - cx0);
     const int lstride_w = A.nl_cap >> 1, cstride_w = A.nc_cap >> 1;   /* odd by construction */
-    const unsigned char *ring = smem_raw;
-    uint32_t *hb_l = reinterpret_cast<uint32_t *>(smem_raw + S8_STAGES * slot);
+    const unsigned char *ring = s8_smem_raw;
+    uint32_t *hb_l = reinterpret_cast<uint32_t *>(s8_smem_raw + S8_STAGES * slot);
     uint32_t *hb_u = hb_l + S8_TW * lstride_w;
     uint32_t *hb_v = hb_u + CW * cstride_w;
 
@@ -432,7 +432,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
          * the byte LUTs in closed form as in the other RGB kernels) ============ */
         const int kind = A.dst_kind;
         const int bpp = kind >= SWSC_DST_RGBA ? 4 : 3;
-        unsigned char *orow = smem_raw + warp * 512;          /* the ring is idle now: 512 B of row staging per warp */
+        unsigned char *orow = s8_smem_raw + warp * 512;          /* the ring is idle now: 512 B of row staging per warp */
         const int cy = A.cy, yb = A.yb;
         S8VRow vl, vc;
         if (warp < th) {

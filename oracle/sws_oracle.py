@@ -287,6 +287,32 @@ def init_filter(x_inc, src_w, dst_w, one, scaler, flags, param, src_pos, dst_pos
 
 
 # --------------------------------------------------------------------------- yuv2rgb tables
+def _tile(t):
+    t = np.array(t, np.int64)
+    return np.tile(t, (8 // t.shape[0], 8 // t.shape[1]))
+
+
+# the ordered-dither matrices of planarCopyWrapper (`dithers[shift - 1]`, swscale_unscaled.c:39-112) as their
+# periodic tiles: 2x2 (1 and 2 bits), 4x4 (3, 4), 8x8 (5, 6 = 7, and 8 = ff_dither_8x8_128)
+_D6 = [[18, 34, 30, 46, 17, 33, 29, 45], [50, 2, 62, 14, 49, 1, 61, 13], [26, 42, 22, 38, 25, 41, 21, 37],
+       [58, 10, 54, 6, 57, 9, 53, 5], [16, 32, 28, 44, 19, 35, 31, 47], [48, 0, 60, 12, 51, 3, 63, 15],
+       [24, 40, 20, 36, 27, 43, 23, 39], [56, 8, 52, 4, 59, 11, 55, 7]]
+DEPTH_DITHER = [
+    _tile([[0, 1], [1, 0]]),
+    _tile([[1, 2], [3, 0]]),
+    _tile([[2, 4, 3, 5], [6, 0, 7, 1], [3, 5, 2, 4], [7, 1, 6, 0]]),
+    _tile([[4, 8, 7, 11], [12, 0, 15, 3], [6, 10, 5, 9], [14, 2, 13, 1]]),
+    _tile([[9, 17, 15, 23, 8, 16, 14, 22], [25, 1, 31, 7, 24, 0, 30, 6], [13, 21, 11, 19, 12, 20, 10, 18],
+           [29, 5, 27, 3, 28, 4, 26, 2], [8, 16, 14, 22, 9, 17, 15, 23], [24, 0, 30, 6, 25, 1, 31, 7],
+           [12, 20, 10, 18, 13, 21, 11, 19], [28, 4, 26, 2, 29, 5, 27, 3]]),
+    _tile(_D6),
+    _tile(_D6),
+    _tile([[36, 68, 60, 92, 34, 66, 58, 90], [100, 4, 124, 28, 98, 2, 122, 26], [52, 84, 44, 76, 50, 82, 42, 74],
+           [116, 20, 108, 12, 114, 18, 106, 10], [32, 64, 56, 88, 38, 70, 62, 94], [96, 0, 120, 24, 102, 6, 126, 30],
+           [48, 80, 40, 72, 54, 86, 46, 78], [112, 16, 104, 8, 118, 22, 110, 14]]),
+]
+
+
 def _round_i16(f):
     """roundToInt16, yuv2rgb.c:705-715 (as the int16_t the caller stores)."""
     r = (f + (1 << 15)) >> 16
@@ -448,7 +474,11 @@ class OracleContext:
             if (not dst_rgb and self.skind in ("planar", "semi") and self.dkind in ("planar", "semi")
                     and (shs, svs) == (dhs, dvs) and (self.skind == "semi") == (self.dkind == "semi")
                     and self.sdepth != self.ddepth):
-                raise NotImplementedError("planarCopyWrapper depth conversion is not restated")
+                if self.skind != "planar" or self.dkind != "planar":
+                    raise NotImplementedError("semi-planar depth conversion is not restated")
+                self.special = "depthcopy"                             # planarCopyWrapper, swscale_unscaled.c:2220-2384
+                self.dither = dither
+                return
         if self.skind == "rgb32" and self.dkind == "rgb32":
             raise NotImplementedError("the alpha plane (alpToYV12 -> yuv2packedX with alpha) is not restated")
         self.full_chr = bool(dst_rgb and flags & SWS_FULL_CHR_H_INT)
@@ -634,7 +664,36 @@ class OracleContext:
         V = (((rv * rx + gv * gx + bv * bx) >> 15) + 128) & 0xFF
         return [Y.astype(np.uint8), U.astype(np.uint8), V.astype(np.uint8)]
 
+    def _depthcopy(self, planes):
+        """planarCopyWrapper between planar YUV depths (swscale_unscaled.c:2160-2218,2249-2346), little-endian
+        formats: ordered dither down (DITHER_COPY, the matrix of level `shift`), shift or bit replication up.
+        Chroma and limited-range luma are `shiftonly`."""
+        sd, dd = self.sdepth, self.ddepth
+        out = []
+        for i, (w, h) in enumerate([(self.sw, self.sh), (self.csw, self.csh), (self.csw, self.csh)]):
+            sdt = np.uint8 if sd == 8 else np.dtype("<u2")
+            v = np.ascontiguousarray(planes[i]).view(sdt)[:h, :w].astype(np.int64)
+            shiftonly = i > 0 or not self.src_range
+            if sd > dd:
+                shift = sd - dd
+                d = DEPTH_DITHER[shift - 1][(np.arange(h) & 7)[:, None], (np.arange(w) & 7)[None, :]]
+                if self.dither == 0:                                   # SWS_DITHER_NONE
+                    t = (v + (1 << (shift - 1))) >> shift
+                    o = t - (t >> dd)
+                elif shiftonly:
+                    t = (v + d) >> shift
+                    o = t - (t >> dd)
+                else:
+                    o = (v - (v >> dd) + d) >> shift
+            else:
+                shift = dd - sd
+                o = v << shift if shiftonly else (v << shift) | (v >> (2 * sd - dd))
+            out.append(o.astype(np.uint8) if dd == 8 else o.astype("<u2"))
+        return out
+
     def scale(self, planes):
+        if self.special == "depthcopy":
+            return self._depthcopy(planes)
         if self.special == "shuffle":
             return self._shuffle(planes[0])
         if self.special == "bgr24_yv12":

@@ -100,6 +100,15 @@ def cases():
                       ("yuv420p", "rgb24", (162, 122, 162, 200)), ("yuv420p", "yuv444p", (162, 122, 323, 122))]:
         out.append(dict(sw=g[0], sh=g[1], sf=sf, dw=g[2], dh=g[3], df=df, flags=FB | BX))
         out.append(dict(sw=g[0], sh=g[1], sf=sf, dw=g[2], dh=g[3], df=df, flags=FB))
+    # unscaled planar depth conversion (planarCopyWrapper): every depth pair class, both luma rules, no dither
+    for sf, df in [("yuv420p10le", "yuv420p"), ("yuv420p", "yuv420p10le"), ("yuv422p10le", "yuv422p12le"),
+                   ("yuv444p16le", "yuv444p"), ("yuv420p16le", "yuv420p10le"), ("yuv420p9le", "yuv420p"),
+                   ("yuv420p", "yuv420p16le"), ("yuv444p12le", "yuv444p10le"), ("yuv420p14le", "yuv420p12le"),
+                   ("yuv420p12le", "yuv420p")]:
+        out.append(dict(sw=162, sh=122, sf=sf, dw=162, dh=122, df=df, flags=R.SWS_BICUBIC | BX))
+        out.append(dict(sw=163, sh=121, sf=sf, dw=163, dh=121, df=df, flags=R.SWS_BICUBIC,
+                        ctx_kwargs=dict(src_range=1, dst_range=1)))
+        out.append(dict(sw=162, sh=122, sf=sf, dw=162, dh=122, df=df, flags=R.SWS_POINT, ctx_kwargs=dict(dither=0)))
     for i, c in enumerate(out):
         c.setdefault("seed", 100 + i)
         c.setdefault("mode", "extreme" if i % 7 == 3 else "noise")

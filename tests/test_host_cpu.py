@@ -199,7 +199,6 @@ def test_no_device_means_loud_failure_not_cpu_fallback():
 
 def test_init_rejects_what_the_hot_path_does_not_cover():
     for kw in (dict(src_fmt="yuv420p", dst_fmt="rgb24", flags=S.SWS_BICUBIC | S.SWS_BILINEAR),
-               dict(src_fmt="yuv420p10le", dst_fmt="yuv420p", flags=S.SWS_BICUBIC | S.BX),   # planarCopyWrapper
                dict(src_fmt="yuv420p", dst_fmt="rgb24", flags=S.SWS_BICUBIC | (1 << 16))):    # chroma drop
         with pytest.raises(RuntimeError):
             S.SwsContext(64, 64, kw["src_fmt"], 64, 64, kw["dst_fmt"], kw["flags"], plan_only=True)

@@ -155,7 +155,7 @@ def test_unsupported_fails_loudly():
     with pytest.raises(RuntimeError):
         S.SwsContext(320, 240, "yuv420p", 320, 240, "rgb24", S.SWS_BICUBIC | (1 << 16))          # vertical chroma drop
     with pytest.raises(RuntimeError):
-        S.SwsContext(320, 240, "yuv420p10le", 320, 240, "yuv420p", S.SWS_BICUBIC | BX)  # planarCopyWrapper
+        S.SwsContext(320, 240, "rgba", 640, 480, "bgra", S.SWS_BICUBIC | BX)             # alpha through the scaler
 
 
 @pytest.mark.parametrize("sf", ["yuv444p", "yuv420p", "yuv422p", "yuv444p10le", "yuv420p12le", "nv12"])
@@ -342,3 +342,29 @@ def test_fast_bilinear(sf, df, geom, extra):
     sw, sh, dw, dh = geom
     for mode in ("noise", "extreme"):
         _check(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=S.SWS_FAST_BILINEAR | extra, seed=99, mode=mode)
+
+
+# ---- unscaled planar depth conversion: planarCopyWrapper's dithered / replicated copies (swscale_unscaled.c:2220-2384) ----
+DEPTHS = ["yuv420p", "yuv420p9le", "yuv420p10le", "yuv420p12le", "yuv420p14le", "yuv420p16le"]
+
+
+@pytest.mark.parametrize("sf", DEPTHS)
+@pytest.mark.parametrize("df", DEPTHS)
+@pytest.mark.parametrize("opts", [dict(), dict(src_range=1, dst_range=1), dict(dither=0)])
+def test_depthcopy(sf, df, opts):
+    if sf == df:
+        pytest.skip("same format")
+    for (w, h) in [(644, 366), (35, 19)]:
+        for mode in ("noise", "extreme"):
+            name = _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=S.SWS_BICUBIC | BX, seed=101, mode=mode,
+                          ctx_kwargs=opts)
+            assert name == "depthcopy", name
+    if not opts:
+        slices = [(y, min(16, 366 - y)) for y in range(0, 366, 16)]         # dither rows count from the slice start
+        _check(sw=644, sh=366, sf=sf, dw=644, dh=366, df=df, flags=S.SWS_BICUBIC, seed=102, slices=slices)
+
+
+@pytest.mark.parametrize("sf,df", [("yuv422p10le", "yuv422p"), ("yuv444p", "yuv444p12le"), ("yuv444p16le", "yuv444p10le")])
+def test_depthcopy_other_subsamplings(sf, df):
+    name = _check(sw=322, sh=243, sf=sf, dw=322, dh=243, df=df, flags=S.SWS_BILINEAR, seed=103)
+    assert name == "depthcopy", name
