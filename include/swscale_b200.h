@@ -63,6 +63,7 @@ enum AVPixelFormat {
     AV_PIX_FMT_YUV422P14LE = 129,
     AV_PIX_FMT_YUV444P12LE = 131,
     AV_PIX_FMT_YUV444P14LE = 133,
+    AV_PIX_FMT_P010LE      = 158,
 };
 #endif
 

@@ -288,6 +288,7 @@ static int dst_kind_of(int fmt, const SwsPixDesc *d)
     case AV_PIX_FMT_BGR48LE: return SWSC_DST_BGR48;
     case AV_PIX_FMT_NV12:    return SWSC_DST_NV12;
     case AV_PIX_FMT_NV21:    return SWSC_DST_NV21;
+    case AV_PIX_FMT_P010LE:  return SWSC_DST_P010;
     }
     if (d->flags & SWSPF_PLANAR)
         return d->depth == 8 ? SWSC_DST_PLANAR8 : d->depth == 16 ? SWSC_DST_PLANAR16 : SWSC_DST_PLANARN;
@@ -490,6 +491,19 @@ static int init_single(SwsContext *sws, int with_device)
             (sws->dither == SWS_DITHER_BAYER || sws->dither == SWS_DITHER_AUTO) && !(dstH & 1)) {
             c->unscaled_lut = 1;        /* yuv2rgb_c_* nearest-chroma LUT converter (a13) */
             c->dst_slice_align = 2;
+        } else if (sws->dst_format == AV_PIX_FMT_P010LE && !(sd->flags & SWSPF_SEMI) && planar_yuv_pair &&
+                   sd->log2_cw == 1 && sd->log2_ch == 1 && sd->depth != 9) {
+            /* planar8ToP01xleWrapper (8-bit: << 8) and planarToP01xWrapper (10/12/14/16-bit: << 16 - depth),
+             * swscale_unscaled.c:273-375,2432-2444 */
+            c->special = SWSC_SPECIAL_P01X;
+        } else if (planar_yuv_pair && sd->depth != dd->depth && (sd->flags & SWSPF_SEMI) && (dd->flags & SWSPF_SEMI) &&
+                   sd->swap_uv == dd->swap_uv) {
+            if (sd->depth != 8) {
+                /* DITHER_COPY's tail loop drops the source shift (swscale_unscaled.c:2174-2176): not restated */
+                set_error(c, "unscaled p010 -> 8-bit semi-planar conversion is not on the CUDA hot path");
+                return AVERROR(ENOTSUP);
+            }
+            c->special = SWSC_SPECIAL_DEPTHCOPY;       /* nv12 -> p010: COPY816, swscale_unscaled.c:2266-2284 */
         } else if (planar_yuv_pair && c->chr_src_hsub == c->chr_dst_hsub &&
                    c->chr_src_vsub == c->chr_dst_vsub && sd->depth != dd->depth &&
                    !(sd->flags & SWSPF_SEMI) && !(dd->flags & SWSPF_SEMI)) {
@@ -561,6 +575,8 @@ static int init_single(SwsContext *sws, int with_device)
     p->src_layout = (sd->flags & SWSPF_SEMI) ? (sd->swap_uv ? SWSC_SRC_NV21 : SWSC_SRC_NV12) : SWSC_SRC_PLANAR;
     p->dst_kind = dst_kind_of(sws->dst_format, dd);
     p->src_bits = c->src_bpc;
+    p->src_shift = sd->shift;
+    p->dst_shift = dd->shift;
     p->dst_bits = c->dst_bpc;
     p->has_chroma = 1;
     p->unscaled_lut = c->unscaled_lut;

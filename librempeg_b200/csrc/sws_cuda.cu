@@ -68,10 +68,10 @@ __device__ __forceinline__ int clip_uintp2(int v, int bits) { return min(max(v, 
 __device__ __forceinline__ int clip_i16(int v) { return min(max(v, -32768), 32767); }
 
 template <bool SRC16>
-__device__ __forceinline__ int fetch(const uint8_t *row, int idx)
+__device__ __forceinline__ int fetch(const uint8_t *row, int idx, int shift = 0)
 {
-    if (SRC16)
-        return reinterpret_cast<const uint16_t *>(row)[idx];
+    if (SRC16)      /* p010: the sample sits in the high bits (p010LEToY_c / p010LEToUV_c, input.c:950-1006) */
+        return reinterpret_cast<const uint16_t *>(row)[idx] >> shift;
     return row[idx];
 }
 
@@ -457,6 +457,51 @@ static cudaError_t upload_depth_dither(void)
     return cudaMemcpyToSymbol(c_depth_dither, t, sizeof(t));
 }
 
+/* planarToP01xWrapper / planar8ToP01xleWrapper (swscale_unscaled.c:273-375): planar 4:2:0 -> p010le, every
+ * sample shifted left into the 16-bit container (8-bit sources by 8, N-bit sources by 16 - N), chroma
+ * interleaved U first.  blockIdx.y: 0 = luma, 1 = chroma; a thread owns 8 luma samples or 8 chroma pairs. */
+struct P01xArgs {
+    const uint8_t *src[3];
+    uint8_t *dst[2];
+    long long src_fstride[3], dst_fstride[2];
+    int src_stride[3], dst_stride[2];
+    int w, cw, y0, rows, cy0, crows;
+    int shift;
+};
+
+template <typename SrcT>
+__global__ void __launch_bounds__(256)
+sws_p01x_kernel(const __grid_constant__ P01xArgs A)
+{
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int f = blockIdx.z;
+    if (blockIdx.y == 0) {
+        const int chunks = (A.w + 7) / 8;
+        const int row = (int)(idx / chunks), c = (int)(idx - (long long)row * chunks);
+        if (row >= A.rows)
+            return;
+        const SrcT *s = reinterpret_cast<const SrcT *>(A.src[0] + f * A.src_fstride[0] + (size_t)(A.y0 + row) * A.src_stride[0]) + 8 * c;
+        uint16_t *d = reinterpret_cast<uint16_t *>(A.dst[0] + f * A.dst_fstride[0] + (size_t)(A.y0 + row) * A.dst_stride[0]) + 8 * c;
+        const int n = min(8, A.w - 8 * c);
+        for (int i = 0; i < n; i++)
+            d[i] = (uint16_t)(s[i] << A.shift);
+        return;
+    }
+    const int chunks = (A.cw + 7) / 8;
+    const int row = (int)(idx / chunks), c = (int)(idx - (long long)row * chunks);
+    if (row >= A.crows)
+        return;
+    const int y = A.cy0 + row;
+    const SrcT *su = reinterpret_cast<const SrcT *>(A.src[1] + f * A.src_fstride[1] + (size_t)y * A.src_stride[1]) + 8 * c;
+    const SrcT *sv = reinterpret_cast<const SrcT *>(A.src[2] + f * A.src_fstride[2] + (size_t)y * A.src_stride[2]) + 8 * c;
+    uint16_t *d = reinterpret_cast<uint16_t *>(A.dst[1] + f * A.dst_fstride[1] + (size_t)y * A.dst_stride[1]) + 16 * c;
+    const int n = min(8, A.cw - 8 * c);
+    for (int i = 0; i < n; i++) {
+        d[2 * i] = (uint16_t)(su[i] << A.shift);
+        d[2 * i + 1] = (uint16_t)(sv[i] << A.shift);
+    }
+}
+
 struct DepthCopyArgs {
     const uint8_t *src[3];
     uint8_t *dst[3];
@@ -465,6 +510,7 @@ struct DepthCopyArgs {
     int w[3], y0[3], rows[3];      /* per plane: width, first row, row count of this launch */
     int chunks[3];                 /* 8-sample chunks per row */
     int src_depth, dst_depth;
+    int src_shift, dst_shift;      /* position of the samples inside 16-bit containers (p010: 6) */
     int luma_shiftonly;            /* limited-range source: luma is shifted like chroma */
     int dither_none;
     int vec;                       /* planes and strides allow 8/16-byte accesses */
@@ -504,6 +550,9 @@ sws_depthcopy_kernel(const __grid_constant__ DepthCopyArgs A)
         for (int i = 0; i < 8; i++)
             v[i] = i < n ? s[i] : 0;
     }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        v[i] >>= A.src_shift;
     if (sd > dd) {
         const int shift = sd - dd;
         const uint2 dq = *reinterpret_cast<const uint2 *>(c_depth_dither[shift - 1][row & 7]);   /* rows count from the slice */
@@ -524,7 +573,7 @@ sws_depthcopy_kernel(const __grid_constant__ DepthCopyArgs A)
         const int shift = dd - sd, rep = 2 * sd - dd;
 #pragma unroll
         for (int i = 0; i < 8; i++)
-            o[i] = shiftonly ? v[i] << shift : (v[i] << shift) | (v[i] >> rep);
+            o[i] = (shiftonly ? v[i] << shift : (v[i] << shift) | (v[i] >> rep)) << A.dst_shift;
     }
     if (n == 8 && A.vec) {
         if (sizeof(DstT) == 1) {
@@ -618,7 +667,7 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
                     val += rgb_luma14(P, row, min(pos + j, P.src_w - 1)) * (int)co[j];
             } else {
                 for (int j = 0; j < fs; j++)
-                    val += fetch<SRC16>(row, min(pos + j, P.src_w - 1)) * (int)co[j];
+                    val += fetch<SRC16>(row, min(pos + j, P.src_w - 1), P.src_shift) * (int)co[j];
             }
             val = min(val >> sh, h_max);
             if (P.range_mode) {
@@ -672,8 +721,8 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
                 for (int j = 0; j < fs; j++) {
                     const int sx = min(pos + j, P.chr_src_w - 1);
                     const int cj = co[j];
-                    u += fetch<SRC16>(ruv, 2 * sx + uo) * cj;
-                    v += fetch<SRC16>(ruv, 2 * sx + 1 - uo) * cj;
+                    u += fetch<SRC16>(ruv, 2 * sx + uo, P.src_shift) * cj;
+                    v += fetch<SRC16>(ruv, 2 * sx + 1 - uo, P.src_shift) * cj;
                 }
             }
             u = min(u >> sh, h_max);
@@ -905,6 +954,9 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
             } else if (kind == SWSC_DST_PLANARN) {
                 const int shift = 27 - bits;
                 reinterpret_cast<uint16_t *>(d)[gx] = clip_uintp2((int)(acc + (1u << (shift - 1))) >> shift, bits);
+            } else if (kind == SWSC_DST_P010) {     /* yuv2p010l1_c / yuv2p010lX_c (output.c:538-566): 10 bits << 6 */
+                const int shift = 27 - 10;
+                reinterpret_cast<uint16_t *>(d)[gx] = clip_uintp2((int)(acc + (1u << (shift - 1))) >> shift, 10) << 6;
             } else {
                 const int v = (int)(acc + (1u << 14) - 0x40000000u) >> 15;
                 reinterpret_cast<uint16_t *>(d)[gx] = 0x8000 + clip_i16(v);
@@ -941,6 +993,11 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
                     uint8_t *d = dst1 + (size_t)y * A.dst_stride[1] + 2 * gx;
                     d[0] = kind == SWSC_DST_NV12 ? u8 : v8;
                     d[1] = kind == SWSC_DST_NV12 ? v8 : u8;
+                } else if (kind == SWSC_DST_P010) { /* yuv2p010cX_c (output.c:568-589): interleaved, U first */
+                    const int shift = 27 - 10;
+                    uint16_t *d = reinterpret_cast<uint16_t *>(dst1 + (size_t)y * A.dst_stride[1]) + 2 * gx;
+                    d[0] = clip_uintp2((int)(au + (1u << (shift - 1))) >> shift, 10) << 6;
+                    d[1] = clip_uintp2((int)(av + (1u << (shift - 1))) >> shift, 10) << 6;
                 } else if (kind == SWSC_DST_PLANARN) {
                     const int shift = 27 - bits;
                     reinterpret_cast<uint16_t *>(dst1 + (size_t)y * A.dst_stride[1])[gx] =
@@ -2127,13 +2184,42 @@ static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const i
             return 1;
         }
     }
+    if (p->special == SWSC_SPECIAL_P01X) {
+        P01xArgs a;
+        memset(&a, 0, sizeof(a));
+        for (int i = 0; i < 3; i++) {
+            if (!src[i] || (i < 2 && !dst[i]))
+                return AVERROR(EINVAL);
+            a.src[i] = src[i]; a.src_stride[i] = src_stride[i]; a.src_fstride[i] = src_fstride ? src_fstride[i] : 0;
+            if (i < 2) {
+                a.dst[i] = dst[i]; a.dst_stride[i] = dst_stride[i]; a.dst_fstride[i] = dst_fstride ? dst_fstride[i] : 0;
+            }
+        }
+        a.w = p->dst_w; a.cw = p->dst_w / 2;                 /* the reference converts src_w / 2 pairs per row */
+        a.y0 = y0; a.rows = y1 - y0;
+        a.cy0 = (y0 + 1) >> 1;                               /* chroma rows at even luma rows (:311,:358) */
+        a.crows = ((y1 + 1) >> 1) - a.cy0;
+        a.shift = p->src_bits == 8 ? 8 : 16 - p->src_bits;
+        const long long lw = (long long)((a.w + 7) / 8) * a.rows, cwk = (long long)((a.cw + 7) / 8) * a.crows;
+        const long long mx = lw > cwk ? lw : cwk;
+        dim3 grid((unsigned)((mx + 255) / 256), 2, nb_frames);
+        if (p->src_bits == 8)
+            sws_p01x_kernel<uint8_t><<<grid, 256, 0, stream>>>(a);
+        else
+            sws_p01x_kernel<uint16_t><<<grid, 256, 0, stream>>>(a);
+        st->kernel_name = "p01x";
+        CUDA_OK(cudaGetLastError());
+        st->launches++;
+        return 1;
+    }
     if (p->special == SWSC_SPECIAL_DEPTHCOPY) {
         DepthCopyArgs a;
         memset(&a, 0, sizeof(a));
-        const int sb = p->src_bits > 8 ? 2 : 1, db = p->dst_bits > 8 ? 2 : 1;
+        const bool semi = p->src_layout != SWSC_SRC_PLANAR;       /* nv12 -> p010: the UV plane is one row of 2 cw samples */
+        const int np = semi ? 2 : 3;
         bool vec = true;
         long long mx = 0;
-        for (int i = 0; i < 3; i++) {
+        for (int i = 0; i < np; i++) {
             if (!src[i] || !dst[i])
                 return AVERROR(EINVAL);
             a.src[i] = src[i]; a.dst[i] = dst[i];
@@ -2142,7 +2228,7 @@ static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const i
             a.dst_fstride[i] = dst_fstride ? dst_fstride[i] : 0;
             vec = vec && aligned16(src[i]) && aligned16(dst[i]) && !(src_stride[i] & 15) && !(dst_stride[i] & 15) &&
                   !(a.src_fstride[i] & 15) && !(a.dst_fstride[i] & 15);
-            a.w[i] = i ? p->chr_dst_w : p->dst_w;
+            a.w[i] = i ? (semi ? 2 * p->chr_dst_w : p->chr_dst_w) : p->dst_w;
             a.y0[i] = i ? (y0 + (1 << p->chr_dst_vsub) - 1) >> p->chr_dst_vsub : y0;       /* AV_CEIL_RSHIFT, :2229-2230 */
             const int yend = i ? (y1 == p->dst_h ? p->chr_dst_h : (y1 + (1 << p->chr_dst_vsub) - 1) >> p->chr_dst_vsub) : y1;
             a.rows[i] = yend - a.y0[i];
@@ -2150,12 +2236,12 @@ static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const i
             const long long work = (long long)a.chunks[i] * a.rows[i];
             if (work > mx) mx = work;
         }
-        (void)sb; (void)db;
         a.src_depth = p->src_bits; a.dst_depth = p->dst_bits;
+        a.src_shift = p->src_shift; a.dst_shift = p->dst_shift;
         a.luma_shiftonly = !p->src_full_range;
         a.dither_none = p->dither_none;
         a.vec = vec;
-        dim3 grid((unsigned)((mx + 255) / 256), 3, nb_frames);
+        dim3 grid((unsigned)((mx + 255) / 256), np, nb_frames);
         if (p->src_bits == 8)
             sws_depthcopy_kernel<uint8_t, uint16_t><<<grid, 256, 0, stream>>>(a);
         else if (p->dst_bits == 8)
@@ -2346,7 +2432,7 @@ static int ensure_staging(SwsCudaState *st)
     default: {
         const int db = p->dst_bits > 8 ? 2 : 1;
         st->dst_rowbytes[0] = p->dst_w * db;
-        if (p->dst_kind == SWSC_DST_NV12 || p->dst_kind == SWSC_DST_NV21) {
+        if (p->dst_kind == SWSC_DST_NV12 || p->dst_kind == SWSC_DST_NV21 || p->dst_kind == SWSC_DST_P010) {
             st->dst_rows[1] = p->chr_dst_h; st->dst_rowbytes[1] = p->chr_dst_w * 2 * db;
         } else {
             st->dst_rows[1] = st->dst_rows[2] = p->chr_dst_h;

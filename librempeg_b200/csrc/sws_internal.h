@@ -37,6 +37,7 @@ typedef struct SwsPixDesc {
     int nb_planes;
     int swap_uv;      /* nv21                                        */
     int as_input, as_output;
+    int shift;        /* samples sit in the high bits of their 16-bit container (p010: 6) */
 } SwsPixDesc;
 
 const SwsPixDesc *ff_b200_pix_desc(int fmt);
@@ -93,6 +94,7 @@ enum {
     SWSC_DST_PLANAR16,
     SWSC_DST_NV12,
     SWSC_DST_NV21,
+    SWSC_DST_P010,         /* semi-planar, 10 bits in the high bits of 16  */
     SWSC_DST_RGB24,
     SWSC_DST_BGR24,
     SWSC_DST_RGBA,
@@ -109,6 +111,7 @@ enum {
     SWSC_SPECIAL_SHUFFLE,        /* rgbToRgbWrapper / packedCopyWrapper between 8-bit packed RGB layouts */
     SWSC_SPECIAL_BGR24_YV12,     /* bgr24ToYv12Wrapper: 2x2 box chroma, truncating 15-bit matrix */
     SWSC_SPECIAL_COPY8,          /* planarCopyWrapper / planarToNv12Wrapper / nv12ToPlanarWrapper, 8-bit */
+    SWSC_SPECIAL_P01X,           /* planarToP01xWrapper / planar8ToP01xleWrapper: shift + chroma interleave */
     SWSC_SPECIAL_DEPTHCOPY,      /* planarCopyWrapper between planar YUV depths (dithered down, replicated up) */
 };
 
@@ -119,6 +122,8 @@ typedef struct SwsCudaPlan {
     int chr_src_hsub, chr_src_vsub, chr_dst_hsub, chr_dst_vsub;
     int src_layout, dst_kind;
     int src_bits, dst_bits;      /* component depth                           */
+    int src_shift;               /* right shift of 16-bit source samples (p010: 6) */
+    int dst_shift;               /* left shift of 16-bit destination samples (p010: 6) */
     int inter_bits;              /* 15 or 19: width of the h-scaled lines     */
     int h_shift;                 /* right shift applied after the H FIR       */
     int has_chroma;              /* 0 for gray sources/destinations           */

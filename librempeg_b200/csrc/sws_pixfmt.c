@@ -34,6 +34,7 @@ static const SwsPixDesc table[] = {
     YUVP(AV_PIX_FMT_YUV444P16LE, "yuv444p16le", 16, 0, 0, 48),
     { AV_PIX_FMT_NV12, "nv12", SWSPF_SEMI, 8, 1, 1, 12, 2, 0, 1, 1 },
     { AV_PIX_FMT_NV21, "nv21", SWSPF_SEMI, 8, 1, 1, 12, 2, 1, 1, 1 },
+    { AV_PIX_FMT_P010LE, "p010le", SWSPF_SEMI, 10, 1, 1, 15, 2, 0, 1, 1, 6 },
     { AV_PIX_FMT_RGB24,   "rgb24",   SWSPF_RGB, 8, 0, 0, 24, 1, 0, 1, 1 },
     { AV_PIX_FMT_BGR24,   "bgr24",   SWSPF_RGB, 8, 0, 0, 24, 1, 0, 1, 1 },
     { AV_PIX_FMT_RGBA,    "rgba",    SWSPF_RGB, 8, 0, 0, 32, 1, 0, 1, 1 },

@@ -68,6 +68,8 @@ def _fmt(name):
         return ("rgb16", 16, 0, 0)
     if name in ("nv12", "nv21"):
         return ("semi", 8, 1, 1)
+    if name == "p010le":
+        return ("semi", 10, 1, 1)
     for key, (cw, ch) in {"420": (1, 1), "422": (1, 0), "444": (0, 0)}.items():
         for pre in ("yuvj", "yuv"):
             head = pre + key + "p"
@@ -471,11 +473,14 @@ class OracleContext:
                     and dither in (1, 2) and not (dh & 1):
                 self.unscaled_lut = True                               # yuv2rgb_c_* (yuv2rgb.c:137-236)
                 return
+            if dfmt == "p010le" and self.skind == "planar" and (shs, svs) == (1, 1) and self.sdepth != 9:
+                self.special = "p01x"                                  # swscale_unscaled.c:273-375,2432-2444
+                return
             if (not dst_rgb and self.skind in ("planar", "semi") and self.dkind in ("planar", "semi")
                     and (shs, svs) == (dhs, dvs) and (self.skind == "semi") == (self.dkind == "semi")
                     and self.sdepth != self.ddepth):
-                if self.skind != "planar" or self.dkind != "planar":
-                    raise NotImplementedError("semi-planar depth conversion is not restated")
+                if self.skind == "semi" and (self.sdepth != 8 or (sfmt == "nv21") != (dfmt == "nv21")):
+                    raise NotImplementedError("p010 -> 8-bit semi-planar copies are not restated")
                 self.special = "depthcopy"                             # planarCopyWrapper, swscale_unscaled.c:2220-2384
                 self.dither = dither
                 return
@@ -511,7 +516,9 @@ class OracleContext:
         if self.skind == "semi":
             uv = np.ascontiguousarray(planes[1]).view(dt)[:self.csh, :2 * self.csw].astype(np.int64)
             a, b = uv[:, 0::2], uv[:, 1::2]
-            u, v = (a, b) if self.sfmt == "nv12" else (b, a)
+            u, v = (b, a) if self.sfmt == "nv21" else (a, b)
+            if self.sfmt == "p010le":                 # p010LEToY_c / p010LEToUV_c (input.c:950-1006): >> 6
+                lum, u, v = lum >> 6, u >> 6, v >> 6
         else:
             u = np.ascontiguousarray(planes[1]).view(dt)[:self.csh, :self.csw].astype(np.int64)
             v = np.ascontiguousarray(planes[2]).view(dt)[:self.csh, :self.csw].astype(np.int64)
@@ -670,7 +677,11 @@ class OracleContext:
         Chroma and limited-range luma are `shiftonly`."""
         sd, dd = self.sdepth, self.ddepth
         out = []
-        for i, (w, h) in enumerate([(self.sw, self.sh), (self.csw, self.csh), (self.csw, self.csh)]):
+        shapes = [(self.sw, self.sh), (self.csw, self.csh), (self.csw, self.csh)]
+        if self.skind == "semi":                       # nv12 -> p010: one interleaved plane of 2 cw samples per row
+            shapes = [(self.sw, self.sh), (2 * self.csw, self.csh)]
+        dst_shift = 6 if self.dfmt == "p010le" else 0
+        for i, (w, h) in enumerate(shapes):
             sdt = np.uint8 if sd == 8 else np.dtype("<u2")
             v = np.ascontiguousarray(planes[i]).view(sdt)[:h, :w].astype(np.int64)
             shiftonly = i > 0 or not self.src_range
@@ -687,11 +698,26 @@ class OracleContext:
                     o = (v - (v >> dd) + d) >> shift
             else:
                 shift = dd - sd
-                o = v << shift if shiftonly else (v << shift) | (v >> (2 * sd - dd))
-            out.append(o.astype(np.uint8) if dd == 8 else o.astype("<u2"))
+                o = (v << shift if shiftonly else (v << shift) | (v >> (2 * sd - dd))) << dst_shift
+            out.append(o.astype(np.uint8) if dd == 8 else o.astype("<u2").view(np.uint8))
         return out
 
+    def _p01x(self, planes):
+        """planar8ToP01xleWrapper (<< 8) / planarToP01xWrapper (<< 16 - depth), swscale_unscaled.c:273-375:
+        chroma interleaved U first, src_w / 2 pairs per row (an odd last column is left untouched)."""
+        sdt = np.uint8 if self.sdepth == 8 else np.dtype("<u2")
+        shift = 8 if self.sdepth == 8 else 16 - self.sdepth
+        y = np.ascontiguousarray(planes[0]).view(sdt)[:self.sh, :self.sw].astype(np.int64)
+        u = np.ascontiguousarray(planes[1]).view(sdt)[:self.csh, :self.csw].astype(np.int64)
+        v = np.ascontiguousarray(planes[2]).view(sdt)[:self.csh, :self.csw].astype(np.int64)
+        uv = np.zeros((self.cdh, 2 * self.cdw), np.int64)
+        n = self.sw // 2
+        uv[:, 0:2 * n:2], uv[:, 1:2 * n:2] = u[:, :n] << shift, v[:, :n] << shift
+        return [((y << shift) & 0xFFFF).astype("<u2").view(np.uint8), (uv & 0xFFFF).astype("<u2").view(np.uint8)]
+
     def scale(self, planes):
+        if self.special == "p01x":
+            return self._p01x(planes)
         if self.special == "depthcopy":
             return self._depthcopy(planes)
         if self.special == "shuffle":
@@ -792,9 +818,11 @@ class OracleContext:
             return (0x8000 + np.clip(val, -32768, 32767)).astype("<u2")
 
         py, pu, pv = out(yl, 0), out(yu, 0), out(yv, 3)
+        if self.dfmt == "p010le":                     # yuv2p010l1/lX/cX_c (output.c:538-589): 10 bits << 6
+            py, pu, pv = (py << 6).astype("<u2"), (pu << 6).astype("<u2"), (pv << 6).astype("<u2")
         if self.dkind == "semi":
             uv = np.zeros((pu.shape[0], pu.shape[1] * 2), pu.dtype)
-            a, b = (pu, pv) if self.dfmt == "nv12" else (pv, pu)
+            a, b = (pv, pu) if self.dfmt == "nv21" else (pu, pv)
             uv[:, 0::2], uv[:, 1::2] = a, b
             return [py.view(np.uint8), uv.view(np.uint8)]
         return [py.view(np.uint8).reshape(py.shape[0], -1), pu.view(np.uint8).reshape(pu.shape[0], -1),

@@ -109,6 +109,18 @@ def cases():
         out.append(dict(sw=163, sh=121, sf=sf, dw=163, dh=121, df=df, flags=R.SWS_BICUBIC,
                         ctx_kwargs=dict(src_range=1, dst_range=1)))
         out.append(dict(sw=162, sh=122, sf=sf, dw=162, dh=122, df=df, flags=R.SWS_POINT, ctx_kwargs=dict(dither=0)))
+    # p010le (the 10-bit surface format of hardware decoders / encoders): reader, writer, unscaled wrappers
+    for sf, df, g in [("p010le", "yuv420p", (162, 122, 200, 150)), ("p010le", "rgb24", (162, 122, 162, 122)),
+                      ("p010le", "nv12", (162, 122, 100, 75)), ("p010le", "yuv420p10le", (162, 122, 162, 122)),
+                      ("p010le", "rgb48le", (162, 122, 200, 150)), ("p010le", "p010le", (162, 122, 100, 75)),
+                      ("yuv420p", "p010le", (162, 122, 200, 150)), ("nv12", "p010le", (162, 122, 100, 75)),
+                      ("yuv420p10le", "p010le", (162, 122, 200, 150)), ("rgb24", "p010le", (162, 122, 162, 122)),
+                      ("yuv420p", "p010le", (162, 122, 162, 122)), ("yuv420p10le", "p010le", (163, 121, 163, 121)),
+                      ("yuv420p12le", "p010le", (162, 122, 162, 122)), ("yuv420p16le", "p010le", (162, 122, 162, 122)),
+                      ("yuv420p9le", "p010le", (162, 122, 162, 122)), ("yuv422p10le", "p010le", (162, 122, 162, 122))]:
+        out.append(dict(sw=g[0], sh=g[1], sf=sf, dw=g[2], dh=g[3], df=df, flags=R.SWS_BICUBIC | BX))
+    out.append(dict(sw=162, sh=122, sf="p010le", dw=200, dh=150, df="yuv420p", flags=R.SWS_BILINEAR | BX,
+                    ctx_kwargs=dict(src_range=0, dst_range=1)))
     for i, c in enumerate(out):
         c.setdefault("seed", 100 + i)
         c.setdefault("mode", "extreme" if i % 7 == 3 else "noise")

@@ -33,6 +33,8 @@ def plane_layout(fmt, w, h):
         return [(h, w * 6)]
     if fmt in ("nv12", "nv21"):
         return [(h, w), (cdiv(h, 1), cdiv(w, 1) * 2)]
+    if fmt == "p010le":
+        return [(h, w * 2), (cdiv(h, 1), cdiv(w, 1) * 4)]
     if fmt == "gray":
         return [(h, w)]
     for key, (cw, ch) in _YUV.items():
@@ -45,6 +47,8 @@ def plane_layout(fmt, w, h):
 
 
 def depth_of(fmt):
+    if fmt == "p010le":
+        return 16            # fill the whole 16-bit container: the readers drop the low six bits
     for d in (9, 10, 12, 14, 16):
         if fmt.endswith("p%dle" % d):
             return d
@@ -160,7 +164,7 @@ def _drive(c, src, dst, sh, slices):
 
 
 def _subs(fmt):
-    if fmt in ("nv12", "nv21"):
+    if fmt in ("nv12", "nv21", "p010le"):
         return "420"
     for k in _YUV:
         if k + "p" in fmt:

@@ -368,3 +368,44 @@ def test_depthcopy(sf, df, opts):
 def test_depthcopy_other_subsamplings(sf, df):
     name = _check(sw=322, sh=243, sf=sf, dw=322, dh=243, df=df, flags=S.SWS_BILINEAR, seed=103)
     assert name == "depthcopy", name
+
+
+# ---- p010le: p010LEToY/UV readers (input.c:950-1006), yuv2p010l1/lX/cX writers (output.c:538-589), the
+# unscaled planarToP01xWrapper / planar8ToP01xleWrapper (swscale_unscaled.c:273-375) ----
+@pytest.mark.parametrize("df", ["yuv420p", "nv12", "rgb24", "bgra", "yuv420p10le", "yuv444p16le", "rgb48le", "p010le"])
+@pytest.mark.parametrize("geom,flags", [((322, 242, 400, 300), S.SWS_BICUBIC | BX), ((322, 242, 160, 120), S.SWS_BILINEAR | BX),
+                                        ((322, 242, 322, 242), S.SWS_BICUBIC | BX), ((323, 241, 323, 241), S.SWS_POINT)])
+def test_p010_source(df, geom, flags):
+    sw, sh, dw, dh = geom
+    if df in ("p010le", "nv12") and (sw, sh) == (dw, dh):
+        pytest.skip("same-size semi-planar copies / depth changes (planarCopyWrapper on p010) are not on the path")
+    for mode in ("noise", "extreme"):
+        _check(sw=sw, sh=sh, sf="p010le", dw=dw, dh=dh, df=df, flags=flags, seed=105, mode=mode)
+
+
+@pytest.mark.parametrize("sf", ["yuv420p", "nv12", "yuv422p", "yuv420p10le", "yuv444p12le", "yuv420p16le", "rgb24", "bgra"])
+@pytest.mark.parametrize("geom,flags", [((322, 242, 400, 300), S.SWS_BICUBIC | BX), ((322, 242, 160, 120), S.SWS_LANCZOS | BX),
+                                        ((322, 242, 322, 242), S.SWS_BICUBIC | BX)])
+def test_p010_destination(sf, geom, flags):
+    sw, sh, dw, dh = geom
+    for mode in ("noise", "extreme"):
+        _check(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df="p010le", flags=flags, seed=106, mode=mode)
+
+
+@pytest.mark.parametrize("sf", ["yuv420p", "yuv420p10le", "yuv420p12le", "yuv420p14le", "yuv420p16le"])
+@pytest.mark.parametrize("geom", [(644, 366), (35, 19), (34, 18)])
+def test_p01x_unscaled_wrappers(sf, geom):
+    w, h = geom
+    name = _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df="p010le", flags=S.SWS_BICUBIC, seed=107)
+    assert name == "p01x", name
+    slices = [(y, min(16, h - y)) for y in range(0, h, 16)]
+    _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df="p010le", flags=S.SWS_BICUBIC, seed=108, slices=slices)
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(src_range=1, dst_range=1)])
+@pytest.mark.parametrize("geom", [(644, 366), (35, 19)])
+def test_nv12_to_p010_unscaled(geom, opts):
+    """planarCopyWrapper's COPY816 on semi-planar planes (swscale_unscaled.c:2266-2284)."""
+    w, h = geom
+    name = _check(sw=w, sh=h, sf="nv12", dw=w, dh=h, df="p010le", flags=S.SWS_BICUBIC, seed=109, ctx_kwargs=opts)
+    assert name == "depthcopy", name
