@@ -122,6 +122,7 @@ __device__ __forceinline__ void rgb_chroma14(const SwsCudaPlan &P, const uint8_t
 #include "sws_scale8.cuh"
 #include "sws_tile15.cuh"
 #include "sws_rgb420.cuh"
+#include "sws_fast420_hi8.cuh"
 
 
 /* ------------------------------------------------------------------------
@@ -1034,6 +1035,7 @@ struct SwsCudaState {
     /* fast420 path */
     int fast_ok;
     int r420_ok, r420_cr;
+    int fasthi8_ok;
     int s8_ok, s8_fs4, s8_tile_h, s8_nl_cap, s8_nc_cap, s8_seg_l, s8_seg_c, s8_slot, s8_vl_n4, s8_vc_n4;
     size_t s8_smem;
     void *s8_tables;
@@ -1367,19 +1369,13 @@ static fast16_kernel_t pick_fast16(int taps, bool bgr)
     }
 }
 
-static int fast16_setup(SwsCudaState *st, const SwsFirBank *vc)
+/* per-row metadata shared by the two high-depth same-size kernels: first chroma source row (tile relative and
+ * absolute) and the eight int16 vertical chroma taps.  Returns 1 when uploaded, 0 when the geometry does not
+ * fit the kernels' 24-row chroma window, < 0 on error. */
+static int fast16_rows(SwsCudaState *st, const SwsFirBank *vc, int taps)
 {
-    const SwsCudaPlan *p = &st->plan;
-    st->fast16_ok = 0;
-    if (p->src_layout != SWSC_SRC_PLANAR || p->src_bits <= 8 || p->src_bits > 16 || p->inter_bits != 19)
-        return 0;
-    if (p->dst_kind != SWSC_DST_RGB48 && p->dst_kind != SWSC_DST_BGR48)
-        return 0;
-    if (!p->lum_identity || !p->chr_h_identity || p->chr_src_hsub != 1 || p->chr_dst_hsub != 1)
-        return 0;
-    if (vc->size > 8 || p->range_mode || p->full_chr || p->unscaled_lut || (p->dst_w & 1) || !get_encode_tiled())
-        return 0;
-    const int taps = vc->size <= 4 ? 4 : vc->size <= 6 ? 6 : 8;
+    if (st->d_fast16_rows)
+        return 1;
     const int padded = ((vc->len + F16_TH - 1) / F16_TH + 1) * F16_TH;
     Fast16Row *rows = (Fast16Row *)calloc(padded, sizeof(Fast16Row));
     if (!rows)
@@ -1409,6 +1405,25 @@ static int fast16_setup(SwsCudaState *st, const SwsFirBank *vc)
         e = cudaMemcpy(st->d_fast16_rows, rows, sizeof(Fast16Row) * padded, cudaMemcpyHostToDevice);
     free(rows);
     CUDA_OK(e);
+    return 1;
+}
+
+static int fast16_setup(SwsCudaState *st, const SwsFirBank *vc)
+{
+    const SwsCudaPlan *p = &st->plan;
+    st->fast16_ok = 0;
+    if (p->src_layout != SWSC_SRC_PLANAR || p->src_bits <= 8 || p->src_bits > 16 || p->inter_bits != 19)
+        return 0;
+    if (p->dst_kind != SWSC_DST_RGB48 && p->dst_kind != SWSC_DST_BGR48)
+        return 0;
+    if (!p->lum_identity || !p->chr_h_identity || p->chr_src_hsub != 1 || p->chr_dst_hsub != 1)
+        return 0;
+    if (vc->size > 8 || p->range_mode || p->full_chr || p->unscaled_lut || (p->dst_w & 1) || !get_encode_tiled())
+        return 0;
+    const int taps = vc->size <= 4 ? 4 : vc->size <= 6 ? 6 : 8;
+    int ret = fast16_rows(st, vc, taps);
+    if (ret <= 0)
+        return ret;
     CUDA_OK(cudaFuncSetAttribute((const void *)pick_fast16(taps, false),
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
     CUDA_OK(cudaFuncSetAttribute((const void *)pick_fast16(taps, true),
@@ -1466,6 +1481,109 @@ static int fast16_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     const int grid = (int)(total < (long long)st->num_sms * F420_CTAS_PER_SM ? total : (long long)st->num_sms * F420_CTAS_PER_SM);
     pick_fast16(st->fast16_taps, a.bgr)<<<grid, F420_THREADS, F16_SMEM, stream>>>(my, mu, mv, mo, a);
     st->kernel_name = "fast420_rgb16_tma";
+    CUDA_OK(cudaGetLastError());
+    st->launches++;
+    return 1;
+}
+
+
+/* ---------------------------------------------------------------- fast420 high-depth -> 8-bit RGB host side */
+
+typedef void (*fasthi8_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                                 const FastHi8Args);
+
+template <int TAPS>
+static fasthi8_kernel_t pick_fasthi8_fmt(int fmt)
+{
+    switch (fmt) {
+    case F420_RGB24: return sws_fast420_hi8_kernel<TAPS, F420_RGB24>;
+    case F420_BGR24: return sws_fast420_hi8_kernel<TAPS, F420_BGR24>;
+    case F420_RGBA:  return sws_fast420_hi8_kernel<TAPS, F420_RGBA>;
+    case F420_BGRA:  return sws_fast420_hi8_kernel<TAPS, F420_BGRA>;
+    case F420_ARGB:  return sws_fast420_hi8_kernel<TAPS, F420_ARGB>;
+    default:         return sws_fast420_hi8_kernel<TAPS, F420_ABGR>;
+    }
+}
+
+static fasthi8_kernel_t pick_fasthi8(int taps, int fmt)
+{
+    return taps == 4 ? pick_fasthi8_fmt<4>(fmt) : taps == 6 ? pick_fasthi8_fmt<6>(fmt) : pick_fasthi8_fmt<8>(fmt);
+}
+
+static int fasthi8_setup(SwsCudaState *st, const SwsFirBank *vc)
+{
+    const SwsCudaPlan *p = &st->plan;
+    st->fasthi8_ok = 0;
+    if (p->src_layout != SWSC_SRC_PLANAR || p->src_bits <= 8 || p->src_bits > 16 || p->inter_bits != 15 || p->src_shift)
+        return 0;
+    if (p->dst_kind < SWSC_DST_RGB24 || p->dst_kind > SWSC_DST_ABGR || p->full_chr || p->special || p->unscaled_lut)
+        return 0;
+    if (!p->lum_identity || !p->chr_h_identity || p->chr_src_hsub != 1 || p->chr_dst_hsub != 1)
+        return 0;
+    if (vc->size > 8 || (p->dst_w & 1) || !get_encode_tiled())
+        return 0;
+    if ((p->dst_kind == SWSC_DST_RGB24 || p->dst_kind == SWSC_DST_BGR24) && (p->dst_w & 3))
+        return 0;                     /* the store tensor map counts 32-bit words */
+    const int taps = vc->size <= 4 ? 4 : vc->size <= 6 ? 6 : 8;
+    int ret = fast16_rows(st, vc, taps);
+    if (ret <= 0)
+        return ret;
+    const int fmt = fast420_fmt(p->dst_kind);
+    CUDA_OK(cudaFuncSetAttribute((const void *)pick_fasthi8(taps, fmt), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 H8_SMEM(fmt >= F420_RGBA ? 4 : 3)));
+    st->fasthi8_ok = 1;
+    st->fast16_taps = taps;
+    st->kernel_name = "fast420_hi8_tma";
+    return 0;
+}
+
+static int fasthi8_launch(SwsCudaState *st, const uint8_t *const src[4], const int src_stride[4],
+                          const int64_t src_fstride[4], uint8_t *const dst[4], const int dst_stride[4],
+                          const int64_t dst_fstride[4], int nb_frames, int y0, int y1, cudaStream_t stream)
+{
+    const SwsCudaPlan *p = &st->plan;
+    if (!st->fasthi8_ok || (st->disabled & 128) || (y0 % F16_TH) || y1 <= y0 || y1 > p->dst_h)
+        return 0;
+    for (int i = 0; i < 3; i++)
+        if (!src[i] || !aligned16(src[i]) || (src_stride[i] & 15) || src_stride[i] <= 0 ||
+            (nb_frames > 1 && (src_fstride[i] & 15 || src_fstride[i] <= 0)))
+            return 0;
+    if (!aligned16(dst[0]) || (dst_stride[0] & 15) || dst_stride[0] <= 0 ||
+        (nb_frames > 1 && (dst_fstride[0] & 15 || dst_fstride[0] <= 0)))
+        return 0;
+    const int fmt = fast420_fmt(p->dst_kind);
+    const int bpp = fmt >= F420_RGBA ? 4 : 3;
+    CUtensorMap my, mu, mv, mo;
+    const uint64_t fs_y = nb_frames > 1 ? src_fstride[0] : (uint64_t)src_stride[0] * p->src_h;
+    const uint64_t fs_u = nb_frames > 1 ? src_fstride[1] : (uint64_t)src_stride[1] * p->chr_src_h;
+    const uint64_t fs_v = nb_frames > 1 ? src_fstride[2] : (uint64_t)src_stride[2] * p->chr_src_h;
+    const uint64_t fs_o = nb_frames > 1 ? dst_fstride[0] : (uint64_t)dst_stride[0] * p->dst_h;
+    int ret;
+    if ((ret = make_map_3d(&my, CU_TENSOR_MAP_DATA_TYPE_UINT16, src[0], p->src_w, p->src_h, nb_frames,
+                           src_stride[0], fs_y, F16_TW, F16_TH)) < 0 ||
+        (ret = make_map_3d(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT16, src[1], p->chr_src_w, p->chr_src_h, nb_frames,
+                           src_stride[1], fs_u, F16_TW / 2, F16_CROWS)) < 0 ||
+        (ret = make_map_3d(&mv, CU_TENSOR_MAP_DATA_TYPE_UINT16, src[2], p->chr_src_w, p->chr_src_h, nb_frames,
+                           src_stride[2], fs_v, F16_TW / 2, F16_CROWS)) < 0 ||
+        (ret = make_map_3d(&mo, CU_TENSOR_MAP_DATA_TYPE_UINT32, dst[0], (uint64_t)p->dst_w * bpp / 4, y1,
+                           nb_frames, dst_stride[0], fs_o, F16_TW * bpp / 4, F16_TH / F420_CWARPS)) < 0)
+        return ret;
+    FastHi8Args a;
+    memset(&a, 0, sizeof(a));
+    a.tiles_x = (p->dst_w + F16_TW - 1) / F16_TW;
+    a.tiles_y = (y1 - y0 + F16_TH - 1) / F16_TH;
+    a.ty_first = y0 / F16_TH;
+    a.frames = nb_frames;
+    a.dst_h = p->dst_h;
+    a.sdown = p->src_bits - 1;
+    a.cy = p->rgb.cy; a.yb = p->rgb.yb;
+    a.crv = p->rgb.crv; a.cbu = p->rgb.cbu; a.cgu = p->rgb.cgu; a.cgv = p->rgb.cgv;
+    a.base_r = p->rgb.base_r; a.base_g = p->rgb.base_g; a.base_b = p->rgb.base_b;
+    a.rows = st->d_fast16_rows;
+    const long long total = (long long)a.tiles_x * a.tiles_y * nb_frames;
+    const int grid = (int)(total < (long long)st->num_sms * F420_CTAS_PER_SM ? total : (long long)st->num_sms * F420_CTAS_PER_SM);
+    pick_fasthi8(st->fast16_taps, fmt)<<<grid, F420_THREADS, H8_SMEM(bpp), stream>>>(my, mu, mv, mo, a);
+    st->kernel_name = "fast420_hi8_tma";
     CUDA_OK(cudaGetLastError());
     st->launches++;
     return 1;
@@ -1809,6 +1927,9 @@ extern "C" int ff_b200_cuda_create(SwsCudaState **out, SwsCudaPlan *plan,
     ret = fast16_setup(st, vc);
     if (ret < 0)
         return ret;
+    ret = fasthi8_setup(st, vc);
+    if (ret < 0)
+        return ret;
     ret = scale8_setup(st, hl, hc, vl, vc);
     if (ret < 0)
         return ret;
@@ -1828,6 +1949,7 @@ extern "C" int ff_b200_cuda_create(SwsCudaState **out, SwsCudaPlan *plan,
             if (strstr(d, "scale8"))  st->disabled |= 4;
             if (strstr(d, "copy8"))   st->disabled |= 32;
             if (strstr(d, "rgb420"))  st->disabled |= 64;
+            if (strstr(d, "hi8"))     st->disabled |= 128;
             if (strstr(d, "tile15"))  st->disabled |= 16;
         }
     }
@@ -2374,6 +2496,9 @@ extern "C" int ff_b200_cuda_launch(SwsCudaState *st,
         if (r != 0)
             return r < 0 ? r : 0;
         r = fast16_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);
+        if (r != 0)
+            return r < 0 ? r : 0;
+        r = fasthi8_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);
         if (r != 0)
             return r < 0 ? r : 0;
         r = rgb420_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);

@@ -409,3 +409,24 @@ def test_nv12_to_p010_unscaled(geom, opts):
     w, h = geom
     name = _check(sw=w, sh=h, sf="nv12", dw=w, dh=h, df="p010le", flags=S.SWS_BICUBIC, seed=109, ctx_kwargs=opts)
     assert name == "depthcopy", name
+
+
+# ---- 9..16-bit planar -> packed 8-bit RGB of the same size: the TMA kernel for 10-bit video to display RGB ----
+@pytest.mark.parametrize("sf", ["yuv420p10le", "yuv420p9le", "yuv420p12le", "yuv420p14le", "yuv420p16le"])
+@pytest.mark.parametrize("df", ["rgb24", "bgr24", "rgba", "bgra", "argb", "abgr"])
+@pytest.mark.parametrize("geom,flags", [((644, 366), S.SWS_BICUBIC | BX), ((256, 34), S.SWS_BILINEAR | BX),
+                                        ((1280, 720), S.SWS_LANCZOS | BX), ((648, 360), S.SWS_BICUBIC),
+                                        ((132, 66), S.SWS_POINT)])
+def test_fast420_hi8_instantiations(sf, df, geom, flags):
+    w, h = geom
+    for mode in ("noise", "extreme"):
+        name = _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=flags, seed=111, mode=mode)
+        assert name.startswith("fast420_hi8"), name
+
+
+def test_fast420_hi8_colorspace_and_slices():
+    colorspace = (9, 1, 9, 0, 0, 1 << 16, 1 << 16)              # BT.2020, full-range source
+    _check(sw=640, sh=360, sf="yuv420p10le", dw=640, dh=360, df="bgra", flags=S.SWS_BICUBIC | BX, seed=112,
+           colorspace=colorspace)
+    slices = [(y, min(64, 360 - y)) for y in range(0, 360, 64)]
+    _check(sw=640, sh=360, sf="yuv420p10le", dw=640, dh=360, df="rgb24", flags=S.SWS_BICUBIC | BX, seed=113, slices=slices)
