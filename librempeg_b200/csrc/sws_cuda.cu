@@ -1492,29 +1492,36 @@ static int fast16_launch(SwsCudaState *st, const uint8_t *const src[4], const in
 typedef void (*fasthi8_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                                  const FastHi8Args);
 
-template <int TAPS>
+template <int TAPS, bool SEMI>
 static fasthi8_kernel_t pick_fasthi8_fmt(int fmt)
 {
     switch (fmt) {
-    case F420_RGB24: return sws_fast420_hi8_kernel<TAPS, F420_RGB24>;
-    case F420_BGR24: return sws_fast420_hi8_kernel<TAPS, F420_BGR24>;
-    case F420_RGBA:  return sws_fast420_hi8_kernel<TAPS, F420_RGBA>;
-    case F420_BGRA:  return sws_fast420_hi8_kernel<TAPS, F420_BGRA>;
-    case F420_ARGB:  return sws_fast420_hi8_kernel<TAPS, F420_ARGB>;
-    default:         return sws_fast420_hi8_kernel<TAPS, F420_ABGR>;
+    case F420_RGB24: return sws_fast420_hi8_kernel<TAPS, F420_RGB24, SEMI>;
+    case F420_BGR24: return sws_fast420_hi8_kernel<TAPS, F420_BGR24, SEMI>;
+    case F420_RGBA:  return sws_fast420_hi8_kernel<TAPS, F420_RGBA, SEMI>;
+    case F420_BGRA:  return sws_fast420_hi8_kernel<TAPS, F420_BGRA, SEMI>;
+    case F420_ARGB:  return sws_fast420_hi8_kernel<TAPS, F420_ARGB, SEMI>;
+    default:         return sws_fast420_hi8_kernel<TAPS, F420_ABGR, SEMI>;
     }
 }
 
-static fasthi8_kernel_t pick_fasthi8(int taps, int fmt)
+static fasthi8_kernel_t pick_fasthi8(int taps, int fmt, bool semi)
 {
-    return taps == 4 ? pick_fasthi8_fmt<4>(fmt) : taps == 6 ? pick_fasthi8_fmt<6>(fmt) : pick_fasthi8_fmt<8>(fmt);
+    if (semi)
+        return taps == 4 ? pick_fasthi8_fmt<4, true>(fmt) : taps == 6 ? pick_fasthi8_fmt<6, true>(fmt)
+                                                                      : pick_fasthi8_fmt<8, true>(fmt);
+    return taps == 4 ? pick_fasthi8_fmt<4, false>(fmt) : taps == 6 ? pick_fasthi8_fmt<6, false>(fmt)
+                                                                   : pick_fasthi8_fmt<8, false>(fmt);
 }
 
 static int fasthi8_setup(SwsCudaState *st, const SwsFirBank *vc)
 {
     const SwsCudaPlan *p = &st->plan;
     st->fasthi8_ok = 0;
-    if (p->src_layout != SWSC_SRC_PLANAR || p->src_bits <= 8 || p->src_bits > 16 || p->inter_bits != 15 || p->src_shift)
+    /* planar 9..16-bit, or p010le (semi-planar, samples in the high bits) */
+    const bool semi = p->src_layout == SWSC_SRC_NV12;
+    if ((p->src_layout != SWSC_SRC_PLANAR && !semi) || p->src_bits <= 8 || p->src_bits > 16 || p->inter_bits != 15 ||
+        (!semi && p->src_shift))
         return 0;
     if (p->dst_kind < SWSC_DST_RGB24 || p->dst_kind > SWSC_DST_ABGR || p->full_chr || p->special || p->unscaled_lut)
         return 0;
@@ -1529,7 +1536,7 @@ static int fasthi8_setup(SwsCudaState *st, const SwsFirBank *vc)
     if (ret <= 0)
         return ret;
     const int fmt = fast420_fmt(p->dst_kind);
-    CUDA_OK(cudaFuncSetAttribute((const void *)pick_fasthi8(taps, fmt), cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_OK(cudaFuncSetAttribute((const void *)pick_fasthi8(taps, fmt, semi), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  H8_SMEM(fmt >= F420_RGBA ? 4 : 3)));
     st->fasthi8_ok = 1;
     st->fast16_taps = taps;
@@ -1544,7 +1551,8 @@ static int fasthi8_launch(SwsCudaState *st, const uint8_t *const src[4], const i
     const SwsCudaPlan *p = &st->plan;
     if (!st->fasthi8_ok || (st->disabled & 128) || (y0 % F16_TH) || y1 <= y0 || y1 > p->dst_h)
         return 0;
-    for (int i = 0; i < 3; i++)
+    const bool semi = p->src_layout == SWSC_SRC_NV12;
+    for (int i = 0; i < (semi ? 2 : 3); i++)
         if (!src[i] || !aligned16(src[i]) || (src_stride[i] & 15) || src_stride[i] <= 0 ||
             (nb_frames > 1 && (src_fstride[i] & 15 || src_fstride[i] <= 0)))
             return 0;
@@ -1556,18 +1564,26 @@ static int fasthi8_launch(SwsCudaState *st, const uint8_t *const src[4], const i
     CUtensorMap my, mu, mv, mo;
     const uint64_t fs_y = nb_frames > 1 ? src_fstride[0] : (uint64_t)src_stride[0] * p->src_h;
     const uint64_t fs_u = nb_frames > 1 ? src_fstride[1] : (uint64_t)src_stride[1] * p->chr_src_h;
-    const uint64_t fs_v = nb_frames > 1 ? src_fstride[2] : (uint64_t)src_stride[2] * p->chr_src_h;
     const uint64_t fs_o = nb_frames > 1 ? dst_fstride[0] : (uint64_t)dst_stride[0] * p->dst_h;
     int ret;
     if ((ret = make_map_3d(&my, CU_TENSOR_MAP_DATA_TYPE_UINT16, src[0], p->src_w, p->src_h, nb_frames,
                            src_stride[0], fs_y, F16_TW, F16_TH)) < 0 ||
-        (ret = make_map_3d(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT16, src[1], p->chr_src_w, p->chr_src_h, nb_frames,
-                           src_stride[1], fs_u, F16_TW / 2, F16_CROWS)) < 0 ||
-        (ret = make_map_3d(&mv, CU_TENSOR_MAP_DATA_TYPE_UINT16, src[2], p->chr_src_w, p->chr_src_h, nb_frames,
-                           src_stride[2], fs_v, F16_TW / 2, F16_CROWS)) < 0 ||
         (ret = make_map_3d(&mo, CU_TENSOR_MAP_DATA_TYPE_UINT32, dst[0], (uint64_t)p->dst_w * bpp / 4, y1,
                            nb_frames, dst_stride[0], fs_o, F16_TW * bpp / 4, F16_TH / F420_CWARPS)) < 0)
         return ret;
+    if (semi) {
+        if ((ret = make_map_3d(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT16, src[1], 2 * (uint64_t)p->chr_src_w, p->chr_src_h,
+                               nb_frames, src_stride[1], fs_u, F16_TW, F16_CROWS)) < 0)
+            return ret;
+        mv = mu;
+    } else {
+        const uint64_t fs_v = nb_frames > 1 ? src_fstride[2] : (uint64_t)src_stride[2] * p->chr_src_h;
+        if ((ret = make_map_3d(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT16, src[1], p->chr_src_w, p->chr_src_h, nb_frames,
+                               src_stride[1], fs_u, F16_TW / 2, F16_CROWS)) < 0 ||
+            (ret = make_map_3d(&mv, CU_TENSOR_MAP_DATA_TYPE_UINT16, src[2], p->chr_src_w, p->chr_src_h, nb_frames,
+                               src_stride[2], fs_v, F16_TW / 2, F16_CROWS)) < 0)
+            return ret;
+    }
     FastHi8Args a;
     memset(&a, 0, sizeof(a));
     a.tiles_x = (p->dst_w + F16_TW - 1) / F16_TW;
@@ -1576,13 +1592,14 @@ static int fasthi8_launch(SwsCudaState *st, const uint8_t *const src[4], const i
     a.frames = nb_frames;
     a.dst_h = p->dst_h;
     a.sdown = p->src_bits - 1;
+    a.sshift = p->src_shift;
     a.cy = p->rgb.cy; a.yb = p->rgb.yb;
     a.crv = p->rgb.crv; a.cbu = p->rgb.cbu; a.cgu = p->rgb.cgu; a.cgv = p->rgb.cgv;
     a.base_r = p->rgb.base_r; a.base_g = p->rgb.base_g; a.base_b = p->rgb.base_b;
     a.rows = st->d_fast16_rows;
     const long long total = (long long)a.tiles_x * a.tiles_y * nb_frames;
     const int grid = (int)(total < (long long)st->num_sms * F420_CTAS_PER_SM ? total : (long long)st->num_sms * F420_CTAS_PER_SM);
-    pick_fasthi8(st->fast16_taps, fmt)<<<grid, F420_THREADS, H8_SMEM(bpp), stream>>>(my, mu, mv, mo, a);
+    pick_fasthi8(st->fast16_taps, fmt, semi)<<<grid, F420_THREADS, H8_SMEM(bpp), stream>>>(my, mu, mv, mo, a);
     st->kernel_name = "fast420_hi8_tma";
     CUDA_OK(cudaGetLastError());
     st->launches++;

@@ -1,6 +1,7 @@
 /*
- * sws_fast420_hi8.cuh -- planar 9..16-bit 4:2:0 -> packed 8-bit RGB (rgb24 / bgr24 / rgba / bgra /
- * argb / abgr) of the same size: the 10-bit-video-to-display conversion.  Luma path = identity, chroma only
+ * sws_fast420_hi8.cuh -- planar 9..16-bit 4:2:0 or p010le -> packed 8-bit RGB (rgb24 / bgr24 / rgba / bgra /
+ * argb / abgr) of the same size: the 10-bit-video-to-display conversion (p010le is what hardware decoders emit:
+ * samples in the high 10 bits, chroma interleaved; p010LEToY/UV_c, input.c:950-1006).  Luma path = identity, chroma only
  * filtered vertically (<= 8 taps), one chroma sample per pixel pair.
  *
  * Same skeleton as sws_fast420_16.cuh (TMA producer warp, mbarrier ring, 8 consumer warps x 4 rows, per-warp
@@ -22,13 +23,14 @@
 struct FastHi8Args {
     int tiles_x, tiles_y, frames, ty_first, dst_h;
     int sdown;                /* source depth - 1: the right shift of the identity horizontal filter */
+    int sshift;               /* position of the samples in their 16-bit containers (p010: 6) */
     int cy, yb;               /* LUT closed form (sws_colorspace.c) */
     int crv, cbu, cgu, cgv;
     int base_r, base_g, base_b;
     const Fast16Row *rows;
 };
 
-template <int TAPS, int FMT>
+template <int TAPS, int FMT, bool SEMI>
 __global__ void __launch_bounds__(F420_THREADS, F420_CTAS_PER_SM)
 sws_fast420_hi8_kernel(const __grid_constant__ CUtensorMap map_y,
                        const __grid_constant__ CUtensorMap map_u,
@@ -61,7 +63,8 @@ sws_fast420_hi8_kernel(const __grid_constant__ CUtensorMap map_y,
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_u) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+            if (!SEMI)
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
             int i = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
                 const int stage = i % F420_STAGES, k = i / F420_STAGES;
@@ -76,8 +79,12 @@ sws_fast420_hi8_kernel(const __grid_constant__ CUtensorMap map_y,
                 tile_info[stage] = make_int4(tx, y0, f, 0);
                 mbar_expect_tx(&full_bar[stage], F16_IN_BYTES);
                 tma_load_3d(b, &map_y, &full_bar[stage], tx * F16_TW, y0, f);
-                tma_load_3d(b + F16_Y_BYTES, &map_u, &full_bar[stage], tx * (F16_TW / 2), c_lo, f);
-                tma_load_3d(b + F16_Y_BYTES + F16_C_BYTES, &map_v, &full_bar[stage], tx * (F16_TW / 2), c_lo, f);
+                if (SEMI) {          /* one box of interleaved UV rows: the same bytes as the two planar boxes */
+                    tma_load_3d(b + F16_Y_BYTES, &map_u, &full_bar[stage], tx * F16_TW, c_lo, f);
+                } else {
+                    tma_load_3d(b + F16_Y_BYTES, &map_u, &full_bar[stage], tx * (F16_TW / 2), c_lo, f);
+                    tma_load_3d(b + F16_Y_BYTES + F16_C_BYTES, &map_v, &full_bar[stage], tx * (F16_TW / 2), c_lo, f);
+                }
                 bulk_load_1d(b + F16_Y_BYTES + 2 * F16_C_BYTES, A.rows + y0, F16_META_BYTES, &full_bar[stage]);
             }
         }
@@ -87,7 +94,7 @@ sws_fast420_hi8_kernel(const __grid_constant__ CUtensorMap map_y,
     /* ===== consumers: each warp converts 4 rows of every tile, 4 pixels per lane ===== */
     if (lane == 0)
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_o) : "memory");
-    const int sdown = A.sdown;
+    const int sdown = A.sdown, sshift = A.sshift;
     const int cy = A.cy, yb = A.yb;
     const int crv = A.crv, cbu = A.cbu, cgu = A.cgu, cgv = A.cgv;
     const int r0 = warp * (F16_TH / F420_CWARPS);
@@ -95,8 +102,19 @@ sws_fast420_hi8_kernel(const __grid_constant__ CUtensorMap map_y,
     unsigned char *so = so_warp + lane * (4 * BPP);
 
     /* 16-bit sample (either half of a packed word) -> 15-bit h-scaled line value */
-    auto lo15 = [&](uint32_t w) { return min((int)(((w & 0xFFFFu) << 14) >> sdown), (1 << 15) - 1); };
-    auto hi15 = [&](uint32_t w) { return min((int)(((w >> 16) << 14) >> sdown), (1 << 15) - 1); };
+    auto lo15 = [&](uint32_t w) { return min((int)((((w & 0xFFFFu) >> sshift) << 14) >> sdown), (1 << 15) - 1); };
+    auto hi15 = [&](uint32_t w) { return min((int)(((w >> (16 + sshift)) << 14) >> sdown), (1 << 15) - 1); };
+    /* chroma words of one source row: two U and two V samples of this lane's columns */
+    auto chroma = [&](const unsigned char *su, const unsigned char *sv, int row, uint32_t &nu, uint32_t &nv) {
+        if (SEMI) {
+            const uint2 q = *reinterpret_cast<const uint2 *>(su + row * (2 * F16_TW));
+            nu = prmt(q.x, q.y, 0x5410);
+            nv = prmt(q.x, q.y, 0x7632);
+        } else {
+            nu = *reinterpret_cast<const uint32_t *>(su + row * F16_TW);
+            nv = *reinterpret_cast<const uint32_t *>(sv + row * F16_TW);
+        }
+    };
 
     int i = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
@@ -107,7 +125,7 @@ sws_fast420_hi8_kernel(const __grid_constant__ CUtensorMap map_y,
         const int4 ti = tile_info[stage];
         const int4 *mrow = reinterpret_cast<const int4 *>(sb + F16_Y_BYTES + 2 * F16_C_BYTES) + 2 * r0;
         const unsigned char *sy = sb + r0 * (F16_TW * 2) + lane * 8;
-        const unsigned char *su = sb + F16_Y_BYTES + lane * 4;
+        const unsigned char *su = sb + F16_Y_BYTES + lane * (SEMI ? 8 : 4);
         const unsigned char *sv = su + F16_C_BYTES;
 
         /* this warp's previous TMA store must have finished READING its staging rows */
@@ -125,16 +143,16 @@ sws_fast420_hi8_kernel(const __grid_constant__ CUtensorMap map_y,
             if (d < 0 || d >= TAPS) {
 #pragma unroll
                 for (int j = 0; j < TAPS; j++) {
-                    const uint32_t nu = *reinterpret_cast<const uint32_t *>(su + (pos + j) * F16_TW);
-                    const uint32_t nv = *reinterpret_cast<const uint32_t *>(sv + (pos + j) * F16_TW);
+                    uint32_t nu, nv;
+                    chroma(su, sv, pos + j, nu, nv);
                     wu[j][0] = lo15(nu); wu[j][1] = hi15(nu);
                     wv[j][0] = lo15(nv); wv[j][1] = hi15(nv);
                 }
             } else {
 #pragma unroll 1
                 for (int nr = wpos + TAPS; d > 0; d--, nr++) {
-                    const uint32_t nu = *reinterpret_cast<const uint32_t *>(su + nr * F16_TW);
-                    const uint32_t nv = *reinterpret_cast<const uint32_t *>(sv + nr * F16_TW);
+                    uint32_t nu, nv;
+                    chroma(su, sv, nr, nu, nv);
 #pragma unroll
                     for (int j = 0; j < TAPS - 1; j++) {
                         wu[j][0] = wu[j + 1][0]; wu[j][1] = wu[j + 1][1];

@@ -27,6 +27,7 @@ CONFIGS = [
     ("C3 4K yuv420p10le->rgb48le lanczos", 3840, 2160, "yuv420p10le", 3840, 2160, "rgb48le", S.SWS_LANCZOS | S.BX),
     ("C3b 4K yuv420p10le->rgb24 bicubic", 3840, 2160, "yuv420p10le", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
     ("C3c 4K yuv420p10le->bgra bicubic", 3840, 2160, "yuv420p10le", 3840, 2160, "bgra", S.SWS_BICUBIC | S.BX),
+    ("C3p 4K p010le->rgb24 bicubic", 3840, 2160, "p010le", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
     ("C4 8K nv12->1080p yuv420p bicubic", 7680, 4320, "nv12", 1920, 1080, "yuv420p", S.SWS_BICUBIC | S.BX),
     ("C5 4K yuv420p->rgb24 bicubic", 3840, 2160, "yuv420p", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
     ("C5' 4K yuv420p->rgb24 default flags (LUT path)", 3840, 2160, "yuv420p", 3840, 2160, "rgb24", S.SWS_BICUBIC),
@@ -67,7 +68,7 @@ def main():
             per_frame = sum(rows * rb for rows, rb in sl) + sum(rows * rb for rows, rb in dl)
             F = max(16, min(1024, int(args.gbytes * 1e9 / per_frame)))
         src = [torch.randint(0, 256, (F, rows * rb), dtype=torch.uint8, device=dev) for rows, rb in sl]
-        if "10le" in sf:   # keep 10-bit samples in range
+        if "10le" in sf and sf != "p010le":   # keep 10-bit samples in range
             for t in src:
                 v = t.view(torch.int16)
                 v &= 0x3FF
