@@ -288,3 +288,46 @@ def test_colour_property_queries_and_default_filter():
     L.sws_convertPalette8ToPacked24(src, d24, 4, pal)
     L.sws_convertPalette8ToPacked32(src, d32, 4, pal)
     assert list(d24) == [10, 20, 30] * 4 and list(d32) == [10, 20, 30, 40] * 4
+
+
+@pytest.mark.parametrize("g", [(352, 288, "yuv420p", 200, 100, "yuv420p"), (176, 144, "yuv420p", 352, 288, "rgb24"),
+                               (640, 360, "nv12", 1000, 360, "yuv420p"), (640, 360, "yuv420p", 640, 200, "rgb24")],
+                         ids=lambda g: "%dx%d_%s_%dx%d_%s" % g)
+def test_fast_bilinear_banks_restate_hyscale_fast(g):
+    """SWS_FAST_BILINEAR: the horizontal banks must reproduce ff_hyscale_fast_c / ff_hcscale_fast_c
+    (hscale_fast_bilinear.c:23-55) sample for sample through the ordinary (sum src*coef) >> 7 stage, and the
+    vertical banks are the reference's 2-tap initFilter branch (compared with the real reference)."""
+    sw, sh, sf, dw, dh, df = g
+    fl = S.SWS_FAST_BILINEAR | S.BX
+    mine = S.SwsContext(sw, sh, sf, dw, dh, df, fl, plan_only=True)
+    orc = O.OracleContext(sw, sh, sf, dw, dh, df, fl)
+    assert orc.fast_h
+    rng = np.random.default_rng(7)
+    for which, (src_w, dst_w, xinc, chroma) in enumerate([(sw, dw, orc.lum_xinc, False),
+                                                          (orc.csw, orc.cdw, orc.chr_xinc, True)]):
+        co, po = mine.filter(which)
+        src = rng.integers(0, 256, (3, src_w)).astype(np.int64)
+        want = O.OracleContext._hscale_fast(src, dst_w, xinc, chroma)
+        acc = np.zeros((3, dst_w), np.int64)
+        for j in range(co.shape[1]):
+            acc += src[:, np.minimum(po.astype(np.int64) + j, src_w - 1)] * co[:, j].astype(np.int64)[None, :]
+        assert np.array_equal(np.minimum(acc >> 7, 32767), want), "bank %d" % which
+        assert (po >= 0).all() and (po + co.shape[1] <= src_w).all()
+    if R.available():
+        ref = R.RefContext(sw, sh, sf, dw, dh, df, fl)
+        for which in (2, 3):
+            co, po = mine.filter(which)
+            rc, rp = ref.filter(which)
+            assert np.array_equal(co, rc) and np.array_equal(po, rp), "vertical bank %d vs reference" % which
+
+
+def test_special_converter_selection_mirrors_the_reference():
+    """Which convert_unscaled hook the reference would install (swscale_unscaled.c:2392-2731) decides the kernel:
+    the plan must make the same choice (special id in info()['special'] when exported, else via the error path)."""
+    ok = [("nv12", "yuv420p"), ("yuv420p", "nv21"), ("yuv420p", "yuv420p"), ("yuv420p10le", "yuv420p"),
+          ("yuv420p", "yuv420p16le"), ("yuv420p", "p010le"), ("yuv420p12le", "p010le"), ("nv12", "p010le"),
+          ("rgba", "bgra"), ("bgr24", "yuv420p")]
+    for sf, df in ok:
+        S.SwsContext(128, 64, sf, 128, 64, df, S.SWS_BICUBIC, plan_only=True)
+    with pytest.raises(RuntimeError):                      # DITHER_COPY's tail quirk on p010 sources: not restated
+        S.SwsContext(128, 64, "p010le", 128, 64, "nv12", S.SWS_BICUBIC, plan_only=True)
