@@ -1035,6 +1035,8 @@ struct SwsCudaState {
     /* fast420 path */
     int fast_ok;
     int r420_ok, r420_cr;
+    int fast_narrow;             /* the 128 x 64 tile shape of the fast420 kernel is set up and preferred */
+    int4 *d_fast_rows_narrow;
     int fasthi8_ok;
     int s8_ok, s8_fs4, s8_tile_h, s8_nl_cap, s8_nc_cap, s8_seg_l, s8_seg_c, s8_slot, s8_vl_n4, s8_vc_n4;
     size_t s8_smem;
@@ -1197,44 +1199,39 @@ static int fast420_fmt(int dst_kind)
     }
 }
 
-template <int FMT>
+template <int FMT, bool NARROW>
 static fast420_kernel_t pick_fast420_src(int layout)
 {
-    return layout == SWSC_SRC_PLANAR ? sws_fast420_rgb8_kernel<FMT, F420_PLANAR>
-         : layout == SWSC_SRC_NV12   ? sws_fast420_rgb8_kernel<FMT, F420_NV12>
-                                     : sws_fast420_rgb8_kernel<FMT, F420_NV21>;
+    return layout == SWSC_SRC_PLANAR ? sws_fast420_rgb8_kernel<FMT, F420_PLANAR, NARROW>
+         : layout == SWSC_SRC_NV12   ? sws_fast420_rgb8_kernel<FMT, F420_NV12, NARROW>
+                                     : sws_fast420_rgb8_kernel<FMT, F420_NV21, NARROW>;
 }
 
-static fast420_kernel_t pick_fast420(int fmt, int layout)
+template <bool NARROW>
+static fast420_kernel_t pick_fast420_shape(int fmt, int layout)
 {
     switch (fmt) {
-    case F420_RGB24: return pick_fast420_src<F420_RGB24>(layout);
-    case F420_BGR24: return pick_fast420_src<F420_BGR24>(layout);
-    case F420_RGBA:  return pick_fast420_src<F420_RGBA>(layout);
-    case F420_BGRA:  return pick_fast420_src<F420_BGRA>(layout);
-    case F420_ARGB:  return pick_fast420_src<F420_ARGB>(layout);
-    default:         return pick_fast420_src<F420_ABGR>(layout);
+    case F420_RGB24: return pick_fast420_src<F420_RGB24, NARROW>(layout);
+    case F420_BGR24: return pick_fast420_src<F420_BGR24, NARROW>(layout);
+    case F420_RGBA:  return pick_fast420_src<F420_RGBA, NARROW>(layout);
+    case F420_BGRA:  return pick_fast420_src<F420_BGRA, NARROW>(layout);
+    case F420_ARGB:  return pick_fast420_src<F420_ARGB, NARROW>(layout);
+    default:         return pick_fast420_src<F420_ABGR, NARROW>(layout);
     }
 }
 
-/* decide at init whether the conversion qualifies for the fast420 kernel and build its row table */
-static int fast420_setup(SwsCudaState *st, const SwsFirBank *vc)
+static fast420_kernel_t pick_fast420(int fmt, int layout, bool narrow = false)
 {
-    const SwsCudaPlan *p = &st->plan;
-    st->fast_ok = 0;
-    if (p->src_bits != 8 || p->inter_bits != 15 || p->src_layout > SWSC_SRC_NV21)
-        return 0;
-    if (p->dst_kind < SWSC_DST_RGB24 || p->dst_kind > SWSC_DST_ABGR || p->full_chr)
-        return 0;
-    if (!p->lum_identity || !p->chr_h_identity || p->chr_src_hsub != 1 || p->chr_dst_hsub != 1)
-        return 0;
-    if (vc->size > 4 || p->range_mode || !get_encode_tiled())
-        return 0;
-    if ((p->dst_kind == SWSC_DST_RGB24 || p->dst_kind == SWSC_DST_BGR24) && (p->dst_w & 3))
-        return 0;                     /* the store tensor map counts 32-bit words */
-    if (max_rows_needed(vc->pos, vc->size > 4 ? vc->size : 4, vc->len, F420_TH) > F420_CROWS)
-        return 0;
-    const int padded = ((vc->len + F420_TH - 1) / F420_TH + 1) * F420_TH;
+    return narrow ? pick_fast420_shape<true>(fmt, layout) : pick_fast420_shape<false>(fmt, layout);
+}
+
+/* per-row metadata of the same-size 8-bit kernel for tiles of `th` rows that stage `crows` chroma rows: returns a
+ * device array, or nullptr with *fits = 0 when some tile's chroma window does not fit */
+static int fast420_rows(const SwsCudaPlan *p, const SwsFirBank *vc, int th, int crows, int4 **d_rows, int *fits)
+{
+    *fits = 0;
+    *d_rows = nullptr;
+    const int padded = ((vc->len + th - 1) / th + 1) * th;
     int4 *rows = (int4 *)calloc(padded, sizeof(int4));
     if (!rows)
         return AVERROR(ENOMEM);
@@ -1260,22 +1257,57 @@ static int fast420_setup(SwsCudaState *st, const SwsFirBank *vc)
     /* the kernel's window only slides down: positions must be monotonic, and every tile must
      * fit the staged chroma rows */
     for (int y = 0; y < padded; y++) {
-        const int base = rows[y & ~(F420_TH - 1)].w;
+        const int base = rows[y - y % th].w;
         rows[y].x = rows[y].w - base;
-        if ((y > 0 && rows[y].w < rows[y - 1].w) || rows[y].x < 0 || rows[y].x + 4 > F420_CROWS) {
+        if ((y > 0 && rows[y].w < rows[y - 1].w) || rows[y].x < 0 || rows[y].x + 4 > crows) {
             free(rows);
             return 0;
         }
     }
-    cudaError_t e = cudaMalloc(&st->d_fast_rows, sizeof(int4) * padded);
+    cudaError_t e = cudaMalloc(d_rows, sizeof(int4) * padded);
     if (e == cudaSuccess)
-        e = cudaMemcpy(st->d_fast_rows, rows, sizeof(int4) * padded, cudaMemcpyHostToDevice);
+        e = cudaMemcpy(*d_rows, rows, sizeof(int4) * padded, cudaMemcpyHostToDevice);
     free(rows);
     CUDA_OK(e);
-    {
-        const int fmt = fast420_fmt(p->dst_kind);
-        CUDA_OK(cudaFuncSetAttribute((const void *)pick_fast420(fmt, p->src_layout),
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, F420_SMEM(fmt >= F420_RGBA ? 4 : 3)));
+    *fits = 1;
+    return 0;
+}
+
+static int fast420_setup(SwsCudaState *st, const SwsFirBank *vc)
+{
+    const SwsCudaPlan *p = &st->plan;
+    st->fast_ok = 0;
+    if (p->src_bits != 8 || p->inter_bits != 15 || p->src_layout > SWSC_SRC_NV21)
+        return 0;
+    if (p->dst_kind < SWSC_DST_RGB24 || p->dst_kind > SWSC_DST_ABGR || p->full_chr)
+        return 0;
+    if (!p->lum_identity || !p->chr_h_identity || p->chr_src_hsub != 1 || p->chr_dst_hsub != 1)
+        return 0;
+    if (vc->size > 4 || p->range_mode || !get_encode_tiled())
+        return 0;
+    if ((p->dst_kind == SWSC_DST_RGB24 || p->dst_kind == SWSC_DST_BGR24) && (p->dst_w & 3))
+        return 0;                     /* the store tensor map counts 32-bit words */
+    if (max_rows_needed(vc->pos, vc->size > 4 ? vc->size : 4, vc->len, F420_TH) > F420_CROWS)
+        return 0;
+    int fits = 0, ret;
+    if ((ret = fast420_rows(p, vc, F420_TH, F420_CROWS, &st->d_fast_rows, &fits)) < 0)
+        return ret;
+    if (!fits)
+        return 0;
+    const int fmt = fast420_fmt(p->dst_kind);
+    CUDA_OK(cudaFuncSetAttribute((const void *)pick_fast420(fmt, p->src_layout),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, F420_SMEM(fmt >= F420_RGBA ? 4 : 3)));
+    /* 128 x 64 tiles when they cover the frame width with less waste than 256 x 32 tiles (1920, 640, ...) */
+    st->fast_narrow = 0;
+    if ((p->dst_w + 127) / 128 * 128 < (p->dst_w + 255) / 256 * 256 && !getenv("SWS_B200_NO_NARROW")) {
+        if ((ret = fast420_rows(p, vc, 2 * F420_TH, F420_CROWS_NARROW, &st->d_fast_rows_narrow, &fits)) < 0)
+            return ret;
+        if (fits) {
+            CUDA_OK(cudaFuncSetAttribute((const void *)pick_fast420(fmt, p->src_layout, true),
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         F420_SMEM(fmt >= F420_RGBA ? 4 : 3)));
+            st->fast_narrow = 1;
+        }
     }
     st->fast_ok = 1;
     {
@@ -1310,44 +1342,48 @@ static int fast420_launch(SwsCudaState *st, const uint8_t *const src[4], const i
     if (!aligned16(dst[0]) || (dst_stride[0] & 15) || dst_stride[0] <= 0 ||
         (nb_frames > 1 && (dst_fstride[0] & 15 || dst_fstride[0] <= 0)))
         return 0;
+    /* tile shape: 128 x 64 when that wastes less of the right-most tile column and the row range allows it */
+    const bool narrow = st->fast_narrow && !(y0 % (2 * F420_TH));
+    const int TW = narrow ? F420_TW / 2 : F420_TW, TH = narrow ? 2 * F420_TH : F420_TH;
+    const int CROWS = narrow ? F420_CROWS_NARROW : F420_CROWS;
     CUtensorMap my, mu, mv, mo;
     const uint64_t fs_y = nb_frames > 1 ? src_fstride[0] : (uint64_t)src_stride[0] * p->src_h;
     const uint64_t fs_u = nb_frames > 1 ? src_fstride[1] : (uint64_t)src_stride[1] * p->chr_src_h;
     const uint64_t fs_o = nb_frames > 1 ? dst_fstride[0] : (uint64_t)dst_stride[0] * p->dst_h;
     int ret;
     if ((ret = make_map_3d(&my, CU_TENSOR_MAP_DATA_TYPE_UINT8, src[0], p->src_w, p->src_h, nb_frames,
-                           src_stride[0], fs_y, F420_TW, F420_TH)) < 0)
+                           src_stride[0], fs_y, TW, TH)) < 0)
         return ret;
     if (planar) {
         const uint64_t fs_v = nb_frames > 1 ? src_fstride[2] : (uint64_t)src_stride[2] * p->chr_src_h;
         if ((ret = make_map_3d(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT8, src[1], p->chr_src_w, p->chr_src_h, nb_frames,
-                               src_stride[1], fs_u, F420_TW / 2, F420_CROWS)) < 0 ||
+                               src_stride[1], fs_u, TW / 2, CROWS)) < 0 ||
             (ret = make_map_3d(&mv, CU_TENSOR_MAP_DATA_TYPE_UINT8, src[2], p->chr_src_w, p->chr_src_h, nb_frames,
-                               src_stride[2], fs_v, F420_TW / 2, F420_CROWS)) < 0)
+                               src_stride[2], fs_v, TW / 2, CROWS)) < 0)
             return ret;
     } else {
-        /* interleaved UV plane: 2 bytes per chroma sample, one 256-byte box row per tile row */
+        /* interleaved UV plane: 2 bytes per chroma sample, one TW-byte box row per tile row */
         if ((ret = make_map_3d(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT8, src[1], 2 * (uint64_t)p->chr_src_w,
-                               p->chr_src_h, nb_frames, src_stride[1], fs_u, F420_TW, F420_CROWS)) < 0)
+                               p->chr_src_h, nb_frames, src_stride[1], fs_u, TW, CROWS)) < 0)
             return ret;
         mv = mu;
     }
     if ((ret = make_map_3d(&mo, CU_TENSOR_MAP_DATA_TYPE_UINT32, dst[0], (uint64_t)p->dst_w * bpp / 4, y1,
-                           nb_frames, dst_stride[0], fs_o, F420_TW * bpp / 4, F420_TH / F420_CWARPS)) < 0)
+                           nb_frames, dst_stride[0], fs_o, TW * bpp / 4, TH / F420_CWARPS)) < 0)
         return ret;
     Fast420Args a;
-    a.tiles_x = (p->dst_w + F420_TW - 1) / F420_TW;
-    a.tiles_y = (y1 - y0 + F420_TH - 1) / F420_TH;
-    a.ty_first = y0 / F420_TH;
+    a.tiles_x = (p->dst_w + TW - 1) / TW;
+    a.tiles_y = (y1 - y0 + TH - 1) / TH;
+    a.ty_first = y0 / TH;
     a.frames = nb_frames;
     a.dst_h = p->dst_h;
     a.cy = p->rgb.cy; a.yb = p->rgb.yb;
     a.crv = p->rgb.crv; a.cbu = p->rgb.cbu; a.cgu = p->rgb.cgu; a.cgv = p->rgb.cgv;
     a.kr = p->rgb.base_r << 16; a.kg = p->rgb.base_g << 16; a.kb = p->rgb.base_b << 16;
-    a.rows = st->d_fast_rows;
+    a.rows = narrow ? st->d_fast_rows_narrow : st->d_fast_rows;
     const long long total = (long long)a.tiles_x * a.tiles_y * nb_frames;
     const int grid = (int)(total < (long long)st->num_sms * F420_CTAS_PER_SM ? total : (long long)st->num_sms * F420_CTAS_PER_SM);
-    pick_fast420(fmt, p->src_layout)<<<grid, F420_THREADS, F420_SMEM(bpp), stream>>>(my, mu, mv, mo, a);
+    pick_fast420(fmt, p->src_layout, narrow)<<<grid, F420_THREADS, F420_SMEM(bpp), stream>>>(my, mu, mv, mo, a);
     st->kernel_name = "fast420_rgb8_tma";     /* the name always reports the last kernel launched */
     CUDA_OK(cudaGetLastError());
     st->launches++;
@@ -1983,6 +2019,7 @@ extern "C" void ff_b200_cuda_destroy(SwsCudaState *st)
     }
     cudaFree(st->tables);
     cudaFree(st->d_fast_rows);
+    cudaFree(st->d_fast_rows_narrow);
     cudaFree(st->d_fast16_rows);
     cudaFree(st->s8_tables);
     if (st->s_in) {
@@ -2630,9 +2667,10 @@ static int pipelined_host_frame(SwsCudaState *st, const uint8_t *const src[4], c
         }
     }
     int bands = st->e2e_bands;
-    int band_h = ((p->dst_h + bands - 1) / bands + F420_TH - 1) / F420_TH * F420_TH;
-    if (band_h < F420_TH)
-        band_h = F420_TH;
+    const int band_unit = st->fast_narrow ? 2 * F420_TH : F420_TH;     /* bands start on tile rows of the shape in use */
+    int band_h = ((p->dst_h + bands - 1) / bands + band_unit - 1) / band_unit * band_unit;
+    if (band_h < band_unit)
+        band_h = band_unit;
     int64_t zero[4] = { 0, 0, 0, 0 };
     int cup = 0;                                   /* chroma source rows uploaded so far */
     int k = 0;

@@ -27,6 +27,7 @@
 #define F420_TW 256          /* tile width  (luma pixels)  */
 #define F420_TH 32           /* tile height (luma rows)    */
 #define F420_CROWS 20        /* chroma source rows staged per tile */
+#define F420_CROWS_NARROW 36 /* the same for the 128 x 64 tile shape */
 #define F420_CWARPS 8        /* consumer warps, 4 rows each */
 #define F420_THREADS (32 * (F420_CWARPS + 1))   /* + one producer warp */
 #define F420_Y_BYTES (F420_TW * F420_TH)                                     /*  8192 */
@@ -161,7 +162,10 @@ __device__ __forceinline__ void transpose4(uint32_t r0, uint32_t r1, uint32_t r2
     w[2] = prmt(c, d, 0x5410); w[3] = prmt(c, d, 0x7632);
 }
 
-template <int FMT, int SRC>
+/* NARROW: tile 128 x 64 instead of 256 x 32 (the same bytes per stage): frames whose width is not a multiple of
+ * 256 waste less of their right-most tile column (1920 = 15 x 128, 640 = 5 x 128).  A warp then owns 8 rows,
+ * lanes 0-15 the first four, lanes 16-31 the last four. */
+template <int FMT, int SRC, bool NARROW>
 __global__ void __launch_bounds__(F420_THREADS, F420_CTAS_PER_SM)
 sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
                         const __grid_constant__ CUtensorMap map_u,
@@ -170,7 +174,12 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
                         const __grid_constant__ Fast420Args A)
 {
     constexpr int BPP = FMT >= F420_RGBA ? 4 : 3;
-    /* [stage: Y | U | V (or interleaved UV) | row meta] x STAGES, then [out: 8 warps x 4 rows] */
+    constexpr int TW = NARROW ? F420_TW / 2 : F420_TW, TH = NARROW ? 2 * F420_TH : F420_TH;
+    constexpr int CROWS = NARROW ? F420_CROWS_NARROW : F420_CROWS;
+    constexpr int RPW = TH / F420_CWARPS;                  /* rows per warp: 4 or 8 */
+    constexpr int Y_BYTES = TW * TH, C_BYTES = (TW / 2) * CROWS, META_BYTES = TH * 16;
+    static_assert(Y_BYTES + 2 * C_BYTES + META_BYTES == F420_IN_BYTES, "both tile shapes fill one ring slot");
+    /* [stage: Y | U | V (or interleaved UV) | row meta] x STAGES, then [out: 8 warps x RPW rows] */
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[F420_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[F420_STAGES];
@@ -205,19 +214,19 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
                 const int f = tile / tiles_per_frame;
                 const int t = tile - f * tiles_per_frame;
                 const int ty = t / A.tiles_x, tx = t - ty * A.tiles_x;
-                const int y0 = (A.ty_first + ty) * F420_TH;
+                const int y0 = (A.ty_first + ty) * TH;
                 const int c_lo = __ldg(&A.rows[y0]).w;
                 unsigned char *b = smem_dyn + stage * F420_IN_BYTES;
                 tile_info[stage] = make_int4(tx, y0, f, 0);
                 mbar_expect_tx(&full_bar[stage], F420_IN_BYTES);
-                tma_load_3d(b, &map_y, &full_bar[stage], tx * F420_TW, y0, f);
+                tma_load_3d(b, &map_y, &full_bar[stage], tx * TW, y0, f);
                 if (SRC == F420_PLANAR) {
-                    tma_load_3d(b + F420_Y_BYTES, &map_u, &full_bar[stage], tx * (F420_TW / 2), c_lo, f);
-                    tma_load_3d(b + F420_Y_BYTES + F420_C_BYTES, &map_v, &full_bar[stage], tx * (F420_TW / 2), c_lo, f);
+                    tma_load_3d(b + Y_BYTES, &map_u, &full_bar[stage], tx * (TW / 2), c_lo, f);
+                    tma_load_3d(b + Y_BYTES + C_BYTES, &map_v, &full_bar[stage], tx * (TW / 2), c_lo, f);
                 } else {   /* nv12 / nv21: one box of interleaved UV rows, same bytes */
-                    tma_load_3d(b + F420_Y_BYTES, &map_u, &full_bar[stage], tx * F420_TW, c_lo, f);
+                    tma_load_3d(b + Y_BYTES, &map_u, &full_bar[stage], tx * TW, c_lo, f);
                 }
-                bulk_load_1d(b + F420_Y_BYTES + 2 * F420_C_BYTES, A.rows + y0, F420_META_BYTES, &full_bar[stage]);
+                bulk_load_1d(b + Y_BYTES + 2 * C_BYTES, A.rows + y0, META_BYTES, &full_bar[stage]);
             }
         }
         return;
@@ -229,12 +238,14 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
     const int cy = A.cy, yb = A.yb;
     const int crv = A.crv, cbu = A.cbu, cgu = A.cgu, cgv = A.cgv;
     const int kr = A.kr, kg = A.kg, kb = A.kb;
-    const int r0 = warp * (F420_TH / F420_CWARPS);
-    unsigned char *so_warp = smem_dyn + F420_STAGES * F420_IN_BYTES + r0 * (F420_TW * BPP);
-    unsigned char *so = so_warp + lane * (8 * BPP);
-    /* chroma rows: planar = 128-byte U row + 128-byte V row (one word each per lane);
-     * semi-planar = one 256-byte UV row (two words per lane) */
-    constexpr int CSTRIDE = SRC == F420_PLANAR ? F420_TW / 2 : F420_TW;
+    const int r0 = warp * RPW;
+    const int g = NARROW ? lane & 15 : lane;               /* 8-pixel column group of this lane */
+    const int rb = NARROW ? r0 + 4 * (lane >> 4) : r0;     /* first of this lane's four rows */
+    unsigned char *so_warp = smem_dyn + F420_STAGES * F420_IN_BYTES + r0 * (TW * BPP);
+    unsigned char *so = so_warp + (rb - r0) * (TW * BPP) + g * (8 * BPP);
+    /* chroma rows: planar = TW/2-byte U row + TW/2-byte V row (one word each per lane);
+     * semi-planar = one TW-byte UV row (two words per lane) */
+    constexpr int CSTRIDE = SRC == F420_PLANAR ? TW / 2 : TW;
 
     int i = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
@@ -243,10 +254,10 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
         mbar_wait(&full_bar[stage], (i / F420_STAGES) & 1);
 
         const int4 ti = tile_info[stage];
-        const int4 *mrow = reinterpret_cast<const int4 *>(sb + F420_Y_BYTES + 2 * F420_C_BYTES) + r0;
-        const unsigned char *sy = sb + r0 * F420_TW + lane * 8;
-        const unsigned char *sp = sb + F420_Y_BYTES + (SRC == F420_PLANAR ? lane * 4 : lane * 8);
-        const unsigned char *sq = SRC == F420_PLANAR ? sp + F420_C_BYTES : sp + 4;
+        const int4 *mrow = reinterpret_cast<const int4 *>(sb + Y_BYTES + 2 * C_BYTES) + rb;
+        const unsigned char *sy = sb + rb * TW + g * 8;
+        const unsigned char *sp = sb + Y_BYTES + (SRC == F420_PLANAR ? g * 4 : g * 8);
+        const unsigned char *sq = SRC == F420_PLANAR ? sp + C_BYTES : sp + 4;
 
         /* this warp's previous TMA store must have finished READING its staging rows */
         if (lane == 0)
@@ -257,7 +268,7 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
         uint32_t P[4], Q[4];
         int wpos = -64;                        /* chroma row (tile relative) held in window byte 0 */
 #pragma unroll
-        for (int rr = 0; rr < F420_TH / F420_CWARPS; rr++) {
+        for (int rr = 0; rr < 4; rr++) {
             const int4 meta = mrow[rr];
             const int pos = meta.x;
             int d = pos - wpos;
@@ -282,7 +293,7 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
             }
             wpos = pos;
             const uint32_t clp = (uint32_t)meta.y, chp = (uint32_t)meta.z;
-            const uint2 yw = *reinterpret_cast<const uint2 *>(sy + rr * F420_TW);
+            const uint2 yw = *reinterpret_cast<const uint2 *>(sy + rr * TW);
             uint32_t h[BPP == 3 ? 12 : 16];
 #pragma unroll
             for (int c = 0; c < 4; c++) {
@@ -330,12 +341,12 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
             }
             /* every h[] holds two bytes (at bits 0 and 16): gather four of them per output word */
             if (BPP == 3) {
-                uint2 *o = reinterpret_cast<uint2 *>(so + rr * (F420_TW * 3));
+                uint2 *o = reinterpret_cast<uint2 *>(so + rr * (TW * 3));
                 o[0] = make_uint2(prmt(h[0], h[1], 0x6420), prmt(h[2], h[3], 0x6420));
                 o[1] = make_uint2(prmt(h[4], h[5], 0x6420), prmt(h[6], h[7], 0x6420));
                 o[2] = make_uint2(prmt(h[8], h[9], 0x6420), prmt(h[10], h[11], 0x6420));
             } else {
-                uint4 *o = reinterpret_cast<uint4 *>(so + rr * (F420_TW * 4));
+                uint4 *o = reinterpret_cast<uint4 *>(so + rr * (TW * 4));
                 o[0] = make_uint4(prmt(h[0], h[1], 0x6420), prmt(h[2], h[3], 0x6420),
                                   prmt(h[4], h[5], 0x6420), prmt(h[6], h[7], 0x6420));
                 o[1] = make_uint4(prmt(h[8], h[9], 0x6420), prmt(h[10], h[11], 0x6420),
@@ -349,7 +360,7 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
         __syncwarp();
         if (lane == 0) {
             mbar_arrive(&empty_bar[stage]);
-            tma_store_3d(&map_o, so_warp, ti.x * (F420_TW * BPP / 4), ti.y + r0, ti.z);
+            tma_store_3d(&map_o, so_warp, ti.x * (TW * BPP / 4), ti.y + r0, ti.z);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }

@@ -25,6 +25,7 @@ cap fast16  sws_fast420_rgb16 "C3 4K" 16 $((3840*2160*16))
 cap scale8  sws_scale8 "C4 8K" 16 $((7680*4320*16))
 cap scale8_rgb sws_scale8 "X1 1080p" 16 $((3840*2160*16))
 cap rgb420 sws_rgb420 "E1 4K" 16 $((3840*2160*16))
+cap fast_hi8 sws_fast420_hi8 "C3b 4K" 16 $((3840*2160*16))
 cap tile15_rgbsrc sws_tile15 "E2 4K" 4 $((3840*2160*4))
 cap copy8 sws_copy8 "U1 4K" 16 $((3840*2160*16))
 ls -la $OUT
