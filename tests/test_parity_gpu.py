@@ -176,6 +176,8 @@ def test_full_chroma_rgb(sf, df, geom, flags):
 @pytest.mark.parametrize("sf", ["yuv420p", "nv12", "nv21"])
 @pytest.mark.parametrize("df", ["rgb24", "bgr24", "rgba", "bgra", "argb", "abgr"])
 @pytest.mark.parametrize("geom,flags", [((644, 366), S.SWS_BICUBIC | BX),          # ragged right/bottom tiles
+                                        ((640, 200), S.SWS_BICUBIC | BX),          # 128 x 64 tile shape, ragged bottom
+                                        ((384, 70), S.SWS_BILINEAR | BX),          # 128 x 64 tile shape
                                         ((256, 34), S.SWS_BILINEAR | BX),
                                         ((1280, 720), S.SWS_POINT | BX),
                                         ((648, 360), S.SWS_BICUBIC)])
