@@ -58,6 +58,9 @@ def test_version_and_queries():
     assert L.sws_isSupportedInput(S.PIX_FMT["yuv420p"]) and L.sws_isSupportedOutput(S.PIX_FMT["rgb24"])
     assert L.sws_isSupportedInput(S.PIX_FMT["rgb24"])        # packed 8-bit RGB input
     assert not L.sws_isSupportedInput(S.PIX_FMT["rgb48le"])  # 16-bit RGB is output-only
+    assert L.sws_isSupportedInput(S.PIX_FMT["p010le"]) and L.sws_isSupportedOutput(S.PIX_FMT["p010le"])
+    if R.available():                                        # the ABI value of the id, libavutil/pixfmt.h
+        assert R.pix_fmt("p010le") == S.PIX_FMT["p010le"]
     assert not L.sws_isSupportedOutput(9999)
     co = L.sws_getCoefficients(1)
     assert [co[i] for i in range(4)] == [117489, 138438, 13975, 34925]
