@@ -255,8 +255,9 @@ SwsVector *sws_getGaussianVec(double variance, double quality);
 void sws_scaleVec(SwsVector *a, double scalar);
 void sws_normalizeVec(SwsVector *a, double height);
 void sws_freeVec(SwsVector *a);
-/* SwsFilter builder: reference swscale.h:719-723 / utils.c:2155-2248.  sws_init_context() on this
- * path rejects non-NULL filters with AVERROR(ENOTSUP); the builder itself is complete. */
+/* SwsFilter builder: reference swscale.h:719-723 / utils.c:2155-2248.  sws_init_context() convolves the
+ * source-side vectors into the FIR banks exactly like initFilter (utils.c:385-413; like the reference it only
+ * widens the rows for the destination-side vectors). */
 SwsFilter *sws_getDefaultFilter(float lumaGBlur, float chromaGBlur, float lumaSharpen, float chromaSharpen,
                                 float chromaHShift, float chromaVShift, int verbose);
 void sws_freeFilter(SwsFilter *filter);

@@ -63,6 +63,7 @@ void  sws_cuda_host_free(void *ptr);
  * sws_b200_get_rgb2yuv(): {ry,gy,by,ru,gu,bu,rv,gv,bv}, the C entries of the reference's
  * input_rgb2yuv_table (swscale_internal.h:467-476, utils.c:614-706); RGB sources only. */
 int sws_b200_plan_only(SwsContext *c);
+int sws_b200_plan_only_filtered(SwsContext *c, SwsFilter *srcFilter, SwsFilter *dstFilter);
 int sws_b200_get_filter(SwsContext *c, int which, const int16_t **coef, const int32_t **pos, int *len);
 int sws_b200_get_info(SwsContext *c, int out[32]);
 int sws_b200_get_rgb2yuv(SwsContext *c, int out[9]);

@@ -418,6 +418,15 @@ static int init_single(SwsContext *sws, int with_device)
     }
 
     unscaled = srcW == dstW && srcH == dstH;
+    {
+        /* SwsFilter vectors longer than one tap keep the unscaled special converters away (utils.c:1256-1263,1624) */
+        const SwsFilter *sf = c->src_filter_tmp, *df = c->dst_filter_tmp;
+        const SwsVector *v[8] = { sf ? sf->lumH : NULL, sf ? sf->chrH : NULL, df ? df->lumH : NULL, df ? df->chrH : NULL,
+                                  sf ? sf->lumV : NULL, sf ? sf->chrV : NULL, df ? df->lumV : NULL, df ? df->chrV : NULL };
+        for (int i = 0; i < 8; i++)
+            if (v[i] && v[i]->length > 1)
+                unscaled = 0;
+    }
     lum_xinc = (((int64_t)srcW << 16) + (dstW >> 1)) / dstW;
     lum_yinc = (((int64_t)srcH << 16) + (dstH >> 1)) / dstH;
 
@@ -527,22 +536,34 @@ static int init_single(SwsContext *sws, int with_device)
     spec.one = 1 << 14;
     spec.inc = lum_xinc; spec.src_len = srcW; spec.dst_len = dstW; spec.scaler = lum_scaler;
     spec.src_pos = local_chroma_pos(0, 0); spec.dst_pos = local_chroma_pos(0, 0);
+    spec.src_vec = c->src_filter_tmp && c->src_filter_tmp->lumH ? c->src_filter_tmp->lumH->coeff : NULL;
+    spec.src_vec_len = spec.src_vec ? c->src_filter_tmp->lumH->length : 0;
+    spec.dst_vec_len = c->dst_filter_tmp && c->dst_filter_tmp->lumH ? c->dst_filter_tmp->lumH->length : 0;
     if ((ret = ff_b200_build_fir(&c->h_lum, &spec)) < 0)
         goto fir_fail;
     spec.inc = chr_xinc; spec.src_len = c->chr_src_w; spec.dst_len = c->chr_dst_w; spec.scaler = chr_scaler;
     spec.src_pos = local_chroma_pos(c->chr_src_hsub, sws->src_h_chr_pos);
     spec.dst_pos = local_chroma_pos(c->chr_dst_hsub, sws->dst_h_chr_pos);
+    spec.src_vec = c->src_filter_tmp && c->src_filter_tmp->chrH ? c->src_filter_tmp->chrH->coeff : NULL;
+    spec.src_vec_len = spec.src_vec ? c->src_filter_tmp->chrH->length : 0;
+    spec.dst_vec_len = c->dst_filter_tmp && c->dst_filter_tmp->chrH ? c->dst_filter_tmp->chrH->length : 0;
     if ((ret = ff_b200_build_fir(&c->h_chr, &spec)) < 0)
         goto fir_fail;
 
     spec.one = 1 << 12;
     spec.inc = lum_yinc; spec.src_len = srcH; spec.dst_len = dstH; spec.scaler = lum_scaler;
     spec.src_pos = local_chroma_pos(0, 0); spec.dst_pos = local_chroma_pos(0, 0);
+    spec.src_vec = c->src_filter_tmp && c->src_filter_tmp->lumV ? c->src_filter_tmp->lumV->coeff : NULL;
+    spec.src_vec_len = spec.src_vec ? c->src_filter_tmp->lumV->length : 0;
+    spec.dst_vec_len = c->dst_filter_tmp && c->dst_filter_tmp->lumV ? c->dst_filter_tmp->lumV->length : 0;
     if ((ret = ff_b200_build_fir(&c->v_lum, &spec)) < 0)
         goto fir_fail;
     spec.inc = chr_yinc; spec.src_len = c->chr_src_h; spec.dst_len = c->chr_dst_h; spec.scaler = chr_scaler;
     spec.src_pos = local_chroma_pos(c->chr_src_vsub, sws->src_v_chr_pos);
     spec.dst_pos = local_chroma_pos(c->chr_dst_vsub, sws->dst_v_chr_pos);
+    spec.src_vec = c->src_filter_tmp && c->src_filter_tmp->chrV ? c->src_filter_tmp->chrV->coeff : NULL;
+    spec.src_vec_len = spec.src_vec ? c->src_filter_tmp->chrV->length : 0;
+    spec.dst_vec_len = c->dst_filter_tmp && c->dst_filter_tmp->chrV ? c->dst_filter_tmp->chrV->length : 0;
     if ((ret = ff_b200_build_fir(&c->v_chr, &spec)) < 0)
         goto fir_fail;
 
@@ -668,14 +689,13 @@ int sws_init_context(SwsContext *sws, SwsFilter *srcFilter, SwsFilter *dstFilter
     int ret;
     if (!c)
         return AVERROR(EINVAL);
-    if (srcFilter || dstFilter) {
-        set_error(c, "SwsFilter pre/post filters are outside the CUDA hot path");
-        return AVERROR(ENOTSUP);
-    }
     release_tables(c);
     sws->src_range |= fold_jpeg_format(&sws->src_format);
     sws->dst_range |= fold_jpeg_format(&sws->dst_format);
+    c->src_filter_tmp = srcFilter;          /* caller-owned, only read while the banks are built */
+    c->dst_filter_tmp = dstFilter;
     ret = init_single(sws, 1);
+    c->src_filter_tmp = c->dst_filter_tmp = NULL;
     if (ret < 0)
         release_tables(c);
     return ret;
@@ -684,7 +704,7 @@ int sws_init_context(SwsContext *sws, SwsFilter *srcFilter, SwsFilter *dstFilter
 /* ------------------------------------------------------------ diagnostics
  * Host-side planning without touching a device, so the table builders can be
  * pinned against the reference on machines that have no GPU. */
-int sws_b200_plan_only(SwsContext *sws)
+int sws_b200_plan_only_filtered(SwsContext *sws, SwsFilter *srcFilter, SwsFilter *dstFilter)
 {
     SwsInternal *c = sws_internal(sws);
     int ret;
@@ -693,10 +713,18 @@ int sws_b200_plan_only(SwsContext *sws)
     release_tables(c);
     sws->src_range |= fold_jpeg_format(&sws->src_format);
     sws->dst_range |= fold_jpeg_format(&sws->dst_format);
+    c->src_filter_tmp = srcFilter;
+    c->dst_filter_tmp = dstFilter;
     ret = init_single(sws, 0);
+    c->src_filter_tmp = c->dst_filter_tmp = NULL;
     if (ret < 0)
         release_tables(c);
     return ret;
+}
+
+int sws_b200_plan_only(SwsContext *sws)
+{
+    return sws_b200_plan_only_filtered(sws, NULL, NULL);
 }
 
 int sws_b200_get_filter(SwsContext *sws, int which, const int16_t **coef, const int32_t **pos, int *len)

@@ -218,6 +218,41 @@ static int generate(Taps *t, const SwsFirSpec *s, int64_t fone)
     return 0;
 }
 
+/* Stage 1b: convolve every row with the source-side SwsFilter vector and widen it for the destination-side one
+ * (utils.c:385-413).  The reference accumulates `double coeff * int64 weight` into int64 cells, i.e. it
+ * truncates toward zero after every single addition; the same is done here. */
+static int apply_vectors(Taps *t, const SwsFirSpec *s)
+{
+    const int width = t->width;
+    int width2 = width;
+    if (s->src_vec && s->src_vec_len > 0)
+        width2 += s->src_vec_len - 1;
+    if (s->dst_vec_len > 0)
+        width2 += s->dst_vec_len - 1;
+    if (width2 == width && !(s->src_vec && s->src_vec_len > 0))
+        return 0;
+    int64_t *w2 = calloc((size_t)t->n * width2, sizeof(*w2));
+    if (!w2)
+        return AVERROR(ENOMEM);
+    for (int i = 0; i < t->n; i++) {
+        const int64_t *row = t->w + (size_t)i * width;
+        int64_t *out = w2 + (size_t)i * width2;
+        if (s->src_vec && s->src_vec_len > 0) {
+            for (int k = 0; k < s->src_vec_len; k++)
+                for (int j = 0; j < width; j++)
+                    out[k + j] = (int64_t)((double)out[k + j] + s->src_vec[k] * (double)row[j]);
+        } else {
+            for (int j = 0; j < width; j++)
+                out[j] = row[j];
+        }
+        t->pos[i] += (width - 1) / 2 - (width2 - 1) / 2;
+    }
+    free(t->w);
+    t->w = w2;
+    t->width = width2;
+    return 0;
+}
+
 /* Stage 2: shift away near-zero leading taps, measure the widest useful row
  * (utils.c:417-457).  Returns the minimal tap count. */
 static int trim(Taps *t, int64_t fone)
@@ -342,6 +377,10 @@ int ff_b200_build_fir(SwsFirBank *out, const SwsFirSpec *s)
         ratio_log = 0;
 
     ret = generate(&t, s, fone);
+    if (ret < 0)
+        goto done;
+
+    ret = apply_vectors(&t, s);
     if (ret < 0)
         goto done;
 

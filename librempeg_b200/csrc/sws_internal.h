@@ -58,6 +58,10 @@ typedef struct SwsFirSpec {
     unsigned flags;        /* full flag word (BITEXACT / ACCURATE_RND matter)    */
     double param[2];
     int src_pos, dst_pos;  /* chroma siting, 1/256 sample units, already local   */
+    /* SwsFilter vectors convolved into every row (utils.c:385-413); NULL = none.  Only the length of the
+     * destination-side vector matters: the reference widens the rows for it but never applies it */
+    const double *src_vec; int src_vec_len;
+    int dst_vec_len;
 } SwsFirSpec;
 
 #define SWS_B200_USE_CASCADE (-12345)
@@ -193,6 +197,7 @@ typedef struct SwsInternal {
     int special;                     /* SWSC_SPECIAL_*: rows map 1:1 like the unscaled LUT converter */
     int dst_slice_align;
     SwsFirBank h_lum, h_chr, v_lum, v_chr;
+    const SwsFilter *src_filter_tmp, *dst_filter_tmp;   /* caller-owned, only read during init (swscale.h:699-723) */
     SwsCudaPlan plan;
     SwsCudaState *cuda;
     /* slice state of the legacy API (reference swscale.c:296-298,562-564) */

@@ -8,15 +8,15 @@
 #include "sws_internal.h"
 
 #define YUVP(id, nm, d, cw, ch, bpp) \
-    { id, nm, SWSPF_PLANAR, d, cw, ch, bpp, 3, 0, 1, 1 }
+    { id, nm, SWSPF_PLANAR, d, cw, ch, bpp, 3, 0, 1, 1, 0 }
 
 static const SwsPixDesc table[] = {
     YUVP(AV_PIX_FMT_YUV420P,     "yuv420p",     8, 1, 1, 12),
     YUVP(AV_PIX_FMT_YUV422P,     "yuv422p",     8, 1, 0, 16),
     YUVP(AV_PIX_FMT_YUV444P,     "yuv444p",     8, 0, 0, 24),
-    { AV_PIX_FMT_YUVJ420P, "yuvj420p", SWSPF_PLANAR | SWSPF_JPEG, 8, 1, 1, 12, 3, 0, 1, 1 },
-    { AV_PIX_FMT_YUVJ422P, "yuvj422p", SWSPF_PLANAR | SWSPF_JPEG, 8, 1, 0, 16, 3, 0, 1, 1 },
-    { AV_PIX_FMT_YUVJ444P, "yuvj444p", SWSPF_PLANAR | SWSPF_JPEG, 8, 0, 0, 24, 3, 0, 1, 1 },
+    { AV_PIX_FMT_YUVJ420P, "yuvj420p", SWSPF_PLANAR | SWSPF_JPEG, 8, 1, 1, 12, 3, 0, 1, 1, 0 },
+    { AV_PIX_FMT_YUVJ422P, "yuvj422p", SWSPF_PLANAR | SWSPF_JPEG, 8, 1, 0, 16, 3, 0, 1, 1, 0 },
+    { AV_PIX_FMT_YUVJ444P, "yuvj444p", SWSPF_PLANAR | SWSPF_JPEG, 8, 0, 0, 24, 3, 0, 1, 1, 0 },
     YUVP(AV_PIX_FMT_YUV420P9LE,  "yuv420p9le",  9, 1, 1, 13),
     YUVP(AV_PIX_FMT_YUV422P9LE,  "yuv422p9le",  9, 1, 0, 18),
     YUVP(AV_PIX_FMT_YUV444P9LE,  "yuv444p9le",  9, 0, 0, 27),
@@ -32,17 +32,17 @@ static const SwsPixDesc table[] = {
     YUVP(AV_PIX_FMT_YUV420P16LE, "yuv420p16le", 16, 1, 1, 24),
     YUVP(AV_PIX_FMT_YUV422P16LE, "yuv422p16le", 16, 1, 0, 32),
     YUVP(AV_PIX_FMT_YUV444P16LE, "yuv444p16le", 16, 0, 0, 48),
-    { AV_PIX_FMT_NV12, "nv12", SWSPF_SEMI, 8, 1, 1, 12, 2, 0, 1, 1 },
-    { AV_PIX_FMT_NV21, "nv21", SWSPF_SEMI, 8, 1, 1, 12, 2, 1, 1, 1 },
+    { AV_PIX_FMT_NV12, "nv12", SWSPF_SEMI, 8, 1, 1, 12, 2, 0, 1, 1, 0 },
+    { AV_PIX_FMT_NV21, "nv21", SWSPF_SEMI, 8, 1, 1, 12, 2, 1, 1, 1, 0 },
     { AV_PIX_FMT_P010LE, "p010le", SWSPF_SEMI, 10, 1, 1, 15, 2, 0, 1, 1, 6 },
-    { AV_PIX_FMT_RGB24,   "rgb24",   SWSPF_RGB, 8, 0, 0, 24, 1, 0, 1, 1 },
-    { AV_PIX_FMT_BGR24,   "bgr24",   SWSPF_RGB, 8, 0, 0, 24, 1, 0, 1, 1 },
-    { AV_PIX_FMT_RGBA,    "rgba",    SWSPF_RGB, 8, 0, 0, 32, 1, 0, 1, 1 },
-    { AV_PIX_FMT_BGRA,    "bgra",    SWSPF_RGB, 8, 0, 0, 32, 1, 0, 1, 1 },
-    { AV_PIX_FMT_ARGB,    "argb",    SWSPF_RGB, 8, 0, 0, 32, 1, 0, 1, 1 },
-    { AV_PIX_FMT_ABGR,    "abgr",    SWSPF_RGB, 8, 0, 0, 32, 1, 0, 1, 1 },
-    { AV_PIX_FMT_RGB48LE, "rgb48le", SWSPF_RGB, 16, 0, 0, 48, 1, 0, 0, 1 },
-    { AV_PIX_FMT_BGR48LE, "bgr48le", SWSPF_RGB, 16, 0, 0, 48, 1, 0, 0, 1 },
+    { AV_PIX_FMT_RGB24,   "rgb24",   SWSPF_RGB, 8, 0, 0, 24, 1, 0, 1, 1, 0 },
+    { AV_PIX_FMT_BGR24,   "bgr24",   SWSPF_RGB, 8, 0, 0, 24, 1, 0, 1, 1, 0 },
+    { AV_PIX_FMT_RGBA,    "rgba",    SWSPF_RGB, 8, 0, 0, 32, 1, 0, 1, 1, 0 },
+    { AV_PIX_FMT_BGRA,    "bgra",    SWSPF_RGB, 8, 0, 0, 32, 1, 0, 1, 1, 0 },
+    { AV_PIX_FMT_ARGB,    "argb",    SWSPF_RGB, 8, 0, 0, 32, 1, 0, 1, 1, 0 },
+    { AV_PIX_FMT_ABGR,    "abgr",    SWSPF_RGB, 8, 0, 0, 32, 1, 0, 1, 1, 0 },
+    { AV_PIX_FMT_RGB48LE, "rgb48le", SWSPF_RGB, 16, 0, 0, 48, 1, 0, 0, 1, 0 },
+    { AV_PIX_FMT_BGR48LE, "bgr48le", SWSPF_RGB, 16, 0, 0, 48, 1, 0, 0, 1, 0 },
 };
 
 const SwsPixDesc *ff_b200_pix_desc(int fmt)

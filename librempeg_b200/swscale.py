@@ -62,6 +62,15 @@ class SwsContextStruct(C.Structure):
 _lib = None
 
 
+class SwsVectorStruct(C.Structure):
+    _fields_ = [("coeff", C.POINTER(C.c_double)), ("length", C.c_int)]
+
+
+class SwsFilterStruct(C.Structure):
+    _fields_ = [("lumH", C.POINTER(SwsVectorStruct)), ("lumV", C.POINTER(SwsVectorStruct)),
+                ("chrH", C.POINTER(SwsVectorStruct)), ("chrV", C.POINTER(SwsVectorStruct))]
+
+
 def lib():
     global _lib
     if _lib is not None:
@@ -105,6 +114,8 @@ def lib():
     L.sws_cuda_host_free.argtypes = [C.c_void_p]
     L.sws_b200_plan_only.restype = C.c_int
     L.sws_b200_plan_only.argtypes = [ctxp]
+    L.sws_b200_plan_only_filtered.restype = C.c_int
+    L.sws_b200_plan_only_filtered.argtypes = [ctxp, C.c_void_p, C.c_void_p]
     L.sws_b200_get_filter.restype = C.c_int
     L.sws_b200_get_filter.argtypes = [ctxp, C.c_int, P(P(C.c_int16)), P(P(C.c_int32)), P(C.c_int)]
     L.sws_b200_get_rgb2yuv.restype = C.c_int
@@ -140,7 +151,7 @@ class SwsContext:
 
     def __init__(self, src_w, src_h, src_fmt, dst_w, dst_h, dst_fmt, flags, param=None,
                  src_range=0, dst_range=0, chr_pos=None, dither=None, plan_only=False,
-                 scaler=None, scaler_sub=None):
+                 scaler=None, scaler_sub=None, src_filter=None, dst_filter=None):
         L = lib()
         self._L = L
         self.p = L.sws_alloc_context()
@@ -161,7 +172,24 @@ class SwsContext:
             s.scaler = scaler
         if scaler_sub is not None:
             s.scaler_sub = scaler_sub
-        ret = L.sws_b200_plan_only(self.p) if plan_only else L.sws_init_context(self.p, None, None)
+        fptr = [None, None]
+        self._filter_keep = []
+        for fi, f in enumerate((src_filter, dst_filter)):
+            if f:           # SwsFilter from a dict of vectors {"lumH": [...], "lumV": ..., "chrH": ..., "chrV": ...}
+                flt = SwsFilterStruct()
+                for k in ("lumH", "lumV", "chrH", "chrV"):
+                    v = f.get(k)
+                    if v is not None:
+                        arr = (C.c_double * len(v))(*v)
+                        vec = SwsVectorStruct(C.cast(arr, C.POINTER(C.c_double)), len(v))
+                        self._filter_keep += [arr, vec]
+                        setattr(flt, k, C.pointer(vec))
+                self._filter_keep.append(flt)
+                fptr[fi] = C.byref(flt)
+        if plan_only and (src_filter or dst_filter):
+            ret = L.sws_b200_plan_only_filtered(self.p, fptr[0], fptr[1])
+        else:
+            ret = L.sws_b200_plan_only(self.p) if plan_only else L.sws_init_context(self.p, fptr[0], fptr[1])
         if ret < 0:
             msg = L.sws_cuda_last_error(self.p).decode()
             L.sws_freeContext(self.p)

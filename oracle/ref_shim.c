@@ -67,6 +67,52 @@ API void *swsref_create(int sw, int sh, int sfmt, int dw, int dh, int dfmt,
     return s;
 }
 
+/* the same with SwsFilter vectors: vec[0..3] = srcFilter lumH, lumV, chrH, chrV; vec[4..7] = dstFilter (NULL = none) */
+API void *swsref_create_filtered(int sw, int sh, int sfmt, int dw, int dh, int dfmt,
+                                 unsigned flags, const double *param, const int *opts,
+                                 const double *const vec[8], const int len[8])
+{
+    SwsVector v[8];
+    SwsFilter f[2];
+    SwsVector **slot[8] = { &f[0].lumH, &f[0].lumV, &f[0].chrH, &f[0].chrV, &f[1].lumH, &f[1].lumV, &f[1].chrH, &f[1].chrV };
+    int used[2] = { 0, 0 };
+    SwsContext *s = sws_alloc_context();
+    if (!s)
+        return NULL;
+    for (int i = 0; i < 8; i++) {
+        *slot[i] = NULL;
+        if (vec[i] && len[i] > 0) {
+            v[i].coeff = (double *)vec[i];
+            v[i].length = len[i];
+            *slot[i] = &v[i];
+            used[i / 4] = 1;
+        }
+    }
+    s->flags = flags;
+    s->src_w = sw; s->src_h = sh; s->src_format = sfmt;
+    s->dst_w = dw; s->dst_h = dh; s->dst_format = dfmt;
+    if (param) {
+        s->scaler_params[0] = param[0];
+        s->scaler_params[1] = param[1];
+    }
+    s->threads = 1;
+    if (opts) {
+        s->threads       = opts[0];
+        s->src_range     = opts[1];
+        s->dst_range     = opts[2];
+        s->src_h_chr_pos = opts[3];
+        s->src_v_chr_pos = opts[4];
+        s->dst_h_chr_pos = opts[5];
+        s->dst_v_chr_pos = opts[6];
+        s->dither        = opts[7];
+    }
+    if (sws_init_context(s, used[0] ? &f[0] : NULL, used[1] ? &f[1] : NULL) < 0) {
+        sws_freeContext(s);
+        return NULL;
+    }
+    return s;
+}
+
 API void swsref_free(void *ctx) { sws_freeContext(ctx); }
 
 API int swsref_set_colorspace(void *ctx, int src_cs, int src_range, int dst_cs,

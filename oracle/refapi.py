@@ -103,7 +103,8 @@ class RefContext:
     """A reference SwsContext (legacy API, sws_init_context'd)."""
 
     def __init__(self, sw, sh, sfmt, dw, dh, dfmt, flags, param=None, threads=1,
-                 src_range=0, dst_range=0, chr_pos=(-513, -513, -513, -513), dither=1):
+                 src_range=0, dst_range=0, chr_pos=(-513, -513, -513, -513), dither=1,
+                 src_filter=None, dst_filter=None):
         self.sw, self.sh, self.dw, self.dh = sw, sh, dw, dh
         self.sfmt = pix_fmt(sfmt) if isinstance(sfmt, str) else sfmt
         self.dfmt = pix_fmt(dfmt) if isinstance(dfmt, str) else dfmt
@@ -111,7 +112,23 @@ class RefContext:
         if param is not None:
             p = (C.c_double * 2)(*param)
         opts = (C.c_int * 8)(threads, src_range, dst_range, chr_pos[0], chr_pos[1], chr_pos[2], chr_pos[3], dither)
-        self.h = lib().swsref_create(sw, sh, self.sfmt, dw, dh, self.dfmt, flags, p, opts)
+        if src_filter or dst_filter:
+            # SwsFilter vectors: dicts {"lumH": [...], "lumV": ..., "chrH": ..., "chrV": ...}
+            L = lib()
+            L.swsref_create_filtered.restype = C.c_void_p
+            keep, ptrs, lens = [], (C.POINTER(C.c_double) * 8)(), (C.c_int * 8)()
+            for fi, f in enumerate((src_filter or {}, dst_filter or {})):
+                for ki, k in enumerate(("lumH", "lumV", "chrH", "chrV")):
+                    v = f.get(k)
+                    if v is not None:
+                        arr = (C.c_double * len(v))(*v)
+                        keep.append(arr)
+                        ptrs[4 * fi + ki] = C.cast(arr, C.POINTER(C.c_double))
+                        lens[4 * fi + ki] = len(v)
+            L.swsref_create_filtered.argtypes = [C.c_int] * 6 + [C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            self.h = L.swsref_create_filtered(sw, sh, self.sfmt, dw, dh, self.dfmt, flags, p, opts, ptrs, lens)
+        else:
+            self.h = lib().swsref_create(sw, sh, self.sfmt, dw, dh, self.dfmt, flags, p, opts)
         if not self.h:
             raise RuntimeError("reference sws_init_context failed")
 

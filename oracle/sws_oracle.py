@@ -107,8 +107,9 @@ def _spline(a, b, c, d, dist):
     return _spline(0.0, b + 2.0 * c + 3.0 * d, c + 3.0 * d, -b - 3.0 * c - 6.0 * d, dist - 1.0)
 
 
-def init_filter(x_inc, src_w, dst_w, one, scaler, flags, param, src_pos, dst_pos, filter_align=1):
-    """initFilter, utils.c:197-612 (srcFilter/dstFilter == NULL).  Returns (coef[dst_w][fs], pos[dst_w])
+def init_filter(x_inc, src_w, dst_w, one, scaler, flags, param, src_pos, dst_pos, filter_align=1,
+                src_vec=None, dst_vec=None):
+    """initFilter, utils.c:197-612; src_vec / dst_vec are the SwsFilter vectors of this bank.  Returns (coef[dst_w][fs], pos[dst_w])
     or None when the reference would ask for a cascade (RETCODE_USE_CASCADE)."""
     ratio = src_w // dst_w
     fone = 1 << (54 - min(int(math.log2(ratio | 1)), 8))
@@ -214,6 +215,23 @@ def init_filter(x_inc, src_w, dst_w, one, scaler, flags, param, src_pos, dst_pos
                 xx += 1
             filt.append(row)
             x += 2 * x_inc
+
+    # :385-413 convolve every row with the source-side vector; the destination-side vector only widens the rows
+    # ("FIXME dstFilter").  int64 += double * int64 truncates toward zero after every addition.
+    f2 = fs + (len(src_vec) - 1 if src_vec is not None else 0) + (len(dst_vec) - 1 if dst_vec is not None else 0)
+    if src_vec is not None or dst_vec is not None:
+        new = []
+        for i in range(dst_w):
+            row = [0] * f2
+            if src_vec is not None:
+                for k, ck in enumerate(src_vec):
+                    for j in range(fs):
+                        row[k + j] = int(float(row[k + j]) + float(ck) * float(filt[i][j]))
+            else:
+                row[:fs] = filt[i]
+            new.append(row)
+            pos[i] += (fs - 1) // 2 - (f2 - 1) // 2
+        filt, fs = new, f2
 
     # :417-457 reduce: shift near-zero taps out on the left, count them on the right
     f2 = fs
@@ -397,7 +415,7 @@ class OracleContext:
     swscale.c / output.c restated on numpy arrays."""
 
     def __init__(self, sw, sh, sfmt, dw, dh, dfmt, flags, param=None, src_range=0, dst_range=0,
-                 chr_pos=(-513, -513, -513, -513), dither=1, colorspace=None):
+                 chr_pos=(-513, -513, -513, -513), dither=1, colorspace=None, src_filter=None, dst_filter=None):
         self.sw, self.sh, self.dw, self.dh = sw, sh, dw, dh
         param = list(param) if param is not None else [SWS_PARAM_DEFAULT, SWS_PARAM_DEFAULT]
         if sfmt.startswith("yuvj"):                                   # handle_jpeg, utils.c:773
@@ -425,6 +443,11 @@ class OracleContext:
         lum_scaler = SWS_BICUBIC if scaler == SWS_BICUBLIN else scaler
         chr_scaler = SWS_BILINEAR if scaler == SWS_BICUBLIN else scaler
         unscaled = sw == dw and sh == dh
+        # SwsFilter: dicts of vectors {"lumH": [...], "lumV": ..., "chrH": ..., "chrV": ...}; any vector longer than
+        # one tap rules the unscaled special converters out (utils.c:1256-1263,1624)
+        sfv, dfv = src_filter or {}, dst_filter or {}
+        if any(v is not None and len(v) > 1 for v in list(sfv.values()) + list(dfv.values())):
+            unscaled = False
         if dst_rgb and not (flags & SWS_FULL_CHR_H_INT):              # :1270-1286
             if dw & 1 or (shs == 0 and svs == 0 and dither != 2 and not flags & SWS_FAST_BILINEAR):
                 flags |= SWS_FULL_CHR_H_INT
@@ -494,12 +517,14 @@ class OracleContext:
             return (pos + 128) >> sub
 
         shp, svp, dhp, dvp = chr_pos
-        self.h_lum = init_filter(lum_xinc, sw, dw, 1 << 14, lum_scaler, flags, param, lpos(0, 0), lpos(0, 0))
+        self.h_lum = init_filter(lum_xinc, sw, dw, 1 << 14, lum_scaler, flags, param, lpos(0, 0), lpos(0, 0),
+                                 src_vec=sfv.get("lumH"), dst_vec=dfv.get("lumH"))
         self.h_chr = init_filter(chr_xinc, self.csw, self.cdw, 1 << 14, chr_scaler, flags, param,
-                                 lpos(shs, shp), lpos(dhs, dhp))
-        self.v_lum = init_filter(lum_yinc, sh, dh, 1 << 12, lum_scaler, flags, param, lpos(0, 0), lpos(0, 0))
+                                 lpos(shs, shp), lpos(dhs, dhp), src_vec=sfv.get("chrH"), dst_vec=dfv.get("chrH"))
+        self.v_lum = init_filter(lum_yinc, sh, dh, 1 << 12, lum_scaler, flags, param, lpos(0, 0), lpos(0, 0),
+                                 src_vec=sfv.get("lumV"), dst_vec=dfv.get("lumV"))
         self.v_chr = init_filter(chr_yinc, self.csh, self.cdh, 1 << 12, chr_scaler, flags, param,
-                                 lpos(svs, svp), lpos(dvs, dvp))
+                                 lpos(svs, svp), lpos(dvs, dvp), src_vec=sfv.get("chrV"), dst_vec=dfv.get("chrV"))
         if None in (self.h_lum, self.h_chr, self.v_lum, self.v_chr):
             raise NotImplementedError("cascaded contexts are not restated")
         # SWS_FAST_BILINEAR on 8-bit sources with <= 14-bit destinations: hyscale_fast / hcscale_fast

@@ -334,3 +334,34 @@ def test_special_converter_selection_mirrors_the_reference():
         S.SwsContext(128, 64, sf, 128, 64, df, S.SWS_BICUBIC, plan_only=True)
     with pytest.raises(RuntimeError):                      # DITHER_COPY's tail quirk on p010 sources: not restated
         S.SwsContext(128, 64, "p010le", 128, 64, "nv12", S.SWS_BICUBIC, plan_only=True)
+
+
+GAUSS5 = [0.06136, 0.24477, 0.38774, 0.24477, 0.06136]
+SHARP3 = [-0.25, 1.5, -0.25]
+
+
+@pytest.mark.parametrize("src_filter,dst_filter", [
+    (dict(lumH=GAUSS5, lumV=GAUSS5), None),
+    (dict(lumH=SHARP3, lumV=SHARP3, chrH=GAUSS5, chrV=GAUSS5), None),
+    (None, dict(lumH=GAUSS5, chrV=SHARP3)),
+    (dict(chrH=[0.5, 0.5]), dict(lumV=[1.0])),
+])
+@pytest.mark.parametrize("g", [(352, 288, "yuv420p", 352, 288, "rgb24", S.SWS_BICUBIC | S.BX),
+                               (352, 288, "yuv420p", 200, 100, "yuv420p", S.SWS_BICUBIC | S.BX),
+                               (176, 144, "yuv420p", 352, 288, "yuv420p", S.SWS_BILINEAR)],
+                         ids=lambda g: "%dx%d_%s_%dx%d_%s_%x" % g)
+def test_swsfilter_vectors_are_convolved_like_initfilter(g, src_filter, dst_filter):
+    """SwsFilter pre/post vectors (swscale.h:699-723): the source-side vector of every bank is convolved into
+    the rows with the reference's int64 += double * int64 truncation, the destination-side vector only widens
+    them (utils.c:385-413); vectors longer than one tap disable the unscaled special converters (:1256,1624)."""
+    sw, sh, sf, dw, dh, df, fl = g
+    mine = S.SwsContext(sw, sh, sf, dw, dh, df, fl, plan_only=True, src_filter=src_filter, dst_filter=dst_filter)
+    orc = O.OracleContext(sw, sh, sf, dw, dh, df, fl, src_filter=src_filter, dst_filter=dst_filter)
+    ref = R.RefContext(sw, sh, sf, dw, dh, df, fl, src_filter=src_filter, dst_filter=dst_filter) if R.available() else None
+    assert not orc.unscaled_lut and not orc.special
+    for which, bank in enumerate((orc.h_lum, orc.h_chr, orc.v_lum, orc.v_chr)):
+        co, po = mine.filter(which)
+        assert np.array_equal(co, bank[0]) and np.array_equal(po, bank[1]), "bank %d vs numpy oracle" % which
+        if ref:
+            rc, rp = ref.filter(which)
+            assert np.array_equal(co, rc) and np.array_equal(po, rp), "bank %d vs reference" % which

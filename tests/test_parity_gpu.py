@@ -432,3 +432,19 @@ def test_fast420_hi8_colorspace_and_slices():
            colorspace=colorspace)
     slices = [(y, min(64, 360 - y)) for y in range(0, 360, 64)]
     _check(sw=640, sh=360, sf="yuv420p10le", dw=640, dh=360, df="rgb24", flags=S.SWS_BICUBIC | BX, seed=113, slices=slices)
+
+
+# ---- SwsFilter pre-filters (vf_smartblur-style): blur / sharpen vectors convolved into the banks ----
+_GAUSS5 = [0.06136, 0.24477, 0.38774, 0.24477, 0.06136]
+_SHARP3 = [-0.25, 1.5, -0.25]
+
+
+@pytest.mark.parametrize("filt", [dict(lumH=_GAUSS5, lumV=_GAUSS5), dict(lumH=_SHARP3, lumV=_SHARP3, chrH=_GAUSS5, chrV=_GAUSS5)])
+@pytest.mark.parametrize("case", [dict(sw=640, sh=360, sf="yuv420p", dw=640, dh=360, df="yuv420p"),
+                                  dict(sw=640, sh=360, sf="yuv420p", dw=640, dh=360, df="rgb24"),
+                                  dict(sw=640, sh=360, sf="nv12", dw=400, dh=300, df="bgra"),
+                                  dict(sw=322, sh=242, sf="yuv420p10le", dw=322, dh=242, df="yuv420p10le"),
+                                  dict(sw=322, sh=242, sf="rgb24", dw=322, dh=242, df="yuv420p")])
+def test_swsfilter_prefilter(case, filt):
+    _check(flags=S.SWS_BICUBIC | BX, seed=115, ctx_kwargs=dict(src_filter=filt), **case)
+    _check(flags=S.SWS_BILINEAR, seed=116, ctx_kwargs=dict(src_filter=filt, dst_filter=dict(lumH=_GAUSS5)), **case)
