@@ -27,6 +27,12 @@
 #define S8_STAGES 2      /* ring depth */
 #endif
 #define S8_THREADS 288   /* 8 filtering warps + 1 TMA producer warp */
+#ifndef S8_LIGHT_FS4
+#define S8_LIGHT_FS4 2    /* planar variants with at most this many tap groups are also compiled for S8_RGB_CTAS CTAs per SM */
+#endif
+#ifndef S8_RGB_CTAS
+#define S8_RGB_CTAS 4     /* CTAs per SM the packed-RGB variant is compiled for (register budget of its V + colour stage) */
+#endif
 #define S8_VF4 5         /* vertical taps: up to 5 groups of 4 (16 taps + parity pad) */
 
 struct S8VRow {          /* per destination row, 48 bytes */
@@ -225,7 +231,7 @@ __device__ __forceinline__ void s8_hfir_uv(const unsigned char *srow, int sh, co
  *  V:       warp = output row, lane = columns lane + 32k.
  */
 template <int FS4, bool RGB>
-__global__ void __launch_bounds__(S8_THREADS, 3)
+__global__ void __launch_bounds__(S8_THREADS, (RGB || FS4 <= S8_LIGHT_FS4) ? S8_RGB_CTAS : 3)
 sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_u,
                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ Scale8Args A)
 {
