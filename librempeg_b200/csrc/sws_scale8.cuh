@@ -454,9 +454,11 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             }
             const int bias = (vl.pos_even & 1) ? 0 : 1 << 18;
             int Y[4], U[2], V[2];
-            s8_vsum<4>(hb_l + lane * lstride_w + (((vl.pos_even & ~1) - lo_l) >> 1), 32 * lstride_w, vl, A.vl_n4, bias, Y);
-            s8_vsum<2>(hb_u + lane * cstride_w + ((vc.pos_even - lo_c) >> 1), 32 * cstride_w, vc, A.vc_n4, bias, U);
-            s8_vsum<2>(hb_v + lane * cstride_w + ((vc.pos_even - lo_c) >> 1), 32 * cstride_w, vc, A.vc_n4, bias, V);
+            /* this row's own tap-group counts (a leading zero tap pads odd first rows), made warp-uniform */
+            const int ln4 = __shfl_sync(0xffffffffu, vl.n4, 0), cn4 = __shfl_sync(0xffffffffu, vc.n4, 0);
+            s8_vsum<4>(hb_l + lane * lstride_w + (((vl.pos_even & ~1) - lo_l) >> 1), 32 * lstride_w, vl, ln4, bias, Y);
+            s8_vsum<2>(hb_u + lane * cstride_w + ((vc.pos_even - lo_c) >> 1), 32 * cstride_w, vc, cn4, bias, U);
+            s8_vsum<2>(hb_v + lane * cstride_w + ((vc.pos_even - lo_c) >> 1), 32 * cstride_w, vc, cn4, bias, V);
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < 2; k++) {
@@ -516,7 +518,6 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
 
     /* ================= stage V, luma: warp = row, lane = columns lane, lane+32, ... ================= */
     {
-        const int n4 = A.vl_n4;
         S8VRow vr;
         if (warp < th)
             vr = s8_load_vrow(A.vl + ry0 + warp);
@@ -525,6 +526,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             S8VRow nx;
             if (ty + 8 < th)
                 nx = s8_load_vrow(A.vl + y + 8);        /* next row's taps are in flight while this row is filtered */
+            const int n4 = __shfl_sync(0xffffffffu, vr.n4, 0);     /* this row's own group count, warp-uniform */
             const uint32_t *hp = hb_l + lane * lstride_w + ((vr.pos_even - lo_l) >> 1);
             uint8_t *d = dst0 + (size_t)y * A.dst_stride[0] + x0 + lane;
             int v[S8_TW / 32];
@@ -538,7 +540,6 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     }
     /* ================= stage V, chroma: task = (plane, row) ================= */
     if (ch > 0) {
-        const int n4 = A.vc_n4;
         const bool semi = A.dst_kind == SWSC_DST_NV12 || A.dst_kind == SWSC_DST_NV21;
         const int first = A.dst_kind == SWSC_DST_NV21 ? 1 : 0;   /* nv12: U first */
         S8VRow vr;
@@ -549,6 +550,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             S8VRow nx;
             if (task + 8 < 2 * ch)
                 nx = s8_load_vrow(A.vc + y + 4);
+            const int n4 = __shfl_sync(0xffffffffu, vr.n4, 0);
             const uint32_t *hp = (pl ? hb_v : hb_u) + lane * cstride_w + ((vr.pos_even - lo_c) >> 1);
             uint8_t *d = semi ? dst1 + (size_t)y * A.dst_stride[1] + 2 * (cx0 + lane) + (pl ^ first)
                               : (pl ? dst2 : dst1) + (size_t)y * A.dst_stride[pl ? 2 : 1] + cx0 + lane;
