@@ -337,6 +337,106 @@ sws_bgr24_to_yv12_vec_kernel(const __grid_constant__ Bgr24Yv12Args A, int chunks
     __stcs(reinterpret_cast<uint2 *>(A.dst[2] + blockIdx.z * A.dst_fstride[2] + crow * A.dst_stride[2] + (size_t)c * 8), make_uint2(vw[0], vw[1]));
 }
 
+/* 8-bit planar 4:4:4 -> packed 8-bit RGB of the same size (yuv444p / yuvj444p -> rgb24 ... abgr): 4:4:4 sources force
+ * SWS_FULL_CHR_H_INT (utils.c:1278-1285), every filter is the identity and vscale.c:135 hands the rows to
+ * yuv2rgb_full_1_c_template with uvalpha = 0 (output.c:2258-2290) + yuv2rgb_write_full (output.c:1998-2051):
+ *   Y = l15 * 4 = y << 9,  U = (u15 - (128 << 7)) * 4 = (u - 128) << 9,
+ *   Y' = (Y - y_offset) * y_coeff + 2^21,  R = Y' + V * v2r,  G = Y' + V * v2g + U * u2g,  B = Y' + U * u2b
+ * (32-bit unsigned wrap-around), clip to 30 bits, >> 22.  With the constants folded on the host that is one IMAD
+ * per term: R = y * ky + v * kvr + cr, ...  A thread owns 16 pixels (three 16-byte loads, 48 or 64 bytes out). */
+struct Full444Args {
+    const uint8_t *src[3];
+    uint8_t *dst;
+    long long src_fstride[3], dst_fstride;
+    int src_stride[3], dst_stride;
+    int w, y0, rows, chunks;
+    unsigned ky, kvr, kvg, kug, kub, cr, cg, cb;
+    int dst_kind;
+    int vec;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+sws_full444_kernel(const __grid_constant__ Full444Args A)
+{
+    constexpr int BPP = KIND == SWSC_DST_RGB24 || KIND == SWSC_DST_BGR24 ? 3 : 4;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int row = (int)(idx / A.chunks), c = (int)(idx - (long long)row * A.chunks);
+    if (row >= A.rows)
+        return;
+    const int y = A.y0 + row, f = blockIdx.z;
+    const uint8_t *sy = A.src[0] + f * A.src_fstride[0] + (size_t)y * A.src_stride[0] + 16 * c;
+    const uint8_t *su = A.src[1] + f * A.src_fstride[1] + (size_t)y * A.src_stride[1] + 16 * c;
+    const uint8_t *sv = A.src[2] + f * A.src_fstride[2] + (size_t)y * A.src_stride[2] + 16 * c;
+    uint8_t *d = A.dst + f * A.dst_fstride + (size_t)y * A.dst_stride + (size_t)16 * c * BPP;
+    const int n = min(16, A.w - 16 * c);
+    const bool vec = n == 16 && A.vec;
+    uint32_t wy[4], wu[4], wv[4];
+    if (vec) {
+        const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(sy)), b = __ldcs(reinterpret_cast<const uint4 *>(su)),
+                    e = __ldcs(reinterpret_cast<const uint4 *>(sv));
+        wy[0] = a.x; wy[1] = a.y; wy[2] = a.z; wy[3] = a.w;
+        wu[0] = b.x; wu[1] = b.y; wu[2] = b.z; wu[3] = b.w;
+        wv[0] = e.x; wv[1] = e.y; wv[2] = e.z; wv[3] = e.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            wy[i] = wu[i] = wv[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            if (i < n) {
+                wy[i >> 2] |= (uint32_t)sy[i] << (8 * (i & 3));
+                wu[i >> 2] |= (uint32_t)su[i] << (8 * (i & 3));
+                wv[i >> 2] |= (uint32_t)sv[i] << (8 * (i & 3));
+            }
+    }
+    constexpr int kind = KIND;
+    /* byte position of R, G, B inside a pixel and the constant alpha word of the 32-bit layouts */
+    constexpr int pr = kind == SWSC_DST_RGB24 || kind == SWSC_DST_RGBA ? 0 : kind == SWSC_DST_BGR24 || kind == SWSC_DST_BGRA ? 2
+                 : kind == SWSC_DST_ARGB ? 1 : 3;
+    constexpr int pb = kind == SWSC_DST_RGB24 || kind == SWSC_DST_RGBA ? 2 : kind == SWSC_DST_BGR24 || kind == SWSC_DST_BGRA ? 0
+                 : kind == SWSC_DST_ARGB ? 3 : 1;
+    constexpr int pg = kind == SWSC_DST_ARGB || kind == SWSC_DST_ABGR ? 2 : 1;
+    constexpr uint32_t alpha = BPP == 3 ? 0u : (kind == SWSC_DST_ARGB || kind == SWSC_DST_ABGR ? 0x000000FFu : 0xFF000000u);
+    uint32_t out[4 * BPP];
+#pragma unroll
+    for (int g4 = 0; g4 < 4; g4++) {            /* four pixels at a time: three or four output words */
+        uint32_t p4[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const unsigned yv = (wy[g4] >> (8 * j)) & 0xFFu, uv = (wu[g4] >> (8 * j)) & 0xFFu, vv = (wv[g4] >> (8 * j)) & 0xFFu;
+            const unsigned yy = yv * A.ky;
+            const int R = (int)(yy + vv * A.kvr + A.cr);
+            const int G = (int)(yy + vv * A.kvg + uv * A.kug + A.cg);
+            const int B = (int)(yy + uv * A.kub + A.cb);
+            const uint32_t r = (uint32_t)clip_uintp2(R, 30) >> 22, g = (uint32_t)clip_uintp2(G, 30) >> 22,
+                           b = (uint32_t)clip_uintp2(B, 30) >> 22;
+            p4[j] = (r << (8 * pr)) | (g << (8 * pg)) | (b << (8 * pb)) | alpha;
+        }
+        if (BPP == 4) {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                out[4 * g4 + j] = p4[j];
+        } else {                                /* 4 x 3 bytes -> 3 words */
+            out[3 * g4 + 0] = p4[0] | (p4[1] << 24);
+            out[3 * g4 + 1] = (p4[1] >> 8) | (p4[2] << 16);
+            out[3 * g4 + 2] = (p4[2] >> 16) | (p4[3] << 8);
+        }
+    }
+    if (vec) {
+#pragma unroll
+        for (int k = 0; k < BPP; k++)
+            __stcs(reinterpret_cast<uint4 *>(d) + k, make_uint4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]));
+    } else {            /* ragged last chunk / unaligned planes: byte stores, indices known at compile time */
+#pragma unroll
+        for (int k = 0; k < 4 * BPP; k++)
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+                if (4 * k + t < n * BPP)
+                    d[4 * k + t] = (uint8_t)(out[k] >> (8 * t));
+    }
+}
+
 /* 8-bit YUV -> 8-bit YUV of the same geometry with identity filters (planarToNv12Wrapper,
  * nv12ToPlanarWrapper, planar copies: swscale_unscaled.c:147-215): the scaler arithmetic collapses to
  * ((x << 7) * 4096 + (64 << 12)) >> 19 == x, so the conversion is a copy with chroma (de)interleaving.
@@ -2003,6 +2103,7 @@ extern "C" int ff_b200_cuda_create(SwsCudaState **out, SwsCudaPlan *plan,
             if (strstr(d, "copy8"))   st->disabled |= 32;
             if (strstr(d, "rgb420"))  st->disabled |= 64;
             if (strstr(d, "hi8"))     st->disabled |= 128;
+            if (strstr(d, "full444")) st->disabled |= 256;
             if (strstr(d, "tile15"))  st->disabled |= 16;
         }
     }
@@ -2359,6 +2460,46 @@ static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const i
             st->launches++;
             return 1;
         }
+    }
+    /* 8-bit 4:4:4 -> packed RGB of the same size: full-chroma arithmetic path with identity filters */
+    if (!p->special && p->full_chr && p->src_bits == 8 && p->src_layout == SWSC_SRC_PLANAR && p->has_chroma &&
+        p->chr_src_hsub == 0 && p->chr_src_vsub == 0 && p->dst_kind >= SWSC_DST_RGB24 && p->dst_kind <= SWSC_DST_ABGR &&
+        p->lum_identity && p->chr_h_identity && p->chr_v_identity && p->src_w == p->dst_w && p->src_h == p->dst_h &&
+        p->chr_dst_w == p->dst_w && !(st->disabled & 256)) {
+        Full444Args a;
+        memset(&a, 0, sizeof(a));
+        bool vec = aligned16(dst[0]) && !(dst_stride[0] & 15) && !(nb_frames > 1 && (dst_fstride[0] & 15));
+        for (int i = 0; i < 3; i++) {
+            if (!src[i])
+                return AVERROR(EINVAL);
+            a.src[i] = src[i]; a.src_stride[i] = src_stride[i]; a.src_fstride[i] = src_fstride ? src_fstride[i] : 0;
+            vec = vec && aligned16(src[i]) && !(src_stride[i] & 15) && !(a.src_fstride[i] & 15);
+        }
+        a.dst = dst[0]; a.dst_stride = dst_stride[0]; a.dst_fstride = dst_fstride ? dst_fstride[0] : 0;
+        a.w = p->dst_w; a.y0 = y0; a.rows = y1 - y0; a.chunks = (p->dst_w + 15) / 16;
+        a.dst_kind = p->dst_kind; a.vec = vec;
+        /* R = ((y << 9) - y_off) * y_coeff + 2^21 + ((v - 128) << 9) * v2r, all mod 2^32 */
+        const unsigned yc = (unsigned)p->rgb.y_coeff, base = (1u << 21) - (unsigned)p->rgb.y_offset * yc;
+        a.ky = yc << 9;
+        a.kvr = (unsigned)p->rgb.v2r << 9; a.kvg = (unsigned)p->rgb.v2g << 9;
+        a.kug = (unsigned)p->rgb.u2g << 9; a.kub = (unsigned)p->rgb.u2b << 9;
+        a.cr = base - 128u * a.kvr;
+        a.cg = base - 128u * a.kvg - 128u * a.kug;
+        a.cb = base - 128u * a.kub;
+        const long long work = (long long)a.chunks * a.rows;
+        dim3 grid((unsigned)((work + 255) / 256), 1, nb_frames);
+        switch (p->dst_kind) {
+        case SWSC_DST_RGB24: sws_full444_kernel<SWSC_DST_RGB24><<<grid, 256, 0, stream>>>(a); break;
+        case SWSC_DST_BGR24: sws_full444_kernel<SWSC_DST_BGR24><<<grid, 256, 0, stream>>>(a); break;
+        case SWSC_DST_RGBA:  sws_full444_kernel<SWSC_DST_RGBA><<<grid, 256, 0, stream>>>(a); break;
+        case SWSC_DST_BGRA:  sws_full444_kernel<SWSC_DST_BGRA><<<grid, 256, 0, stream>>>(a); break;
+        case SWSC_DST_ARGB:  sws_full444_kernel<SWSC_DST_ARGB><<<grid, 256, 0, stream>>>(a); break;
+        default:             sws_full444_kernel<SWSC_DST_ABGR><<<grid, 256, 0, stream>>>(a); break;
+        }
+        st->kernel_name = "full444";
+        CUDA_OK(cudaGetLastError());
+        st->launches++;
+        return 1;
     }
     if (p->special == SWSC_SPECIAL_P01X) {
         P01xArgs a;

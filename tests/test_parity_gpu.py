@@ -448,3 +448,18 @@ _SHARP3 = [-0.25, 1.5, -0.25]
 def test_swsfilter_prefilter(case, filt):
     _check(flags=S.SWS_BICUBIC | BX, seed=115, ctx_kwargs=dict(src_filter=filt), **case)
     _check(flags=S.SWS_BILINEAR, seed=116, ctx_kwargs=dict(src_filter=filt, dst_filter=dict(lumH=_GAUSS5)), **case)
+
+
+# ---- 8-bit 4:4:4 -> packed RGB of the same size: yuv2rgb_full_1_c + yuv2rgb_write_full with identity filters ----
+@pytest.mark.parametrize("sf", ["yuv444p", "yuvj444p"])
+@pytest.mark.parametrize("df", ["rgb24", "bgr24", "rgba", "bgra", "argb", "abgr"])
+@pytest.mark.parametrize("geom,flags", [((644, 366), S.SWS_BICUBIC | BX), ((35, 19), S.SWS_BILINEAR), ((1280, 720), S.SWS_POINT | BX)])
+def test_full444_kernel(sf, df, geom, flags):
+    w, h = geom
+    for mode in ("noise", "extreme"):
+        name = _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=flags, seed=117, mode=mode)
+        assert name == "full444", name
+    slices = [(y, min(20, h - y)) for y in range(0, h, 20)]
+    _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=flags, seed=118, slices=slices)
+    colorspace = (1, 1, 1, 0, 0, 1 << 16, 1 << 16)
+    _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=flags, seed=119, colorspace=colorspace)
