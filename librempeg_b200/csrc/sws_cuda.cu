@@ -437,6 +437,100 @@ sws_full444_kernel(const __grid_constant__ Full444Args A)
     }
 }
 
+/* packed 8-bit RGB -> 8-bit planar 4:4:4 of the same size (rgb24 ... abgr -> yuv444p): the full-resolution readers
+ * rgb24ToY_c / rgb24ToUV_c and the 32-bit templates (input.c:264-345,1068-1180), identity hScale16To15_c, yuv2plane1_8_c
+ * with the constant dither 64.  As in sws_rgb420.cuh a pixel is one word and a matrix row two IDP.2A; with
+ * S = dot + bias the chain (2 * (S >> 9) + 64) >> 7 folds to (S + 16384) >> 15 (floor of floor), the host admits only
+ * matrices whose 14-bit samples stay below 16384 (no uint16 wrap, no clip at 32767).  16 pixels per thread. */
+struct Rgb444Args {
+    const uint8_t *src;
+    uint8_t *dst[3];
+    long long src_fstride, dst_fstride[3];
+    int src_stride, dst_stride[3];
+    int w, y0, rows, chunks;
+    uint32_t ylo, yhi, ulo, uhi, vlo, vhi;
+    int vec;
+};
+
+template <int BPP>
+__global__ void __launch_bounds__(256)
+sws_rgb444_kernel(const __grid_constant__ Rgb444Args A)
+{
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int row = (int)(idx / A.chunks), c = (int)(idx - (long long)row * A.chunks);
+    if (row >= A.rows)
+        return;
+    const int y = A.y0 + row, f = blockIdx.z;
+    const uint8_t *s = A.src + f * A.src_fstride + (size_t)y * A.src_stride + (size_t)16 * c * BPP;
+    const int n = min(16, A.w - 16 * c);
+    const bool vec = n == 16 && A.vec;
+    uint32_t px[16];
+    if (vec) {
+        constexpr int NW = 4 * BPP;
+        uint32_t w[NW];
+#pragma unroll
+        for (int i = 0; i < BPP; i++) {
+            const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(s) + i);
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+        if (BPP == 4) {
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                px[i] = w[i];
+        } else {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                px[4 * g] = w[3 * g];
+                px[4 * g + 1] = __funnelshift_r(w[3 * g], w[3 * g + 1], 24);
+                px[4 * g + 2] = __funnelshift_r(w[3 * g + 1], w[3 * g + 2], 16);
+                px[4 * g + 3] = w[3 * g + 2] >> 8;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            px[i] = 0;
+            if (i < n) {
+#pragma unroll
+                for (int k = 0; k < BPP; k++)
+                    px[i] |= (uint32_t)s[i * BPP + k] << (8 * k);
+            }
+        }
+    }
+    uint32_t oy[4], ou[4], ov[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        uint32_t yw = 0, uw = 0, vw = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t p = px[4 * g + j];
+            const int sy = dp2a_hi_su(A.yhi, p, dp2a_lo_su(A.ylo, p, (32 << 14) + (1 << 8) + 16384));
+            const int su = dp2a_hi_su(A.uhi, p, dp2a_lo_su(A.ulo, p, (256 << 14) + (1 << 8) + 16384));
+            const int sv = dp2a_hi_su(A.vhi, p, dp2a_lo_su(A.vlo, p, (256 << 14) + (1 << 8) + 16384));
+            yw |= (uint32_t)min(sy >> 15, 255) << (8 * j);
+            uw |= (uint32_t)min(su >> 15, 255) << (8 * j);
+            vw |= (uint32_t)min(sv >> 15, 255) << (8 * j);
+        }
+        oy[g] = yw; ou[g] = uw; ov[g] = vw;
+    }
+    uint8_t *d0 = A.dst[0] + f * A.dst_fstride[0] + (size_t)y * A.dst_stride[0] + 16 * c;
+    uint8_t *d1 = A.dst[1] + f * A.dst_fstride[1] + (size_t)y * A.dst_stride[1] + 16 * c;
+    uint8_t *d2 = A.dst[2] + f * A.dst_fstride[2] + (size_t)y * A.dst_stride[2] + 16 * c;
+    if (vec) {
+        __stcs(reinterpret_cast<uint4 *>(d0), make_uint4(oy[0], oy[1], oy[2], oy[3]));
+        __stcs(reinterpret_cast<uint4 *>(d1), make_uint4(ou[0], ou[1], ou[2], ou[3]));
+        __stcs(reinterpret_cast<uint4 *>(d2), make_uint4(ov[0], ov[1], ov[2], ov[3]));
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            if (i < n) {
+                d0[i] = (uint8_t)(oy[i >> 2] >> (8 * (i & 3)));
+                d1[i] = (uint8_t)(ou[i >> 2] >> (8 * (i & 3)));
+                d2[i] = (uint8_t)(ov[i >> 2] >> (8 * (i & 3)));
+            }
+    }
+}
+
 /* 8-bit YUV -> 8-bit YUV of the same geometry with identity filters (planarToNv12Wrapper,
  * nv12ToPlanarWrapper, planar copies: swscale_unscaled.c:147-215): the scaler arithmetic collapses to
  * ((x << 7) * 4096 + (64 << 12)) >> 19 == x, so the conversion is a copy with chroma (de)interleaving.
@@ -2104,6 +2198,7 @@ extern "C" int ff_b200_cuda_create(SwsCudaState **out, SwsCudaPlan *plan,
             if (strstr(d, "rgb420"))  st->disabled |= 64;
             if (strstr(d, "hi8"))     st->disabled |= 128;
             if (strstr(d, "full444")) st->disabled |= 256;
+            if (strstr(d, "rgb444"))  st->disabled |= 512;
             if (strstr(d, "tile15"))  st->disabled |= 16;
         }
     }
@@ -2410,6 +2505,26 @@ static int rgb420_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     return 1;
 }
 
+/* sws_rgb444_kernel drops the readers' uint16 wrap and the 15-bit clip: admit only matrices whose 14-bit samples stay in
+ * [0, 16384) for every pixel (luma bias (32 << 14) + (1 << 8), chroma bias (256 << 14) + (1 << 8), both >> 9) */
+static bool rgb444_matrix_ok(const SwsCudaPlan *p)
+{
+    for (int i = 0; i < 9; i++)
+        if (p->rgb2yuv[i] < -32768 || p->rgb2yuv[i] > 32767)
+            return false;
+    for (int r = 0; r < 3; r++) {
+        long long lo = 0, hi = 0;
+        for (int k = 0; k < 3; k++) {
+            const long long c = p->rgb2yuv[3 * r + k];
+            (c < 0 ? lo : hi) += c * 255;
+        }
+        const long long bias = r ? (256LL << 14) + (1 << 8) : (32LL << 14) + (1 << 8);
+        if (bias + lo < 0 || ((bias + hi) >> 9) >= 16384)
+            return false;
+    }
+    return true;
+}
+
 /* whole-frame special converters; returns 1 if launched */
 static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const int src_stride[4],
                           const int64_t src_fstride[4], uint8_t *const dst[4], const int dst_stride[4],
@@ -2460,6 +2575,44 @@ static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const i
             st->launches++;
             return 1;
         }
+    }
+    /* packed 8-bit RGB -> 8-bit planar 4:4:4 of the same size: full-resolution readers, identity filters */
+    if (!p->special && p->src_layout == SWSC_SRC_RGB && !p->src_rgb_half && p->dst_kind == SWSC_DST_PLANAR8 &&
+        p->chr_dst_hsub == 0 && p->chr_dst_vsub == 0 && p->has_chroma && !p->range_mode && !p->dither_bayer &&
+        p->inter_bits == 15 && p->h_shift == 13 && p->lum_identity && p->chr_h_identity && p->chr_v_identity &&
+        p->src_w == p->dst_w && p->src_h == p->dst_h && p->chr_src_w == p->dst_w && !(st->disabled & 512) &&
+        rgb444_matrix_ok(p)) {
+        Rgb444Args a;
+        memset(&a, 0, sizeof(a));
+        if (!src[0])
+            return AVERROR(EINVAL);
+        bool vec = aligned16(src[0]) && !(src_stride[0] & 15) && !(nb_frames > 1 && (src_fstride[0] & 15));
+        a.src = src[0]; a.src_stride = src_stride[0]; a.src_fstride = src_fstride ? src_fstride[0] : 0;
+        for (int i = 0; i < 3; i++) {
+            if (!dst[i])
+                return AVERROR(EINVAL);
+            a.dst[i] = dst[i]; a.dst_stride[i] = dst_stride[i]; a.dst_fstride[i] = dst_fstride ? dst_fstride[i] : 0;
+            vec = vec && aligned16(dst[i]) && !(dst_stride[i] & 15) && !(a.dst_fstride[i] & 15);
+        }
+        a.w = p->dst_w; a.y0 = y0; a.rows = y1 - y0; a.chunks = (p->dst_w + 15) / 16; a.vec = vec;
+        int ky[4] = { 0, 0, 0, 0 }, ku[4] = { 0, 0, 0, 0 }, kv[4] = { 0, 0, 0, 0 };
+        ky[p->src_ro] = p->rgb2yuv[0]; ky[p->src_go] = p->rgb2yuv[1]; ky[p->src_bo] = p->rgb2yuv[2];
+        ku[p->src_ro] = p->rgb2yuv[3]; ku[p->src_go] = p->rgb2yuv[4]; ku[p->src_bo] = p->rgb2yuv[5];
+        kv[p->src_ro] = p->rgb2yuv[6]; kv[p->src_go] = p->rgb2yuv[7]; kv[p->src_bo] = p->rgb2yuv[8];
+        auto pair = [](int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); };
+        a.ylo = pair(ky[0], ky[1]); a.yhi = pair(ky[2], ky[3]);
+        a.ulo = pair(ku[0], ku[1]); a.uhi = pair(ku[2], ku[3]);
+        a.vlo = pair(kv[0], kv[1]); a.vhi = pair(kv[2], kv[3]);
+        const long long work = (long long)a.chunks * a.rows;
+        dim3 grid((unsigned)((work + 255) / 256), 1, nb_frames);
+        if (p->src_bpp == 3)
+            sws_rgb444_kernel<3><<<grid, 256, 0, stream>>>(a);
+        else
+            sws_rgb444_kernel<4><<<grid, 256, 0, stream>>>(a);
+        st->kernel_name = "rgb444";
+        CUDA_OK(cudaGetLastError());
+        st->launches++;
+        return 1;
     }
     /* 8-bit 4:4:4 -> packed RGB of the same size: full-chroma arithmetic path with identity filters */
     if (!p->special && p->full_chr && p->src_bits == 8 && p->src_layout == SWSC_SRC_PLANAR && p->has_chroma &&

@@ -463,3 +463,17 @@ def test_full444_kernel(sf, df, geom, flags):
     _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=flags, seed=118, slices=slices)
     colorspace = (1, 1, 1, 0, 0, 1 << 16, 1 << 16)
     _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=flags, seed=119, colorspace=colorspace)
+
+
+# ---- packed RGB -> 8-bit planar 4:4:4 of the same size: full-resolution readers, identity filters ----
+@pytest.mark.parametrize("sf", RGB_SRC)
+@pytest.mark.parametrize("geom,flags", [((644, 366), S.SWS_BICUBIC | BX), ((35, 19), S.SWS_BILINEAR), ((1280, 720), S.SWS_POINT | BX)])
+def test_rgb444_kernel(sf, geom, flags):
+    w, h = geom
+    for mode in ("noise", "extreme"):
+        name = _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df="yuv444p", flags=flags, seed=121, mode=mode)
+        assert name == "rgb444", name
+    slices = [(y, min(20, h - y)) for y in range(0, h, 20)]
+    _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df="yuv444p", flags=flags, seed=122, slices=slices)
+    _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df="yuv444p", flags=flags, seed=123, colorspace=(1, 0, 1, 0, 0, 1 << 16, 1 << 16))
+    _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df="yuvj444p", flags=flags, seed=124)       # range conversion: another kernel
