@@ -1,5 +1,5 @@
 /*
- * sws_fast420.cuh -- the headline kernel: planar 8-bit 4:2:0 / 4:2:2 -> packed 8-bit RGB
+ * sws_fast420.cuh -- the headline kernel: planar 8-bit 4:2:0 (any 2:1 horizontal chroma whose vertical window fits) -> packed 8-bit RGB
  * when the luma path is the identity and chroma is only filtered vertically
  * (BASELINE configs C1, C2, C5 and the default-flags LUT converter).
  *

@@ -1,5 +1,5 @@
 /*
- * sws_fast420_16.cuh -- planar 9..16-bit 4:2:0 / 4:2:2 -> rgb48le / bgr48le when the luma path is
+ * sws_fast420_16.cuh -- planar 9..16-bit 4:2:0 -> rgb48le / bgr48le when the luma path is
  * the identity and chroma is only filtered vertically (BASELINE config C3: 4K yuv420p10le ->
  * rgb48le, lanczos => 6 vertical chroma taps).
  *

@@ -44,6 +44,8 @@ CONFIGS = [
     ("E4 4K rgba->bgra shuffle", 3840, 2160, "rgba", 3840, 2160, "bgra", S.SWS_BICUBIC | S.BX),
     ("U1 4K nv12->yuv420p (de-interleave copy)", 3840, 2160, "nv12", 3840, 2160, "yuv420p", S.SWS_BICUBIC | S.BX),
     ("U2 4K yuv420p->nv12 (interleave copy)", 3840, 2160, "yuv420p", 3840, 2160, "nv12", S.SWS_BICUBIC | S.BX),
+    ("D1 4K yuv420p10le->yuv420p (dithered depth copy)", 3840, 2160, "yuv420p10le", 3840, 2160, "yuv420p", S.SWS_BICUBIC | S.BX),
+    ("D2 4K yuv420p10le->p010le (planar to p010)", 3840, 2160, "yuv420p10le", 3840, 2160, "p010le", S.SWS_BICUBIC | S.BX),
     ("X1 1080p->4K yuv420p->rgb24 bicubic", 1920, 1080, "yuv420p", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
     ("X2 4K->1080p yuv420p->yuv420p bicubic", 3840, 2160, "yuv420p", 1920, 1080, "yuv420p", S.SWS_BICUBIC | S.BX),
 ]

@@ -28,4 +28,6 @@ cap rgb420 sws_rgb420 "E1 4K" 16 $((3840*2160*16))
 cap fast_hi8 sws_fast420_hi8 "C3b 4K" 16 $((3840*2160*16))
 cap tile15_rgbsrc sws_tile15 "E2 4K" 4 $((3840*2160*4))
 cap copy8 sws_copy8 "U1 4K" 16 $((3840*2160*16))
+cap full444 sws_full444 "F1 4K" 16 $((3840*2160*16))
+cap rgb444 sws_rgb444 "F3 4K" 16 $((3840*2160*16))
 ls -la $OUT
