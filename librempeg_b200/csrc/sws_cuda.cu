@@ -662,72 +662,14 @@ struct P01xArgs {
     int src_stride[3], dst_stride[2];
     int w, cw, y0, rows, cy0, crows;
     int shift;
+    int vec;                       /* every plane and stride allows 16-byte accesses */
 };
 
+/* eight samples of a row as 32-bit values (8- or 16-bit containers; one 8- or 16-byte load when `vec`) */
 template <typename SrcT>
-__global__ void __launch_bounds__(256)
-sws_p01x_kernel(const __grid_constant__ P01xArgs A)
+__device__ __forceinline__ void load8(const SrcT *s, int n, bool vec, unsigned (&v)[8])
 {
-    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-    const int f = blockIdx.z;
-    if (blockIdx.y == 0) {
-        const int chunks = (A.w + 7) / 8;
-        const int row = (int)(idx / chunks), c = (int)(idx - (long long)row * chunks);
-        if (row >= A.rows)
-            return;
-        const SrcT *s = reinterpret_cast<const SrcT *>(A.src[0] + f * A.src_fstride[0] + (size_t)(A.y0 + row) * A.src_stride[0]) + 8 * c;
-        uint16_t *d = reinterpret_cast<uint16_t *>(A.dst[0] + f * A.dst_fstride[0] + (size_t)(A.y0 + row) * A.dst_stride[0]) + 8 * c;
-        const int n = min(8, A.w - 8 * c);
-        for (int i = 0; i < n; i++)
-            d[i] = (uint16_t)(s[i] << A.shift);
-        return;
-    }
-    const int chunks = (A.cw + 7) / 8;
-    const int row = (int)(idx / chunks), c = (int)(idx - (long long)row * chunks);
-    if (row >= A.crows)
-        return;
-    const int y = A.cy0 + row;
-    const SrcT *su = reinterpret_cast<const SrcT *>(A.src[1] + f * A.src_fstride[1] + (size_t)y * A.src_stride[1]) + 8 * c;
-    const SrcT *sv = reinterpret_cast<const SrcT *>(A.src[2] + f * A.src_fstride[2] + (size_t)y * A.src_stride[2]) + 8 * c;
-    uint16_t *d = reinterpret_cast<uint16_t *>(A.dst[1] + f * A.dst_fstride[1] + (size_t)y * A.dst_stride[1]) + 16 * c;
-    const int n = min(8, A.cw - 8 * c);
-    for (int i = 0; i < n; i++) {
-        d[2 * i] = (uint16_t)(su[i] << A.shift);
-        d[2 * i + 1] = (uint16_t)(sv[i] << A.shift);
-    }
-}
-
-struct DepthCopyArgs {
-    const uint8_t *src[3];
-    uint8_t *dst[3];
-    long long src_fstride[3], dst_fstride[3];
-    int src_stride[3], dst_stride[3];
-    int w[3], y0[3], rows[3];      /* per plane: width, first row, row count of this launch */
-    int chunks[3];                 /* 8-sample chunks per row */
-    int src_depth, dst_depth;
-    int src_shift, dst_shift;      /* position of the samples inside 16-bit containers (p010: 6) */
-    int luma_shiftonly;            /* limited-range source: luma is shifted like chroma */
-    int dither_none;
-    int vec;                       /* planes and strides allow 8/16-byte accesses */
-};
-
-template <typename SrcT, typename DstT>
-__global__ void __launch_bounds__(256)
-sws_depthcopy_kernel(const __grid_constant__ DepthCopyArgs A)
-{
-    const int plane = blockIdx.y;
-    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-    const int row = (int)(idx / A.chunks[plane]), c = (int)(idx - (long long)row * A.chunks[plane]);
-    if (row >= A.rows[plane])
-        return;
-    const int y = A.y0[plane] + row;
-    const SrcT *s = reinterpret_cast<const SrcT *>(A.src[plane] + blockIdx.z * A.src_fstride[plane] + (size_t)y * A.src_stride[plane]) + 8 * c;
-    DstT *d = reinterpret_cast<DstT *>(A.dst[plane] + blockIdx.z * A.dst_fstride[plane] + (size_t)y * A.dst_stride[plane]) + 8 * c;
-    const int n = min(8, A.w[plane] - 8 * c);
-    const bool shiftonly = plane != 0 || A.luma_shiftonly;
-    const int sd = A.src_depth, dd = A.dst_depth;
-    unsigned v[8], o[8];
-    if (n == 8 && A.vec) {
+    if (vec && n == 8) {
         if (sizeof(SrcT) == 1) {
             const uint2 q = __ldcs(reinterpret_cast<const uint2 *>(s));
 #pragma unroll
@@ -745,6 +687,138 @@ sws_depthcopy_kernel(const __grid_constant__ DepthCopyArgs A)
         for (int i = 0; i < 8; i++)
             v[i] = i < n ? s[i] : 0;
     }
+}
+
+template <typename SrcT>
+__global__ void __launch_bounds__(256)
+sws_p01x_kernel(const __grid_constant__ P01xArgs A)
+{
+    /* one index space: the luma chunks of all rows, then the chroma chunks (8 samples / 8 pairs per thread) */
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int f = blockIdx.z;
+    const int lchunks = (A.w + 7) / 8, cchunks = (A.cw + 7) / 8;
+    const long long lwork = (long long)lchunks * A.rows;
+    if (idx < lwork) {
+        const int row = (int)(idx / lchunks), c = (int)(idx - (long long)row * lchunks);
+        const SrcT *s = reinterpret_cast<const SrcT *>(A.src[0] + f * A.src_fstride[0] + (size_t)(A.y0 + row) * A.src_stride[0]) + 8 * c;
+        uint16_t *d = reinterpret_cast<uint16_t *>(A.dst[0] + f * A.dst_fstride[0] + (size_t)(A.y0 + row) * A.dst_stride[0]) + 8 * c;
+        const int n = min(8, A.w - 8 * c);
+        unsigned v[8];
+        load8<SrcT>(s, n, A.vec, v);
+        if (A.vec && n == 8) {
+            __stcs(reinterpret_cast<uint4 *>(d), make_uint4(((v[0] << A.shift) & 0xFFFFu) | (v[1] << (A.shift + 16)),
+                                                            ((v[2] << A.shift) & 0xFFFFu) | (v[3] << (A.shift + 16)),
+                                                            ((v[4] << A.shift) & 0xFFFFu) | (v[5] << (A.shift + 16)),
+                                                            ((v[6] << A.shift) & 0xFFFFu) | (v[7] << (A.shift + 16))));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (i < n)
+                    d[i] = (uint16_t)(v[i] << A.shift);
+        }
+        return;
+    }
+    const long long cidx = idx - lwork;
+    const int row = (int)(cidx / cchunks), c = (int)(cidx - (long long)row * cchunks);
+    if (row >= A.crows)
+        return;
+    const int y = A.cy0 + row;
+    const SrcT *su = reinterpret_cast<const SrcT *>(A.src[1] + f * A.src_fstride[1] + (size_t)y * A.src_stride[1]) + 8 * c;
+    const SrcT *sv = reinterpret_cast<const SrcT *>(A.src[2] + f * A.src_fstride[2] + (size_t)y * A.src_stride[2]) + 8 * c;
+    uint16_t *d = reinterpret_cast<uint16_t *>(A.dst[1] + f * A.dst_fstride[1] + (size_t)y * A.dst_stride[1]) + 16 * c;
+    const int n = min(8, A.cw - 8 * c);
+    unsigned u[8], v[8];
+    load8<SrcT>(su, n, A.vec, u);
+    load8<SrcT>(sv, n, A.vec, v);
+    if (A.vec && n == 8) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            w[i] = ((u[i] << A.shift) & 0xFFFFu) | (v[i] << (A.shift + 16));
+        __stcs(reinterpret_cast<uint4 *>(d), make_uint4(w[0], w[1], w[2], w[3]));
+        __stcs(reinterpret_cast<uint4 *>(d) + 1, make_uint4(w[4], w[5], w[6], w[7]));
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (i < n) {
+                d[2 * i] = (uint16_t)(u[i] << A.shift);
+                d[2 * i + 1] = (uint16_t)(v[i] << A.shift);
+            }
+    }
+}
+
+struct DepthCopyArgs {
+    const uint8_t *src[3];
+    uint8_t *dst[3];
+    long long src_fstride[3], dst_fstride[3];
+    int src_stride[3], dst_stride[3];
+    int w[3], y0[3], rows[3];      /* per plane: width, first row, row count of this launch */
+    int chunks[3];                 /* 8-sample chunks per row */
+    int src_depth, dst_depth;
+    int src_shift, dst_shift;      /* position of the samples inside 16-bit containers (p010: 6) */
+    int luma_shiftonly;            /* limited-range source: luma is shifted like chroma */
+    int dither_none;
+    int vec;                       /* planes and strides allow 8/16-byte accesses */
+    int nplanes;
+};
+
+template <typename SrcT, typename DstT>
+__global__ void __launch_bounds__(256)
+sws_depthcopy_kernel(const __grid_constant__ DepthCopyArgs A)
+{
+    /* one index space over the planes: no block is launched only to find its plane already done */
+    long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    int plane = 0;
+#pragma unroll
+    for (int pl = 0; pl < 2; pl++) {
+        const long long work = (long long)A.chunks[plane] * A.rows[plane];
+        if (plane == pl && idx >= work) {
+            idx -= work;
+            plane = pl + 1;
+        }
+    }
+    if (plane >= A.nplanes)
+        return;
+    const unsigned i32 = (unsigned)idx, nch = (unsigned)A.chunks[plane];       /* a plane has < 2^31 chunks */
+    const int row = (int)(i32 / nch), c = (int)(i32 - (unsigned)row * nch);
+    if (row >= A.rows[plane])
+        return;
+    const int y = A.y0[plane] + row;
+    const SrcT *s = reinterpret_cast<const SrcT *>(A.src[plane] + blockIdx.z * A.src_fstride[plane] + (size_t)y * A.src_stride[plane]) + 8 * c;
+    DstT *d = reinterpret_cast<DstT *>(A.dst[plane] + blockIdx.z * A.dst_fstride[plane] + (size_t)y * A.dst_stride[plane]) + 8 * c;
+    const int n = min(8, A.w[plane] - 8 * c);
+    const bool shiftonly = plane != 0 || A.luma_shiftonly;
+    const int sd = A.src_depth, dd = A.dst_depth;
+    if (sizeof(SrcT) == 2 && sd > dd && sd <= 15 && A.vec && n == 8 && A.src_shift == 0) {
+        /* two samples per 32-bit word: with at most 15 source bits v + dither cannot carry into the upper half,
+         * and t - (t >> dst_depth) cannot borrow.  Same numbers as the scalar path below. */
+        const int shift = sd - dd;
+        const uint4 q = __ldcs(reinterpret_cast<const uint4 *>(s));
+        const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+        const uint2 dq = *reinterpret_cast<const uint2 *>(c_depth_dither[shift - 1][row & 7]);
+        const uint32_t half = 0x00010001u;
+        const uint32_t hm = (0xFFFFu >> shift) * half;
+        uint32_t r[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t dw = k < 2 ? dq.x : dq.y;
+            const uint32_t d2 = A.dither_none ? (1u << (shift - 1)) * half : prmt(dw, 0u, (k & 1) ? 0x4342 : 0x4140);
+            if (A.dither_none || shiftonly) {
+                const uint32_t t = ((w[k] + d2) >> shift) & hm;
+                r[k] = t - ((t >> dd) & half);
+            } else {
+                const uint32_t x = w[k] - ((w[k] >> dd) & ((0xFFFFu >> dd) * half));
+                r[k] = ((x + d2) >> shift) & hm;
+            }
+        }
+        if (sizeof(DstT) == 1)
+            __stcs(reinterpret_cast<uint2 *>(d), make_uint2(prmt(r[0], r[1], 0x6420), prmt(r[2], r[3], 0x6420)));
+        else
+            __stcs(reinterpret_cast<uint4 *>(d), make_uint4(r[0], r[1], r[2], r[3]));
+        return;
+    }
+    unsigned v[8], o[8];
+    load8<SrcT>(s, n, A.vec, v);
 #pragma unroll
     for (int i = 0; i < 8; i++)
         v[i] >>= A.src_shift;
@@ -2670,9 +2744,13 @@ static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const i
         a.cy0 = (y0 + 1) >> 1;                               /* chroma rows at even luma rows (:311,:358) */
         a.crows = ((y1 + 1) >> 1) - a.cy0;
         a.shift = p->src_bits == 8 ? 8 : 16 - p->src_bits;
-        const long long lw = (long long)((a.w + 7) / 8) * a.rows, cwk = (long long)((a.cw + 7) / 8) * a.crows;
-        const long long mx = lw > cwk ? lw : cwk;
-        dim3 grid((unsigned)((mx + 255) / 256), 2, nb_frames);
+        a.vec = 1;
+        for (int i = 0; i < 3; i++)
+            a.vec = a.vec && aligned16(src[i]) && !(src_stride[i] & 15) && !(a.src_fstride[i] & 15);
+        for (int i = 0; i < 2; i++)
+            a.vec = a.vec && aligned16(dst[i]) && !(dst_stride[i] & 15) && !(a.dst_fstride[i] & 15);
+        const long long work = (long long)((a.w + 7) / 8) * a.rows + (long long)((a.cw + 7) / 8) * a.crows;
+        dim3 grid((unsigned)((work + 255) / 256), 1, nb_frames);
         if (p->src_bits == 8)
             sws_p01x_kernel<uint8_t><<<grid, 256, 0, stream>>>(a);
         else
@@ -2711,7 +2789,12 @@ static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const i
         a.luma_shiftonly = !p->src_full_range;
         a.dither_none = p->dither_none;
         a.vec = vec;
-        dim3 grid((unsigned)((mx + 255) / 256), np, nb_frames);
+        a.nplanes = np;
+        long long total = 0;
+        for (int i = 0; i < np; i++)
+            total += (long long)a.chunks[i] * a.rows[i];
+        (void)mx;
+        dim3 grid((unsigned)((total + 255) / 256), 1, nb_frames);
         if (p->src_bits == 8)
             sws_depthcopy_kernel<uint8_t, uint16_t><<<grid, 256, 0, stream>>>(a);
         else if (p->dst_bits == 8)
