@@ -106,6 +106,7 @@ sws_tile15_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_constant__
         for (int row = warp; row < nr; row += 8) {
             const uint8_t *srow = src0 + (size_t)(lo_l + r + row) * A.src_stride[0];
             samp_t *d = stage_l + row * seg;
+#pragma unroll 4
             for (int i = lane; i < seg; i += 32) {
                 const int sx = min(a0 + i, P.src_w - 1);
                 if (SRCK == T15_SRC_U8)
@@ -122,6 +123,7 @@ sws_tile15_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_constant__
         for (int row = warp; row < nr; row += 8) {
             const int sy = lo_c + r + row;
             samp_t *du = stage_c + row * seg, *dv = stage_c + (src_rows + row) * seg;
+#pragma unroll 4
             for (int i = lane; i < seg; i += 32) {
                 const int sx = min(ca0 + i, P.chr_src_w - 1);
                 if (SRCK == T15_SRC_RGB) {
