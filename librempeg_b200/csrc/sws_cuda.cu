@@ -1305,7 +1305,7 @@ struct SwsCudaState {
     int r420_ok, r420_cr;
     int fast_narrow;             /* the 128 x 64 tile shape of the fast420 kernel is set up and preferred */
     int4 *d_fast_rows_narrow;
-    int fasthi8_ok;
+    int fasthi8_ok, fasthi8_crows;
     int s8_ok, s8_fs4, s8_tile_h, s8_nl_cap, s8_nc_cap, s8_seg_l, s8_seg_c, s8_slot, s8_vl_n4, s8_vc_n4;
     size_t s8_smem;
     void *s8_tables;
@@ -1676,7 +1676,7 @@ static fast16_kernel_t pick_fast16(int taps, bool bgr)
 /* per-row metadata shared by the two high-depth same-size kernels: first chroma source row (tile relative and
  * absolute) and the eight int16 vertical chroma taps.  Returns 1 when uploaded, 0 when the geometry does not
  * fit the kernels' 24-row chroma window, < 0 on error. */
-static int fast16_rows(SwsCudaState *st, const SwsFirBank *vc, int taps)
+static int fast16_rows(SwsCudaState *st, const SwsFirBank *vc, int taps, int crows = F16_CROWS)
 {
     if (st->d_fast16_rows)
         return 1;
@@ -1699,7 +1699,7 @@ static int fast16_rows(SwsCudaState *st, const SwsFirBank *vc, int taps)
         const int base = rows[y & ~(F16_TH - 1)].pos_abs;
         rows[y].pos_rel = rows[y].pos_abs - base;
         if ((y > 0 && rows[y].pos_abs < rows[y - 1].pos_abs) || rows[y].pos_rel < 0 ||
-            rows[y].pos_rel + taps > F16_CROWS) {
+            rows[y].pos_rel + taps > crows) {
             free(rows);
             return 0;
         }
@@ -1836,12 +1836,19 @@ static int fasthi8_setup(SwsCudaState *st, const SwsFirBank *vc)
     if ((p->dst_kind == SWSC_DST_RGB24 || p->dst_kind == SWSC_DST_BGR24) && (p->dst_w & 3))
         return 0;                     /* the store tensor map counts 32-bit words */
     const int taps = vc->size <= 4 ? 4 : vc->size <= 6 ? 6 : 8;
-    int ret = fast16_rows(st, vc, taps);
+    /* 24 staged chroma rows cover 4:2:0; sources without vertical chroma subsampling (4:2:2) need 32 + taps */
+    int crows = F16_CROWS;
+    int ret = fast16_rows(st, vc, taps, crows);
+    if (ret == 0) {
+        crows = 36;
+        ret = fast16_rows(st, vc, taps, crows);
+    }
     if (ret <= 0)
         return ret;
+    st->fasthi8_crows = crows;
     const int fmt = fast420_fmt(p->dst_kind);
     CUDA_OK(cudaFuncSetAttribute((const void *)pick_fasthi8(taps, fmt, semi), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 H8_SMEM(fmt >= F420_RGBA ? 4 : 3)));
+                                 H8_SMEM(fmt >= F420_RGBA ? 4 : 3, crows)));
     st->fasthi8_ok = 1;
     st->fast16_taps = taps;
     st->kernel_name = "fast420_hi8_tma";
@@ -1865,6 +1872,7 @@ static int fasthi8_launch(SwsCudaState *st, const uint8_t *const src[4], const i
         return 0;
     const int fmt = fast420_fmt(p->dst_kind);
     const int bpp = fmt >= F420_RGBA ? 4 : 3;
+    const int crows = st->fasthi8_crows;
     CUtensorMap my, mu, mv, mo;
     const uint64_t fs_y = nb_frames > 1 ? src_fstride[0] : (uint64_t)src_stride[0] * p->src_h;
     const uint64_t fs_u = nb_frames > 1 ? src_fstride[1] : (uint64_t)src_stride[1] * p->chr_src_h;
@@ -1877,15 +1885,15 @@ static int fasthi8_launch(SwsCudaState *st, const uint8_t *const src[4], const i
         return ret;
     if (semi) {
         if ((ret = make_map_3d(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT16, src[1], 2 * (uint64_t)p->chr_src_w, p->chr_src_h,
-                               nb_frames, src_stride[1], fs_u, F16_TW, F16_CROWS)) < 0)
+                               nb_frames, src_stride[1], fs_u, F16_TW, crows)) < 0)
             return ret;
         mv = mu;
     } else {
         const uint64_t fs_v = nb_frames > 1 ? src_fstride[2] : (uint64_t)src_stride[2] * p->chr_src_h;
         if ((ret = make_map_3d(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT16, src[1], p->chr_src_w, p->chr_src_h, nb_frames,
-                               src_stride[1], fs_u, F16_TW / 2, F16_CROWS)) < 0 ||
+                               src_stride[1], fs_u, F16_TW / 2, crows)) < 0 ||
             (ret = make_map_3d(&mv, CU_TENSOR_MAP_DATA_TYPE_UINT16, src[2], p->chr_src_w, p->chr_src_h, nb_frames,
-                               src_stride[2], fs_v, F16_TW / 2, F16_CROWS)) < 0)
+                               src_stride[2], fs_v, F16_TW / 2, crows)) < 0)
             return ret;
     }
     FastHi8Args a;
@@ -1897,13 +1905,14 @@ static int fasthi8_launch(SwsCudaState *st, const uint8_t *const src[4], const i
     a.dst_h = p->dst_h;
     a.sdown = p->src_bits - 1;
     a.sshift = p->src_shift;
+    a.crows = crows;
     a.cy = p->rgb.cy; a.yb = p->rgb.yb;
     a.crv = p->rgb.crv; a.cbu = p->rgb.cbu; a.cgu = p->rgb.cgu; a.cgv = p->rgb.cgv;
     a.base_r = p->rgb.base_r; a.base_g = p->rgb.base_g; a.base_b = p->rgb.base_b;
     a.rows = st->d_fast16_rows;
     const long long total = (long long)a.tiles_x * a.tiles_y * nb_frames;
     const int grid = (int)(total < (long long)st->num_sms * F420_CTAS_PER_SM ? total : (long long)st->num_sms * F420_CTAS_PER_SM);
-    pick_fasthi8(st->fast16_taps, fmt, semi)<<<grid, F420_THREADS, H8_SMEM(bpp), stream>>>(my, mu, mv, mo, a);
+    pick_fasthi8(st->fast16_taps, fmt, semi)<<<grid, F420_THREADS, H8_SMEM(bpp, crows), stream>>>(my, mu, mv, mo, a);
     st->kernel_name = "fast420_hi8_tma";
     CUDA_OK(cudaGetLastError());
     st->launches++;

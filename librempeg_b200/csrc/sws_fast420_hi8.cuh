@@ -18,12 +18,17 @@
 #include "sws_fast420_16.cuh"
 
 #define H8_OUT_BYTES(bpp) (F16_TW * (bpp) * F16_TH)                          /* 12288 / 16384 */
-#define H8_SMEM(bpp) (F420_STAGES * F16_IN_BYTES + H8_OUT_BYTES(bpp))
+/* chroma rows staged per tile are a launch parameter: 24 for 4:2:0 (16 + the vertical taps), 36 for 4:2:2 sources
+ * whose chroma is not subsampled vertically (32 + taps: yuv422p10le, the ProRes / DNxHR decode format) */
+#define H8_C_BYTES(crows) ((F16_TW / 2) * 2 * (crows))
+#define H8_IN_BYTES(crows) (F16_Y_BYTES + 2 * H8_C_BYTES(crows) + F16_META_BYTES)
+#define H8_SMEM(bpp, crows) (F420_STAGES * H8_IN_BYTES(crows) + H8_OUT_BYTES(bpp))
 
 struct FastHi8Args {
     int tiles_x, tiles_y, frames, ty_first, dst_h;
     int sdown;                /* source depth - 1: the right shift of the identity horizontal filter */
     int sshift;               /* position of the samples in their 16-bit containers (p010: 6) */
+    int crows;                /* chroma source rows staged per tile (24 or 36) */
     int cy, yb;               /* LUT closed form (sws_colorspace.c) */
     int crv, cbu, cgu, cgv;
     int base_r, base_g, base_b;
@@ -48,6 +53,7 @@ sws_fast420_hi8_kernel(const __grid_constant__ CUtensorMap map_y,
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int tiles_per_frame = A.tiles_x * A.tiles_y;
     const int total = tiles_per_frame * A.frames;
+    const int c_bytes = H8_C_BYTES(A.crows), in_bytes = H8_IN_BYTES(A.crows);
 
     if (tid == 0) {
         for (int s = 0; s < F420_STAGES; s++) {
@@ -75,17 +81,17 @@ sws_fast420_hi8_kernel(const __grid_constant__ CUtensorMap map_y,
                 const int ty = t / A.tiles_x, tx = t - ty * A.tiles_x;
                 const int y0 = (A.ty_first + ty) * F16_TH;
                 const int c_lo = __ldg(&A.rows[y0].pos_abs);
-                unsigned char *b = smem_dyn + stage * F16_IN_BYTES;
+                unsigned char *b = smem_dyn + stage * in_bytes;
                 tile_info[stage] = make_int4(tx, y0, f, 0);
-                mbar_expect_tx(&full_bar[stage], F16_IN_BYTES);
+                mbar_expect_tx(&full_bar[stage], in_bytes);
                 tma_load_3d(b, &map_y, &full_bar[stage], tx * F16_TW, y0, f);
                 if (SEMI) {          /* one box of interleaved UV rows: the same bytes as the two planar boxes */
                     tma_load_3d(b + F16_Y_BYTES, &map_u, &full_bar[stage], tx * F16_TW, c_lo, f);
                 } else {
                     tma_load_3d(b + F16_Y_BYTES, &map_u, &full_bar[stage], tx * (F16_TW / 2), c_lo, f);
-                    tma_load_3d(b + F16_Y_BYTES + F16_C_BYTES, &map_v, &full_bar[stage], tx * (F16_TW / 2), c_lo, f);
+                    tma_load_3d(b + F16_Y_BYTES + c_bytes, &map_v, &full_bar[stage], tx * (F16_TW / 2), c_lo, f);
                 }
-                bulk_load_1d(b + F16_Y_BYTES + 2 * F16_C_BYTES, A.rows + y0, F16_META_BYTES, &full_bar[stage]);
+                bulk_load_1d(b + F16_Y_BYTES + 2 * c_bytes, A.rows + y0, F16_META_BYTES, &full_bar[stage]);
             }
         }
         return;
@@ -98,7 +104,7 @@ sws_fast420_hi8_kernel(const __grid_constant__ CUtensorMap map_y,
     const int cy = A.cy, yb = A.yb;
     const int crv = A.crv, cbu = A.cbu, cgu = A.cgu, cgv = A.cgv;
     const int r0 = warp * (F16_TH / F420_CWARPS);
-    unsigned char *so_warp = smem_dyn + F420_STAGES * F16_IN_BYTES + r0 * (F16_TW * BPP);
+    unsigned char *so_warp = smem_dyn + F420_STAGES * in_bytes + r0 * (F16_TW * BPP);
     unsigned char *so = so_warp + lane * (4 * BPP);
 
     /* 16-bit sample (either half of a packed word) -> 15-bit h-scaled line value */
@@ -119,14 +125,14 @@ sws_fast420_hi8_kernel(const __grid_constant__ CUtensorMap map_y,
     int i = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
         const int stage = i % F420_STAGES;
-        const unsigned char *sb = smem_dyn + stage * F16_IN_BYTES;
+        const unsigned char *sb = smem_dyn + stage * in_bytes;
         mbar_wait(&full_bar[stage], (i / F420_STAGES) & 1);
 
         const int4 ti = tile_info[stage];
-        const int4 *mrow = reinterpret_cast<const int4 *>(sb + F16_Y_BYTES + 2 * F16_C_BYTES) + 2 * r0;
+        const int4 *mrow = reinterpret_cast<const int4 *>(sb + F16_Y_BYTES + 2 * c_bytes) + 2 * r0;
         const unsigned char *sy = sb + r0 * (F16_TW * 2) + lane * 8;
         const unsigned char *su = sb + F16_Y_BYTES + lane * (SEMI ? 8 : 4);
-        const unsigned char *sv = su + F16_C_BYTES;
+        const unsigned char *sv = su + c_bytes;
 
         /* this warp's previous TMA store must have finished READING its staging rows */
         if (lane == 0)

@@ -414,7 +414,8 @@ def test_nv12_to_p010_unscaled(geom, opts):
 
 
 # ---- 9..16-bit planar -> packed 8-bit RGB of the same size: the TMA kernel for 10-bit video to display RGB ----
-@pytest.mark.parametrize("sf", ["yuv420p10le", "yuv420p9le", "yuv420p12le", "yuv420p14le", "yuv420p16le", "p010le"])
+@pytest.mark.parametrize("sf", ["yuv420p10le", "yuv420p9le", "yuv420p12le", "yuv420p14le", "yuv420p16le", "p010le",
+                                "yuv422p10le", "yuv422p12le"])
 @pytest.mark.parametrize("df", ["rgb24", "bgr24", "rgba", "bgra", "argb", "abgr"])
 @pytest.mark.parametrize("geom,flags", [((644, 366), S.SWS_BICUBIC | BX), ((256, 34), S.SWS_BILINEAR | BX),
                                         ((1280, 720), S.SWS_LANCZOS | BX), ((648, 360), S.SWS_BICUBIC),

@@ -27,6 +27,7 @@ CONFIGS = [
     ("C3 4K yuv420p10le->rgb48le lanczos", 3840, 2160, "yuv420p10le", 3840, 2160, "rgb48le", S.SWS_LANCZOS | S.BX),
     ("C3b 4K yuv420p10le->rgb24 bicubic", 3840, 2160, "yuv420p10le", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
     ("C3c 4K yuv420p10le->bgra bicubic", 3840, 2160, "yuv420p10le", 3840, 2160, "bgra", S.SWS_BICUBIC | S.BX),
+    ("C3q 4K yuv422p10le->bgra bicubic (ProRes-style source)", 3840, 2160, "yuv422p10le", 3840, 2160, "bgra", S.SWS_BICUBIC | S.BX),
     ("C3p 4K p010le->rgb24 bicubic", 3840, 2160, "p010le", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
     ("C4 8K nv12->1080p yuv420p bicubic", 7680, 4320, "nv12", 1920, 1080, "yuv420p", S.SWS_BICUBIC | S.BX),
     ("C5 4K yuv420p->rgb24 bicubic", 3840, 2160, "yuv420p", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
