@@ -1303,6 +1303,7 @@ struct SwsCudaState {
     /* fast420 path */
     int fast_ok;
     int r420_ok, r420_cr;
+    int fast_v422;               /* the source has one chroma row per luma row: TH + 4 staged chroma rows */
     int fast_narrow;             /* the 128 x 64 tile shape of the fast420 kernel is set up and preferred */
     int4 *d_fast_rows_narrow;
     int fasthi8_ok, fasthi8_crows;
@@ -1467,30 +1468,33 @@ static int fast420_fmt(int dst_kind)
     }
 }
 
-template <int FMT, bool NARROW>
+template <int FMT, bool NARROW, bool V422>
 static fast420_kernel_t pick_fast420_src(int layout)
 {
-    return layout == SWSC_SRC_PLANAR ? sws_fast420_rgb8_kernel<FMT, F420_PLANAR, NARROW>
-         : layout == SWSC_SRC_NV12   ? sws_fast420_rgb8_kernel<FMT, F420_NV12, NARROW>
-                                     : sws_fast420_rgb8_kernel<FMT, F420_NV21, NARROW>;
+    return layout == SWSC_SRC_PLANAR ? sws_fast420_rgb8_kernel<FMT, F420_PLANAR, NARROW, V422>
+         : layout == SWSC_SRC_NV12   ? sws_fast420_rgb8_kernel<FMT, F420_NV12, NARROW, V422>
+                                     : sws_fast420_rgb8_kernel<FMT, F420_NV21, NARROW, V422>;
 }
 
-template <bool NARROW>
+template <bool NARROW, bool V422>
 static fast420_kernel_t pick_fast420_shape(int fmt, int layout)
 {
     switch (fmt) {
-    case F420_RGB24: return pick_fast420_src<F420_RGB24, NARROW>(layout);
-    case F420_BGR24: return pick_fast420_src<F420_BGR24, NARROW>(layout);
-    case F420_RGBA:  return pick_fast420_src<F420_RGBA, NARROW>(layout);
-    case F420_BGRA:  return pick_fast420_src<F420_BGRA, NARROW>(layout);
-    case F420_ARGB:  return pick_fast420_src<F420_ARGB, NARROW>(layout);
-    default:         return pick_fast420_src<F420_ABGR, NARROW>(layout);
+    case F420_RGB24: return pick_fast420_src<F420_RGB24, NARROW, V422>(layout);
+    case F420_BGR24: return pick_fast420_src<F420_BGR24, NARROW, V422>(layout);
+    case F420_RGBA:  return pick_fast420_src<F420_RGBA, NARROW, V422>(layout);
+    case F420_BGRA:  return pick_fast420_src<F420_BGRA, NARROW, V422>(layout);
+    case F420_ARGB:  return pick_fast420_src<F420_ARGB, NARROW, V422>(layout);
+    default:         return pick_fast420_src<F420_ABGR, NARROW, V422>(layout);
     }
 }
 
-static fast420_kernel_t pick_fast420(int fmt, int layout, bool narrow = false)
+/* narrow = 128 x 64 tiles; v422 = TH + 4 staged chroma rows (sources without vertical chroma subsampling; wide shape only) */
+static fast420_kernel_t pick_fast420(int fmt, int layout, bool narrow = false, bool v422 = false)
 {
-    return narrow ? pick_fast420_shape<true>(fmt, layout) : pick_fast420_shape<false>(fmt, layout);
+    if (v422)
+        return pick_fast420_shape<false, true>(fmt, layout);
+    return narrow ? pick_fast420_shape<true, false>(fmt, layout) : pick_fast420_shape<false, false>(fmt, layout);
 }
 
 /* per-row metadata of the same-size 8-bit kernel for tiles of `th` rows that stage `crows` chroma rows: returns a
@@ -1555,25 +1559,32 @@ static int fast420_setup(SwsCudaState *st, const SwsFirBank *vc)
         return 0;
     if ((p->dst_kind == SWSC_DST_RGB24 || p->dst_kind == SWSC_DST_BGR24) && (p->dst_w & 3))
         return 0;                     /* the store tensor map counts 32-bit words */
-    if (max_rows_needed(vc->pos, vc->size > 4 ? vc->size : 4, vc->len, F420_TH) > F420_CROWS)
-        return 0;
+    /* staged chroma rows per tile: 20 (36 for the narrow shape) cover vertically subsampled chroma; 4:2:2 sources
+     * need one chroma row per luma row, TH + 4 (a separate instantiation of the wide shape) */
     int fits = 0, ret;
+    st->fast_v422 = 0;
     if ((ret = fast420_rows(p, vc, F420_TH, F420_CROWS, &st->d_fast_rows, &fits)) < 0)
         return ret;
+    if (!fits) {
+        if ((ret = fast420_rows(p, vc, F420_TH, F420_TH + 4, &st->d_fast_rows, &fits)) < 0)
+            return ret;
+        st->fast_v422 = fits;
+    }
     if (!fits)
         return 0;
     const int fmt = fast420_fmt(p->dst_kind);
-    CUDA_OK(cudaFuncSetAttribute((const void *)pick_fast420(fmt, p->src_layout),
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, F420_SMEM(fmt >= F420_RGBA ? 4 : 3)));
+    const int bpp = fmt >= F420_RGBA ? 4 : 3;
+    CUDA_OK(cudaFuncSetAttribute((const void *)pick_fast420(fmt, p->src_layout, false, st->fast_v422),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 F420_SMEM_CROWS(bpp, F420_TW, F420_TH, st->fast_v422 ? F420_TH + 4 : F420_CROWS)));
     /* 128 x 64 tiles when they cover the frame width with less waste than 256 x 32 tiles (1920, 640, ...) */
     st->fast_narrow = 0;
-    if ((p->dst_w + 127) / 128 * 128 < (p->dst_w + 255) / 256 * 256 && !getenv("SWS_B200_NO_NARROW")) {
+    if (!st->fast_v422 && (p->dst_w + 127) / 128 * 128 < (p->dst_w + 255) / 256 * 256 && !getenv("SWS_B200_NO_NARROW")) {
         if ((ret = fast420_rows(p, vc, 2 * F420_TH, F420_CROWS_NARROW, &st->d_fast_rows_narrow, &fits)) < 0)
             return ret;
         if (fits) {
             CUDA_OK(cudaFuncSetAttribute((const void *)pick_fast420(fmt, p->src_layout, true),
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         F420_SMEM(fmt >= F420_RGBA ? 4 : 3)));
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, F420_SMEM(bpp)));
             st->fast_narrow = 1;
         }
     }
@@ -1613,7 +1624,7 @@ static int fast420_launch(SwsCudaState *st, const uint8_t *const src[4], const i
     /* tile shape: 128 x 64 when that wastes less of the right-most tile column and the row range allows it */
     const bool narrow = st->fast_narrow && !(y0 % (2 * F420_TH));
     const int TW = narrow ? F420_TW / 2 : F420_TW, TH = narrow ? 2 * F420_TH : F420_TH;
-    const int CROWS = narrow ? F420_CROWS_NARROW : F420_CROWS;
+    const int CROWS = st->fast_v422 ? F420_TH + 4 : narrow ? F420_CROWS_NARROW : F420_CROWS;
     CUtensorMap my, mu, mv, mo;
     const uint64_t fs_y = nb_frames > 1 ? src_fstride[0] : (uint64_t)src_stride[0] * p->src_h;
     const uint64_t fs_u = nb_frames > 1 ? src_fstride[1] : (uint64_t)src_stride[1] * p->chr_src_h;
@@ -1651,7 +1662,7 @@ static int fast420_launch(SwsCudaState *st, const uint8_t *const src[4], const i
     a.rows = narrow ? st->d_fast_rows_narrow : st->d_fast_rows;
     const long long total = (long long)a.tiles_x * a.tiles_y * nb_frames;
     const int grid = (int)(total < (long long)st->num_sms * F420_CTAS_PER_SM ? total : (long long)st->num_sms * F420_CTAS_PER_SM);
-    pick_fast420(fmt, p->src_layout, narrow)<<<grid, F420_THREADS, F420_SMEM(bpp), stream>>>(my, mu, mv, mo, a);
+    pick_fast420(fmt, p->src_layout, narrow, st->fast_v422)<<<grid, F420_THREADS, F420_SMEM_CROWS(bpp, TW, TH, CROWS), stream>>>(my, mu, mv, mo, a);
     st->kernel_name = "fast420_rgb8_tma";     /* the name always reports the last kernel launched */
     CUDA_OK(cudaGetLastError());
     st->launches++;

@@ -42,6 +42,10 @@
 #define F420_CTAS_PER_SM 3
 #endif
 #define F420_SMEM(bpp) (F420_STAGES * F420_IN_BYTES + F420_OUT_BYTES(bpp))
+/* sources without vertical chroma subsampling (4:2:2: yuv422p / yuvj422p, the MJPEG decode format) stage TH + 4
+ * chroma rows per tile instead of 20 (36 for the narrow shape): the ring slot grows, the kernel is the same */
+#define F420_IN_BYTES_CROWS(tw, th, crows) ((tw) * (th) + 2 * ((tw) / 2) * (crows) + (th) * 16)
+#define F420_SMEM_CROWS(bpp, tw, th, crows) (F420_STAGES * F420_IN_BYTES_CROWS(tw, th, crows) + F420_OUT_BYTES(bpp))
 
 /* destination byte orders and source chroma layouts the kernel is instantiated for */
 enum { F420_RGB24 = 0, F420_BGR24, F420_RGBA, F420_BGRA, F420_ARGB, F420_ABGR };
@@ -165,7 +169,7 @@ __device__ __forceinline__ void transpose4(uint32_t r0, uint32_t r1, uint32_t r2
 /* NARROW: tile 128 x 64 instead of 256 x 32 (the same bytes per stage): frames whose width is not a multiple of
  * 256 waste less of their right-most tile column (1920 = 15 x 128, 640 = 5 x 128).  A warp then owns 8 rows,
  * lanes 0-15 the first four, lanes 16-31 the last four. */
-template <int FMT, int SRC, bool NARROW>
+template <int FMT, int SRC, bool NARROW, bool V422>
 __global__ void __launch_bounds__(F420_THREADS, F420_CTAS_PER_SM)
 sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
                         const __grid_constant__ CUtensorMap map_u,
@@ -175,10 +179,12 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
 {
     constexpr int BPP = FMT >= F420_RGBA ? 4 : 3;
     constexpr int TW = NARROW ? F420_TW / 2 : F420_TW, TH = NARROW ? 2 * F420_TH : F420_TH;
-    constexpr int CROWS = NARROW ? F420_CROWS_NARROW : F420_CROWS;
     constexpr int RPW = TH / F420_CWARPS;                  /* rows per warp: 4 or 8 */
-    constexpr int Y_BYTES = TW * TH, C_BYTES = (TW / 2) * CROWS, META_BYTES = TH * 16;
-    static_assert(Y_BYTES + 2 * C_BYTES + META_BYTES == F420_IN_BYTES, "both tile shapes fill one ring slot");
+    constexpr int Y_BYTES = TW * TH, META_BYTES = TH * 16;
+    /* staged chroma rows: compile-time constants so that the headline instantiation keeps immediate offsets */
+    constexpr int CROWS = V422 ? TH + 4 : (NARROW ? F420_CROWS_NARROW : F420_CROWS);
+    constexpr int C_BYTES = (TW / 2) * CROWS, IN_BYTES = Y_BYTES + 2 * C_BYTES + META_BYTES;
+    static_assert(V422 || IN_BYTES == F420_IN_BYTES, "both tile shapes fill one ring slot for 4:2:0 sources");
     /* [stage: Y | U | V (or interleaved UV) | row meta] x STAGES, then [out: 8 warps x RPW rows] */
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[F420_STAGES];
@@ -216,9 +222,9 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
                 const int ty = t / A.tiles_x, tx = t - ty * A.tiles_x;
                 const int y0 = (A.ty_first + ty) * TH;
                 const int c_lo = __ldg(&A.rows[y0]).w;
-                unsigned char *b = smem_dyn + stage * F420_IN_BYTES;
+                unsigned char *b = smem_dyn + stage * IN_BYTES;
                 tile_info[stage] = make_int4(tx, y0, f, 0);
-                mbar_expect_tx(&full_bar[stage], F420_IN_BYTES);
+                mbar_expect_tx(&full_bar[stage], IN_BYTES);
                 tma_load_3d(b, &map_y, &full_bar[stage], tx * TW, y0, f);
                 if (SRC == F420_PLANAR) {
                     tma_load_3d(b + Y_BYTES, &map_u, &full_bar[stage], tx * (TW / 2), c_lo, f);
@@ -241,7 +247,7 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
     const int r0 = warp * RPW;
     const int g = NARROW ? lane & 15 : lane;               /* 8-pixel column group of this lane */
     const int rb = NARROW ? r0 + 4 * (lane >> 4) : r0;     /* first of this lane's four rows */
-    unsigned char *so_warp = smem_dyn + F420_STAGES * F420_IN_BYTES + r0 * (TW * BPP);
+    unsigned char *so_warp = smem_dyn + F420_STAGES * IN_BYTES + r0 * (TW * BPP);
     unsigned char *so = so_warp + (rb - r0) * (TW * BPP) + g * (8 * BPP);
     /* chroma rows: planar = TW/2-byte U row + TW/2-byte V row (one word each per lane);
      * semi-planar = one TW-byte UV row (two words per lane) */
@@ -250,7 +256,7 @@ sws_fast420_rgb8_kernel(const __grid_constant__ CUtensorMap map_y,
     int i = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
         const int stage = i % F420_STAGES;
-        const unsigned char *sb = smem_dyn + stage * F420_IN_BYTES;
+        const unsigned char *sb = smem_dyn + stage * IN_BYTES;
         mbar_wait(&full_bar[stage], (i / F420_STAGES) & 1);
 
         const int4 ti = tile_info[stage];

@@ -173,7 +173,7 @@ def test_full_chroma_rgb(sf, df, geom, flags):
 
 
 # ---- every instantiation of the same-size 8-bit 4:2:0 kernel (3 chroma layouts x 6 byte orders) ----
-@pytest.mark.parametrize("sf", ["yuv420p", "nv12", "nv21"])
+@pytest.mark.parametrize("sf", ["yuv420p", "nv12", "nv21", "yuv422p", "yuvj422p"])
 @pytest.mark.parametrize("df", ["rgb24", "bgr24", "rgba", "bgra", "argb", "abgr"])
 @pytest.mark.parametrize("geom,flags", [((644, 366), S.SWS_BICUBIC | BX),          # ragged right/bottom tiles
                                         ((640, 200), S.SWS_BICUBIC | BX),          # 128 x 64 tile shape, ragged bottom

@@ -39,6 +39,7 @@ CONFIGS = [
     ("F2 4K yuv444p->bgra bicubic (full chroma)", 3840, 2160, "yuv444p", 3840, 2160, "bgra", S.SWS_BICUBIC | S.BX),
     ("F3 4K rgb24->yuv444p bicubic", 3840, 2160, "rgb24", 3840, 2160, "yuv444p", S.SWS_BICUBIC | S.BX),
     ("F4 4K bgra->yuv444p bicubic", 3840, 2160, "bgra", 3840, 2160, "yuv444p", S.SWS_BICUBIC | S.BX),
+    ("C5j 4K yuvj422p->rgb24 bicubic (MJPEG-style source)", 3840, 2160, "yuvj422p", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
     ("E1 4K rgb24->yuv420p bicubic", 3840, 2160, "rgb24", 3840, 2160, "yuv420p", S.SWS_BICUBIC | S.BX),
     ("E2 4K bgra->1080p nv12 bicubic", 3840, 2160, "bgra", 1920, 1080, "nv12", S.SWS_BICUBIC | S.BX),
     ("E3 4K bgr24->yuv420p default flags (box converter)", 3840, 2160, "bgr24", 3840, 2160, "yuv420p", S.SWS_BICUBIC),
