@@ -46,6 +46,10 @@ enum AVPixelFormat {
     AV_PIX_FMT_ABGR        = 27,
     AV_PIX_FMT_BGRA        = 28,
     AV_PIX_FMT_RGB48LE     = 35,
+    AV_PIX_FMT_RGB565LE    = 37,   /* output only */
+    AV_PIX_FMT_RGB555LE    = 39,   /* output only */
+    AV_PIX_FMT_BGR565LE    = 41,   /* output only */
+    AV_PIX_FMT_BGR555LE    = 43,   /* output only */
     AV_PIX_FMT_YUV420P16LE = 45,
     AV_PIX_FMT_YUV422P16LE = 47,
     AV_PIX_FMT_YUV444P16LE = 49,

@@ -286,6 +286,10 @@ static int dst_kind_of(int fmt, const SwsPixDesc *d)
     case AV_PIX_FMT_ABGR:    return SWSC_DST_ABGR;
     case AV_PIX_FMT_RGB48LE: return SWSC_DST_RGB48;
     case AV_PIX_FMT_BGR48LE: return SWSC_DST_BGR48;
+    case AV_PIX_FMT_RGB565LE: return SWSC_DST_RGB565;
+    case AV_PIX_FMT_BGR565LE: return SWSC_DST_BGR565;
+    case AV_PIX_FMT_RGB555LE: return SWSC_DST_RGB555;
+    case AV_PIX_FMT_BGR555LE: return SWSC_DST_BGR555;
     case AV_PIX_FMT_NV12:    return SWSC_DST_NV12;
     case AV_PIX_FMT_NV21:    return SWSC_DST_NV21;
     case AV_PIX_FMT_P010LE:  return SWSC_DST_P010;
@@ -441,6 +445,20 @@ static int init_single(SwsContext *sws, int with_device)
         if (c->chr_src_hsub == 0 && c->chr_src_vsub == 0 && sws->dither != SWS_DITHER_BAYER &&
             !(flags & SWS_FAST_BILINEAR))                      /* utils.c:1278-1285 */
             flags |= SWS_FULL_CHR_H_INT;
+        sws->flags = flags;
+    }
+    if (is_rgb(sws->dst_format) && dd->bpp <= 16) {
+        /* 15/16 bpp destinations have no full-chroma writer: the reference drops the flag again
+         * (utils.c:1329-1357) and its pair writer then stores one pixel past an odd width */
+        if (dstW & 1) {
+            set_error(c, "odd widths of 15/16 bpp RGB destinations are not on the CUDA hot path");
+            return AVERROR(ENOTSUP);
+        }
+        if (is_rgb(sws->src_format) && srcW == dstW && srcH == dstH) {
+            set_error(c, "unscaled RGB -> 15/16 bpp RGB (rgb24to16 & co.) is not on the CUDA hot path");
+            return AVERROR(ENOTSUP);
+        }
+        flags &= ~SWS_FULL_CHR_H_INT;
         sws->flags = flags;
     }
     if (is_rgb(sws->dst_format) && !(flags & SWS_FULL_CHR_H_INT))

@@ -1028,7 +1028,7 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
         /* packed RGB with full horizontal chroma (odd width / 4:4:4 source): every pixel has its own
          * U,V and the colour step is arithmetic, not LUT based: yuv2rgb_full_{X,1,2}_c_template +
          * yuv2rgb_write_full (output.c:1998-2051,2160-2330), yuv2rgba64_full_X_c_template (:1373-1430) */
-        const bool is16 = kind >= SWSC_DST_RGB48;
+        const bool is16 = kind == SWSC_DST_RGB48 || kind == SWSC_DST_BGR48;
         for (int idx = threadIdx.x; idx < th * TW; idx += blockDim.x) {
             const int ty = idx / TW, x = idx - ty * TW;
             if (x >= tw)
@@ -1097,7 +1097,7 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
     } else if (kind >= SWSC_DST_RGB24) {
         /* packed RGB: one chroma pair per two pixels (output.c:1788-1840 / 1115-1196) */
         const int pw = tw >> 1;                       /* pairs in this tile (dst_w even here) */
-        const bool is16 = kind >= SWSC_DST_RGB48;
+        const bool is16 = kind == SWSC_DST_RGB48 || kind == SWSC_DST_BGR48;
         for (int idx = threadIdx.x; idx < th * (TW >> 1); idx += blockDim.x) {
             const int ty = idx / (TW >> 1), i = idx - ty * (TW >> 1);
             if (i >= pw)
@@ -1145,6 +1145,29 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
                 const int oG = P.rgb.base_g + ((u8 * P.rgb.cgu) >> 16) + ((v8 * P.rgb.cgv) >> 16);
                 const int oB = P.rgb.base_b + ((u8 * P.rgb.cbu) >> 16);
                 const int cy = P.rgb.cy, yb = P.rgb.yb;
+                if (kind >= SWSC_DST_RGB565) {
+                    /* 15/16 bpp: the 2x2 ordered-dither offsets move the LUT index, then the bytes are
+                     * truncated into their fields (output.c:1714-1747; tables yuv2rgb.c:878-900;
+                     * unscaled twin yuv2rgb.c:371-398).  ff_dither_2x2_8 = {6,2 / 0,4}, 2x2_4 = {1,3 / 2,0}. */
+                    const int odd = y & 1;
+                    const bool is565 = kind <= SWSC_DST_BGR565;
+                    const int dr1 = odd ? 0 : 6, dr2 = odd ? 4 : 2;
+                    const int db1 = odd ? 6 : 0, db2 = odd ? 2 : 4;
+                    const int dg1 = is565 ? (odd ? 2 : 1) : dr2, dg2 = is565 ? (odd ? 0 : 3) : dr1;
+                    const int gsh = is565 ? 2 : 3, hi = is565 ? 11 : 10;
+                    const bool rgb = kind == SWSC_DST_RGB565 || kind == SWSC_DST_RGB555;   /* R in the high bits */
+                    const int r1 = clip_u8((yb + (y1v + oR + dr1) * cy) >> 16) >> 3;
+                    const int g1 = clip_u8((yb + (y1v + oG + dg1) * cy) >> 16) >> gsh;
+                    const int b1 = clip_u8((yb + (y1v + oB + db1) * cy) >> 16) >> 3;
+                    const int r2 = clip_u8((yb + (y2v + oR + dr2) * cy) >> 16) >> 3;
+                    const int g2 = clip_u8((yb + (y2v + oG + dg2) * cy) >> 16) >> gsh;
+                    const int b2 = clip_u8((yb + (y2v + oB + db2) * cy) >> 16) >> 3;
+                    const uint32_t p1 = rgb ? (r1 << hi) | (g1 << 5) | b1 : (b1 << hi) | (g1 << 5) | r1;
+                    const uint32_t p2 = rgb ? (r2 << hi) | (g2 << 5) | b2 : (b2 << hi) | (g2 << 5) | r2;
+                    uint16_t *w = reinterpret_cast<uint16_t *>(dst0 + (size_t)y * A.dst_stride[0]) + 2 * ((x0 >> 1) + i);
+                    w[0] = (uint16_t)p1; w[1] = (uint16_t)p2;
+                    continue;
+                }
                 const int r1 = clip_u8((yb + (y1v + oR) * cy) >> 16);
                 const int g1 = clip_u8((yb + (y1v + oG) * cy) >> 16);
                 const int b1 = clip_u8((yb + (y1v + oB) * cy) >> 16);
@@ -3005,6 +3028,8 @@ static int ensure_staging(SwsCudaState *st)
     case SWSC_DST_RGBA: case SWSC_DST_BGRA: case SWSC_DST_ARGB: case SWSC_DST_ABGR:
         st->dst_rowbytes[0] = p->dst_w * 4; break;
     case SWSC_DST_RGB48: case SWSC_DST_BGR48: st->dst_rowbytes[0] = p->dst_w * 6; break;
+    case SWSC_DST_RGB565: case SWSC_DST_BGR565: case SWSC_DST_RGB555: case SWSC_DST_BGR555:
+        st->dst_rowbytes[0] = p->dst_w * 2; break;
     default: {
         const int db = p->dst_bits > 8 ? 2 : 1;
         st->dst_rowbytes[0] = p->dst_w * db;

@@ -107,6 +107,10 @@ enum {
     SWSC_DST_ABGR,
     SWSC_DST_RGB48,
     SWSC_DST_BGR48,
+    SWSC_DST_RGB565,       /* 16 bpp, ordered 2x2 dither (output.c:1714-1747) */
+    SWSC_DST_BGR565,
+    SWSC_DST_RGB555,
+    SWSC_DST_BGR555,
 };
 
 /* unscaled converters the reference installs instead of the scaler (swscale_unscaled.c) */

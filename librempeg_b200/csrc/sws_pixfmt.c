@@ -43,6 +43,11 @@ static const SwsPixDesc table[] = {
     { AV_PIX_FMT_ABGR,    "abgr",    SWSPF_RGB, 8, 0, 0, 32, 1, 0, 1, 1, 0 },
     { AV_PIX_FMT_RGB48LE, "rgb48le", SWSPF_RGB, 16, 0, 0, 48, 1, 0, 0, 1, 0 },
     { AV_PIX_FMT_BGR48LE, "bgr48le", SWSPF_RGB, 16, 0, 0, 48, 1, 0, 0, 1, 0 },
+    /* 16 bpp packed RGB: destinations only (the rgb16/15 readers are not on the CUDA hot path) */
+    { AV_PIX_FMT_RGB565LE, "rgb565le", SWSPF_RGB, 5, 0, 0, 16, 1, 0, 0, 1, 0 },
+    { AV_PIX_FMT_BGR565LE, "bgr565le", SWSPF_RGB, 5, 0, 0, 16, 1, 0, 0, 1, 0 },
+    { AV_PIX_FMT_RGB555LE, "rgb555le", SWSPF_RGB, 5, 0, 0, 15, 1, 0, 0, 1, 0 },
+    { AV_PIX_FMT_BGR555LE, "bgr555le", SWSPF_RGB, 5, 0, 0, 15, 1, 0, 0, 1, 0 },
 };
 
 const SwsPixDesc *ff_b200_pix_desc(int fmt)

@@ -18,6 +18,7 @@ PIX_FMT = {
     "yuv420p": 0, "rgb24": 2, "bgr24": 3, "yuv422p": 4, "yuv444p": 5, "gray": 8,
     "yuvj420p": 12, "yuvj422p": 13, "yuvj444p": 14, "nv12": 23, "nv21": 24,
     "argb": 25, "rgba": 26, "abgr": 27, "bgra": 28, "rgb48le": 35,
+    "rgb565le": 37, "rgb555le": 39, "bgr565le": 41, "bgr555le": 43,
     "yuv420p16le": 45, "yuv422p16le": 47, "yuv444p16le": 49, "bgr48le": 58,
     "yuv420p9le": 60, "yuv420p10le": 62, "yuv422p10le": 64, "yuv444p9le": 66,
     "yuv444p10le": 68, "yuv422p9le": 70, "yuv420p12le": 123, "yuv420p14le": 125,

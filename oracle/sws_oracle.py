@@ -66,6 +66,8 @@ def _fmt(name):
         return ("rgb32", 8, 0, 0)
     if name in ("rgb48le", "bgr48le"):
         return ("rgb16", 16, 0, 0)
+    if name in ("rgb565le", "bgr565le", "rgb555le", "bgr555le"):
+        return ("rgb565", 5, 0, 0)          # 15/16 bpp, destinations only
     if name in ("nv12", "nv21"):
         return ("semi", 8, 1, 1)
     if name == "p010le":
@@ -427,8 +429,8 @@ class OracleContext:
         self.dkind, self.ddepth, dhs, dvs = _fmt(dfmt)
         dst_rgb = self.dkind.startswith("rgb")
         src_rgb = self.skind.startswith("rgb")
-        if self.skind == "rgb16":
-            raise NotImplementedError("16-bit RGB sources are not restated")
+        if self.skind in ("rgb16", "rgb565"):
+            raise NotImplementedError("16-bit and 15/16 bpp RGB sources are not restated")
         # formats that are neither YUV nor gray carry no range, utils.c:844-880
         self.src_range, self.dst_range = (0 if src_rgb else src_range), (0 if dst_rgb else dst_range)
         src_range = self.src_range
@@ -451,6 +453,12 @@ class OracleContext:
         if dst_rgb and not (flags & SWS_FULL_CHR_H_INT):              # :1270-1286
             if dw & 1 or (shs == 0 and svs == 0 and dither != 2 and not flags & SWS_FAST_BILINEAR):
                 flags |= SWS_FULL_CHR_H_INT
+        if self.dkind == "rgb565":                                    # no full-chroma writer, :1329-1357
+            if dw & 1:
+                raise NotImplementedError("odd widths of 15/16 bpp destinations are not restated")
+            if src_rgb and sw == dw and sh == dh:
+                raise NotImplementedError("rgb24to16 & co. are not restated")
+            flags &= ~SWS_FULL_CHR_H_INT
         if dst_rgb and not (flags & SWS_FULL_CHR_H_INT):              # :1359
             dhs = 1
         # packed RGB sources: chroma from summed pixel pairs (the *_half readers), utils.c:1367-1390
@@ -886,6 +894,25 @@ class OracleContext:
         R = t["y_table"][Yp + rep(r_idx)]
         G = t["y_table"][Yp + rep(g_idx)]
         B = t["y_table"][Yp + rep(b_idx)]
+        if self.dkind == "rgb565":
+            # yuv2rgb_write 15/16 bpp (output.c:1714-1747), tables yuv2rgb.c:878-900; the unscaled converters
+            # (yuv2rgb.c:371-398) index the same 2x2 tiles by row and column parity
+            d8 = np.array([[6, 2], [0, 4]], np.int64)                  # ff_dither_2x2_8, output.c:46-50
+            d4 = np.array([[1, 3], [2, 0]], np.int64)                  # ff_dither_2x2_4, output.c:40-44
+            yy = (np.arange(rows) & 1)[:, None]
+            xx = (np.arange(px) & 1)[None, :]
+            is565 = self.dfmt in ("rgb565le", "bgr565le")
+            dr = d8[yy, xx]
+            db = d8[yy ^ 1, xx]
+            dg = d4[yy, xx] if is565 else d8[yy, xx ^ 1]
+            R = t["y_table"][Yp + rep(r_idx) + dr].astype(np.uint16) >> 3
+            G = t["y_table"][Yp + rep(g_idx) + dg].astype(np.uint16) >> (2 if is565 else 3)
+            B = t["y_table"][Yp + rep(b_idx) + db].astype(np.uint16) >> 3
+            hi = 11 if is565 else 10
+            pix = (R << hi) | (G << 5) | B if self.dfmt.startswith("rgb") else (B << hi) | (G << 5) | R
+            out = np.zeros((rows, self.dw), "<u2")
+            out[:, :px] = pix
+            return out.view(np.uint8).reshape(rows, -1)
         order = {"rgb24": (R, G, B), "bgr24": (B, G, R), "rgba": (R, G, B, None), "bgra": (B, G, R, None),
                  "argb": (None, R, G, B), "abgr": (None, B, G, R),
                  "rgb48le": (R, G, B), "bgr48le": (B, G, R)}[self.dfmt]

@@ -121,6 +121,18 @@ def cases():
         out.append(dict(sw=g[0], sh=g[1], sf=sf, dw=g[2], dh=g[3], df=df, flags=R.SWS_BICUBIC | BX))
     out.append(dict(sw=162, sh=122, sf="p010le", dw=200, dh=150, df="yuv420p", flags=R.SWS_BILINEAR | BX,
                     ctx_kwargs=dict(src_range=0, dst_range=1)))
+    # 15/16 bpp packed RGB destinations: 2x2 ordered dither in the pair writer
+    # (output.c:1714-1747) and in the unscaled LUT converters (yuv2rgb.c:371-398)
+    for df in ["rgb565le", "bgr565le", "rgb555le", "bgr555le"]:
+        for sf, g, fl in [("yuv420p", (162, 122, 162, 122), R.SWS_BICUBIC | BX), ("yuv420p", (162, 122, 162, 122), R.SWS_BICUBIC),
+                          ("yuv422p", (162, 122, 162, 122), R.SWS_POINT), ("yuv420p", (162, 122, 200, 150), R.SWS_BICUBIC | BX),
+                          ("yuv444p", (162, 122, 100, 76), R.SWS_BILINEAR | BX), ("nv12", (162, 122, 200, 150), R.SWS_LANCZOS | BX),
+                          ("yuv420p10le", (162, 122, 162, 122), R.SWS_BICUBIC | BX), ("p010le", (162, 122, 100, 76), R.SWS_BILINEAR),
+                          ("rgb24", (162, 122, 200, 150), R.SWS_BICUBIC | BX), ("yuvj420p", (162, 122, 162, 122), R.SWS_POINT | BX),
+                          ("yuv420p", (176, 144, 352, 288), R.SWS_FAST_BILINEAR)]:
+            out.append(dict(sw=g[0], sh=g[1], sf=sf, dw=g[2], dh=g[3], df=df, flags=fl))
+    out.append(dict(sw=160, sh=120, sf="yuv420p", dw=160, dh=120, df="rgb565le", flags=R.SWS_BICUBIC | BX,
+                    colorspace=[1, 1, 1, 0, 0, 1 << 16, 1 << 16]))
     for i, c in enumerate(out):
         c.setdefault("seed", 100 + i)
         c.setdefault("mode", "extreme" if i % 7 == 3 else "noise")

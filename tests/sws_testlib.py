@@ -31,6 +31,8 @@ def plane_layout(fmt, w, h):
         return [(h, w * 4)]
     if fmt in ("rgb48le", "bgr48le"):
         return [(h, w * 6)]
+    if fmt in ("rgb565le", "bgr565le", "rgb555le", "bgr555le"):
+        return [(h, w * 2)]
     if fmt in ("nv12", "nv21"):
         return [(h, w), (cdiv(h, 1), cdiv(w, 1) * 2)]
     if fmt == "p010le":

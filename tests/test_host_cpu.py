@@ -58,6 +58,8 @@ def test_version_and_queries():
     assert L.sws_isSupportedInput(S.PIX_FMT["yuv420p"]) and L.sws_isSupportedOutput(S.PIX_FMT["rgb24"])
     assert L.sws_isSupportedInput(S.PIX_FMT["rgb24"])        # packed 8-bit RGB input
     assert not L.sws_isSupportedInput(S.PIX_FMT["rgb48le"])  # 16-bit RGB is output-only
+    for f in ("rgb565le", "bgr565le", "rgb555le", "bgr555le"):   # 15/16 bpp RGB: output-only
+        assert L.sws_isSupportedOutput(S.PIX_FMT[f]) and not L.sws_isSupportedInput(S.PIX_FMT[f])
     assert L.sws_isSupportedInput(S.PIX_FMT["p010le"]) and L.sws_isSupportedOutput(S.PIX_FMT["p010le"])
     if R.available():                                        # the ABI value of the id, libavutil/pixfmt.h
         assert R.pix_fmt("p010le") == S.PIX_FMT["p010le"]

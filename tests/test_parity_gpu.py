@@ -478,3 +478,29 @@ def test_rgb444_kernel(sf, geom, flags):
     _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df="yuv444p", flags=flags, seed=122, slices=slices)
     _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df="yuv444p", flags=flags, seed=123, colorspace=(1, 0, 1, 0, 0, 1 << 16, 1 << 16))
     _check(sw=w, sh=h, sf=sf, dw=w, dh=h, df="yuvj444p", flags=flags, seed=124)       # range conversion: another kernel
+
+
+# ---- 15/16 bpp packed RGB destinations: 2x2 ordered dither in the pair writer and the unscaled LUT converters ----
+@pytest.mark.parametrize("df", ["rgb565le", "bgr565le", "rgb555le", "bgr555le"])
+@pytest.mark.parametrize("sf,geom,flags", [
+    ("yuv420p", (644, 366, 644, 366), S.SWS_BICUBIC | BX), ("yuv420p", (644, 366, 644, 366), S.SWS_BICUBIC),
+    ("yuv422p", (322, 182, 322, 182), S.SWS_POINT), ("yuv420p", (322, 182, 400, 300), S.SWS_BICUBIC | BX),
+    ("yuv444p", (322, 182, 160, 90), S.SWS_BILINEAR | BX), ("nv12", (322, 182, 400, 300), S.SWS_LANCZOS | BX),
+    ("yuv420p10le", (322, 182, 322, 182), S.SWS_BICUBIC | BX), ("p010le", (322, 182, 160, 90), S.SWS_BILINEAR),
+    ("bgra", (322, 182, 400, 300), S.SWS_BICUBIC | BX), ("yuv420p", (176, 144, 352, 288), S.SWS_FAST_BILINEAR)])
+def test_rgb16bpp_destinations(df, sf, geom, flags):
+    sw, sh, dw, dh = geom
+    for mode in ("noise", "extreme"):
+        _check(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags, seed=131, mode=mode)
+    slices = [(y, min(24, sh - y)) for y in range(0, sh, 24)]
+    _check(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags, seed=132, slices=slices)
+
+
+def test_rgb16bpp_rejections():
+    """Odd widths (the reference's pair writer stores past the row) and the unscaled rgb24to16 family are refused."""
+    for kw in [dict(sw=64, sh=36, sf="yuv420p", dw=63, dh=36, df="rgb565le"),
+               dict(sw=64, sh=36, sf="rgb24", dw=64, dh=36, df="bgr555le")]:
+        with pytest.raises(Exception):
+            S.SwsContext(kw["sw"], kw["sh"], kw["sf"], kw["dw"], kw["dh"], kw["df"], S.SWS_BICUBIC | BX)
+    L = S.lib()
+    assert not L.sws_isSupportedInput(S.PIX_FMT["rgb565le"]) and L.sws_isSupportedOutput(S.PIX_FMT["rgb565le"])
