@@ -248,8 +248,10 @@ int sws_setColorspaceDetails(SwsContext *sws, const int inv_table[4], int srcRan
         memcmp(c->dst_colorspace, c->src_colorspace, sizeof(int) * 4)) {
         /* the reference cascades through an RGB intermediate here (utils.c:915-984) */
         set_error(c, "YUV->YUV with differing matrices is not on the CUDA hot path");
+        c->refused = 1;             /* the plan no longer describes what the reference would compute: scaling fails */
         return -1;
     }
+    c->refused = 0;
     plan_range_convert(c);
     if (plan_colorspace(c) < 0)
         return -1;
@@ -518,24 +520,30 @@ static int init_single(SwsContext *sws, int with_device)
             (sws->dither == SWS_DITHER_BAYER || sws->dither == SWS_DITHER_AUTO) && !(dstH & 1)) {
             c->unscaled_lut = 1;        /* yuv2rgb_c_* nearest-chroma LUT converter (a13) */
             c->dst_slice_align = 2;
+            /* one chroma sample per pixel pair whatever the flags say (an odd width forced SWS_FULL_CHR_H_INT
+             * above; the converter ignores it and leaves the last pixel of the row untouched) */
+            c->chr_dst_hsub = 1;
+            c->chr_dst_w = ceil_rshift(dstW, 1);
         } else if (sws->dst_format == AV_PIX_FMT_P010LE && !(sd->flags & SWSPF_SEMI) && planar_yuv_pair &&
                    sd->log2_cw == 1 && sd->log2_ch == 1 && sd->depth != 9) {
             /* planar8ToP01xleWrapper (8-bit: << 8) and planarToP01xWrapper (10/12/14/16-bit: << 16 - depth),
              * swscale_unscaled.c:273-375,2432-2444 */
             c->special = SWSC_SPECIAL_P01X;
-        } else if (planar_yuv_pair && sd->depth != dd->depth && (sd->flags & SWSPF_SEMI) && (dd->flags & SWSPF_SEMI) &&
-                   sd->swap_uv == dd->swap_uv) {
-            if (sd->depth != 8) {
+        } else if (planar_yuv_pair && (sd->depth != dd->depth || sd->depth > 8) && (sd->flags & SWSPF_SEMI) &&
+                   (dd->flags & SWSPF_SEMI) && sd->swap_uv == dd->swap_uv) {
+            if (sd->depth != 8 && sd->depth != dd->depth) {
                 /* DITHER_COPY's tail loop drops the source shift (swscale_unscaled.c:2174-2176): not restated */
                 set_error(c, "unscaled p010 -> 8-bit semi-planar conversion is not on the CUDA hot path");
                 return AVERROR(ENOTSUP);
             }
             c->special = SWSC_SPECIAL_DEPTHCOPY;       /* nv12 -> p010: COPY816, swscale_unscaled.c:2266-2284 */
         } else if (planar_yuv_pair && c->chr_src_hsub == c->chr_dst_hsub &&
-                   c->chr_src_vsub == c->chr_dst_vsub && sd->depth != dd->depth &&
+                   c->chr_src_vsub == c->chr_dst_vsub && (sd->depth != dd->depth || sd->depth > 8) &&
                    !(sd->flags & SWSPF_SEMI) && !(dd->flags & SWSPF_SEMI)) {
             /* planarCopyWrapper between depths (swscale_unscaled.c:2220-2384): ordered dither down,
-             * bit replication (full-range luma) or plain shift up */
+             * bit replication (full-range luma) or plain shift up.  Equal depths above 8 bits are the same
+             * wrapper with a zero shift: a copy that, like every convert_unscaled hook, stays in place when
+             * sws_setColorspaceDetails() later makes the ranges differ */
             c->special = SWSC_SPECIAL_DEPTHCOPY;
             if (sws->dither != SWS_DITHER_NONE)
                 c->dst_slice_align = 8 << c->chr_dst_vsub;      /* :2694-2696: the dither rows count from the slice */
@@ -870,6 +878,15 @@ int sws_scale(SwsContext *sws, const uint8_t *const srcSlice[], const int srcStr
         set_error(c, "one of the input parameters to sws_scale() is NULL");
         return AVERROR(EINVAL);
     }
+    if (c->refused) {
+        set_error(c, "the last sws_setColorspaceDetails() asked for a conversion that is not on the CUDA hot path");
+        return AVERROR(ENOTSUP);
+    }
+    if ((c->src_bpc > 8 && !is_rgb(sws->src_format) && ((srcStride[0] | srcStride[1] | srcStride[2]) & 1)) ||
+        (c->dst_bpc > 8 && ((dstStride[0] | dstStride[1] | dstStride[2]) & 1))) {
+        set_error(c, "16-bit samples need even strides");
+        return AVERROR(EINVAL);
+    }
     macro_src = 1 << c->chr_src_vsub;
     if ((srcSliceY & (macro_src - 1)) ||
         ((srcSliceH & (macro_src - 1)) && srcSliceY + srcSliceH != sws->src_h) ||
@@ -939,6 +956,10 @@ int sws_cuda_scale_batch(SwsContext *sws, const uint8_t *const src[4], const int
     int ret;
     if (!c || !c->initialized || !src || !dst || nb_frames < 1)
         return AVERROR(EINVAL);
+    if (c->refused) {
+        set_error(c, "the last sws_setColorspaceDetails() asked for a conversion that is not on the CUDA hot path");
+        return AVERROR(ENOTSUP);
+    }
     ret = ff_b200_cuda_launch(c->cuda, src, srcStride, srcFrameStride, dst, dstStride,
                               dstFrameStride, nb_frames, 0, sws->dst_h);
     return ret < 0 ? ret : sws->dst_h;

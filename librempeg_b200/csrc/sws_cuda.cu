@@ -779,29 +779,35 @@ sws_depthcopy_kernel(const __grid_constant__ DepthCopyArgs A)
     }
     if (plane >= A.nplanes)
         return;
+    /* 10..16 -> 8 bit moves 16 samples per thread (two 16-byte loads, one 16-byte store); the others 8 */
+    constexpr int CH = (sizeof(SrcT) == 2 && sizeof(DstT) == 1) ? 16 : 8;
     const unsigned i32 = (unsigned)idx, nch = (unsigned)A.chunks[plane];       /* a plane has < 2^31 chunks */
     const int row = (int)(i32 / nch), c = (int)(i32 - (unsigned)row * nch);
     if (row >= A.rows[plane])
         return;
     const int y = A.y0[plane] + row;
-    const SrcT *s = reinterpret_cast<const SrcT *>(A.src[plane] + blockIdx.z * A.src_fstride[plane] + (size_t)y * A.src_stride[plane]) + 8 * c;
-    DstT *d = reinterpret_cast<DstT *>(A.dst[plane] + blockIdx.z * A.dst_fstride[plane] + (size_t)y * A.dst_stride[plane]) + 8 * c;
-    const int n = min(8, A.w[plane] - 8 * c);
+    const SrcT *s = reinterpret_cast<const SrcT *>(A.src[plane] + blockIdx.z * A.src_fstride[plane] + (size_t)y * A.src_stride[plane]) + CH * c;
+    DstT *d = reinterpret_cast<DstT *>(A.dst[plane] + blockIdx.z * A.dst_fstride[plane] + (size_t)y * A.dst_stride[plane]) + CH * c;
+    const int n = min(CH, A.w[plane] - CH * c);
     const bool shiftonly = plane != 0 || A.luma_shiftonly;
     const int sd = A.src_depth, dd = A.dst_depth;
-    if (sizeof(SrcT) == 2 && sd > dd && sd <= 15 && A.vec && n == 8 && A.src_shift == 0) {
+    if (sizeof(SrcT) == 2 && sd > dd && sd <= 15 && A.vec && n == CH && A.src_shift == 0) {
         /* two samples per 32-bit word: with at most 15 source bits v + dither cannot carry into the upper half,
          * and t - (t >> dst_depth) cannot borrow.  Same numbers as the scalar path below. */
         const int shift = sd - dd;
-        const uint4 q = __ldcs(reinterpret_cast<const uint4 *>(s));
-        const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+        uint32_t w[CH / 2];
+#pragma unroll
+        for (int g = 0; g < CH / 8; g++) {
+            const uint4 q = __ldcs(reinterpret_cast<const uint4 *>(s) + g);
+            w[4 * g] = q.x; w[4 * g + 1] = q.y; w[4 * g + 2] = q.z; w[4 * g + 3] = q.w;
+        }
         const uint2 dq = *reinterpret_cast<const uint2 *>(c_depth_dither[shift - 1][row & 7]);
         const uint32_t half = 0x00010001u;
         const uint32_t hm = (0xFFFFu >> shift) * half;
-        uint32_t r[4];
+        uint32_t r[CH / 2];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t dw = k < 2 ? dq.x : dq.y;
+        for (int k = 0; k < CH / 2; k++) {
+            const uint32_t dw = (k & 3) < 2 ? dq.x : dq.y;
             const uint32_t d2 = A.dither_none ? (1u << (shift - 1)) * half : prmt(dw, 0u, (k & 1) ? 0x4342 : 0x4140);
             if (A.dither_none || shiftonly) {
                 const uint32_t t = ((w[k] + d2) >> shift) & hm;
@@ -812,49 +818,68 @@ sws_depthcopy_kernel(const __grid_constant__ DepthCopyArgs A)
             }
         }
         if (sizeof(DstT) == 1)
-            __stcs(reinterpret_cast<uint2 *>(d), make_uint2(prmt(r[0], r[1], 0x6420), prmt(r[2], r[3], 0x6420)));
+            __stcs(reinterpret_cast<uint4 *>(d), make_uint4(prmt(r[0], r[1], 0x6420), prmt(r[2], r[3], 0x6420),
+                                                            prmt(r[CH / 2 - 4], r[CH / 2 - 3], 0x6420), prmt(r[CH / 2 - 2], r[CH / 2 - 1], 0x6420)));
         else
             __stcs(reinterpret_cast<uint4 *>(d), make_uint4(r[0], r[1], r[2], r[3]));
         return;
     }
-    unsigned v[8], o[8];
-    load8<SrcT>(s, n, A.vec, v);
 #pragma unroll
-    for (int i = 0; i < 8; i++)
-        v[i] >>= A.src_shift;
-    if (sd > dd) {
-        const int shift = sd - dd;
-        const uint2 dq = *reinterpret_cast<const uint2 *>(c_depth_dither[shift - 1][row & 7]);   /* rows count from the slice */
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const unsigned dz = ((i < 4 ? dq.x : dq.y) >> (8 * (i & 3))) & 0xFFu;
-            if (A.dither_none) {
-                const unsigned t = (v[i] + (1u << (shift - 1))) >> shift;
-                o[i] = t - (t >> dd);
-            } else if (shiftonly) {
-                const unsigned t = (v[i] + dz) >> shift;
-                o[i] = t - (t >> dd);
-            } else {
-                o[i] = (v[i] - (v[i] >> dd) + dz) >> shift;
-            }
-        }
-    } else {
-        const int shift = dd - sd, rep = 2 * sd - dd;
+    for (int g = 0; g < CH / 8; g++) {
+        const int ng = min(8, n - 8 * g);
+        if (ng <= 0)
+            break;
+        const SrcT *sg = s + 8 * g;
+        DstT *dg = d + 8 * g;
+        unsigned v[8], o[8];
+        load8<SrcT>(sg, ng, A.vec, v);
 #pragma unroll
         for (int i = 0; i < 8; i++)
-            o[i] = (shiftonly ? v[i] << shift : (v[i] << shift) | (v[i] >> rep)) << A.dst_shift;
-    }
-    if (n == 8 && A.vec) {
-        if (sizeof(DstT) == 1) {
-            __stcs(reinterpret_cast<uint2 *>(d), make_uint2((o[0] & 0xFF) | (o[1] & 0xFF) << 8 | (o[2] & 0xFF) << 16 | o[3] << 24,
-                                                            (o[4] & 0xFF) | (o[5] & 0xFF) << 8 | (o[6] & 0xFF) << 16 | o[7] << 24));
+            v[i] >>= A.src_shift;
+        if (sd > dd) {
+            const int shift = sd - dd;
+            const uint2 dq = *reinterpret_cast<const uint2 *>(c_depth_dither[shift - 1][row & 7]);   /* rows count from the slice */
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const unsigned dz = ((i < 4 ? dq.x : dq.y) >> (8 * (i & 3))) & 0xFFu;
+                if (A.dither_none) {
+                    const unsigned t = (v[i] + (1u << (shift - 1))) >> shift;
+                    o[i] = t - (t >> dd);
+                } else if (shiftonly) {
+                    const unsigned t = (v[i] + dz) >> shift;
+                    o[i] = t - (t >> dd);
+                } else {
+                    o[i] = (v[i] - (v[i] >> dd) + dz) >> shift;
+                }
+            }
         } else {
-            __stcs(reinterpret_cast<uint4 *>(d), make_uint4((o[0] & 0xFFFF) | o[1] << 16, (o[2] & 0xFFFF) | o[3] << 16,
-                                                            (o[4] & 0xFFFF) | o[5] << 16, (o[6] & 0xFFFF) | o[7] << 16));
+            const int shift = dd - sd, rep = 2 * sd - dd;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                o[i] = (shiftonly ? v[i] << shift : (v[i] << shift) | (v[i] >> rep)) << A.dst_shift;
+            if (shiftonly && A.src_shift && sizeof(SrcT) == 2) {
+                /* p010 -> p010: the reference shifts four samples at a time as one 64-bit word
+                 * (swscale_unscaled.c:2291-2296), so only the first of each full group of four loses the
+                 * bits below its sample; the scalar tail clears them for every sample */
+                const int j0 = CH * c + 8 * g, len = A.w[plane];
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (i < ng && (i & 3) && ((j0 + i) & ~3) + 3 < len)
+                        o[i] = (unsigned)sg[i];
+            }
         }
-    } else {
-        for (int i = 0; i < n; i++)
-            d[i] = (DstT)o[i];
+        if (ng == 8 && A.vec) {
+            if (sizeof(DstT) == 1) {
+                __stcs(reinterpret_cast<uint2 *>(dg), make_uint2((o[0] & 0xFF) | (o[1] & 0xFF) << 8 | (o[2] & 0xFF) << 16 | o[3] << 24,
+                                                                 (o[4] & 0xFF) | (o[5] & 0xFF) << 8 | (o[6] & 0xFF) << 16 | o[7] << 24));
+            } else {
+                __stcs(reinterpret_cast<uint4 *>(dg), make_uint4((o[0] & 0xFFFF) | o[1] << 16, (o[2] & 0xFFFF) | o[3] << 16,
+                                                                 (o[4] & 0xFFFF) | o[5] << 16, (o[6] & 0xFFFF) | o[7] << 16));
+            }
+        } else {
+            for (int i = 0; i < ng; i++)
+                dg[i] = (DstT)o[i];
+        }
     }
 }
 
@@ -1081,8 +1106,14 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
                 }
             } else {
                 int Yi = ((int)(Yv - 0x40000000u) >> 14) + 0x10000;
-                const int Ui = (int)(U - (128u << 23)) >> 14;
-                const int Vi = (int)(V - (128u << 23)) >> 14;
+                int Ui = (int)(U - (128u << 23)) >> 14;
+                int Vi = (int)(V - (128u << 23)) >> 14;
+                if (lfs == 1 && cfs == 2 && cf[0] + cf[1] == 4096 && cf[1] > 0 && cf[1] <= 4096) {
+                    /* yuv2rgba64_full_1_c_template with uvalpha != 0 keeps U and V unsigned: its >> 14 is a
+                     * logical shift (output.c:1537-1545; chooser vscale.c:138-143) */
+                    Ui = (int)((U - (128u << 23)) >> 14);
+                    Vi = (int)((V - (128u << 23)) >> 14);
+                }
                 const unsigned Yu = (unsigned)(Yi - P.rgb.y_offset) * (unsigned)P.rgb.y_coeff + (1u << 13) - (1u << 29);
                 const unsigned R = (unsigned)Vi * (unsigned)P.rgb.v2r;
                 const unsigned G = (unsigned)Vi * (unsigned)P.rgb.v2g + (unsigned)Ui * (unsigned)P.rgb.u2g;
@@ -1582,6 +1613,8 @@ static int fast420_setup(SwsCudaState *st, const SwsFirBank *vc)
         return 0;
     if ((p->dst_kind == SWSC_DST_RGB24 || p->dst_kind == SWSC_DST_BGR24) && (p->dst_w & 3))
         return 0;                     /* the store tensor map counts 32-bit words */
+    if (p->unscaled_lut && (p->dst_w & 1))
+        return 0;                     /* the LUT converters leave the last pixel of an odd row untouched */
     /* staged chroma rows per tile: 20 (36 for the narrow shape) cover vertically subsampled chroma; 4:2:2 sources
      * need one chroma row per luma row, TH + 4 (a separate instantiation of the wide shape) */
     int fits = 0, ret;
@@ -2420,7 +2453,7 @@ static int tile15_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
 {
     const SwsCudaPlan *p = &st->plan;
     st->t15_ok = 0;
-    if (p->inter_bits != 15 || p->full_chr || p->special || !p->has_chroma)
+    if (p->inter_bits != 15 || p->full_chr || p->special || !p->has_chroma || (p->unscaled_lut && (p->dst_w & 1)))
         return 0;
     int outk;
     if (p->dst_kind == SWSC_DST_PLANAR8 || p->dst_kind == SWSC_DST_NV12 || p->dst_kind == SWSC_DST_NV21)
@@ -2823,7 +2856,8 @@ static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const i
             a.y0[i] = i ? (y0 + (1 << p->chr_dst_vsub) - 1) >> p->chr_dst_vsub : y0;       /* AV_CEIL_RSHIFT, :2229-2230 */
             const int yend = i ? (y1 == p->dst_h ? p->chr_dst_h : (y1 + (1 << p->chr_dst_vsub) - 1) >> p->chr_dst_vsub) : y1;
             a.rows[i] = yend - a.y0[i];
-            a.chunks[i] = (a.w[i] + 7) / 8;
+            const int ch = p->src_bits > 8 && p->dst_bits == 8 ? 16 : 8;      /* samples per thread, as in the kernel */
+            a.chunks[i] = (a.w[i] + ch - 1) / ch;
             const long long work = (long long)a.chunks[i] * a.rows[i];
             if (work > mx) mx = work;
         }

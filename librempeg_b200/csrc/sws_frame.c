@@ -309,6 +309,8 @@ int sws_receive_slice(SwsContext *ctx, unsigned int slice_start, unsigned int sl
     int ret;
     if (!c || !c->initialized || !c->frame_src)
         return AVERROR(EINVAL);
+    if (c->refused)
+        return AVERROR(ENOTSUP);
     if (c->frame_rows_sent < ctx->src_h)
         return AVERROR(EAGAIN);                 /* wait until the whole input was signalled */
     if (slice_start + slice_height > (unsigned)ctx->dst_h)

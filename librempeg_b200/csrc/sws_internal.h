@@ -190,6 +190,7 @@ const char *ff_b200_cuda_kernel_name(SwsCudaState *st);
 typedef struct SwsInternal {
     SwsContext opts;                 /* must be first (reference swscale_internal.h:79-82) */
     int initialized;
+    int refused;                     /* a post-init option change was refused: scaling fails until it is undone */
     int planned;                     /* tables built by sws_b200_plan_only() (no device) */
     int src_colorspace[4], dst_colorspace[4];
     int brightness, contrast, saturation;

@@ -509,8 +509,9 @@ class OracleContext:
                 return
             if (not dst_rgb and self.skind in ("planar", "semi") and self.dkind in ("planar", "semi")
                     and (shs, svs) == (dhs, dvs) and (self.skind == "semi") == (self.dkind == "semi")
-                    and self.sdepth != self.ddepth):
-                if self.skind == "semi" and (self.sdepth != 8 or (sfmt == "nv21") != (dfmt == "nv21")):
+                    and (self.sdepth != self.ddepth or self.sdepth > 8)):
+                if self.skind == "semi" and ((self.sdepth != 8 and self.sdepth != self.ddepth)
+                                             or (sfmt == "nv21") != (dfmt == "nv21")):
                     raise NotImplementedError("p010 -> 8-bit semi-planar copies are not restated")
                 self.special = "depthcopy"                             # planarCopyWrapper, swscale_unscaled.c:2220-2384
                 self.dither = dither
@@ -731,7 +732,15 @@ class OracleContext:
                     o = (v - (v >> dd) + d) >> shift
             else:
                 shift = dd - sd
+                src_shift = 6 if self.sfmt == "p010le" else 0
+                raw, v = v, v >> src_shift
                 o = (v << shift if shiftonly else (v << shift) | (v >> (2 * sd - dd))) << dst_shift
+                if shiftonly and src_shift:
+                    # the 64-bit fast loop (swscale_unscaled.c:2291-2296) shifts four samples as one word: only
+                    # the first sample of every full group of four loses its low bits
+                    j = np.arange(w)[None, :]
+                    keep = ((j & 3) != 0) & ((j & ~3) + 3 < w)
+                    o = np.where(keep, raw, o)
             out.append(o.astype(np.uint8) if dd == 8 else o.astype("<u2").view(np.uint8))
         return out
 
@@ -788,8 +797,17 @@ class OracleContext:
         V = self._vsum(hv, self.v_chr, n)[:, :w]
         if self.dkind == "rgb16":
             Y = (_wrap32(Y - 0x40000000) >> 14) + 0x10000
-            U = _wrap32(U - (128 << 23)) >> 14
-            V = _wrap32(V - (128 << 23)) >> 14
+            U = _wrap32(U - (128 << 23))
+            V = _wrap32(V - (128 << 23))
+            if lcoef.shape[1] == 1 and ccoef.shape[1] == 2:
+                # yuv2rgba64_full_1_c_template with uvalpha != 0 (output.c:1537-1545) keeps U and V in SUINT, so its
+                # >> 14 is a LOGICAL shift: chroma below 128 wraps.  Rows the chooser (vscale.c:138-143) sends there:
+                c0, c1 = ccoef[:n, 0].astype(np.int64), ccoef[:n, 1].astype(np.int64)
+                quirk = ((c0 + c1 == 4096) & (c1 > 0) & (c1 <= 4096))[:, None]
+                U = np.where(quirk, _wrap32((U & 0xFFFFFFFF) >> 14), U >> 14)
+                V = np.where(quirk, _wrap32((V & 0xFFFFFFFF) >> 14), V >> 14)
+            else:
+                U, V = U >> 14, V >> 14
             Y = _wrap32(_wrap32((Y - t["y_offset"]) * t["y_coeff"]) + (1 << 13) - (1 << 29))
             R = _wrap32(V * t["v2r"]); G = _wrap32(V * t["v2g"] + U * t["u2g"]); B = _wrap32(U * t["u2b"])
             comp = lambda c: np.clip((_wrap32(c + Y) >> 14) + (1 << 15), 0, 65535).astype("<u2")

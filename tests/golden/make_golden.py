@@ -133,6 +133,22 @@ def cases():
             out.append(dict(sw=g[0], sh=g[1], sf=sf, dw=g[2], dh=g[3], df=df, flags=fl))
     out.append(dict(sw=160, sh=120, sf="yuv420p", dw=160, dh=120, df="rgb565le", flags=R.SWS_BICUBIC | BX,
                     colorspace=[1, 1, 1, 0, 0, 1 << 16, 1 << 16]))
+    # found by tools/fuzz_parity.py: the unscaled LUT converter on an odd width (last pixel untouched), the logical
+    # shift of yuv2rgba64_full_1_c_template (1 luma tap, 2 chroma taps, 16-bit full-chroma RGB), same-depth copies
+    # (p010 -> p010 keeps the low bits of three samples out of four; a range change after init keeps the copy)
+    out.append(dict(sw=391, sh=16, sf="yuv420p", dw=391, dh=16, df="abgr", flags=R.SWS_BILINEAR | R.SWS_FULL_CHR_H_INT))
+    out.append(dict(sw=163, sh=62, sf="yuv422p", dw=163, dh=62, df="rgb24", flags=R.SWS_POINT))
+    out.append(dict(sw=163, sh=61, sf="yuv420p14le", dw=163, dh=61, df="rgb48le", flags=R.SWS_AREA))
+    out.append(dict(sw=163, sh=61, sf="yuv420p", dw=163, dh=61, df="bgr48le", flags=R.SWS_BILINEAR | BX))
+    out.append(dict(sw=162, sh=61, sf="yuv420p10le", dw=162, dh=61, df="rgb48le", flags=R.SWS_FAST_BILINEAR | R.SWS_FULL_CHR_H_INT))
+    out.append(dict(sw=117, sh=57, sf="p010le", dw=117, dh=57, df="p010le", flags=R.SWS_POINT, mode="extreme"))
+    out.append(dict(sw=118, sh=57, sf="p010le", dw=118, dh=57, df="p010le", flags=R.SWS_BICUBIC | BX, mode="noise",
+                    ctx_kwargs=dict(src_range=1, dst_range=1)))
+    out.append(dict(sw=163, sh=61, sf="yuv420p12le", dw=163, dh=61, df="yuv420p12le", flags=R.SWS_BILINEAR,
+                    colorspace=[5, 0, 5, 1, 0, 1 << 16, 1 << 16]))
+    out.append(dict(sw=163, sh=61, sf="yuv444p16le", dw=163, dh=61, df="yuv444p16le", flags=R.SWS_BICUBIC | BX,
+                    colorspace=[5, 1, 5, 0, 0, 1 << 16, 1 << 16]))
+    out.append(dict(sw=163, sh=61, sf="yuv422p10le", dw=163, dh=61, df="yuv422p10le", flags=R.SWS_BICUBIC | BX))
     for i, c in enumerate(out):
         c.setdefault("seed", 100 + i)
         c.setdefault("mode", "extreme" if i % 7 == 3 else "noise")

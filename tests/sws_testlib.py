@@ -137,8 +137,10 @@ def run_cuda(sw, sh, sf, dw, dh, df, flags, src, dst_pad=0, param=None, ctx_kwar
              colorspace=None, slices=None):
     kw = dict(ctx_kwargs or {})
     c = S.SwsContext(sw, sh, sf, dw, dh, df, flags, param=param, **kw)
-    if colorspace:
-        c.set_colorspace(*colorspace)
+    if colorspace and c.set_colorspace(*colorspace) < 0:
+        err = c.last_error
+        c.close()
+        raise NotImplementedError("sws_setColorspaceDetails refused: %s" % err)
     dst = Frame(df, dw, dh, pad=dst_pad, fill=0)
     _drive(c, src, dst, sh, slices)
     name = c.kernel_name

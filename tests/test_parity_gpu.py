@@ -504,3 +504,15 @@ def test_rgb16bpp_rejections():
             S.SwsContext(kw["sw"], kw["sh"], kw["sf"], kw["dw"], kw["dh"], kw["df"], S.SWS_BICUBIC | BX)
     L = S.lib()
     assert not L.sws_isSupportedInput(S.PIX_FMT["rgb565le"]) and L.sws_isSupportedOutput(S.PIX_FMT["rgb565le"])
+
+
+def test_fuzz_differential_smoke():
+    """A fixed-seed slice of tools/fuzz_parity.py (random formats, sizes, scalers, flags, ranges, strides) against the
+    real reference, in a subprocess: the full tool found the odd-width LUT, full_1 and same-depth copy cases above."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "--seed", "11", "--cases", "600",
+                        "--seconds", "60", "--no-slices"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert "0 mismatches" in r.stdout, r.stdout[-3000:]

@@ -67,7 +67,7 @@ def main():
     except Exception:
         pass
     for (name, sw, sh, sf, dw, dh, df, flags) in CONFIGS:
-        if args.only and args.only not in name:
+        if args.only and not any(name.split()[0] == k or (len(k) > 3 and k in name) for k in args.only.split(",")):
             continue
         ctx = S.SwsContext(sw, sh, sf, dw, dh, df, flags)
         sl, dl = T.plane_layout(sf, sw, sh), T.plane_layout(df, dw, dh)

@@ -1,0 +1,127 @@
+#!/usr/bin/env python3
+"""Randomised differential test: the CUDA path (through the C ABI) against the real reference build
+(oracle/_ref/libswsref.so) on random formats, sizes, scalers, flags, ranges, strides and slicings.
+
+    python tools/fuzz_parity.py [--cases 3000] [--seed 1] [--seconds 150]
+
+A case the CUDA path refuses at init (ENOTSUP, documented in DESIGN.md section 7) or the reference refuses
+counts as skipped.  Every mismatch is printed as a dict that can be pasted into tests/test_parity_gpu.py.
+Exit status 1 if anything differed.
+"""
+import argparse
+import os
+import random
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from librempeg_b200 import swscale as S  # noqa: E402
+from tests import sws_testlib as T       # noqa: E402
+
+SRC = ["yuv420p", "yuv422p", "yuv444p", "yuvj420p", "yuvj422p", "yuvj444p", "nv12", "nv21", "p010le",
+       "yuv420p9le", "yuv420p10le", "yuv422p10le", "yuv444p10le", "yuv420p12le", "yuv422p12le", "yuv444p12le",
+       "yuv420p14le", "yuv420p16le", "yuv422p16le", "yuv444p16le", "rgb24", "bgr24", "rgba", "bgra", "argb", "abgr"]
+DST = SRC + ["rgb48le", "bgr48le", "rgb565le", "bgr565le", "rgb555le", "bgr555le"]
+SCALERS = [S.SWS_FAST_BILINEAR, S.SWS_BILINEAR, S.SWS_BICUBIC, S.SWS_X, S.SWS_POINT, S.SWS_AREA, S.SWS_BICUBLIN,
+           S.SWS_GAUSS, S.SWS_SINC, S.SWS_LANCZOS, S.SWS_SPLINE]
+
+
+def rand_dim(rng):
+    r = rng.random()
+    if r < 0.15:
+        return rng.randint(1, 16)
+    if r < 0.75:
+        return rng.randint(17, 400)
+    return rng.choice([128, 256, 320, 352, 512, 640, 644, 720, 1280]) + rng.choice([0, 0, 0, 1, 2, -2, 4])
+
+
+def make_case(rng):
+    sw, sh = rand_dim(rng), rand_dim(rng)
+    r = rng.random()
+    if r < 0.35:
+        dw, dh = sw, sh
+    elif r < 0.45:
+        dw, dh = sw, rand_dim(rng)
+    elif r < 0.55:
+        dw, dh = rand_dim(rng), sh
+    else:
+        dw, dh = rand_dim(rng), rand_dim(rng)
+    # keep the filters within what one context serves (no cascades): ratio <= 12 either way
+    dw = min(max(dw, (sw + 11) // 12), sw * 12)
+    dh = min(max(dh, (sh + 11) // 12), sh * 12)
+    flags = rng.choice(SCALERS)
+    r = rng.random()
+    if r < 0.55:
+        flags |= S.BX
+    elif r < 0.65:
+        flags |= S.SWS_ACCURATE_RND
+    elif r < 0.75:
+        flags |= S.SWS_BITEXACT
+    if rng.random() < 0.12:
+        flags |= S.SWS_FULL_CHR_H_INT
+    if rng.random() < 0.08:
+        flags |= S.SWS_FULL_CHR_H_INP
+    case = dict(sw=sw, sh=sh, sf=rng.choice(SRC), dw=dw, dh=dh, df=rng.choice(DST), flags=flags,
+                seed=rng.randint(1, 10 ** 6), mode=rng.choice(["noise", "noise", "smooth", "extreme"]))
+    if rng.random() < 0.2:
+        case["ctx_kwargs"] = dict(src_range=rng.randint(0, 1), dst_range=rng.randint(0, 1))
+    if rng.random() < 0.1:
+        cs = rng.choice([1, 5, 7, 9])
+        case["colorspace"] = (cs, rng.randint(0, 1), rng.choice([cs, 5]), rng.randint(0, 1), 0, 1 << 16, 1 << 16)
+    if rng.random() < 0.25:
+        # 16-bit samples need even strides (the reference reads them through uint16_t pointers)
+        case["src_pad"] = rng.choice([0, 1, 3, 16, 64] if T.depth_of(case["sf"]) == 8 else [0, 2, 6, 16, 64])
+        case["dst_pad"] = rng.choice([0, 1, 5, 16, 64] if T.depth_of(case["df"]) == 8 and "48" not in case["df"]
+                                     and "5le" not in case["df"] else [0, 2, 6, 16, 64])
+    return case
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", type=int, default=3000)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--seconds", type=float, default=150.0)
+    ap.add_argument("--start", type=int, default=0, help="skip the first N cases (resume after a reference abort)")
+    ap.add_argument("--no-slices", action="store_true")
+    ap.add_argument("--cursor", default="", help="file that receives the index of the case being run")
+    args = ap.parse_args()
+    rng = random.Random(args.seed)
+    t0 = time.time()
+    ran = skipped = bad = 0
+    kernels = {}
+    for i in range(args.cases):
+        if time.time() - t0 > args.seconds:
+            break
+        case = make_case(rng)
+        # (the reference asserts, swscale.c:474, when slices meet a strong vertical downscale: stay below 4x)
+        if rng.random() < 0.2 and case["sh"] >= 8 and case["sh"] <= 4 * case["dh"] and not args.no_slices:
+            # top-down slices; chroma rows stay aligned (multiples of 2 rows except the last)
+            step = 2 * rng.randint(1, max(1, case["sh"] // 4))
+            case["slices"] = [(y, min(step, case["sh"] - y)) for y in range(0, case["sh"], step)]
+        if i < args.start:
+            continue
+        if args.cursor:
+            with open(args.cursor, "w") as f:
+                f.write("%d %r\n" % (i, case))
+        try:
+            got, want, name = T.run_case_both(**case)
+        except Exception as e:  # refused at init by either side
+            skipped += 1
+            if "--verbose" in sys.argv:
+                print("skip", case, repr(e)[:100])
+            continue
+        ran += 1
+        kernels[name] = kernels.get(name, 0) + 1
+        diff = T.first_diff(got, want)
+        if diff is not None:
+            bad += 1
+            print("MISMATCH via %s: %r\n    %s" % (name, case, diff), flush=True)
+    print("fuzz: seed %d cases %d..%d: %d compared, %d refused, %d mismatches in %.0f s; kernels %s"
+          % (args.seed, args.start, i, ran, skipped, bad, time.time() - t0, dict(sorted(kernels.items()))))
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
