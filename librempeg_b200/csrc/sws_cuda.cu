@@ -1446,17 +1446,20 @@ static int plan_tiles(SwsCudaState *st)
     int tw = 128;
     while (tw > 32 && tw / 2 >= p->dst_w)
         tw /= 2;
-    for (int th = 32; th >= (1 << vs); th >>= 1) {
-        int rl = max_rows_needed(st->h_vl_pos, p->vl_size, p->dst_h, th);
-        int cth = th >> vs ? th >> vs : 1;
-        int rc = max_rows_needed(st->h_vc_pos, p->vc_size, p->chr_dst_h, cth);
-        size_t need = ((size_t)rl * tw + 2 * (size_t)rc * (tw >> hs)) * isz;
-        if (need <= budget || th == (1 << vs)) {
-            if (need > 200 * 1024)
-                return AVERROR(ENOTSUP);
-            st->tile_w = tw; st->tile_h = th; st->rows_l_cap = rl; st->rows_c_cap = rc;
-            st->smem_bytes = need;
-            return 0;
+    /* very long vertical filters (strong downscales into 19-bit lines) trade tile width for rows */
+    for (; tw >= 32; tw >>= 1) {
+        for (int th = 32; th >= (1 << vs); th >>= 1) {
+            int rl = max_rows_needed(st->h_vl_pos, p->vl_size, p->dst_h, th);
+            int cth = th >> vs ? th >> vs : 1;
+            int rc = max_rows_needed(st->h_vc_pos, p->vc_size, p->chr_dst_h, cth);
+            size_t need = ((size_t)rl * tw + 2 * (size_t)rc * (tw >> hs)) * isz;
+            if (need <= budget || th == (1 << vs)) {
+                if (need > 200 * 1024)
+                    break;
+                st->tile_w = tw; st->tile_h = th; st->rows_l_cap = rl; st->rows_c_cap = rc;
+                st->smem_bytes = need;
+                return 0;
+            }
         }
     }
     return AVERROR(ENOTSUP);

@@ -509,6 +509,7 @@ def test_rgb16bpp_rejections():
 def test_fuzz_differential_smoke():
     """A fixed-seed slice of tools/fuzz_parity.py (random formats, sizes, scalers, flags, ranges, strides) against the
     real reference, in a subprocess: the full tool found the odd-width LUT, full_1 and same-depth copy cases above."""
+    import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -516,3 +517,10 @@ def test_fuzz_differential_smoke():
                         "--seconds", "60", "--no-slices"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     assert "0 mismatches" in r.stdout, r.stdout[-3000:]
+
+
+@pytest.mark.parametrize("df", ["yuv420p16le", "rgb48le", "yuv444p"])
+def test_very_long_vertical_filter(df):
+    """12x vertical sinc downscale: ~240 vertical taps; the generic kernel narrows its tile to keep the rows in shared memory."""
+    _check(sw=200, sh=1200, sf="yuv420p", dw=200, dh=100, df=df, flags=S.SWS_SINC | BX, seed=141)
+    _check(sw=322, sh=1100, sf="yuv420p10le", dw=322, dh=92, df=df, flags=S.SWS_SINC | BX, seed=142, mode="extreme")
