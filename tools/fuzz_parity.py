@@ -121,6 +121,39 @@ def make_case(rng):
     return case
 
 
+def check_batch(case, frames=3):
+    """The device-resident batched entry point (sws_cuda_scale_batch, frames strided in HBM) against the host
+    path of the same context, which the caller has just compared with the reference.  Returns a diff string or None."""
+    import numpy as np
+    import torch
+    dev = torch.device("cuda", 0)
+    kw = dict(case.get("ctx_kwargs") or {})
+    c = S.SwsContext(case["sw"], case["sh"], case["sf"], case["dw"], case["dh"], case["df"], case["flags"], **kw)
+    try:
+        if case.get("colorspace") and c.set_colorspace(*case["colorspace"]) < 0:
+            return None
+        srcs = [T.Frame(case["sf"], case["sw"], case["sh"], pad=case.get("src_pad", 0)).randomize(case["seed"] + 7 * f, case["mode"])
+                for f in range(frames)]
+        d0 = T.Frame(case["df"], case["dw"], case["dh"], pad=case.get("dst_pad", 0), fill=0)
+        st = [torch.from_numpy(np.stack([s.planes[i].reshape(-1) for s in srcs])).to(dev) for i in range(len(srcs[0].planes))]
+        dt = [torch.zeros((frames, a.size), dtype=torch.uint8, device=dev) for a in d0.planes]
+        torch.cuda.synchronize()
+        r = c.scale_batch_device(st, srcs[0].strides, [a.size for a in srcs[0].planes], dt, d0.strides,
+                                 [a.size for a in d0.planes], frames)
+        if r != case["dh"] or c.sync() != 0:
+            return "sws_cuda_scale_batch returned %d: %s" % (r, c.last_error)
+        for f in range(frames):
+            want = T.Frame(case["df"], case["dw"], case["dh"], pad=case.get("dst_pad", 0), fill=0)
+            assert c.scale(srcs[f].planes, srcs[f].strides, want.planes, want.strides, 0, case["sh"]) == case["dh"]
+            got = [t[f].cpu().numpy().reshape(a.shape)[:, :rb] for t, a, (rows, rb) in zip(dt, d0.planes, d0.layout)]
+            diff = T.first_diff(got, want.valid())
+            if diff is not None:
+                return "frame %d of the batch: %s" % (f, diff)
+        return None
+    finally:
+        c.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=3000)
@@ -128,11 +161,12 @@ def main():
     ap.add_argument("--seconds", type=float, default=150.0)
     ap.add_argument("--start", type=int, default=0, help="skip the first N cases (resume after a reference abort)")
     ap.add_argument("--no-slices", action="store_true")
+    ap.add_argument("--batch-prob", type=float, default=0.2, help="share of cases also run as a 3-frame device batch")
     ap.add_argument("--cursor", default="", help="file that receives the index of the case being run")
     args = ap.parse_args()
     rng = random.Random(args.seed)
     t0 = time.time()
-    ran = skipped = bad = 0
+    ran = skipped = bad = batches = 0
     kernels = {}
     reasons = {}
     for i in range(args.cases):
@@ -164,8 +198,14 @@ def main():
         if diff is not None:
             bad += 1
             print("MISMATCH via %s: %r\n    %s" % (name, case, diff), flush=True)
-    print("fuzz: seed %d cases %d..%d: %d compared, %d refused, %d mismatches in %.0f s; kernels %s"
-          % (args.seed, args.start, i, ran, skipped, bad, time.time() - t0, dict(sorted(kernels.items()))))
+        elif rng.random() < args.batch_prob and "slices" not in case:
+            bdiff = check_batch(case)
+            batches += 1
+            if bdiff is not None:
+                bad += 1
+                print("MISMATCH (device batch) via %s: %r\n    %s" % (name, case, bdiff), flush=True)
+    print("fuzz: seed %d cases %d..%d: %d compared (+%d as device batches), %d refused, %d mismatches in %.0f s; kernels %s"
+          % (args.seed, args.start, i, ran, batches, skipped, bad, time.time() - t0, dict(sorted(kernels.items()))))
     for why, n in sorted(reasons.items(), key=lambda kv: -kv[1]):
         print("  refused %5d x %s" % (n, why))
     return 1 if bad else 0
