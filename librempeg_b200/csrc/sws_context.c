@@ -451,11 +451,8 @@ static int init_single(SwsContext *sws, int with_device)
     }
     if (is_rgb(sws->dst_format) && dd->bpp <= 16) {
         /* 15/16 bpp destinations have no full-chroma writer: the reference drops the flag again
-         * (utils.c:1329-1357) and its pair writer then stores one pixel past an odd width */
-        if (dstW & 1) {
-            set_error(c, "odd widths of 15/16 bpp RGB destinations are not on the CUDA hot path");
-            return AVERROR(ENOTSUP);
-        }
+         * (utils.c:1329-1357).  Its pair writer then stores one pixel past an odd width (into the row
+         * padding); the kernel stops at the last valid pixel */
         if (is_rgb(sws->src_format) && srcW == dstW && srcH == dstH) {
             set_error(c, "unscaled RGB -> 15/16 bpp RGB (rgb24to16 & co.) is not on the CUDA hot path");
             return AVERROR(ENOTSUP);

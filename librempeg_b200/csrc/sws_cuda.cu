@@ -1127,7 +1127,9 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
         }
     } else if (kind >= SWSC_DST_RGB24) {
         /* packed RGB: one chroma pair per two pixels (output.c:1788-1840 / 1115-1196) */
-        const int pw = tw >> 1;                       /* pairs in this tile (dst_w even here) */
+        /* pairs in this tile; widths are even here except for 15/16 bpp destinations (no full-chroma writer), whose
+         * last pair keeps only its first pixel, and the unscaled LUT converters, which leave the odd pixel alone */
+        const int pw = (tw + (kind >= SWSC_DST_RGB565 && !P.unscaled_lut ? 1 : 0)) >> 1;
         const bool is16 = kind == SWSC_DST_RGB48 || kind == SWSC_DST_BGR48;
         for (int idx = threadIdx.x; idx < th * (TW >> 1); idx += blockDim.x) {
             const int ty = idx / (TW >> 1), i = idx - ty * (TW >> 1);
@@ -1196,7 +1198,9 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
                     const uint32_t p1 = rgb ? (r1 << hi) | (g1 << 5) | b1 : (b1 << hi) | (g1 << 5) | r1;
                     const uint32_t p2 = rgb ? (r2 << hi) | (g2 << 5) | b2 : (b2 << hi) | (g2 << 5) | r2;
                     uint16_t *w = reinterpret_cast<uint16_t *>(dst0 + (size_t)y * A.dst_stride[0]) + 2 * ((x0 >> 1) + i);
-                    w[0] = (uint16_t)p1; w[1] = (uint16_t)p2;
+                    w[0] = (uint16_t)p1;
+                    if (2 * i + 1 < tw)
+                        w[1] = (uint16_t)p2;
                     continue;
                 }
                 const int r1 = clip_u8((yb + (y1v + oR) * cy) >> 16);

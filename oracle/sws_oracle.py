@@ -454,8 +454,6 @@ class OracleContext:
             if dw & 1 or (shs == 0 and svs == 0 and dither != 2 and not flags & SWS_FAST_BILINEAR):
                 flags |= SWS_FULL_CHR_H_INT
         if self.dkind == "rgb565":                                    # no full-chroma writer, :1329-1357
-            if dw & 1:
-                raise NotImplementedError("odd widths of 15/16 bpp destinations are not restated")
             if src_rgb and sw == dw and sh == dh:
                 raise NotImplementedError("rgb24to16 & co. are not restated")
             flags &= ~SWS_FULL_CHR_H_INT
@@ -906,7 +904,7 @@ class OracleContext:
         g_idx = t["gU"][U + 512] + t["gV"][V + 512]
         b_idx = t["bU"][U + 512]
         rows = Y.shape[0]
-        px = pairs * 2
+        px = min(pairs * 2, self.dw)       # 15/16 bpp, odd width: the second pixel of the last pair falls off the row
         Yp = Y[:, :px]
         rep = lambda a: np.repeat(a, 2, axis=1)[:, :px]
         R = t["y_table"][Yp + rep(r_idx)]

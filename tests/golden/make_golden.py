@@ -149,6 +149,10 @@ def cases():
     out.append(dict(sw=163, sh=61, sf="yuv444p16le", dw=163, dh=61, df="yuv444p16le", flags=R.SWS_BICUBIC | BX,
                     colorspace=[5, 1, 5, 0, 0, 1 << 16, 1 << 16]))
     out.append(dict(sw=163, sh=61, sf="yuv422p10le", dw=163, dh=61, df="yuv422p10le", flags=R.SWS_BICUBIC | BX))
+    for df in ["rgb565le", "bgr555le"]:       # odd widths of 15/16 bpp destinations: pair writer, last pair of one pixel
+        out.append(dict(sw=162, sh=122, sf="yuv420p", dw=161, dh=122, df=df, flags=R.SWS_BICUBIC | BX))
+        out.append(dict(sw=163, sh=122, sf="yuv420p", dw=163, dh=122, df=df, flags=R.SWS_BICUBIC))
+        out.append(dict(sw=81, sh=61, sf="yuv444p", dw=201, dh=151, df=df, flags=R.SWS_BILINEAR | BX))
     for i, c in enumerate(out):
         c.setdefault("seed", 100 + i)
         c.setdefault("mode", "extreme" if i % 7 == 3 else "noise")

@@ -497,9 +497,8 @@ def test_rgb16bpp_destinations(df, sf, geom, flags):
 
 
 def test_rgb16bpp_rejections():
-    """Odd widths (the reference's pair writer stores past the row) and the unscaled rgb24to16 family are refused."""
-    for kw in [dict(sw=64, sh=36, sf="yuv420p", dw=63, dh=36, df="rgb565le"),
-               dict(sw=64, sh=36, sf="rgb24", dw=64, dh=36, df="bgr555le")]:
+    """The unscaled rgb24to16 family is refused."""
+    for kw in [dict(sw=64, sh=36, sf="rgb24", dw=64, dh=36, df="bgr555le")]:
         with pytest.raises(Exception):
             S.SwsContext(kw["sw"], kw["sh"], kw["sf"], kw["dw"], kw["dh"], kw["df"], S.SWS_BICUBIC | BX)
     L = S.lib()
@@ -524,3 +523,12 @@ def test_very_long_vertical_filter(df):
     """12x vertical sinc downscale: ~240 vertical taps; the generic kernel narrows its tile to keep the rows in shared memory."""
     _check(sw=200, sh=1200, sf="yuv420p", dw=200, dh=100, df=df, flags=S.SWS_SINC | BX, seed=141)
     _check(sw=322, sh=1100, sf="yuv420p10le", dw=322, dh=92, df=df, flags=S.SWS_SINC | BX, seed=142, mode="extreme")
+
+
+@pytest.mark.parametrize("df", ["rgb565le", "bgr565le", "rgb555le", "bgr555le"])
+def test_rgb16bpp_odd_widths(df):
+    """No full-chroma writer exists for these formats: an odd width keeps the pair writer and its last pair holds one pixel."""
+    for sf, g, fl in [("yuv420p", (322, 182, 321, 182), S.SWS_BICUBIC | BX), ("yuv420p", (323, 181, 323, 181), S.SWS_BICUBIC | BX),
+                      ("yuv420p", (323, 182, 323, 182), S.SWS_BICUBIC), ("yuv444p", (161, 90, 387, 201), S.SWS_BILINEAR | BX),
+                      ("bgra", (163, 91, 257, 131), S.SWS_LANCZOS | BX), ("yuv420p10le", (322, 182, 129, 71), S.SWS_FAST_BILINEAR)]:
+        _check(sw=g[0], sh=g[1], sf=sf, dw=g[2], dh=g[3], df=df, flags=fl, seed=151)
