@@ -453,10 +453,6 @@ static int init_single(SwsContext *sws, int with_device)
         /* 15/16 bpp destinations have no full-chroma writer: the reference drops the flag again
          * (utils.c:1329-1357).  Its pair writer then stores one pixel past an odd width (into the row
          * padding); the kernel stops at the last valid pixel */
-        if (is_rgb(sws->src_format) && srcW == dstW && srcH == dstH) {
-            set_error(c, "unscaled RGB -> 15/16 bpp RGB (rgb24to16 & co.) is not on the CUDA hot path");
-            return AVERROR(ENOTSUP);
-        }
         flags &= ~SWS_FULL_CHR_H_INT;
         sws->flags = flags;
     }
@@ -498,6 +494,11 @@ static int init_single(SwsContext *sws, int with_device)
                 sws->dst_format == AV_PIX_FMT_ARGB || sws->dst_format == AV_PIX_FMT_ABGR)
                 c->special = SWSC_SPECIAL_SHUFFLE;
         }
+        if (is_rgb(sws->src_format) && is_rgb(sws->dst_format) && sd->depth == 8 && dd->bpp <= 16 &&
+            (flags & (SWS_FAST_BILINEAR | SWS_POINT)))
+            /* rgb24to16, rgb32tobgr15, ... (findRgbConvFn): plain truncation, chosen only when the caller's
+             * scaler says no dither is wanted (swscale_unscaled.c:2459-2466); otherwise the dithering scaler runs */
+            c->special = SWSC_SPECIAL_RGB16PACK;
         if (sws->src_format == AV_PIX_FMT_BGR24 && sws->dst_format == AV_PIX_FMT_YUV420P &&
             !(flags & SWS_ACCURATE_RND) && !(dstW & 1))
             c->special = SWSC_SPECIAL_BGR24_YV12;     /* swscale_unscaled.c:2062-2077,2453-2457 */

@@ -137,6 +137,39 @@ struct ShuffleArgs {
     int map[4];            /* destination byte k of a pixel <- source byte map[k]; 4 = constant 255 */
 };
 
+/* rgb24to16 / rgb24tobgr16 / rgb32to15 ... (rgb2rgb_template.c via rgbToRgbWrapper): every 8-bit channel is truncated
+ * into its 5- or 6-bit field.  Two pixels per thread. */
+struct Rgb16PackArgs {
+    const uint8_t *src;
+    uint8_t *dst;
+    long long src_fstride, dst_fstride;
+    int src_stride, dst_stride;
+    int w, y0, rows;
+    int bpp, ro, go, bo;       /* source pixel size and channel byte offsets */
+    int gbits, rgb;            /* green field width (6 / 5); 1 when red sits in the high bits */
+};
+
+__global__ void __launch_bounds__(256)
+sws_rgb16pack_kernel(const __grid_constant__ Rgb16PackArgs A)
+{
+    const int pairs = (A.w + 1) >> 1;
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int row = (int)(idx / pairs), i = (int)(idx - (long long)row * pairs);
+    if (row >= A.rows)
+        return;
+    const uint8_t *s = A.src + blockIdx.z * A.src_fstride + (size_t)(A.y0 + row) * A.src_stride + (size_t)2 * i * A.bpp;
+    uint16_t *d = reinterpret_cast<uint16_t *>(A.dst + blockIdx.z * A.dst_fstride + (size_t)(A.y0 + row) * A.dst_stride) + 2 * i;
+    const int hi = 5 + A.gbits;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        if (2 * i + k >= A.w)
+            break;
+        const uint8_t *px = s + k * A.bpp;
+        const unsigned r = px[A.ro] >> 3, g = px[A.go] >> (8 - A.gbits), b = px[A.bo] >> 3;
+        d[k] = (uint16_t)(A.rgb ? (r << hi) | (g << 5) | b : (b << hi) | (g << 5) | r);
+    }
+}
+
 #define SHUF_PX 1024       /* pixels of one row per block */
 
 /* rgbToRgbWrapper / packedCopyWrapper between 8-bit packed RGB layouts (swscale_unscaled.c:2001-2060):
@@ -2886,6 +2919,27 @@ static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const i
         else
             sws_depthcopy_kernel<uint16_t, uint16_t><<<grid, 256, 0, stream>>>(a);
         st->kernel_name = "depthcopy";
+        CUDA_OK(cudaGetLastError());
+        st->launches++;
+        return 1;
+    }
+    if (p->special == SWSC_SPECIAL_RGB16PACK) {
+        Rgb16PackArgs a;
+        memset(&a, 0, sizeof(a));
+        if (!src[0] || !dst[0])
+            return AVERROR(EINVAL);
+        a.src = src[0]; a.dst = dst[0];
+        a.src_fstride = src_fstride ? src_fstride[0] : 0;
+        a.dst_fstride = dst_fstride ? dst_fstride[0] : 0;
+        a.src_stride = src_stride[0]; a.dst_stride = dst_stride[0];
+        a.w = p->src_w; a.y0 = y0; a.rows = y1 - y0;
+        a.bpp = p->src_bpp; a.ro = p->src_ro; a.go = p->src_go; a.bo = p->src_bo;
+        a.gbits = p->dst_kind == SWSC_DST_RGB565 || p->dst_kind == SWSC_DST_BGR565 ? 6 : 5;
+        a.rgb = p->dst_kind == SWSC_DST_RGB565 || p->dst_kind == SWSC_DST_RGB555;
+        const long long work = (long long)((a.w + 1) >> 1) * a.rows;
+        dim3 grid((unsigned)((work + 255) / 256), 1, nb_frames);
+        sws_rgb16pack_kernel<<<grid, 256, 0, stream>>>(a);
+        st->kernel_name = "rgb16pack";
         CUDA_OK(cudaGetLastError());
         st->launches++;
         return 1;

@@ -121,6 +121,7 @@ enum {
     SWSC_SPECIAL_COPY8,          /* planarCopyWrapper / planarToNv12Wrapper / nv12ToPlanarWrapper, 8-bit */
     SWSC_SPECIAL_P01X,           /* planarToP01xWrapper / planar8ToP01xleWrapper: shift + chroma interleave */
     SWSC_SPECIAL_DEPTHCOPY,      /* planarCopyWrapper between planar YUV depths (dithered down, replicated up) */
+    SWSC_SPECIAL_RGB16PACK,      /* rgb24to16 / rgb32tobgr15 & co.: 8-bit packed RGB truncated into 15/16 bpp */
 };
 
 /* POD description of one conversion; passed by value to the kernels. */

@@ -454,8 +454,6 @@ class OracleContext:
             if dw & 1 or (shs == 0 and svs == 0 and dither != 2 and not flags & SWS_FAST_BILINEAR):
                 flags |= SWS_FULL_CHR_H_INT
         if self.dkind == "rgb565":                                    # no full-chroma writer, :1329-1357
-            if src_rgb and sw == dw and sh == dh:
-                raise NotImplementedError("rgb24to16 & co. are not restated")
             flags &= ~SWS_FULL_CHR_H_INT
         if dst_rgb and not (flags & SWS_FULL_CHR_H_INT):              # :1359
             dhs = 1
@@ -488,13 +486,18 @@ class OracleContext:
         self.unscaled_lut = False
         self.special = None
         if unscaled and (self.src_range == self.dst_range or dst_rgb):
-            if src_rgb and dst_rgb and self.dkind != "rgb16":
+            if src_rgb and dst_rgb and self.dkind not in ("rgb16", "rgb565"):
                 # rgbToRgbWrapper (findRgbConvFn, swscale_unscaled.c:1843-2060,2463-2466), packedCopyWrapper
                 # for identical formats; with SWS_BITEXACT 24 -> rgba/bgra is left to the scaler (:1992-1996)
                 s32, d32 = self.skind == "rgb32", self.dkind == "rgb32"
                 if sfmt == dfmt or s32 or not d32 or not (flags & SWS_BITEXACT) or dfmt in ("argb", "abgr"):
                     self.special = "shuffle"
                     return
+            if src_rgb and self.dkind == "rgb565" and flags & (SWS_FAST_BILINEAR | SWS_POINT):
+                # rgb24to16 / rgb32tobgr15 ... (findRgbConvFn): truncation, only when the scaler flag says that no
+                # dither is wanted (swscale_unscaled.c:2459-2466)
+                self.special = "rgb16pack"
+                return
             if sfmt == "bgr24" and dfmt == "yuv420p" and not (flags & SWS_ACCURATE_RND) and not (dw & 1):
                 self.special = "bgr24_yv12"                            # swscale_unscaled.c:2062-2077,2453-2457
                 return
@@ -677,6 +680,17 @@ class OracleContext:
     # ---- the conversion
     _ORDER = {"rgb24": "rgb", "bgr24": "bgr", "rgba": "rgba", "bgra": "bgra", "argb": "argb", "abgr": "abgr"}
 
+    def _rgb16pack(self, plane):
+        """rgb24to16, rgb24tobgr15, rgb32to16 ... (rgb2rgb_template.c through rgbToRgbWrapper): channel truncation."""
+        ro, go, bo, bpp = {"rgb24": (0, 1, 2, 3), "bgr24": (2, 1, 0, 3), "rgba": (0, 1, 2, 4), "bgra": (2, 1, 0, 4),
+                           "argb": (1, 2, 3, 4), "abgr": (3, 2, 1, 4)}[self.sfmt]
+        px = np.ascontiguousarray(plane)[:self.sh, :self.sw * bpp].reshape(self.sh, self.sw, bpp).astype(np.uint16)
+        is565 = self.dfmt in ("rgb565le", "bgr565le")
+        r, g, b = px[..., ro] >> 3, px[..., go] >> (2 if is565 else 3), px[..., bo] >> 3
+        hi = 11 if is565 else 10
+        out = (r << hi) | (g << 5) | b if self.dfmt.startswith("rgb") else (b << hi) | (g << 5) | r
+        return [out.astype("<u2").view(np.uint8).reshape(self.sh, -1)]
+
     def _shuffle(self, plane):
         """Byte permutation per pixel; alpha carried when both sides have it, else 255."""
         so, do = self._ORDER[self.sfmt], self._ORDER[self.dfmt]
@@ -760,6 +774,8 @@ class OracleContext:
             return self._p01x(planes)
         if self.special == "depthcopy":
             return self._depthcopy(planes)
+        if self.special == "rgb16pack":
+            return self._rgb16pack(planes[0])
         if self.special == "shuffle":
             return self._shuffle(planes[0])
         if self.special == "bgr24_yv12":

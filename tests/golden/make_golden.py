@@ -153,6 +153,9 @@ def cases():
         out.append(dict(sw=162, sh=122, sf="yuv420p", dw=161, dh=122, df=df, flags=R.SWS_BICUBIC | BX))
         out.append(dict(sw=163, sh=122, sf="yuv420p", dw=163, dh=122, df=df, flags=R.SWS_BICUBIC))
         out.append(dict(sw=81, sh=61, sf="yuv444p", dw=201, dh=151, df=df, flags=R.SWS_BILINEAR | BX))
+    for sf, df in [("rgb24", "rgb565le"), ("bgra", "bgr555le"), ("argb", "bgr565le"), ("bgr24", "rgb555le")]:
+        out.append(dict(sw=163, sh=61, sf=sf, dw=163, dh=61, df=df, flags=R.SWS_POINT))            # rgb24to16 & co.
+        out.append(dict(sw=163, sh=61, sf=sf, dw=163, dh=61, df=df, flags=R.SWS_BICUBIC | BX))     # dithering scaler
     for i, c in enumerate(out):
         c.setdefault("seed", 100 + i)
         c.setdefault("mode", "extreme" if i % 7 == 3 else "noise")

@@ -496,11 +496,20 @@ def test_rgb16bpp_destinations(df, sf, geom, flags):
     _check(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags, seed=132, slices=slices)
 
 
-def test_rgb16bpp_rejections():
-    """The unscaled rgb24to16 family is refused."""
-    for kw in [dict(sw=64, sh=36, sf="rgb24", dw=64, dh=36, df="bgr555le")]:
-        with pytest.raises(Exception):
-            S.SwsContext(kw["sw"], kw["sh"], kw["sf"], kw["dw"], kw["dh"], kw["df"], S.SWS_BICUBIC | BX)
+@pytest.mark.parametrize("sf", RGB_SRC)
+@pytest.mark.parametrize("df", ["rgb565le", "bgr565le", "rgb555le", "bgr555le"])
+def test_rgb16bpp_from_unscaled_rgb(sf, df):
+    """SWS_POINT / SWS_FAST_BILINEAR pick the truncating rgb24to16 family (swscale_unscaled.c:2459-2466); every other
+    scaler flag leaves the conversion to the dithering scaler."""
+    for g in [(644, 366), (35, 19)]:
+        for fl in (S.SWS_POINT, S.SWS_FAST_BILINEAR | BX):
+            assert _check(sw=g[0], sh=g[1], sf=sf, dw=g[0], dh=g[1], df=df, flags=fl, seed=161) == "rgb16pack"
+        assert _check(sw=g[0], sh=g[1], sf=sf, dw=g[0], dh=g[1], df=df, flags=S.SWS_BICUBIC | BX, seed=162) != "rgb16pack"
+    slices = [(y, min(30, 366 - y)) for y in range(0, 366, 30)]
+    _check(sw=644, sh=366, sf=sf, dw=644, dh=366, df=df, flags=S.SWS_POINT, seed=163, slices=slices)
+
+
+def test_rgb16bpp_is_output_only():
     L = S.lib()
     assert not L.sws_isSupportedInput(S.PIX_FMT["rgb565le"]) and L.sws_isSupportedOutput(S.PIX_FMT["rgb565le"])
 
