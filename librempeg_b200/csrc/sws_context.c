@@ -686,6 +686,26 @@ static int init_single(SwsContext *sws, int with_device)
         c->planned = 1;
         return 0;
     }
+    /* One-tap vertical filters run through yuv2plane1 / yuv2packed1, which never look at the coefficient
+     * (vscale.c:135-143,296-316).  It is 4096 except where initFilter's edge fix-up left 4095 behind (a few
+     * source rows with a large chroma offset): make the device banks say what those writers compute. */
+    {
+        const int packed = is_rgb(sws->dst_format);
+        if (c->v_lum.size == 1) {
+            for (int y = 0; y < c->v_lum.len; y++) {
+                int one = !packed || c->v_chr.size == 1;
+                if (packed && c->v_chr.size == 2 && y < c->v_chr.len) {
+                    const int c0 = c->v_chr.coef[2 * y], c1 = c->v_chr.coef[2 * y + 1];
+                    one = c0 + c1 == 4096 && (unsigned)c1 <= 4096u;
+                }
+                if (one)
+                    c->v_lum.coef[y] = 4096;
+            }
+        }
+        if (c->v_chr.size == 1 && (packed ? c->v_lum.size == 1 : !(dd->flags & SWSPF_SEMI)))
+            for (int y = 0; y < c->v_chr.len; y++)
+                c->v_chr.coef[y] = 4096;
+    }
     ret = ff_b200_cuda_create(&c->cuda, p, &c->h_lum, &c->h_chr, &c->v_lum, &c->v_chr);
     if (ret < 0) {
         set_error(c, "CUDA initialisation failed (%d): no CPU fallback exists on this path", ret);

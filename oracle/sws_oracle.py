@@ -505,6 +505,13 @@ class OracleContext:
                     and dither in (1, 2) and not (dh & 1):
                 self.unscaled_lut = True                               # yuv2rgb_c_* (yuv2rgb.c:137-236)
                 return
+            if (not src_rgb and not dst_rgb and self.sdepth == 8 and self.ddepth == 8 and
+                    (((shs, svs) == (1, 1) == (dhs, dvs) and (self.skind == "semi") != (self.dkind == "semi")) or
+                     ((shs, svs) == (dhs, dvs) and self.skind == self.dkind and (sfmt == "nv21") == (dfmt == "nv21")))):
+                # planarCopyWrapper / planarToNv12Wrapper / nv12ToPlanarWrapper (swscale_unscaled.c:147-215,2405-2420,
+                # 2675-2700): plain copies, whatever the chroma siting options say
+                self.special = "copy8"
+                return
             if dfmt == "p010le" and self.skind == "planar" and (shs, svs) == (1, 1) and self.sdepth != 9:
                 self.special = "p01x"                                  # swscale_unscaled.c:273-375,2432-2444
                 return
@@ -537,6 +544,19 @@ class OracleContext:
                                  lpos(svs, svp), lpos(dvs, dvp), src_vec=sfv.get("chrV"), dst_vec=dfv.get("chrV"))
         if None in (self.h_lum, self.h_chr, self.v_lum, self.v_chr):
             raise NotImplementedError("cascaded contexts are not restated")
+        # one-tap vertical filters go through yuv2plane1 / yuv2packed1, which ignore the coefficient
+        # (vscale.c:135-143,296-316); initFilter's edge fix-up can leave 4095 there
+        vl, vc = self.v_lum[0], self.v_chr[0]
+        if vl.shape[1] == 1:
+            one = np.ones(vl.shape[0], bool)
+            if dst_rgb and vc.shape[1] == 2:
+                c0, c1 = vc[:vl.shape[0], 0].astype(np.int64), vc[:vl.shape[0], 1].astype(np.int64)
+                one = (c0 + c1 == 4096) & (c1 >= 0) & (c1 <= 4096)
+            elif dst_rgb and vc.shape[1] != 1:
+                one[:] = False
+            vl[one, 0] = 4096
+        if vc.shape[1] == 1 and ((vl.shape[1] == 1) if dst_rgb else self.dkind != "semi"):
+            vc[:, 0] = 4096
         # SWS_FAST_BILINEAR on 8-bit sources with <= 14-bit destinations: hyscale_fast / hcscale_fast
         # replace the horizontal FIR (swscale.c:675-681, hscale.c:54,188)
         self.fast_h = bool(flags & SWS_FAST_BILINEAR) and self.src_bpc == 8 and self.dst_bpc <= 14
@@ -774,6 +794,15 @@ class OracleContext:
             return self._p01x(planes)
         if self.special == "depthcopy":
             return self._depthcopy(planes)
+        if self.special == "copy8":
+            lum, u, v = self._unpack(planes)
+            y8, u8, v8 = (np.asarray(a).astype(np.uint8) for a in (lum, u, v))
+            if self.dkind == "semi":
+                uv = np.zeros((self.cdh, 2 * self.cdw), np.uint8)
+                a, b = (v8, u8) if self.dfmt == "nv21" else (u8, v8)
+                uv[:, 0::2], uv[:, 1::2] = a[:self.cdh, :self.cdw], b[:self.cdh, :self.cdw]
+                return [y8, uv]
+            return [y8, u8[:self.cdh, :self.cdw], v8[:self.cdh, :self.cdw]]
         if self.special == "rgb16pack":
             return self._rgb16pack(planes[0])
         if self.special == "shuffle":

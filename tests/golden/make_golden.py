@@ -156,6 +156,18 @@ def cases():
     for sf, df in [("rgb24", "rgb565le"), ("bgra", "bgr555le"), ("argb", "bgr565le"), ("bgr24", "rgb555le")]:
         out.append(dict(sw=163, sh=61, sf=sf, dw=163, dh=61, df=df, flags=R.SWS_POINT))            # rgb24to16 & co.
         out.append(dict(sw=163, sh=61, sf=sf, dw=163, dh=61, df=df, flags=R.SWS_BICUBIC | BX))     # dithering scaler
+    # one-tap vertical filters ignore their coefficient (yuv2plane1 / yuv2packed1); initFilter leaves 4095 there when a
+    # large chroma offset meets a source of two or three rows.  Unscaled copies ignore the chroma siting options.
+    out.append(dict(sw=128, sh=2, sf="rgb24", dw=96, dh=24, df="yuv420p14le", flags=R.SWS_LANCZOS | BX,
+                    ctx_kwargs=dict(chr_pos=[0, 256, 128, -513])))
+    out.append(dict(sw=69, sh=3, sf="bgra", dw=184, dh=36, df="yuv420p12le", flags=R.SWS_SPLINE | BX,
+                    ctx_kwargs=dict(src_range=0, dst_range=1, chr_pos=[64, 256, 64, 64])))
+    out.append(dict(sw=128, sh=2, sf="yuv444p", dw=96, dh=24, df="rgb24", flags=R.SWS_BICUBIC | BX,
+                    ctx_kwargs=dict(chr_pos=[0, 256, 128, -513])))
+    out.append(dict(sw=245, sh=229, sf="yuvj420p", dw=245, dh=229, df="yuvj420p", flags=R.SWS_AREA | R.SWS_ACCURATE_RND,
+                    ctx_kwargs=dict(chr_pos=[256, 64, 128, 64])))
+    out.append(dict(sw=87, sh=198, sf="yuv422p", dw=87, dh=198, df="nv12", flags=R.SWS_BICUBIC | BX,
+                    ctx_kwargs=dict(chr_pos=[0, 64, 128, 128])))
     for i, c in enumerate(out):
         c.setdefault("seed", 100 + i)
         c.setdefault("mode", "extreme" if i % 7 == 3 else "noise")

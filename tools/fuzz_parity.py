@@ -113,6 +113,25 @@ def make_case(rng):
         if min(case["sw"], case["sh"], case["dw"], case["dh"]) < 16:
             other = cs
         case["colorspace"] = (cs, rng.randint(0, 1), other, rng.randint(0, 1), 0, 1 << 16, 1 << 16)
+    # less common options: scaler parameters, chroma siting, dither mode, picture controls
+    if rng.random() < 0.1:
+        base = flags & 0x7FF
+        if base == S.SWS_BICUBIC:
+            case["param"] = (rng.choice([0.0, 1 / 3.0, 1.0, 0.5]), rng.choice([0.5, 1 / 3.0, 0.0, 0.6]))
+        elif base == S.SWS_GAUSS:
+            case["param"] = (rng.choice([2.0, 3.0, 4.5]), 123456.0)
+        elif base == S.SWS_LANCZOS:
+            case["param"] = (float(rng.choice([2, 3, 4, 5])), 123456.0)
+    if rng.random() < 0.1:
+        kw = case.setdefault("ctx_kwargs", {})
+        kw["chr_pos"] = tuple(rng.choice([-513, 0, 64, 128, 256]) for _ in range(4))
+    if rng.random() < 0.1:
+        kw = case.setdefault("ctx_kwargs", {})
+        kw["dither"] = rng.choice([0, 1, 2, 4, 5])
+    if "colorspace" in case and rng.random() < 0.3:
+        cs = list(case["colorspace"])
+        cs[4:] = [rng.choice([0, 3000, -5000]), rng.choice([1 << 16, 78643, 52000]), rng.choice([1 << 16, 52428, 90000])]
+        case["colorspace"] = tuple(cs)
     if rng.random() < 0.25:
         # 16-bit samples need even strides (the reference reads them through uint16_t pointers)
         case["src_pad"] = rng.choice([0, 1, 3, 16, 64] if T.depth_of(case["sf"]) == 8 else [0, 2, 6, 16, 64])
@@ -128,7 +147,8 @@ def check_batch(case, frames=3):
     import torch
     dev = torch.device("cuda", 0)
     kw = dict(case.get("ctx_kwargs") or {})
-    c = S.SwsContext(case["sw"], case["sh"], case["sf"], case["dw"], case["dh"], case["df"], case["flags"], **kw)
+    c = S.SwsContext(case["sw"], case["sh"], case["sf"], case["dw"], case["dh"], case["df"], case["flags"],
+                     param=case.get("param"), **kw)
     try:
         if case.get("colorspace") and c.set_colorspace(*case["colorspace"]) < 0:
             return None
