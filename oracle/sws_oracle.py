@@ -475,17 +475,24 @@ class OracleContext:
         cs = colorspace or (5, src_range, 5, dst_range, 0, 1 << 16, 1 << 16)
         self.rgb = None
         if dst_rgb:
-            self.rgb = yuv2rgb_tables(YUV2RGB_COEFFS[cs[0]], cs[1] if colorspace else src_range,
+            self.rgb = yuv2rgb_tables(YUV2RGB_COEFFS[cs[0]], (0 if src_rgb else cs[1]) if colorspace else src_range,
                                       cs[4], cs[5], cs[6])
-            if colorspace and not src_rgb:
-                self.src_range = cs[1]
         if src_rgb:
             self.rgb2yuv = rgb2yuv_table(YUV2RGB_COEFFS[cs[2]])
+        # `colorspace` restates a sws_setColorspaceDetails() call made AFTER init (utils.c:849-905): the special
+        # converter below was chosen with the init-time ranges and stays; everything computed per frame sees the
+        # new ranges (formats that are neither YUV nor gray carry none)
+        sel_ranges = (self.src_range, self.dst_range)
+        if colorspace and not src_rgb and not dst_rgb and YUV2RGB_COEFFS[cs[0]] != YUV2RGB_COEFFS[cs[2]]:
+            raise NotImplementedError("YUV->YUV with two matrices cascades through RGB (utils.c:915-984): not restated")
+        if colorspace:
+            self.src_range = 0 if src_rgb else cs[1]
+            self.dst_range = 0 if dst_rgb else cs[3]
 
         # unscaled special converters, swscale_unscaled.c:2392-2731 (only the ones that differ)
         self.unscaled_lut = False
         self.special = None
-        if unscaled and (self.src_range == self.dst_range or dst_rgb):
+        if unscaled and (sel_ranges[0] == sel_ranges[1] or dst_rgb):
             if src_rgb and dst_rgb and self.dkind not in ("rgb16", "rgb565"):
                 # rgbToRgbWrapper (findRgbConvFn, swscale_unscaled.c:1843-2060,2463-2466), packedCopyWrapper
                 # for identical formats; with SWS_BITEXACT 24 -> rgba/bgra is left to the scaler (:1992-1996)

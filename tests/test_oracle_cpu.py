@@ -134,3 +134,34 @@ def test_survey_md5_recipe_c1_c2():
         c = R.RefContext(w, h, "yuv420p", w, h, "rgb24", flags)
         c.scale(planes, [w, w // 2, w // 2], [dst], [w * 3])
         assert R.md5(dst) == md5
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref/libswsref.so not built")
+def test_oracle_matches_reference_on_random_cases():
+    """The case generator of tools/fuzz_parity.py (formats, sizes, scalers and their parameters, flags, ranges,
+    colourspace, chroma siting, dither modes) on the CPU: the numpy restatement against the live reference build.
+    Cases neither side restates (cascades, alpha through the scaler, ...) are skipped; nothing may differ."""
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_parity as F
+    rng = random.Random(2024)
+    compared = 0
+    for _ in range(6000):
+        c = F.make_case(rng)
+        if max(c["sw"], c["sh"], c["dw"], c["dh"]) > 200:
+            continue
+        kw = {k: v for k, v in c.items() if k not in ("seed", "mode", "src_pad", "dst_pad")}
+        src = T.Frame(c["sf"], c["sw"], c["sh"]).randomize(c["seed"], c["mode"])
+        try:
+            want = T.run_reference(src=src, **kw)[0].valid()
+            got = T.run_oracle(src=src, **kw)
+        except NotImplementedError:
+            continue
+        except RuntimeError as e:
+            if "reference" in str(e):
+                continue
+            raise
+        assert T.first_diff(got, want) is None, "%r: %s" % (c, T.first_diff(got, want))
+        compared += 1
+    assert compared > 800
