@@ -21,6 +21,7 @@
 
 #include <stdint.h>
 #include <stddef.h>
+#include "swscale_b200_prefix.h"   /* no-op unless an in-tree build defines SWS_B200_PREFIX */
 
 #ifdef __cplusplus
 extern "C" {

@@ -14,7 +14,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(HERE, "libswscale_b200.so")
 
-C_SOURCES = ["sws_context.c", "sws_filter.c", "sws_colorspace.c", "sws_pixfmt.c", "sws_frame.c", "sws_compat.c"]
+C_SOURCES = ["sws_context.c", "sws_filter.c", "sws_colorspace.c", "sws_pixfmt.c", "sws_frame.c", "sws_compat.c",
+             "sws_hook.c", "sws_options.c"]
 CU_SOURCES = ["sws_cuda.cu"]
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

@@ -23,26 +23,12 @@
 #define LIBSWSCALE_VERSION_MINOR 2
 #define LIBSWSCALE_VERSION_MICRO 100
 
-/* Minimal stand-in for libavutil's AVClass when built outside the librempeg tree
- * (only class_name is meaningful); in-tree builds use the reference's options.c
- * unchanged, see INTEGRATION.md. */
-struct AVClass {
-    const char *class_name;
-    const char *(*item_name)(void *ctx);
-    const void *option;
-    int version;
-};
-
-static const char *ctx_name(void *ctx) { (void)ctx; return "swscaler-b200"; }
-static const struct AVClass sws_b200_class = { "SWScaler", ctx_name, NULL, 0 };
-
 unsigned swscale_version(void)
 {
     return (LIBSWSCALE_VERSION_MAJOR << 16) | (LIBSWSCALE_VERSION_MINOR << 8) | LIBSWSCALE_VERSION_MICRO;
 }
 const char *swscale_configuration(void) { return "b200-native sm_100a (no CPU fallback)"; }
 const char *swscale_license(void) { return "LGPL version 2.1 or later"; }
-const struct AVClass *sws_get_class(void) { return &sws_b200_class; }
 
 static void set_error(SwsInternal *c, const char *fmt, ...)
 {
@@ -61,18 +47,9 @@ SwsContext *sws_alloc_context(void)
     SwsInternal *c = calloc(1, sizeof(*c));
     if (!c)
         return NULL;
-    /* defaults of the reference's AVOption table (options.c:34-118) */
-    c->opts.av_class = &sws_b200_class;
-    c->opts.flags = SWS_BICUBIC;
-    c->opts.scaler_params[0] = SWS_PARAM_DEFAULT;
-    c->opts.scaler_params[1] = SWS_PARAM_DEFAULT;
-    c->opts.threads = 1;
-    c->opts.dither = SWS_DITHER_AUTO;
-    c->opts.alpha_blend = SWS_ALPHA_BLEND_NONE;
-    c->opts.src_w = c->opts.src_h = c->opts.dst_w = c->opts.dst_h = 16;
-    c->opts.src_v_chr_pos = c->opts.src_h_chr_pos = -513;
-    c->opts.dst_v_chr_pos = c->opts.dst_h_chr_pos = -513;
-    c->opts.intent = 1;
+    /* av_class first, then the defaults of the AVOption table (reference utils.c:1032-1045) */
+    c->opts.av_class = sws_get_class();
+    ff_b200_option_defaults(&c->opts);
     return &c->opts;
 }
 
@@ -624,6 +601,7 @@ static int init_single(SwsContext *sws, int with_device)
     p->dst_shift = dd->shift;
     p->dst_bits = c->dst_bpc;
     p->has_chroma = 1;
+    p->dst_has_chroma = 1;
     p->unscaled_lut = c->unscaled_lut;
     p->special = c->special;
     p->full_chr = is_rgb(sws->dst_format) && (flags & SWS_FULL_CHR_H_INT) && !c->unscaled_lut;
@@ -889,6 +867,9 @@ int sws_scale(SwsContext *sws, const uint8_t *const srcSlice[], const int srcStr
 {
     SwsInternal *c = sws_internal(sws);
     int macro_src, y0, y1, ret, avail_l, avail_c;
+    const uint8_t *src2[4];
+    uint8_t *dst2[4];
+    int sstride[4], dstride[4];
 
     if (!c || !c->initialized)
         return AVERROR(EINVAL);
@@ -924,12 +905,32 @@ int sws_scale(SwsContext *sws, const uint8_t *const srcSlice[], const int srcStr
             set_error(c, "slices start in the middle");
             return AVERROR(EINVAL);
         }
-        if (srcSliceY != 0) {
-            set_error(c, "bottom-to-top slice order is not on the CUDA hot path");
-            return AVERROR(ENOTSUP);
-        }
-        c->slice_dir = 1;
+        c->slice_dir = srcSliceY == 0 ? 1 : -1;
         c->dst_y = 0;
+    }
+
+    for (int i = 0; i < 4; i++) {
+        src2[i] = srcSlice[i]; dst2[i] = dst[i];
+        sstride[i] = srcStride[i]; dstride[i] = dstStride[i];
+    }
+    if (c->slice_dir != 1) {
+        /* slices arrive bottom to top: flip the picture internally, exactly like the reference
+         * (swscale.c:1141-1159) -- every stride negated, pointers moved to the last row, the slice
+         * position mirrored -- and convert it top-down */
+        const int csh = (srcSliceH >> c->chr_src_vsub) - 1;
+        for (int i = 0; i < 4; i++) {
+            sstride[i] = -sstride[i];
+            dstride[i] = -dstride[i];
+        }
+        if (src2[0]) src2[0] += (ptrdiff_t)(srcSliceH - 1) * srcStride[0];
+        if (src2[1]) src2[1] += (ptrdiff_t)csh * srcStride[1];
+        if (src2[2]) src2[2] += (ptrdiff_t)csh * srcStride[2];
+        if (src2[3]) src2[3] += (ptrdiff_t)(srcSliceH - 1) * srcStride[3];
+        if (dst2[0]) dst2[0] += (ptrdiff_t)(sws->dst_h - 1) * dstStride[0];
+        if (dst2[1]) dst2[1] += (ptrdiff_t)((sws->dst_h >> c->chr_dst_vsub) - 1) * dstStride[1];
+        if (dst2[2]) dst2[2] += (ptrdiff_t)((sws->dst_h >> c->chr_dst_vsub) - 1) * dstStride[2];
+        if (dst2[3]) dst2[3] += (ptrdiff_t)(sws->dst_h - 1) * dstStride[3];
+        srcSliceY = sws->src_h - srcSliceY - srcSliceH;
     }
     if (srcSliceY == 0)
         c->dst_y = 0;
@@ -952,16 +953,28 @@ int sws_scale(SwsContext *sws, const uint8_t *const srcSlice[], const int srcStr
         }
     }
 
-    ret = ff_b200_cuda_scale_host(c->cuda, srcSlice, srcStride, srcSliceY, srcSliceH, 1,
-                                  dst, dstStride, y0, y1);
+    ret = ff_b200_cuda_scale_host(c->cuda, src2, sstride, srcSliceY, srcSliceH, 1,
+                                  dst2, dstride, y0, y1);
     if (ret < 0) {
         set_error(c, "CUDA conversion failed (%d)", ret);
+        c->slice_dir = 0;
         return ret;
     }
     c->dst_y = y1;
     if (srcSliceY + srcSliceH == sws->src_h)
         c->slice_dir = 0;
     return y1 - y0;
+}
+
+/* Whole source frame in, destination rows [y0, y1) out (dst[] addresses frame row 0): sws_receive_slice()
+ * and the destination-slice mode of the in-tree hook (reference swscale.c:371-375). */
+int ff_b200_scale_frame_rows(SwsInternal *c, const uint8_t *const src[4], const int srcStride[4],
+                             uint8_t *const dst[4], const int dstStride[4], int y0, int y1)
+{
+    int ret = ff_b200_cuda_scale_host(c->cuda, src, srcStride, 0, c->opts.src_h, 1, dst, dstStride, y0, y1);
+    if (ret < 0)
+        set_error(c, "CUDA conversion failed (%d)", ret);
+    return ret;
 }
 
 /* ------------------------------------------------------------ CUDA extension */
@@ -974,6 +987,14 @@ int sws_cuda_scale_batch(SwsContext *sws, const uint8_t *const src[4], const int
     int ret;
     if (!c || !c->initialized || !src || !dst || nb_frames < 1)
         return AVERROR(EINVAL);
+    if (!srcStride || !dstStride || (nb_frames > 1 && (!srcFrameStride || !dstFrameStride))) {
+        set_error(c, "sws_cuda_scale_batch(): stride arrays must not be NULL");
+        return AVERROR(EINVAL);
+    }
+    if (!src[0] || !dst[0] || srcStride[0] <= 0 || dstStride[0] <= 0) {
+        set_error(c, "sws_cuda_scale_batch(): bad image pointers or strides");
+        return AVERROR(EINVAL);
+    }
     if (c->refused) {
         set_error(c, "the last sws_setColorspaceDetails() asked for a conversion that is not on the CUDA hot path");
         return AVERROR(ENOTSUP);

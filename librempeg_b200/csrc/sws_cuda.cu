@@ -38,6 +38,23 @@
         }                                                                       \
     } while (0)
 
+/* Every entry point runs on the device the context was created on, whatever device the calling thread
+ * has current, and leaves the caller's current device as it found it. */
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev)
+            switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (switched)
+            cudaSetDevice(prev);
+    }
+};
+
 /* ordered-dither rows for 8-bit planar output of >8-bit sources; same matrix as
  * ff_dither_8x8_128 (reference swscale.c:42-52) */
 __constant__ __align__(8) uint8_t c_dither_8x8_128[8][8] = {
@@ -1386,6 +1403,10 @@ struct SwsCudaState {
     int32_t *h_vl_pos, *h_vc_pos;
     /* staging frames for host-pointer sws_scale() */
     uint8_t *d_src[4], *d_dst[4];
+    uint8_t *h_src[4], *h_dst[4];   /* page-locked twins of the staging planes: bounce ring for pageable frames */
+    uint8_t *d_flip;                /* scratch for mirroring the rows of bottom-up frames */
+    size_t flip_bytes;
+    int staging_ready, bounce_src_ready, bounce_dst_ready;
     int d_src_stride[4], d_dst_stride[4];
     int src_rows[4], dst_rows[4];
     int src_rowbytes[4], dst_rowbytes[4];
@@ -1412,7 +1433,7 @@ struct SwsCudaState {
     Fast16Row *d_fast16_rows;
     int e2e_mode, e2e_bands; /* how sws_scale() moves page-locked host frames (see scale_host)  */
     cudaStream_t s_in, s_out;
-    cudaEvent_t ev_in[16], ev_k[16];
+    cudaEvent_t ev_in[16], ev_k[16], ev_out[16];
     int4 *d_fast_rows;
     int num_sms;
     int tile_w, tile_h, rows_l_cap, rows_c_cap;
@@ -1685,13 +1706,6 @@ static int fast420_setup(SwsCudaState *st, const SwsFirBank *vc)
         }
     }
     st->fast_ok = 1;
-    {
-        const char *e = getenv("SWS_B200_E2E_MODE"), *b = getenv("SWS_B200_E2E_BANDS");
-        st->e2e_mode = e ? atoi(e) : 3;
-        st->e2e_bands = b ? atoi(b) : 4;
-        if (st->e2e_bands < 1) st->e2e_bands = 1;
-        if (st->e2e_bands > 16) st->e2e_bands = 16;
-    }
     st->kernel_name = "fast420_rgb8_tma";
     return 0;
 }
@@ -2351,6 +2365,13 @@ extern "C" int ff_b200_cuda_create(SwsCudaState **out, SwsCudaPlan *plan,
     memcpy(st->h_vl_pos, vl->pos, sizeof(int32_t) * vl->len);
     memcpy(st->h_vc_pos, vc->pos, sizeof(int32_t) * vc->len);
 
+    {
+        const char *e = getenv("SWS_B200_E2E_MODE"), *b = getenv("SWS_B200_E2E_BANDS");
+        st->e2e_mode = e ? atoi(e) : 3;
+        st->e2e_bands = b ? atoi(b) : 4;
+        if (st->e2e_bands < 1) st->e2e_bands = 1;
+        if (st->e2e_bands > 16) st->e2e_bands = 16;
+    }
     int ret = plan_tiles(st);
     if (ret < 0)
         return ret;
@@ -2395,10 +2416,13 @@ extern "C" int ff_b200_cuda_create(SwsCudaState **out, SwsCudaPlan *plan,
     return 0;
 }
 
+static void free_staging(SwsCudaState *st);
+
 extern "C" void ff_b200_cuda_destroy(SwsCudaState *st)
 {
     if (!st)
         return;
+    DeviceGuard guard(st->device);
     if (st->stream) {
         cudaStreamSynchronize(st->stream);
         cudaStreamDestroy(st->stream);
@@ -2414,12 +2438,10 @@ extern "C" void ff_b200_cuda_destroy(SwsCudaState *st)
         for (int k = 0; k < 16; k++) {
             cudaEventDestroy(st->ev_in[k]);
             cudaEventDestroy(st->ev_k[k]);
+            cudaEventDestroy(st->ev_out[k]);
         }
     }
-    for (int i = 0; i < 4; i++) {
-        cudaFree(st->d_src[i]);
-        cudaFree(st->d_dst[i]);
-    }
+    free_staging(st);
     free(st->h_vl_pos);
     free(st->h_vc_pos);
     free(st);
@@ -3054,9 +3076,7 @@ extern "C" int ff_b200_cuda_launch(SwsCudaState *st,
 {
     if (y1 <= y0)
         return 0;
-    int cur = -1;
-    if (cudaGetDevice(&cur) == cudaSuccess && cur != st->device)
-        CUDA_OK(cudaSetDevice(st->device));
+    DeviceGuard guard(st->device);
     {
         int r = special_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);
         if (r != 0)
@@ -3100,241 +3120,11 @@ extern "C" int ff_b200_cuda_launch(SwsCudaState *st,
     return 0;
 }
 
-static int ensure_staging(SwsCudaState *st)
-{
-    if (st->d_src[0])
-        return 0;
-    const SwsCudaPlan *p = &st->plan;
-    const int sb = p->src_bits > 8 ? 2 : 1;
-    /* source planes */
-    st->src_rows[0] = p->src_h; st->src_rowbytes[0] = p->src_w * sb;
-    if (p->src_layout == SWSC_SRC_RGB) {
-        st->src_rowbytes[0] = p->src_w * p->src_bpp;
-    } else if (p->src_layout == SWSC_SRC_PLANAR) {
-        st->src_rows[1] = st->src_rows[2] = p->chr_src_h;
-        st->src_rowbytes[1] = st->src_rowbytes[2] = p->chr_src_w * sb;
-    } else {
-        st->src_rows[1] = p->chr_src_h;
-        st->src_rowbytes[1] = p->chr_src_w * 2 * sb;
-    }
-    /* destination planes */
-    switch (p->dst_kind) {
-    case SWSC_DST_RGB24: case SWSC_DST_BGR24: st->dst_rowbytes[0] = p->dst_w * 3; break;
-    case SWSC_DST_RGBA: case SWSC_DST_BGRA: case SWSC_DST_ARGB: case SWSC_DST_ABGR:
-        st->dst_rowbytes[0] = p->dst_w * 4; break;
-    case SWSC_DST_RGB48: case SWSC_DST_BGR48: st->dst_rowbytes[0] = p->dst_w * 6; break;
-    case SWSC_DST_RGB565: case SWSC_DST_BGR565: case SWSC_DST_RGB555: case SWSC_DST_BGR555:
-        st->dst_rowbytes[0] = p->dst_w * 2; break;
-    default: {
-        const int db = p->dst_bits > 8 ? 2 : 1;
-        st->dst_rowbytes[0] = p->dst_w * db;
-        if (p->dst_kind == SWSC_DST_NV12 || p->dst_kind == SWSC_DST_NV21 || p->dst_kind == SWSC_DST_P010) {
-            st->dst_rows[1] = p->chr_dst_h; st->dst_rowbytes[1] = p->chr_dst_w * 2 * db;
-        } else {
-            st->dst_rows[1] = st->dst_rows[2] = p->chr_dst_h;
-            st->dst_rowbytes[1] = st->dst_rowbytes[2] = p->chr_dst_w * db;
-        }
-    } }
-    st->dst_rows[0] = p->dst_h;
-    for (int i = 0; i < 4; i++) {
-        if (st->src_rows[i]) {
-            st->d_src_stride[i] = (st->src_rowbytes[i] + 15) & ~15;
-            CUDA_OK(cudaMalloc(&st->d_src[i], (size_t)st->d_src_stride[i] * st->src_rows[i]));
-        }
-        if (st->dst_rows[i]) {
-            st->d_dst_stride[i] = (st->dst_rowbytes[i] + 15) & ~15;
-            CUDA_OK(cudaMalloc(&st->d_dst[i], (size_t)st->d_dst_stride[i] * st->dst_rows[i]));
-        }
-    }
-    return 0;
-}
-
-
-
-/* rows x rowbytes copy; one contiguous DMA when both pitches equal the row size */
-static cudaError_t copy_rows_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t rowbytes,
-                                   size_t rows, cudaMemcpyKind kind, cudaStream_t s)
-{
-    if (dpitch == rowbytes && spitch == rowbytes)
-        return cudaMemcpyAsync(dst, src, rowbytes * rows, kind, s);
-    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, rowbytes, rows, kind, s);
-}
-
-/* One synchronous host-frame conversion as a pipeline of row bands:
- *   stream s_in : H2D of band k+1        (copy engine)
- *   st->stream  : kernel on band k       (SMs)
- *   stream s_out: D2H of band k-1        (second copy engine)   [or the kernel stores to the host frame]
- * PCIe is full duplex, so the frame costs ~max(H2D, D2H) instead of their sum.
- * Returns 0 when done, 1 if the caller should fall back to the serial path, <0 on error. */
-#define E2E_MAX_BANDS 16
-static int pipelined_host_frame(SwsCudaState *st, const uint8_t *const src[4], const int src_stride[4],
-                                uint8_t *const dst[4], const int dst_stride[4], uint8_t *const ddst[4],
-                                bool store_to_host)
-{
-    const SwsCudaPlan *p = &st->plan;
-    int ret = ensure_staging(st);
-    if (ret < 0)
-        return ret;
-    if (!st->s_in) {
-        CUDA_OK(cudaStreamCreateWithFlags(&st->s_in, cudaStreamNonBlocking));
-        CUDA_OK(cudaStreamCreateWithFlags(&st->s_out, cudaStreamNonBlocking));
-        for (int k = 0; k < E2E_MAX_BANDS; k++) {
-            CUDA_OK(cudaEventCreateWithFlags(&st->ev_in[k], cudaEventDisableTiming));
-            CUDA_OK(cudaEventCreateWithFlags(&st->ev_k[k], cudaEventDisableTiming));
-        }
-    }
-    int bands = st->e2e_bands;
-    const int band_unit = st->fast_narrow ? 2 * F420_TH : F420_TH;     /* bands start on tile rows of the shape in use */
-    int band_h = ((p->dst_h + bands - 1) / bands + band_unit - 1) / band_unit * band_unit;
-    if (band_h < band_unit)
-        band_h = band_unit;
-    int64_t zero[4] = { 0, 0, 0, 0 };
-    int cup = 0;                                   /* chroma source rows uploaded so far */
-    int k = 0;
-    for (int y0 = 0; y0 < p->dst_h; y0 += band_h, k++) {
-        const int y1 = y0 + band_h < p->dst_h ? y0 + band_h : p->dst_h;
-        /* identity luma: source rows == destination rows */
-        CUDA_OK(copy_rows_async(st->d_src[0] + (size_t)y0 * st->d_src_stride[0], st->d_src_stride[0],
-                                  src[0] + (size_t)y0 * src_stride[0], src_stride[0], st->src_rowbytes[0],
-                                  y1 - y0, cudaMemcpyHostToDevice, st->s_in));
-        int chi = y1 == p->dst_h ? p->chr_src_h : st->h_vc_pos[y1 - 1] + 4;
-        if (chi > p->chr_src_h)
-            chi = p->chr_src_h;
-        if (chi > cup) {
-            for (int i = 1; i < 3 && st->src_rows[i]; i++)     /* U and V planes, or the one UV plane */
-                CUDA_OK(copy_rows_async(st->d_src[i] + (size_t)cup * st->d_src_stride[i], st->d_src_stride[i],
-                                          src[i] + (size_t)cup * src_stride[i], src_stride[i],
-                                          st->src_rowbytes[i], chi - cup, cudaMemcpyHostToDevice, st->s_in));
-            cup = chi;
-        }
-        CUDA_OK(cudaEventRecord(st->ev_in[k], st->s_in));
-        CUDA_OK(cudaStreamWaitEvent(st->stream, st->ev_in[k], 0));
-        int r;
-        if (store_to_host)
-            r = fast420_launch(st, st->d_src, st->d_src_stride, zero, ddst, dst_stride, zero, 1, y0, y1, st->stream);
-        else
-            r = fast420_launch(st, st->d_src, st->d_src_stride, zero, st->d_dst, st->d_dst_stride, zero, 1, y0, y1,
-                               st->stream);
-        if (r < 0)
-            return r;
-        if (r == 0) {                              /* cannot happen for staging buffers; be safe */
-            cudaStreamSynchronize(st->s_in);
-            cudaStreamSynchronize(st->stream);
-            return 1;
-        }
-        if (!store_to_host) {
-            CUDA_OK(cudaEventRecord(st->ev_k[k], st->stream));
-            CUDA_OK(cudaStreamWaitEvent(st->s_out, st->ev_k[k], 0));
-            CUDA_OK(copy_rows_async(dst[0] + (size_t)y0 * dst_stride[0], dst_stride[0],
-                                      st->d_dst[0] + (size_t)y0 * st->d_dst_stride[0], st->d_dst_stride[0],
-                                      st->dst_rowbytes[0], y1 - y0, cudaMemcpyDeviceToHost, st->s_out));
-        }
-    }
-    if (store_to_host)
-        CUDA_OK(cudaStreamSynchronize(st->stream));
-    else
-        CUDA_OK(cudaStreamSynchronize(st->s_out));
-    return 0;
-}
-
-extern "C" int ff_b200_cuda_scale_host(SwsCudaState *st,
-                                       const uint8_t *const src[4], const int src_stride[4],
-                                       int src_y, int src_h, int upload,
-                                       uint8_t *const dst[4], const int dst_stride[4], int y0, int y1)
-{
-    const SwsCudaPlan *p = &st->plan;
-    int ret;
-
-    /* Page-locked caller frames (cudaHostAlloc / cudaHostRegister, e.g. sws_cuda_host_alloc) let a
-     * single synchronous sws_scale() overlap PCIe traffic in both directions.  e2e_mode:
-     *   0  serial   : H2D, kernel, D2H back to back (also the path for pageable frames)
-     *   1  zero-copy: the TMA kernel reads and writes the host frames directly
-     *   2  chunked  : row bands pipelined over three streams (H2D | kernel | D2H)
-     *   3  chunked H2D + kernel writing the host destination directly */
-    if (st->fast_ok && !(st->disabled & 1) && st->e2e_mode && src_y == 0 && src_h == p->src_h && y0 == 0 && y1 == p->dst_h) {
-        const uint8_t *dsrc[4] = { nullptr, nullptr, nullptr, nullptr };
-        uint8_t *ddst[4] = { nullptr, nullptr, nullptr, nullptr };
-        bool ok = true;
-        const int nb_src = p->src_layout == SWSC_SRC_PLANAR ? 3 : 2;
-        for (int i = 0; i < nb_src && ok; i++) {
-            cudaPointerAttributes at;
-            if (!src[i] || cudaPointerGetAttributes(&at, src[i]) != cudaSuccess ||
-                at.type != cudaMemoryTypeHost || !at.devicePointer)
-                ok = false;
-            else
-                dsrc[i] = (const uint8_t *)at.devicePointer;
-        }
-        if (ok) {
-            cudaPointerAttributes at;
-            if (!dst[0] || cudaPointerGetAttributes(&at, dst[0]) != cudaSuccess ||
-                at.type != cudaMemoryTypeHost || !at.devicePointer)
-                ok = false;
-            else
-                ddst[0] = (uint8_t *)at.devicePointer;
-        }
-        cudaGetLastError();   /* pageable pointers make cudaPointerGetAttributes report an error */
-        if (ok && st->e2e_mode == 1) {
-            int r = fast420_launch(st, dsrc, src_stride, nullptr, ddst, dst_stride, nullptr, 1, 0, p->dst_h, st->stream);
-            if (r < 0)
-                return r;
-            if (r == 1) {
-                CUDA_OK(cudaStreamSynchronize(st->stream));
-                return 0;
-            }
-        } else if (ok && (st->e2e_mode == 2 || st->e2e_mode == 3)) {
-            int r = pipelined_host_frame(st, src, src_stride, dst, dst_stride, ddst,
-                                         st->e2e_mode == 3 && aligned16(ddst[0]) && !(dst_stride[0] & 15));
-            if (r <= 0)
-                return r;
-        }
-    }
-
-    ret = ensure_staging(st);
-    if (ret < 0)
-        return ret;
-    if (upload) {
-        for (int i = 0; i < 3; i++) {
-            if (!st->src_rows[i])
-                continue;
-            if (!src[i])
-                return AVERROR(EINVAL);
-            const int vs = i ? p->chr_src_vsub : 0;
-            const int r0 = src_y >> vs;
-            int r1 = -((-(src_y + src_h)) >> vs);
-            if (r1 > st->src_rows[i])
-                r1 = st->src_rows[i];
-            /* slice pointers address the first row of the slice (swscale.h:566-576) */
-            CUDA_OK(copy_rows_async(st->d_src[i] + (size_t)r0 * st->d_src_stride[i], st->d_src_stride[i],
-                                      src[i], src_stride[i], st->src_rowbytes[i], r1 - r0,
-                                      cudaMemcpyHostToDevice, st->stream));
-        }
-    }
-    if (y1 > y0) {
-        int64_t zero[4] = { 0, 0, 0, 0 };
-        ret = ff_b200_cuda_launch(st, st->d_src, st->d_src_stride, zero, st->d_dst, st->d_dst_stride, zero, 1, y0, y1);
-        if (ret < 0)
-            return ret;
-        for (int i = 0; i < 3; i++) {
-            if (!st->dst_rows[i])
-                continue;
-            if (!dst[i])
-                return AVERROR(EINVAL);
-            const int vs = i ? p->chr_dst_vsub : 0;
-            const int r0 = y0 >> vs;
-            int r1 = (y1 == p->dst_h) ? st->dst_rows[i] : (y1 >> vs);
-            if (r1 <= r0)
-                continue;
-            CUDA_OK(copy_rows_async(dst[i] + (size_t)r0 * dst_stride[i], dst_stride[i],
-                                      st->d_dst[i] + (size_t)r0 * st->d_dst_stride[i], st->d_dst_stride[i],
-                                      st->dst_rowbytes[i], r1 - r0, cudaMemcpyDeviceToHost, st->stream));
-        }
-    }
-    CUDA_OK(cudaStreamSynchronize(st->stream));
-    return 0;
-}
+#include "sws_xfer.cuh"
 
 extern "C" int ff_b200_cuda_sync(SwsCudaState *st)
 {
+    DeviceGuard guard(st->device);
     CUDA_OK(cudaStreamSynchronize(st->stream));
     return 0;
 }

@@ -111,6 +111,10 @@ enum {
     SWSC_DST_BGR565,
     SWSC_DST_RGB555,
     SWSC_DST_BGR555,
+    SWSC_DST_RGBA64,       /* 16-bit packed RGB with alpha (output.c:1115-1196, hasAlpha) */
+    SWSC_DST_BGRA64,
+    SWSC_DST_GBRP,         /* planar RGB, plane order G, B, R [, A] (output.c:2378-2610) */
+    SWSC_DST_PLANARF32,    /* 32-bit float planes (output.c:219-316) */
 };
 
 /* unscaled converters the reference installs instead of the scaler (swscale_unscaled.c) */
@@ -135,7 +139,9 @@ typedef struct SwsCudaPlan {
     int dst_shift;               /* left shift of 16-bit destination samples (p010: 6) */
     int inter_bits;              /* 15 or 19: width of the h-scaled lines     */
     int h_shift;                 /* right shift applied after the H FIR       */
-    int has_chroma;              /* 0 for gray sources/destinations           */
+    int has_chroma;              /* 0 for gray sources                        */
+    int dst_has_chroma;          /* 0 for gray destinations                   */
+    int src_alpha, dst_alpha;    /* an alpha plane / channel is read / written through the scaler */
     int unscaled_lut;            /* 1: reference would take convert_unscaled  */
     int special;                 /* whole-frame special converter, SWSC_SPECIAL_* */
     int shuf_map[4];             /* SHUFFLE: source byte of every destination byte, 4 = constant 255 */
@@ -219,6 +225,10 @@ typedef struct SwsInternal {
 } SwsInternal;
 
 static inline SwsInternal *sws_internal(const SwsContext *s) { return (SwsInternal *)s; }
+
+void ff_b200_option_defaults(SwsContext *s);
+int ff_b200_scale_frame_rows(SwsInternal *c, const uint8_t *const src[4], const int srcStride[4],
+                             uint8_t *const dst[4], const int dstStride[4], int y0, int y1);
 
 #ifdef __cplusplus
 }

@@ -314,3 +314,48 @@ API void swsref_hw_offsets(int out[16])
     out[i++] = offsetof(AVHWFramesContext, width);      out[i++] = offsetof(AVHWFramesContext, height);
     out[i++] = AV_HWDEVICE_TYPE_CUDA;                   out[i++] = AV_PIX_FMT_CUDA;
 }
+
+/* the reference's AVOption table, one line per entry (tests/test_options_cpu.py holds ours against it) */
+#include "libavutil/opt.h"
+#include <inttypes.h>
+#include <stdio.h>
+API int swsref_dump_options(char *buf, int size)
+{
+    SwsContext *s = sws_alloc_context();
+    const AVOption *o = NULL;
+    int n = 0;
+    if (!s)
+        return -1;
+    while ((o = av_opt_next(s, o)) && n < size)
+        n += snprintf(buf + n, size - n, "opt %s|%s|%d|%d|%" PRId64 "|%g|%g|%g|%d|%s\n", o->name, o->help ? o->help : "",
+                      o->offset, (int)o->type, o->type == AV_OPT_TYPE_DOUBLE ? 0 : o->default_val.i64,
+                      o->type == AV_OPT_TYPE_DOUBLE ? o->default_val.dbl : 0.0, o->min, o->max, o->flags,
+                      o->unit ? o->unit : "");
+    sws_free_context(&s);
+    return n;
+}
+
+#ifdef SWSREF_HOOKED
+/* ---- integration/build_hooked.py only: the reference built with ff_sws_init_swscale_cuda() ---- */
+/* kernels launched by the B200 context behind this reference context (-1: the hook is not installed,
+ * the C kernels run); cascaded sub-contexts are summed */
+API long swsref_hook_launches(void *ctx)
+{
+    SwsInternal *c = first_ctx(ctx);
+    long n = ff_sws_cuda_launches(c), any = n >= 0;
+    if (n < 0)
+        n = 0;
+    for (int i = 0; i < 3; i++)
+        if (c->cascaded_context[i]) {
+            long k = swsref_hook_launches(c->cascaded_context[i]);
+            if (k >= 0) {
+                n += k;
+                any = 1;
+            }
+        }
+    return any ? n : -1;
+}
+API const char *swsref_hook_kernel(void *ctx) { return ff_sws_cuda_kernel(first_ctx(ctx)); }
+/* slices any context of this process handed to the GPU so far (covers the contexts sws_scale_frame() builds internally) */
+API long swsref_hook_slices_total(void) { return ff_sws_cuda_slices_total(); }
+#endif

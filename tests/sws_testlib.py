@@ -39,6 +39,8 @@ def plane_layout(fmt, w, h):
         return [(h, w * 2), (cdiv(h, 1), cdiv(w, 1) * 4)]
     if fmt == "gray":
         return [(h, w)]
+    if fmt == "gbrp":
+        return [(h, w)] * 3
     for key, (cw, ch) in _YUV.items():
         for pre in ("yuv", "yuvj"):
             if fmt.startswith(pre + key + "p"):
