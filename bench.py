@@ -13,7 +13,10 @@ are partitioned across ranks with no data-path collective (weak scaling).
 value   : Mpixels/s, whole job, frames already resident in HBM (one batched
           launch per step through sws_cuda_scale_batch()).
 e2e     : Mpixels/s through the reference-facing call sws_scale() with HOST
-          (pinned) buffers -- H2D + kernel + D2H inside the timed region.
+          (page-locked) buffers -- H2D + kernel + D2H inside the timed region.
+e2e_pageable   : the same call on plain pageable numpy buffers (what av_frame_get_buffer() hands a caller).
+e2e_batch_host : sws_cuda_scale_batch_host(), several host frames in flight per device.
+configs : BASELINE.json configs[0..3] (C1..C4) device-resident, same method as `value` (N=1 only).
 roofline: algorithmic bytes (4.5 B/pixel) / average kernel
           duration, against MEASURED_PEAKS.json hbm_gbs.
 cpu_baseline: the real reference C path (oracle/_ref) on the host cores, bounded sample.
@@ -57,19 +60,14 @@ def run_reference_arm(args, rank, world):
     import numpy as np
     cores = host_cores()
     ctx = R.RefContext(W, H, "yuv420p", W, H, "rgb24", R.SWS_BICUBIC | R.BX, threads=cores)
-    src = R.RefFrame(W, H, "yuv420p")
-    dst = R.RefFrame(W, H, "rgb24")
-    rng = np.random.default_rng(1234)
-    for i, rows in enumerate((H, H // 2, H // 2)):
-        a, ls = src.plane(i, rows)
-        a[:] = rng.integers(0, 256, a.shape, dtype=np.uint8)
+    ring, dsts, srcs = _ref_ring(R, np)
     frames_per_step = 8          # bounded sample of the 64-frame step
     L = R.lib()
     for _ in range(max(args.warmup, 1)):
-        L.swsref_bench_frame(ctx.h, dst.f, src.f, 2)
+        L.swsref_bench_frames(ctx.h, dsts, srcs, ring, ring)
     t = 0.0
     for _ in range(args.steps):
-        dt = L.swsref_bench_frame(ctx.h, dst.f, src.f, frames_per_step)
+        dt = L.swsref_bench_frames(ctx.h, dsts, srcs, ring, frames_per_step)
         if dt < 0:
             raise RuntimeError("reference sws_scale_frame failed")
         t += dt
@@ -79,15 +77,42 @@ def run_reference_arm(args, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": frames_per_step,
-                   "note": "reference C path (sws_scale_frame, slice-threaded) on host cores; "
-                           "bounded sample of the 64-frame step"},
+        "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": FRAMES_PER_GPU,
+                   "bytes_per_step_per_gpu": int(ALG_BYTES_PER_PIXEL * FRAMES_PER_GPU * W * H),
+                   "note": "reference C path (sws_scale_frame, slice-threaded) on the host cores; each timed step "
+                           "is a bounded sample (%d frames out of a ring of %d distinct ones) of the %d-frame step; "
+                           "generic C build (no hand-written SIMD is selected on the bit-exact accurate_rnd path)"
+                           % (frames_per_step, ring, FRAMES_PER_GPU)},
         "cpu_baseline": {"value": mpix, "unit": "Mpixels/s", "cores": cores, "kind": "reference",
-                         "sample": "%d frames x %d steps, threads=%d" % (frames_per_step, args.steps, cores)},
+                         "sample": "%d frames x %d steps over a ring of %d distinct 4K frames, threads=%d"
+                                   % (frames_per_step, args.steps, ring, cores)},
         "e2e": {"value": mpix, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+_REF_KEEP = []
+
+
+def _ref_ring(R, np, ring=8):
+    """`ring` distinct 4K source/destination AVFrame pairs (300 MB: beyond the last-level cache) for the
+    reference arm, as ctypes arrays of frame pointers."""
+    rng = np.random.default_rng(1234)
+    srcs, dsts = [], []
+    for _ in range(ring):
+        s, d = R.RefFrame(W, H, "yuv420p"), R.RefFrame(W, H, "rgb24")
+        for i, rows in enumerate((H, H // 2, H // 2)):
+            a, ls = s.plane(i, rows)
+            a[:] = rng.integers(0, 256, a.shape, dtype=np.uint8)
+        srcs.append(s)
+        dsts.append(d)
+    _REF_KEEP.extend(srcs + dsts)
+    L = R.lib()
+    L.swsref_bench_frames.restype = ctypes.c_double
+    L.swsref_bench_frames.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                      ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int]
+    return ring, (ctypes.c_void_p * ring)(*[f.f for f in dsts]), (ctypes.c_void_p * ring)(*[f.f for f in srcs])
 
 
 def cpu_baseline_sample(seconds=12.0):
@@ -98,27 +123,23 @@ def cpu_baseline_sample(seconds=12.0):
     import numpy as np
     cores = host_cores()
     out = {}
-    rng = np.random.default_rng(1234)
-    src = R.RefFrame(W, H, "yuv420p")
-    dst = R.RefFrame(W, H, "rgb24")
-    for i, rows in enumerate((H, H // 2, H // 2)):
-        a, ls = src.plane(i, rows)
-        a[:] = rng.integers(0, 256, a.shape, dtype=np.uint8)
+    ring, dsts, srcs = _ref_ring(R, np)
     L = R.lib()
     for label, threads in (("threads_all", cores), ("threads_1", 1)):
         ctx = R.RefContext(W, H, "yuv420p", W, H, "rgb24", R.SWS_BICUBIC | R.BX, threads=threads)
-        L.swsref_bench_frame(ctx.h, dst.f, src.f, 1)
+        L.swsref_bench_frames(ctx.h, dsts, srcs, ring, 1)
         n, t = 0, 0.0
         budget = seconds * (0.7 if threads > 1 else 0.3)
         while t < budget:
-            k = 4 if threads > 1 else 1
-            t += L.swsref_bench_frame(ctx.h, dst.f, src.f, k)
+            k = 8 if threads > 1 else 1
+            t += L.swsref_bench_frames(ctx.h, dsts, srcs, ring, k)
             n += k
         out[label] = (n * W * H / t / 1e6, n, t)
         ctx.close()
     return {"value": out["threads_all"][0], "unit": "Mpixels/s", "cores": cores, "kind": "reference",
-            "sample": "%d 4K frames in %.1f s with %d threads (sws_scale_frame, bitexact+accurate_rnd C path); "
-                      "1 thread: %.1f Mpixels/s" % (out["threads_all"][1], out["threads_all"][2], cores,
+            "sample": "%d 4K frames (ring of %d distinct ones) in %.1f s with %d threads (sws_scale_frame, "
+                      "bitexact+accurate_rnd generic-C path: no hand-written SIMD is selected there); "
+                      "1 thread: %.1f Mpixels/s" % (out["threads_all"][1], ring, out["threads_all"][2], cores,
                                                     out["threads_1"][0])}
 
 
@@ -176,6 +197,9 @@ def run_b200_arm(args, rank, local_rank, world):
         raise RuntimeError("bench.py needs a CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # run next to the GPU: this rank's thread and every page-locked frame it allocates live on the NUMA node
+    # the device hangs off (SWS_B200_NUMA=0 switches it off for A/B runs)
+    numa = {"node": S.device_numa_node(local_rank), "cpus_bound": S.bind_thread_to_device(local_rank)}
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -250,37 +274,70 @@ def run_b200_arm(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
 
-    # ---- e2e: sws_scale() on pinned HOST frames, H2D + kernel + D2H timed ----
+    # ---- e2e: sws_scale() on HOST frames, H2D + kernel + D2H timed ----
     EF = E2E_FRAMES
-    h_y = torch.empty((EF, ysz), dtype=torch.uint8).pin_memory()
-    h_u = torch.empty((EF, csz), dtype=torch.uint8).pin_memory()
-    h_v = torch.empty((EF, csz), dtype=torch.uint8).pin_memory()
-    h_o = torch.empty((EF, osz), dtype=torch.uint8).pin_memory()
-    h_y.copy_(src_y[:EF]); h_u.copy_(src_u[:EF]); h_v.copy_(src_v[:EF])
-    torch.cuda.synchronize()
+    host_src = src_y[:EF].cpu().numpy(), src_u[:EF].cpu().numpy(), src_v[:EF].cpu().numpy()
+    sizes = (ysz, csz, csz, osz)
 
-    def e2e_step():
-        for f in range(EF):
-            r = ctx.scale([h_y[f].data_ptr(), h_u[f].data_ptr(), h_v[f].data_ptr()], [W, W // 2, W // 2],
-                          [h_o[f].data_ptr()], [W * 3], 0, H)
+    def host_buffers(pinned):
+        if pinned:          # sws_cuda_host_alloc(): page-locked, on the NUMA node of this rank's device
+            bufs = [S.PinnedBuffer(EF * n) for n in sizes]
+            arrs = [b.array.reshape(EF, n) for b, n in zip(bufs, sizes)]
+        else:               # plain pageable memory, what av_frame_get_buffer() / malloc hand a caller
+            bufs = None
+            arrs = [np.empty((EF, n), dtype=np.uint8) for n in sizes]
+        for a, h in zip(arrs[:3], host_src):
+            a[:] = h
+        arrs[3][:] = 0
+        return bufs, arrs
+
+    def time_e2e(fn):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        n = max(1, min(args.steps, 5))
+        for _ in range(n):
+            fn()
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if dist:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return world * EF * n * W * H / float(te.item()) / 1e6
+
+    def per_frame(arrs):
+        ptrs = [[a[f].ctypes.data for a in arrs] for f in range(EF)]
+
+        def fn():
+            for f in range(EF):
+                r = ctx.scale(ptrs[f][:3], [W, W // 2, W // 2], [ptrs[f][3]], [W * 3], 0, H)
+                if r != H:
+                    raise RuntimeError("sws_scale failed: %d %s" % (r, ctx.last_error))
+        return fn
+
+    def batched(arrs):
+        def fn():
+            r = ctx.scale_batch_host([a.ctypes.data for a in arrs[:3]], [W, W // 2, W // 2], [ysz, csz, csz],
+                                     [arrs[3].ctypes.data], [W * 3], [osz], EF, 1, 0)
             if r != H:
-                raise RuntimeError("sws_scale failed: %d" % r)
+                raise RuntimeError("sws_cuda_scale_batch_host failed: %d %s" % (r, ctx.last_error))
+        return fn
 
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if dist:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_mpix = world * EF * e2e_steps * W * H / float(te.item()) / 1e6
-    if rank == 0 and parity is not None:
-        # the host path must give the same bytes as the device path
-        assert np.array_equal(h_o[0].numpy(), dst[0].cpu().numpy()), "host and device paths disagree"
+    want0 = dst[0].cpu().numpy() if (rank == 0 and parity is not None) else None
+    pin_bufs, pin_arrs = host_buffers(True)
+    e2e_mpix = time_e2e(per_frame(pin_arrs))
+    if want0 is not None:       # the host path must give the same bytes as the device path
+        assert np.array_equal(pin_arrs[3][0], want0), "host and device paths disagree"
+    pin_arrs[3][:] = 0
+    e2e_batch = time_e2e(batched(pin_arrs))
+    if want0 is not None:
+        assert np.array_equal(pin_arrs[3][0], want0), "batched host path and device path disagree"
+    _, pag_arrs = host_buffers(False)
+    e2e_pageable = time_e2e(per_frame(pag_arrs))
+    if want0 is not None:
+        assert np.array_equal(pag_arrs[3][0], want0), "pageable host path and device path disagree"
+    pin_arrs = None
+    for b in pin_bufs:
+        b.close()
 
     if rank != 0:
         if dist:
@@ -309,6 +366,22 @@ def run_b200_arm(args, rank, local_rank, world):
     except Exception:
         pass
 
+    # ---- the other BASELINE configurations, device-resident, same method (N=1: the box is otherwise idle) ----
+    configs = None
+    if world == 1 and not args.no_configs:
+        from tools import bench_configs as BC
+        configs = {}
+        for cfg in BC.CONFIGS:
+            tag = cfg[0].split()[0]
+            if tag not in ("C1", "C2", "C3", "C4"):
+                continue
+            r = BC.measure(cfg, dev, peak, steps=max(5, min(args.steps, 20)))
+            configs[tag] = {"workload": r["name"], "kernel": r["kernel"], "frames_per_step": r["frames"],
+                            "ms_per_step": r["ms"], "value": r["mpix_in"], "unit": "Mpixels/s (source pixels)",
+                            "mpix_out": r["mpix_out"],
+                            "roofline": {"bound": "hbm", "achieved": r["gbs"], "peak": peak, "unit": "GB/s",
+                                         "frac": r["frac"], "algorithmic_bytes_per_launch": r["algorithmic_bytes"]}}
+
     line = {
         "metric": "Mpixels/s", "value": value, "unit": "Mpixels/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
@@ -321,15 +394,26 @@ def run_b200_arm(args, rank, local_rank, world):
                    "partition": "frames round-robin over ranks, no collective",
                    "kernel": ctx.kernel_name, "parity_checked_vs_reference": parity},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                       "ncu --set full capture of this launch shape; not measured in this run)",
+                     "peak_source": peak_src,
                      "kernel": ctx.kernel_name, "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": bytes_per_launch},
         "e2e": {"value": e2e_mpix, "unit": "Mpixels/s",
                 "h2d_bytes_per_step": int(EF * (ysz + 2 * csz)), "d2h_bytes_per_step": int(EF * osz),
-                "frames_per_step": EF, "call": "sws_scale() per frame, pinned host buffers"},
+                "frames_per_step": EF,
+                "call": "sws_scale() per frame, page-locked host buffers (sws_cuda_host_alloc)"},
+        "e2e_pageable": {"value": e2e_pageable, "unit": "Mpixels/s", "frames_per_step": EF,
+                         "call": "sws_scale() per frame, pageable numpy buffers (bounce ring + copy threads)"},
+        "e2e_batch_host": {"value": e2e_batch, "unit": "Mpixels/s", "frames_per_step": EF,
+                           "call": "sws_cuda_scale_batch_host(), page-locked buffers, 3 frames in flight"},
+        "numa": numa,
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
+    if configs:
+        line["configs"] = configs
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline_sample()
         if cb:
@@ -346,6 +430,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

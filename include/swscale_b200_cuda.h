@@ -34,6 +34,21 @@ int sws_cuda_scale_batch(SwsContext *c,
                          uint8_t *const dst[4], const int dstStride[4],
                          const int64_t dstFrameStride[4], int nb_frames);
 
+/*
+ * The same for HOST frames (pageable or page-locked): frame f of plane p lives at src[p] + f * srcFrameStride[p].
+ * Synchronous: every frame is in dst when the call returns.  Frames share nothing, so frame f goes to device
+ * f mod nb_devices (nb_devices <= 0: every visible device), and on each device `depth` frames are in flight
+ * at once (depth <= 0: 3 -- upload of one, kernel of another, download of a third), each on its own stream
+ * and staging set; worker threads run next to their device (NUMA).  One process drives the whole box; no
+ * collective is involved (BASELINE.json configs[4]: a batch round-robin across 8 GPUs).
+ * Returns dst_h on success or a negative AVERROR.
+ */
+int sws_cuda_scale_batch_host(SwsContext *c,
+                              const uint8_t *const src[4], const int srcStride[4],
+                              const int64_t srcFrameStride[4],
+                              uint8_t *const dst[4], const int dstStride[4],
+                              const int64_t dstFrameStride[4], int nb_frames, int nb_devices, int depth);
+
 /* Block until all work queued on the context's stream has finished. */
 int sws_cuda_sync(SwsContext *c);
 
@@ -52,6 +67,13 @@ const char *sws_cuda_last_error(SwsContext *c);
 /* Page-locked host memory for callers that want DMA-speed sws_scale() (optional). */
 void *sws_cuda_host_alloc(size_t size);
 void  sws_cuda_host_free(void *ptr);
+
+/* NUMA placement on multi-socket hosts.  sws_cuda_host_alloc() already places its pages on the NUMA node of
+ * the current CUDA device; sws_cuda_bind_thread_to_device() moves the calling thread next to a device as well
+ * (returns the number of CPUs in the new affinity set, -1 if the topology is unknown: nothing changed).
+ * SWS_B200_NUMA=0 disables both. */
+int sws_cuda_bind_thread_to_device(int device);
+int sws_cuda_device_numa_node(int device);
 
 /* ---- diagnostics (used by the CPU-only test-suite; no device is touched) ----
  * sws_b200_plan_only(): run everything sws_init_context() (reference utils.c:1884)

@@ -38,7 +38,7 @@ OBJ = os.path.join(OUT, "obj")
 SO = os.path.join(OUT, "libswsref_hooked.so")
 CSRC = os.path.join(ROOT, "librempeg_b200", "csrc")
 B200_C = ["sws_context.c", "sws_filter.c", "sws_colorspace.c", "sws_pixfmt.c", "sws_frame.c", "sws_compat.c",
-          "sws_hook.c", "sws_options.c"]
+          "sws_hook.c", "sws_options.c", "sws_numa.c"]
 
 
 def run(cmd):

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(HERE, "libswscale_b200.so")
 
 C_SOURCES = ["sws_context.c", "sws_filter.c", "sws_colorspace.c", "sws_pixfmt.c", "sws_frame.c", "sws_compat.c",
-             "sws_hook.c", "sws_options.c"]
+             "sws_hook.c", "sws_options.c", "sws_numa.c"]
 CU_SOURCES = ["sws_cuda.cu"]
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

@@ -17,6 +17,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <pthread.h>
+
 #include "sws_internal.h"
 
 #define LIBSWSCALE_VERSION_MAJOR 10
@@ -53,8 +55,18 @@ SwsContext *sws_alloc_context(void)
     return &c->opts;
 }
 
+static void release_lanes(SwsInternal *c)
+{
+    for (int i = 0; i < c->nb_lanes; i++)
+        if (c->lanes[i])
+            ff_b200_cuda_destroy(c->lanes[i]);
+    memset(c->lanes, 0, sizeof(c->lanes));
+    c->nb_lanes = 0;
+}
+
 static void release_tables(SwsInternal *c)
 {
+    release_lanes(c);
     if (c->cuda)
         ff_b200_cuda_destroy(c->cuda);
     c->cuda = NULL;
@@ -229,6 +241,7 @@ int sws_setColorspaceDetails(SwsContext *sws, const int inv_table[4], int srcRan
         return -1;
     }
     c->refused = 0;
+    release_lanes(c);               /* lanes carry copies of the plan: rebuilt on the next batch call */
     plan_range_convert(c);
     if (plan_colorspace(c) < 0)
         return -1;
@@ -1002,6 +1015,116 @@ int sws_cuda_scale_batch(SwsContext *sws, const uint8_t *const src[4], const int
     ret = ff_b200_cuda_launch(c->cuda, src, srcStride, srcFrameStride, dst, dstStride,
                               dstFrameStride, nb_frames, 0, sws->dst_h);
     return ret < 0 ? ret : sws->dst_h;
+}
+
+/* ---- host frames, several in flight, all visible devices (frames round-robin) ---- */
+
+typedef struct LaneJob {
+    SwsInternal *c;
+    SwsCudaState *st;
+    int lane, nb_lanes, nb_frames, own_thread;
+    const uint8_t *const *src; const int *src_stride; const int64_t *src_fstride;
+    uint8_t *const *dst; const int *dst_stride; const int64_t *dst_fstride;
+    int ret;
+} LaneJob;
+
+static void *lane_main(void *arg)
+{
+    LaneJob *j = arg;
+    const SwsInternal *c = j->c;
+    if (j->own_thread)              /* never touch the affinity of the caller's thread */
+        sws_cuda_bind_thread_to_device(ff_b200_cuda_device_of(j->st));
+    /* frame f belongs to lane f mod nb_lanes, and lane l to device l mod nb_devices: consecutive frames land
+     * on different devices, consecutive frames of one device on different lanes */
+    for (int f = j->lane; f < j->nb_frames; f += j->nb_lanes) {
+        const uint8_t *s[4];
+        uint8_t *d[4];
+        for (int i = 0; i < 4; i++) {
+            s[i] = j->src[i] ? j->src[i] + (j->src_fstride ? j->src_fstride[i] : 0) * f : NULL;
+            d[i] = j->dst[i] ? j->dst[i] + (j->dst_fstride ? j->dst_fstride[i] : 0) * f : NULL;
+        }
+        j->ret = ff_b200_cuda_scale_host(j->st, s, j->src_stride, 0, c->opts.src_h, 1, d, j->dst_stride, 0, c->opts.dst_h);
+        if (j->ret < 0)
+            break;
+    }
+    return NULL;
+}
+
+int sws_cuda_scale_batch_host(SwsContext *sws, const uint8_t *const src[4], const int srcStride[4],
+                              const int64_t srcFrameStride[4], uint8_t *const dst[4],
+                              const int dstStride[4], const int64_t dstFrameStride[4],
+                              int nb_frames, int nb_devices, int depth)
+{
+    SwsInternal *c = sws_internal(sws);
+    LaneJob jobs[SWS_B200_MAX_LANES];
+    pthread_t tid[SWS_B200_MAX_LANES];
+    int started[SWS_B200_MAX_LANES] = { 0 };
+    int visible, lanes, ret = 0;
+    if (!c || !c->initialized || !src || !dst || nb_frames < 1 || !srcStride || !dstStride ||
+        (nb_frames > 1 && (!srcFrameStride || !dstFrameStride)))
+        return AVERROR(EINVAL);
+    if (c->refused) {
+        set_error(c, "the last sws_setColorspaceDetails() asked for a conversion that is not on the CUDA hot path");
+        return AVERROR(ENOTSUP);
+    }
+    visible = sws_cuda_device_count();
+    if (nb_devices <= 0 || nb_devices > visible)
+        nb_devices = visible;
+    if (depth <= 0)
+        depth = 3;                      /* H2D of one frame, kernel of another, D2H of a third */
+    if (nb_devices * depth > SWS_B200_MAX_LANES)
+        depth = SWS_B200_MAX_LANES / nb_devices;
+    lanes = nb_devices * depth;
+    if (lanes > nb_frames)
+        lanes = nb_frames;
+    if (c->nb_lanes && (c->lanes_devices != nb_devices || c->lanes_depth != depth))
+        release_lanes(c);
+    /* every lane is a clone of the context's device state with its own stream and staging set
+     * (tables < 1 MB per lane) */
+    for (int l = c->nb_lanes; l < lanes; l++) {
+        SwsCudaPlan plan = c->plan;
+        /* the rotation starts at the context's own device: lane l -> device (base + l mod nb_devices) */
+        const int dev = (ff_b200_cuda_device_of(c->cuda) + l % nb_devices) % visible;
+        int r = ff_b200_cuda_create_on(dev, &c->lanes[l], &plan, &c->h_lum, &c->h_chr, &c->v_lum, &c->v_chr);
+        if (r < 0) {
+            if (c->lanes[l])
+                ff_b200_cuda_destroy(c->lanes[l]);
+            c->lanes[l] = NULL;
+            set_error(c, "could not create lane %d of the host batch (%d)", l, r);
+            return r;
+        }
+        c->nb_lanes = l + 1;
+    }
+    c->lanes_devices = nb_devices;
+    c->lanes_depth = depth;
+
+    for (int l = 0; l < lanes; l++) {
+        LaneJob *j = &jobs[l];
+        j->c = c; j->st = c->lanes[l]; j->lane = l; j->nb_lanes = lanes; j->nb_frames = nb_frames;
+        j->src = src; j->src_stride = srcStride; j->src_fstride = srcFrameStride;
+        j->dst = dst; j->dst_stride = dstStride; j->dst_fstride = dstFrameStride;
+        j->ret = 0;
+        j->own_thread = l != lanes - 1;
+        if (l == lanes - 1) {
+            lane_main(j);               /* the calling thread works too */
+        } else if (pthread_create(&tid[l], NULL, lane_main, j) == 0) {
+            started[l] = 1;
+        } else {
+            j->own_thread = 0;
+            lane_main(j);
+        }
+    }
+    for (int l = 0; l < lanes; l++) {
+        if (started[l])
+            pthread_join(tid[l], NULL);
+        if (jobs[l].ret < 0 && ret >= 0)
+            ret = jobs[l].ret;
+    }
+    if (ret < 0) {
+        set_error(c, "host batch conversion failed (%d)", ret);
+        return ret;
+    }
+    return sws->dst_h;
 }
 
 int sws_cuda_sync(SwsContext *sws)

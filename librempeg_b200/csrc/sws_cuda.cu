@@ -1450,14 +1450,59 @@ extern "C" int sws_cuda_device_count(void)
     return n;
 }
 
+/* NUMA node the PCIe root of a device hangs off (-1: unknown or single-node box) */
+static int device_numa_node(int dev)
+{
+    static int cache[64];
+    static bool known[64];
+    if (dev < 0 || dev >= 64)
+        return -1;
+    if (!known[dev]) {
+        char id[32] = { 0 };
+        cache[dev] = -1;
+        if (cudaDeviceGetPCIBusId(id, sizeof(id), dev) == cudaSuccess)
+            cache[dev] = ff_b200_numa_node_of_pci(id);
+        else
+            cudaGetLastError();
+        known[dev] = true;
+    }
+    return cache[dev];
+}
+
+/* page-locked memory on the NUMA node of the current device: DMA does not cross the inter-socket link */
+static cudaError_t host_alloc_local(void **p, size_t size)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess)
+        dev = -1;
+    const int node = device_numa_node(dev);
+    const bool bound = node >= 0 && ff_b200_numa_prefer(node) == 0;
+    cudaError_t e = cudaHostAlloc(p, size, cudaHostAllocDefault);
+    if (bound)
+        ff_b200_numa_restore();
+    return e;
+}
+
 extern "C" void *sws_cuda_host_alloc(size_t size)
 {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, size, cudaHostAllocDefault) != cudaSuccess) {
+    if (host_alloc_local(&p, size) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
     return p;
+}
+
+/* Run the calling thread on the CPUs next to `device` (its NUMA node); returns the number of CPUs in the
+ * new affinity set, or -1 when the topology is unknown / SWS_B200_NUMA=0 (nothing changed). */
+extern "C" int sws_cuda_bind_thread_to_device(int device)
+{
+    return ff_b200_numa_bind_thread(device_numa_node(device));
+}
+
+extern "C" int sws_cuda_device_numa_node(int device)
+{
+    return device_numa_node(device);
 }
 
 extern "C" void sws_cuda_host_free(void *ptr)
@@ -2314,6 +2359,18 @@ static generic_kernel_t pick_generic(const SwsCudaPlan *p)
         return i32 ? sws_generic_tile_kernel<true, true> : sws_generic_tile_kernel<true, false>;
     return i32 ? sws_generic_tile_kernel<false, true> : sws_generic_tile_kernel<false, false>;
 }
+
+extern "C" int ff_b200_cuda_create_on(int device, SwsCudaState **out, SwsCudaPlan *plan,
+                                      const SwsFirBank *hl, const SwsFirBank *hc,
+                                      const SwsFirBank *vl, const SwsFirBank *vc)
+{
+    if (device < 0 || device >= sws_cuda_device_count())
+        return AVERROR(EINVAL);
+    DeviceGuard guard(device);
+    return ff_b200_cuda_create(out, plan, hl, hc, vl, vc);
+}
+
+extern "C" int ff_b200_cuda_device_of(SwsCudaState *st) { return st->device; }
 
 extern "C" int ff_b200_cuda_create(SwsCudaState **out, SwsCudaPlan *plan,
                                    const SwsFirBank *hl, const SwsFirBank *hc,

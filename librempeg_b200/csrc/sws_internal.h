@@ -65,6 +65,7 @@ typedef struct SwsFirSpec {
 } SwsFirSpec;
 
 #define SWS_B200_USE_CASCADE (-12345)
+#define SWS_B200_MAX_LANES 64
 
 int  ff_b200_build_fir(SwsFirBank *out, const SwsFirSpec *spec);
 void ff_b200_free_fir(SwsFirBank *b);
@@ -176,6 +177,11 @@ int  ff_b200_cuda_probe(void);    /* >=0: device ordinal in use, <0: AVERROR    
 int  ff_b200_cuda_create(SwsCudaState **st, SwsCudaPlan *plan,
                          const SwsFirBank *hl, const SwsFirBank *hc,
                          const SwsFirBank *vl, const SwsFirBank *vc);
+/* the same on an explicit device ordinal (the caller's current device is left alone) */
+int  ff_b200_cuda_create_on(int device, SwsCudaState **st, SwsCudaPlan *plan,
+                            const SwsFirBank *hl, const SwsFirBank *hc,
+                            const SwsFirBank *vl, const SwsFirBank *vc);
+int  ff_b200_cuda_device_of(SwsCudaState *st);
 void ff_b200_cuda_destroy(SwsCudaState *st);
 int  ff_b200_cuda_update_plan(SwsCudaState *st, const SwsCudaPlan *plan);
 /* device-resident frames; rows [y0,y1) of every frame; async on the context stream */
@@ -221,12 +227,21 @@ typedef struct SwsInternal {
     void *dyn_key;                   /* description it was planned for */
     const void *frame_src, *frame_dst;   /* sws_frame_start() .. sws_frame_end() */
     int frame_rows_sent, frame_uploaded;
+    /* lanes of sws_cuda_scale_batch_host(): extra device states (own stream, own staging) spread over the
+     * visible devices so that several host frames are in flight at once */
+    SwsCudaState *lanes[SWS_B200_MAX_LANES];
+    int nb_lanes, lanes_devices, lanes_depth;
     char last_error[256];
 } SwsInternal;
 
 static inline SwsInternal *sws_internal(const SwsContext *s) { return (SwsInternal *)s; }
 
 void ff_b200_option_defaults(SwsContext *s);
+/* NUMA placement of page-locked host memory and of the calling thread (sws_numa.c) */
+int  ff_b200_numa_node_of_pci(const char *bus_id);
+int  ff_b200_numa_prefer(int node);
+void ff_b200_numa_restore(void);
+int  ff_b200_numa_bind_thread(int node);
 int ff_b200_scale_frame_rows(SwsInternal *c, const uint8_t *const src[4], const int srcStride[4],
                              uint8_t *const dst[4], const int dstStride[4], int y0, int y1);
 

@@ -266,7 +266,7 @@ static int ensure_bounce(SwsCudaState *st, bool src_side)
         uint8_t **slot = src_side ? &st->h_src[i] : &st->h_dst[i];
         if (!rows || *slot)
             continue;
-        if (cudaHostAlloc((void **)slot, (size_t)pitch * rows, cudaHostAllocDefault) != cudaSuccess) {
+        if (host_alloc_local((void **)slot, (size_t)pitch * rows) != cudaSuccess) {
             cudaGetLastError();
             *slot = nullptr;
             return AVERROR(ENOMEM);

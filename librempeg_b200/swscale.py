@@ -100,6 +100,13 @@ def lib():
     L.sws_cuda_scale_batch.restype = C.c_int
     L.sws_cuda_scale_batch.argtypes = [ctxp, P(C.c_void_p), P(C.c_int), P(C.c_int64),
                                        P(C.c_void_p), P(C.c_int), P(C.c_int64), C.c_int]
+    L.sws_cuda_scale_batch_host.restype = C.c_int
+    L.sws_cuda_scale_batch_host.argtypes = [ctxp, P(C.c_void_p), P(C.c_int), P(C.c_int64),
+                                            P(C.c_void_p), P(C.c_int), P(C.c_int64), C.c_int, C.c_int, C.c_int]
+    L.sws_cuda_bind_thread_to_device.restype = C.c_int
+    L.sws_cuda_bind_thread_to_device.argtypes = [C.c_int]
+    L.sws_cuda_device_numa_node.restype = C.c_int
+    L.sws_cuda_device_numa_node.argtypes = [C.c_int]
     L.sws_cuda_sync.restype = C.c_int
     L.sws_cuda_sync.argtypes = [ctxp]
     L.sws_cuda_stream.restype = C.c_void_p
@@ -241,6 +248,17 @@ class SwsContext:
         df = _arr4(C.c_int64, dst_fstrides)
         return self._L.sws_cuda_scale_batch(self.p, sp, ss, sf, dp, ds, df, nb_frames)
 
+    def scale_batch_host(self, src_ptrs, src_strides, src_fstrides, dst_ptrs, dst_strides,
+                         dst_fstrides, nb_frames, nb_devices=0, depth=0):
+        """sws_cuda_scale_batch_host(): HOST frames, several in flight, spread over the visible devices."""
+        sp = _arr4(C.c_void_p, [_ptr_of(p) for p in src_ptrs])
+        ss = _arr4(C.c_int, src_strides)
+        sf = _arr4(C.c_int64, src_fstrides)
+        dp = _arr4(C.c_void_p, [_ptr_of(p) for p in dst_ptrs])
+        ds = _arr4(C.c_int, dst_strides)
+        df = _arr4(C.c_int64, dst_fstrides)
+        return self._L.sws_cuda_scale_batch_host(self.p, sp, ss, sf, dp, ds, df, nb_frames, nb_devices, depth)
+
     def sync(self):
         return self._L.sws_cuda_sync(self.p)
 
@@ -316,3 +334,12 @@ class PinnedBuffer:
 
 def device_count():
     return lib().sws_cuda_device_count()
+
+
+def bind_thread_to_device(device):
+    """Run the calling thread next to `device` (its NUMA node); -1 if the topology is unknown."""
+    return lib().sws_cuda_bind_thread_to_device(device)
+
+
+def device_numa_node(device):
+    return lib().sws_cuda_device_numa_node(device)

@@ -162,6 +162,19 @@ API double swsref_bench_frame(void *ctx, void *dst, void *src, int iters)
     return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
 
+/* the same over a ring of `nb` distinct frame pairs (working set beyond the last-level cache, like a real
+ * stream of frames): conversion i uses pair i mod nb */
+API double swsref_bench_frames(void *ctx, void *const dst[], void *const src[], int nb, int iters)
+{
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int i = 0; i < iters; i++)
+        if (sws_scale_frame(ctx, dst[i % nb], src[i % nb]) < 0)
+            return -1.0;
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
 /* ---- introspection: what did the reference compute at init? ---- */
 static SwsInternal *first_ctx(void *ctx)
 {

@@ -53,6 +53,51 @@ CONFIGS = [
 ]
 
 
+def measure(cfg, dev, peak, frames=0, gbytes=1.5, steps=20):
+    """One configuration, frames resident in HBM, one batched launch per step, CUDA events on the library
+    stream.  Returns a dict (kernel, ms per launch, Mpixel/s in and out, algorithmic GB/s, fraction of peak)."""
+    (name, sw, sh, sf, dw, dh, df, flags) = cfg
+    ctx = S.SwsContext(sw, sh, sf, dw, dh, df, flags)
+    sl, dl = T.plane_layout(sf, sw, sh), T.plane_layout(df, dw, dh)
+    F = frames
+    if F <= 0:
+        per_frame = sum(rows * rb for rows, rb in sl) + sum(rows * rb for rows, rb in dl)
+        F = max(16, min(1024, int(gbytes * 1e9 / per_frame)))
+    src = [torch.randint(0, 256, (F, rows * rb), dtype=torch.uint8, device=dev) for rows, rb in sl]
+    if "10le" in sf and sf != "p010le":   # keep 10-bit samples in range
+        for t in src:
+            v = t.view(torch.int16)
+            v &= 0x3FF
+    dst = [torch.zeros((F, rows * rb), dtype=torch.uint8, device=dev) for rows, rb in dl]
+    sstr, dstr = [rb for _, rb in sl], [rb for _, rb in dl]
+    sfs, dfs = [rows * rb for rows, rb in sl], [rows * rb for rows, rb in dl]
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def step():
+        r = ctx.scale_batch_device(src, sstr, sfs, dst, dstr, dfs, F)
+        assert r == dh, ctx.last_error
+    for _ in range(3):
+        step()
+    ctx.sync()
+    n0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    ctx.sync()
+    torch.cuda.synchronize()
+    launches = ctx.launch_count - n0
+    ms = e0.elapsed_time(e1) / steps
+    by = (sum(sfs) + sum(dfs)) * F
+    gbs = by / (ms * 1e-3) / 1e9
+    out = {"name": name, "kernel": ctx.kernel_name, "frames": F, "ms": ms, "launches_per_step": launches / steps,
+           "mpix_in": F * sw * sh / ms / 1e3, "mpix_out": F * dw * dh / ms / 1e3,
+           "algorithmic_bytes": by, "gbs": gbs, "frac": gbs / peak, "peak": peak}
+    ctx.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=0)
@@ -66,44 +111,13 @@ def main():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    for (name, sw, sh, sf, dw, dh, df, flags) in CONFIGS:
+    for cfg in CONFIGS:
+        name = cfg[0]
         if args.only and not any(name.split()[0] == k or (len(k) > 3 and k in name) for k in args.only.split(",")):
             continue
-        ctx = S.SwsContext(sw, sh, sf, dw, dh, df, flags)
-        sl, dl = T.plane_layout(sf, sw, sh), T.plane_layout(df, dw, dh)
-        F = args.frames
-        if F <= 0:
-            per_frame = sum(rows * rb for rows, rb in sl) + sum(rows * rb for rows, rb in dl)
-            F = max(16, min(1024, int(args.gbytes * 1e9 / per_frame)))
-        src = [torch.randint(0, 256, (F, rows * rb), dtype=torch.uint8, device=dev) for rows, rb in sl]
-        if "10le" in sf and sf != "p010le":   # keep 10-bit samples in range
-            for t in src:
-                v = t.view(torch.int16)
-                v &= 0x3FF
-        dst = [torch.zeros((F, rows * rb), dtype=torch.uint8, device=dev) for rows, rb in dl]
-        sstr, dstr = [rb for _, rb in sl], [rb for _, rb in dl]
-        sfs, dfs = [rows * rb for rows, rb in sl], [rows * rb for rows, rb in dl]
-        stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-
-        def step():
-            r = ctx.scale_batch_device(src, sstr, sfs, dst, dstr, dfs, F)
-            assert r == dh, ctx.last_error
-        for _ in range(3):
-            step()
-        ctx.sync()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(args.steps):
-            step()
-        e1.record(stream)
-        ctx.sync()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
-        by = (sum(sfs) + sum(dfs)) * F
-        gbs = by / (ms * 1e-3) / 1e9
+        r = measure(cfg, dev, peak, args.frames, args.gbytes, args.steps)
         print("%-48s %-18s %8.3f ms/%d frames  in %8.1f Mpix/s  out %8.1f Mpix/s  %7.1f GB/s = %5.1f%% of %.0f"
-              % (name, ctx.kernel_name, ms, F, F * sw * sh / ms / 1e3, F * dw * dh / ms / 1e3, gbs, 100 * gbs / peak, peak))
-        ctx.close()
+              % (name, r["kernel"], r["ms"], r["frames"], r["mpix_in"], r["mpix_out"], r["gbs"], 100 * r["frac"], peak))
 
 
 if __name__ == "__main__":
