@@ -1059,7 +1059,7 @@ int sws_cuda_scale_batch_host(SwsContext *sws, const uint8_t *const src[4], cons
     LaneJob jobs[SWS_B200_MAX_LANES];
     pthread_t tid[SWS_B200_MAX_LANES];
     int started[SWS_B200_MAX_LANES] = { 0 };
-    int visible, lanes, ret = 0;
+    int visible, lanes, pinned, ret = 0;
     if (!c || !c->initialized || !src || !dst || nb_frames < 1 || !srcStride || !dstStride ||
         (nb_frames > 1 && (!srcFrameStride || !dstFrameStride)))
         return AVERROR(EINVAL);
@@ -1074,12 +1074,27 @@ int sws_cuda_scale_batch_host(SwsContext *sws, const uint8_t *const src[4], cons
         depth = 3;                      /* H2D of one frame, kernel of another, D2H of a third */
     if (nb_devices * depth > SWS_B200_MAX_LANES)
         depth = SWS_B200_MAX_LANES / nb_devices;
-    lanes = nb_devices * depth;
+    {
+        /* page-locked frames need no host work at all: one lane per device, everything enqueued from this thread */
+        const uint8_t *last_s[4];
+        const uint8_t *last_d[4];
+        for (int i = 0; i < 4; i++) {
+            last_s[i] = src[i] ? src[i] + (srcFrameStride ? srcFrameStride[i] : 0) * (nb_frames - 1) : NULL;
+            last_d[i] = dst[i] ? dst[i] + (dstFrameStride ? dstFrameStride[i] : 0) * (nb_frames - 1) : NULL;
+        }
+        pinned = ff_b200_cuda_frame_is_pinned(c->cuda, src, 0) && ff_b200_cuda_frame_is_pinned(c->cuda, last_s, 0) &&
+                 ff_b200_cuda_frame_is_pinned(c->cuda, (const uint8_t *const *)dst, 1) &&
+                 ff_b200_cuda_frame_is_pinned(c->cuda, last_d, 1);
+        for (int i = 0; i < 4; i++)
+            if ((src[i] && srcStride[i] <= 0) || (dst[i] && dstStride[i] <= 0))
+                pinned = 0;
+    }
+    lanes = pinned ? nb_devices : nb_devices * depth;
     if (lanes > nb_frames)
         lanes = nb_frames;
-    if (c->nb_lanes && (c->lanes_devices != nb_devices || c->lanes_depth != depth))
+    if (c->nb_lanes && c->lanes_devices != nb_devices)
         release_lanes(c);
-    /* every lane is a clone of the context's device state with its own stream and staging set
+    /* every lane is a clone of the context's device state with its own streams and staging
      * (tables < 1 MB per lane) */
     for (int l = c->nb_lanes; l < lanes; l++) {
         SwsCudaPlan plan = c->plan;
@@ -1097,6 +1112,22 @@ int sws_cuda_scale_batch_host(SwsContext *sws, const uint8_t *const src[4], cons
     }
     c->lanes_devices = nb_devices;
     c->lanes_depth = depth;
+
+    if (pinned) {
+        for (int l = 0; l < lanes && ret >= 0; l++)
+            ret = ff_b200_cuda_frames_enqueue(c->lanes[l], src, srcStride, srcFrameStride, dst, dstStride,
+                                              dstFrameStride, l, lanes, nb_frames);
+        for (int l = 0; l < lanes; l++) {
+            int r = ff_b200_cuda_frames_wait(c->lanes[l]);
+            if (r < 0 && ret >= 0)
+                ret = r;
+        }
+        if (ret < 0) {
+            set_error(c, "host batch conversion failed (%d)", ret);
+            return ret;
+        }
+        return sws->dst_h;
+    }
 
     for (int l = 0; l < lanes; l++) {
         LaneJob *j = &jobs[l];

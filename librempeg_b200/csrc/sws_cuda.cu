@@ -1404,6 +1404,11 @@ struct SwsCudaState {
     /* staging frames for host-pointer sws_scale() */
     uint8_t *d_src[4], *d_dst[4];
     uint8_t *h_src[4], *h_dst[4];   /* page-locked twins of the staging planes: bounce ring for pageable frames */
+    /* frame ring of sws_cuda_scale_batch_host(): RING_DEPTH staging sets so that the upload of one frame, the
+     * kernel of another and the download of a third overlap (slot 0 is d_src/d_dst) */
+    uint8_t *ring_src[4][4], *ring_dst[4][4];
+    int ring_ready;
+    cudaEvent_t rev_in[4], rev_k[4], rev_out[4];
     uint8_t *d_flip;                /* scratch for mirroring the rows of bottom-up frames */
     size_t flip_bytes;
     int staging_ready, bounce_src_ready, bounce_dst_ready;
@@ -1424,6 +1429,9 @@ struct SwsCudaState {
     void *s8_tables;
     int *s8_hl_pos, *s8_hc_pos;
     uint32_t *s8_hl_cl, *s8_hl_ch, *s8_hc_cl, *s8_hc_ch;
+    int s8_mma;                  /* horizontal stage on the tensor pipe: s8_fs4 counts K steps of 32 samples */
+    int *s8_hl_goff, *s8_hc_goff;
+    uint32_t *s8_hl_B, *s8_hc_B;
     S8VRow *s8_vl, *s8_vc;
     int fast16_ok, fast16_taps;
     /* tile15 path */
@@ -2089,11 +2097,115 @@ static int fasthi8_launch(SwsCudaState *st, const uint8_t *const src[4], const i
 /* ---------------------------------------------------------------- scale8 host side */
 
 typedef void (*scale8_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Scale8Args);
-static scale8_kernel_t pick_scale8(int fs4, bool rgb)
+static scale8_kernel_t pick_scale8(int fs4, bool rgb, bool mma)
 {
+    if (mma) {          /* fs4 = K steps of the tensor-pipe horizontal stage */
+        if (rgb)
+            return fs4 == 1 ? sws_scale8_kernel<1, true, true> : fs4 == 2 ? sws_scale8_kernel<2, true, true>
+                                                                          : sws_scale8_kernel<4, true, true>;
+        return fs4 == 1 ? sws_scale8_kernel<1, false, true> : fs4 == 2 ? sws_scale8_kernel<2, false, true>
+                                                                       : sws_scale8_kernel<4, false, true>;
+    }
     if (rgb)
-        return fs4 == 1 ? sws_scale8_kernel<1, true> : fs4 == 2 ? sws_scale8_kernel<2, true> : sws_scale8_kernel<4, true>;
-    return fs4 == 1 ? sws_scale8_kernel<1, false> : fs4 == 2 ? sws_scale8_kernel<2, false> : sws_scale8_kernel<4, false>;
+        return fs4 == 1 ? sws_scale8_kernel<1, true, false> : fs4 == 2 ? sws_scale8_kernel<2, true, false>
+                                                                       : sws_scale8_kernel<4, true, false>;
+    return fs4 == 1 ? sws_scale8_kernel<1, false, false> : fs4 == 2 ? sws_scale8_kernel<2, false, false>
+                                                                    : sws_scale8_kernel<4, false, false>;
+}
+
+/* ---- tensor-pipe horizontal stage: per group of 8 output columns, the K window and the banded B fragments ----
+ * Window of group G of a tile starting at column x0: first sample = min pos of the group rounded down to a
+ * 16-byte boundary of the staged row (the tile's rows start at a0 = pos[x0] & ~15).  `inter` = interleaved
+ * nv12 / nv21 chroma: two bytes per sample, and the kernel cuts the planes out of the fragments with PRMT, which
+ * reorders the K axis as s8_mma_perm() says.  Returns the K steps needed (0: not expressible). */
+static int s8_mma_perm(int k, bool inter)
+{
+    if (!inter)
+        return k;
+    const int half = k >> 4, t = (k & 15) >> 2, j = k & 3;
+    static const int base[4] = { 0, 1, 8, 9 };
+    return 16 * half + 2 * t + base[j];
+}
+
+static void s8_mma_window(const SwsFirBank *b, int x0, int G, bool inter, int *wstart, int *wend)
+{
+    const int xa = x0 + 8 * G;
+    int lo = INT32_MAX, hi = 0;
+    for (int x = xa; x < xa + 8 && x < b->len; x++) {
+        if (b->pos[x] < lo) lo = b->pos[x];
+        if (b->pos[x] + b->size > hi) hi = b->pos[x] + b->size;
+    }
+    if (lo == INT32_MAX)
+        lo = hi = b->pos[x0];
+    if (lo < 0)
+        lo = 0;
+    *wstart = lo & ~(inter ? 7 : 15);
+    *wend = hi;
+}
+
+static int s8_mma_ksteps(const SwsFirBank *b, int tile_cols, bool inter)
+{
+    int ks = 1;
+    for (int x0 = 0; x0 < b->len; x0 += tile_cols)
+        for (int G = 0; G < tile_cols / 8; G++) {
+            int ws, we;
+            s8_mma_window(b, x0, G, inter, &ws, &we);
+            const int need = (we - ws + 31) / 32;
+            if (need > ks) ks = need;
+        }
+    return ks;
+}
+
+/* staged samples per row so that every window of every tile is inside the TMA box */
+static int s8_mma_seg(const SwsFirBank *b, int tile_cols, bool inter, int ks)
+{
+    int worst = 16;
+    for (int x0 = 0; x0 < b->len; x0 += tile_cols) {
+        const int a0 = b->pos[x0] & ~15;
+        for (int G = 0; G < tile_cols / 8; G++) {
+            int ws, we;
+            s8_mma_window(b, x0, G, inter, &ws, &we);
+            if (ws < a0)
+                return -1;
+            if (ws - a0 + 32 * ks > worst) worst = ws - a0 + 32 * ks;
+        }
+    }
+    return worst;
+}
+
+static void s8_mma_tables(const SwsFirBank *b, int tile_cols, bool inter, int ks, int *goff, uint32_t *B)
+{
+    const int gpt = tile_cols / 8;
+    const int tiles = (b->len + tile_cols - 1) / tile_cols;
+    for (int tx = 0; tx < tiles; tx++) {
+        const int x0 = tx * tile_cols, a0 = b->pos[x0] & ~15;
+        for (int G = 0; G < gpt; G++) {
+            int ws, we;
+            s8_mma_window(b, x0, G, inter, &ws, &we);
+            const int gi = tx * gpt + G;
+            goff[gi] = (ws - a0) * (inter ? 2 : 1);
+            uint32_t *out = B + (size_t)gi * ks * 4 * 32;
+            for (int step = 0; step < ks; step++)
+                for (int lane = 0; lane < 32; lane++) {
+                    const int t = lane & 3, n = lane >> 2, x = x0 + 8 * G + n;
+                    uint32_t r[4] = { 0, 0, 0, 0 };
+                    for (int reg = 0; reg < 2; reg++)
+                        for (int j = 0; j < 4; j++) {
+                            const int smp = ws + 32 * step + s8_mma_perm(16 * reg + 4 * t + j, inter);
+                            int c = 0;
+                            if (x < b->len) {
+                                const int tap = smp - b->pos[x];
+                                if (tap >= 0 && tap < b->size)
+                                    c = b->coef[(size_t)x * b->size + tap];
+                            }
+                            r[reg] |= (uint32_t)(c & 0xFF) << (8 * j);
+                            r[2 + reg] |= (uint32_t)((c >> 8) & 0xFF) << (8 * j);
+                        }
+                    for (int q = 0; q < 4; q++)
+                        out[(step * 4 + q) * 32 + lane] = r[q];
+                }
+        }
+    }
 }
 
 /* pack one horizontal bank: per output, fs4 words of low bytes and fs4 words of high bytes */
@@ -2211,8 +2323,33 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
                 hvl[y].pos_even |= 1;
         }
     }
-    const int seg_l = ret ? -1 : s8_seg_bytes(hl, fs4, S8_TW);
-    const int seg_c = ret ? -1 : s8_seg_bytes(hc, fs4, cw);
+    int seg_l = ret ? -1 : s8_seg_bytes(hl, fs4, S8_TW);
+    int seg_c = ret ? -1 : s8_seg_bytes(hc, fs4, cw);
+    /* tensor-pipe horizontal stage when every 8-column window fits K <= 128 samples (SWS_B200_DISABLE=s8mma: A/B) */
+    const bool inter = p->src_layout != SWSC_SRC_PLANAR;
+    int mma = 0, ks = 0;
+    if (!ret && seg_l >= 0 && seg_c >= 0 && !(getenv("SWS_B200_DISABLE") && strstr(getenv("SWS_B200_DISABLE"), "s8mma"))) {
+        const int kl = s8_mma_ksteps(hl, S8_TW, false), kc = s8_mma_ksteps(hc, cw, inter);
+        ks = kl > kc ? kl : kc;
+        ks = ks <= 1 ? 1 : ks == 2 ? 2 : ks <= 4 ? 4 : 0;
+        if (ks) {
+            int ml = s8_mma_seg(hl, S8_TW, false, ks), mc = s8_mma_seg(hc, cw, inter, ks);
+            if (ml > 0 && mc > 0) {
+                /* row pitch = odd multiple of 16 bytes: the eight rows of an ldmatrix tile hit eight bank groups */
+                ml = (ml + 15) & ~15;
+                if (!((ml >> 4) & 1)) ml += 16;
+                if (inter) {
+                    mc = (mc + 7) & ~7;
+                    if (!((mc >> 3) & 1)) mc += 8;       /* 2 * mc bytes per row */
+                } else {
+                    mc = (mc + 15) & ~15;
+                    if (!((mc >> 4) & 1)) mc += 16;
+                }
+                seg_l = ml; seg_c = mc;
+                mma = 1;
+            }
+        }
+    }
     if (seg_l < 0 || seg_c < 0)
         ret = 1;
     else if (seg_l > 1024 || seg_c > 512 || !get_encode_tiled())
@@ -2223,8 +2360,10 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
         ret = 1;
         /* largest tile that still leaves three CTAs per SM (about 74 KB each); failing that, two */
         const size_t budget[2] = { 74 * 1024 + 512, 100 * 1024 };
+        const char *th_env = getenv("SWS_B200_S8_TH");
+        const int th_max = th_env && atoi(th_env) >= 2 ? atoi(th_env) : 32;
         for (int pass = 0; pass < 2 && ret; pass++)
-            for (th = 32; th >= 2; th >>= 1) {
+            for (th = th_max; th >= 2; th >>= 1) {
                 const int cth = th >> p->chr_dst_vsub ? th >> p->chr_dst_vsub : 1;
                 nl_cap = s8_rows_cap(hvl, vl->len, th);
                 nc_cap = s8_rows_cap(hvc, vc->len, cth);
@@ -2249,6 +2388,12 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     o_hlcl = take(4 * (size_t)hl->len * fs4); o_hlch = take(4 * (size_t)hl->len * fs4);
     o_hccl = take(4 * (size_t)hc->len * fs4); o_hcch = take(4 * (size_t)hc->len * fs4);
     o_vl = take(sizeof(S8VRow) * vl->len); o_vc = take(sizeof(S8VRow) * vc->len);
+    const int ngl = (hl->len + S8_TW - 1) / S8_TW * (S8_TW / 8) + 2, ngc = (hc->len + cw - 1) / cw * (cw / 8) + 2;
+    size_t o_gl = 0, o_gc = 0, o_bl = 0, o_bc = 0;
+    if (mma) {
+        o_gl = take(sizeof(int) * ngl); o_gc = take(sizeof(int) * ngc);
+        o_bl = take((size_t)ngl * ks * 4 * 32 * 4); o_bc = take((size_t)ngc * ks * 4 * 32 * 4);
+    }
     uint8_t *host = (uint8_t *)calloc(1, off);
     if (!host) {
         free(hvl); free(hvc);
@@ -2265,6 +2410,10 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
         if (hvc[y].n4 > st->s8_vc_n4) st->s8_vc_n4 = hvc[y].n4;
     memcpy(host + o_vl, hvl, sizeof(S8VRow) * vl->len);
     memcpy(host + o_vc, hvc, sizeof(S8VRow) * vc->len);
+    if (mma) {
+        s8_mma_tables(hl, S8_TW, false, ks, (int *)(host + o_gl), (uint32_t *)(host + o_bl));
+        s8_mma_tables(hc, cw, inter, ks, (int *)(host + o_gc), (uint32_t *)(host + o_bc));
+    }
     free(hvl); free(hvc);
     cudaError_t e = cudaMalloc(&st->s8_tables, off);
     if (e == cudaSuccess)
@@ -2276,16 +2425,21 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     st->s8_hl_cl = (uint32_t *)(t + o_hlcl); st->s8_hl_ch = (uint32_t *)(t + o_hlch);
     st->s8_hc_cl = (uint32_t *)(t + o_hccl); st->s8_hc_ch = (uint32_t *)(t + o_hcch);
     st->s8_vl = (S8VRow *)(t + o_vl); st->s8_vc = (S8VRow *)(t + o_vc);
-    st->s8_fs4 = fs4; st->s8_tile_h = th; st->s8_nl_cap = nl_cap; st->s8_nc_cap = nc_cap;
+    st->s8_fs4 = mma ? ks : fs4; st->s8_tile_h = th; st->s8_nl_cap = nl_cap; st->s8_nc_cap = nc_cap;
     st->s8_seg_l = seg_l; st->s8_seg_c = seg_c; st->s8_smem = smem; st->s8_slot = slot;
-    CUDA_OK(cudaFuncSetAttribute((const void *)pick_scale8(fs4, rgb), cudaFuncAttributeMaxDynamicSharedMemorySize,
+    st->s8_mma = mma;
+    if (mma) {
+        st->s8_hl_goff = (int *)(t + o_gl); st->s8_hc_goff = (int *)(t + o_gc);
+        st->s8_hl_B = (uint32_t *)(t + o_bl); st->s8_hc_B = (uint32_t *)(t + o_bc);
+    }
+    CUDA_OK(cudaFuncSetAttribute((const void *)pick_scale8(st->s8_fs4, rgb, mma), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
     st->s8_ok = 1;
     if (getenv("SWS_B200_DEBUG"))
-        fprintf(stderr, "[swscaler-b200] scale8: fs4=%d tile_h=%d nl_cap=%d nc_cap=%d seg_l=%d seg_c=%d slot=%d smem=%zu\n",
-                fs4, th, nl_cap, nc_cap, seg_l, seg_c, slot, smem);
+        fprintf(stderr, "[swscaler-b200] scale8: %s fs4=%d tile_h=%d nl_cap=%d nc_cap=%d seg_l=%d seg_c=%d slot=%d smem=%zu\n",
+                mma ? "mma" : "dp4a", st->s8_fs4, th, nl_cap, nc_cap, seg_l, seg_c, slot, smem);
     if (!st->fast_ok && !st->fast16_ok)
-        st->kernel_name = "scale8_dp4a";
+        st->kernel_name = mma ? "scale8_mma" : "scale8_dp4a";
     return 0;
 }
 
@@ -2342,9 +2496,10 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.hl_pos = st->s8_hl_pos; a.hc_pos = st->s8_hc_pos;
     a.hl_cl = st->s8_hl_cl; a.hl_ch = st->s8_hl_ch; a.hc_cl = st->s8_hc_cl; a.hc_ch = st->s8_hc_ch;
     a.vl = st->s8_vl; a.vc = st->s8_vc;
+    a.hl_goff = st->s8_hl_goff; a.hc_goff = st->s8_hc_goff; a.hl_B = st->s8_hl_B; a.hc_B = st->s8_hc_B;
     dim3 grid((p->dst_w + S8_TW - 1) / S8_TW, (y1 - y0 + st->s8_tile_h - 1) / st->s8_tile_h, nb_frames);
-    pick_scale8(st->s8_fs4, rgb)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
-    st->kernel_name = "scale8_dp4a";
+    pick_scale8(st->s8_fs4, rgb, st->s8_mma)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
+    st->kernel_name = st->s8_mma ? "scale8_mma" : "scale8_dp4a";
     CUDA_OK(cudaGetLastError());
     st->launches++;
     return 1;

@@ -194,6 +194,13 @@ int  ff_b200_cuda_scale_host(SwsCudaState *st,
                              const uint8_t *const src[4], const int src_stride[4],
                              int src_y, int src_h, int upload,
                              uint8_t *const dst[4], const int dst_stride[4], int y0, int y1);
+/* page-locked host frames first, first+step, ... through a ring of staging sets; enqueue only, then wait */
+int  ff_b200_cuda_frames_enqueue(SwsCudaState *st,
+                                 const uint8_t *const src[4], const int src_stride[4], const int64_t src_fstride[4],
+                                 uint8_t *const dst[4], const int dst_stride[4], const int64_t dst_fstride[4],
+                                 int first, int step, int nb_frames);
+int  ff_b200_cuda_frames_wait(SwsCudaState *st);
+int  ff_b200_cuda_frame_is_pinned(SwsCudaState *st, const uint8_t *const planes[4], int dst_side);
 int  ff_b200_cuda_sync(SwsCudaState *st);
 void *ff_b200_cuda_stream(SwsCudaState *st);
 long ff_b200_cuda_launch_count(SwsCudaState *st);

@@ -16,6 +16,19 @@
  *  V: IDP.2A consumes those pairs: two taps per instruction pair, again with split coefficients;
  *     an odd first source row is absorbed by a leading zero tap prepared on the host.
  * H and V stay separate stages with the reference's 15-bit clip in between.
+ *
+ * MMA = true (round 2): the horizontal stage runs on the tensor pipe instead.  For 8 neighbouring output
+ * columns the FIR is a banded 8-column matrix B[k][n] = coef[n][window + k - pos[n]] over a K = 32*KS byte
+ * window of the staged rows, so 16 source rows x 8 columns are KS x 2 warp-level integer MMAs
+ *   mma.sync.m16n8k32  u8 (rows) x u8 (low coefficient bytes)  and  u8 x s8 (high bytes),  s32 accumulate
+ * -- exact: sum src*c = 256*sum src*ch + sum src*cl, the 15-bit clip stays after it (swscale.c:128-142).
+ * A fragments come straight out of the TMA ring with ldmatrix (MMA row i = source row 2i, row 8+i = source row
+ * 2i+1, so a thread's accumulator pair is the vertically adjacent sample pair the transposed line buffer
+ * stores as one word); B fragments are prepared on the host per column group and live in registers for the
+ * whole tile.  Interleaved nv12 / nv21 chroma is de-interleaved with two PRMT per fragment (the K order of a
+ * contraction is free: the host permutes B to match).  Measured: the legacy integer MMA sustains 2044 MAC /
+ * clk / SM on B200, 8x the IDP.4A pipe (profiles/microbench/mma_i8_bench.cu), and the dot-product pipe is
+ * left to the vertical stage.
  */
 #pragma once
 
@@ -59,7 +72,110 @@ struct Scale8Args {
     const int *hl_pos, *hc_pos;
     const uint32_t *hl_cl, *hl_ch, *hc_cl, *hc_ch;
     const S8VRow *vl, *vc;
+    /* MMA horizontal stage: per group of 8 output columns the byte offset of its K window inside the staged
+     * row, and the B fragments [group][KS][lo0 lo1 hi0 hi1][lane] */
+    const int *hl_goff, *hc_goff;
+    const uint32_t *hl_B, *hc_B;
 };
+
+/* ---- warp-level integer MMA helpers ---- */
+__device__ __forceinline__ void s8_ldmatrix4(uint32_t addr, uint32_t (&a)[4])
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
+}
+__device__ __forceinline__ void s8_mma_uu(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void s8_mma_us(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int KS>
+struct S8Bfrag {
+    uint32_t r[KS][4];       /* lo0 lo1 hi0 hi1 per K step */
+};
+
+template <int KS>
+__device__ __forceinline__ void s8_load_bfrag(const uint32_t *tab, int group, int lane, S8Bfrag<KS> &b)
+{
+    const uint32_t *p = tab + (size_t)group * (KS * 4 * 32) + lane;
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            b.r[ks][j] = __ldg(p + (ks * 4 + j) * 32);
+}
+
+/* Which staged row feeds which MMA row.  A thread's accumulators c0/c1 (MMA row g) and c2/c3 (MMA row g + 8) must
+ * be the vertically adjacent pair (2g, 2g+1) that one word of the transposed line buffer holds, and the eight
+ * rows of each ldmatrix matrix must fall into eight different 16-byte bank groups (row pitch = odd multiple of
+ * 16 bytes): MMA rows 0..3 take the even row of their pair, rows 4..7 the odd one (rows 0 2 4 6 9 11 13 15 are
+ * all different mod 8), MMA rows 8..15 the other one.  S8_PAIR_SEL(lane) orders the two halves of the word. */
+__device__ __forceinline__ uint32_t s8_ldm_row(int lane)
+{
+    const int i = lane & 7;
+    return 2 * i + (((lane >> 3) & 1) ^ (i >> 2));
+}
+#define S8_PAIR_SEL(lane) (((lane) & 16) ? 0x1054u : 0x5410u)
+
+/* 16 staged rows x 8 output columns: accumulators to two words of vertically adjacent 15-bit samples
+ * (columns 2t and 2t+1 of the group, source rows 2g and 2g+1 of the slot; t = lane & 3, g = lane >> 2) */
+__device__ __forceinline__ void s8_mma_pack(const int (&lo)[4], const int (&hi)[4], uint32_t sel, uint32_t &wa, uint32_t &wb)
+{
+    const int v0 = min(((hi[0] << 8) + lo[0]) >> 7, (1 << 15) - 1);
+    const int v1 = min(((hi[1] << 8) + lo[1]) >> 7, (1 << 15) - 1);
+    const int v2 = min(((hi[2] << 8) + lo[2]) >> 7, (1 << 15) - 1);
+    const int v3 = min(((hi[3] << 8) + lo[3]) >> 7, (1 << 15) - 1);
+    wa = prmt((uint32_t)v0, (uint32_t)v2, sel);
+    wb = prmt((uint32_t)v1, (uint32_t)v3, sel);
+}
+
+/* plain rows (luma, planar chroma): KS ldmatrix + 2 KS MMAs */
+template <int KS>
+__device__ __forceinline__ void s8_mma_rows(uint32_t addr, const S8Bfrag<KS> &b, uint32_t sel, uint32_t &wa, uint32_t &wb)
+{
+    int lo[4] = { 0, 0, 0, 0 }, hi[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+        uint32_t a[4];
+        s8_ldmatrix4(addr + 32 * ks, a);
+        s8_mma_uu(lo, a, b.r[ks][0], b.r[ks][1]);
+        s8_mma_us(hi, a, b.r[ks][2], b.r[ks][3]);
+    }
+    s8_mma_pack(lo, hi, sel, wa, wb);
+}
+
+/* interleaved chroma rows (nv12 / nv21): two ldmatrix per K step of 32 chroma samples, U and V fragments cut
+ * out of them with PRMT; `even` = the plane stored first in memory */
+template <int KS>
+__device__ __forceinline__ void s8_mma_rows_uv(uint32_t addr, const S8Bfrag<KS> &b, uint32_t sel, uint32_t &ea,
+                                               uint32_t &eb, uint32_t &oa, uint32_t &ob)
+{
+    int elo[4] = { 0, 0, 0, 0 }, ehi[4] = { 0, 0, 0, 0 }, olo[4] = { 0, 0, 0, 0 }, ohi[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+        uint32_t p[4], q[4], e[4], o[4];
+        s8_ldmatrix4(addr + 64 * ks, p);
+        s8_ldmatrix4(addr + 64 * ks + 32, q);
+        e[0] = prmt(p[0], p[2], 0x6420); e[1] = prmt(p[1], p[3], 0x6420);
+        e[2] = prmt(q[0], q[2], 0x6420); e[3] = prmt(q[1], q[3], 0x6420);
+        o[0] = prmt(p[0], p[2], 0x7531); o[1] = prmt(p[1], p[3], 0x7531);
+        o[2] = prmt(q[0], q[2], 0x7531); o[3] = prmt(q[1], q[3], 0x7531);
+        s8_mma_uu(elo, e, b.r[ks][0], b.r[ks][1]);
+        s8_mma_us(ehi, e, b.r[ks][2], b.r[ks][3]);
+        s8_mma_uu(olo, o, b.r[ks][0], b.r[ks][1]);
+        s8_mma_us(ohi, o, b.r[ks][2], b.r[ks][3]);
+    }
+    s8_mma_pack(elo, ehi, sel, ea, eb);
+    s8_mma_pack(olo, ohi, sel, oa, ob);
+}
 
 __device__ __forceinline__ int dp2a_lo_su(uint32_t a, uint32_t b, int c)
 {
@@ -230,8 +346,8 @@ __device__ __forceinline__ void s8_hfir_uv(const unsigned char *srow, int sh, co
  *           de-interleaved on the fly).
  *  V:       warp = output row, lane = columns lane + 32k.
  */
-template <int FS4, bool RGB>
-__global__ void __launch_bounds__(S8_THREADS, (RGB || FS4 <= S8_LIGHT_FS4) ? S8_RGB_CTAS : 3)
+template <int FS4, bool RGB, bool MMA>
+__global__ void __launch_bounds__(S8_THREADS, (MMA && FS4 > 2) ? 3 : (RGB || FS4 <= S8_LIGHT_FS4) ? S8_RGB_CTAS : 3)
 sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_u,
                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ Scale8Args A)
 {
@@ -344,8 +460,39 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
         }
     };
 
-    /* ================= stage H, luma: thread = (column, half of the slot's rows) ================= */
-    {
+    /* ================= stage H, luma ================= */
+    if (MMA) {
+        /* warp = 16 output columns (two groups of 8), all 16 rows of a slot per pass: FS4 = K steps of 32 bytes */
+        const int t = lane & 3, g = lane >> 2;
+        const int grp = (x0 >> 3) + 2 * warp;
+        S8Bfrag<FS4> b0, b1;
+        s8_load_bfrag<FS4>(A.hl_B, grp, lane, b0);
+        s8_load_bfrag<FS4>(A.hl_B, grp + 1, lane, b1);
+        /* ldmatrix row address of this lane: matrix = lane >> 3 (bit 0: odd source rows, bit 1: bytes 16..31) */
+        const uint32_t lrow = s8_ldm_row(lane) * A.seg_l + (lane >> 4) * 16;
+        const uint32_t sel = S8_PAIR_SEL(lane);
+        const uint32_t o0 = lrow + __ldg(A.hl_goff + grp), o1 = lrow + __ldg(A.hl_goff + grp + 1);
+        const int c0 = 16 * warp + 2 * t, c1 = c0 + 8;           /* tile columns of the two words per group */
+        uint32_t *h00 = hb_l + (RGB ? (c0 >> 1) : c0) * lstride_w + g;
+        uint32_t *h01 = hb_l + (RGB ? (c0 >> 1) + 64 : c0 + 1) * lstride_w + g;
+        uint32_t *h10 = hb_l + (RGB ? (c1 >> 1) : c1) * lstride_w + g;
+        uint32_t *h11 = hb_l + (RGB ? (c1 >> 1) + 64 : c1 + 1) * lstride_w + g;
+        int left = nl - 2 * g;                                   /* rows of this lane's pair still inside the window */
+        for (int q = 0; q < npl; q++) {
+            s8_wait(full_a + 8 * sb, sphase);
+            const uint32_t base = ring_a + sb * slot;
+            uint32_t wa, wb, wc, wd;
+            s8_mma_rows<FS4>(base + o0, b0, sel, wa, wb);
+            s8_mma_rows<FS4>(base + o1, b1, sel, wc, wd);
+            if (left > 0) {
+                h00[0] = wa; h01[0] = wb; h10[0] = wc; h11[0] = wd;
+            }
+            h00 += S8_ROWS / 2; h01 += S8_ROWS / 2; h10 += S8_ROWS / 2; h11 += S8_ROWS / 2;
+            left -= S8_ROWS;
+            release();
+        }
+    } else {
+        /* thread = (column, half of the slot's rows) */
         constexpr int NP = S8_ROWS / 4;          /* row pairs per thread and pass */
         const int x = tid & (S8_TW - 1), g = tid >> 7;
         const int gx = min(x0 + x, A.dst_w - 1);
@@ -380,8 +527,61 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             release();
         }
     }
-    /* ================= stage H, chroma: thread = (column, row group), both planes ================= */
-    if (npc > 0) {
+    /* ================= stage H, chroma ================= */
+    if (MMA) {
+        if (npc > 0) {
+            /* hs = 1: 8 groups per plane, warp = group `warp` of U and of V; hs = 0: 16 groups, warp = two of them */
+            const int t = lane & 3, g = lane >> 2;
+            const int ng = A.hs ? 1 : 2;
+            const int grp = (cx0 >> 3) + ng * warp;
+            const bool vfirst = A.src_layout == SWSC_SRC_NV21;
+            const int rowbytes = planar ? A.seg_c : 2 * A.seg_c;
+            const uint32_t lrow = s8_ldm_row(lane) * rowbytes + (lane >> 4) * 16;
+            const uint32_t sel = S8_PAIR_SEL(lane);
+            S8Bfrag<FS4> b0, b1;
+            s8_load_bfrag<FS4>(A.hc_B, grp, lane, b0);
+            uint32_t o0 = lrow + __ldg(A.hc_goff + grp), o1 = 0;
+            if (ng == 2) {
+                s8_load_bfrag<FS4>(A.hc_B, grp + 1, lane, b1);
+                o1 = lrow + __ldg(A.hc_goff + grp + 1);
+            }
+            const int c0 = 8 * ng * warp + 2 * t;
+            uint32_t *hu = hb_u + c0 * cstride_w + g, *hv = hb_v + c0 * cstride_w + g;
+            int left = nc - 2 * g;
+            for (int qc = 0; qc < npc; qc++) {
+                s8_wait(full_a + 8 * sb, sphase);
+                const uint32_t base = ring_a + sb * slot;
+                uint32_t ua, ub, va, vb;
+                if (planar) {
+                    s8_mma_rows<FS4>(base + o0, b0, sel, ua, ub);
+                    s8_mma_rows<FS4>(base + S8_ROWS * A.seg_c + o0, b0, sel, va, vb);
+                } else if (vfirst) {
+                    s8_mma_rows_uv<FS4>(base + o0, b0, sel, va, vb, ua, ub);
+                } else {
+                    s8_mma_rows_uv<FS4>(base + o0, b0, sel, ua, ub, va, vb);
+                }
+                if (left > 0) {
+                    hu[0] = ua; hu[cstride_w] = ub; hv[0] = va; hv[cstride_w] = vb;
+                }
+                if (ng == 2) {
+                    if (planar) {
+                        s8_mma_rows<FS4>(base + o1, b1, sel, ua, ub);
+                        s8_mma_rows<FS4>(base + S8_ROWS * A.seg_c + o1, b1, sel, va, vb);
+                    } else if (vfirst) {
+                        s8_mma_rows_uv<FS4>(base + o1, b1, sel, va, vb, ua, ub);
+                    } else {
+                        s8_mma_rows_uv<FS4>(base + o1, b1, sel, ua, ub, va, vb);
+                    }
+                    if (left > 0) {
+                        hu[8 * cstride_w] = ua; hu[9 * cstride_w] = ub; hv[8 * cstride_w] = va; hv[9 * cstride_w] = vb;
+                    }
+                }
+                hu += S8_ROWS / 2; hv += S8_ROWS / 2;
+                left -= S8_ROWS;
+                release();
+            }
+        }
+    } else if (npc > 0) {
         const int x = tid & (CW - 1), g = tid >> cs;
         const int npair = A.hs ? S8_ROWS / 8 : S8_ROWS / 4;          /* row pairs per thread and pass */
         const int gx = min(cx0 + x, A.chr_dst_w - 1);

@@ -18,6 +18,10 @@
 
 #include <atomic>
 #include <condition_variable>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#define SWS_B200_NT_COPY 1
+#endif
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -78,8 +82,12 @@ private:
         if (e) {
             n = atoi(e);
         } else {
+            /* the copies are memory-bound: a handful of cores saturate the host; one process per GPU is the
+             * common deployment, so share the cores between the devices of the box */
             const unsigned hc = std::thread::hardware_concurrency();
-            n = hc >= 32 ? 8 : hc >= 8 ? 4 : hc >= 4 ? 2 : 1;
+            int devs = sws_cuda_device_count();
+            n = (int)hc / (devs > 0 ? devs : 1);
+            n = n > 12 ? 12 : n < 2 ? 2 : n;
         }
         if (n > 32)
             n = 32;
@@ -89,16 +97,44 @@ private:
             w.detach();
     }
 
+    /* Frames are written once and next read by a DMA engine or much later by the caller: streaming
+     * (non-temporal) stores skip the read-for-ownership of the destination lines, a third of the traffic. */
+    static void stream_copy(uint8_t *d, const uint8_t *s, size_t n)
+    {
+#ifdef SWS_B200_NT_COPY
+        if (n >= 4096) {
+            const size_t head = (16 - ((uintptr_t)d & 15)) & 15;
+            memcpy(d, s, head);
+            d += head; s += head; n -= head;
+            size_t blocks = n >> 6;
+            for (; blocks; blocks--, d += 64, s += 64) {
+                const __m128i a = _mm_loadu_si128((const __m128i *)(s));
+                const __m128i b = _mm_loadu_si128((const __m128i *)(s + 16));
+                const __m128i c = _mm_loadu_si128((const __m128i *)(s + 32));
+                const __m128i e = _mm_loadu_si128((const __m128i *)(s + 48));
+                _mm_stream_si128((__m128i *)(d), a);
+                _mm_stream_si128((__m128i *)(d + 16), b);
+                _mm_stream_si128((__m128i *)(d + 32), c);
+                _mm_stream_si128((__m128i *)(d + 48), e);
+            }
+            n &= 63;
+        }
+#endif
+        memcpy(d, s, n);
+    }
+
     static void run_rows(const CopyJob &j, int r0, int r1)
     {
         if (r1 <= r0)
             return;
-        if (j.dpitch == (ptrdiff_t)j.rowbytes && j.spitch == (ptrdiff_t)j.rowbytes) {
-            memcpy(j.dst + (size_t)r0 * j.rowbytes, j.src + (size_t)r0 * j.rowbytes, (size_t)(r1 - r0) * j.rowbytes);
-            return;
-        }
-        for (int r = r0; r < r1; r++)
-            memcpy(j.dst + r * j.dpitch, j.src + r * j.spitch, j.rowbytes);
+        if (j.dpitch == (ptrdiff_t)j.rowbytes && j.spitch == (ptrdiff_t)j.rowbytes)
+            stream_copy(j.dst + (size_t)r0 * j.rowbytes, j.src + (size_t)r0 * j.rowbytes, (size_t)(r1 - r0) * j.rowbytes);
+        else
+            for (int r = r0; r < r1; r++)
+                stream_copy(j.dst + r * j.dpitch, j.src + r * j.spitch, j.rowbytes);
+#ifdef SWS_B200_NT_COPY
+        _mm_sfence();
+#endif
     }
 
     static void run_part(const CopyJob &j, int part, int parts)
@@ -161,6 +197,8 @@ sws_flip_rows_kernel(uint8_t *dst, int dpitch, const uint8_t *src, int spitch, i
 
 /* ------------------------------------------------------------------ staging */
 
+#define RING_DEPTH 3
+
 static void free_staging(SwsCudaState *st)
 {
     for (int i = 0; i < 4; i++) {
@@ -172,6 +210,21 @@ static void free_staging(SwsCudaState *st)
         if (st->h_dst[i])
             cudaFreeHost(st->h_dst[i]);
         st->h_src[i] = st->h_dst[i] = nullptr;
+    }
+    if (st->ring_ready) {
+        for (int r = 1; r < RING_DEPTH; r++)
+            for (int i = 0; i < 4; i++) {
+                cudaFree(st->ring_src[r][i]);
+                cudaFree(st->ring_dst[r][i]);
+            }
+        for (int r = 0; r < RING_DEPTH; r++) {
+            cudaEventDestroy(st->rev_in[r]);
+            cudaEventDestroy(st->rev_k[r]);
+            cudaEventDestroy(st->rev_out[r]);
+        }
+        memset(st->ring_src, 0, sizeof(st->ring_src));
+        memset(st->ring_dst, 0, sizeof(st->ring_dst));
+        st->ring_ready = 0;
     }
     cudaFree(st->d_flip);
     st->d_flip = nullptr;
@@ -568,6 +621,121 @@ static int banded_host_frame(SwsCudaState *st, const uint8_t *const src[4], cons
     }
     CUDA_OK(cudaStreamSynchronize(st->stream));
     return 0;
+}
+
+/* ------------------------------------------------------------------ frame ring */
+
+static int ensure_ring(SwsCudaState *st)
+{
+    int ret;
+    if (st->ring_ready)
+        return 0;
+    if ((ret = ensure_staging(st)) < 0 || (ret = ensure_pipeline(st)) < 0)
+        return ret;
+    for (int i = 0; i < 4; i++) {
+        st->ring_src[0][i] = st->d_src[i];
+        st->ring_dst[0][i] = st->d_dst[i];
+    }
+    for (int r = 1; r < RING_DEPTH; r++)
+        for (int i = 0; i < 4; i++) {
+            if (st->src_rows[i])
+                CUDA_OK(cudaMalloc(&st->ring_src[r][i], (size_t)st->d_src_stride[i] * st->src_rows[i]));
+            if (st->dst_rows[i])
+                CUDA_OK(cudaMalloc(&st->ring_dst[r][i], (size_t)st->d_dst_stride[i] * st->dst_rows[i]));
+        }
+    for (int r = 0; r < RING_DEPTH; r++) {
+        CUDA_OK(cudaEventCreateWithFlags(&st->rev_in[r], cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&st->rev_k[r], cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&st->rev_out[r], cudaEventDisableTiming));
+    }
+    st->ring_ready = 1;
+    return 0;
+}
+
+/* Page-locked host frames first, first + step, ... < nb_frames through this device, nothing but enqueues:
+ *   s_in   H2D of frame i into ring slot i mod RING_DEPTH   (after the kernel that last read the slot)
+ *   stream kernel of frame i                                  (after its H2D, and after the D2H that last read the slot)
+ *   s_out  D2H of frame i                                     (after its kernel)   [absent when the kernel stores to host]
+ * The host never blocks here; ff_b200_cuda_frames_wait() drains the device.  One host thread can feed every
+ * device of the box this way. */
+extern "C" int ff_b200_cuda_frames_enqueue(SwsCudaState *st,
+                                           const uint8_t *const src[4], const int src_stride[4], const int64_t src_fstride[4],
+                                           uint8_t *const dst[4], const int dst_stride[4], const int64_t dst_fstride[4],
+                                           int first, int step, int nb_frames)
+{
+    const SwsCudaPlan *p = &st->plan;
+    DeviceGuard guard(st->device);
+    int ret = ensure_ring(st);
+    if (ret < 0)
+        return ret;
+    int64_t zero[4] = { 0, 0, 0, 0 };
+    const bool fast = st->fast_ok && !(st->disabled & 1) && st->e2e_mode == 3;
+    int slot = 0;
+    for (int f = first; f < nb_frames; f += step, slot = (slot + 1) % RING_DEPTH) {
+        const uint8_t *s[4];
+        uint8_t *d[4];
+        for (int i = 0; i < 4; i++) {
+            s[i] = src[i] ? src[i] + (src_fstride ? src_fstride[i] : 0) * f : nullptr;
+            d[i] = dst[i] ? dst[i] + (dst_fstride ? dst_fstride[i] : 0) * f : nullptr;
+        }
+        CUDA_OK(cudaStreamWaitEvent(st->s_in, st->rev_k[slot], 0));
+        for (int i = 0; i < 4; i++) {
+            if (!st->src_rows[i])
+                continue;
+            if (!s[i] || src_stride[i] <= 0)
+                return AVERROR(EINVAL);
+            CUDA_OK(copy_rows_async(st->ring_src[slot][i], st->d_src_stride[i], s[i], src_stride[i],
+                                    st->src_rowbytes[i], st->src_rows[i], cudaMemcpyHostToDevice, st->s_in));
+        }
+        CUDA_OK(cudaEventRecord(st->rev_in[slot], st->s_in));
+        CUDA_OK(cudaStreamWaitEvent(st->stream, st->rev_in[slot], 0));
+        int direct = 0;
+        if (fast && d[0] && aligned16(d[0]) && !(dst_stride[0] & 15)) {
+            /* page-locked memory is mapped at the same address under unified addressing */
+            direct = fast420_launch(st, st->ring_src[slot], st->d_src_stride, zero, d, dst_stride, zero, 1, 0, p->dst_h, st->stream);
+            if (direct < 0)
+                return direct;
+        }
+        if (!direct) {
+            CUDA_OK(cudaStreamWaitEvent(st->stream, st->rev_out[slot], 0));
+            ret = ff_b200_cuda_launch(st, st->ring_src[slot], st->d_src_stride, zero, st->ring_dst[slot], st->d_dst_stride,
+                                      zero, 1, 0, p->dst_h);
+            if (ret < 0)
+                return ret;
+        }
+        CUDA_OK(cudaEventRecord(st->rev_k[slot], st->stream));
+        if (!direct) {
+            CUDA_OK(cudaStreamWaitEvent(st->s_out, st->rev_k[slot], 0));
+            for (int i = 0; i < 4; i++) {
+                if (!st->dst_rows[i])
+                    continue;
+                if (!d[i] || dst_stride[i] <= 0)
+                    return AVERROR(EINVAL);
+                CUDA_OK(copy_rows_async(d[i], dst_stride[i], st->ring_dst[slot][i], st->d_dst_stride[i],
+                                        st->dst_rowbytes[i], st->dst_rows[i], cudaMemcpyDeviceToHost, st->s_out));
+            }
+            CUDA_OK(cudaEventRecord(st->rev_out[slot], st->s_out));
+        }
+    }
+    return 0;
+}
+
+extern "C" int ff_b200_cuda_frames_wait(SwsCudaState *st)
+{
+    DeviceGuard guard(st->device);
+    CUDA_OK(cudaStreamSynchronize(st->stream));
+    if (st->s_out)
+        CUDA_OK(cudaStreamSynchronize(st->s_out));
+    return 0;
+}
+
+/* 1 if every plane the plan reads (source side) / writes (destination side) is page-locked host memory */
+extern "C" int ff_b200_cuda_frame_is_pinned(SwsCudaState *st, const uint8_t *const planes[4], int dst_side)
+{
+    DeviceGuard guard(st->device);
+    if (ensure_staging(st) < 0)
+        return 0;
+    return planes_pinned(planes, dst_side ? st->dst_rows : st->src_rows, nullptr) ? 1 : 0;
 }
 
 extern "C" int ff_b200_cuda_scale_host(SwsCudaState *st,
