@@ -2443,6 +2443,7 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     return 0;
 }
 
+
 static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const int src_stride[4],
                          const int64_t src_fstride[4], uint8_t *const dst[4], const int dst_stride[4],
                          const int64_t dst_fstride[4], int nb_frames, int y0, int y1, cudaStream_t stream)
@@ -2489,6 +2490,7 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.y0 = y0; a.y1 = y1; a.tile_h = st->s8_tile_h;
     a.nl_cap = st->s8_nl_cap; a.nc_cap = st->s8_nc_cap; a.seg_l = st->s8_seg_l; a.seg_c = st->s8_seg_c;
     a.slot_bytes = st->s8_slot;
+    a.stages = S8_STAGES;
     a.vl_n4 = st->s8_vl_n4; a.vc_n4 = st->s8_vc_n4;
     a.cy = p->rgb.cy; a.yb = p->rgb.yb; a.base_r = p->rgb.base_r; a.base_g = p->rgb.base_g; a.base_b = p->rgb.base_b;
     a.crv = p->rgb.crv; a.cgu = p->rgb.cgu; a.cgv = p->rgb.cgv; a.cbu = p->rgb.cbu;

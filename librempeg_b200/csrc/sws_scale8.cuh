@@ -39,6 +39,7 @@
 #ifndef S8_STAGES
 #define S8_STAGES 2      /* ring depth */
 #endif
+#define S8_MAX_STAGES 6  /* the ring depth is a launch parameter: as many slots as the shared-memory budget leaves */
 #define S8_THREADS 288   /* 8 filtering warps + 1 TMA producer warp */
 #ifndef S8_LIGHT_FS4
 #define S8_LIGHT_FS4 2    /* planar variants with at most this many tap groups are also compiled for S8_RGB_CTAS CTAs per SM */
@@ -69,6 +70,7 @@ struct Scale8Args {
     int vl_n4, vc_n4;        /* vertical tap groups of four in use (max over rows) */
     int seg_l, seg_c;        /* staged bytes per luma row / chroma samples per chroma row */
     int slot_bytes;          /* one ring slot: max(8 luma rows, 8 rows of both chroma planes), 128-byte multiple */
+    int stages;              /* ring depth, 2 .. S8_MAX_STAGES */
     const int *hl_pos, *hc_pos;
     const uint32_t *hl_cl, *hl_ch, *hc_cl, *hc_ch;
     const S8VRow *vl, *vc;
@@ -352,8 +354,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ Scale8Args A)
 {
     extern __shared__ __align__(128) unsigned char s8_smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[S8_STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[S8_STAGES];
+    __shared__ __align__(8) uint64_t full_bar[S8_MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[S8_MAX_STAGES];
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int f = blockIdx.z;
@@ -371,8 +373,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     const int slot = A.slot_bytes;
 
     if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < S8_STAGES; s++) {
+        for (int s = 0; s < A.stages; s++) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 8);
         }
@@ -411,7 +412,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             int b = 0;
             uint32_t par = 1;              /* parity of the previous use of slot b */
             for (int q = 0; q < npl + npc; q++) {
-                if (q >= S8_STAGES)
+                if (q >= A.stages)
                     s8_wait(empty_a + 8 * b, par);          /* all 8 warps released the slot */
                 const uint32_t d = ring_a + b * slot, bar = full_a + 8 * b;
                 if (q < npl) {
@@ -427,7 +428,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                         s8_tma_load(d, &map_u, bar, a0c >> 1, row, f);
                     }
                 }
-                if (++b == S8_STAGES) {
+                if (++b == A.stages) {
                     b = 0;
                     par ^= 1;
                 }
@@ -443,7 +444,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     const int cw = min(CW, A.chr_dst_w - cx0);
     const int lstride_w = A.nl_cap >> 1, cstride_w = A.nc_cap >> 1;   /* odd by construction */
     const unsigned char *ring = s8_smem_raw;
-    uint32_t *hb_l = reinterpret_cast<uint32_t *>(s8_smem_raw + S8_STAGES * slot);
+    uint32_t *hb_l = reinterpret_cast<uint32_t *>(s8_smem_raw + A.stages * slot);
     uint32_t *hb_u = hb_l + S8_TW * lstride_w;
     uint32_t *hb_v = hb_u + CW * cstride_w;
 
@@ -454,7 +455,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
         __syncwarp();
         if (lane == 0)
             s8_arrive(empty_a + 8 * sb);
-        if (++sb == S8_STAGES) {
+        if (++sb == A.stages) {
             sb = 0;
             sphase ^= 1;
         }

@@ -43,11 +43,22 @@ def test_c4_full_size_uses_tensor_pipe(mode):
     assert T.first_diff(got.valid(), want.valid()) is None
 
 
-def test_dot_product_variant_still_selectable(monkeypatch):
-    monkeypatch.setenv("SWS_B200_DISABLE", "s8mma")
+@pytest.mark.parametrize("disable,expect", [("s8mma", "scale8_dp4a")])
+def test_older_variants_still_selectable(disable, expect, monkeypatch):
+    monkeypatch.setenv("SWS_B200_DISABLE", disable)
     case = dict(sw=1280, sh=720, sf="nv12", dw=320, dh=180, df="yuv420p", flags=S.SWS_BICUBIC | BX)
     src = T.Frame("nv12", 1280, 720).randomize(3)
     want, _ = T.run_reference(src=src, **case)
     got, name = T.run_cuda(src=src, **case)
-    assert name == "scale8_dp4a"
+    assert name == expect
     assert T.first_diff(got.valid(), want.valid()) is None
+
+
+@pytest.mark.parametrize("slices", [[(0, 128), (128, 232)], [(0, 64), (64, 64), (128, 232)]])
+def test_slices_take_the_row_aligned_paths(slices):
+    """Destination row ranges that do not start on a 16-row block fall back to the dot-product V stage."""
+    case = dict(sw=640, sh=360, sf="yuv420p", dw=320, dh=180, df="yuv420p", flags=S.SWS_BICUBIC | BX)
+    src = T.Frame("yuv420p", 640, 360).randomize(9)
+    want, _ = T.run_reference(src=src, slices=slices, **case)
+    got, name = T.run_cuda(src=src, slices=slices, **case)
+    assert T.first_diff(got.valid(), want.valid()) is None, name
