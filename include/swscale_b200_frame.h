@@ -114,8 +114,10 @@ int sws_is_noop(const AVFrame *dst, const AVFrame *src);
 /* reference swscale.h:392 / format.c:680-691: format, colour properties, range and siting all supported */
 int sws_test_frame(const AVFrame *frame, int output);
 
-/* reference swscale.h:439 / swscale.c:1405.  dst must carry buffers (the frame-pool allocator of the
- * reference lives in libavutil); returns >= 0 or a negative AVERROR. */
+/* reference swscale.h:439 / swscale.c:1405.  A dst without buffers is allocated like the reference does
+ * (swscale.c:1316-1330,1437-1467) through the av_frame_get_buffer() of the libavutil loaded in the calling
+ * process (looked up at run time: this library does not link libavutil); ENOTSUP if there is none.
+ * Returns >= 0 or a negative AVERROR. */
 int sws_scale_frame(SwsContext *c, AVFrame *dst, const AVFrame *src);
 
 /* reference swscale.h:613-669 / swscale.c:1219-1403: the slice-wise frame API of a legacy context */

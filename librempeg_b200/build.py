@@ -61,7 +61,7 @@ def build_native(force=False, verbose=False):
     if force or _newer(SO_PATH, objs):
         log += _run(["nvcc"] + NVCC_ARCH + ["-shared", "-o", SO_PATH] + objs +
                     ["-Xlinker", "--version-script=" + os.path.join(CSRC, "libswscale_b200.ver"),
-                     "-Xlinker", "-Bsymbolic", "-lm"])
+                     "-Xlinker", "-Bsymbolic", "-lm", "-ldl"])
     if verbose:
         print(log)
     return SO_PATH

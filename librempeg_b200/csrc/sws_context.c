@@ -64,8 +64,26 @@ static void release_lanes(SwsInternal *c)
     c->nb_lanes = 0;
 }
 
+static void release_cascade(SwsInternal *c)
+{
+    for (int i = 0; i < 2; i++) {
+        if (c->cascade[i])
+            sws_freeContext(c->cascade[i]);
+        c->cascade[i] = NULL;
+    }
+    for (int i = 0; i < 4; i++) {
+        if (c->cascade_tmp[i])
+            ff_b200_cuda_free(c->cascade_tmp[i]);
+        c->cascade_tmp[i] = NULL;
+        c->cascade_tmp_stride[i] = 0;
+    }
+    c->cascade_main = 0;
+    c->cascade_frame_done = 0;
+}
+
 static void release_tables(SwsInternal *c)
 {
+    release_cascade(c);
     release_lanes(c);
     if (c->cuda)
         ff_b200_cuda_destroy(c->cuda);
@@ -199,6 +217,109 @@ static int plan_colorspace(SwsInternal *c)
                               c->brightness, c->contrast, c->saturation);
 }
 
+/* ------------------------------------------------------------ cascaded contexts
+ * The reference splits a conversion it cannot do in one pass into two contexts with an intermediate picture
+ * (utils.c:1803-1832: a filter longer than the per-line kernels take; utils.c:915-984: YUV -> YUV with two
+ * different matrices goes through packed RGB) and runs them back to back (scale_cascaded(), swscale.c:992-1020).
+ * Same here, with the intermediate picture in HBM: stage 0 stores to device planes, stage 1 reads them. */
+
+static int cascade_alloc_tmp(SwsInternal *c, int w, int h, int fmt)
+{
+    const SwsPixDesc *d = ff_b200_pix_desc(fmt);
+    if (!d)
+        return AVERROR(EINVAL);
+    for (int i = 0; i < d->nb_planes; i++) {
+        const int chroma = i == 1 || i == 2;
+        const int pw = chroma ? ceil_rshift(w, d->log2_cw) : w, ph = chroma ? ceil_rshift(h, d->log2_ch) : h;
+        int rowbytes;
+        if (d->flags & SWSPF_RGB)
+            rowbytes = pw * (d->bpp / 8);
+        else
+            rowbytes = pw * (d->depth > 8 ? 2 : 1) * ((d->flags & SWSPF_SEMI) && i == 1 ? 2 : 1);
+        c->cascade_tmp_stride[i] = (rowbytes + 63) & ~63;          /* av_image_alloc(..., 64) */
+        c->cascade_tmp[i] = ff_b200_cuda_alloc((size_t)c->cascade_tmp_stride[i] * ph);
+        if (!c->cascade_tmp[i])
+            return AVERROR(ENOMEM);
+    }
+    return 0;
+}
+
+static SwsContext *cascade_stage(const SwsContext *parent, int sw, int sh, int sf, int dw, int dh, int df)
+{
+    SwsContext *s = sws_alloc_context();                            /* alloc_set_opts(), utils.c:1076-1102 */
+    if (!s)
+        return NULL;
+    s->flags = parent->flags;
+    s->src_w = sw; s->src_h = sh; s->src_format = sf;
+    s->dst_w = dw; s->dst_h = dh; s->dst_format = df;
+    s->scaler_params[0] = parent->scaler_params[0];
+    s->scaler_params[1] = parent->scaler_params[1];
+    return s;
+}
+
+/* utils.c:1803-1832 */
+static int cascade_long_filter(SwsContext *sws, SwsFilter *srcFilter, SwsFilter *dstFilter)
+{
+    SwsInternal *c = sws_internal(sws);
+    const int srcW = sws->src_w, srcH = sws->src_h, dstW = sws->dst_w, dstH = sws->dst_h;
+    const int tmpW = (int)sqrt((double)(srcW * (int64_t)dstW)), tmpH = (int)sqrt((double)(srcH * (int64_t)dstH));
+    int ret;
+    if (srcW * (int64_t)srcH <= 4LL * dstW * dstH)
+        return AVERROR(EINVAL);
+    if ((ret = cascade_alloc_tmp(c, tmpW, tmpH, AV_PIX_FMT_YUV420P)) < 0)
+        return ret;
+    c->cascade[0] = cascade_stage(sws, srcW, srcH, sws->src_format, tmpW, tmpH, AV_PIX_FMT_YUV420P);
+    c->cascade[1] = cascade_stage(sws, tmpW, tmpH, AV_PIX_FMT_YUV420P, dstW, dstH, sws->dst_format);
+    if (!c->cascade[0] || !c->cascade[1])
+        return AVERROR(ENOMEM);
+    if ((ret = sws_init_context(c->cascade[0], srcFilter, NULL)) < 0 ||
+        (ret = sws_init_context(c->cascade[1], NULL, dstFilter)) < 0) {
+        set_error(c, "cascade stage failed: %s | %s", sws_internal(c->cascade[0])->last_error,
+                  sws_internal(c->cascade[1])->last_error);
+        return ret;
+    }
+    c->cascade_main = 0;
+    return 0;
+}
+
+/* utils.c:915-984: YUV (or gray) on both sides and two different matrices */
+static int cascade_matrix_change(SwsContext *sws, const int inv_table[4], int srcRange, const int table[4],
+                                 int dstRange, int brightness, int contrast, int saturation)
+{
+    SwsInternal *c = sws_internal(sws);
+    const int srcW = sws->src_w, srcH = sws->src_h, dstW = sws->dst_w, dstH = sws->dst_h;
+    const int tmp_fmt = c->dst_bpc > 8 ? AV_PIX_FMT_BGR48LE : AV_PIX_FMT_BGR24;
+    const int small = srcW * (int64_t)srcH > dstW * (int64_t)dstH;
+    const int tmpW = small ? dstW : srcW, tmpH = small ? dstH : srcH;
+    int ret;
+    if (!ff_b200_pix_desc(tmp_fmt)->as_input) {
+        set_error(c, "YUV->YUV matrix change into a >8-bit destination needs a 16-bit RGB source reader");
+        return AVERROR(ENOTSUP);
+    }
+    if ((ret = cascade_alloc_tmp(c, tmpW, tmpH, tmp_fmt)) < 0)
+        return ret;
+    c->cascade[0] = cascade_stage(sws, srcW, srcH, sws->src_format, tmpW, tmpH, tmp_fmt);
+    c->cascade[1] = cascade_stage(sws, tmpW, tmpH, tmp_fmt, dstW, dstH, sws->dst_format);
+    if (!c->cascade[0] || !c->cascade[1])
+        return AVERROR(ENOMEM);
+    c->cascade[0]->alpha_blend = sws->alpha_blend;
+    if ((ret = sws_init_context(c->cascade[0], NULL, NULL)) < 0) {
+        set_error(c, "cascade stage 0: %s", sws_internal(c->cascade[0])->last_error);
+        return ret;
+    }
+    /* both sides are set although the RGB side of each stage is ignored */
+    sws_setColorspaceDetails(c->cascade[0], inv_table, srcRange, table, dstRange, brightness, contrast, saturation);
+    c->cascade[1]->src_range = srcRange;
+    c->cascade[1]->dst_range = dstRange;
+    if ((ret = sws_init_context(c->cascade[1], NULL, NULL)) < 0) {
+        set_error(c, "cascade stage 1: %s", sws_internal(c->cascade[1])->last_error);
+        return ret;
+    }
+    sws_setColorspaceDetails(c->cascade[1], inv_table, srcRange, table, dstRange, 0, 1 << 16, 1 << 16);
+    c->cascade_main = 0;
+    return 0;
+}
+
 /* ------------------------------------------------------------ colourspace API */
 
 int sws_setColorspaceDetails(SwsContext *sws, const int inv_table[4], int srcRange,
@@ -230,15 +351,23 @@ int sws_setColorspaceDetails(SwsContext *sws, const int inv_table[4], int srcRan
     sws->dst_range = dstRange;
     c->colorspace_set = 1;
 
+    if (c->cascade[c->cascade_main])        /* utils.c:909-910 */
+        return sws_setColorspaceDetails(c->cascade[c->cascade_main], inv_table, srcRange, table, dstRange,
+                                        brightness, contrast, saturation);
     if (!changed || !c->initialized)
         return 0;
 
     if (!is_rgb(sws->dst_format) && !is_rgb(sws->src_format) &&
         memcmp(c->dst_colorspace, c->src_colorspace, sizeof(int) * 4)) {
         /* the reference cascades through an RGB intermediate here (utils.c:915-984) */
-        set_error(c, "YUV->YUV with differing matrices is not on the CUDA hot path");
-        c->refused = 1;             /* the plan no longer describes what the reference would compute: scaling fails */
-        return -1;
+        int ret = cascade_matrix_change(sws, inv_table, srcRange, table, dstRange, brightness, contrast, saturation);
+        if (ret < 0) {
+            release_cascade(c);
+            c->refused = 1;         /* the plan no longer describes what the reference would compute: scaling fails */
+            return -1;
+        }
+        c->refused = 0;
+        return 0;
     }
     c->refused = 0;
     release_lanes(c);               /* lanes carry copies of the plan: rebuilt on the next batch call */
@@ -710,8 +839,11 @@ static int init_single(SwsContext *sws, int with_device)
 
 fir_fail:
     if (ret == SWS_B200_USE_CASCADE) {
-        set_error(c, "filter too long: the reference would cascade two contexts (utils.c:1803-1832)");
-        ret = AVERROR(ENOTSUP);
+        if (!with_device) {
+            set_error(c, "filter too long: the reference cascades two contexts (utils.c:1803-1832)");
+            return AVERROR(ENOTSUP);
+        }
+        ret = SWS_B200_USE_CASCADE;          /* sws_init_context() builds the two stages */
     } else {
         set_error(c, "filter construction failed (%d)", ret);
     }
@@ -731,6 +863,16 @@ int sws_init_context(SwsContext *sws, SwsFilter *srcFilter, SwsFilter *dstFilter
     c->dst_filter_tmp = dstFilter;
     ret = init_single(sws, 1);
     c->src_filter_tmp = c->dst_filter_tmp = NULL;
+    if (ret == SWS_B200_USE_CASCADE) {
+        release_tables(c);
+        ret = cascade_long_filter(sws, srcFilter, dstFilter);
+        if (ret >= 0) {
+            c->initialized = 1;
+            c->dst_y = 0;
+            c->slice_dir = 0;
+            return 0;
+        }
+    }
     if (ret < 0)
         release_tables(c);
     return ret;
@@ -875,8 +1017,9 @@ static void rows_needed(const SwsInternal *c, int y, int *last_lum, int *last_ch
         *last_chr = c->chr_src_h - 1;
 }
 
-int sws_scale(SwsContext *sws, const uint8_t *const srcSlice[], const int srcStride[],
-              int srcSliceY, int srcSliceH, uint8_t *const dst[], const int dstStride[])
+/* one slice through one (non-cascaded) context; mem: SWS_MEM_* for device-resident sides */
+static int scale_slice(SwsContext *sws, const uint8_t *const srcSlice[], const int srcStride[],
+                       int srcSliceY, int srcSliceH, uint8_t *const dst[], const int dstStride[], int mem)
 {
     SwsInternal *c = sws_internal(sws);
     int macro_src, y0, y1, ret, avail_l, avail_c;
@@ -967,7 +1110,7 @@ int sws_scale(SwsContext *sws, const uint8_t *const srcSlice[], const int srcStr
     }
 
     ret = ff_b200_cuda_scale_host(c->cuda, src2, sstride, srcSliceY, srcSliceH, 1,
-                                  dst2, dstride, y0, y1);
+                                  dst2, dstride, y0, y1, mem);
     if (ret < 0) {
         set_error(c, "CUDA conversion failed (%d)", ret);
         c->slice_dir = 0;
@@ -979,12 +1122,67 @@ int sws_scale(SwsContext *sws, const uint8_t *const srcSlice[], const int srcStr
     return y1 - y0;
 }
 
+/* scale_cascaded() (swscale.c:992-1020): the first stage assembles the intermediate picture slice by slice; the
+ * second runs once the whole source has been consumed.  The intermediate never leaves the device. */
+static int scale_cascaded(SwsInternal *c, const uint8_t *const srcSlice[], const int srcStride[],
+                          int srcSliceY, int srcSliceH, uint8_t *const dst[], const int dstStride[])
+{
+    SwsInternal *c0 = sws_internal(c->cascade[0]);
+    int ret = scale_slice(c->cascade[0], srcSlice, srcStride, srcSliceY, srcSliceH, c->cascade_tmp,
+                          c->cascade_tmp_stride, SWS_MEM_DST_DEVICE);
+    if (ret < 0) {
+        set_error(c, "cascade stage 0: %s", c0->last_error);
+        return ret;
+    }
+    if (c0->slice_dir != 0)
+        return 0;                       /* intermediate incomplete: no output lines yet */
+    ret = scale_slice(c->cascade[1], (const uint8_t *const *)c->cascade_tmp, c->cascade_tmp_stride, 0,
+                      c->cascade[0]->dst_h, dst, dstStride, SWS_MEM_SRC_DEVICE);
+    if (ret < 0)
+        set_error(c, "cascade stage 1: %s", sws_internal(c->cascade[1])->last_error);
+    return ret;
+}
+
+int sws_scale(SwsContext *sws, const uint8_t *const srcSlice[], const int srcStride[],
+              int srcSliceY, int srcSliceH, uint8_t *const dst[], const int dstStride[])
+{
+    SwsInternal *c = sws_internal(sws);
+    if (!c || !c->initialized)
+        return AVERROR(EINVAL);
+    if (c->cascade[0]) {
+        if (!srcStride || !dstStride || !dst || !srcSlice)
+            return AVERROR(EINVAL);
+        if (c->refused)
+            return AVERROR(ENOTSUP);
+        return scale_cascaded(c, srcSlice, srcStride, srcSliceY, srcSliceH, dst, dstStride);
+    }
+    return scale_slice(sws, srcSlice, srcStride, srcSliceY, srcSliceH, dst, dstStride, 0);
+}
+
 /* Whole source frame in, destination rows [y0, y1) out (dst[] addresses frame row 0): sws_receive_slice()
- * and the destination-slice mode of the in-tree hook (reference swscale.c:371-375). */
-int ff_b200_scale_frame_rows(SwsInternal *c, const uint8_t *const src[4], const int srcStride[4],
+ * and the destination-slice mode of the in-tree hook (reference swscale.c:371-375).  `upload` = 0: the source
+ * was already moved (and, cascaded, the intermediate built) by an earlier call for the same frame. */
+int ff_b200_scale_frame_rows(SwsInternal *c, const uint8_t *const src[4], const int srcStride[4], int upload,
                              uint8_t *const dst[4], const int dstStride[4], int y0, int y1)
 {
-    int ret = ff_b200_cuda_scale_host(c->cuda, src, srcStride, 0, c->opts.src_h, 1, dst, dstStride, y0, y1);
+    int ret;
+    if (c->cascade[0]) {
+        SwsInternal *c0 = sws_internal(c->cascade[0]), *c1 = sws_internal(c->cascade[1]);
+        if (upload) {
+            ret = ff_b200_cuda_scale_host(c0->cuda, src, srcStride, 0, c0->opts.src_h, 1, c->cascade_tmp,
+                                          c->cascade_tmp_stride, 0, c0->opts.dst_h, SWS_MEM_DST_DEVICE);
+            if (ret < 0) {
+                set_error(c, "cascade stage 0 failed (%d)", ret);
+                return ret;
+            }
+        }
+        ret = ff_b200_cuda_scale_host(c1->cuda, (const uint8_t *const *)c->cascade_tmp, c->cascade_tmp_stride, 0,
+                                      c1->opts.src_h, 0, dst, dstStride, y0, y1, SWS_MEM_SRC_DEVICE);
+        if (ret < 0)
+            set_error(c, "cascade stage 1 failed (%d)", ret);
+        return ret;
+    }
+    ret = ff_b200_cuda_scale_host(c->cuda, src, srcStride, 0, c->opts.src_h, upload, dst, dstStride, y0, y1, 0);
     if (ret < 0)
         set_error(c, "CUDA conversion failed (%d)", ret);
     return ret;
@@ -1011,6 +1209,30 @@ int sws_cuda_scale_batch(SwsContext *sws, const uint8_t *const src[4], const int
     if (c->refused) {
         set_error(c, "the last sws_setColorspaceDetails() asked for a conversion that is not on the CUDA hot path");
         return AVERROR(ENOTSUP);
+    }
+    if (c->cascade[0]) {
+        /* frame by frame through both stages, the intermediate stays in HBM */
+        SwsInternal *c0 = sws_internal(c->cascade[0]), *c1 = sws_internal(c->cascade[1]);
+        for (int f = 0; f < nb_frames; f++) {
+            const uint8_t *s[4];
+            uint8_t *d[4];
+            for (int i = 0; i < 4; i++) {
+                s[i] = src[i] ? src[i] + (srcFrameStride ? srcFrameStride[i] : 0) * f : NULL;
+                d[i] = dst[i] ? dst[i] + (dstFrameStride ? dstFrameStride[i] : 0) * f : NULL;
+            }
+            ret = ff_b200_cuda_launch(c0->cuda, s, srcStride, NULL, c->cascade_tmp, c->cascade_tmp_stride, NULL, 1, 0,
+                                      c0->opts.dst_h);
+            if (ret >= 0)
+                ret = ff_b200_cuda_sync(c0->cuda);
+            if (ret >= 0)
+                ret = ff_b200_cuda_launch(c1->cuda, (const uint8_t *const *)c->cascade_tmp, c->cascade_tmp_stride, NULL,
+                                          d, dstStride, NULL, 1, 0, sws->dst_h);
+            if (ret >= 0)
+                ret = ff_b200_cuda_sync(c1->cuda);
+            if (ret < 0)
+                return ret;
+        }
+        return sws->dst_h;
     }
     ret = ff_b200_cuda_launch(c->cuda, src, srcStride, srcFrameStride, dst, dstStride,
                               dstFrameStride, nb_frames, 0, sws->dst_h);
@@ -1043,7 +1265,7 @@ static void *lane_main(void *arg)
             s[i] = j->src[i] ? j->src[i] + (j->src_fstride ? j->src_fstride[i] : 0) * f : NULL;
             d[i] = j->dst[i] ? j->dst[i] + (j->dst_fstride ? j->dst_fstride[i] : 0) * f : NULL;
         }
-        j->ret = ff_b200_cuda_scale_host(j->st, s, j->src_stride, 0, c->opts.src_h, 1, d, j->dst_stride, 0, c->opts.dst_h);
+        j->ret = ff_b200_cuda_scale_host(j->st, s, j->src_stride, 0, c->opts.src_h, 1, d, j->dst_stride, 0, c->opts.dst_h, 0);
         if (j->ret < 0)
             break;
     }
@@ -1066,6 +1288,20 @@ int sws_cuda_scale_batch_host(SwsContext *sws, const uint8_t *const src[4], cons
     if (c->refused) {
         set_error(c, "the last sws_setColorspaceDetails() asked for a conversion that is not on the CUDA hot path");
         return AVERROR(ENOTSUP);
+    }
+    if (c->cascade[0]) {                /* cascaded conversions go frame by frame through sws_scale() */
+        for (int f = 0; f < nb_frames; f++) {
+            const uint8_t *s[4];
+            uint8_t *d[4];
+            for (int i = 0; i < 4; i++) {
+                s[i] = src[i] ? src[i] + (srcFrameStride ? srcFrameStride[i] : 0) * f : NULL;
+                d[i] = dst[i] ? dst[i] + (dstFrameStride ? dstFrameStride[i] : 0) * f : NULL;
+            }
+            ret = sws_scale(sws, s, srcStride, 0, sws->src_h, d, dstStride);
+            if (ret < 0)
+                return ret;
+        }
+        return sws->dst_h;
     }
     visible = sws_cuda_device_count();
     if (nb_devices <= 0 || nb_devices > visible)
@@ -1161,24 +1397,32 @@ int sws_cuda_scale_batch_host(SwsContext *sws, const uint8_t *const src[4], cons
 int sws_cuda_sync(SwsContext *sws)
 {
     SwsInternal *c = sws_internal(sws);
+    if (c && c->cascade[1])
+        return sws_cuda_sync(c->cascade[1]);
     return c && c->cuda ? ff_b200_cuda_sync(c->cuda) : AVERROR(EINVAL);
 }
 
 void *sws_cuda_stream(SwsContext *sws)
 {
     SwsInternal *c = sws_internal(sws);
+    if (c && c->cascade[1])
+        return sws_cuda_stream(c->cascade[1]);
     return c && c->cuda ? ff_b200_cuda_stream(c->cuda) : NULL;
 }
 
 long sws_cuda_launch_count(SwsContext *sws)
 {
     SwsInternal *c = sws_internal(sws);
+    if (c && c->cascade[0])
+        return sws_cuda_launch_count(c->cascade[0]) + sws_cuda_launch_count(c->cascade[1]);
     return c && c->cuda ? ff_b200_cuda_launch_count(c->cuda) : 0;
 }
 
 const char *sws_cuda_kernel_name(SwsContext *sws)
 {
     SwsInternal *c = sws_internal(sws);
+    if (c && c->cascade[1])
+        return "cascade";
     return c && c->cuda ? ff_b200_cuda_kernel_name(c->cuda) : "";
 }
 

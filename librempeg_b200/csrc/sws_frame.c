@@ -10,6 +10,7 @@
  * and dither from the outer context.  A frame is always ONE launch (the reference splits it over
  * slice threads, graph.c:228-235; a GPU pass wants num_slices = 1 as for error diffusion, :475-476).
  */
+#include <dlfcn.h>
 #include <errno.h>
 #include <stdlib.h>
 #include <string.h>
@@ -17,6 +18,28 @@
 #include "sws_internal.h"
 #include "swscale_b200_frame.h"
 #include "swscale_b200_cuda.h"
+
+/* Destination buffers (reference swscale.c:1316-1330,1437-1467: av_frame_get_buffer() on a legacy context, the
+ * frame pool in the dynamic mode).  AVBufferRef objects can only be made by libavutil itself, and this library
+ * does not link it: every caller that owns an AVFrame has it loaded, so the allocator is looked up in the
+ * running process.  Without it (a caller with hand-built frame structs) the old answer stands: ENOTSUP. */
+typedef int (*get_buffer_fn)(AVFrame *frame, int align);
+
+static int alloc_dst(AVFrame *dst, int width, int height, int format)
+{
+    static get_buffer_fn get_buffer;
+    static int looked_up;
+    if (!looked_up) {
+        get_buffer = (get_buffer_fn)dlsym(RTLD_DEFAULT, "av_frame_get_buffer");
+        looked_up = 1;
+    }
+    if (!get_buffer)
+        return AVERROR(ENOTSUP);
+    dst->width  = width;
+    dst->height = height;
+    dst->format = format;
+    return get_buffer(dst, 0);
+}
 
 typedef struct FrameDesc {
     int format, width, height, range, csp, loc;
@@ -234,8 +257,13 @@ int sws_scale_frame(SwsContext *ctx, AVFrame *dst, const AVFrame *src)
         return ret;
     if (!src->data[0])
         return 0;
-    if (!dst->data[0])
-        return AVERROR(ENOTSUP);   /* buffer allocation needs libavutil's frame pool (swscale.c:1437-1467) */
+    if (!dst->data[0]) {
+        /* user did not provide buffers: allocate them like the reference (swscale.c:1437-1467); hardware frames
+         * must come allocated (sws_frame_setup() checked that) */
+        ret = alloc_dst(dst, dst->width, dst->height, dst->format);
+        if (ret < 0)
+            return ret;
+    }
     if (src->format == AV_PIX_FMT_CUDA) {
         /* device-resident planes: one launch on the context stream, complete on return */
         ret = sws_cuda_scale_batch(c->dyn, (const uint8_t *const *)src->data, src->linesize, NULL,
@@ -260,8 +288,11 @@ int sws_frame_start(SwsContext *ctx, AVFrame *dst, const AVFrame *src)
     SwsInternal *c = sws_internal(ctx);
     if (!c || !c->initialized || !dst || !src)
         return AVERROR(EINVAL);
-    if (!dst->data[0])
-        return AVERROR(ENOTSUP);
+    if (!dst->data[0]) {                    /* swscale.c:1316-1330: the context describes the destination */
+        int ret = alloc_dst(dst, ctx->dst_w, ctx->dst_h, ctx->dst_format);
+        if (ret < 0)
+            return ret;
+    }
     if (!frame_matches(ctx, dst, src))
         return AVERROR(EINVAL);
     c->frame_src = src;
@@ -322,9 +353,8 @@ int sws_receive_slice(SwsContext *ctx, unsigned int slice_start, unsigned int sl
     dst = (AVFrame *)c->frame_dst;
     /* whole source is available: upload it once, then convert exactly the requested rows
      * (the reference's scale_dst mode, swscale.c:371-375) */
-    ret = ff_b200_cuda_scale_host(c->cuda, (const uint8_t *const *)src->data, src->linesize, 0, ctx->src_h,
-                                  !c->frame_uploaded, dst->data, dst->linesize,
-                                  (int)slice_start, (int)(slice_start + slice_height));
+    ret = ff_b200_scale_frame_rows(c, (const uint8_t *const *)src->data, src->linesize, !c->frame_uploaded,
+                                   dst->data, dst->linesize, (int)slice_start, (int)(slice_start + slice_height));
     if (ret < 0)
         return ret;
     c->frame_uploaded = 1;

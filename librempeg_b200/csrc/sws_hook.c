@@ -106,7 +106,7 @@ int sws_b200_hook_scale_rows(void *h, const uint8_t *const src[4], const int src
     for (int i = 0; i < 4; i++)
         if (dst[i])
             base[i] = dst[i] - (ptrdiff_t)(dstY >> ((i == 1 || i == 2) ? c->chr_dst_vsub : 0)) * dstStride[i];
-    ret = ff_b200_scale_frame_rows(c, src, srcStride, base, dstStride, dstY, dstY + dstH);
+    ret = ff_b200_scale_frame_rows(c, src, srcStride, 1, base, dstStride, dstY, dstY + dstH);
     return ret < 0 ? ret : dstH;
 }
 

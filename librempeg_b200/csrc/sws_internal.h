@@ -190,10 +190,14 @@ int  ff_b200_cuda_launch(SwsCudaState *st,
                          uint8_t *const dst[4], const int dst_stride[4], const int64_t dst_fstride[4],
                          int nb_frames, int y0, int y1);
 /* host frame in, host rows [y0,y1) out; synchronous */
+#define SWS_MEM_SRC_DEVICE 1   /* src[] are device pointers to whole planes */
+#define SWS_MEM_DST_DEVICE 2   /* dst[] are device pointers to whole planes */
 int  ff_b200_cuda_scale_host(SwsCudaState *st,
                              const uint8_t *const src[4], const int src_stride[4],
                              int src_y, int src_h, int upload,
-                             uint8_t *const dst[4], const int dst_stride[4], int y0, int y1);
+                             uint8_t *const dst[4], const int dst_stride[4], int y0, int y1, int mem);
+void *ff_b200_cuda_alloc(size_t bytes);
+void ff_b200_cuda_free(void *p);
 /* page-locked host frames first, first+step, ... through a ring of staging sets; enqueue only, then wait */
 int  ff_b200_cuda_frames_enqueue(SwsCudaState *st,
                                  const uint8_t *const src[4], const int src_stride[4], const int64_t src_fstride[4],
@@ -234,6 +238,13 @@ typedef struct SwsInternal {
     void *dyn_key;                   /* description it was planned for */
     const void *frame_src, *frame_dst;   /* sws_frame_start() .. sws_frame_end() */
     int frame_rows_sent, frame_uploaded;
+    /* cascaded contexts (reference utils.c:1803-1832 filters too long for one pass; utils.c:915-984 YUV -> YUV with
+     * two different matrices goes through RGB): two inner contexts and an intermediate picture kept in HBM */
+    SwsContext *cascade[2];
+    int cascade_main;                /* which inner context sws_setColorspaceDetails() is forwarded to */
+    uint8_t *cascade_tmp[4];
+    int cascade_tmp_stride[4];
+    int cascade_frame_done;          /* the first stage has consumed the whole source frame */
     /* lanes of sws_cuda_scale_batch_host(): extra device states (own stream, own staging) spread over the
      * visible devices so that several host frames are in flight at once */
     SwsCudaState *lanes[SWS_B200_MAX_LANES];
@@ -249,7 +260,7 @@ int  ff_b200_numa_node_of_pci(const char *bus_id);
 int  ff_b200_numa_prefer(int node);
 void ff_b200_numa_restore(void);
 int  ff_b200_numa_bind_thread(int node);
-int ff_b200_scale_frame_rows(SwsInternal *c, const uint8_t *const src[4], const int srcStride[4],
+int ff_b200_scale_frame_rows(SwsInternal *c, const uint8_t *const src[4], const int srcStride[4], int upload,
                              uint8_t *const dst[4], const int dstStride[4], int y0, int y1);
 
 #ifdef __cplusplus

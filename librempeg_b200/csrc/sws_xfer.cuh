@@ -738,16 +738,101 @@ extern "C" int ff_b200_cuda_frame_is_pinned(SwsCudaState *st, const uint8_t *con
     return planes_pinned(planes, dst_side ? st->dst_rows : st->src_rows, nullptr) ? 1 : 0;
 }
 
+extern "C" void *ff_b200_cuda_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void ff_b200_cuda_free(void *p)
+{
+    cudaFree(p);
+}
+
+/* mem: SWS_MEM_SRC_DEVICE -- src[] are DEVICE pointers to whole planes (frame row 0), nothing is uploaded;
+ *      SWS_MEM_DST_DEVICE -- dst[] are DEVICE pointers to whole planes, the kernel stores there, nothing is
+ *      downloaded.  Cascaded contexts keep their intermediate picture in HBM this way. */
 extern "C" int ff_b200_cuda_scale_host(SwsCudaState *st,
                                        const uint8_t *const src[4], const int src_stride[4],
                                        int src_y, int src_h, int upload,
-                                       uint8_t *const dst[4], const int dst_stride[4], int y0, int y1)
+                                       uint8_t *const dst[4], const int dst_stride[4], int y0, int y1, int mem)
 {
     const SwsCudaPlan *p = &st->plan;
     DeviceGuard guard(st->device);
     int ret = ensure_staging(st);
     if (ret < 0)
         return ret;
+    if (mem) {
+        const bool sdev = mem & SWS_MEM_SRC_DEVICE, ddev = mem & SWS_MEM_DST_DEVICE;
+        if (upload && !sdev)
+            for (int i = 0; i < 4; i++) {
+                if (!st->src_rows[i])
+                    continue;
+                if (!src[i])
+                    return AVERROR(EINVAL);
+                const int vs = (i == 1 || i == 2) ? p->chr_src_vsub : 0;
+                const int r0 = src_y >> vs;
+                int r1 = -((-(src_y + src_h)) >> vs);
+                if (r1 > st->src_rows[i])
+                    r1 = st->src_rows[i];
+                ret = upload_rows(st, st->d_src[i] + (size_t)r0 * st->d_src_stride[i], st->d_src_stride[i],
+                                  src[i], src_stride[i], st->src_rowbytes[i], r1 - r0, st->stream);
+                if (ret < 0)
+                    return ret;
+            }
+        if (y1 > y0) {
+            int64_t zero[4] = { 0, 0, 0, 0 };
+            /* a bottom-up device destination (the first stage of a cascade fed with bottom-up slices): convert into
+             * the staging planes, then mirror the rows into place */
+            const bool flip = ddev && dst_stride[0] < 0;
+            const bool direct = ddev && !flip;
+            ret = ff_b200_cuda_launch(st, sdev ? src : (const uint8_t *const *)st->d_src, sdev ? src_stride : st->d_src_stride, zero,
+                                      direct ? dst : (uint8_t *const *)st->d_dst, direct ? dst_stride : st->d_dst_stride, zero,
+                                      1, y0, y1);
+            if (ret < 0)
+                return ret;
+            if (flip)
+                for (int i = 0; i < 4; i++) {
+                    if (!st->dst_rows[i] || !dst[i])
+                        continue;
+                    const int vs = (i == 1 || i == 2) && st->dst_rows[i] != p->dst_h ? p->chr_dst_vsub : 0;
+                    const int r0 = y0 >> vs;
+                    const int r1 = (y1 == p->dst_h) ? st->dst_rows[i] : (y1 >> vs);
+                    if (r1 <= r0)
+                        continue;
+                    /* picture row r lives at dst[i] + r * stride (stride < 0): rows r1-1 .. r0 in memory order */
+                    const long long n = (long long)((st->dst_rowbytes[i] + 15) >> 4) * (r1 - r0);
+                    sws_flip_rows_kernel<<<(unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st->stream>>>(
+                        dst[i] + (ptrdiff_t)(r1 - 1) * dst_stride[i], -dst_stride[i],
+                        st->d_dst[i] + (size_t)r0 * st->d_dst_stride[i], st->d_dst_stride[i], st->dst_rowbytes[i], r1 - r0);
+                    CUDA_OK(cudaGetLastError());
+                    st->launches++;
+                }
+            if (!ddev)
+                for (int i = 0; i < 4; i++) {
+                    if (!st->dst_rows[i])
+                        continue;
+                    if (!dst[i])
+                        return AVERROR(EINVAL);
+                    const int vs = (i == 1 || i == 2) && st->dst_rows[i] != p->dst_h ? p->chr_dst_vsub : 0;
+                    const int r0 = y0 >> vs;
+                    const int r1 = (y1 == p->dst_h) ? st->dst_rows[i] : (y1 >> vs);
+                    if (r1 <= r0)
+                        continue;
+                    ret = download_rows(st, dst[i] + (ptrdiff_t)r0 * dst_stride[i], dst_stride[i],
+                                        st->d_dst[i] + (size_t)r0 * st->d_dst_stride[i], st->d_dst_stride[i],
+                                        st->dst_rowbytes[i], r1 - r0, st->stream);
+                    if (ret < 0)
+                        return ret;
+                }
+        }
+        CUDA_OK(cudaStreamSynchronize(st->stream));
+        return 0;
+    }
 
     bool positive = true;
     for (int i = 0; i < 4; i++) {

@@ -301,3 +301,41 @@ def test_scale_frame_cuda_hw_frames(geom):
             assert np.array_equal(got.cpu().numpy()[:rows, :rb], w[:rows, :rb])
     finally:
         S.lib().sws_freeContext(ctx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["dynamic", "legacy"])
+@pytest.mark.parametrize("case", [(640, 360, "yuv420p", 640, 360, "rgb24"), (640, 360, "yuv420p", 320, 180, "yuv420p"),
+                                  (322, 242, "nv12", 400, 300, "bgra")])
+def test_scale_frame_allocates_destination(mode, case, tmp_path):
+    """swscale.c:1316-1330,1437-1467: a destination frame without buffers is allocated by sws_scale_frame().  The
+    library finds libavutil's allocator in the calling process; here that process is a small C program that
+    links the reference's own libavutil objects."""
+    import glob
+    import subprocess
+    from librempeg_b200 import build as native
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    objs = sorted(glob.glob(os.path.join(root, "oracle", "_ref", "obj", "avu_*.o")))
+    if not objs:
+        pytest.skip("oracle/_ref/obj (reference libavutil objects) not built")
+    exe = os.path.join(root, "tests", "native", "_frame_alloc_probe")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(exe[:-len("_frame_alloc_probe")] + "frame_alloc_probe.c"):
+        cmd = ["gcc", "-O1", "-rdynamic", "-o", exe, os.path.join(root, "tests", "native", "frame_alloc_probe.c"),
+               "-I", os.path.join(root, "include")] + objs + \
+              ["-L", os.path.dirname(native.SO_PATH), "-lswscale_b200", "-Wl,-rpath," + os.path.dirname(native.SO_PATH),
+               "-lm", "-lpthread", "-ldl"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+    sw, sh, sf, dw, dh, df = case
+    flags = S.SWS_BICUBIC | S.BX
+    src = T.Frame(sf, sw, sh).randomize(77)
+    # the dynamic mode reads the frames' (unspecified) colour properties: same defaults as a legacy context
+    want, _ = T.run_reference(sw, sh, sf, dw, dh, df, flags, src)
+    sp, dp = tmp_path / "src.bin", tmp_path / "dst.bin"
+    sp.write_bytes(b"".join(p.tobytes() for p in src.valid()))
+    r = subprocess.run([exe, mode, str(sw), str(sh), str(S.pix_fmt(sf)), str(dw), str(dh), str(S.pix_fmt(df)),
+                        str(flags), str(sp), str(dp)], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, (r.returncode, r.stderr[-500:])
+    got = np.frombuffer(dp.read_bytes(), np.uint8)
+    exp = np.concatenate([p.reshape(-1) for p in want.valid()])
+    assert got.size == exp.size and np.array_equal(got, exp)
