@@ -55,6 +55,36 @@ struct DeviceGuard {
     }
 };
 
+/* cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the FUNCTION (per device), not of a launch: two
+ * live contexts that use the same kernel instantiation with different tile geometries would lower each other's
+ * limit.  Keep the largest size ever asked for. */
+#include <mutex>
+static cudaError_t set_max_smem(const void *func, size_t bytes)
+{
+    struct Entry { const void *func; int dev; size_t bytes; };
+    static Entry table[512];
+    static int used;
+    static std::mutex lock;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(lock);
+    Entry *e = nullptr;
+    for (int i = 0; i < used; i++)
+        if (table[i].func == func && table[i].dev == dev)
+            e = &table[i];
+    if (e && e->bytes >= bytes)
+        return cudaSuccess;
+    cudaError_t r = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (r != cudaSuccess)
+        return r;
+    if (!e && used < 512)
+        e = &table[used++];
+    if (e) {
+        e->func = func; e->dev = dev; e->bytes = bytes;
+    }
+    return cudaSuccess;
+}
+
 /* ordered-dither rows for 8-bit planar output of >8-bit sources; same matrix as
  * ff_dither_8x8_128 (reference swscale.c:42-52) */
 __constant__ __align__(8) uint8_t c_dither_8x8_128[8][8] = {
@@ -1744,17 +1774,14 @@ static int fast420_setup(SwsCudaState *st, const SwsFirBank *vc)
         return 0;
     const int fmt = fast420_fmt(p->dst_kind);
     const int bpp = fmt >= F420_RGBA ? 4 : 3;
-    CUDA_OK(cudaFuncSetAttribute((const void *)pick_fast420(fmt, p->src_layout, false, st->fast_v422),
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 F420_SMEM_CROWS(bpp, F420_TW, F420_TH, st->fast_v422 ? F420_TH + 4 : F420_CROWS)));
+    CUDA_OK(set_max_smem((const void *)pick_fast420(fmt, p->src_layout, false, st->fast_v422), (size_t)(F420_SMEM_CROWS(bpp, F420_TW, F420_TH, st->fast_v422 ? F420_TH + 4 : F420_CROWS))));
     /* 128 x 64 tiles when they cover the frame width with less waste than 256 x 32 tiles (1920, 640, ...) */
     st->fast_narrow = 0;
     if (!st->fast_v422 && (p->dst_w + 127) / 128 * 128 < (p->dst_w + 255) / 256 * 256 && !getenv("SWS_B200_NO_NARROW")) {
         if ((ret = fast420_rows(p, vc, 2 * F420_TH, F420_CROWS_NARROW, &st->d_fast_rows_narrow, &fits)) < 0)
             return ret;
         if (fits) {
-            CUDA_OK(cudaFuncSetAttribute((const void *)pick_fast420(fmt, p->src_layout, true),
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, F420_SMEM(bpp)));
+            CUDA_OK(set_max_smem((const void *)pick_fast420(fmt, p->src_layout, true), (size_t)(F420_SMEM(bpp))));
             st->fast_narrow = 1;
         }
     }
@@ -1902,10 +1929,8 @@ static int fast16_setup(SwsCudaState *st, const SwsFirBank *vc)
     int ret = fast16_rows(st, vc, taps);
     if (ret <= 0)
         return ret;
-    CUDA_OK(cudaFuncSetAttribute((const void *)pick_fast16(taps, false),
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
-    CUDA_OK(cudaFuncSetAttribute((const void *)pick_fast16(taps, true),
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
+    CUDA_OK(set_max_smem((const void *)pick_fast16(taps, false), (size_t)(F16_SMEM)));
+    CUDA_OK(set_max_smem((const void *)pick_fast16(taps, true), (size_t)(F16_SMEM)));
     st->fast16_ok = 1;
     st->fast16_taps = taps;
     st->kernel_name = "fast420_rgb16_tma";
@@ -2021,8 +2046,7 @@ static int fasthi8_setup(SwsCudaState *st, const SwsFirBank *vc)
         return ret;
     st->fasthi8_crows = crows;
     const int fmt = fast420_fmt(p->dst_kind);
-    CUDA_OK(cudaFuncSetAttribute((const void *)pick_fasthi8(taps, fmt, semi), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 H8_SMEM(fmt >= F420_RGBA ? 4 : 3, crows)));
+    CUDA_OK(set_max_smem((const void *)pick_fasthi8(taps, fmt, semi), (size_t)(H8_SMEM(fmt >= F420_RGBA ? 4 : 3, crows))));
     st->fasthi8_ok = 1;
     st->fast16_taps = taps;
     st->kernel_name = "fast420_hi8_tma";
@@ -2432,8 +2456,7 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
         st->s8_hl_goff = (int *)(t + o_gl); st->s8_hc_goff = (int *)(t + o_gc);
         st->s8_hl_B = (uint32_t *)(t + o_bl); st->s8_hc_B = (uint32_t *)(t + o_bc);
     }
-    CUDA_OK(cudaFuncSetAttribute((const void *)pick_scale8(st->s8_fs4, rgb, mma), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
+    CUDA_OK(set_max_smem((const void *)pick_scale8(st->s8_fs4, rgb, mma), (size_t)((int)smem)));
     st->s8_ok = 1;
     if (getenv("SWS_B200_DEBUG"))
         fprintf(stderr, "[swscaler-b200] scale8: %s fs4=%d tile_h=%d nl_cap=%d nc_cap=%d seg_l=%d seg_c=%d slot=%d smem=%zu\n",
@@ -2590,8 +2613,7 @@ extern "C" int ff_b200_cuda_create(SwsCudaState **out, SwsCudaPlan *plan,
     if (ret < 0)
         return ret;
     st->kernel_name = "generic_tile";
-    CUDA_OK(cudaFuncSetAttribute((const void *)pick_generic(&st->plan),
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem_bytes));
+    CUDA_OK(set_max_smem((const void *)pick_generic(&st->plan), (size_t)((int)st->smem_bytes)));
     CUDA_OK(cudaDeviceGetAttribute(&st->num_sms, cudaDevAttrMultiProcessorCount, dev));
     ret = fast420_setup(st, vc);
     if (ret < 0)
@@ -2785,8 +2807,7 @@ static int tile15_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
         return 0;
     st->t15_srck = srck; st->t15_ht = ht; st->t15_outk = outk;
     st->t15_seg_l = seg_l; st->t15_seg_c = seg_c;
-    CUDA_OK(cudaFuncSetAttribute((const void *)pick_tile15(srck, ht, outk),
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->t15_smem));
+    CUDA_OK(set_max_smem((const void *)pick_tile15(srck, ht, outk), (size_t)((int)st->t15_smem)));
     st->t15_ok = 1;
     return 0;
 }

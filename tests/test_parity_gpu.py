@@ -541,3 +541,21 @@ def test_rgb16bpp_odd_widths(df):
                       ("yuv420p", (323, 182, 323, 182), S.SWS_BICUBIC), ("yuv444p", (161, 90, 387, 201), S.SWS_BILINEAR | BX),
                       ("bgra", (163, 91, 257, 131), S.SWS_LANCZOS | BX), ("yuv420p10le", (322, 182, 129, 71), S.SWS_FAST_BILINEAR)]:
         _check(sw=g[0], sh=g[1], sf=sf, dw=g[2], dh=g[3], df=df, flags=fl, seed=151)
+
+
+def test_two_live_contexts_with_different_tiles():
+    """The dynamic shared-memory limit is a property of the kernel function, not of a context: a second context
+    using the same kernel with a smaller tile must not lower the limit of the first one."""
+    big = dict(sw=4096, sh=64, sf="yuv420p10le", dw=181, dh=45, df="yuv420p16le", flags=S.SWS_BICUBIC | BX)
+    small = dict(sw=64, sh=48, sf="yuv420p10le", dw=32, dh=24, df="yuv420p16le", flags=S.SWS_BICUBIC | BX)
+    ctxs, srcs = [], []
+    for case in (big, small):
+        ctxs.append(S.SwsContext(case["sw"], case["sh"], case["sf"], case["dw"], case["dh"], case["df"], case["flags"]))
+        srcs.append(T.Frame(case["sf"], case["sw"], case["sh"]).randomize(3))
+    for case, c, src in zip((big, small), ctxs, srcs):
+        want, _ = T.run_reference(src=src, **case)
+        dst = T.Frame(case["df"], case["dw"], case["dh"], fill=0)
+        assert c.scale(src.planes, src.strides, dst.planes, dst.strides, 0, case["sh"]) == case["dh"], c.last_error
+        assert T.first_diff(dst.valid(), want.valid()) is None, c.kernel_name
+    for c in ctxs:
+        c.close()
