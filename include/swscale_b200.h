@@ -69,6 +69,8 @@ enum AVPixelFormat {
     AV_PIX_FMT_YUV444P12LE = 131,
     AV_PIX_FMT_YUV444P14LE = 133,
     AV_PIX_FMT_P010LE      = 158,
+    AV_PIX_FMT_GBRPF32LE   = 175,   /* output only */
+    AV_PIX_FMT_GRAYF32LE   = 183,   /* output only */
 };
 #endif
 

@@ -415,6 +415,10 @@ static int dst_kind_of(int fmt, const SwsPixDesc *d)
     case AV_PIX_FMT_NV21:    return SWSC_DST_NV21;
     case AV_PIX_FMT_P010LE:  return SWSC_DST_P010;
     }
+    if ((d->flags & SWSPF_PLANAR) && (d->flags & SWSPF_RGB))
+        return SWSC_DST_GBRP;
+    if (d->depth == 32)
+        return SWSC_DST_PLANARF32;
     if (d->flags & SWSPF_PLANAR)
         return d->depth == 8 ? SWSC_DST_PLANAR8 : d->depth == 16 ? SWSC_DST_PLANAR16 : SWSC_DST_PLANARN;
     return -1;
@@ -536,11 +540,16 @@ static int init_single(SwsContext *sws, int with_device)
         set_error(c, "%dx%d -> %dx%d is invalid scaling dimension", srcW, srcH, dstW, dstH);
         return AVERROR(EINVAL);
     }
-    if (sws->gamma_flag || (flags & SWS_SRC_V_CHR_DROP_MASK) ||
-        sws->dither == SWS_DITHER_ED || (flags & SWS_ERROR_DIFFUSION)) {
-        set_error(c, "gamma / chroma-drop / error-diffusion are outside the CUDA hot path");
+    if (sws->gamma_flag || (flags & SWS_SRC_V_CHR_DROP_MASK)) {
+        set_error(c, "gamma / chroma-drop are outside the CUDA hot path");
         return AVERROR(ENOTSUP);
     }
+    /* Error diffusion (utils.c:1288-1291).  The diffusing writers exist only for the 1- to 8-bit-per-pixel
+     * destinations (output.c:692-830,2085-2158: monoblack/white, rgb8, bgr8, rgb4_byte, bgr4_byte), none of which
+     * is on this path; for every other destination the setting changes path selection only (the unscaled
+     * yuv2rgb LUT converter steps aside, swscale_unscaled.c:2428), which init_single() reproduces below. */
+    if (sws->dither == SWS_DITHER_AUTO && (flags & SWS_ERROR_DIFFUSION))
+        sws->dither = SWS_DITHER_ED;
 
     unscaled = srcW == dstW && srcH == dstH;
     {
@@ -566,6 +575,10 @@ static int init_single(SwsContext *sws, int with_device)
         if (c->chr_src_hsub == 0 && c->chr_src_vsub == 0 && sws->dither != SWS_DITHER_BAYER &&
             !(flags & SWS_FAST_BILINEAR))                      /* utils.c:1278-1285 */
             flags |= SWS_FULL_CHR_H_INT;
+        sws->flags = flags;
+    }
+    if (dd->flags & SWSPF_PLANAR && is_rgb(sws->dst_format) && !(flags & SWS_FULL_CHR_H_INT)) {
+        flags |= SWS_FULL_CHR_H_INT;                   /* planar RGB has no half-chroma writer (utils.c:1317-1325) */
         sws->flags = flags;
     }
     if (is_rgb(sws->dst_format) && dd->bpp <= 16) {
@@ -603,7 +616,9 @@ static int init_single(SwsContext *sws, int with_device)
     c->unscaled_lut = 0;
     c->special = SWSC_SPECIAL_NONE;
     if (unscaled && (sws->src_range == sws->dst_range || is_rgb(sws->dst_format))) {
-        const int planar_yuv_pair = !is_rgb(sws->src_format) && !is_rgb(sws->dst_format);
+        /* the plane-copy wrappers need isFloat(src) == isFloat(dst) (swscale_unscaled.c:2656-2663): float destinations
+         * always go through the scaler */
+        const int planar_yuv_pair = !is_rgb(sws->src_format) && !is_rgb(sws->dst_format) && dd->depth <= 16;
         if (is_rgb(sws->src_format) && is_rgb(sws->dst_format) && sd->depth == 8 && dd->depth == 8) {
             /* rgbToRgbWrapper (findRgbConvFn, swscale_unscaled.c:1843-2060,2463-2466) and
              * packedCopyWrapper for identical formats (:2689-2707).  With SWS_BITEXACT the reference
@@ -633,7 +648,7 @@ static int init_single(SwsContext *sws, int with_device)
                 c->special = SWSC_SPECIAL_COPY8;
         }
         if ((sws->src_format == AV_PIX_FMT_YUV420P || sws->src_format == AV_PIX_FMT_YUV422P) &&
-            is_rgb(sws->dst_format) && !(flags & SWS_ACCURATE_RND) &&
+            is_rgb(sws->dst_format) && !(dd->flags & SWSPF_PLANAR) && !(flags & SWS_ACCURATE_RND) &&
             (sws->dither == SWS_DITHER_BAYER || sws->dither == SWS_DITHER_AUTO) && !(dstH & 1)) {
             c->unscaled_lut = 1;        /* yuv2rgb_c_* nearest-chroma LUT converter (a13) */
             c->dst_slice_align = 2;
@@ -742,8 +757,8 @@ static int init_single(SwsContext *sws, int with_device)
     p->src_shift = sd->shift;
     p->dst_shift = dd->shift;
     p->dst_bits = c->dst_bpc;
-    p->has_chroma = 1;
-    p->dst_has_chroma = 1;
+    p->has_chroma = !(sd->flags & SWSPF_GRAY) && !(dd->flags & SWSPF_GRAY);   /* a gray side: luma only */
+    p->dst_has_chroma = !(dd->flags & SWSPF_GRAY);
     p->unscaled_lut = c->unscaled_lut;
     p->special = c->special;
     p->full_chr = is_rgb(sws->dst_format) && (flags & SWS_FULL_CHR_H_INT) && !c->unscaled_lut;
@@ -809,7 +824,7 @@ static int init_single(SwsContext *sws, int with_device)
     /* One-tap vertical filters run through yuv2plane1 / yuv2packed1, which never look at the coefficient
      * (vscale.c:135-143,296-316).  It is 4096 except where initFilter's edge fix-up left 4095 behind (a few
      * source rows with a large chroma offset): make the device banks say what those writers compute. */
-    {
+    if (!((dd->flags & SWSPF_PLANAR) && is_rgb(sws->dst_format))) {     /* planar RGB always runs yuv2anyX with the real taps (vscale.c:173-215) */
         const int packed = is_rgb(sws->dst_format);
         if (c->v_lum.size == 1) {
             for (int y = 0; y < c->v_lum.len; y++) {

@@ -1129,7 +1129,47 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
     const int lfs = P.vl_size, cfs = P.vc_size;
 
     /* ---- stage V + pack ---- */
-    if (kind >= SWSC_DST_RGB24 && P.full_chr) {
+    if (kind == SWSC_DST_GBRP) {
+        /* planar RGB, 32-bit float: yuv2gbrpf32_full_X_c (output.c:2536-2610) -- always the X writer with the real
+         * taps, 32-bit wrap-around in Y + R, the 16-bit result times 1.0f / 65535.0f (one IEEE multiply: bit-exact) */
+        const float float_mult = 1.0f / 65535.0f;
+        for (int idx = threadIdx.x; idx < th * TW; idx += blockDim.x) {
+            const int ty = idx / TW, x = idx - ty * TW;
+            if (x >= tw)
+                continue;
+            const int y = ry0 + ty;
+            const int16_t *lf = P.vl_coef + (size_t)y * lfs;
+            const int16_t *cf = P.vc_coef + (size_t)y * cfs;
+            const int rl = max(P.vl_pos[y], 0) - lo_l;
+            const int rc = max(P.vc_pos[y], 0) - lo_c;
+            const inter_t *pl = hb_l + (size_t)rl * TW + x;
+            const inter_t *pu = hb_u + (size_t)rc * CW + x;
+            const inter_t *pv = hb_v + (size_t)rc * CW + x;
+            unsigned Yv = 0u - 0x40000000u, U = 0u - (128u << 23), V = 0u - (128u << 23);
+            for (int j = 0; j < lfs; j++)
+                Yv += (unsigned)(int)pl[(size_t)(min(rl + j, nl - 1) - rl) * TW] * (unsigned)(int)lf[j];
+            for (int j = 0; j < cfs; j++) {
+                const int r = min(rc + j, nc - 1) - rc;
+                const unsigned c = (unsigned)(int)cf[j];
+                U += (unsigned)(int)pu[(size_t)r * CW] * c;
+                V += (unsigned)(int)pv[(size_t)r * CW] * c;
+            }
+            int Yi = ((int)Yv >> 14) + 0x10000;
+            const int Ui = (int)U >> 14, Vi = (int)V >> 14;
+            Yi -= P.rgb.y_offset;
+            const unsigned Yu = (unsigned)Yi * (unsigned)P.rgb.y_coeff + (1u << 13) - (1u << 29);
+            const unsigned R = (unsigned)Vi * (unsigned)P.rgb.v2r;
+            const unsigned G = (unsigned)Vi * (unsigned)P.rgb.v2g + (unsigned)Ui * (unsigned)P.rgb.u2g;
+            const unsigned B = (unsigned)Ui * (unsigned)P.rgb.u2b;
+            const int r = clip_uintp2(((int)(Yu + R) >> 14) + (1 << 15), 16);
+            const int g = clip_uintp2(((int)(Yu + G) >> 14) + (1 << 15), 16);
+            const int b = clip_uintp2(((int)(Yu + B) >> 14) + (1 << 15), 16);
+            const int gx = x0 + x;
+            reinterpret_cast<float *>(dst0 + (size_t)y * A.dst_stride[0])[gx] = __fmul_rn(float_mult, (float)g);
+            reinterpret_cast<float *>(dst1 + (size_t)y * A.dst_stride[1])[gx] = __fmul_rn(float_mult, (float)b);
+            reinterpret_cast<float *>(dst2 + (size_t)y * A.dst_stride[2])[gx] = __fmul_rn(float_mult, (float)r);
+        }
+    } else if (kind >= SWSC_DST_RGB24 && kind <= SWSC_DST_BGRA64 && P.full_chr) {
         /* packed RGB with full horizontal chroma (odd width / 4:4:4 source): every pixel has its own
          * U,V and the colour step is arithmetic, not LUT based: yuv2rgb_full_{X,1,2}_c_template +
          * yuv2rgb_write_full (output.c:1998-2051,2160-2330), yuv2rgba64_full_X_c_template (:1373-1430) */
@@ -1205,7 +1245,7 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
                 w[0] = kind == SWSC_DST_RGB48 ? r : b; w[1] = g; w[2] = kind == SWSC_DST_RGB48 ? b : r;
             }
         }
-    } else if (kind >= SWSC_DST_RGB24) {
+    } else if (kind >= SWSC_DST_RGB24 && kind <= SWSC_DST_BGRA64) {
         /* packed RGB: one chroma pair per two pixels (output.c:1788-1840 / 1115-1196) */
         /* pairs in this tile; widths are even here except for 15/16 bpp destinations (no full-chroma writer), whose
          * last pair keeps only its first pixel, and the unscaled LUT converters, which leave the odd pixel alone */
@@ -1364,12 +1404,16 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
             } else if (kind == SWSC_DST_P010) {     /* yuv2p010l1_c / yuv2p010lX_c (output.c:538-566): 10 bits << 6 */
                 const int shift = 27 - 10;
                 reinterpret_cast<uint16_t *>(d)[gx] = clip_uintp2((int)(acc + (1u << (shift - 1))) >> shift, 10) << 6;
+            } else if (kind == SWSC_DST_PLANARF32) {
+                /* yuv2plane1_float / yuv2planeX_float (output.c:219-263): the 16-bit planar result times 1/65535 */
+                const int v = (int)(acc + (1u << 14) - 0x40000000u) >> 15;
+                reinterpret_cast<float *>(d)[gx] = __fmul_rn(1.0f / 65535.0f, (float)(0x8000 + clip_i16(v)));
             } else {
                 const int v = (int)(acc + (1u << 14) - 0x40000000u) >> 15;
                 reinterpret_cast<uint16_t *>(d)[gx] = 0x8000 + clip_i16(v);
             }
         }
-        if (P.has_chroma && ch > 0) {
+        if (P.has_chroma && P.dst_has_chroma && ch > 0) {
             for (int idx = threadIdx.x; idx < ch * CW; idx += blockDim.x) {
                 const int ty = idx / CW, x = idx - ty * CW;
                 if (x >= cw)

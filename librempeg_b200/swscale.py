@@ -23,6 +23,7 @@ PIX_FMT = {
     "yuv420p9le": 60, "yuv420p10le": 62, "yuv422p10le": 64, "yuv444p9le": 66,
     "yuv444p10le": 68, "yuv422p9le": 70, "yuv420p12le": 123, "yuv420p14le": 125,
     "yuv422p12le": 127, "yuv422p14le": 129, "yuv444p12le": 131, "yuv444p14le": 133, "p010le": 158,
+    "gbrpf32le": 175, "grayf32le": 183,
 }
 
 # SwsFlags (reference libswscale/swscale.h:131-208)

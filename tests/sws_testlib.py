@@ -41,6 +41,10 @@ def plane_layout(fmt, w, h):
         return [(h, w)]
     if fmt == "gbrp":
         return [(h, w)] * 3
+    if fmt == "grayf32le":
+        return [(h, w * 4)]
+    if fmt == "gbrpf32le":
+        return [(h, w * 4)] * 3
     for key, (cw, ch) in _YUV.items():
         for pre in ("yuv", "yuvj"):
             if fmt.startswith(pre + key + "p"):
