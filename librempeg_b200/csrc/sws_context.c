@@ -681,10 +681,9 @@ static int init_single(SwsContext *sws, int with_device)
                 c->dst_slice_align = 8 << c->chr_dst_vsub;      /* :2694-2696: the dither rows count from the slice */
         }
     }
-    if (!c->special && is_rgb(sws->src_format) && sd->bpp == 32 && is_rgb(sws->dst_format) && dd->bpp == 32) {
-        set_error(c, "carrying an alpha plane through the scaler is not on the CUDA hot path");
-        return AVERROR(ENOTSUP);
-    }
+    /* an alpha channel on both sides travels through the scaler as a fourth line set (needAlpha, utils.c:1427) */
+    const int need_alpha = !c->special && is_rgb(sws->src_format) && sd->bpp == 32 && is_rgb(sws->dst_format) &&
+                           dd->bpp == 32 && !(dd->flags & SWSPF_PLANAR);
     /* ---- FIR banks: horizontal 1<<14, vertical 1<<12 (utils.c:1681-1729) ---- */
     memset(&spec, 0, sizeof(spec));
     spec.flags = flags;
@@ -791,6 +790,10 @@ static int init_single(SwsContext *sws, int with_device)
             return AVERROR(ENOTSUP);
         }
         p->src_rgb_half = c->chr_src_hsub;
+        if (need_alpha) {
+            p->src_alpha = p->dst_alpha = 1;
+            p->src_ao = 6 - p->src_ro - p->src_go - p->src_bo;
+        }
         if (c->special == SWSC_SPECIAL_SHUFFLE) {
             /* destination byte k <- source byte of the same component; a missing alpha becomes 255 */
             int so[4] = { -1, -1, -1, -1 }, dorder[4] = { 4, 4, 4, 4 };   /* component (r,g,b,a) -> byte */

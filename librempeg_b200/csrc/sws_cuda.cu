@@ -1003,6 +1003,7 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
     inter_t *hb_l = reinterpret_cast<inter_t *>(smem_raw);
     inter_t *hb_u = hb_l + (size_t)A.rows_l_cap * TW;
     inter_t *hb_v = hb_u + (size_t)A.rows_c_cap * CW;
+    inter_t *hb_a = hb_v + (size_t)A.rows_c_cap * CW;      /* alpha lines (P.src_alpha), laid out like luma */
 
     /* source row windows (positions are monotonic; take min/max defensively) */
     int lo_l = INT_MAX, hi_l = 0, lo_c = INT_MAX, hi_c = 0;
@@ -1057,6 +1058,27 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
                 }
             }
             hb_l[idx] = (inter_t)val;
+        }
+    }
+    /* ---- stage H, alpha: rgbaToA_c / abgrToA_c (input.c:455-471) through the luma bank; no range conversion ---- */
+    if (P.src_alpha) {
+        const int fs = P.hl_size;
+        const int ao = P.src_ao;
+        for (int idx = threadIdx.x; idx < nl * TW; idx += blockDim.x) {
+            const int r = idx / TW, x = idx - r * TW;
+            if (x >= tw)
+                continue;
+            const int sy = min(lo_l + r, P.src_h - 1);
+            const uint8_t *row = src0 + (size_t)sy * A.src_stride[0] + ao;
+            const int gx = x0 + x;
+            const int pos = P.hl_pos[gx];
+            const int16_t *co = P.hl_coef + (size_t)gx * fs;
+            int val = 0;
+            for (int j = 0; j < fs; j++) {
+                const int a8 = row[4 * min(pos + j, P.src_w - 1)];
+                val += ((a8 << 6) | (a8 >> 2)) * (int)co[j];
+            }
+            hb_a[idx] = (inter_t)min(val >> sh, h_max);
         }
     }
     /* ---- stage H, chroma (input unpack of nv12/nv21 fused into the fetch) ---- */
@@ -1216,13 +1238,31 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
                 int G = (int)(Yu + (unsigned)Vi * (unsigned)P.rgb.v2g + (unsigned)Ui * (unsigned)P.rgb.u2g);
                 int B = (int)(Yu + (unsigned)Ui * (unsigned)P.rgb.u2b);
                 R = clip_uintp2(R, 30) >> 22; G = clip_uintp2(G, 30) >> 22; B = clip_uintp2(B, 30) >> 22;
+                int Av = 255;
+                if (P.src_alpha) {
+                    /* yuv2rgb_full_{X,2,1}_c_template (output.c:2193-2201,2241-2245,2278-2282): the same three
+                     * writers vscale.c:135-169 picks for Y, U, V */
+                    const inter_t *pa = hb_a + (size_t)rl * TW + x;
+                    const bool chr2 = cfs == 2 && cf[0] + cf[1] == 4096 && (unsigned)(int)cf[1] <= 4096u;
+                    if (lfs == 1 && (cfs == 1 || chr2)) {
+                        Av = ((int)pa[0] + 64) >> 7;
+                    } else {
+                        unsigned acc = 1u << 18;       /* _2 and _X both round */
+                        for (int j = 0; j < lfs; j++)
+                            acc += (unsigned)(int)pa[(size_t)(min(rl + j, nl - 1) - rl) * TW] * (unsigned)(int)lf[j];
+                        Av = (int)acc >> 19;
+                    }
+                    if (Av & 0x100)
+                        Av = clip_u8(Av);
+                    Av &= 0xFF;
+                }
                 switch (kind) {
                 case SWSC_DST_RGB24: d += 3 * gx; d[0] = R; d[1] = G; d[2] = B; break;
                 case SWSC_DST_BGR24: d += 3 * gx; d[0] = B; d[1] = G; d[2] = R; break;
-                case SWSC_DST_RGBA: d += 4 * gx; d[0] = R; d[1] = G; d[2] = B; d[3] = 255; break;
-                case SWSC_DST_BGRA: d += 4 * gx; d[0] = B; d[1] = G; d[2] = R; d[3] = 255; break;
-                case SWSC_DST_ARGB: d += 4 * gx; d[0] = 255; d[1] = R; d[2] = G; d[3] = B; break;
-                case SWSC_DST_ABGR: d += 4 * gx; d[0] = 255; d[1] = B; d[2] = G; d[3] = R; break;
+                case SWSC_DST_RGBA: d += 4 * gx; d[0] = R; d[1] = G; d[2] = B; d[3] = Av; break;
+                case SWSC_DST_BGRA: d += 4 * gx; d[0] = B; d[1] = G; d[2] = R; d[3] = Av; break;
+                case SWSC_DST_ARGB: d += 4 * gx; d[0] = Av; d[1] = R; d[2] = G; d[3] = B; break;
+                case SWSC_DST_ABGR: d += 4 * gx; d[0] = Av; d[1] = B; d[2] = G; d[3] = R; break;
                 }
             } else {
                 int Yi = ((int)(Yv - 0x40000000u) >> 14) + 0x10000;
@@ -1329,6 +1369,35 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
                 const int r2 = clip_u8((yb + (y2v + oR) * cy) >> 16);
                 const int g2 = clip_u8((yb + (y2v + oG) * cy) >> 16);
                 const int b2 = clip_u8((yb + (y2v + oB) * cy) >> 16);
+                int a1 = 255, a2 = 255;
+                if (P.src_alpha) {
+                    /* alpha of yuv2rgb_{1,2,X}_c_template (output.c:1818-1829,1870-1875,1903-1932), chosen per row
+                     * like the colour channels (vscale.c:135-169) */
+                    const inter_t *pa = hb_a + (size_t)rl * TW + 2 * i;
+                    const bool chr2 = cfs == 2 && cf[0] + cf[1] == 4096 && (unsigned)(int)cf[1] <= 4096u;
+                    const bool lum2 = lfs == 2 && lf[0] + lf[1] == 4096 && (unsigned)(int)lf[1] <= 4096u;
+                    if (lfs == 1 && cfs == 1) {                 /* yuv2packed1, uvalpha == 0 */
+                        a1 = clip_u8(((int)pa[0] * 255 + 16384) >> 15);
+                        a2 = clip_u8(((int)pa[1] * 255 + 16384) >> 15);
+                    } else if (lfs == 1 && chr2) {              /* yuv2packed1, uvalpha != 0 */
+                        a1 = clip_u8(((int)pa[0] + 64) >> 7);
+                        a2 = clip_u8(((int)pa[1] + 64) >> 7);
+                    } else {
+                        const bool two = lum2 && chr2;          /* yuv2packed2: no rounding bias */
+                        unsigned s1 = two ? 0u : 1u << 18, s2 = s1;
+                        for (int j = 0; j < lfs; j++) {
+                            const int r = min(rl + j, nl - 1) - rl;
+                            const unsigned c = (unsigned)(int)lf[j];
+                            s1 += (unsigned)(int)pa[(size_t)r * TW] * c;
+                            s2 += (unsigned)(int)pa[(size_t)r * TW + 1] * c;
+                        }
+                        a1 = (int)s1 >> 19; a2 = (int)s2 >> 19;
+                        if (two || ((a1 | a2) & 0x100)) {
+                            a1 = clip_u8(a1); a2 = clip_u8(a2);
+                        }
+                        a1 &= 0xFF; a2 &= 0xFF;
+                    }
+                }
                 uint8_t *d = dst0 + (size_t)y * A.dst_stride[0];
                 const int gx = (x0 >> 1) + i;          /* pair index in the row */
                 switch (kind) {
@@ -1337,13 +1406,13 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
                 case SWSC_DST_BGR24: d += 6 * gx;
                     d[0] = b1; d[1] = g1; d[2] = r1; d[3] = b2; d[4] = g2; d[5] = r2; break;
                 case SWSC_DST_RGBA: d += 8 * gx;
-                    d[0] = r1; d[1] = g1; d[2] = b1; d[3] = 255; d[4] = r2; d[5] = g2; d[6] = b2; d[7] = 255; break;
+                    d[0] = r1; d[1] = g1; d[2] = b1; d[3] = a1; d[4] = r2; d[5] = g2; d[6] = b2; d[7] = a2; break;
                 case SWSC_DST_BGRA: d += 8 * gx;
-                    d[0] = b1; d[1] = g1; d[2] = r1; d[3] = 255; d[4] = b2; d[5] = g2; d[6] = r2; d[7] = 255; break;
+                    d[0] = b1; d[1] = g1; d[2] = r1; d[3] = a1; d[4] = b2; d[5] = g2; d[6] = r2; d[7] = a2; break;
                 case SWSC_DST_ARGB: d += 8 * gx;
-                    d[0] = 255; d[1] = r1; d[2] = g1; d[3] = b1; d[4] = 255; d[5] = r2; d[6] = g2; d[7] = b2; break;
+                    d[0] = a1; d[1] = r1; d[2] = g1; d[3] = b1; d[4] = a2; d[5] = r2; d[6] = g2; d[7] = b2; break;
                 case SWSC_DST_ABGR: d += 8 * gx;
-                    d[0] = 255; d[1] = b1; d[2] = g1; d[3] = r1; d[4] = 255; d[5] = b2; d[6] = g2; d[7] = r2; break;
+                    d[0] = a1; d[1] = b1; d[2] = g1; d[3] = r1; d[4] = a2; d[5] = b2; d[6] = g2; d[7] = r2; break;
                 case SWSC_DST_RGB48: { uint16_t *w = reinterpret_cast<uint16_t *>(d) + 6 * gx;
                     w[0] = r1 * 257; w[1] = g1 * 257; w[2] = b1 * 257; w[3] = r2 * 257; w[4] = g2 * 257; w[5] = b2 * 257; break; }
                 case SWSC_DST_BGR48: { uint16_t *w = reinterpret_cast<uint16_t *>(d) + 6 * gx;
@@ -1637,7 +1706,7 @@ static int plan_tiles(SwsCudaState *st)
             int rl = max_rows_needed(st->h_vl_pos, p->vl_size, p->dst_h, th);
             int cth = th >> vs ? th >> vs : 1;
             int rc = max_rows_needed(st->h_vc_pos, p->vc_size, p->chr_dst_h, cth);
-            size_t need = ((size_t)rl * tw + 2 * (size_t)rc * (tw >> hs)) * isz;
+            size_t need = ((size_t)rl * tw * (p->src_alpha ? 2 : 1) + 2 * (size_t)rc * (tw >> hs)) * isz;
             if (need <= budget || th == (1 << vs)) {
                 if (need > 200 * 1024)
                     break;
@@ -2795,7 +2864,8 @@ static int tile15_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
 {
     const SwsCudaPlan *p = &st->plan;
     st->t15_ok = 0;
-    if (p->inter_bits != 15 || p->full_chr || p->special || !p->has_chroma || (p->unscaled_lut && (p->dst_w & 1)))
+    if (p->inter_bits != 15 || p->full_chr || p->special || !p->has_chroma || (p->unscaled_lut && (p->dst_w & 1)) ||
+        p->src_alpha)
         return 0;
     int outk;
     if (p->dst_kind == SWSC_DST_PLANAR8 || p->dst_kind == SWSC_DST_NV12 || p->dst_kind == SWSC_DST_NV21)

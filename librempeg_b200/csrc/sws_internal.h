@@ -143,6 +143,7 @@ typedef struct SwsCudaPlan {
     int has_chroma;              /* 0 for gray sources                        */
     int dst_has_chroma;          /* 0 for gray destinations                   */
     int src_alpha, dst_alpha;    /* an alpha plane / channel is read / written through the scaler */
+    int src_ao;                  /* packed RGB32 sources: byte offset of A inside a pixel */
     int unscaled_lut;            /* 1: reference would take convert_unscaled  */
     int special;                 /* whole-frame special converter, SWSC_SPECIAL_* */
     int shuf_map[4];             /* SHUFFLE: source byte of every destination byte, 4 = constant 255 */

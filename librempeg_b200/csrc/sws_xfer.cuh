@@ -254,7 +254,7 @@ static int ensure_staging(SwsCudaState *st)
         st->src_rows[1] = p->chr_src_h;
         st->src_rowbytes[1] = p->chr_src_w * 2 * sb;
     }
-    if (p->src_alpha) {
+    if (p->src_alpha && p->src_layout != SWSC_SRC_RGB) {      /* a separate alpha plane (packed RGB carries it in plane 0) */
         st->src_rows[3] = p->src_h;
         st->src_rowbytes[3] = p->src_w * sb;
     }
