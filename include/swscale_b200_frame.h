@@ -86,6 +86,12 @@ typedef struct AVHWDeviceContext {
     int type;                        /* enum AVHWDeviceType */
     void *hwctx;
 } AVHWDeviceContext;
+/* what AVHWDeviceContext.hwctx points at for AV_HWDEVICE_TYPE_CUDA (reference libavutil/hwcontext_cuda.h:42-46) */
+typedef struct AVCUDADeviceContext {
+    void *cuda_ctx;                  /* CUcontext */
+    void *stream;                    /* CUstream the producer / consumer of the frames works on */
+    void *internal;
+} AVCUDADeviceContext;
 typedef struct AVHWFramesContext {
     const void *av_class;
     AVBufferRef *device_ref;         /* -> AVHWDeviceContext */

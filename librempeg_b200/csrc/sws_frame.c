@@ -12,6 +12,7 @@
  */
 #include <dlfcn.h>
 #include <errno.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -119,6 +120,7 @@ typedef struct DynKey {
     unsigned flags;
     int dither, scaler, scaler_sub;
     int chr_pos[4];
+    int device;             /* CUDA device of hardware frames, -1: the caller's current device */
     double param[2];
 } DynKey;
 
@@ -127,7 +129,7 @@ int sws_frame_setup(SwsContext *ctx, const AVFrame *dst, const AVFrame *src)
     SwsInternal *c = sws_internal(ctx);
     DynKey key;
     SwsContext *in;
-    int ret, sx, sy, dx, dy;
+    int ret, sx, sy, dx, dy, hw_device = -1, prev_device;
 
     if (!c || !src || !dst)
         return AVERROR(EINVAL);
@@ -146,6 +148,21 @@ int sws_frame_setup(SwsContext *ctx, const AVFrame *dst, const AVFrame *src)
         if (((const AVHWDeviceContext *)sf->device_ref->data)->type != AV_HWDEVICE_TYPE_CUDA ||
             src->format != AV_PIX_FMT_CUDA || dst->format != AV_PIX_FMT_CUDA)
             return AVERROR(ENOTSUP);            /* only CUDA devices are supported */
+        {
+            /* libavutil creates its own CUcontext unless told to use the primary one (hwcontext_cuda.c:740,
+             * AV_CUDA_USE_PRIMARY_CONTEXT): the kernels run in the primary context of the frames' device */
+            const AVCUDADeviceContext *cu = ((const AVHWDeviceContext *)sf->device_ref->data)->hwctx;
+            hw_device = -1;
+            if (cu && cu->cuda_ctx) {
+                hw_device = ff_b200_cuda_hwctx_device(cu->cuda_ctx);
+                if (hw_device < 0) {
+                    snprintf(c->last_error, sizeof(c->last_error),
+                             "AV_PIX_FMT_CUDA frames must live in the primary context of their device "
+                             "(create the device with AV_CUDA_USE_PRIMARY_CONTEXT)");
+                    return hw_device == AVERROR(ENOTSUP) ? AVERROR(ENOTSUP) : AVERROR(EINVAL);
+                }
+            }
+        }
     } else if (src->format == AV_PIX_FMT_CUDA || dst->format == AV_PIX_FMT_CUDA) {
         return AVERROR(EINVAL);
     }
@@ -164,6 +181,7 @@ int sws_frame_setup(SwsContext *ctx, const AVFrame *dst, const AVFrame *src)
         return AVERROR(ENOTSUP);
     if (src->color_trc != dst->color_trc && src->color_trc > 2 && dst->color_trc > 2)
         return AVERROR(ENOTSUP);
+    key.device = hw_device;
     key.flags = ctx->flags; key.dither = ctx->dither; key.scaler = ctx->scaler; key.scaler_sub = ctx->scaler_sub;
     key.param[0] = ctx->scaler_params[0]; key.param[1] = ctx->scaler_params[1];
     chroma_pos(&key.src, &sx, &sy);
@@ -194,7 +212,12 @@ int sws_frame_setup(SwsContext *ctx, const AVFrame *dst, const AVFrame *src)
     in->src_h_chr_pos = key.chr_pos[0]; in->src_v_chr_pos = key.chr_pos[1];
     in->dst_h_chr_pos = key.chr_pos[2]; in->dst_v_chr_pos = key.chr_pos[3];
     in->scaler_params[0] = key.param[0]; in->scaler_params[1] = key.param[1];
+    prev_device = ff_b200_cuda_current_device();
+    if (hw_device >= 0)
+        ff_b200_cuda_use_device(hw_device);       /* the inner context binds to the device of the frames */
     ret = sws_init_context(in, NULL, NULL);
+    if (hw_device >= 0)
+        ff_b200_cuda_use_device(prev_device);
     if (ret < 0) {
         memcpy(c->last_error, sws_internal(in)->last_error, sizeof(c->last_error));
         sws_free_context(&in);
@@ -265,7 +288,13 @@ int sws_scale_frame(SwsContext *ctx, AVFrame *dst, const AVFrame *src)
             return ret;
     }
     if (src->format == AV_PIX_FMT_CUDA) {
-        /* device-resident planes: one launch on the context stream, complete on return */
+        /* device-resident planes: one launch on the context stream, complete on return.  Work the producer of the
+         * source frame queued on the device context's stream (NVDEC, hwupload, a previous filter) comes first. */
+        const AVHWFramesContext *sf = frames_ctx(src);
+        const AVCUDADeviceContext *cu = sf && sf->device_ref ? ((const AVHWDeviceContext *)sf->device_ref->data)->hwctx : NULL;
+        SwsInternal *in = sws_internal(c->dyn);
+        if (cu && cu->cuda_ctx && in->cuda && (ret = ff_b200_cuda_wait_stream(in->cuda, cu->stream)) < 0)
+            return ret;
         ret = sws_cuda_scale_batch(c->dyn, (const uint8_t *const *)src->data, src->linesize, NULL,
                                    dst->data, dst->linesize, NULL, 1);
         if (ret >= 0)

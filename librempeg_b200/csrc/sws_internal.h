@@ -197,6 +197,10 @@ int  ff_b200_cuda_scale_host(SwsCudaState *st,
                              const uint8_t *const src[4], const int src_stride[4],
                              int src_y, int src_h, int upload,
                              uint8_t *const dst[4], const int dst_stride[4], int y0, int y1, int mem);
+int  ff_b200_cuda_hwctx_device(void *cuda_ctx);
+int  ff_b200_cuda_current_device(void);
+void ff_b200_cuda_use_device(int dev);
+int  ff_b200_cuda_wait_stream(SwsCudaState *st, void *producer_stream);
 void *ff_b200_cuda_alloc(size_t bytes);
 void ff_b200_cuda_free(void *p);
 /* page-locked host frames first, first+step, ... through a ring of staging sets; enqueue only, then wait */

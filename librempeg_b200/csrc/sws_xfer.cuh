@@ -738,6 +738,75 @@ extern "C" int ff_b200_cuda_frame_is_pinned(SwsCudaState *st, const uint8_t *con
     return planes_pinned(planes, dst_side ? st->dst_rows : st->src_rows, nullptr) ? 1 : 0;
 }
 
+/* ---- AV_PIX_FMT_CUDA frames of a real libavutil CUDA device (hwcontext_cuda.h: AVCUDADeviceContext) ----
+ * The kernels run through the CUDA runtime, i.e. in the PRIMARY context of a device.  A frame pool created by
+ * libavutil may live in any CUcontext: find out which device it belongs to and whether it is that device's
+ * primary context (then its allocations are ours to address); anything else is refused, not guessed. */
+typedef CUresult (*ctx_push_fn)(CUcontext);
+typedef CUresult (*ctx_pop_fn)(CUcontext *);
+typedef CUresult (*ctx_getdev_fn)(CUdevice *);
+typedef CUresult (*pctx_retain_fn)(CUcontext *, CUdevice);
+typedef CUresult (*pctx_release_fn)(CUdevice);
+
+static void *driver_entry(const char *name)
+{
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    return p;
+}
+
+/* >= 0: device ordinal whose primary context `cuda_ctx` is; AVERROR(ENOTSUP): some other context */
+extern "C" int ff_b200_cuda_hwctx_device(void *cuda_ctx)
+{
+    static ctx_push_fn push = (ctx_push_fn)driver_entry("cuCtxPushCurrent");
+    static ctx_pop_fn pop = (ctx_pop_fn)driver_entry("cuCtxPopCurrent");
+    static ctx_getdev_fn getdev = (ctx_getdev_fn)driver_entry("cuCtxGetDevice");
+    static pctx_retain_fn retain = (pctx_retain_fn)driver_entry("cuDevicePrimaryCtxRetain");
+    static pctx_release_fn release = (pctx_release_fn)driver_entry("cuDevicePrimaryCtxRelease");
+    if (!cuda_ctx || !push || !pop || !getdev || !retain || !release)
+        return AVERROR(ENOSYS);
+    CUdevice dev = -1;
+    CUcontext dummy = nullptr, primary = nullptr;
+    if (push((CUcontext)cuda_ctx) != CUDA_SUCCESS)
+        return AVERROR(EINVAL);
+    const CUresult r = getdev(&dev);
+    pop(&dummy);
+    if (r != CUDA_SUCCESS)
+        return AVERROR(EINVAL);
+    if (retain(&primary, dev) != CUDA_SUCCESS)
+        return AVERROR(EIO);
+    release(dev);
+    return primary == (CUcontext)cuda_ctx ? (int)dev : AVERROR(ENOTSUP);
+}
+
+extern "C" int ff_b200_cuda_current_device(void)
+{
+    int d = -1;
+    return cudaGetDevice(&d) == cudaSuccess ? d : -1;
+}
+
+extern "C" void ff_b200_cuda_use_device(int dev)
+{
+    if (dev >= 0)
+        cudaSetDevice(dev);
+}
+
+/* order the context stream after everything queued so far on the producer's stream (AVCUDADeviceContext.stream) */
+extern "C" int ff_b200_cuda_wait_stream(SwsCudaState *st, void *producer_stream)
+{
+    DeviceGuard guard(st->device);
+    cudaEvent_t ev;
+    CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ev, (cudaStream_t)producer_stream);
+    if (e == cudaSuccess)
+        e = cudaStreamWaitEvent(st->stream, ev, 0);
+    cudaEventDestroy(ev);
+    CUDA_OK(e);
+    return 0;
+}
+
 extern "C" void *ff_b200_cuda_alloc(size_t bytes)
 {
     void *p = nullptr;

@@ -339,3 +339,71 @@ def test_scale_frame_allocates_destination(mode, case, tmp_path):
     got = np.frombuffer(dp.read_bytes(), np.uint8)
     exp = np.concatenate([p.reshape(-1) for p in want.valid()])
     assert got.size == exp.size and np.array_equal(got, exp)
+
+
+class AVCUDADeviceContext(C.Structure):
+    _fields_ = [("cuda_ctx", C.c_void_p), ("stream", C.c_void_p), ("internal", C.c_void_p)]
+
+
+@pytest.mark.gpu
+def test_cuda_frames_of_a_real_device_context():
+    """frames of a libavutil CUDA device carry a CUcontext and a stream (hwcontext_cuda.h).  The primary
+    context of the device is accepted and the producer's stream is honoured (a fill queued on it just before the
+    call must be seen); a context made by cuCtxCreate() -- libavutil's default -- is refused, not guessed."""
+    torch = pytest.importorskip("torch")
+    cu = C.CDLL("libcuda.so.1")
+    dev = torch.device("cuda", 0)
+    torch.zeros(1, device=dev)                    # runtime initialised: the primary context exists
+    primary = C.c_void_p()
+    assert cu.cuDevicePrimaryCtxRetain(C.byref(primary), 0) == 0
+    other = C.c_void_p()
+    create = getattr(cu, "cuCtxCreate_v2")
+    assert create(C.byref(other), 0, 0) == 0      # pushes it: pop again
+    popped = C.c_void_p()
+    assert cu.cuCtxPopCurrent_v2(C.byref(popped)) == 0
+    L = _bind()
+    sw, sh = 640, 360
+    src = T.Frame("nv12", sw, sh).randomize(5)
+    want = T.Frame("rgb24", sw, sh, fill=0)
+    props, dprops = (1, 1, 1), (0, 1, 0)
+    try:
+        # reference result through the host path
+        fs, fd = make_avframe(src, "nv12", props), make_avframe(want, "rgb24", dprops)
+        ctx = L.sws_alloc_context()
+        ctx.contents.flags = S.SWS_BICUBIC | S.BX
+        assert L.sws_scale_frame(ctx, C.byref(fd), C.byref(fs)) >= 0
+        S.lib().sws_freeContext(ctx)
+
+        producer = torch.cuda.Stream(device=dev)
+        for cuctx, expect_ok in ((primary, True), (other, False)):
+            hwdev = AVCUDADeviceContext(cuctx.value, producer.cuda_stream, None)
+            device = AVHWDeviceContext(None, 2, C.addressof(hwdev))
+            cs, cd = CudaFramesCtx("nv12", sw, sh, device=device), CudaFramesCtx("rgb24", sw, sh, device=device)
+            cd.fc.device_ref = cs.fc.device_ref
+            d_src = [torch.zeros(p.shape, dtype=torch.uint8, device=dev) for p in src.planes]
+            d_dst = [torch.zeros(p.shape, dtype=torch.uint8, device=dev) for p in want.planes]
+            h_src = [torch.from_numpy(np.ascontiguousarray(p)).pin_memory() for p in src.planes]
+            torch.cuda.synchronize()
+            with torch.cuda.stream(producer):     # the "decoder": a long spin, then the upload, all async
+                torch.cuda._sleep(200_000_000)
+                for d, h in zip(d_src, h_src):
+                    d.copy_(h, non_blocking=True)
+            hs, hd = make_avframe(src, "nv12", props), make_avframe(want, "rgb24", dprops)
+            for f, planes, fc in ((hs, d_src, cs), (hd, d_dst, cd)):
+                for i in range(8):
+                    f.data[i] = planes[i].data_ptr() if i < len(planes) else None
+                f.format, f.hw_frames_ctx = AV_PIX_FMT_CUDA, C.addressof(fc.ref)
+            ctx2 = L.sws_alloc_context()
+            ctx2.contents.flags = S.SWS_BICUBIC | S.BX
+            ret = L.sws_scale_frame(ctx2, C.byref(hd), C.byref(hs))
+            S.lib().sws_freeContext(ctx2)
+            torch.cuda.synchronize()
+            if expect_ok:
+                assert ret >= 0
+                for got, w, (rows, rb) in zip(d_dst, want.planes, want.layout):
+                    assert np.array_equal(got.cpu().numpy()[:rows, :rb], w[:rows, :rb])
+            else:
+                assert ret == -95                 # ENOTSUP
+    finally:
+        cu.cuCtxDestroy_v2(other)
+        cu.cuDevicePrimaryCtxRelease_v2(0)
