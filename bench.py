@@ -339,6 +339,36 @@ def run_b200_arm(args, rank, local_rank, world):
     for b in pin_bufs:
         b.close()
 
+    # ---- what the box allows: page-locked frames copied in and out at the same time on every rank at once, no kernel.
+    # The host-frame numbers above cannot exceed  min(H2D / bytes in, D2H / bytes out)  frames per second. ----
+    def host_ceiling(seconds=0.6):
+        hin = torch.empty(ysz + 2 * csz, dtype=torch.uint8).pin_memory()
+        hout = torch.empty(osz, dtype=torch.uint8).pin_memory()
+        din = torch.empty(ysz + 2 * csz, dtype=torch.uint8, device=dev)
+        dout = torch.empty(osz, dtype=torch.uint8, device=dev)
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        barrier()
+        t0 = time.perf_counter()
+        n = 0
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(8):
+                with torch.cuda.stream(s_in):
+                    din.copy_(hin, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    hout.copy_(dout, non_blocking=True)
+            s_in.synchronize()
+            s_out.synchronize()
+            n += 8
+        dt = time.perf_counter() - t0
+        t = torch.tensor([n * hin.numel() / dt / 1e9, n * hout.numel() / dt / 1e9, n * W * H / dt / 1e6],
+                         dtype=torch.float64, device=dev)
+        if dist:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return {"value": float(t[2].item()), "unit": "Mpixels/s", "h2d_gbs": float(t[0].item()), "d2h_gbs": float(t[1].item()),
+                "how": "%d rank(s) at once: page-locked 4K frames copied in (12.4 MB) and out (24.9 MB) concurrently for "
+                       "%.1f s, no kernel; sum over ranks" % (world, seconds)}
+    ceiling = host_ceiling()
+
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -408,6 +438,7 @@ def run_b200_arm(args, rank, local_rank, world):
                          "call": "sws_scale() per frame, pageable numpy buffers (bounce ring + copy threads)"},
         "e2e_batch_host": {"value": e2e_batch, "unit": "Mpixels/s", "frames_per_step": EF,
                            "call": "sws_cuda_scale_batch_host(), page-locked buffers, 3 frames in flight"},
+        "e2e_ceiling": ceiling,
         "numa": numa,
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
