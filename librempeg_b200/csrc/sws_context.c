@@ -1060,6 +1060,10 @@ static int scale_slice(SwsContext *sws, const uint8_t *const srcSlice[], const i
         set_error(c, "16-bit samples need even strides");
         return AVERROR(EINVAL);
     }
+    if (c->dst_bpc == 32 && ((dstStride[0] | dstStride[1] | dstStride[2]) & 3)) {
+        set_error(c, "32-bit float samples need strides that are multiples of 4");
+        return AVERROR(EINVAL);
+    }
     macro_src = 1 << c->chr_src_vsub;
     if ((srcSliceY & (macro_src - 1)) ||
         ((srcSliceH & (macro_src - 1)) && srcSliceY + srcSliceH != sws->src_h) ||
@@ -1105,6 +1109,9 @@ static int scale_slice(SwsContext *sws, const uint8_t *const srcSlice[], const i
         if (dst2[2]) dst2[2] += (ptrdiff_t)((sws->dst_h >> c->chr_dst_vsub) - 1) * dstStride[2];
         if (dst2[3]) dst2[3] += (ptrdiff_t)(sws->dst_h - 1) * dstStride[3];
         srcSliceY = sws->src_h - srcSliceY - srcSliceH;
+        /* with an odd dst_h the reference stores the last chroma row one row BEFORE the plane (a heap underflow the
+         * fuzz ran into): that row is dropped here instead */
+        mem |= SWS_MEM_DST_FLIPPED;
     }
     if (srcSliceY == 0)
         c->dst_y = 0;

@@ -193,6 +193,8 @@ int  ff_b200_cuda_launch(SwsCudaState *st,
 /* host frame in, host rows [y0,y1) out; synchronous */
 #define SWS_MEM_SRC_DEVICE 1   /* src[] are device pointers to whole planes */
 #define SWS_MEM_DST_DEVICE 2   /* dst[] are device pointers to whole planes */
+#define SWS_MEM_DST_FLIPPED 4  /* bottom-up frame: dst[1], dst[2] address row (dst_h >> vsub) - 1 (swscale.c:1153-1154), so with an
+                                * odd dst_h the last chroma row has no memory behind it: it is converted but never stored */
 int  ff_b200_cuda_scale_host(SwsCudaState *st,
                              const uint8_t *const src[4], const int src_stride[4],
                              int src_y, int src_h, int upload,

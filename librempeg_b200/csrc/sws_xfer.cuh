@@ -835,6 +835,8 @@ extern "C" int ff_b200_cuda_scale_host(SwsCudaState *st,
     int ret = ensure_staging(st);
     if (ret < 0)
         return ret;
+    const bool flipped = mem & SWS_MEM_DST_FLIPPED;
+    mem &= SWS_MEM_SRC_DEVICE | SWS_MEM_DST_DEVICE;
     if (mem) {
         const bool sdev = mem & SWS_MEM_SRC_DEVICE, ddev = mem & SWS_MEM_DST_DEVICE;
         if (upload && !sdev)
@@ -870,7 +872,9 @@ extern "C" int ff_b200_cuda_scale_host(SwsCudaState *st,
                         continue;
                     const int vs = (i == 1 || i == 2) && st->dst_rows[i] != p->dst_h ? p->chr_dst_vsub : 0;
                     const int r0 = y0 >> vs;
-                    const int r1 = (y1 == p->dst_h) ? st->dst_rows[i] : (y1 >> vs);
+                    int r1 = (y1 == p->dst_h) ? st->dst_rows[i] : (y1 >> vs);
+                    if (flipped && vs && r1 > (p->dst_h >> vs))
+                        r1 = p->dst_h >> vs;
                     if (r1 <= r0)
                         continue;
                     /* picture row r lives at dst[i] + r * stride (stride < 0): rows r1-1 .. r0 in memory order */
@@ -889,7 +893,9 @@ extern "C" int ff_b200_cuda_scale_host(SwsCudaState *st,
                         return AVERROR(EINVAL);
                     const int vs = (i == 1 || i == 2) && st->dst_rows[i] != p->dst_h ? p->chr_dst_vsub : 0;
                     const int r0 = y0 >> vs;
-                    const int r1 = (y1 == p->dst_h) ? st->dst_rows[i] : (y1 >> vs);
+                    int r1 = (y1 == p->dst_h) ? st->dst_rows[i] : (y1 >> vs);
+                    if (flipped && vs && r1 > (p->dst_h >> vs))
+                        r1 = p->dst_h >> vs;
                     if (r1 <= r0)
                         continue;
                     ret = download_rows(st, dst[i] + (ptrdiff_t)r0 * dst_stride[i], dst_stride[i],
@@ -966,7 +972,9 @@ extern "C" int ff_b200_cuda_scale_host(SwsCudaState *st,
                 continue;
             const int vs = (i == 1 || i == 2) && st->dst_rows[i] != p->dst_h ? p->chr_dst_vsub : 0;
             const int r0 = y0 >> vs;
-            const int r1 = (y1 == p->dst_h) ? st->dst_rows[i] : (y1 >> vs);
+            int r1 = (y1 == p->dst_h) ? st->dst_rows[i] : (y1 >> vs);
+            if (flipped && vs && r1 > (p->dst_h >> vs))
+                r1 = p->dst_h >> vs;
             if (r1 <= r0)
                 continue;
             ret = download_rows(st, dst[i] + (ptrdiff_t)r0 * dst_stride[i], dst_stride[i],

@@ -72,6 +72,10 @@ def _fmt(name):
         return ("semi", 8, 1, 1)
     if name == "p010le":
         return ("semi", 10, 1, 1)
+    if name == "grayf32le":
+        return ("grayf", 32, 0, 0)          # destinations only
+    if name == "gbrpf32le":
+        return ("rgbpf", 32, 0, 0)          # destinations only; planar RGB always takes the full-chroma path
     for key, (cw, ch) in {"420": (1, 1), "422": (1, 0), "444": (0, 0)}.items():
         for pre in ("yuvj", "yuv"):
             head = pre + key + "p"
@@ -453,6 +457,8 @@ class OracleContext:
         if dst_rgb and not (flags & SWS_FULL_CHR_H_INT):              # :1270-1286
             if dw & 1 or (shs == 0 and svs == 0 and dither != 2 and not flags & SWS_FAST_BILINEAR):
                 flags |= SWS_FULL_CHR_H_INT
+        if self.dkind == "rgbpf":                                     # planar RGB: full chroma forced, :1298-1306
+            flags |= SWS_FULL_CHR_H_INT
         if self.dkind == "rgb565":                                    # no full-chroma writer, :1329-1357
             flags &= ~SWS_FULL_CHR_H_INT
         if dst_rgb and not (flags & SWS_FULL_CHR_H_INT):              # :1359
@@ -493,7 +499,7 @@ class OracleContext:
         self.unscaled_lut = False
         self.special = None
         if unscaled and (sel_ranges[0] == sel_ranges[1] or dst_rgb):
-            if src_rgb and dst_rgb and self.dkind not in ("rgb16", "rgb565"):
+            if src_rgb and dst_rgb and self.dkind not in ("rgb16", "rgb565", "rgbpf"):
                 # rgbToRgbWrapper (findRgbConvFn, swscale_unscaled.c:1843-2060,2463-2466), packedCopyWrapper
                 # for identical formats; with SWS_BITEXACT 24 -> rgba/bgra is left to the scaler (:1992-1996)
                 s32, d32 = self.skind == "rgb32", self.dkind == "rgb32"
@@ -655,8 +661,8 @@ class OracleContext:
 
     # ---- range conversion on the h-scaled lines (swscale.c:163-255, constants :577-624)
     def _range(self, lum, u, v):
-        if self.src_range == self.dst_range or self.dkind.startswith("rgb"):
-            return lum, u, v
+        if self.src_range == self.dst_range or self.dkind.startswith("rgb") or self.dst_bpc >= 32:
+            return lum, u, v                          # swscale.c:610: no range conversion into float samples
         bd = min(self.dst_bpc, 16)
         src_bits = 15 if bd <= 14 else 19
         src_shift, mult_shift = src_bits - bd, (14 if bd <= 14 else 18)
@@ -830,6 +836,10 @@ class OracleContext:
         hl, hu, hv = self._range(hl, hu, hv)
         if self.dkind in ("planar", "semi"):
             return self._planar_out(hl, hu, hv)
+        if self.dkind == "grayf":
+            return self._grayf_out(hl)
+        if self.dkind == "rgbpf":
+            return self._gbrpf32_out(hl, hu, hv)
         if self.full_chr:
             return self._rgb_full_out(hl, hu, hv)
         if self.dkind == "rgb16":
@@ -893,6 +903,35 @@ class OracleContext:
         for k, comp in enumerate(order):
             out[:, k::bpp] = 255 if comp is None else comp
         return [out]
+
+    # yuv2plane1_float_c_template / yuv2planeX_float_c_template (output.c:219-268): the 16-bit writers' integer
+    # value times 1.0f / 65535.0f in single precision; one-tap filters go through yuv2plane1 (vscale.c:56-61)
+    def _grayf_out(self, hl):
+        coef, pos = self.v_lum
+        if coef.shape[1] == 1:
+            idx = np.clip(pos.astype(np.int64), 0, hl.shape[0] - 1)
+            val = np.clip(_wrap32(hl[idx] + 4) >> 3, 0, 65535)
+        else:
+            val = _wrap32(self._vsum(hl, self.v_lum) + (1 << 14) - 0x40000000) >> 15
+            val = 0x8000 + np.clip(val, -32768, 32767)
+        out = np.float32(1.0) / np.float32(65535.0) * val[:, :self.dw].astype(np.float32)
+        return [out.astype("<f4").view(np.uint8).reshape(out.shape[0], -1)]
+
+    # yuv2gbrpf32_full_X_c (output.c:2536-2610): the 16-bit full-chroma arithmetic, planes in G, B, R order
+    def _gbrpf32_out(self, hl, hu, hv):
+        t = self.rgb
+        n, w = self.dh, self.dw
+        Y = (_wrap32(self._vsum(hl, self.v_lum)[:, :w] - 0x40000000) >> 14) + 0x10000
+        U = _wrap32(self._vsum(hu, self.v_chr, n)[:, :w] - (128 << 23)) >> 14
+        V = _wrap32(self._vsum(hv, self.v_chr, n)[:, :w] - (128 << 23)) >> 14
+        Y = _wrap32(_wrap32((Y - t["y_offset"]) * t["y_coeff"]) + (1 << 13) - (1 << 29))
+        R = _wrap32(V * t["v2r"]); G = _wrap32(V * t["v2g"] + U * t["u2g"]); B = _wrap32(U * t["u2b"])
+        mult = np.float32(1.0) / np.float32(65535.0)
+
+        def comp(c):
+            v = np.clip((_wrap32(c + Y) >> 14) + (1 << 15), 0, 65535).astype(np.float32) * mult
+            return v.astype("<f4").view(np.uint8).reshape(n, -1)
+        return [comp(G), comp(B), comp(R)]
 
     # yuv2planeX_8_c / yuv2planeX_10_c / yuv2planeX_16_c / yuv2nv12cX_c (output.c:163-187,340-357,468-528)
     def _planar_out(self, hl, hu, hv):

@@ -155,7 +155,7 @@ def test_unsupported_fails_loudly():
     with pytest.raises(RuntimeError):
         S.SwsContext(320, 240, "yuv420p", 320, 240, "rgb24", S.SWS_BICUBIC | (1 << 16))          # vertical chroma drop
     with pytest.raises(RuntimeError):
-        S.SwsContext(320, 240, "rgba", 640, 480, "bgra", S.SWS_BICUBIC | BX)             # alpha through the scaler
+        S.SwsContext(320, 240, "p010le", 320, 240, "nv12", S.SWS_BICUBIC | BX)           # DITHER_COPY tail quirk
 
 
 @pytest.mark.parametrize("sf", ["yuv444p", "yuv420p", "yuv422p", "yuv444p10le", "yuv420p12le", "nv12"])

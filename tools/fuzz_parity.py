@@ -23,7 +23,7 @@ from tests import sws_testlib as T       # noqa: E402
 SRC = ["yuv420p", "yuv422p", "yuv444p", "yuvj420p", "yuvj422p", "yuvj444p", "nv12", "nv21", "p010le",
        "yuv420p9le", "yuv420p10le", "yuv422p10le", "yuv444p10le", "yuv420p12le", "yuv422p12le", "yuv444p12le",
        "yuv420p14le", "yuv420p16le", "yuv422p16le", "yuv444p16le", "rgb24", "bgr24", "rgba", "bgra", "argb", "abgr"]
-DST = SRC + ["rgb48le", "bgr48le", "rgb565le", "bgr565le", "rgb555le", "bgr555le"]
+DST = SRC + ["rgb48le", "bgr48le", "rgb565le", "bgr565le", "rgb555le", "bgr555le", "grayf32le", "gbrpf32le"]
 SCALERS = [S.SWS_FAST_BILINEAR, S.SWS_BILINEAR, S.SWS_BICUBIC, S.SWS_X, S.SWS_POINT, S.SWS_AREA, S.SWS_BICUBLIN,
            S.SWS_GAUSS, S.SWS_SINC, S.SWS_LANCZOS, S.SWS_SPLINE]
 
@@ -106,10 +106,10 @@ def make_case(rng):
         case["ctx_kwargs"] = dict(src_range=rng.randint(0, 1), dst_range=rng.randint(0, 1))
     if rng.random() < 0.1:
         cs = rng.choice([1, 5, 7, 9])
-        # YUV -> YUV with two different matrices makes the reference cascade through RGB (refused here, and the
-        # reference itself crashes on some tiny sizes): differ only when one side is RGB, where one matrix is unused
-        is_rgb = lambda f: f.startswith(("rgb", "bgr", "argb", "abgr"))
-        other = rng.choice([cs, 5]) if is_rgb(case["sf"]) or is_rgb(case["df"]) or rng.random() < 0.1 else cs
+        # YUV -> YUV with two different matrices makes the reference cascade through RGB (the reference itself
+        # crashes on some tiny sizes, hence the size guard below)
+        is_rgb = lambda f: f.startswith(("rgb", "bgr", "argb", "abgr", "gbr"))
+        other = rng.choice([cs, 5]) if is_rgb(case["sf"]) or is_rgb(case["df"]) or rng.random() < 0.4 else cs
         if min(case["sw"], case["sh"], case["dw"], case["dh"]) < 16:
             other = cs
         case["colorspace"] = (cs, rng.randint(0, 1), other, rng.randint(0, 1), 0, 1 << 16, 1 << 16)
@@ -127,7 +127,7 @@ def make_case(rng):
         kw["chr_pos"] = tuple(rng.choice([-513, 0, 64, 128, 256]) for _ in range(4))
     if rng.random() < 0.1:
         kw = case.setdefault("ctx_kwargs", {})
-        kw["dither"] = rng.choice([0, 1, 2, 4, 5])
+        kw["dither"] = rng.choice([0, 1, 2, 3, 4, 5])
     if "colorspace" in case and rng.random() < 0.3:
         cs = list(case["colorspace"])
         cs[4:] = [rng.choice([0, 3000, -5000]), rng.choice([1 << 16, 78643, 52000]), rng.choice([1 << 16, 52428, 90000])]
@@ -136,7 +136,8 @@ def make_case(rng):
         # 16-bit samples need even strides (the reference reads them through uint16_t pointers)
         case["src_pad"] = rng.choice([0, 1, 3, 16, 64] if T.depth_of(case["sf"]) == 8 else [0, 2, 6, 16, 64])
         case["dst_pad"] = rng.choice([0, 1, 5, 16, 64] if T.depth_of(case["df"]) == 8 and "48" not in case["df"]
-                                     and "5le" not in case["df"] else [0, 2, 6, 16, 64])
+                                     and "5le" not in case["df"] and "f32" not in case["df"] else
+                                     [0, 4, 16, 64] if "f32" in case["df"] else [0, 2, 6, 16, 64])
     return case
 
 
@@ -198,6 +199,10 @@ def main():
             # top-down slices; chroma rows stay aligned (multiples of 2 rows except the last)
             step = 2 * rng.randint(1, max(1, case["sh"] // 4))
             case["slices"] = [(y, min(step, case["sh"] - y)) for y in range(0, case["sh"], step)]
+            # bottom-up: the last slice first (swscale.c:1141-1159).  Even heights only: with an odd dst_h the reference
+            # writes the last chroma row in front of the plane (heap underflow), with an odd src_h it reads one there
+            if rng.random() < 0.25 and not ((case["sh"] | case["dh"]) & 1):
+                case["slices"].reverse()
         if i < args.start:
             continue
         if args.cursor:
