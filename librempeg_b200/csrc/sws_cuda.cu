@@ -1567,6 +1567,7 @@ struct SwsCudaState {
     int fast_narrow;             /* the 128 x 64 tile shape of the fast420 kernel is set up and preferred */
     int4 *d_fast_rows_narrow;
     int fasthi8_ok, fasthi8_crows;
+    int s8_stages, s8_s16, s8_elt_shift;
     int s8_ok, s8_fs4, s8_tile_h, s8_nl_cap, s8_nc_cap, s8_seg_l, s8_seg_c, s8_slot, s8_vl_n4, s8_vc_n4;
     size_t s8_smem;
     void *s8_tables;
@@ -2234,20 +2235,27 @@ static int fasthi8_launch(SwsCudaState *st, const uint8_t *const src[4], const i
 /* ---------------------------------------------------------------- scale8 host side */
 
 typedef void (*scale8_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Scale8Args);
-static scale8_kernel_t pick_scale8(int fs4, bool rgb, bool mma)
+static scale8_kernel_t pick_scale8(int fs4, bool rgb, bool mma, bool s16)
 {
+    if (s16) {          /* 9..16-bit planar sources: IDP.2A horizontal stage */
+        if (rgb)
+            return fs4 == 1 ? sws_scale8_kernel<1, true, false, true> : fs4 == 2 ? sws_scale8_kernel<2, true, false, true>
+                                                                                 : sws_scale8_kernel<4, true, false, true>;
+        return fs4 == 1 ? sws_scale8_kernel<1, false, false, true> : fs4 == 2 ? sws_scale8_kernel<2, false, false, true>
+                                                                              : sws_scale8_kernel<4, false, false, true>;
+    }
     if (mma) {          /* fs4 = K steps of the tensor-pipe horizontal stage */
         if (rgb)
-            return fs4 == 1 ? sws_scale8_kernel<1, true, true> : fs4 == 2 ? sws_scale8_kernel<2, true, true>
-                                                                          : sws_scale8_kernel<4, true, true>;
-        return fs4 == 1 ? sws_scale8_kernel<1, false, true> : fs4 == 2 ? sws_scale8_kernel<2, false, true>
-                                                                       : sws_scale8_kernel<4, false, true>;
+            return fs4 == 1 ? sws_scale8_kernel<1, true, true, false> : fs4 == 2 ? sws_scale8_kernel<2, true, true, false>
+                                                                                 : sws_scale8_kernel<4, true, true, false>;
+        return fs4 == 1 ? sws_scale8_kernel<1, false, true, false> : fs4 == 2 ? sws_scale8_kernel<2, false, true, false>
+                                                                              : sws_scale8_kernel<4, false, true, false>;
     }
     if (rgb)
-        return fs4 == 1 ? sws_scale8_kernel<1, true, false> : fs4 == 2 ? sws_scale8_kernel<2, true, false>
-                                                                       : sws_scale8_kernel<4, true, false>;
-    return fs4 == 1 ? sws_scale8_kernel<1, false, false> : fs4 == 2 ? sws_scale8_kernel<2, false, false>
-                                                                    : sws_scale8_kernel<4, false, false>;
+        return fs4 == 1 ? sws_scale8_kernel<1, true, false, false> : fs4 == 2 ? sws_scale8_kernel<2, true, false, false>
+                                                                              : sws_scale8_kernel<4, true, false, false>;
+    return fs4 == 1 ? sws_scale8_kernel<1, false, false, false> : fs4 == 2 ? sws_scale8_kernel<2, false, false, false>
+                                                                           : sws_scale8_kernel<4, false, false, false>;
 }
 
 /* ---- tensor-pipe horizontal stage: per group of 8 output columns, the K window and the banded B fragments ----
@@ -2424,19 +2432,47 @@ static int s8_seg_bytes(const SwsFirBank *b, int fs4, int tile_cols)
     return worst;
 }
 
+/* 16-bit samples: rows start at a multiple of 8 samples, a column reads 2 fs4 + 1 words from its even first sample */
+static int s16_seg_bytes(const SwsFirBank *b, int fs4, int tile_cols)
+{
+    int worst = 16;
+    for (int x0 = 0; x0 < b->len; x0 += tile_cols) {
+        const int x1 = x0 + tile_cols - 1 < b->len - 1 ? x0 + tile_cols - 1 : b->len - 1;
+        const int a0 = b->pos[x0] & ~7;
+        int need = 0;
+        for (int x = x0; x <= x1; x++) {
+            if (b->pos[x] < b->pos[x0])
+                return -1;
+            const int e = ((b->pos[x] - a0) >> 1) * 4 + 8 * fs4 + 4;
+            if (e > need) need = e;
+        }
+        need = (need + 15) & ~15;
+        if (need > worst) worst = need;
+    }
+    return worst;
+}
+
 static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank *hc,
                         const SwsFirBank *vl, const SwsFirBank *vc)
 {
     const SwsCudaPlan *p = &st->plan;
     st->s8_ok = 0;
-    if (p->src_bits != 8 || p->inter_bits != 15 || p->range_mode || p->src_layout > SWSC_SRC_NV21)
+    if (p->inter_bits != 15 || p->src_layout > SWSC_SRC_NV21 || p->src_alpha || p->dst_alpha)
         return 0;
-    /* destinations: 8-bit planar / semi-planar YUV, or packed 8-bit RGB with one chroma sample per pixel pair */
+    /* sources: 8-bit planar / nv12 / nv21, or 9..16-bit little-endian planar (hScale16To15_c) */
+    const bool s16 = p->src_bits > 8;
+    if (s16 && (p->src_layout != SWSC_SRC_PLANAR || p->src_shift || p->src_bits > 16))
+        return 0;
+    /* destinations: 8-bit planar / semi-planar YUV, 9..14-bit planar YUV, or packed 8-bit RGB with one chroma
+     * sample per pixel pair */
     const bool rgb = p->dst_kind >= SWSC_DST_RGB24 && p->dst_kind <= SWSC_DST_ABGR;
     if (rgb && (p->chr_dst_hsub != 1 || p->chr_dst_vsub != 0 || p->full_chr || p->special || p->unscaled_lut ||
                 !p->has_chroma))
         return 0;
-    if (!rgb && p->dst_kind != SWSC_DST_PLANAR8 && p->dst_kind != SWSC_DST_NV12 && p->dst_kind != SWSC_DST_NV21)
+    if (!rgb && p->dst_kind != SWSC_DST_PLANAR8 && p->dst_kind != SWSC_DST_NV12 && p->dst_kind != SWSC_DST_NV21 &&
+        !(p->dst_kind == SWSC_DST_PLANARN && p->dst_bits >= 9 && p->dst_bits <= 14 && !p->dst_shift))
+        return 0;
+    if (!p->has_chroma || !p->dst_has_chroma || p->special || p->unscaled_lut)
         return 0;
     if (hl->size > 16 || hc->size > 16 || vl->size > 16 || vc->size > 16)
         return 0;
@@ -2460,12 +2496,14 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
                 hvl[y].pos_even |= 1;
         }
     }
-    int seg_l = ret ? -1 : s8_seg_bytes(hl, fs4, S8_TW);
-    int seg_c = ret ? -1 : s8_seg_bytes(hc, fs4, cw);
+    int seg_l = ret ? -1 : s16 ? s16_seg_bytes(hl, fs4, S8_TW) : s8_seg_bytes(hl, fs4, S8_TW);
+    int seg_c = ret ? -1 : s16 ? s16_seg_bytes(hc, fs4, cw) : s8_seg_bytes(hc, fs4, cw);
     /* tensor-pipe horizontal stage when every 8-column window fits K <= 128 samples (SWS_B200_DISABLE=s8mma: A/B) */
     const bool inter = p->src_layout != SWSC_SRC_PLANAR;
     int mma = 0, ks = 0;
-    if (!ret && seg_l >= 0 && seg_c >= 0 && !(getenv("SWS_B200_DISABLE") && strstr(getenv("SWS_B200_DISABLE"), "s8mma"))) {
+    const bool plain = !p->range_mode && p->dst_kind != SWSC_DST_PLANARN;       /* what the MMA variants are compiled for */
+    if (!ret && !s16 && plain && seg_l >= 0 && seg_c >= 0 &&
+        !(getenv("SWS_B200_DISABLE") && strstr(getenv("SWS_B200_DISABLE"), "s8mma"))) {
         const int kl = s8_mma_ksteps(hl, S8_TW, false), kc = s8_mma_ksteps(hc, cw, inter);
         ks = kl > kc ? kl : kc;
         ks = ks <= 1 ? 1 : ks == 2 ? 2 : ks <= 4 ? 4 : 0;
@@ -2489,26 +2527,40 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     }
     if (seg_l < 0 || seg_c < 0)
         ret = 1;
-    else if (seg_l > 1024 || seg_c > 512 || !get_encode_tiled())
-        ret = 1;                      /* one ring-slot row is one TMA box row of at most 256 32-bit elements */
-    int th = 0, nl_cap = 0, nc_cap = 0, slot = 0;
+    else if (seg_l > 2048 || seg_c > (s16 ? 2048 : 1024) || !get_encode_tiled())
+        ret = 1;                      /* one ring-slot row is one TMA box row of at most 256 elements of 4 or 8 bytes */
+    /* bytes per row of one chroma plane; interleaved rows are 2 seg_c bytes */
+    const int rowc = p->src_layout == SWSC_SRC_PLANAR ? seg_c : 2 * seg_c;
+    const int elt_shift = (seg_l > 1024 || rowc > 1024) ? 3 : 2;
+    int th = 0, nl_cap = 0, nc_cap = 0, slot = 0, stages = 0;
     size_t smem = 0;
     if (!ret) {
         ret = 1;
-        /* largest tile that still leaves three CTAs per SM (about 74 KB each); failing that, two */
-        const size_t budget[2] = { 74 * 1024 + 512, 100 * 1024 };
-        const char *th_env = getenv("SWS_B200_S8_TH");
+        /* largest tile that still leaves three CTAs per SM (about 74 KB each) with a ring of two slots; failing that,
+         * two CTAs.  SWS_B200_S8_STAGES raises the ring depth up to what the budget leaves: measured on C4 / X1 / X2
+         * with 2..5 slots, no difference (the kernel does not wait on TMA), and a persistent grid with the ring
+         * running ahead across tiles was slower (profiles/r02/scale8_persistent_r02.txt). */
+        size_t budget[2] = { 74 * 1024 + 512, 100 * 1024 };
+        const char *th_env = getenv("SWS_B200_S8_TH"), *st_env = getenv("SWS_B200_S8_STAGES"), *kb_env = getenv("SWS_B200_S8_KB");
         const int th_max = th_env && atoi(th_env) >= 2 ? atoi(th_env) : 32;
+        const int st_max = st_env && atoi(st_env) >= 2 && atoi(st_env) <= S8_MAX_STAGES ? atoi(st_env) : S8_STAGES;
+        if (kb_env && atoi(kb_env) >= 32 && atoi(kb_env) <= 200)
+            budget[0] = budget[1] = (size_t)atoi(kb_env) * 1024;
         for (int pass = 0; pass < 2 && ret; pass++)
             for (th = th_max; th >= 2; th >>= 1) {
                 const int cth = th >> p->chr_dst_vsub ? th >> p->chr_dst_vsub : 1;
                 nl_cap = s8_rows_cap(hvl, vl->len, th);
                 nc_cap = s8_rows_cap(hvc, vc->len, cth);
                 slot = (S8_ROWS * (seg_l > 2 * seg_c ? seg_l : 2 * seg_c) + 127) & ~127;
+                if (slot > 48 * 1024)
+                    break;
                 if (rgb && S8_STAGES * slot < 8 * 512)
                     slot = 8 * 512 / S8_STAGES;       /* the idle ring stages the packed RGB rows of the 8 warps */
-                smem = ((size_t)S8_TW * nl_cap + 2 * (size_t)cw * nc_cap) * 2 + (size_t)S8_STAGES * slot;
-                if (smem <= budget[pass]) {
+                const size_t lines = ((size_t)S8_TW * nl_cap + 2 * (size_t)cw * nc_cap) * 2;
+                if (lines + 2 * (size_t)slot <= budget[pass]) {
+                    stages = (int)((budget[pass] - lines) / slot);
+                    if (stages > st_max) stages = st_max;
+                    smem = lines + (size_t)stages * slot;
                     ret = 0;
                     break;
                 }
@@ -2563,19 +2615,19 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     st->s8_hc_cl = (uint32_t *)(t + o_hccl); st->s8_hc_ch = (uint32_t *)(t + o_hcch);
     st->s8_vl = (S8VRow *)(t + o_vl); st->s8_vc = (S8VRow *)(t + o_vc);
     st->s8_fs4 = mma ? ks : fs4; st->s8_tile_h = th; st->s8_nl_cap = nl_cap; st->s8_nc_cap = nc_cap;
-    st->s8_seg_l = seg_l; st->s8_seg_c = seg_c; st->s8_smem = smem; st->s8_slot = slot;
+    st->s8_seg_l = seg_l; st->s8_seg_c = seg_c; st->s8_smem = smem; st->s8_slot = slot; st->s8_stages = stages; st->s8_s16 = s16; st->s8_elt_shift = elt_shift;
     st->s8_mma = mma;
     if (mma) {
         st->s8_hl_goff = (int *)(t + o_gl); st->s8_hc_goff = (int *)(t + o_gc);
         st->s8_hl_B = (uint32_t *)(t + o_bl); st->s8_hc_B = (uint32_t *)(t + o_bc);
     }
-    CUDA_OK(set_max_smem((const void *)pick_scale8(st->s8_fs4, rgb, mma), (size_t)((int)smem)));
+    CUDA_OK(set_max_smem((const void *)pick_scale8(st->s8_fs4, rgb, mma, s16), (size_t)((int)smem)));
     st->s8_ok = 1;
     if (getenv("SWS_B200_DEBUG"))
-        fprintf(stderr, "[swscaler-b200] scale8: %s fs4=%d tile_h=%d nl_cap=%d nc_cap=%d seg_l=%d seg_c=%d slot=%d smem=%zu\n",
-                mma ? "mma" : "dp4a", st->s8_fs4, th, nl_cap, nc_cap, seg_l, seg_c, slot, smem);
+        fprintf(stderr, "[swscaler-b200] scale8: %s fs4=%d tile_h=%d nl_cap=%d nc_cap=%d seg_l=%d seg_c=%d slot=%d stages=%d smem=%zu\n",
+                s16 ? "dp2a16" : mma ? "mma" : "dp4a", st->s8_fs4, th, nl_cap, nc_cap, seg_l, seg_c, slot, stages, smem);
     if (!st->fast_ok && !st->fast16_ok)
-        st->kernel_name = mma ? "scale8_mma" : "scale8_dp4a";
+        st->kernel_name = s16 ? "scale16_dp2a" : mma ? "scale8_mma" : "scale8_dp4a";
     return 0;
 }
 
@@ -2585,31 +2637,36 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
                          const int64_t dst_fstride[4], int nb_frames, int y0, int y1, cudaStream_t stream)
 {
     const SwsCudaPlan *p = &st->plan;
-    if (!st->s8_ok || (st->disabled & 4) || p->range_mode)
+    /* a range change after init (sws_setColorspaceDetails) finds the tensor-pipe variant compiled without it */
+    if (!st->s8_ok || (st->disabled & 4) || (st->s8_mma && p->range_mode))
         return 0;
     const int nsrc = p->src_layout == SWSC_SRC_PLANAR ? 3 : 2;
     for (int i = 0; i < nsrc; i++)
         if (!src[i] || !aligned16(src[i]) || (src_stride[i] & 15) || src_stride[i] < 16 ||
             (nb_frames > 1 && (src_fstride[i] & 15)))
             return 0;
-    /* source planes as 32-bit-element tensors {row words, rows, frames}: a ring slot is one 8-row box */
+    /* source planes as tensors of 4- or 8-byte elements {row elements, rows, frames}: a ring slot is one box of S8_ROWS rows */
     CUtensorMap my, mu, mv;
     const bool planar = p->src_layout == SWSC_SRC_PLANAR;
+    const int es = st->s8_elt_shift, bps = st->s8_s16 ? 1 : 0;
+    const CUtensorMapDataType edt = es == 3 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+    const uint64_t emask = (1u << es) - 1;
     const uint64_t fs_y = nb_frames > 1 ? src_fstride[0] : (uint64_t)src_stride[0] * p->src_h;
     const uint64_t fs_u = nb_frames > 1 ? src_fstride[1] : (uint64_t)src_stride[1] * p->chr_src_h;
-    const uint64_t cbytes = planar ? (uint64_t)p->chr_src_w : 2 * (uint64_t)p->chr_src_w;
+    const uint64_t ybytes = (uint64_t)p->src_w << bps;
+    const uint64_t cbytes = (planar ? (uint64_t)p->chr_src_w : 2 * (uint64_t)p->chr_src_w) << bps;
     int ret;
-    if ((ret = make_map_3d(&my, CU_TENSOR_MAP_DATA_TYPE_UINT32, src[0], ((uint64_t)p->src_w + 3) / 4, p->src_h,
-                           nb_frames, src_stride[0], fs_y, st->s8_seg_l / 4, S8_ROWS)) < 0 ||
-        (ret = make_map_3d(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT32, src[1], (cbytes + 3) / 4, p->chr_src_h,
-                           nb_frames, src_stride[1], fs_u, (planar ? st->s8_seg_c : 2 * st->s8_seg_c) / 4,
+    if ((ret = make_map_3d(&my, edt, src[0], (ybytes + emask) >> es, p->src_h,
+                           nb_frames, src_stride[0], fs_y, st->s8_seg_l >> es, S8_ROWS)) < 0 ||
+        (ret = make_map_3d(&mu, edt, src[1], (cbytes + emask) >> es, p->chr_src_h,
+                           nb_frames, src_stride[1], fs_u, (planar ? st->s8_seg_c : 2 * st->s8_seg_c) >> es,
                            S8_ROWS)) < 0)
         return ret;
     mv = mu;
     if (planar) {
         const uint64_t fs_v = nb_frames > 1 ? src_fstride[2] : (uint64_t)src_stride[2] * p->chr_src_h;
-        if ((ret = make_map_3d(&mv, CU_TENSOR_MAP_DATA_TYPE_UINT32, src[2], (cbytes + 3) / 4, p->chr_src_h,
-                               nb_frames, src_stride[2], fs_v, st->s8_seg_c / 4, S8_ROWS)) < 0)
+        if ((ret = make_map_3d(&mv, edt, src[2], (cbytes + emask) >> es, p->chr_src_h,
+                               nb_frames, src_stride[2], fs_v, st->s8_seg_c >> es, S8_ROWS)) < 0)
             return ret;
     }
     Scale8Args a;
@@ -2626,7 +2683,13 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.y0 = y0; a.y1 = y1; a.tile_h = st->s8_tile_h;
     a.nl_cap = st->s8_nl_cap; a.nc_cap = st->s8_nc_cap; a.seg_l = st->s8_seg_l; a.seg_c = st->s8_seg_c;
     a.slot_bytes = st->s8_slot;
-    a.stages = S8_STAGES;
+    a.stages = st->s8_stages;
+    a.bps = bps; a.elt_shift = es; a.h_shift = p->h_shift;
+    a.range_mode = p->range_mode;
+    a.lum_rc_coeff = (int)p->lum_rc_coeff; a.lum_rc_offset = (int)p->lum_rc_offset;
+    a.chr_rc_coeff = (int)p->chr_rc_coeff; a.chr_rc_offset = (int)p->chr_rc_offset;
+    a.out_bits = p->dst_kind == SWSC_DST_PLANARN ? p->dst_bits : 8;
+    a.dither_bayer = p->dither_bayer;
     a.vl_n4 = st->s8_vl_n4; a.vc_n4 = st->s8_vc_n4;
     a.cy = p->rgb.cy; a.yb = p->rgb.yb; a.base_r = p->rgb.base_r; a.base_g = p->rgb.base_g; a.base_b = p->rgb.base_b;
     a.crv = p->rgb.crv; a.cgu = p->rgb.cgu; a.cgv = p->rgb.cgv; a.cbu = p->rgb.cbu;
@@ -2636,8 +2699,8 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.vl = st->s8_vl; a.vc = st->s8_vc;
     a.hl_goff = st->s8_hl_goff; a.hc_goff = st->s8_hc_goff; a.hl_B = st->s8_hl_B; a.hc_B = st->s8_hc_B;
     dim3 grid((p->dst_w + S8_TW - 1) / S8_TW, (y1 - y0 + st->s8_tile_h - 1) / st->s8_tile_h, nb_frames);
-    pick_scale8(st->s8_fs4, rgb, st->s8_mma)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
-    st->kernel_name = st->s8_mma ? "scale8_mma" : "scale8_dp4a";
+    pick_scale8(st->s8_fs4, rgb, st->s8_mma, st->s8_s16)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
+    st->kernel_name = st->s8_s16 ? "scale16_dp2a" : st->s8_mma ? "scale8_mma" : "scale8_dp4a";
     CUDA_OK(cudaGetLastError());
     st->launches++;
     return 1;

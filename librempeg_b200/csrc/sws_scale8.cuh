@@ -71,6 +71,13 @@ struct Scale8Args {
     int seg_l, seg_c;        /* staged bytes per luma row / chroma samples per chroma row */
     int slot_bytes;          /* one ring slot: max(8 luma rows, 8 rows of both chroma planes), 128-byte multiple */
     int stages;              /* ring depth, 2 .. S8_MAX_STAGES */
+    int bps;                 /* log2 bytes per source sample: 0 (8-bit) or 1 (9..16-bit little-endian planar) */
+    int elt_shift;           /* log2 bytes per TMA element of the source maps (2: u32, 3: u64 for rows beyond 1 KB) */
+    int h_shift;             /* 16-bit sources: right shift after the horizontal FIR (depth - 1, swscale.c:99-125) */
+    int range_mode;          /* 0 none, 1 to full range, 2 to limited range (swscale.c:163-216), on the h-scaled lines */
+    int lum_rc_coeff, lum_rc_offset, chr_rc_coeff, chr_rc_offset;
+    int out_bits;            /* planar destinations: 8, or 9..14 (16-bit little-endian samples) */
+    int dither_bayer;        /* 8-bit planar output of > 8-bit sources: ff_dither_8x8_128 instead of the constant 64 */
     const int *hl_pos, *hc_pos;
     const uint32_t *hl_cl, *hl_ch, *hc_cl, *hc_ch;
     const S8VRow *vl, *vc;
@@ -129,19 +136,31 @@ __device__ __forceinline__ uint32_t s8_ldm_row(int lane)
 
 /* 16 staged rows x 8 output columns: accumulators to two words of vertically adjacent 15-bit samples
  * (columns 2t and 2t+1 of the group, source rows 2g and 2g+1 of the slot; t = lane & 3, g = lane >> 2) */
-__device__ __forceinline__ void s8_mma_pack(const int (&lo)[4], const int (&hi)[4], uint32_t sel, uint32_t &wa, uint32_t &wb)
+struct S8Range {         /* range conversion of the h-scaled lines; mode 0 = none */
+    int mode, coeff, offset;
+};
+
+__device__ __forceinline__ int s8_range(int val, int mode, int coeff, int offset);
+
+__device__ __forceinline__ void s8_mma_pack(const int (&lo)[4], const int (&hi)[4], uint32_t sel, const S8Range &rc,
+                                            uint32_t &wa, uint32_t &wb)
 {
-    const int v0 = min(((hi[0] << 8) + lo[0]) >> 7, (1 << 15) - 1);
-    const int v1 = min(((hi[1] << 8) + lo[1]) >> 7, (1 << 15) - 1);
-    const int v2 = min(((hi[2] << 8) + lo[2]) >> 7, (1 << 15) - 1);
-    const int v3 = min(((hi[3] << 8) + lo[3]) >> 7, (1 << 15) - 1);
+    int v0 = min(((hi[0] << 8) + lo[0]) >> 7, (1 << 15) - 1);
+    int v1 = min(((hi[1] << 8) + lo[1]) >> 7, (1 << 15) - 1);
+    int v2 = min(((hi[2] << 8) + lo[2]) >> 7, (1 << 15) - 1);
+    int v3 = min(((hi[3] << 8) + lo[3]) >> 7, (1 << 15) - 1);
+    if (rc.mode) {
+        v0 = s8_range(v0, rc.mode, rc.coeff, rc.offset); v1 = s8_range(v1, rc.mode, rc.coeff, rc.offset);
+        v2 = s8_range(v2, rc.mode, rc.coeff, rc.offset); v3 = s8_range(v3, rc.mode, rc.coeff, rc.offset);
+    }
     wa = prmt((uint32_t)v0, (uint32_t)v2, sel);
     wb = prmt((uint32_t)v1, (uint32_t)v3, sel);
 }
 
 /* plain rows (luma, planar chroma): KS ldmatrix + 2 KS MMAs */
 template <int KS>
-__device__ __forceinline__ void s8_mma_rows(uint32_t addr, const S8Bfrag<KS> &b, uint32_t sel, uint32_t &wa, uint32_t &wb)
+__device__ __forceinline__ void s8_mma_rows(uint32_t addr, const S8Bfrag<KS> &b, uint32_t sel, const S8Range &rc,
+                                            uint32_t &wa, uint32_t &wb)
 {
     int lo[4] = { 0, 0, 0, 0 }, hi[4] = { 0, 0, 0, 0 };
 #pragma unroll
@@ -151,14 +170,14 @@ __device__ __forceinline__ void s8_mma_rows(uint32_t addr, const S8Bfrag<KS> &b,
         s8_mma_uu(lo, a, b.r[ks][0], b.r[ks][1]);
         s8_mma_us(hi, a, b.r[ks][2], b.r[ks][3]);
     }
-    s8_mma_pack(lo, hi, sel, wa, wb);
+    s8_mma_pack(lo, hi, sel, rc, wa, wb);
 }
 
 /* interleaved chroma rows (nv12 / nv21): two ldmatrix per K step of 32 chroma samples, U and V fragments cut
  * out of them with PRMT; `even` = the plane stored first in memory */
 template <int KS>
-__device__ __forceinline__ void s8_mma_rows_uv(uint32_t addr, const S8Bfrag<KS> &b, uint32_t sel, uint32_t &ea,
-                                               uint32_t &eb, uint32_t &oa, uint32_t &ob)
+__device__ __forceinline__ void s8_mma_rows_uv(uint32_t addr, const S8Bfrag<KS> &b, uint32_t sel, const S8Range &rc,
+                                               uint32_t &ea, uint32_t &eb, uint32_t &oa, uint32_t &ob)
 {
     int elo[4] = { 0, 0, 0, 0 }, ehi[4] = { 0, 0, 0, 0 }, olo[4] = { 0, 0, 0, 0 }, ohi[4] = { 0, 0, 0, 0 };
 #pragma unroll
@@ -175,8 +194,8 @@ __device__ __forceinline__ void s8_mma_rows_uv(uint32_t addr, const S8Bfrag<KS> 
         s8_mma_uu(olo, o, b.r[ks][0], b.r[ks][1]);
         s8_mma_us(ohi, o, b.r[ks][2], b.r[ks][3]);
     }
-    s8_mma_pack(elo, ehi, sel, ea, eb);
-    s8_mma_pack(olo, ohi, sel, oa, ob);
+    s8_mma_pack(elo, ehi, sel, rc, ea, eb);
+    s8_mma_pack(olo, ohi, sel, rc, oa, ob);
 }
 
 __device__ __forceinline__ int dp2a_lo_su(uint32_t a, uint32_t b, int c)
@@ -221,6 +240,64 @@ __device__ __forceinline__ int s8_hfir(const unsigned char *srow, int sh, const 
         w0 = w1;
     }
     return min(((acc_h << 8) + acc_l) >> 7, (1 << 15) - 1);
+}
+
+/* lumRangeToJpeg_c / lumRangeFromJpeg_c and the chroma twins (swscale.c:163-216) on one 15-bit sample:
+ * (x * coeff + offset) >> 14, clipped towards full range only, stored as int16 */
+__device__ __forceinline__ int s8_range(int val, int mode, int coeff, int offset)
+{
+    val = (val * coeff + offset) >> 14;
+    if (mode == 1)
+        val = min(val, (1 << 15) - 1);
+    return (int)(int16_t)val;
+}
+
+__device__ __forceinline__ int dp2a_lo_uu(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_uu(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_lo_us(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_us(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+/* hScale16To15_c (swscale.c:99-125) of one staged row of 16-bit samples for one output column: two samples per
+ * word, an odd first sample is a 16-bit funnel shift; IDP.2A against the split coefficient bytes, everything
+ * modulo 2^32 like the C code's int accumulator */
+template <int FS4>
+__device__ __forceinline__ int s16_hfir(const unsigned char *srow, int sh, int hshift, const uint32_t (&cl)[FS4],
+                                        const uint32_t (&ch)[FS4])
+{
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(srow);
+    uint32_t w0 = wp[0];
+    int acc_l = 0, acc_h = 0;
+#pragma unroll
+    for (int k = 0; k < FS4; k++) {
+        const uint32_t w1 = wp[2 * k + 1], w2 = wp[2 * k + 2];
+        const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
+        acc_l = dp2a_lo_uu(v0, cl[k], acc_l);
+        acc_h = dp2a_lo_us(v0, ch[k], acc_h);
+        acc_l = dp2a_hi_uu(v1, cl[k], acc_l);
+        acc_h = dp2a_hi_us(v1, ch[k], acc_h);
+        w0 = w2;
+    }
+    return min(((acc_h << 8) + acc_l) >> hshift, (1 << 15) - 1);
 }
 
 /* vertical FIR for NC columns (transposed 15-bit lines, cstep words apart): bias + sum of taps, before
@@ -348,8 +425,8 @@ __device__ __forceinline__ void s8_hfir_uv(const unsigned char *srow, int sh, co
  *           de-interleaved on the fly).
  *  V:       warp = output row, lane = columns lane + 32k.
  */
-template <int FS4, bool RGB, bool MMA>
-__global__ void __launch_bounds__(S8_THREADS, (MMA && FS4 > 2) ? 3 : (RGB || FS4 <= S8_LIGHT_FS4) ? S8_RGB_CTAS : 3)
+template <int FS4, bool RGB, bool MMA, bool S16>
+__global__ void __launch_bounds__(S8_THREADS, (S16 || (MMA && FS4 > 2)) ? 3 : (RGB || FS4 <= S8_LIGHT_FS4) ? S8_RGB_CTAS : 3)
 sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_u,
                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ Scale8Args A)
 {
@@ -400,8 +477,9 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     const int nc = ch > 0 ? min(min(hi_c, A.chr_src_h) - lo_c, A.nc_cap) : 0;
     const int npl = (nl + S8_ROWS - 1) / S8_ROWS, npc = (nc + S8_ROWS - 1) / S8_ROWS;
 
-    const int a0l = __ldg(A.hl_pos + x0) & ~15;
-    const int a0c = ch > 0 ? __ldg(A.hc_pos + cx0) & ~15 : 0;
+    /* first staged sample of the tile's rows: 16-byte aligned */
+    const int a0l = __ldg(A.hl_pos + x0) & ~(15 >> A.bps);
+    const int a0c = ch > 0 ? __ldg(A.hc_pos + cx0) & ~(15 >> A.bps) : 0;
     const bool planar = A.src_layout == SWSC_SRC_PLANAR;
     const uint32_t ring_a = smem_u32(s8_smem_raw), full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
     __syncthreads();
@@ -417,13 +495,14 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 const uint32_t d = ring_a + b * slot, bar = full_a + 8 * b;
                 if (q < npl) {
                     s8_expect_tx(bar, S8_ROWS * A.seg_l);
-                    s8_tma_load(d, &map_y, bar, a0l >> 2, lo_l + S8_ROWS * q, f);
+                    s8_tma_load(d, &map_y, bar, (a0l << A.bps) >> A.elt_shift, lo_l + S8_ROWS * q, f);
                 } else {
                     const int row = lo_c + S8_ROWS * (q - npl);
                     s8_expect_tx(bar, 2 * S8_ROWS * A.seg_c);
                     if (planar) {
-                        s8_tma_load(d, &map_u, bar, a0c >> 2, row, f);
-                        s8_tma_load(d + S8_ROWS * A.seg_c, &map_v, bar, a0c >> 2, row, f);
+                        const int cx = (a0c << A.bps) >> A.elt_shift;
+                        s8_tma_load(d, &map_u, bar, cx, row, f);
+                        s8_tma_load(d + S8_ROWS * A.seg_c, &map_v, bar, cx, row, f);
                     } else {
                         s8_tma_load(d, &map_u, bar, a0c >> 1, row, f);
                     }
@@ -461,6 +540,12 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
         }
     };
 
+    /* The tensor-pipe variants are compiled without range conversion, 9..14-bit output and ordered dither (the
+     * host keeps those conversions on the dot-product variants): C4 pays 12 % in instructions for the checks. */
+    constexpr bool GEN = !MMA;
+    const S8Range rcl = { GEN ? A.range_mode : 0, A.lum_rc_coeff, A.lum_rc_offset };
+    const S8Range rcc = { GEN ? A.range_mode : 0, A.chr_rc_coeff, A.chr_rc_offset };
+
     /* ================= stage H, luma ================= */
     if (MMA) {
         /* warp = 16 output columns (two groups of 8), all 16 rows of a slot per pass: FS4 = K steps of 32 bytes */
@@ -483,8 +568,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             s8_wait(full_a + 8 * sb, sphase);
             const uint32_t base = ring_a + sb * slot;
             uint32_t wa, wb, wc, wd;
-            s8_mma_rows<FS4>(base + o0, b0, sel, wa, wb);
-            s8_mma_rows<FS4>(base + o1, b1, sel, wc, wd);
+            s8_mma_rows<FS4>(base + o0, b0, sel, rcl, wa, wb);
+            s8_mma_rows<FS4>(base + o1, b1, sel, rcl, wc, wd);
             if (left > 0) {
                 h00[0] = wa; h01[0] = wb; h10[0] = wc; h11[0] = wd;
             }
@@ -498,7 +583,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
         const int x = tid & (S8_TW - 1), g = tid >> 7;
         const int gx = min(x0 + x, A.dst_w - 1);
         const int off = __ldg(A.hl_pos + gx) - a0l;
-        const int sh = (off & 3) * 8;
+        const int sh = S16 ? (off & 1) * 16 : (off & 3) * 8;
         uint32_t cl[FS4], chh[FS4];
 #pragma unroll
         for (int k = 0; k < FS4; k++) {
@@ -506,7 +591,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             chh[k] = __ldg(A.hl_ch + (size_t)gx * FS4 + k);
         }
         const int seg = A.seg_l;
-        const int so = 2 * NP * g * seg + (off & ~3);
+        const int so = 2 * NP * g * seg + (S16 ? (off >> 1) * 4 : (off & ~3));
         /* RGB output: even columns in slots 0..63, odd columns in 64..127, so that a lane of the V stage
          * finds both pixels of its pair at a conflict-free stride */
         const int lslot = RGB ? (x >> 1) + 64 * (x & 1) : x;
@@ -518,8 +603,18 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
 #pragma unroll
             for (int m = 0; m < NP; m++) {
                 if (2 * m < left) {
-                    const int va = s8_hfir<FS4>(sp + (2 * m) * seg, sh, cl, chh);
-                    const int vb = s8_hfir<FS4>(sp + (2 * m + 1) * seg, sh, cl, chh);
+                    int va, vb;
+                    if (S16) {
+                        va = s16_hfir<FS4>(sp + (2 * m) * seg, sh, A.h_shift, cl, chh);
+                        vb = s16_hfir<FS4>(sp + (2 * m + 1) * seg, sh, A.h_shift, cl, chh);
+                    } else {
+                        va = s8_hfir<FS4>(sp + (2 * m) * seg, sh, cl, chh);
+                        vb = s8_hfir<FS4>(sp + (2 * m + 1) * seg, sh, cl, chh);
+                    }
+                    if (rcl.mode) {
+                        va = s8_range(va, rcl.mode, rcl.coeff, rcl.offset);
+                        vb = s8_range(vb, rcl.mode, rcl.coeff, rcl.offset);
+                    }
                     hp[m] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
                 }
             }
@@ -554,24 +649,24 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 const uint32_t base = ring_a + sb * slot;
                 uint32_t ua, ub, va, vb;
                 if (planar) {
-                    s8_mma_rows<FS4>(base + o0, b0, sel, ua, ub);
-                    s8_mma_rows<FS4>(base + S8_ROWS * A.seg_c + o0, b0, sel, va, vb);
+                    s8_mma_rows<FS4>(base + o0, b0, sel, rcc, ua, ub);
+                    s8_mma_rows<FS4>(base + S8_ROWS * A.seg_c + o0, b0, sel, rcc, va, vb);
                 } else if (vfirst) {
-                    s8_mma_rows_uv<FS4>(base + o0, b0, sel, va, vb, ua, ub);
+                    s8_mma_rows_uv<FS4>(base + o0, b0, sel, rcc, va, vb, ua, ub);
                 } else {
-                    s8_mma_rows_uv<FS4>(base + o0, b0, sel, ua, ub, va, vb);
+                    s8_mma_rows_uv<FS4>(base + o0, b0, sel, rcc, ua, ub, va, vb);
                 }
                 if (left > 0) {
                     hu[0] = ua; hu[cstride_w] = ub; hv[0] = va; hv[cstride_w] = vb;
                 }
                 if (ng == 2) {
                     if (planar) {
-                        s8_mma_rows<FS4>(base + o1, b1, sel, ua, ub);
-                        s8_mma_rows<FS4>(base + S8_ROWS * A.seg_c + o1, b1, sel, va, vb);
+                        s8_mma_rows<FS4>(base + o1, b1, sel, rcc, ua, ub);
+                        s8_mma_rows<FS4>(base + S8_ROWS * A.seg_c + o1, b1, sel, rcc, va, vb);
                     } else if (vfirst) {
-                        s8_mma_rows_uv<FS4>(base + o1, b1, sel, va, vb, ua, ub);
+                        s8_mma_rows_uv<FS4>(base + o1, b1, sel, rcc, va, vb, ua, ub);
                     } else {
-                        s8_mma_rows_uv<FS4>(base + o1, b1, sel, ua, ub, va, vb);
+                        s8_mma_rows_uv<FS4>(base + o1, b1, sel, rcc, ua, ub, va, vb);
                     }
                     if (left > 0) {
                         hu[8 * cstride_w] = ua; hu[9 * cstride_w] = ub; hv[8 * cstride_w] = va; hv[9 * cstride_w] = vb;
@@ -598,8 +693,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
         uint32_t *hpu = hb_u + x * cstride_w + npair * g;
         uint32_t *hpv = hb_v + x * cstride_w + npair * g;
         const int rowbytes = planar ? seg : 2 * seg;
-        const int so = 2 * npair * g * rowbytes + (planar ? (off & ~3) : ((2 * off) & ~3));
-        const int sh = planar ? (off & 3) * 8 : (off & 1) * 16;
+        const int so = 2 * npair * g * rowbytes + (S16 ? (off >> 1) * 4 : planar ? (off & ~3) : ((2 * off) & ~3));
+        const int sh = S16 ? (off & 1) * 16 : planar ? (off & 3) * 8 : (off & 1) * 16;
         int left = nc - 2 * npair * g;
         for (int qc = 0; qc < npc; qc++) {
             s8_wait(full_a + 8 * sb, sphase);
@@ -607,7 +702,12 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             for (int m = 0; m < npair; m++) {
                 if (2 * m < left) {
                     int ua, ub, va, vb;
-                    if (planar) {
+                    if (S16) {               /* planar 16-bit chroma */
+                        ua = s16_hfir<FS4>(sp, sh, A.h_shift, cl, chh);
+                        ub = s16_hfir<FS4>(sp + seg, sh, A.h_shift, cl, chh);
+                        va = s16_hfir<FS4>(sp + S8_ROWS * seg, sh, A.h_shift, cl, chh);
+                        vb = s16_hfir<FS4>(sp + (S8_ROWS + 1) * seg, sh, A.h_shift, cl, chh);
+                    } else if (planar) {
                         ua = s8_hfir<FS4>(sp, sh, cl, chh);
                         ub = s8_hfir<FS4>(sp + seg, sh, cl, chh);
                         va = s8_hfir<FS4>(sp + S8_ROWS * seg, sh, cl, chh);
@@ -619,6 +719,10 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                             int t = ua; ua = va; va = t;
                             t = ub; ub = vb; vb = t;
                         }
+                    }
+                    if (rcc.mode) {
+                        ua = s8_range(ua, rcc.mode, rcc.coeff, rcc.offset); ub = s8_range(ub, rcc.mode, rcc.coeff, rcc.offset);
+                        va = s8_range(va, rcc.mode, rcc.coeff, rcc.offset); vb = s8_range(vb, rcc.mode, rcc.coeff, rcc.offset);
                     }
                     hpu[m] = prmt((uint32_t)ua, (uint32_t)ub, 0x5410);
                     hpv[m] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
@@ -718,6 +822,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     }
 
     /* ================= stage V, luma: warp = row, lane = columns lane, lane+32, ... ================= */
+    const int obits = GEN ? A.out_bits : 8, oshift = 27 - obits;
+    const bool bayer = GEN && A.dither_bayer != 0;
     {
         S8VRow vr;
         if (warp < th)
@@ -729,13 +835,23 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 nx = s8_load_vrow(A.vl + y + 8);        /* next row's taps are in flight while this row is filtered */
             const int n4 = __shfl_sync(0xffffffffu, vr.n4, 0);     /* this row's own group count, warp-uniform */
             const uint32_t *hp = hb_l + lane * lstride_w + ((vr.pos_even - lo_l) >> 1);
-            uint8_t *d = dst0 + (size_t)y * A.dst_stride[0] + x0 + lane;
             int v[S8_TW / 32];
-            s8_vfir<S8_TW / 32>(hp, 32 * lstride_w, vr, n4, v);
+            s8_vsum<S8_TW / 32>(hp, 32 * lstride_w, vr, n4, 0, v);
+            if (obits == 8) {
+                uint8_t *d = dst0 + (size_t)y * A.dst_stride[0] + x0 + lane;
+                /* lane + 32 c == lane (mod 8): one dither value per lane and row */
+                const int dz = (bayer ? c_dither_8x8_128[y & 7][lane & 7] : 64) << 12;
 #pragma unroll
-            for (int c = 0; c < S8_TW / 32; c++)
-                if (lane + 32 * c < tw)
-                    d[32 * c] = (uint8_t)v[c];
+                for (int c = 0; c < S8_TW / 32; c++)
+                    if (lane + 32 * c < tw)
+                        d[32 * c] = (uint8_t)clip_u8((v[c] + dz) >> 19);
+            } else {                                   /* yuv2planeX_10_c_template / yuv2plane1_10 (output.c:340-357) */
+                uint16_t *d = reinterpret_cast<uint16_t *>(dst0 + (size_t)y * A.dst_stride[0]) + x0 + lane;
+#pragma unroll
+                for (int c = 0; c < S8_TW / 32; c++)
+                    if (lane + 32 * c < tw)
+                        d[32 * c] = (uint16_t)clip_uintp2((v[c] + (1 << (oshift - 1))) >> oshift, obits);
+            }
             vr = nx;
         }
     }
@@ -753,16 +869,30 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 nx = s8_load_vrow(A.vc + y + 4);
             const int n4 = __shfl_sync(0xffffffffu, vr.n4, 0);
             const uint32_t *hp = (pl ? hb_v : hb_u) + lane * cstride_w + ((vr.pos_even - lo_c) >> 1);
-            uint8_t *d = semi ? dst1 + (size_t)y * A.dst_stride[1] + 2 * (cx0 + lane) + (pl ^ first)
-                              : (pl ? dst2 : dst1) + (size_t)y * A.dst_stride[pl ? 2 : 1] + cx0 + lane;
-            const int dstep = semi ? 64 : 32;
-            for (int c = 0; 32 * c < CW; c += 2) {
-                int v[2];
-                s8_vfir<2>(hp + 32 * c * cstride_w, 32 * cstride_w, vr, n4, v);
-                if (lane + 32 * c < cw)
-                    d[dstep * c] = (uint8_t)v[0];
-                if (lane + 32 * c + 32 < cw)
-                    d[dstep * (c + 1)] = (uint8_t)v[1];
+            /* chroma dither: U reads column x, V column x + 3 of the row (swscale.c:519-522, output.c:468-528) */
+            const int dz = (bayer ? c_dither_8x8_128[y & 7][(cx0 + lane + 3 * pl) & 7] : 64) << 12;
+            if (obits == 8) {
+                uint8_t *d = semi ? dst1 + (size_t)y * A.dst_stride[1] + 2 * (cx0 + lane) + (pl ^ first)
+                                  : (pl ? dst2 : dst1) + (size_t)y * A.dst_stride[pl ? 2 : 1] + cx0 + lane;
+                const int dstep = semi ? 64 : 32;
+                for (int c = 0; 32 * c < CW; c += 2) {
+                    int v[2];
+                    s8_vsum<2>(hp + 32 * c * cstride_w, 32 * cstride_w, vr, n4, 0, v);
+                    if (lane + 32 * c < cw)
+                        d[dstep * c] = (uint8_t)clip_u8((v[0] + dz) >> 19);
+                    if (lane + 32 * c + 32 < cw)
+                        d[dstep * (c + 1)] = (uint8_t)clip_u8((v[1] + dz) >> 19);
+                }
+            } else {
+                uint16_t *d = reinterpret_cast<uint16_t *>((pl ? dst2 : dst1) + (size_t)y * A.dst_stride[pl ? 2 : 1]) + cx0 + lane;
+                for (int c = 0; 32 * c < CW; c += 2) {
+                    int v[2];
+                    s8_vsum<2>(hp + 32 * c * cstride_w, 32 * cstride_w, vr, n4, 0, v);
+                    if (lane + 32 * c < cw)
+                        d[32 * c] = (uint16_t)clip_uintp2((v[0] + (1 << (oshift - 1))) >> oshift, obits);
+                    if (lane + 32 * c + 32 < cw)
+                        d[32 * (c + 1)] = (uint16_t)clip_uintp2((v[1] + (1 << (oshift - 1))) >> oshift, obits);
+                }
             }
             vr = nx;
         }

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libswscale_b200.so")
+# SWS_B200_LIB: another build of the same library (A/B runs of tools/*.sh)
+SO_PATH = os.environ.get("SWS_B200_LIB") or os.path.join(_HERE, "libswscale_b200.so")
 
 # enum AVPixelFormat (values are ABI; reference libavutil/pixfmt.h)
 PIX_FMT = {

@@ -1,0 +1,95 @@
+"""The scaling kernel on 9..16-bit planar sources (sws_scale8_kernel<KS, RGB, MMA = false, S16 = true>:
+hScale16To15_c as IDP.2A over sample pairs, swscale.c:99-125), range conversion of the h-scaled lines
+(swscale.c:163-216) inside the kernel, and its 9..14-bit planar / dithered 8-bit writers
+(output.c:340-357,468-528): bit-exact against the real reference build, with the kernel that ran asserted."""
+import pytest
+
+from tests import sws_testlib as T
+from librempeg_b200 import swscale as S
+
+pytestmark = pytest.mark.gpu
+BX = S.SWS_BITEXACT | S.SWS_ACCURATE_RND
+
+GEOMS = [
+    ((640, 360, 320, 180), S.SWS_BICUBIC),       # 2:1, 8 taps
+    ((644, 366, 1288, 732), S.SWS_BICUBIC),      # 1:2 upscale, 4 taps, ragged tiles
+    ((1920, 1080, 480, 270), S.SWS_BICUBIC),     # 4:1, 16 taps
+    ((1280, 720, 642, 362), S.SWS_LANCZOS),      # 13 taps
+    ((322, 242, 400, 300), S.SWS_BILINEAR),
+    ((350, 130, 350, 260), S.SWS_BILINEAR),      # vertical only
+    ((64, 48, 24, 20), S.SWS_AREA),              # tiles narrower than one warp row
+    ((3000, 64, 400, 64), S.SWS_BILINEAR),       # 7.5:1: rows beyond 1 KB, 64-bit TMA elements
+]
+
+
+def _sub(fmt):
+    return (1, 1) if "420" in fmt or fmt.startswith("nv") else (1, 0) if "422" in fmt else (0, 0)
+
+
+def _run(case, seed=71, mode="noise", **kw):
+    src = T.Frame(case["sf"], case["sw"], case["sh"]).randomize(seed, mode)
+    want, _ = T.run_reference(src=src, **case, **kw)
+    got, name = T.run_cuda(src=src, **case, **kw)
+    assert T.first_diff(got.valid(), want.valid()) is None, (name, case)
+    return name
+
+
+@pytest.mark.parametrize("sf", ["yuv420p10le", "yuv422p10le", "yuv444p12le", "yuv420p9le", "yuv420p14le", "yuv420p16le"])
+@pytest.mark.parametrize("df", ["yuv420p10le", "yuv420p", "yuv444p12le", "nv12", "yuv422p9le", "yuv420p14le"])
+@pytest.mark.parametrize("geom,flags", GEOMS)
+def test_high_depth_sources(sf, df, geom, flags):
+    sw, sh, dw, dh = geom
+    case = dict(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags | BX)
+    # a less subsampled source doubles the chroma ratio: its filter can exceed the kernel's 16 taps, and the conversion
+    # then stays on the general kernels; with equal subsampling every geometry above fits
+    for mode in ("noise", "extreme"):
+        name = _run(case, mode=mode)
+        if _sub(sf) == _sub(df) and sw <= 7 * dw:      # (7.5:1 rows of 4:4:4 samples exceed the 2 KB TMA box row)
+            assert name == "scale16_dp2a", name
+
+
+@pytest.mark.parametrize("sf", ["yuv420p10le", "yuv422p12le", "yuv420p16le"])
+@pytest.mark.parametrize("df", ["rgb24", "bgra", "abgr"])
+@pytest.mark.parametrize("geom,flags", GEOMS[:5])
+def test_high_depth_to_packed_rgb(sf, df, geom, flags):
+    sw, sh, dw, dh = geom
+    name = _run(dict(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags | BX))
+    assert name == "scale16_dp2a", name
+
+
+@pytest.mark.parametrize("sf,df", [("yuvj420p", "yuv420p"), ("yuv420p", "yuvj420p"), ("yuv420p10le", "yuvj420p"),
+                                   ("yuvj422p", "yuv420p10le"), ("nv12", "yuvj444p"), ("yuv444p16le", "yuvj420p"),
+                                   ("yuvj420p", "nv21"), ("yuv420p12le", "yuv420p12le")])
+@pytest.mark.parametrize("geom,flags", GEOMS[:6])
+@pytest.mark.parametrize("ranges", [(0, 1), (1, 0)])
+def test_range_conversion_inside_the_scaler(sf, df, geom, flags, ranges):
+    """lum/chrRangeToJpeg_c and FromJpeg_c between the two FIR stages, both kernels' horizontal stages."""
+    sw, sh, dw, dh = geom
+    case = dict(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags | BX)
+    name = _run(case, ctx_kwargs=dict(src_range=ranges[0], dst_range=ranges[1]))
+    if _sub(sf) == _sub(df):
+        assert name.startswith("scale8") or name == "scale16_dp2a", name
+
+
+@pytest.mark.parametrize("sf", ["yuv420p", "nv12", "yuv422p"])
+@pytest.mark.parametrize("df", ["yuv420p10le", "yuv444p12le", "yuv422p9le"])
+@pytest.mark.parametrize("geom,flags", GEOMS[:5])
+def test_8bit_sources_to_high_depth_planar(sf, df, geom, flags):
+    sw, sh, dw, dh = geom
+    name = _run(dict(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags | BX))
+    if _sub(sf) == _sub(df):
+        assert name.startswith("scale8"), name
+
+
+def test_high_depth_slices_and_strides():
+    case = dict(sw=644, sh=366, sf="yuv420p10le", dw=400, dh=222, df="yuv420p10le", flags=S.SWS_BICUBIC | BX)
+    src = T.Frame("yuv420p10le", 644, 366, pad=16).randomize(5)
+    slices = [(y, min(64, 366 - y)) for y in range(0, 366, 64)]
+    want, _ = T.run_reference(src=src, slices=slices, dst_pad=6, **case)
+    got, name = T.run_cuda(src=src, slices=slices, dst_pad=6, **case)
+    assert T.first_diff(got.valid(), want.valid()) is None, name
+
+
+def test_4k_10bit_downscale_full_size():
+    case = dict(sw=3840, sh=2160, sf="yuv420p10le", dw=1920, dh=1080, df="yuv420p10le", flags=S.SWS_BICUBIC | BX)
+    assert _run(case) == "scale16_dp2a"

@@ -50,6 +50,9 @@ CONFIGS = [
     ("D2 4K yuv420p10le->p010le (planar to p010)", 3840, 2160, "yuv420p10le", 3840, 2160, "p010le", S.SWS_BICUBIC | S.BX),
     ("X1 1080p->4K yuv420p->rgb24 bicubic", 1920, 1080, "yuv420p", 3840, 2160, "rgb24", S.SWS_BICUBIC | S.BX),
     ("X2 4K->1080p yuv420p->yuv420p bicubic", 3840, 2160, "yuv420p", 1920, 1080, "yuv420p", S.SWS_BICUBIC | S.BX),
+    ("X3 4K->1080p yuv420p10le->yuv420p10le bicubic", 3840, 2160, "yuv420p10le", 1920, 1080, "yuv420p10le", S.SWS_BICUBIC | S.BX),
+    ("X4 4K->1080p yuv420p10le->yuv420p bicubic", 3840, 2160, "yuv420p10le", 1920, 1080, "yuv420p", S.SWS_BICUBIC | S.BX),
+    ("X5 1080p yuvj420p->720p yuv420p bicubic (range)", 1920, 1080, "yuvj420p", 1280, 720, "yuv420p", S.SWS_BICUBIC | S.BX),
 ]
 
 
