@@ -1567,7 +1567,7 @@ struct SwsCudaState {
     int fast_narrow;             /* the 128 x 64 tile shape of the fast420 kernel is set up and preferred */
     int4 *d_fast_rows_narrow;
     int fasthi8_ok, fasthi8_crows;
-    int s8_stages, s8_s16, s8_elt_shift;
+    int s8_stages, s8_srck, s8_elt_shift, s8_seg_sy, s8_seg_sc;
     int s8_ok, s8_fs4, s8_tile_h, s8_nl_cap, s8_nc_cap, s8_seg_l, s8_seg_c, s8_slot, s8_vl_n4, s8_vc_n4;
     size_t s8_smem;
     void *s8_tables;
@@ -2235,27 +2235,34 @@ static int fasthi8_launch(SwsCudaState *st, const uint8_t *const src[4], const i
 /* ---------------------------------------------------------------- scale8 host side */
 
 typedef void (*scale8_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Scale8Args);
-static scale8_kernel_t pick_scale8(int fs4, bool rgb, bool mma, bool s16)
+static scale8_kernel_t pick_scale8(int fs4, bool rgb, bool mma, int srck)
 {
-    if (s16) {          /* 9..16-bit planar sources: IDP.2A horizontal stage */
+    if (srck == S8_SRC_RGB) {   /* packed 8-bit RGB sources: reader stage + IDP.2A horizontal stage */
         if (rgb)
-            return fs4 == 1 ? sws_scale8_kernel<1, true, false, true> : fs4 == 2 ? sws_scale8_kernel<2, true, false, true>
-                                                                                 : sws_scale8_kernel<4, true, false, true>;
-        return fs4 == 1 ? sws_scale8_kernel<1, false, false, true> : fs4 == 2 ? sws_scale8_kernel<2, false, false, true>
-                                                                              : sws_scale8_kernel<4, false, false, true>;
+            return fs4 == 1 ? sws_scale8_kernel<1, true, false, S8_SRC_RGB> : fs4 == 2 ? sws_scale8_kernel<2, true, false, S8_SRC_RGB>
+                                                                                       : sws_scale8_kernel<4, true, false, S8_SRC_RGB>;
+        return fs4 == 1 ? sws_scale8_kernel<1, false, false, S8_SRC_RGB> : fs4 == 2 ? sws_scale8_kernel<2, false, false, S8_SRC_RGB>
+                                                                                    : sws_scale8_kernel<4, false, false, S8_SRC_RGB>;
+    }
+    if (srck == S8_SRC_U16) {   /* 9..16-bit planar sources: IDP.2A horizontal stage */
+        if (rgb)
+            return fs4 == 1 ? sws_scale8_kernel<1, true, false, S8_SRC_U16> : fs4 == 2 ? sws_scale8_kernel<2, true, false, S8_SRC_U16>
+                                                                                       : sws_scale8_kernel<4, true, false, S8_SRC_U16>;
+        return fs4 == 1 ? sws_scale8_kernel<1, false, false, S8_SRC_U16> : fs4 == 2 ? sws_scale8_kernel<2, false, false, S8_SRC_U16>
+                                                                                    : sws_scale8_kernel<4, false, false, S8_SRC_U16>;
     }
     if (mma) {          /* fs4 = K steps of the tensor-pipe horizontal stage */
         if (rgb)
-            return fs4 == 1 ? sws_scale8_kernel<1, true, true, false> : fs4 == 2 ? sws_scale8_kernel<2, true, true, false>
-                                                                                 : sws_scale8_kernel<4, true, true, false>;
-        return fs4 == 1 ? sws_scale8_kernel<1, false, true, false> : fs4 == 2 ? sws_scale8_kernel<2, false, true, false>
-                                                                              : sws_scale8_kernel<4, false, true, false>;
+            return fs4 == 1 ? sws_scale8_kernel<1, true, true, S8_SRC_U8> : fs4 == 2 ? sws_scale8_kernel<2, true, true, S8_SRC_U8>
+                                                                                 : sws_scale8_kernel<4, true, true, S8_SRC_U8>;
+        return fs4 == 1 ? sws_scale8_kernel<1, false, true, S8_SRC_U8> : fs4 == 2 ? sws_scale8_kernel<2, false, true, S8_SRC_U8>
+                                                                              : sws_scale8_kernel<4, false, true, S8_SRC_U8>;
     }
     if (rgb)
-        return fs4 == 1 ? sws_scale8_kernel<1, true, false, false> : fs4 == 2 ? sws_scale8_kernel<2, true, false, false>
-                                                                              : sws_scale8_kernel<4, true, false, false>;
-    return fs4 == 1 ? sws_scale8_kernel<1, false, false, false> : fs4 == 2 ? sws_scale8_kernel<2, false, false, false>
-                                                                           : sws_scale8_kernel<4, false, false, false>;
+        return fs4 == 1 ? sws_scale8_kernel<1, true, false, S8_SRC_U8> : fs4 == 2 ? sws_scale8_kernel<2, true, false, S8_SRC_U8>
+                                                                              : sws_scale8_kernel<4, true, false, S8_SRC_U8>;
+    return fs4 == 1 ? sws_scale8_kernel<1, false, false, S8_SRC_U8> : fs4 == 2 ? sws_scale8_kernel<2, false, false, S8_SRC_U8>
+                                                                           : sws_scale8_kernel<4, false, false, S8_SRC_U8>;
 }
 
 /* ---- tensor-pipe horizontal stage: per group of 8 output columns, the K window and the banded B fragments ----
@@ -2452,15 +2459,71 @@ static int s16_seg_bytes(const SwsFirBank *b, int fs4, int tile_cols)
     return worst;
 }
 
+static bool rgb420_matrix_ok(const SwsCudaPlan *p);
+static bool rgb444_matrix_ok(const SwsCudaPlan *p);
+
+/* packed RGB sources: bytes of raw row a tile stages (first pixel = the lower of both banks' first reads, rounded down to
+ * 16 pixels), and the bytes per row of the luma / chroma sample buffers the horizontal stage reads (2 fs4 + 1 words from
+ * every column's even first sample).  Returns -1 when a bank is not monotonic. */
+static int s8_rgb_segs(const SwsFirBank *hl, const SwsFirBank *hc, int hs, int half, int bpp, int fs4, int *seg_raw,
+                       int *seg_sy, int *seg_sc)
+{
+    int raw = 16, sy = 16, sc = 16;
+    const int cw = S8_TW >> hs;
+    for (int x0 = 0, cx0 = 0; x0 < hl->len; x0 += S8_TW, cx0 += cw) {
+        const int x1 = x0 + S8_TW < hl->len ? x0 + S8_TW : hl->len;
+        const int c1 = cx0 + cw < hc->len ? cx0 + cw : hc->len;
+        int a0 = hl->pos[x0];
+        if (cx0 < hc->len && (hc->pos[cx0] << half) < a0)
+            a0 = hc->pos[cx0] << half;
+        a0 &= ~15;
+        int end = 0;
+        for (int x = x0; x < x1; x++) {
+            if (hl->pos[x] < hl->pos[x0])
+                return -1;
+            const int off = hl->pos[x] - a0;
+            if (hl->pos[x] + hl->size > end) end = hl->pos[x] + hl->size;
+            const int need = ((off >> 1) + 2 * fs4 + 1) * 4;
+            if (need > sy) sy = need;
+        }
+        for (int x = cx0; x < c1; x++) {
+            if (hc->pos[x] < hc->pos[cx0])
+                return -1;
+            const int off = hc->pos[x] - (a0 >> half);
+            if (((hc->pos[x] + hc->size) << half) > end) end = (hc->pos[x] + hc->size) << half;
+            const int need = ((off >> 1) + 2 * fs4 + 1) * 4;
+            if (need > sc) sc = need;
+        }
+        const int bytes = (end - a0) * bpp;
+        if (bytes > raw) raw = bytes;
+    }
+    const int unit = bpp == 3 ? 48 : 16;
+    raw = (raw + unit - 1) / unit * unit;
+    const int npx = raw / bpp;                  /* pixels the reader converts per row: a multiple of four */
+    if (2 * npx > sy) sy = 2 * npx;
+    if (2 * (npx >> half) > sc) sc = 2 * (npx >> half);
+    *seg_raw = raw;
+    *seg_sy = (sy + 15) & ~15;
+    *seg_sc = (sc + 15) & ~15;
+    return 0;
+}
+
 static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank *hc,
                         const SwsFirBank *vl, const SwsFirBank *vc)
 {
     const SwsCudaPlan *p = &st->plan;
     st->s8_ok = 0;
-    if (p->inter_bits != 15 || p->src_layout > SWSC_SRC_NV21 || p->src_alpha || p->dst_alpha)
+    const bool rgbs = p->src_layout == SWSC_SRC_RGB;
+    if (p->inter_bits != 15 || (p->src_layout > SWSC_SRC_NV21 && !rgbs) || p->src_alpha || p->dst_alpha)
+        return 0;
+    /* packed 8-bit RGB sources: samples the readers keep inside 14 bits (checked again at every launch: the matrix can
+     * change), luma and chroma out of the same rows */
+    if (rgbs && (p->h_shift != 13 || p->chr_src_h != p->src_h || (p->src_bpp != 3 && p->src_bpp != 4) ||
+                 !(p->src_rgb_half ? rgb420_matrix_ok(p) : rgb444_matrix_ok(p))))
         return 0;
     /* sources: 8-bit planar / nv12 / nv21, or 9..16-bit little-endian planar (hScale16To15_c) */
-    const bool s16 = p->src_bits > 8;
+    const bool s16 = !rgbs && p->src_bits > 8;
+    const int srck = rgbs ? S8_SRC_RGB : s16 ? S8_SRC_U16 : S8_SRC_U8;
     if (s16 && (p->src_layout != SWSC_SRC_PLANAR || p->src_shift || p->src_bits > 16))
         return 0;
     /* destinations: 8-bit planar / semi-planar YUV, 9..14-bit planar YUV, or packed 8-bit RGB with one chroma
@@ -2498,11 +2561,17 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     }
     int seg_l = ret ? -1 : s16 ? s16_seg_bytes(hl, fs4, S8_TW) : s8_seg_bytes(hl, fs4, S8_TW);
     int seg_c = ret ? -1 : s16 ? s16_seg_bytes(hc, fs4, cw) : s8_seg_bytes(hc, fs4, cw);
+    int seg_sy = 0, seg_sc = 0;
+    if (!ret && rgbs) {
+        if (s8_rgb_segs(hl, hc, p->chr_dst_hsub, p->src_rgb_half, p->src_bpp, fs4, &seg_l, &seg_sy, &seg_sc) < 0)
+            seg_l = -1;
+        seg_c = 0;
+    }
     /* tensor-pipe horizontal stage when every 8-column window fits K <= 128 samples (SWS_B200_DISABLE=s8mma: A/B) */
     const bool inter = p->src_layout != SWSC_SRC_PLANAR;
     int mma = 0, ks = 0;
     const bool plain = !p->range_mode && p->dst_kind != SWSC_DST_PLANARN;       /* what the MMA variants are compiled for */
-    if (!ret && !s16 && plain && seg_l >= 0 && seg_c >= 0 &&
+    if (!ret && !s16 && !rgbs && plain && seg_l >= 0 && seg_c >= 0 &&
         !(getenv("SWS_B200_DISABLE") && strstr(getenv("SWS_B200_DISABLE"), "s8mma"))) {
         const int kl = s8_mma_ksteps(hl, S8_TW, false), kc = s8_mma_ksteps(hc, cw, inter);
         ks = kl > kc ? kl : kc;
@@ -2546,25 +2615,41 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
         const int st_max = st_env && atoi(st_env) >= 2 && atoi(st_env) <= S8_MAX_STAGES ? atoi(st_env) : S8_STAGES;
         if (kb_env && atoi(kb_env) >= 32 && atoi(kb_env) <= 200)
             budget[0] = budget[1] = (size_t)atoi(kb_env) * 1024;
-        for (int pass = 0; pass < 2 && ret; pass++)
-            for (th = th_max; th >= 2; th >>= 1) {
-                const int cth = th >> p->chr_dst_vsub ? th >> p->chr_dst_vsub : 1;
-                nl_cap = s8_rows_cap(hvl, vl->len, th);
-                nc_cap = s8_rows_cap(hvc, vc->len, cth);
-                slot = (S8_ROWS * (seg_l > 2 * seg_c ? seg_l : 2 * seg_c) + 127) & ~127;
-                if (slot > 48 * 1024)
-                    break;
-                if (rgb && S8_STAGES * slot < 8 * 512)
-                    slot = 8 * 512 / S8_STAGES;       /* the idle ring stages the packed RGB rows of the 8 warps */
-                const size_t lines = ((size_t)S8_TW * nl_cap + 2 * (size_t)cw * nc_cap) * 2;
-                if (lines + 2 * (size_t)slot <= budget[pass]) {
-                    stages = (int)((budget[pass] - lines) / slot);
-                    if (stages > st_max) stages = st_max;
-                    smem = lines + (size_t)stages * slot;
-                    ret = 0;
-                    break;
+        /* Every (CTAs per SM, tile height) pair that fits is a candidate; the cost of one is the h-scaled samples it
+         * computes per output row (the rows of vertical halo are recomputed by the neighbouring tile), with 10 % added
+         * for running two CTAs per SM instead of three.  Conversions whose staging is small (every BASELINE
+         * configuration) end up with 32-row tiles at three CTAs as before; wide raw rows (packed RGB sources) trade
+         * occupancy for taller tiles instead of shrinking to 8 rows. */
+        budget[1] = kb_env ? budget[1] : 112 * 1024;
+        double best = 0;
+        int best_th = 0, best_pass = 0;
+        slot = (S8_ROWS * (seg_l > 2 * seg_c ? seg_l : 2 * seg_c) + 127) & ~127;
+        if (rgb && S8_STAGES * slot < 8 * 512)
+            slot = 8 * 512 / S8_STAGES;               /* the idle ring stages the packed RGB rows of the 8 warps */
+        for (int pass = 0; pass < 2 && slot <= 48 * 1024; pass++)
+            for (int t = th_max; t >= 2; t >>= 1) {
+                const int cth = t >> p->chr_dst_vsub ? t >> p->chr_dst_vsub : 1;
+                const int nl = s8_rows_cap(hvl, vl->len, t), nc = s8_rows_cap(hvc, vc->len, cth);
+                const size_t lines = ((size_t)S8_TW * nl + 2 * (size_t)cw * nc) * 2 +
+                                     (size_t)S8_ROWS * (seg_sy + 2 * seg_sc);     /* + the RGB readers' sample rows */
+                if (lines + 2 * (size_t)slot > budget[pass])
+                    continue;
+                const double cost = ((double)S8_TW * nl + 2.0 * cw * nc) / t * (pass ? 1.1 : 1.0);
+                if (!best_th || cost < best) {
+                    best = cost; best_th = t; best_pass = pass;
                 }
             }
+        if (best_th) {
+            th = best_th;
+            const int cth = th >> p->chr_dst_vsub ? th >> p->chr_dst_vsub : 1;
+            nl_cap = s8_rows_cap(hvl, vl->len, th);
+            nc_cap = s8_rows_cap(hvc, vc->len, cth);
+            const size_t lines = ((size_t)S8_TW * nl_cap + 2 * (size_t)cw * nc_cap) * 2 + (size_t)S8_ROWS * (seg_sy + 2 * seg_sc);
+            stages = (int)((budget[best_pass] - lines) / slot);
+            if (stages > st_max) stages = st_max;
+            smem = lines + (size_t)stages * slot;
+            ret = 0;
+        }
     }
     if (ret) {
         free(hvl); free(hvc);
@@ -2615,19 +2700,20 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     st->s8_hc_cl = (uint32_t *)(t + o_hccl); st->s8_hc_ch = (uint32_t *)(t + o_hcch);
     st->s8_vl = (S8VRow *)(t + o_vl); st->s8_vc = (S8VRow *)(t + o_vc);
     st->s8_fs4 = mma ? ks : fs4; st->s8_tile_h = th; st->s8_nl_cap = nl_cap; st->s8_nc_cap = nc_cap;
-    st->s8_seg_l = seg_l; st->s8_seg_c = seg_c; st->s8_smem = smem; st->s8_slot = slot; st->s8_stages = stages; st->s8_s16 = s16; st->s8_elt_shift = elt_shift;
+    st->s8_seg_l = seg_l; st->s8_seg_c = seg_c; st->s8_smem = smem; st->s8_slot = slot; st->s8_stages = stages; st->s8_srck = srck; st->s8_elt_shift = elt_shift;
+    st->s8_seg_sy = seg_sy; st->s8_seg_sc = seg_sc;
     st->s8_mma = mma;
     if (mma) {
         st->s8_hl_goff = (int *)(t + o_gl); st->s8_hc_goff = (int *)(t + o_gc);
         st->s8_hl_B = (uint32_t *)(t + o_bl); st->s8_hc_B = (uint32_t *)(t + o_bc);
     }
-    CUDA_OK(set_max_smem((const void *)pick_scale8(st->s8_fs4, rgb, mma, s16), (size_t)((int)smem)));
+    CUDA_OK(set_max_smem((const void *)pick_scale8(st->s8_fs4, rgb, mma, srck), (size_t)((int)smem)));
     st->s8_ok = 1;
     if (getenv("SWS_B200_DEBUG"))
         fprintf(stderr, "[swscaler-b200] scale8: %s fs4=%d tile_h=%d nl_cap=%d nc_cap=%d seg_l=%d seg_c=%d slot=%d stages=%d smem=%zu\n",
-                s16 ? "dp2a16" : mma ? "mma" : "dp4a", st->s8_fs4, th, nl_cap, nc_cap, seg_l, seg_c, slot, stages, smem);
+                rgbs ? "rgb" : s16 ? "dp2a16" : mma ? "mma" : "dp4a", st->s8_fs4, th, nl_cap, nc_cap, seg_l, seg_c, slot, stages, smem);
     if (!st->fast_ok && !st->fast16_ok)
-        st->kernel_name = s16 ? "scale16_dp2a" : mma ? "scale8_mma" : "scale8_dp4a";
+        st->kernel_name = rgbs ? "scale_rgb_dp2a" : s16 ? "scale16_dp2a" : mma ? "scale8_mma" : "scale8_dp4a";
     return 0;
 }
 
@@ -2640,7 +2726,10 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     /* a range change after init (sws_setColorspaceDetails) finds the tensor-pipe variant compiled without it */
     if (!st->s8_ok || (st->disabled & 4) || (st->s8_mma && p->range_mode))
         return 0;
-    const int nsrc = p->src_layout == SWSC_SRC_PLANAR ? 3 : 2;
+    const bool rgbs = st->s8_srck == S8_SRC_RGB;
+    if (rgbs && !(p->src_rgb_half ? rgb420_matrix_ok(p) : rgb444_matrix_ok(p)))
+        return 0;                     /* sws_setColorspaceDetails() installed a matrix the 14-bit readers cannot take */
+    const int nsrc = rgbs ? 1 : p->src_layout == SWSC_SRC_PLANAR ? 3 : 2;
     for (int i = 0; i < nsrc; i++)
         if (!src[i] || !aligned16(src[i]) || (src_stride[i] & 15) || src_stride[i] < 16 ||
             (nb_frames > 1 && (src_fstride[i] & 15)))
@@ -2648,22 +2737,24 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     /* source planes as tensors of 4- or 8-byte elements {row elements, rows, frames}: a ring slot is one box of S8_ROWS rows */
     CUtensorMap my, mu, mv;
     const bool planar = p->src_layout == SWSC_SRC_PLANAR;
-    const int es = st->s8_elt_shift, bps = st->s8_s16 ? 1 : 0;
+    const int es = st->s8_elt_shift, bps = st->s8_srck == S8_SRC_U16 ? 1 : 0;
     const CUtensorMapDataType edt = es == 3 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
     const uint64_t emask = (1u << es) - 1;
     const uint64_t fs_y = nb_frames > 1 ? src_fstride[0] : (uint64_t)src_stride[0] * p->src_h;
     const uint64_t fs_u = nb_frames > 1 ? src_fstride[1] : (uint64_t)src_stride[1] * p->chr_src_h;
-    const uint64_t ybytes = (uint64_t)p->src_w << bps;
+    const uint64_t ybytes = rgbs ? (uint64_t)p->src_w * p->src_bpp : (uint64_t)p->src_w << bps;
     const uint64_t cbytes = (planar ? (uint64_t)p->chr_src_w : 2 * (uint64_t)p->chr_src_w) << bps;
     int ret;
     if ((ret = make_map_3d(&my, edt, src[0], (ybytes + emask) >> es, p->src_h,
-                           nb_frames, src_stride[0], fs_y, st->s8_seg_l >> es, S8_ROWS)) < 0 ||
-        (ret = make_map_3d(&mu, edt, src[1], (cbytes + emask) >> es, p->chr_src_h,
-                           nb_frames, src_stride[1], fs_u, (planar ? st->s8_seg_c : 2 * st->s8_seg_c) >> es,
-                           S8_ROWS)) < 0)
+                           nb_frames, src_stride[0], fs_y, st->s8_seg_l >> es, S8_ROWS)) < 0)
+        return ret;
+    mu = my;
+    if (!rgbs && (ret = make_map_3d(&mu, edt, src[1], (cbytes + emask) >> es, p->chr_src_h,
+                                    nb_frames, src_stride[1], fs_u, (planar ? st->s8_seg_c : 2 * st->s8_seg_c) >> es,
+                                    S8_ROWS)) < 0)
         return ret;
     mv = mu;
-    if (planar) {
+    if (planar && !rgbs) {
         const uint64_t fs_v = nb_frames > 1 ? src_fstride[2] : (uint64_t)src_stride[2] * p->chr_src_h;
         if ((ret = make_map_3d(&mv, edt, src[2], (cbytes + emask) >> es, p->chr_src_h,
                                nb_frames, src_stride[2], fs_v, st->s8_seg_c >> es, S8_ROWS)) < 0)
@@ -2689,6 +2780,19 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.lum_rc_coeff = (int)p->lum_rc_coeff; a.lum_rc_offset = (int)p->lum_rc_offset;
     a.chr_rc_coeff = (int)p->chr_rc_coeff; a.chr_rc_offset = (int)p->chr_rc_offset;
     a.out_bits = p->dst_kind == SWSC_DST_PLANARN ? p->dst_bits : 8;
+    if (rgbs) {
+        /* matrix rows as 16-bit pairs in the byte order of a pixel word (unused bytes get a zero coefficient) */
+        int ky[4] = { 0, 0, 0, 0 }, ku[4] = { 0, 0, 0, 0 }, kv[4] = { 0, 0, 0, 0 };
+        ky[p->src_ro] = p->rgb2yuv[0]; ky[p->src_go] = p->rgb2yuv[1]; ky[p->src_bo] = p->rgb2yuv[2];
+        ku[p->src_ro] = p->rgb2yuv[3]; ku[p->src_go] = p->rgb2yuv[4]; ku[p->src_bo] = p->rgb2yuv[5];
+        kv[p->src_ro] = p->rgb2yuv[6]; kv[p->src_go] = p->rgb2yuv[7]; kv[p->src_bo] = p->rgb2yuv[8];
+        auto pair = [](int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); };
+        a.ylo = pair(ky[0], ky[1]); a.yhi = pair(ky[2], ky[3]);
+        a.ulo = pair(ku[0], ku[1]); a.uhi = pair(ku[2], ku[3]);
+        a.vlo = pair(kv[0], kv[1]); a.vhi = pair(kv[2], kv[3]);
+        a.src_bpp = p->src_bpp; a.rgb_half = p->src_rgb_half;
+        a.seg_sy = st->s8_seg_sy; a.seg_sc = st->s8_seg_sc;
+    }
     a.dither_bayer = p->dither_bayer;
     a.vl_n4 = st->s8_vl_n4; a.vc_n4 = st->s8_vc_n4;
     a.cy = p->rgb.cy; a.yb = p->rgb.yb; a.base_r = p->rgb.base_r; a.base_g = p->rgb.base_g; a.base_b = p->rgb.base_b;
@@ -2699,8 +2803,8 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.vl = st->s8_vl; a.vc = st->s8_vc;
     a.hl_goff = st->s8_hl_goff; a.hc_goff = st->s8_hc_goff; a.hl_B = st->s8_hl_B; a.hc_B = st->s8_hc_B;
     dim3 grid((p->dst_w + S8_TW - 1) / S8_TW, (y1 - y0 + st->s8_tile_h - 1) / st->s8_tile_h, nb_frames);
-    pick_scale8(st->s8_fs4, rgb, st->s8_mma, st->s8_s16)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
-    st->kernel_name = st->s8_s16 ? "scale16_dp2a" : st->s8_mma ? "scale8_mma" : "scale8_dp4a";
+    pick_scale8(st->s8_fs4, rgb, st->s8_mma, st->s8_srck)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
+    st->kernel_name = rgbs ? "scale_rgb_dp2a" : st->s8_srck == S8_SRC_U16 ? "scale16_dp2a" : st->s8_mma ? "scale8_mma" : "scale8_dp4a";
     CUDA_OK(cudaGetLastError());
     st->launches++;
     return 1;

@@ -48,6 +48,7 @@
 #define S8_RGB_CTAS 4     /* CTAs per SM the packed-RGB variant is compiled for (register budget of its V + colour stage) */
 #endif
 #define S8_VF4 5         /* vertical taps: up to 5 groups of 4 (16 taps + parity pad) */
+enum { S8_SRC_U8 = 0, S8_SRC_U16 = 1, S8_SRC_RGB = 2 };
 
 struct S8VRow {          /* per destination row, 48 bytes */
     int pos_even;        /* first source row, rounded down to even; luma bank, RGB output: bit 0 = this row takes
@@ -76,6 +77,10 @@ struct Scale8Args {
     int h_shift;             /* 16-bit sources: right shift after the horizontal FIR (depth - 1, swscale.c:99-125) */
     int range_mode;          /* 0 none, 1 to full range, 2 to limited range (swscale.c:163-216), on the h-scaled lines */
     int lum_rc_coeff, lum_rc_offset, chr_rc_coeff, chr_rc_offset;
+    /* packed 8-bit RGB sources: bytes per pixel, chroma from summed pixel pairs (the *_half readers), the matrix rows
+     * as 16-bit pairs in the byte order of a pixel word, bytes per row of the luma / chroma sample buffers */
+    int src_bpp, rgb_half, seg_sy, seg_sc;
+    uint32_t ylo, yhi, ulo, uhi, vlo, vhi;
     int out_bits;            /* planar destinations: 8, or 9..14 (16-bit little-endian samples) */
     int dither_bayer;        /* 8-bit planar output of > 8-bit sources: ff_dither_8x8_128 instead of the constant 64 */
     const int *hl_pos, *hc_pos;
@@ -425,11 +430,13 @@ __device__ __forceinline__ void s8_hfir_uv(const unsigned char *srow, int sh, co
  *           de-interleaved on the fly).
  *  V:       warp = output row, lane = columns lane + 32k.
  */
-template <int FS4, bool RGB, bool MMA, bool S16>
-__global__ void __launch_bounds__(S8_THREADS, (S16 || (MMA && FS4 > 2)) ? 3 : (RGB || FS4 <= S8_LIGHT_FS4) ? S8_RGB_CTAS : 3)
+template <int FS4, bool RGB, bool MMA, int SRCK>
+__global__ void __launch_bounds__(S8_THREADS, (SRCK != S8_SRC_U8 || (MMA && FS4 > 2)) ? 3 : (RGB || FS4 <= S8_LIGHT_FS4) ? S8_RGB_CTAS : 3)
 sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_u,
                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ Scale8Args A)
 {
+    constexpr bool S16 = SRCK == S8_SRC_U16;      /* 16-bit samples straight from the ring */
+    constexpr bool RGBS = SRCK == S8_SRC_RGB;     /* packed 8-bit RGB rows in the ring, converted to 14-bit Y/U/V samples per slot */
     extern __shared__ __align__(128) unsigned char s8_smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[S8_MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[S8_MAX_STAGES];
@@ -482,6 +489,21 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     const int a0c = ch > 0 ? __ldg(A.hc_pos + cx0) & ~(15 >> A.bps) : 0;
     const bool planar = A.src_layout == SWSC_SRC_PLANAR;
     const uint32_t ring_a = smem_u32(s8_smem_raw), full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+    /* packed RGB: luma and chroma come out of the same rows (no vertical subsampling), so ONE window of raw rows is
+     * streamed: the union of both row windows (both start on even rows), from the first pixel either bank reads */
+    int a0r = 0, lo_r = 0, npr = 0;
+    if (RGBS) {
+        a0r = __ldg(A.hl_pos + x0);
+        lo_r = lo_l;
+        int hi_r = lo_l + nl;
+        if (ch > 0) {
+            a0r = min(a0r, __ldg(A.hc_pos + cx0) << A.rgb_half);
+            lo_r = min(lo_l, lo_c);
+            hi_r = max(hi_r, lo_c + nc);
+        }
+        a0r &= ~15;
+        npr = (hi_r - lo_r + S8_ROWS - 1) / S8_ROWS;
+    }
     __syncthreads();
 
     if (warp == 8) {
@@ -489,11 +511,14 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
         if (lane == 0) {
             int b = 0;
             uint32_t par = 1;              /* parity of the previous use of slot b */
-            for (int q = 0; q < npl + npc; q++) {
+            for (int q = 0; q < (RGBS ? npr : npl + npc); q++) {
                 if (q >= A.stages)
                     s8_wait(empty_a + 8 * b, par);          /* all 8 warps released the slot */
                 const uint32_t d = ring_a + b * slot, bar = full_a + 8 * b;
-                if (q < npl) {
+                if (RGBS) {
+                    s8_expect_tx(bar, S8_ROWS * A.seg_l);
+                    s8_tma_load(d, &map_y, bar, (a0r * A.src_bpp) >> A.elt_shift, lo_r + S8_ROWS * q, f);
+                } else if (q < npl) {
                     s8_expect_tx(bar, S8_ROWS * A.seg_l);
                     s8_tma_load(d, &map_y, bar, (a0l << A.bps) >> A.elt_shift, lo_l + S8_ROWS * q, f);
                 } else {
@@ -546,6 +571,127 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     const S8Range rcl = { GEN ? A.range_mode : 0, A.lum_rc_coeff, A.lum_rc_offset };
     const S8Range rcc = { GEN ? A.range_mode : 0, A.chr_rc_coeff, A.chr_rc_offset };
 
+    if (RGBS) {
+        /* ================= packed RGB source: per ring slot  reader -> samples -> H luma + H chroma =================
+         * rgb24ToY_c / rgb24ToUV[_half]_c and the 32-bit template readers (input.c:264-345,1068-1180) as two IDP.2A
+         * per matrix row and pixel (the host admits only matrices whose samples stay inside 14 bits, where the
+         * readers' 16-bit store and the 24- / 32-bit forms of the rounding are the same number); then
+         * hScale16To15_c with shift 13 over the sample rows exactly like the 16-bit planar sources. */
+        unsigned char *smp_y = reinterpret_cast<unsigned char *>(hb_v + CW * cstride_w);
+        unsigned char *smp_u = smp_y + S8_ROWS * A.seg_sy;
+        unsigned char *smp_v = smp_u + S8_ROWS * A.seg_sc;
+        const int bpp = A.src_bpp, half = A.rgb_half;
+        const int units = A.seg_l / (4 * bpp);                       /* groups of four pixels per staged row */
+        /* H stage roles, fixed for the tile */
+        const int xl = tid & (S8_TW - 1), gl = tid >> 7;
+        const int gxl = min(x0 + xl, A.dst_w - 1);
+        const int offl = __ldg(A.hl_pos + gxl) - a0r;
+        const int lslot = RGB ? (xl >> 1) + 64 * (xl & 1) : xl;
+        uint32_t lcl[FS4], lch[FS4], ccl[FS4], cch[FS4];
+#pragma unroll
+        for (int k = 0; k < FS4; k++) {
+            lcl[k] = __ldg(A.hl_cl + (size_t)gxl * FS4 + k);
+            lch[k] = __ldg(A.hl_ch + (size_t)gxl * FS4 + k);
+        }
+        const int xc = tid & (CW - 1), gc = tid >> cs;
+        const int npair = A.hs ? S8_ROWS / 8 : S8_ROWS / 4;
+        const int gxc = min(cx0 + xc, A.chr_dst_w - 1);
+        const int offc = ch > 0 ? __ldg(A.hc_pos + gxc) - (a0r >> half) : 0;
+#pragma unroll
+        for (int k = 0; k < FS4; k++) {
+            ccl[k] = ch > 0 ? __ldg(A.hc_cl + (size_t)gxc * FS4 + k) : 0;
+            cch[k] = ch > 0 ? __ldg(A.hc_ch + (size_t)gxc * FS4 + k) : 0;
+        }
+        const int ybias = (32 << 14) + (1 << 8);
+        const int cbias = half ? (256 << 15) + (1 << 9) : (256 << 14) + (1 << 8);
+        const int cshift = half ? 10 : 9;
+        for (int q = 0; q < npr; q++) {
+            s8_wait(full_a + 8 * sb, sphase);
+            const int rbase = lo_r + S8_ROWS * q;
+            /* ---- reader: warp = rows warp and warp + 8 of the slot, lane = groups of four pixels ---- */
+#pragma unroll 1
+            for (int rr = warp; rr < S8_ROWS; rr += 8) {
+                const unsigned char *raw = ring + sb * slot + rr * A.seg_l;
+                uint2 *yo = reinterpret_cast<uint2 *>(smp_y + rr * A.seg_sy);
+                for (int k = lane; k < units; k += 32) {
+                    uint32_t px[4];
+                    if (bpp == 4) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(raw + 16 * k);
+                        px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w;
+                    } else {
+                        const uint32_t *wq = reinterpret_cast<const uint32_t *>(raw + 12 * k);
+                        const uint32_t w0 = wq[0], w1 = wq[1], w2 = wq[2];
+                        px[0] = w0;
+                        px[1] = __funnelshift_r(w0, w1, 24);
+                        px[2] = __funnelshift_r(w1, w2, 16);
+                        px[3] = w2 >> 8;
+                    }
+                    int y[4], u[4], v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        y[j] = dp2a_hi_su(A.yhi, px[j], dp2a_lo_su(A.ylo, px[j], ybias)) >> 9;
+                        u[j] = dp2a_hi_su(A.uhi, px[j], dp2a_lo_su(A.ulo, px[j], (j & 1) && half ? u[j - 1] : cbias));
+                        v[j] = dp2a_hi_su(A.vhi, px[j], dp2a_lo_su(A.vlo, px[j], (j & 1) && half ? v[j - 1] : cbias));
+                    }
+                    yo[k] = make_uint2(prmt((uint32_t)y[0], (uint32_t)y[1], 0x5410), prmt((uint32_t)y[2], (uint32_t)y[3], 0x5410));
+                    if (half) {
+                        reinterpret_cast<uint32_t *>(smp_u + rr * A.seg_sc)[k] =
+                            prmt((uint32_t)(u[1] >> cshift), (uint32_t)(u[3] >> cshift), 0x5410);
+                        reinterpret_cast<uint32_t *>(smp_v + rr * A.seg_sc)[k] =
+                            prmt((uint32_t)(v[1] >> cshift), (uint32_t)(v[3] >> cshift), 0x5410);
+                    } else {
+                        reinterpret_cast<uint2 *>(smp_u + rr * A.seg_sc)[k] =
+                            make_uint2(prmt((uint32_t)(u[0] >> cshift), (uint32_t)(u[1] >> cshift), 0x5410),
+                                       prmt((uint32_t)(u[2] >> cshift), (uint32_t)(u[3] >> cshift), 0x5410));
+                        reinterpret_cast<uint2 *>(smp_v + rr * A.seg_sc)[k] =
+                            make_uint2(prmt((uint32_t)(v[0] >> cshift), (uint32_t)(v[1] >> cshift), 0x5410),
+                                       prmt((uint32_t)(v[2] >> cshift), (uint32_t)(v[3] >> cshift), 0x5410));
+                    }
+                }
+            }
+            release();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            /* ---- H luma: thread = (column, half of the slot's row pairs) ---- */
+            {
+                const int shl = (offl & 1) * 16;
+                const unsigned char *sp = smp_y + (offl >> 1) * 4;
+#pragma unroll
+                for (int m = 0; m < S8_ROWS / 4; m++) {
+                    const int r = 2 * ((S8_ROWS / 4) * gl + m), li = rbase + r - lo_l;
+                    if (li >= 0 && li < nl) {
+                        int va = s16_hfir<FS4>(sp + r * A.seg_sy, shl, 13, lcl, lch);
+                        int vb = s16_hfir<FS4>(sp + (r + 1) * A.seg_sy, shl, 13, lcl, lch);
+                        if (rcl.mode) {
+                            va = s8_range(va, rcl.mode, rcl.coeff, rcl.offset);
+                            vb = s8_range(vb, rcl.mode, rcl.coeff, rcl.offset);
+                        }
+                        hb_l[lslot * lstride_w + (li >> 1)] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
+                    }
+                }
+            }
+            /* ---- H chroma: thread = (column, row-pair group), both planes ---- */
+            if (ch > 0) {
+                const int shc = (offc & 1) * 16;
+                const unsigned char *su = smp_u + (offc >> 1) * 4, *sv = smp_v + (offc >> 1) * 4;
+                for (int m = 0; m < npair; m++) {
+                    const int r = 2 * (npair * gc + m), ci = rbase + r - lo_c;
+                    if (ci >= 0 && ci < nc) {
+                        int ua = s16_hfir<FS4>(su + r * A.seg_sc, shc, 13, ccl, cch);
+                        int ub = s16_hfir<FS4>(su + (r + 1) * A.seg_sc, shc, 13, ccl, cch);
+                        int va = s16_hfir<FS4>(sv + r * A.seg_sc, shc, 13, ccl, cch);
+                        int vb = s16_hfir<FS4>(sv + (r + 1) * A.seg_sc, shc, 13, ccl, cch);
+                        if (rcc.mode) {
+                            ua = s8_range(ua, rcc.mode, rcc.coeff, rcc.offset); ub = s8_range(ub, rcc.mode, rcc.coeff, rcc.offset);
+                            va = s8_range(va, rcc.mode, rcc.coeff, rcc.offset); vb = s8_range(vb, rcc.mode, rcc.coeff, rcc.offset);
+                        }
+                        hb_u[xc * cstride_w + (ci >> 1)] = prmt((uint32_t)ua, (uint32_t)ub, 0x5410);
+                        hb_v[xc * cstride_w + (ci >> 1)] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");      /* the sample rows are rewritten by the next slot */
+        }
+    } else {
     /* ================= stage H, luma ================= */
     if (MMA) {
         /* warp = 16 output columns (two groups of 8), all 16 rows of a slot per pass: FS4 = K steps of 32 bytes */
@@ -734,6 +880,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             left -= S8_ROWS;
             release();
         }
+    }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");      /* the 8 filtering warps: all h-scaled lines are in place */
 

@@ -93,3 +93,53 @@ def test_high_depth_slices_and_strides():
 def test_4k_10bit_downscale_full_size():
     case = dict(sw=3840, sh=2160, sf="yuv420p10le", dw=1920, dh=1080, df="yuv420p10le", flags=S.SWS_BICUBIC | BX)
     assert _run(case) == "scale16_dp2a"
+
+
+# ---- packed 8-bit RGB sources through the scaler: reader stage (input.c:264-345,1068-1180) + IDP.2A FIR stages ----
+RGB_GEOMS = [
+    ((640, 360, 320, 180), S.SWS_BICUBIC),       # 2:1: chroma from pixel pairs (the *_half readers)
+    ((644, 366, 1288, 732), S.SWS_BICUBIC),      # 1:2 upscale: full-resolution chroma readers, ragged tiles
+    ((1280, 720, 480, 270), S.SWS_BICUBIC),      # 2.7:1, 12 taps
+    ((322, 242, 400, 300), S.SWS_BILINEAR),
+    ((350, 130, 350, 260), S.SWS_BILINEAR),      # vertical only
+    ((642, 362, 322, 182), S.SWS_LANCZOS),
+    ((66, 50, 24, 20), S.SWS_AREA),
+]
+
+
+@pytest.mark.parametrize("sf", ["rgb24", "bgr24", "rgba", "bgra", "argb", "abgr"])
+@pytest.mark.parametrize("df", ["yuv420p", "nv12", "yuv444p", "yuv422p10le", "yuvj420p", "nv21"])
+@pytest.mark.parametrize("geom,flags", RGB_GEOMS)
+def test_packed_rgb_sources(sf, df, geom, flags):
+    sw, sh, dw, dh = geom
+    case = dict(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags | BX)
+    for mode in ("noise", "extreme"):
+        name = _run(case, mode=mode)
+        # wider raw rows than the 2 KB TMA box row, and vertical chroma filters beyond 16 taps (RGB rows are not
+        # subsampled: a 4:2:0 destination doubles the vertical chroma ratio), stay on the general kernels
+        vsub = "420" in df or df.startswith("nv")
+        if sw <= 2 * dw and not (vsub and flags == S.SWS_LANCZOS and sh > dh):
+            assert name == "scale_rgb_dp2a", name
+
+
+@pytest.mark.parametrize("sf,df", [("rgb24", "bgr24"), ("bgra", "rgb24"), ("rgb24", "bgra"), ("argb", "abgr")])
+@pytest.mark.parametrize("geom,flags", RGB_GEOMS[:4])
+def test_packed_rgb_to_packed_rgb_scaled(sf, df, geom, flags):
+    """RGB -> YUV -> RGB, as the reference does when it has to scale (an even destination width keeps shared chroma)."""
+    sw, sh, dw, dh = geom
+    _run(dict(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags | BX))
+
+
+def test_packed_rgb_source_slices_strides_colorspace():
+    case = dict(sw=644, sh=366, sf="bgra", dw=400, dh=222, df="nv12", flags=S.SWS_BICUBIC | BX)
+    src = T.Frame("bgra", 644, 366, pad=16).randomize(5)
+    slices = [(y, min(64, 366 - y)) for y in range(0, 366, 64)]
+    for cs in (None, (1, 0, 1, 0, 0, 1 << 16, 1 << 16), (5, 0, 7, 1, 0, 1 << 16, 1 << 16)):
+        want, _ = T.run_reference(src=src, slices=slices, dst_pad=6, colorspace=cs, **case)
+        got, name = T.run_cuda(src=src, slices=slices, dst_pad=6, colorspace=cs, **case)
+        assert T.first_diff(got.valid(), want.valid()) is None, (name, cs)
+
+
+def test_4k_bgra_to_1080p_nv12_full_size():
+    case = dict(sw=3840, sh=2160, sf="bgra", dw=1920, dh=1080, df="nv12", flags=S.SWS_BICUBIC | BX)
+    assert _run(case) == "scale_rgb_dp2a"
