@@ -628,6 +628,10 @@ static int init_single(SwsContext *sws, int with_device)
                 sws->dst_format == AV_PIX_FMT_ARGB || sws->dst_format == AV_PIX_FMT_ABGR)
                 c->special = SWSC_SPECIAL_SHUFFLE;
         }
+        if (is_rgb(sws->src_format) && is_rgb(sws->dst_format) && sd->depth == 16 && dd->depth == 16 && dd->bpp == 48)
+            /* identical formats: packedCopyWrapper; rgb48le <-> bgr48le: rgb48tobgr48_nobswap through rgbToRgbWrapper
+             * (findRgbConvFn, swscale_unscaled.c:1869-1873; no dither is ever needed between 48-bit layouts) */
+            c->special = SWSC_SPECIAL_RGB48;
         if (is_rgb(sws->src_format) && is_rgb(sws->dst_format) && sd->depth == 8 && dd->bpp <= 16 &&
             (flags & (SWS_FAST_BILINEAR | SWS_POINT)))
             /* rgb24to16, rgb32tobgr15, ... (findRgbConvFn): plain truncation, chosen only when the caller's
@@ -763,7 +767,7 @@ static int init_single(SwsContext *sws, int with_device)
     p->full_chr = is_rgb(sws->dst_format) && (flags & SWS_FULL_CHR_H_INT) && !c->unscaled_lut;
     /* hScale selection (swscale.c:675-688) and its shift (swscale.c:69-159) */
     p->inter_bits = c->dst_bpc > 14 ? 19 : 15;
-    if (is_rgb(sws->src_format))
+    if (is_rgb(sws->src_format) && sd->depth < 16)
         p->h_shift = p->inter_bits == 15 ? 13 : 9;         /* swscale.c:80-81,108-109 */
     else if (c->src_bpc == 8)
         p->h_shift = p->inter_bits == 15 ? 7 : 3;
@@ -777,9 +781,11 @@ static int init_single(SwsContext *sws, int with_device)
             { AV_PIX_FMT_RGB24, 3, 0, 1, 2 }, { AV_PIX_FMT_BGR24, 3, 2, 1, 0 },
             { AV_PIX_FMT_RGBA,  4, 0, 1, 2 }, { AV_PIX_FMT_BGRA,  4, 2, 1, 0 },
             { AV_PIX_FMT_ARGB,  4, 1, 2, 3 }, { AV_PIX_FMT_ABGR,  4, 3, 2, 1 },
+            /* 16 bits per component: indices of the components, not bytes (rgb48ToY_c & co., input.c:111-196) */
+            { AV_PIX_FMT_RGB48LE, 6, 0, 1, 2 }, { AV_PIX_FMT_BGR48LE, 6, 2, 1, 0 },
         };
         p->src_layout = SWSC_SRC_RGB;
-        p->src_bits = 8;
+        p->src_bits = sd->depth == 16 ? 16 : 8;
         for (size_t i = 0; i < sizeof(order) / sizeof(order[0]); i++)
             if (order[i].fmt == sws->src_format) {
                 p->src_bpp = order[i].bpp;
@@ -1055,7 +1061,8 @@ static int scale_slice(SwsContext *sws, const uint8_t *const srcSlice[], const i
         set_error(c, "the last sws_setColorspaceDetails() asked for a conversion that is not on the CUDA hot path");
         return AVERROR(ENOTSUP);
     }
-    if ((c->src_bpc > 8 && !is_rgb(sws->src_format) && ((srcStride[0] | srcStride[1] | srcStride[2]) & 1)) ||
+    if ((c->src_bpc > 8 && (!is_rgb(sws->src_format) || ff_b200_pix_desc(sws->src_format)->depth == 16) &&
+         ((srcStride[0] | srcStride[1] | srcStride[2]) & 1)) ||
         (c->dst_bpc > 8 && ((dstStride[0] | dstStride[1] | dstStride[2]) & 1))) {
         set_error(c, "16-bit samples need even strides");
         return AVERROR(EINVAL);

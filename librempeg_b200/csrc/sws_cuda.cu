@@ -127,8 +127,39 @@ __device__ __forceinline__ int fetch(const uint8_t *row, int idx, int shift = 0)
  * 3-byte pixels and the rgb16_32To{Y,UV,UV_half}_c_template instances for 4-byte pixels
  * (input.c:264-345,391-394: coefficients << 8, unsigned rounding constant, logical shift).  Both
  * store into int16 lines that the horizontal scaler reads back as uint16 (swscale.c:99-125). */
+/* 48-bit pixels: rgb48ToY_c / rgb48ToUV_c / rgb48ToUV_half_c (input.c:111-196): 16-bit components, the matrix product in
+ * unsigned arithmetic (int32 coefficient x unsigned sample), rounding 0x2001 << 14 (luma) / 0x10001 << 14 (chroma), a
+ * logical >> 15 and a 16-bit store; the *_half reader averages the pixel pair with rounding first */
+__device__ __forceinline__ int rgb48_luma16(const SwsCudaPlan &P, const uint8_t *row, int x)
+{
+    const uint16_t *px = reinterpret_cast<const uint16_t *>(row) + 3 * x;
+    const unsigned r = px[P.src_ro], g = px[P.src_go], b = px[P.src_bo];
+    const unsigned s = (unsigned)P.rgb2yuv[0] * r + (unsigned)P.rgb2yuv[1] * g + (unsigned)P.rgb2yuv[2] * b;
+    return (uint16_t)((s + (0x2001u << 14)) >> 15);
+}
+
+__device__ __forceinline__ void rgb48_chroma16(const SwsCudaPlan &P, const uint8_t *row, int x, int &u, int &v)
+{
+    unsigned r, g, b;
+    if (P.src_rgb_half) {
+        const uint16_t *px = reinterpret_cast<const uint16_t *>(row) + 6 * x;
+        r = (px[P.src_ro] + px[3 + P.src_ro] + 1u) >> 1;
+        g = (px[P.src_go] + px[3 + P.src_go] + 1u) >> 1;
+        b = (px[P.src_bo] + px[3 + P.src_bo] + 1u) >> 1;
+    } else {
+        const uint16_t *px = reinterpret_cast<const uint16_t *>(row) + 3 * x;
+        r = px[P.src_ro]; g = px[P.src_go]; b = px[P.src_bo];
+    }
+    const unsigned su = (unsigned)P.rgb2yuv[3] * r + (unsigned)P.rgb2yuv[4] * g + (unsigned)P.rgb2yuv[5] * b;
+    const unsigned sv = (unsigned)P.rgb2yuv[6] * r + (unsigned)P.rgb2yuv[7] * g + (unsigned)P.rgb2yuv[8] * b;
+    u = (uint16_t)((su + (0x10001u << 14)) >> 15);
+    v = (uint16_t)((sv + (0x10001u << 14)) >> 15);
+}
+
 __device__ __forceinline__ int rgb_luma14(const SwsCudaPlan &P, const uint8_t *row, int x)
 {
+    if (P.src_bpp == 6)
+        return rgb48_luma16(P, row, x);
     const uint8_t *px = row + x * P.src_bpp;
     const int r = px[P.src_ro], g = px[P.src_go], b = px[P.src_bo];
     const int s = P.rgb2yuv[0] * r + P.rgb2yuv[1] * g + P.rgb2yuv[2] * b;
@@ -139,6 +170,10 @@ __device__ __forceinline__ int rgb_luma14(const SwsCudaPlan &P, const uint8_t *r
 
 __device__ __forceinline__ void rgb_chroma14(const SwsCudaPlan &P, const uint8_t *row, int x, int &u, int &v)
 {
+    if (P.src_bpp == 6) {
+        rgb48_chroma16(P, row, x, u, v);
+        return;
+    }
     int r, g, b;
     if (P.src_rgb_half) {
         const uint8_t *px = row + 2 * x * P.src_bpp, *qx = px + P.src_bpp;
@@ -183,6 +218,31 @@ struct ShuffleArgs {
     int w, y0;
     int map[4];            /* destination byte k of a pixel <- source byte map[k]; 4 = constant 255 */
 };
+
+/* packedCopyWrapper (identical 48-bit formats) and rgb48tobgr48_nobswap (rgb2rgb_template.c via rgbToRgbWrapper):
+ * components 0 and 2 of every pixel change places, or nothing does.  One pixel per thread. */
+struct Rgb48Args {
+    const uint8_t *src;
+    uint8_t *dst;
+    long long src_fstride, dst_fstride;
+    int src_stride, dst_stride;
+    int w, y0, rows, swap;
+};
+
+__global__ void __launch_bounds__(256)
+sws_rgb48_kernel(const Rgb48Args A)
+{
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (long long)A.w * A.rows)
+        return;
+    const int y = A.y0 + (int)(idx / A.w), x = (int)(idx % A.w);
+    const uint16_t *s = reinterpret_cast<const uint16_t *>(A.src + blockIdx.z * A.src_fstride + (size_t)y * A.src_stride) + 3 * x;
+    uint16_t *d = reinterpret_cast<uint16_t *>(A.dst + blockIdx.z * A.dst_fstride + (size_t)y * A.dst_stride) + 3 * x;
+    const uint16_t c0 = s[0], c1 = s[1], c2 = s[2];
+    d[0] = A.swap ? c2 : c0;
+    d[1] = c1;
+    d[2] = A.swap ? c0 : c2;
+}
 
 /* rgb24to16 / rgb24tobgr16 / rgb32to15 ... (rgb2rgb_template.c via rgbToRgbWrapper): every 8-bit channel is truncated
  * into its 5- or 6-bit field.  Two pixels per thread. */
@@ -1274,6 +1334,15 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
                     Ui = (int)((U - (128u << 23)) >> 14);
                     Vi = (int)((V - (128u << 23)) >> 14);
                 }
+                if (lfs == 1 && (cfs == 1 || (cfs == 2 && cf[0] + cf[1] == 4096 && (unsigned)(int)cf[1] <= 4096u))) {
+                    /* the _1 writers shift the line itself (output.c:1497-1500,1278-1281): no x 4096 that could
+                     * wrap for 19-bit samples below -2^19 (overshoot is only clipped upwards) */
+                    Yi = (int)pl[0] >> 2;
+                    if (cfs == 1 || cf[1] == 0) {
+                        Ui = ((int)pu[0] - (128 << 11)) >> 2;
+                        Vi = ((int)pv[0] - (128 << 11)) >> 2;
+                    }
+                }
                 const unsigned Yu = (unsigned)(Yi - P.rgb.y_offset) * (unsigned)P.rgb.y_coeff + (1u << 13) - (1u << 29);
                 const unsigned R = (unsigned)Vi * (unsigned)P.rgb.v2r;
                 const unsigned G = (unsigned)Vi * (unsigned)P.rgb.v2g + (unsigned)Ui * (unsigned)P.rgb.u2g;
@@ -1376,7 +1445,8 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
                     const inter_t *pa = hb_a + (size_t)rl * TW + 2 * i;
                     const bool chr2 = cfs == 2 && cf[0] + cf[1] == 4096 && (unsigned)(int)cf[1] <= 4096u;
                     const bool lum2 = lfs == 2 && lf[0] + lf[1] == 4096 && (unsigned)(int)lf[1] <= 4096u;
-                    if (lfs == 1 && cfs == 1) {                 /* yuv2packed1, uvalpha == 0 */
+                    if (lfs == 1 && (cfs == 1 || (chr2 && cf[1] == 0))) {   /* yuv2packed1, uvalpha == 0 (a 2-tap chroma
+                                                                              * row of {4096, 0} lands here too) */
                         a1 = clip_u8(((int)pa[0] * 255 + 16384) >> 15);
                         a2 = clip_u8(((int)pa[1] * 255 + 16384) >> 15);
                     } else if (lfs == 1 && chr2) {              /* yuv2packed1, uvalpha != 0 */
@@ -1426,6 +1496,15 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
                 y2u = (unsigned)((int)y2u >> 14) + 0x10000u;
                 uu = (unsigned)((int)uu >> 14);
                 vu = (unsigned)((int)vu >> 14);
+                if (lfs == 1 && (cfs == 1 || (cfs == 2 && cf[0] + cf[1] == 4096 && (unsigned)(int)cf[1] <= 4096u))) {
+                    /* yuv2rgba64_1_c_template (output.c:1278-1281): the line itself >> 2, nothing that could wrap */
+                    y1u = (unsigned)((int)pl[0] >> 2);
+                    y2u = (unsigned)((int)pl[1] >> 2);
+                    if (cfs == 1 || cf[1] == 0) {
+                        uu = (unsigned)(((int)pu[0] - (128 << 11)) >> 2);
+                        vu = (unsigned)(((int)pv[0] - (128 << 11)) >> 2);
+                    }
+                }
                 y1u -= (unsigned)P.rgb.y_offset; y2u -= (unsigned)P.rgb.y_offset;
                 y1u *= (unsigned)P.rgb.y_coeff;  y2u *= (unsigned)P.rgb.y_coeff;
                 y1u += (1u << 13) - (1u << 29);  y2u += (1u << 13) - (1u << 29);
@@ -1473,13 +1552,16 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
             } else if (kind == SWSC_DST_P010) {     /* yuv2p010l1_c / yuv2p010lX_c (output.c:538-566): 10 bits << 6 */
                 const int shift = 27 - 10;
                 reinterpret_cast<uint16_t *>(d)[gx] = clip_uintp2((int)(acc + (1u << (shift - 1))) >> shift, 10) << 6;
-            } else if (kind == SWSC_DST_PLANARF32) {
-                /* yuv2plane1_float / yuv2planeX_float (output.c:219-263): the 16-bit planar result times 1/65535 */
-                const int v = (int)(acc + (1u << 14) - 0x40000000u) >> 15;
-                reinterpret_cast<float *>(d)[gx] = __fmul_rn(1.0f / 65535.0f, (float)(0x8000 + clip_i16(v)));
             } else {
-                const int v = (int)(acc + (1u << 14) - 0x40000000u) >> 15;
-                reinterpret_cast<uint16_t *>(d)[gx] = 0x8000 + clip_i16(v);
+                /* yuv2planeX_16_c (output.c:163-187).  One tap goes through yuv2plane1_16_c, which never multiplies:
+                 * a 19-bit line below -2^19 (hScale*To19 only clips upwards; sinc / lanczos overshoot of noise gets
+                 * there) must not wrap through the x 4096 of the general form */
+                const int v16 = lfs == 1 ? clip_uintp2(((int)pl[0] + 4) >> 3, 16)
+                                         : 0x8000 + clip_i16((int)(acc + (1u << 14) - 0x40000000u) >> 15);
+                if (kind == SWSC_DST_PLANARF32)     /* yuv2plane1_float / yuv2planeX_float (output.c:219-263): x 1/65535 */
+                    reinterpret_cast<float *>(d)[gx] = __fmul_rn(1.0f / 65535.0f, (float)v16);
+                else
+                    reinterpret_cast<uint16_t *>(d)[gx] = (uint16_t)v16;
             }
         }
         if (P.has_chroma && P.dst_has_chroma && ch > 0) {
@@ -1525,10 +1607,12 @@ sws_generic_tile_kernel(const __grid_constant__ SwsCudaPlan P, const __grid_cons
                     reinterpret_cast<uint16_t *>(dst2 + (size_t)y * A.dst_stride[2])[gx] =
                         clip_uintp2((int)(av + (1u << (shift - 1))) >> shift, bits);
                 } else {
-                    const int u = (int)(au + (1u << 14) - 0x40000000u) >> 15;
-                    const int v = (int)(av + (1u << 14) - 0x40000000u) >> 15;
-                    reinterpret_cast<uint16_t *>(dst1 + (size_t)y * A.dst_stride[1])[gx] = 0x8000 + clip_i16(u);
-                    reinterpret_cast<uint16_t *>(dst2 + (size_t)y * A.dst_stride[2])[gx] = 0x8000 + clip_i16(v);
+                    const int u = cfs == 1 ? clip_uintp2(((int)pu[0] + 4) >> 3, 16)
+                                           : 0x8000 + clip_i16((int)(au + (1u << 14) - 0x40000000u) >> 15);
+                    const int v = cfs == 1 ? clip_uintp2(((int)pv[0] + 4) >> 3, 16)
+                                           : 0x8000 + clip_i16((int)(av + (1u << 14) - 0x40000000u) >> 15);
+                    reinterpret_cast<uint16_t *>(dst1 + (size_t)y * A.dst_stride[1])[gx] = (uint16_t)u;
+                    reinterpret_cast<uint16_t *>(dst2 + (size_t)y * A.dst_stride[2])[gx] = (uint16_t)v;
                 }
             }
         }
@@ -3046,6 +3130,8 @@ static int tile15_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     const int srck = p->src_layout == SWSC_SRC_RGB ? T15_SRC_RGB : p->src_bits == 8 ? T15_SRC_U8 : T15_SRC_U16;
     if (srck == T15_SRC_U16 && p->src_layout != SWSC_SRC_PLANAR)
         return 0;
+    if (srck == T15_SRC_RGB && p->src_bpp == 6)
+        return 0;                     /* 48-bit pixels: the general kernel's readers */
     const int fs = hl->size > hc->size ? hl->size : hc->size;
     if (fs > 16)
         return 0;
@@ -3478,6 +3564,28 @@ static int special_launch(SwsCudaState *st, const uint8_t *const src[4], const i
         dim3 grid((unsigned)((work + 255) / 256), 1, nb_frames);
         sws_rgb16pack_kernel<<<grid, 256, 0, stream>>>(a);
         st->kernel_name = "rgb16pack";
+        CUDA_OK(cudaGetLastError());
+        st->launches++;
+        return 1;
+    }
+    if (p->special == SWSC_SPECIAL_RGB48) {
+        if (!src[0] || !dst[0])
+            return AVERROR(EINVAL);
+        Rgb48Args a;
+        a.src = src[0]; a.dst = dst[0];
+        a.src_fstride = src_fstride ? src_fstride[0] : 0;
+        a.dst_fstride = dst_fstride ? dst_fstride[0] : 0;
+        a.src_stride = src_stride[0]; a.dst_stride = dst_stride[0];
+        a.w = p->src_w; a.y0 = y0; a.rows = y1 - y0;
+        a.swap = (p->src_ro == 0) != (p->dst_kind == SWSC_DST_RGB48);
+        const long long work = (long long)a.w * a.rows;
+        for (int f0 = 0; f0 < nb_frames; f0 += 65535) {
+            Rgb48Args b = a;
+            b.src += f0 * a.src_fstride; b.dst += f0 * a.dst_fstride;
+            dim3 grid((unsigned)((work + 255) / 256), 1, nb_frames - f0 < 65535 ? nb_frames - f0 : 65535);
+            sws_rgb48_kernel<<<grid, 256, 0, stream>>>(b);
+        }
+        st->kernel_name = "rgb48";
         CUDA_OK(cudaGetLastError());
         st->launches++;
         return 1;

@@ -127,6 +127,7 @@ enum {
     SWSC_SPECIAL_P01X,           /* planarToP01xWrapper / planar8ToP01xleWrapper: shift + chroma interleave */
     SWSC_SPECIAL_DEPTHCOPY,      /* planarCopyWrapper between planar YUV depths (dithered down, replicated up) */
     SWSC_SPECIAL_RGB16PACK,      /* rgb24to16 / rgb32tobgr15 & co.: 8-bit packed RGB truncated into 15/16 bpp */
+    SWSC_SPECIAL_RGB48,          /* packedCopyWrapper / rgb48tobgr48_nobswap between rgb48le and bgr48le */
 };
 
 /* POD description of one conversion; passed by value to the kernels. */
@@ -157,7 +158,8 @@ typedef struct SwsCudaPlan {
     uint32_t lum_rc_coeff, chr_rc_coeff;
     int64_t  lum_rc_offset, chr_rc_offset;
     SwsRgbConsts rgb;
-    /* packed-RGB sources (reference input.c:264-345,1068-1180): pixel stride, byte offsets of R,G,B,
+    /* packed-RGB sources (reference input.c:264-345,1068-1180): pixel stride, byte offsets of R,G,B (48-bit pixels,
+     * src_bpp = 6: component indices; readers input.c:111-196),
      * chroma taken from horizontally summed pixel pairs (the *_half readers), and the 15-bit matrix */
     int src_bpp, src_ro, src_go, src_bo, src_rgb_half;
     int32_t rgb2yuv[9];

@@ -41,8 +41,8 @@ static const SwsPixDesc table[] = {
     { AV_PIX_FMT_BGRA,    "bgra",    SWSPF_RGB, 8, 0, 0, 32, 1, 0, 1, 1, 0 },
     { AV_PIX_FMT_ARGB,    "argb",    SWSPF_RGB, 8, 0, 0, 32, 1, 0, 1, 1, 0 },
     { AV_PIX_FMT_ABGR,    "abgr",    SWSPF_RGB, 8, 0, 0, 32, 1, 0, 1, 1, 0 },
-    { AV_PIX_FMT_RGB48LE, "rgb48le", SWSPF_RGB, 16, 0, 0, 48, 1, 0, 0, 1, 0 },
-    { AV_PIX_FMT_BGR48LE, "bgr48le", SWSPF_RGB, 16, 0, 0, 48, 1, 0, 0, 1, 0 },
+    { AV_PIX_FMT_RGB48LE, "rgb48le", SWSPF_RGB, 16, 0, 0, 48, 1, 0, 1, 1, 0 },
+    { AV_PIX_FMT_BGR48LE, "bgr48le", SWSPF_RGB, 16, 0, 0, 48, 1, 0, 1, 1, 0 },
     /* 32-bit float destinations (output.c:219-316 yuv2plane1/X_float, output.c:2536-2610 yuv2gbrpf32_full_X_c): the
      * 16-bit integer result of the 19-bit pipeline times 1.0f / 65535.0f */
     { AV_PIX_FMT_GRAYF32LE, "grayf32le", SWSPF_PLANAR | SWSPF_GRAY, 32, 0, 0, 32, 1, 0, 0, 1, 0 },

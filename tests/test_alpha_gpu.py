@@ -43,3 +43,14 @@ def test_rgb32_alpha_overshoot(mode, flags):
     got, name = T.run_cuda(src=src, **case)
     assert T.first_diff(got.valid(), want.valid()) is None, name
     assert len(np.unique(got.valid()[0].reshape(-1, 4)[:, 3])) > 1      # alpha really varies
+
+
+def test_alpha_of_packed1_with_a_4096_0_chroma_row():
+    """A vertical chroma offset turns the 1-tap chroma filter into {4096, 0} rows: yuv2packed1 is then called with
+    uvalpha == 0 and takes its a * 255 alpha form, not (a + 64) >> 7 (output.c:1904-1905 vs 1929-1930; fuzz seed 301)."""
+    case = dict(sw=512, sh=98, sf="argb", dw=230, dh=98, df="rgba", flags=S.SWS_FAST_BILINEAR | BX)
+    src = T.Frame("argb", 512, 98).randomize(978701, "smooth")
+    kw = dict(ctx_kwargs=dict(src_range=1, dst_range=1, chr_pos=(256, 256, 0, 128)))
+    want, _ = T.run_reference(src=src, **case, **kw)
+    got, name = T.run_cuda(src=src, **case, **kw)
+    assert T.first_diff(got.valid(), want.valid()) is None, name

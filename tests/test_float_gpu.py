@@ -41,3 +41,17 @@ def test_float_range_and_colourspace(df):
     want, _ = T.run_reference(src=src, colorspace=cs, **case)
     got, name = T.run_cuda(src=src, colorspace=cs, **case)
     assert T.first_diff(got.valid(), want.valid()) is None, name
+
+
+@pytest.mark.parametrize("df", ["grayf32le", "yuv444p16le", "yuv420p16le", "rgb48le", "bgr48le", "gbrpf32le"])
+@pytest.mark.parametrize("sf", ["yuvj444p", "yuvj420p"])
+@pytest.mark.parametrize("flags", [S.SWS_SINC, S.SWS_LANCZOS])
+def test_one_tap_rows_do_not_wrap_on_overshoot(sf, df, flags):
+    """Horizontal sinc / lanczos upscale of full-range noise drives 19-bit lines below -2^19 (hScale*To19 only clips
+    upwards); with one vertical tap the reference's _1 writers shift the line itself (yuv2plane1_16 / _float,
+    yuv2rgba64[_full]_1), so nothing may wrap through a x 4096 (found by the fuzz: seed 301)."""
+    case = dict(sw=53, sh=274, sf=sf, dw=266, dh=274, df=df, flags=flags | BX)
+    src = T.Frame(sf, 53, 274).randomize(571967, "noise")
+    want, _ = T.run_reference(src=src, **case)
+    got, name = T.run_cuda(src=src, **case)
+    assert T.first_diff(got.valid(), want.valid()) is None, name

@@ -57,7 +57,7 @@ def test_version_and_queries():
     assert L.swscale_version() >> 16 == 10          # LIBSWSCALE_VERSION_MAJOR, version_major.h:27
     assert L.sws_isSupportedInput(S.PIX_FMT["yuv420p"]) and L.sws_isSupportedOutput(S.PIX_FMT["rgb24"])
     assert L.sws_isSupportedInput(S.PIX_FMT["rgb24"])        # packed 8-bit RGB input
-    assert not L.sws_isSupportedInput(S.PIX_FMT["rgb48le"])  # 16-bit RGB is output-only
+    assert L.sws_isSupportedInput(S.PIX_FMT["rgb48le"])      # 16-bit RGB input (rgb48ToY_c & co., input.c:111-196)
     for f in ("rgb565le", "bgr565le", "rgb555le", "bgr555le"):   # 15/16 bpp RGB: output-only
         assert L.sws_isSupportedOutput(S.PIX_FMT[f]) and not L.sws_isSupportedInput(S.PIX_FMT[f])
     assert L.sws_isSupportedInput(S.PIX_FMT["p010le"]) and L.sws_isSupportedOutput(S.PIX_FMT["p010le"])

@@ -22,8 +22,9 @@ from tests import sws_testlib as T       # noqa: E402
 
 SRC = ["yuv420p", "yuv422p", "yuv444p", "yuvj420p", "yuvj422p", "yuvj444p", "nv12", "nv21", "p010le",
        "yuv420p9le", "yuv420p10le", "yuv422p10le", "yuv444p10le", "yuv420p12le", "yuv422p12le", "yuv444p12le",
-       "yuv420p14le", "yuv420p16le", "yuv422p16le", "yuv444p16le", "rgb24", "bgr24", "rgba", "bgra", "argb", "abgr"]
-DST = SRC + ["rgb48le", "bgr48le", "rgb565le", "bgr565le", "rgb555le", "bgr555le", "grayf32le", "gbrpf32le"]
+       "yuv420p14le", "yuv420p16le", "yuv422p16le", "yuv444p16le", "rgb24", "bgr24", "rgba", "bgra", "argb", "abgr",
+       "rgb48le", "bgr48le"]
+DST = SRC + ["rgb565le", "bgr565le", "rgb555le", "bgr555le", "grayf32le", "gbrpf32le"]
 SCALERS = [S.SWS_FAST_BILINEAR, S.SWS_BILINEAR, S.SWS_BICUBIC, S.SWS_X, S.SWS_POINT, S.SWS_AREA, S.SWS_BICUBLIN,
            S.SWS_GAUSS, S.SWS_SINC, S.SWS_LANCZOS, S.SWS_SPLINE]
 
@@ -134,7 +135,7 @@ def make_case(rng):
         case["colorspace"] = tuple(cs)
     if rng.random() < 0.25:
         # 16-bit samples need even strides (the reference reads them through uint16_t pointers)
-        case["src_pad"] = rng.choice([0, 1, 3, 16, 64] if T.depth_of(case["sf"]) == 8 else [0, 2, 6, 16, 64])
+        case["src_pad"] = rng.choice([0, 1, 3, 16, 64] if T.depth_of(case["sf"]) == 8 and "48" not in case["sf"] else [0, 2, 6, 16, 64])
         case["dst_pad"] = rng.choice([0, 1, 5, 16, 64] if T.depth_of(case["df"]) == 8 and "48" not in case["df"]
                                      and "5le" not in case["df"] and "f32" not in case["df"] else
                                      [0, 4, 16, 64] if "f32" in case["df"] else [0, 2, 6, 16, 64])
