@@ -667,12 +667,9 @@ static int init_single(SwsContext *sws, int with_device)
             c->special = SWSC_SPECIAL_P01X;
         } else if (planar_yuv_pair && (sd->depth != dd->depth || sd->depth > 8) && (sd->flags & SWSPF_SEMI) &&
                    (dd->flags & SWSPF_SEMI) && sd->swap_uv == dd->swap_uv) {
-            if (sd->depth != 8 && sd->depth != dd->depth) {
-                /* DITHER_COPY's tail loop drops the source shift (swscale_unscaled.c:2174-2176): not restated */
-                set_error(c, "unscaled p010 -> 8-bit semi-planar conversion is not on the CUDA hot path");
-                return AVERROR(ENOTSUP);
-            }
-            c->special = SWSC_SPECIAL_DEPTHCOPY;       /* nv12 -> p010: COPY816, swscale_unscaled.c:2266-2284 */
+            /* nv12 -> p010: COPY816 (swscale_unscaled.c:2266-2284); p010 -> nv12: DITHER_COPY, whose scalar tail drops the
+             * source shift for the last width & 7 samples of a row (:2174-2176) -- reproduced by the kernel */
+            c->special = SWSC_SPECIAL_DEPTHCOPY;
         } else if (planar_yuv_pair && c->chr_src_hsub == c->chr_dst_hsub &&
                    c->chr_src_vsub == c->chr_dst_vsub && (sd->depth != dd->depth || sd->depth > 8) &&
                    !(sd->flags & SWSPF_SEMI) && !(dd->flags & SWSPF_SEMI)) {

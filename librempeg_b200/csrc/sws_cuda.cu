@@ -973,9 +973,20 @@ sws_depthcopy_kernel(const __grid_constant__ DepthCopyArgs A)
         DstT *dg = d + 8 * g;
         unsigned v[8], o[8];
         load8<SrcT>(sg, ng, A.vec, v);
+        if (sd > dd && A.src_shift) {
+            /* DITHER_COPY's scalar tail (the last width & 7 samples of a row, swscale_unscaled.c:2174-2176,2193-2195,
+             * 2212-2214) forgets the source shift: p010 samples go in with their six low bits, and the 8-bit store
+             * keeps the low byte of what comes out */
+            const int j0 = CH * c + 8 * g, body = A.w[plane] & ~7;
 #pragma unroll
-        for (int i = 0; i < 8; i++)
-            v[i] >>= A.src_shift;
+            for (int i = 0; i < 8; i++)
+                if (j0 + i < body)
+                    v[i] >>= A.src_shift;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                v[i] >>= A.src_shift;
+        }
         if (sd > dd) {
             const int shift = sd - dd;
             const uint2 dq = *reinterpret_cast<const uint2 *>(c_depth_dither[shift - 1][row & 7]);   /* rows count from the slice */

@@ -331,11 +331,11 @@ def test_special_converter_selection_mirrors_the_reference():
     the plan must make the same choice (special id in info()['special'] when exported, else via the error path)."""
     ok = [("nv12", "yuv420p"), ("yuv420p", "nv21"), ("yuv420p", "yuv420p"), ("yuv420p10le", "yuv420p"),
           ("yuv420p", "yuv420p16le"), ("yuv420p", "p010le"), ("yuv420p12le", "p010le"), ("nv12", "p010le"),
-          ("rgba", "bgra"), ("bgr24", "yuv420p")]
+          ("rgba", "bgra"), ("bgr24", "yuv420p"), ("p010le", "nv12"), ("rgb48le", "bgr48le"), ("bgr48le", "bgr48le")]
     for sf, df in ok:
         S.SwsContext(128, 64, sf, 128, 64, df, S.SWS_BICUBIC, plan_only=True)
-    with pytest.raises(RuntimeError):                      # DITHER_COPY's tail quirk on p010 sources: not restated
-        S.SwsContext(128, 64, "p010le", 128, 64, "nv12", S.SWS_BICUBIC, plan_only=True)
+    with pytest.raises(RuntimeError):                      # 15/16 bpp RGB readers are not on the path
+        S.SwsContext(128, 64, "rgb565le", 128, 64, "nv12", S.SWS_BICUBIC, plan_only=True)
 
 
 GAUSS5 = [0.06136, 0.24477, 0.38774, 0.24477, 0.06136]

@@ -155,7 +155,7 @@ def test_unsupported_fails_loudly():
     with pytest.raises(RuntimeError):
         S.SwsContext(320, 240, "yuv420p", 320, 240, "rgb24", S.SWS_BICUBIC | (1 << 16))          # vertical chroma drop
     with pytest.raises(RuntimeError):
-        S.SwsContext(320, 240, "p010le", 320, 240, "nv12", S.SWS_BICUBIC | BX)           # DITHER_COPY tail quirk
+        S.SwsContext(320, 240, "rgb565le", 320, 240, "yuv420p", S.SWS_BICUBIC | BX)      # 15/16 bpp RGB readers
 
 
 @pytest.mark.parametrize("sf", ["yuv444p", "yuv420p", "yuv422p", "yuv444p10le", "yuv420p12le", "nv12"])
@@ -379,8 +379,6 @@ def test_depthcopy_other_subsamplings(sf, df):
                                         ((322, 242, 322, 242), S.SWS_BICUBIC | BX), ((323, 241, 323, 241), S.SWS_POINT)])
 def test_p010_source(df, geom, flags):
     sw, sh, dw, dh = geom
-    if df in ("p010le", "nv12") and (sw, sh) == (dw, dh):
-        pytest.skip("same-size semi-planar copies / depth changes (planarCopyWrapper on p010) are not on the path")
     for mode in ("noise", "extreme"):
         _check(sw=sw, sh=sh, sf="p010le", dw=dw, dh=dh, df=df, flags=flags, seed=105, mode=mode)
 
@@ -411,6 +409,19 @@ def test_nv12_to_p010_unscaled(geom, opts):
     w, h = geom
     name = _check(sw=w, sh=h, sf="nv12", dw=w, dh=h, df="p010le", flags=S.SWS_BICUBIC, seed=109, ctx_kwargs=opts)
     assert name == "depthcopy", name
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(src_range=1, dst_range=1), dict(dither=0)])
+@pytest.mark.parametrize("geom", [(644, 366), (35, 19), (640, 360), (1287, 33)])
+def test_p010_to_nv12_unscaled(geom, opts):
+    """planarCopyWrapper's DITHER_COPY on semi-planar planes, including its scalar tail (the last width & 7 samples of a
+    row), which forgets the >> 6 of the p010 container (swscale_unscaled.c:2174-2176,2193-2195,2212-2214)."""
+    w, h = geom
+    for mode in ("noise", "extreme"):
+        name = _check(sw=w, sh=h, sf="p010le", dw=w, dh=h, df="nv12", flags=S.SWS_BICUBIC, seed=110, mode=mode, ctx_kwargs=opts)
+        assert name == "depthcopy", name
+    slices = [(y, min(16, h - y)) for y in range(0, h, 16)]
+    _check(sw=w, sh=h, sf="p010le", dw=w, dh=h, df="nv12", flags=S.SWS_BICUBIC, seed=111, slices=slices, ctx_kwargs=opts)
 
 
 # ---- 9..16-bit planar -> packed 8-bit RGB of the same size: the TMA kernel for 10-bit video to display RGB ----
