@@ -38,6 +38,14 @@
         }                                                                       \
     } while (0)
 
+/* NVTX ranges (header-only NVTX 3: free when no tool is attached) around the three things a timeline of this library
+ * shows: host -> device rows, the conversion launch, device -> host rows; plus the whole-frame pipelines */
+#include <nvtx3/nvToolsExt.h>
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 /* Every entry point runs on the device the context was created on, whatever device the calling thread
  * has current, and leaves the caller's current device as it found it. */
 struct DeviceGuard {
@@ -903,7 +911,7 @@ struct DepthCopyArgs {
 };
 
 template <typename SrcT, typename DstT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)       /* 32 registers: full occupancy is what the streaming path lives on */
 sws_depthcopy_kernel(const __grid_constant__ DepthCopyArgs A)
 {
     /* one index space over the planes: no block is launched only to find its plane already done */
@@ -3712,6 +3720,7 @@ extern "C" int ff_b200_cuda_launch(SwsCudaState *st,
     if (y1 <= y0)
         return 0;
     DeviceGuard guard(st->device);
+    NvtxRange nvtx("sws_b200: convert");
     {
         int r = special_launch(st, src, src_stride, src_fstride, dst, dst_stride, dst_fstride, nb_frames, y0, y1, st->stream);
         if (r != 0)

@@ -360,6 +360,7 @@ static int upload_rows(SwsCudaState *st, uint8_t *d, int dpitch, const uint8_t *
 {
     if (rows <= 0)
         return 0;
+    NvtxRange nvtx("sws_b200: upload rows");
     if (spitch >= 0 || rows == 1) {
         CUDA_OK(copy_rows_async(d, dpitch, src, (size_t)spitch, rowbytes, rows, cudaMemcpyHostToDevice, s));
         return 0;
@@ -385,6 +386,7 @@ static int download_rows(SwsCudaState *st, uint8_t *dst, ptrdiff_t dpitch, const
 {
     if (rows <= 0)
         return 0;
+    NvtxRange nvtx("sws_b200: download rows");
     if (dpitch >= 0 || rows == 1) {
         CUDA_OK(copy_rows_async(dst, (size_t)dpitch, d, spitch, rowbytes, rows, cudaMemcpyDeviceToHost, s));
         return 0;
@@ -484,6 +486,7 @@ static int banded_host_frame(SwsCudaState *st, const uint8_t *const src[4], cons
 {
     const SwsCudaPlan *p = &st->plan;
     int ret;
+    NvtxRange nvtx("sws_b200: banded frame (H2D | convert | D2H)");
     if ((ret = ensure_pipeline(st)) < 0)
         return ret;
 
@@ -665,6 +668,7 @@ extern "C" int ff_b200_cuda_frames_enqueue(SwsCudaState *st,
 {
     const SwsCudaPlan *p = &st->plan;
     DeviceGuard guard(st->device);
+    NvtxRange nvtx("sws_b200: enqueue host frames");
     int ret = ensure_ring(st);
     if (ret < 0)
         return ret;

@@ -2,7 +2,7 @@
 # One GPU call that refreshes the evidence under profiles/ (run through gpurun; outputs land in gpurun_out/).
 #   tools/profile_round.sh <round tag, e.g. r01>
 set -u
-TAG=${1:-r01}
+TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT
 python tools/bench_configs.py > $OUT/configs_$TAG.txt 2>&1
@@ -26,7 +26,9 @@ cap scale8  sws_scale8 "C4 8K" 16 $((7680*4320*16))
 cap scale8_rgb sws_scale8 "X1 1080p" 16 $((3840*2160*16))
 cap rgb420 sws_rgb420 "E1 4K" 16 $((3840*2160*16))
 cap fast_hi8 sws_fast420_hi8 "C3b 4K" 16 $((3840*2160*16))
-cap tile15_rgbsrc sws_tile15 "E2 4K" 4 $((3840*2160*4))
+cap scale_rgb sws_scale8 "E2 4K" 16 $((3840*2160*16))
+cap scale16 sws_scale8 "X3 4K" 16 $((3840*2160*16))
+cap scale8_x2 sws_scale8 "X2 4K" 16 $((3840*2160*16))
 cap copy8 sws_copy8 "U1 4K" 16 $((3840*2160*16))
 cap full444 sws_full444 "F1 4K" 16 $((3840*2160*16))
 cap rgb444 sws_rgb444 "F3 4K" 16 $((3840*2160*16))
