@@ -14,8 +14,9 @@
  *                                                                  yuv2rgb.c:680-703
  *
  * so r = y_table[Y + base_r + ((V8*crv)>>16)] is an exact integer expression in
- * (Y, V8); the kernels evaluate it directly.  tests/test_host_tables.py checks
- * the closed form against the LUTs the real reference builds, entry by entry.
+ * (Y, V8); the kernels evaluate it directly.  tests/test_host_cpu.py
+ * (test_rgb_closed_form_equals_reference_luts) checks the closed form against the LUTs the real reference
+ * builds, entry by entry.
  */
 #include <errno.h>
 #include <string.h>

@@ -70,9 +70,9 @@ int sws_test_frame(const AVFrame *frame, int output)
 }
 
 /* ---- SwsFilter builder (reference libswscale/utils.c:1956-2248) ----
- * The CUDA path rejects pre/post filters at init (AVERROR(ENOTSUP)); the builder exists so that
- * callers which construct one unconditionally (libavfilter/vf_smartblur.c:144-163) link and get
- * the same vectors. */
+ * sws_init_context() convolves these vectors into the FIR banks exactly like initFilter does (sws_filter.c,
+ * stage 1b); callers that construct one (libavfilter/vf_smartblur.c:144-163) get the same vectors and the
+ * same pictures. */
 
 static SwsVector *const_vec(double c, int length)
 {

@@ -11,7 +11,7 @@
  * Deliberate differences (all result-neutral under SWS_BITEXACT):
  *  - filterAlign is 1 (the "generic arch" choice, utils.c:1675-1679,1708-1710);
  *    x86 pads to 4/2 with zero taps, which cannot change any output;
- *  - SwsFilter pre/post vectors are not supported (init rejects them).
+ *  - none else: SwsFilter pre/post vectors are convolved into the rows like utils.c:385-413 (stage 1b below).
  */
 #include <math.h>
 #include <stdlib.h>
