@@ -288,7 +288,9 @@ static int cascade_matrix_change(SwsContext *sws, const int inv_table[4], int sr
 {
     SwsInternal *c = sws_internal(sws);
     const int srcW = sws->src_w, srcH = sws->src_h, dstW = sws->dst_w, dstH = sws->dst_h;
-    const int tmp_fmt = c->dst_bpc > 8 ? AV_PIX_FMT_BGR48LE : AV_PIX_FMT_BGR24;
+    /* isNBPS(dst) || is16BPS(dst) (utils.c:928): depths 9..16; a 32-bit float gray destination is neither and goes
+     * through bgr24 like the 8-bit formats */
+    const int tmp_fmt = c->dst_bpc > 8 && c->dst_bpc <= 16 ? AV_PIX_FMT_BGR48LE : AV_PIX_FMT_BGR24;
     const int small = srcW * (int64_t)srcH > dstW * (int64_t)dstH;
     const int tmpW = small ? dstW : srcW, tmpH = small ? dstH : srcH;
     int ret;

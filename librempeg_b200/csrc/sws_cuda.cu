@@ -1679,7 +1679,7 @@ struct SwsCudaState {
     int s8_mma;                  /* horizontal stage on the tensor pipe: s8_fs4 counts K steps of 32 samples */
     int *s8_hl_goff, *s8_hc_goff;
     uint32_t *s8_hl_B, *s8_hc_B;
-    S8VRow *s8_vl, *s8_vc;
+    S8VRow *s8_vl, *s8_vc, *s8_vl2, *s8_vc2;
     int fast16_ok, fast16_taps;
     /* tile15 path */
     int t15_ok, t15_srck, t15_ht, t15_outk, t15_tile_h, t15_nl_cap, t15_nc_cap, t15_seg_l, t15_seg_c, t15_srl, t15_src;
@@ -2340,32 +2340,19 @@ static int fasthi8_launch(SwsCudaState *st, const uint8_t *const src[4], const i
 typedef void (*scale8_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Scale8Args);
 static scale8_kernel_t pick_scale8(int fs4, bool rgb, bool mma, int srck)
 {
-    if (srck == S8_SRC_RGB) {   /* packed 8-bit RGB sources: reader stage + IDP.2A horizontal stage */
-        if (rgb)
-            return fs4 == 1 ? sws_scale8_kernel<1, true, false, S8_SRC_RGB> : fs4 == 2 ? sws_scale8_kernel<2, true, false, S8_SRC_RGB>
-                                                                                       : sws_scale8_kernel<4, true, false, S8_SRC_RGB>;
-        return fs4 == 1 ? sws_scale8_kernel<1, false, false, S8_SRC_RGB> : fs4 == 2 ? sws_scale8_kernel<2, false, false, S8_SRC_RGB>
-                                                                                    : sws_scale8_kernel<4, false, false, S8_SRC_RGB>;
-    }
-    if (srck == S8_SRC_U16) {   /* 9..16-bit planar sources: IDP.2A horizontal stage */
-        if (rgb)
-            return fs4 == 1 ? sws_scale8_kernel<1, true, false, S8_SRC_U16> : fs4 == 2 ? sws_scale8_kernel<2, true, false, S8_SRC_U16>
-                                                                                       : sws_scale8_kernel<4, true, false, S8_SRC_U16>;
-        return fs4 == 1 ? sws_scale8_kernel<1, false, false, S8_SRC_U16> : fs4 == 2 ? sws_scale8_kernel<2, false, false, S8_SRC_U16>
-                                                                                    : sws_scale8_kernel<4, false, false, S8_SRC_U16>;
-    }
-    if (mma) {          /* fs4 = K steps of the tensor-pipe horizontal stage */
-        if (rgb)
-            return fs4 == 1 ? sws_scale8_kernel<1, true, true, S8_SRC_U8> : fs4 == 2 ? sws_scale8_kernel<2, true, true, S8_SRC_U8>
-                                                                                 : sws_scale8_kernel<4, true, true, S8_SRC_U8>;
-        return fs4 == 1 ? sws_scale8_kernel<1, false, true, S8_SRC_U8> : fs4 == 2 ? sws_scale8_kernel<2, false, true, S8_SRC_U8>
-                                                                              : sws_scale8_kernel<4, false, true, S8_SRC_U8>;
-    }
-    if (rgb)
-        return fs4 == 1 ? sws_scale8_kernel<1, true, false, S8_SRC_U8> : fs4 == 2 ? sws_scale8_kernel<2, true, false, S8_SRC_U8>
-                                                                              : sws_scale8_kernel<4, true, false, S8_SRC_U8>;
-    return fs4 == 1 ? sws_scale8_kernel<1, false, false, S8_SRC_U8> : fs4 == 2 ? sws_scale8_kernel<2, false, false, S8_SRC_U8>
-                                                                           : sws_scale8_kernel<4, false, false, S8_SRC_U8>;
+#define S8_PICK(R, M, K) (fs4 == 1 ? sws_scale8_kernel<1, R, M, K> : fs4 == 2 ? sws_scale8_kernel<2, R, M, K> \
+                          : fs4 == 4 ? sws_scale8_kernel<4, R, M, K> : sws_scale8_kernel<8, R, M, K>)
+#define S8_PICK_MMA(R) (fs4 == 1 ? sws_scale8_kernel<1, R, true, S8_SRC_U8> : fs4 == 2 ? sws_scale8_kernel<2, R, true, S8_SRC_U8> \
+                        : sws_scale8_kernel<4, R, true, S8_SRC_U8>)
+    if (srck == S8_SRC_RGB)     /* packed 8-bit RGB sources: reader stage + IDP.2A horizontal stage */
+        return rgb ? S8_PICK(true, false, S8_SRC_RGB) : S8_PICK(false, false, S8_SRC_RGB);
+    if (srck == S8_SRC_U16)     /* 9..16-bit planar sources: IDP.2A horizontal stage */
+        return rgb ? S8_PICK(true, false, S8_SRC_U16) : S8_PICK(false, false, S8_SRC_U16);
+    if (mma)                    /* fs4 = K steps of the tensor-pipe horizontal stage */
+        return rgb ? S8_PICK_MMA(true) : S8_PICK_MMA(false);
+    return rgb ? S8_PICK(true, false, S8_SRC_U8) : S8_PICK(false, false, S8_SRC_U8);
+#undef S8_PICK
+#undef S8_PICK_MMA
 }
 
 /* ---- tensor-pipe horizontal stage: per group of 8 output columns, the K window and the banded B fragments ----
@@ -2480,34 +2467,47 @@ static void s8_pack_h(const SwsFirBank *b, int fs4, uint32_t *cl, uint32_t *ch)
         }
 }
 
-/* vertical bank: even first row, leading zero tap when the true first row is odd */
-static int s8_pack_v(const SwsFirBank *b, S8VRow *rows)
+/* vertical bank: even first row, leading zero tap when the true first row is odd; taps 21..40 of a row go to a second
+ * record (rows2) whose first row is 20 further down.  Returns the number of records in use (1 or 2), -1: not expressible */
+static int s8_pack_v(const SwsFirBank *b, S8VRow *rows, S8VRow *rows2)
 {
+    int parts = 1;
     for (int y = 0; y < b->len; y++) {
         const int par = b->pos[y] & 1;
         const int n = b->size + par;
-        S8VRow *r = &rows[y];
+        S8VRow *r = &rows[y], *r2 = &rows2[y];
         memset(r, 0, sizeof(*r));
+        memset(r2, 0, sizeof(*r2));
         r->pos_even = b->pos[y] - par;
-        r->n4 = (n + 3) / 4;
-        if (r->n4 > S8_VF4 || b->pos[y] < 0)
+        const int n4 = (n + 3) / 4;
+        if (n4 > 2 * S8_VF4 || b->pos[y] < 0)
             return -1;
+        r->n4 = n4 < S8_VF4 ? n4 : S8_VF4;
+        r2->n4 = n4 - r->n4;
+        r2->pos_even = r2->n4 ? r->pos_even + 4 * S8_VF4 : r->pos_even;
+        if (r2->n4)
+            parts = 2;
         for (int j = 0; j < b->size; j++) {
             const int c = b->coef[(size_t)y * b->size + j];
-            const int t = j + par;
-            r->cl[t >> 2] |= (uint32_t)(c & 0xFF) << (8 * (t & 3));
-            r->ch[t >> 2] |= (uint32_t)((c >> 8) & 0xFF) << (8 * (t & 3));
+            int t = j + par;
+            S8VRow *d = r;
+            if (t >= 4 * S8_VF4) {
+                t -= 4 * S8_VF4;
+                d = r2;
+            }
+            d->cl[t >> 2] |= (uint32_t)(c & 0xFF) << (8 * (t & 3));
+            d->ch[t >> 2] |= (uint32_t)((c >> 8) & 0xFF) << (8 * (t & 3));
         }
     }
-    return 0;
+    return parts;
 }
 
 /* rows of transposed h-scaled lines any window of th output rows needs; == 2 (mod 4) for bank spread */
-static int s8_rows_cap(const S8VRow *rows, int n, int th)
+static int s8_rows_cap(const S8VRow *rows, const S8VRow *rows2, int n, int th)
 {
     int worst = 4, n4 = 0;
-    for (int y = 0; y < n; y++)            /* the kernel reads the bank's largest group count for every row */
-        if (rows[y].n4 > n4) n4 = rows[y].n4;
+    for (int y = 0; y < n; y++)            /* the bank's largest group count stands for every row */
+        if (rows[y].n4 + rows2[y].n4 > n4) n4 = rows[y].n4 + rows2[y].n4;
     for (int y = 0; y < n; y++) {
         const int y1 = y + th < n ? y + th : n;
         int lo = INT32_MAX, hi = 0;
@@ -2640,19 +2640,22 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
         return 0;
     if (!p->has_chroma || !p->dst_has_chroma || p->special || p->unscaled_lut)
         return 0;
-    if (hl->size > 16 || hc->size > 16 || vl->size > 16 || vc->size > 16)
-        return 0;
+    if (hl->size > 32 || hc->size > 32 || vl->size > 38 || vc->size > 38)
+        return 0;                     /* horizontal: 8 tap groups of four; vertical: two records of 20 taps (39 + parity pad) */
     if (hl->size > p->src_w || hc->size > p->chr_src_w || p->chr_dst_hsub > 1 || p->chr_dst_vsub > 1)
         return 0;
     const int fs = hl->size > hc->size ? hl->size : hc->size;
-    const int fs4 = fs <= 4 ? 1 : fs <= 8 ? 2 : 4;
+    int fs4 = fs <= 4 ? 1 : fs <= 8 ? 2 : fs <= 16 ? 4 : 8;
     const int cw = S8_TW >> p->chr_dst_hsub;
 
-    S8VRow *hvl = (S8VRow *)malloc(sizeof(S8VRow) * vl->len);
-    S8VRow *hvc = (S8VRow *)malloc(sizeof(S8VRow) * vc->len);
-    int ret = 0;
-    if (!hvl || !hvc || s8_pack_v(vl, hvl) < 0 || s8_pack_v(vc, hvc) < 0)
+    /* [0, len): first records, [len, 2 len): second records */
+    S8VRow *hvl = (S8VRow *)malloc(sizeof(S8VRow) * vl->len * 2);
+    S8VRow *hvc = (S8VRow *)malloc(sizeof(S8VRow) * vc->len * 2);
+    int ret = 0, lparts = 1, cparts = 1;
+    if (!hvl || !hvc || (lparts = s8_pack_v(vl, hvl, hvl + vl->len)) < 0 || (cparts = s8_pack_v(vc, hvc, hvc + vc->len)) < 0)
         ret = 1;
+    if (lparts == 2 || cparts == 2)
+        fs4 = 8;                      /* only the eight-group variants are compiled with the second vertical record */
     if (!ret && rgb && vl->size == 2 && vc->size == 2) {
         /* rows the reference hands to yuv2packed2 (both filters 2-tap bilinear) round without a bias
          * (vscale.c:148-163, output.c:1861-1864): flagged in bit 0 of the even first row */
@@ -2673,7 +2676,8 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     /* tensor-pipe horizontal stage when every 8-column window fits K <= 128 samples (SWS_B200_DISABLE=s8mma: A/B) */
     const bool inter = p->src_layout != SWSC_SRC_PLANAR;
     int mma = 0, ks = 0;
-    const bool plain = !p->range_mode && p->dst_kind != SWSC_DST_PLANARN;       /* what the MMA variants are compiled for */
+    /* what the MMA variants are compiled for: no range conversion, 8-bit output, vertical banks of one record */
+    const bool plain = !p->range_mode && p->dst_kind != SWSC_DST_PLANARN && lparts == 1 && cparts == 1;
     if (!ret && !s16 && !rgbs && plain && seg_l >= 0 && seg_c >= 0 &&
         !(getenv("SWS_B200_DISABLE") && strstr(getenv("SWS_B200_DISABLE"), "s8mma"))) {
         const int kl = s8_mma_ksteps(hl, S8_TW, false), kc = s8_mma_ksteps(hc, cw, inter);
@@ -2732,7 +2736,7 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
         for (int pass = 0; pass < 2 && slot <= 48 * 1024; pass++)
             for (int t = th_max; t >= 2; t >>= 1) {
                 const int cth = t >> p->chr_dst_vsub ? t >> p->chr_dst_vsub : 1;
-                const int nl = s8_rows_cap(hvl, vl->len, t), nc = s8_rows_cap(hvc, vc->len, cth);
+                const int nl = s8_rows_cap(hvl, hvl + vl->len, vl->len, t), nc = s8_rows_cap(hvc, hvc + vc->len, vc->len, cth);
                 const size_t lines = ((size_t)S8_TW * nl + 2 * (size_t)cw * nc) * 2 +
                                      (size_t)S8_ROWS * (seg_sy + 2 * seg_sc);     /* + the RGB readers' sample rows */
                 if (lines + 2 * (size_t)slot > budget[pass])
@@ -2745,8 +2749,8 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
         if (best_th) {
             th = best_th;
             const int cth = th >> p->chr_dst_vsub ? th >> p->chr_dst_vsub : 1;
-            nl_cap = s8_rows_cap(hvl, vl->len, th);
-            nc_cap = s8_rows_cap(hvc, vc->len, cth);
+            nl_cap = s8_rows_cap(hvl, hvl + vl->len, vl->len, th);
+            nc_cap = s8_rows_cap(hvc, hvc + vc->len, vc->len, cth);
             const size_t lines = ((size_t)S8_TW * nl_cap + 2 * (size_t)cw * nc_cap) * 2 + (size_t)S8_ROWS * (seg_sy + 2 * seg_sc);
             stages = (int)((budget[best_pass] - lines) / slot);
             if (stages > st_max) stages = st_max;
@@ -2764,7 +2768,7 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     o_hlp = take(sizeof(int) * hl->len); o_hcp = take(sizeof(int) * hc->len);
     o_hlcl = take(4 * (size_t)hl->len * fs4); o_hlch = take(4 * (size_t)hl->len * fs4);
     o_hccl = take(4 * (size_t)hc->len * fs4); o_hcch = take(4 * (size_t)hc->len * fs4);
-    o_vl = take(sizeof(S8VRow) * vl->len); o_vc = take(sizeof(S8VRow) * vc->len);
+    o_vl = take(sizeof(S8VRow) * vl->len * 2); o_vc = take(sizeof(S8VRow) * vc->len * 2);
     const int ngl = (hl->len + S8_TW - 1) / S8_TW * (S8_TW / 8) + 2, ngc = (hc->len + cw - 1) / cw * (cw / 8) + 2;
     size_t o_gl = 0, o_gc = 0, o_bl = 0, o_bc = 0;
     if (mma) {
@@ -2785,8 +2789,8 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
         if (hvl[y].n4 > st->s8_vl_n4) st->s8_vl_n4 = hvl[y].n4;
     for (int y = 0; y < vc->len; y++)
         if (hvc[y].n4 > st->s8_vc_n4) st->s8_vc_n4 = hvc[y].n4;
-    memcpy(host + o_vl, hvl, sizeof(S8VRow) * vl->len);
-    memcpy(host + o_vc, hvc, sizeof(S8VRow) * vc->len);
+    memcpy(host + o_vl, hvl, sizeof(S8VRow) * vl->len * 2);
+    memcpy(host + o_vc, hvc, sizeof(S8VRow) * vc->len * 2);
     if (mma) {
         s8_mma_tables(hl, S8_TW, false, ks, (int *)(host + o_gl), (uint32_t *)(host + o_bl));
         s8_mma_tables(hc, cw, inter, ks, (int *)(host + o_gc), (uint32_t *)(host + o_bc));
@@ -2802,6 +2806,8 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     st->s8_hl_cl = (uint32_t *)(t + o_hlcl); st->s8_hl_ch = (uint32_t *)(t + o_hlch);
     st->s8_hc_cl = (uint32_t *)(t + o_hccl); st->s8_hc_ch = (uint32_t *)(t + o_hcch);
     st->s8_vl = (S8VRow *)(t + o_vl); st->s8_vc = (S8VRow *)(t + o_vc);
+    st->s8_vl2 = lparts == 2 ? st->s8_vl + vl->len : nullptr;
+    st->s8_vc2 = cparts == 2 ? st->s8_vc + vc->len : nullptr;
     st->s8_fs4 = mma ? ks : fs4; st->s8_tile_h = th; st->s8_nl_cap = nl_cap; st->s8_nc_cap = nc_cap;
     st->s8_seg_l = seg_l; st->s8_seg_c = seg_c; st->s8_smem = smem; st->s8_slot = slot; st->s8_stages = stages; st->s8_srck = srck; st->s8_elt_shift = elt_shift;
     st->s8_seg_sy = seg_sy; st->s8_seg_sc = seg_sc;
@@ -2903,7 +2909,7 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     const bool rgb = p->dst_kind >= SWSC_DST_RGB24 && p->dst_kind <= SWSC_DST_ABGR;
     a.hl_pos = st->s8_hl_pos; a.hc_pos = st->s8_hc_pos;
     a.hl_cl = st->s8_hl_cl; a.hl_ch = st->s8_hl_ch; a.hc_cl = st->s8_hc_cl; a.hc_ch = st->s8_hc_ch;
-    a.vl = st->s8_vl; a.vc = st->s8_vc;
+    a.vl = st->s8_vl; a.vc = st->s8_vc; a.vl2 = st->s8_vl2; a.vc2 = st->s8_vc2;
     a.hl_goff = st->s8_hl_goff; a.hc_goff = st->s8_hc_goff; a.hl_B = st->s8_hl_B; a.hc_B = st->s8_hc_B;
     dim3 grid((p->dst_w + S8_TW - 1) / S8_TW, (y1 - y0 + st->s8_tile_h - 1) / st->s8_tile_h, nb_frames);
     pick_scale8(st->s8_fs4, rgb, st->s8_mma, st->s8_srck)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);

@@ -86,6 +86,10 @@ struct Scale8Args {
     const int *hl_pos, *hc_pos;
     const uint32_t *hl_cl, *hl_ch, *hc_cl, *hc_ch;
     const S8VRow *vl, *vc;
+    /* vertical banks of 21..40 taps (incl. the parity pad): the taps beyond the first 20 of every row, as a second
+     * record per row (first row = the first record's + 20; n4 = 0 and the same first row where a row has none);
+     * nullptr for banks that fit one record */
+    const S8VRow *vl2, *vc2;
     /* MMA horizontal stage: per group of 8 output columns the byte offset of its K window inside the staged
      * row, and the B fragments [group][KS][lo0 lo1 hi0 hi1][lane] */
     const int *hl_goff, *hc_goff;
@@ -346,6 +350,23 @@ __device__ __forceinline__ void s8_vfir(const uint32_t *hp, int cstep, const S8V
         out[c] = clip_u8(out[c] >> 19);
 }
 
+__device__ __forceinline__ S8VRow s8_load_vrow(const S8VRow *p);
+
+/* taps 21..40 of a row: the second record's sum added to `out` (rows without such taps have n4 = 0) */
+template <int NC>
+__device__ __forceinline__ void s8_vsum_more(const S8VRow *rec, const uint32_t *col0, int lo, int cstep, int (&out)[NC])
+{
+    const S8VRow v2 = s8_load_vrow(rec);
+    const int m4 = __shfl_sync(0xffffffffu, v2.n4, 0);
+    if (m4) {
+        int t[NC];
+        s8_vsum<NC>(col0 + (((v2.pos_even & ~1) - lo) >> 1), cstep, v2, m4, 0, t);
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+            out[c] += t[c];
+    }
+}
+
 __device__ __forceinline__ S8VRow s8_load_vrow(const S8VRow *p)
 {
     S8VRow r;
@@ -470,11 +491,19 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
         const int2 pn = __ldg(reinterpret_cast<const int2 *>(A.vl + ry0 + lane));
         lo_l = pn.x & ~1;
         hi_l = lo_l + 4 * pn.y;
+        if (FS4 == 8 && A.vl2) {
+            const int2 p2 = __ldg(reinterpret_cast<const int2 *>(A.vl2 + ry0 + lane));
+            hi_l = max(hi_l, (p2.x & ~1) + 4 * p2.y);
+        }
     }
     if (cy0 + lane < cy1) {
         const int2 pn = __ldg(reinterpret_cast<const int2 *>(A.vc + cy0 + lane));
         lo_c = pn.x;
         hi_c = pn.x + 4 * pn.y;
+        if (FS4 == 8 && A.vc2) {
+            const int2 p2 = __ldg(reinterpret_cast<const int2 *>(A.vc2 + cy0 + lane));
+            hi_c = max(hi_c, p2.x + 4 * p2.y);
+        }
     }
     lo_l = __reduce_min_sync(0xffffffffu, lo_l);
     hi_l = __reduce_max_sync(0xffffffffu, hi_l);
@@ -529,7 +558,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                         s8_tma_load(d, &map_u, bar, cx, row, f);
                         s8_tma_load(d + S8_ROWS * A.seg_c, &map_v, bar, cx, row, f);
                     } else {
-                        s8_tma_load(d, &map_u, bar, a0c >> 1, row, f);
+                        s8_tma_load(d, &map_u, bar, (a0c << 1) >> A.elt_shift, row, f);   /* two bytes per sample pair */
                     }
                 }
                 if (++b == A.stages) {
@@ -565,9 +594,12 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
         }
     };
 
-    /* The tensor-pipe variants are compiled without range conversion, 9..14-bit output and ordered dither (the
-     * host keeps those conversions on the dot-product variants): C4 pays 12 % in instructions for the checks. */
+    /* The tensor-pipe variants are compiled without range conversion, 9..14-bit output and ordered dither (the host
+     * keeps those conversions on the dot-product variants): C4 pays 12 % in instructions for the checks.  Vertical
+     * banks of more than 20 taps (a second record per row) run the eight-group variants only: X3 paid 6 % for
+     * carrying that code. */
     constexpr bool GEN = !MMA;
+    constexpr bool LONGV = FS4 == 8;      /* second vertical records: only the eight-group variants carry the code */
     const S8Range rcl = { GEN ? A.range_mode : 0, A.lum_rc_coeff, A.lum_rc_offset };
     const S8Range rcc = { GEN ? A.range_mode : 0, A.chr_rc_coeff, A.chr_rc_offset };
 
@@ -911,6 +943,12 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             s8_vsum<4>(hb_l + lane * lstride_w + (((vl.pos_even & ~1) - lo_l) >> 1), 32 * lstride_w, vl, ln4, bias, Y);
             s8_vsum<2>(hb_u + lane * cstride_w + ((vc.pos_even - lo_c) >> 1), 32 * cstride_w, vc, cn4, bias, U);
             s8_vsum<2>(hb_v + lane * cstride_w + ((vc.pos_even - lo_c) >> 1), 32 * cstride_w, vc, cn4, bias, V);
+            if (LONGV && A.vl2)
+                s8_vsum_more<4>(A.vl2 + y, hb_l + lane * lstride_w, lo_l, 32 * lstride_w, Y);
+            if (LONGV && A.vc2) {
+                s8_vsum_more<2>(A.vc2 + y, hb_u + lane * cstride_w, lo_c, 32 * cstride_w, U);
+                s8_vsum_more<2>(A.vc2 + y, hb_v + lane * cstride_w, lo_c, 32 * cstride_w, V);
+            }
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < 2; k++) {
@@ -984,6 +1022,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             const uint32_t *hp = hb_l + lane * lstride_w + ((vr.pos_even - lo_l) >> 1);
             int v[S8_TW / 32];
             s8_vsum<S8_TW / 32>(hp, 32 * lstride_w, vr, n4, 0, v);
+            if (LONGV && A.vl2)
+                s8_vsum_more<S8_TW / 32>(A.vl2 + y, hb_l + lane * lstride_w, lo_l, 32 * lstride_w, v);
             if (obits == 8) {
                 uint8_t *d = dst0 + (size_t)y * A.dst_stride[0] + x0 + lane;
                 /* lane + 32 c == lane (mod 8): one dither value per lane and row */
@@ -1025,6 +1065,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 for (int c = 0; 32 * c < CW; c += 2) {
                     int v[2];
                     s8_vsum<2>(hp + 32 * c * cstride_w, 32 * cstride_w, vr, n4, 0, v);
+                    if (LONGV && A.vc2)
+                        s8_vsum_more<2>(A.vc2 + y, (pl ? hb_v : hb_u) + (lane + 32 * c) * cstride_w, lo_c, 32 * cstride_w, v);
                     if (lane + 32 * c < cw)
                         d[dstep * c] = (uint8_t)clip_u8((v[0] + dz) >> 19);
                     if (lane + 32 * c + 32 < cw)
@@ -1035,6 +1077,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 for (int c = 0; 32 * c < CW; c += 2) {
                     int v[2];
                     s8_vsum<2>(hp + 32 * c * cstride_w, 32 * cstride_w, vr, n4, 0, v);
+                    if (LONGV && A.vc2)
+                        s8_vsum_more<2>(A.vc2 + y, (pl ? hb_v : hb_u) + (lane + 32 * c) * cstride_w, lo_c, 32 * cstride_w, v);
                     if (lane + 32 * c < cw)
                         d[32 * c] = (uint16_t)clip_uintp2((v[0] + (1 << (oshift - 1))) >> oshift, obits);
                     if (lane + 32 * c + 32 < cw)

@@ -30,7 +30,9 @@ def test_fate_sws_yuv_colorspace(vsynth1):  # noqa: F811
 
 @pytest.mark.parametrize("sf,df", [("yuv420p", "yuv420p"), ("nv12", "yuv444p"), ("yuv422p", "nv12"), ("yuv420p10le", "yuv420p"),
                                    # > 8-bit destinations go through bgr48le (utils.c:928-934): the 16-bit RGB readers
-                                   ("yuv420p10le", "yuv420p10le"), ("yuv420p", "yuv444p16le"), ("yuv422p12le", "p010le")])
+                                   ("yuv420p10le", "yuv420p10le"), ("yuv420p", "yuv444p16le"), ("yuv422p12le", "p010le"),
+                                   # a float gray destination is neither isNBPS nor is16BPS: bgr24 again (fuzz seeds 402, 403)
+                                   ("nv21", "grayf32le"), ("yuv420p12le", "grayf32le")])
 @pytest.mark.parametrize("geom", [(352, 288, 352, 288), (640, 360, 320, 180), (320, 180, 500, 300)])
 @pytest.mark.parametrize("cs", [(1, 0, 5, 1), (5, 1, 1, 0, 2000, 70000, 60000), (9, 0, 1, 0)])
 def test_yuv_matrix_change(sf, df, geom, cs):

@@ -143,3 +143,40 @@ def test_packed_rgb_source_slices_strides_colorspace():
 def test_4k_bgra_to_1080p_nv12_full_size():
     case = dict(sw=3840, sh=2160, sf="bgra", dw=1920, dh=1080, df="nv12", flags=S.SWS_BICUBIC | BX)
     assert _run(case) == "scale_rgb_dp2a"
+
+
+# ---- 17..32 horizontal taps (eight tap groups) and 21..40 vertical taps (a second record per row) ----
+LONG_GEOMS = [
+    ((1920, 1080, 320, 180), S.SWS_BICUBIC),     # 6:1, 24 taps both ways
+    ((1280, 720, 160, 90), S.SWS_BICUBIC),       # 8:1, 32 taps
+    ((1280, 720, 426, 240), S.SWS_LANCZOS),      # 3:1 lanczos, 19 taps
+    ((640, 1080, 640, 200), S.SWS_BICUBIC),      # vertical only, 5.4:1
+    ((1920, 360, 300, 360), S.SWS_BILINEAR),     # horizontal only, 6.4:1
+    ((1000, 600, 130, 70), S.SWS_GAUSS),
+]
+
+
+@pytest.mark.parametrize("sf,df", [("yuv420p", "yuv420p"), ("nv12", "yuv420p"), ("yuv420p", "rgb24"), ("yuv422p", "yuv420p"),
+                                   ("yuvj420p", "yuv420p"), ("yuv420p", "yuv420p10le"),
+                                   ("yuv420p10le", "yuv420p10le"), ("yuv422p10le", "yuv420p"), ("yuv444p12le", "nv12"),
+                                   ("bgra", "yuv420p"), ("rgb24", "nv12")])
+@pytest.mark.parametrize("geom,flags", LONG_GEOMS)
+def test_long_filters(sf, df, geom, flags):
+    sw, sh, dw, dh = geom
+    case = dict(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags | BX)
+    names = set()
+    for mode in ("noise", "extreme"):
+        names.add(_run(case, mode=mode))
+    # whatever kernel took it, the bytes are the reference's; the family is expected where its limits allow
+    # (32 horizontal / 38 vertical taps per bank, 2 KB of staged row)
+    if sf in ("yuv420p", "nv12", "yuvj420p") and (sw, sh, dw, dh) != (1280, 720, 160, 90):
+        assert names <= {"scale8_mma", "scale8_dp4a"}, names
+
+
+def test_long_filters_slices():
+    case = dict(sw=1280, sh=720, sf="yuv420p", dw=213, dh=120, df="yuv420p", flags=S.SWS_BICUBIC | BX)
+    src = T.Frame("yuv420p", 1280, 720).randomize(7)
+    slices = [(y, min(180, 720 - y)) for y in range(0, 720, 180)]
+    want, _ = T.run_reference(src=src, slices=slices, **case)
+    got, name = T.run_cuda(src=src, slices=slices, **case)
+    assert T.first_diff(got.valid(), want.valid()) is None, name

@@ -29,7 +29,11 @@ def test_mma_hstage_matches_reference(sf, df, geom, flags):
     want, _ = T.run_reference(src=src, **case)
     got, name = T.run_cuda(src=src, **case)
     assert T.first_diff(got.valid(), want.valid()) is None, name
-    if name.startswith("scale8"):
+    # a 4:2:2 / 4:4:4 source into a vertically subsampled destination doubles the vertical chroma ratio: past 20 taps
+    # the bank needs a second record per row, which only the dot-product variant carries
+    vsub_s = sf in ("yuv420p", "nv12", "nv21")
+    vsub_d = df in ("yuv420p", "nv12")
+    if name.startswith("scale8") and not (vsub_d and not vsub_s):
         assert name == "scale8_mma", name
 
 
