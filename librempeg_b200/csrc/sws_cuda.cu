@@ -1670,7 +1670,7 @@ struct SwsCudaState {
     int fast_narrow;             /* the 128 x 64 tile shape of the fast420 kernel is set up and preferred */
     int4 *d_fast_rows_narrow;
     int fasthi8_ok, fasthi8_crows;
-    int s8_stages, s8_srck, s8_elt_shift, s8_seg_sy, s8_seg_sc;
+    int s8_stages, s8_srck, s8_elt_shift, s8_seg_sy, s8_seg_sc, s8_wide;
     int s8_ok, s8_fs4, s8_tile_h, s8_nl_cap, s8_nc_cap, s8_seg_l, s8_seg_c, s8_slot, s8_vl_n4, s8_vc_n4;
     size_t s8_smem;
     void *s8_tables;
@@ -2338,8 +2338,11 @@ static int fasthi8_launch(SwsCudaState *st, const uint8_t *const src[4], const i
 /* ---------------------------------------------------------------- scale8 host side */
 
 typedef void (*scale8_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Scale8Args);
-static scale8_kernel_t pick_scale8(int fs4, bool rgb, bool mma, int srck)
+static scale8_kernel_t pick_scale8(int fs4, bool rgb, bool mma, int srck, bool wide = false)
 {
+    /* `wide`: the tile's shared memory admits at most three CTAs per SM: take the 72-register build */
+    if (wide && mma && !rgb && srck == S8_SRC_U8 && fs4 <= 2)
+        return fs4 == 1 ? sws_scale8_kernel<1, false, true, S8_SRC_U8, 3> : sws_scale8_kernel<2, false, true, S8_SRC_U8, 3>;
 #define S8_PICK(R, M, K) (fs4 == 1 ? sws_scale8_kernel<1, R, M, K> : fs4 == 2 ? sws_scale8_kernel<2, R, M, K> \
                           : fs4 == 4 ? sws_scale8_kernel<4, R, M, K> : sws_scale8_kernel<8, R, M, K>)
 #define S8_PICK_MMA(R) (fs4 == 1 ? sws_scale8_kernel<1, R, true, S8_SRC_U8> : fs4 == 2 ? sws_scale8_kernel<2, R, true, S8_SRC_U8> \
@@ -2810,13 +2813,14 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     st->s8_vc2 = cparts == 2 ? st->s8_vc + vc->len : nullptr;
     st->s8_fs4 = mma ? ks : fs4; st->s8_tile_h = th; st->s8_nl_cap = nl_cap; st->s8_nc_cap = nc_cap;
     st->s8_seg_l = seg_l; st->s8_seg_c = seg_c; st->s8_smem = smem; st->s8_slot = slot; st->s8_stages = stages; st->s8_srck = srck; st->s8_elt_shift = elt_shift;
+    st->s8_wide = 4 * (smem + 1024) > 227 * 1024;
     st->s8_seg_sy = seg_sy; st->s8_seg_sc = seg_sc;
     st->s8_mma = mma;
     if (mma) {
         st->s8_hl_goff = (int *)(t + o_gl); st->s8_hc_goff = (int *)(t + o_gc);
         st->s8_hl_B = (uint32_t *)(t + o_bl); st->s8_hc_B = (uint32_t *)(t + o_bc);
     }
-    CUDA_OK(set_max_smem((const void *)pick_scale8(st->s8_fs4, rgb, mma, srck), (size_t)((int)smem)));
+    CUDA_OK(set_max_smem((const void *)pick_scale8(st->s8_fs4, rgb, mma, srck, st->s8_wide), (size_t)((int)smem)));
     st->s8_ok = 1;
     if (getenv("SWS_B200_DEBUG"))
         fprintf(stderr, "[swscaler-b200] scale8: %s fs4=%d tile_h=%d nl_cap=%d nc_cap=%d seg_l=%d seg_c=%d slot=%d stages=%d smem=%zu\n",
@@ -2912,7 +2916,7 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.vl = st->s8_vl; a.vc = st->s8_vc; a.vl2 = st->s8_vl2; a.vc2 = st->s8_vc2;
     a.hl_goff = st->s8_hl_goff; a.hc_goff = st->s8_hc_goff; a.hl_B = st->s8_hl_B; a.hc_B = st->s8_hc_B;
     dim3 grid((p->dst_w + S8_TW - 1) / S8_TW, (y1 - y0 + st->s8_tile_h - 1) / st->s8_tile_h, nb_frames);
-    pick_scale8(st->s8_fs4, rgb, st->s8_mma, st->s8_srck)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
+    pick_scale8(st->s8_fs4, rgb, st->s8_mma, st->s8_srck, st->s8_wide)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
     st->kernel_name = rgbs ? "scale_rgb_dp2a" : st->s8_srck == S8_SRC_U16 ? "scale16_dp2a" : st->s8_mma ? "scale8_mma" : "scale8_dp4a";
     CUDA_OK(cudaGetLastError());
     st->launches++;

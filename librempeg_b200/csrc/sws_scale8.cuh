@@ -310,11 +310,11 @@ __device__ __forceinline__ int s16_hfir(const unsigned char *srow, int sh, int h
 }
 
 /* vertical FIR for NC columns (transposed 15-bit lines, cstep words apart): bias + sum of taps, before
- * the >> 19; n4 = tap groups in use by any row of the bank (kernel argument, warp-uniform), rows with
- * fewer have zero taps there.  Columns are the inner loop: 2 NC independent accumulator chains. */
-template <int NC>
-__device__ __forceinline__ void s8_vsum(const uint32_t *hp, int cstep, const S8VRow &vr, int n4, int bias,
-                                        int (&out)[NC])
+ * the >> 19.  G = tap groups of four in use by this row (warp-uniform): the body is compiled once per group count
+ * and picked with one switch -- the former `if (k < n4)` cascade cost 10 instructions per call and kept the
+ * compiler from hoisting the column addresses.  Columns are the inner loop: 2 NC independent accumulator chains. */
+template <int NC, int G>
+__device__ __forceinline__ void s8_vsum_g(const uint32_t *hp, int cstep, const S8VRow &vr, int bias, int (&out)[NC])
 {
     int acc_l[NC], acc_h[NC];
 #pragma unroll
@@ -323,21 +323,32 @@ __device__ __forceinline__ void s8_vsum(const uint32_t *hp, int cstep, const S8V
         acc_h[c] = 0;
     }
 #pragma unroll
-    for (int k = 0; k < S8_VF4; k++) {
-        if (k < n4) {
+    for (int k = 0; k < G; k++) {
 #pragma unroll
-            for (int c = 0; c < NC; c++) {
-                const uint32_t w0 = hp[c * cstep + 2 * k], w1 = hp[c * cstep + 2 * k + 1];
-                acc_l[c] = dp2a_lo_su(w0, vr.cl[k], acc_l[c]);
-                acc_h[c] = dp2a_lo_ss(w0, vr.ch[k], acc_h[c]);
-                acc_l[c] = dp2a_hi_su(w1, vr.cl[k], acc_l[c]);
-                acc_h[c] = dp2a_hi_ss(w1, vr.ch[k], acc_h[c]);
-            }
+        for (int c = 0; c < NC; c++) {
+            const uint32_t w0 = hp[c * cstep + 2 * k], w1 = hp[c * cstep + 2 * k + 1];
+            acc_l[c] = dp2a_lo_su(w0, vr.cl[k], acc_l[c]);
+            acc_h[c] = dp2a_lo_ss(w0, vr.ch[k], acc_h[c]);
+            acc_l[c] = dp2a_hi_su(w1, vr.cl[k], acc_l[c]);
+            acc_h[c] = dp2a_hi_ss(w1, vr.ch[k], acc_h[c]);
         }
     }
 #pragma unroll
     for (int c = 0; c < NC; c++)
         out[c] = (acc_h[c] << 8) + acc_l[c];
+}
+
+template <int NC>
+__device__ __forceinline__ void s8_vsum(const uint32_t *hp, int cstep, const S8VRow &vr, int n4, int bias,
+                                        int (&out)[NC])
+{
+    switch (n4) {
+    case 1:  s8_vsum_g<NC, 1>(hp, cstep, vr, bias, out); break;
+    case 2:  s8_vsum_g<NC, 2>(hp, cstep, vr, bias, out); break;
+    case 3:  s8_vsum_g<NC, 3>(hp, cstep, vr, bias, out); break;
+    case 4:  s8_vsum_g<NC, 4>(hp, cstep, vr, bias, out); break;
+    default: s8_vsum_g<NC, S8_VF4>(hp, cstep, vr, bias, out); break;
+    }
 }
 
 /* planar 8-bit output: dither 64 for 8-bit sources (swscale.c:54-56,385-387), clip */
@@ -451,8 +462,11 @@ __device__ __forceinline__ void s8_hfir_uv(const unsigned char *srow, int sh, co
  *           de-interleaved on the fly).
  *  V:       warp = output row, lane = columns lane + 32k.
  */
-template <int FS4, bool RGB, bool MMA, int SRCK>
-__global__ void __launch_bounds__(S8_THREADS, (SRCK != S8_SRC_U8 || (MMA && FS4 > 2)) ? 3 : (RGB || FS4 <= S8_LIGHT_FS4) ? S8_RGB_CTAS : 3)
+/* MINB = 3: the same kernel compiled for three CTAs per SM (72 registers instead of 56) -- picked when the tile's
+ * shared memory allows no more than three anyway (C4: 45.5 -> 47.5 % of the HBM peak; X1 / X2, which fit four,
+ * lose 0.7 points with it and keep the 56-register build) */
+template <int FS4, bool RGB, bool MMA, int SRCK, int MINB = 0>
+__global__ void __launch_bounds__(S8_THREADS, MINB ? MINB : (SRCK != S8_SRC_U8 || (MMA && FS4 > 2)) ? 3 : (RGB || FS4 <= S8_LIGHT_FS4) ? S8_RGB_CTAS : 3)
 sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_u,
                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ Scale8Args A)
 {
