@@ -2634,7 +2634,8 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
         return 0;
     /* destinations: 8-bit planar / semi-planar YUV, 9..14-bit planar YUV, or packed 8-bit RGB with one chroma
      * sample per pixel pair */
-    const bool rgb = p->dst_kind >= SWSC_DST_RGB24 && p->dst_kind <= SWSC_DST_ABGR;
+    const bool rgb = (p->dst_kind >= SWSC_DST_RGB24 && p->dst_kind <= SWSC_DST_ABGR) ||
+                     (p->dst_kind >= SWSC_DST_RGB565 && p->dst_kind <= SWSC_DST_BGR555);
     if (rgb && (p->chr_dst_hsub != 1 || p->chr_dst_vsub != 0 || p->full_chr || p->special || p->unscaled_lut ||
                 !p->has_chroma))
         return 0;
@@ -2910,7 +2911,8 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.vl_n4 = st->s8_vl_n4; a.vc_n4 = st->s8_vc_n4;
     a.cy = p->rgb.cy; a.yb = p->rgb.yb; a.base_r = p->rgb.base_r; a.base_g = p->rgb.base_g; a.base_b = p->rgb.base_b;
     a.crv = p->rgb.crv; a.cgu = p->rgb.cgu; a.cgv = p->rgb.cgv; a.cbu = p->rgb.cbu;
-    const bool rgb = p->dst_kind >= SWSC_DST_RGB24 && p->dst_kind <= SWSC_DST_ABGR;
+    const bool rgb = (p->dst_kind >= SWSC_DST_RGB24 && p->dst_kind <= SWSC_DST_ABGR) ||
+                     (p->dst_kind >= SWSC_DST_RGB565 && p->dst_kind <= SWSC_DST_BGR555);
     a.hl_pos = st->s8_hl_pos; a.hc_pos = st->s8_hc_pos;
     a.hl_cl = st->s8_hl_cl; a.hl_ch = st->s8_hl_ch; a.hc_cl = st->s8_hc_cl; a.hc_ch = st->s8_hc_ch;
     a.vl = st->s8_vl; a.vc = st->s8_vc; a.vl2 = st->s8_vl2; a.vc2 = st->s8_vc2;

@@ -935,7 +935,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
          * lane = pairs lane and lane + 32 (yuv2rgb_X/_1/_2_c_template + yuv2rgb_write, output.c:1662-1939;
          * the byte LUTs in closed form as in the other RGB kernels) ============ */
         const int kind = A.dst_kind;
-        const int bpp = kind >= SWSC_DST_RGBA ? 4 : 3;
+        const bool rgb16 = kind >= SWSC_DST_RGB565;              /* 15/16 bpp: rgb565le, bgr565le, rgb555le, bgr555le */
+        const int bpp = rgb16 ? 2 : kind >= SWSC_DST_RGBA ? 4 : 3;
         unsigned char *orow = s8_smem_raw + warp * 512;          /* the ring is idle now: 512 B of row staging per warp */
         const int cy = A.cy, yb = A.yb;
         S8VRow vl, vc;
@@ -975,7 +976,23 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 const uint32_t tRb = y2v * cy + pR, tGb = y2v * cy + pG, tBb = y2v * cy + pB;
                 constexpr uint32_t FF = 0x00FF0000u;
                 const int p = lane + 32 * k;
-                if (bpp == 3) {
+                if (rgb16) {
+                    /* yuv2rgb_write, 15/16 bpp (output.c:1714-1747; tables yuv2rgb.c:878-900): the 2 x 2 ordered-dither
+                     * offsets move the LUT index (ff_dither_2x2_8 = {6,2 / 0,4}, ff_dither_2x2_4 = {1,3 / 2,0}), then
+                     * the bytes are truncated into their fields */
+                    const int odd = y & 1;
+                    const bool is565 = kind <= SWSC_DST_BGR565;
+                    const int dr1 = odd ? 0 : 6, dr2 = odd ? 4 : 2, db1 = odd ? 6 : 0, db2 = odd ? 2 : 4;
+                    const int dg1 = is565 ? (odd ? 2 : 1) : dr2, dg2 = is565 ? (odd ? 0 : 3) : dr1;
+                    const int gsh = is565 ? 2 : 3, hi = is565 ? 11 : 10;
+                    const int r1 = clamp_u8((int)(tRa + dr1 * cy) >> 16) >> 3, r2 = clamp_u8((int)(tRb + dr2 * cy) >> 16) >> 3;
+                    const int g1 = clamp_u8((int)(tGa + dg1 * cy) >> 16) >> gsh, g2 = clamp_u8((int)(tGb + dg2 * cy) >> 16) >> gsh;
+                    const int b1 = clamp_u8((int)(tBa + db1 * cy) >> 16) >> 3, b2 = clamp_u8((int)(tBb + db2 * cy) >> 16) >> 3;
+                    const bool rfirst = kind == SWSC_DST_RGB565 || kind == SWSC_DST_RGB555;   /* R in the high bits */
+                    const uint32_t p1 = rfirst ? (r1 << hi) | (g1 << 5) | b1 : (b1 << hi) | (g1 << 5) | r1;
+                    const uint32_t p2 = rfirst ? (r2 << hi) | (g2 << 5) | b2 : (b2 << hi) | (g2 << 5) | r2;
+                    *reinterpret_cast<uint32_t *>(orow + 4 * p) = p1 | (p2 << 16);
+                } else if (bpp == 3) {
                     uint32_t h0, h1, h2;
                     if (kind == SWSC_DST_RGB24) {
                         h0 = clamp_u8x2(prmt(tRa, tGa, 0x7632)); h1 = clamp_u8x2(prmt(tBa, tRb, 0x7632));

@@ -180,3 +180,17 @@ def test_long_filters_slices():
     want, _ = T.run_reference(src=src, slices=slices, **case)
     got, name = T.run_cuda(src=src, slices=slices, **case)
     assert T.first_diff(got.valid(), want.valid()) is None, name
+
+
+# ---- 15/16 bpp packed RGB out of the scaling kernel (2 x 2 ordered dither of yuv2rgb_write, output.c:1714-1747) ----
+@pytest.mark.parametrize("df", ["rgb565le", "bgr565le", "rgb555le", "bgr555le"])
+@pytest.mark.parametrize("sf", ["yuv420p", "nv12", "yuv422p", "yuv420p10le", "bgra", "rgb24"])
+@pytest.mark.parametrize("geom,flags", [((322, 182, 400, 300), S.SWS_BICUBIC), ((640, 360, 320, 180), S.SWS_BILINEAR),
+                                        ((322, 182, 322, 182), S.SWS_BICUBIC), ((323, 181, 401, 301), S.SWS_LANCZOS),
+                                        ((176, 144, 352, 288), S.SWS_BICUBIC)])
+def test_rgb16bpp_out_of_the_scaling_kernel(df, sf, geom, flags):
+    sw, sh, dw, dh = geom
+    case = dict(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags | BX)
+    for mode in ("noise", "extreme"):
+        name = _run(case, mode=mode)
+        assert name.startswith("scale"), name
