@@ -2338,24 +2338,27 @@ static int fasthi8_launch(SwsCudaState *st, const uint8_t *const src[4], const i
 /* ---------------------------------------------------------------- scale8 host side */
 
 typedef void (*scale8_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Scale8Args);
-static scale8_kernel_t pick_scale8(int fs4, bool rgb, bool mma, int srck, bool wide = false)
+static scale8_kernel_t pick_scale8(int fs4, int rgbk, bool mma, int srck, bool wide = false)
 {
-    /* `wide`: the tile's shared memory admits at most three CTAs per SM: take the 72-register build */
-    if (wide && mma && !rgb && srck == S8_SRC_U8 && fs4 <= 2)
-        return fs4 == 1 ? sws_scale8_kernel<1, false, true, S8_SRC_U8, 3> : sws_scale8_kernel<2, false, true, S8_SRC_U8, 3>;
+    /* rgbk: 0 planar output, 1 packed RGB with shared chroma, 2 packed RGB with full chroma.
+     * `wide`: the tile's shared memory admits at most three CTAs per SM: take the 72-register build */
+    if (wide && mma && !rgbk && srck == S8_SRC_U8 && fs4 <= 2)
+        return fs4 == 1 ? sws_scale8_kernel<1, 0, true, S8_SRC_U8, 3> : sws_scale8_kernel<2, 0, true, S8_SRC_U8, 3>;
 #define S8_PICK(R, M, K) (fs4 == 1 ? sws_scale8_kernel<1, R, M, K> : fs4 == 2 ? sws_scale8_kernel<2, R, M, K> \
                           : fs4 == 4 ? sws_scale8_kernel<4, R, M, K> : sws_scale8_kernel<8, R, M, K>)
 #define S8_PICK_MMA(R) (fs4 == 1 ? sws_scale8_kernel<1, R, true, S8_SRC_U8> : fs4 == 2 ? sws_scale8_kernel<2, R, true, S8_SRC_U8> \
                         : sws_scale8_kernel<4, R, true, S8_SRC_U8>)
+#define S8_PICK_K(M, K) (rgbk == 2 ? S8_PICK(2, M, K) : rgbk == 1 ? S8_PICK(1, M, K) : S8_PICK(0, M, K))
     if (srck == S8_SRC_RGB)     /* packed 8-bit RGB sources: reader stage + IDP.2A horizontal stage */
-        return rgb ? S8_PICK(true, false, S8_SRC_RGB) : S8_PICK(false, false, S8_SRC_RGB);
+        return S8_PICK_K(false, S8_SRC_RGB);
     if (srck == S8_SRC_U16)     /* 9..16-bit planar sources: IDP.2A horizontal stage */
-        return rgb ? S8_PICK(true, false, S8_SRC_U16) : S8_PICK(false, false, S8_SRC_U16);
+        return S8_PICK_K(false, S8_SRC_U16);
     if (mma)                    /* fs4 = K steps of the tensor-pipe horizontal stage */
-        return rgb ? S8_PICK_MMA(true) : S8_PICK_MMA(false);
-    return rgb ? S8_PICK(true, false, S8_SRC_U8) : S8_PICK(false, false, S8_SRC_U8);
+        return rgbk == 2 ? S8_PICK_MMA(2) : rgbk == 1 ? S8_PICK_MMA(1) : S8_PICK_MMA(0);
+    return S8_PICK_K(false, S8_SRC_U8);
 #undef S8_PICK
 #undef S8_PICK_MMA
+#undef S8_PICK_K
 }
 
 /* ---- tensor-pipe horizontal stage: per group of 8 output columns, the K window and the banded B fragments ----
@@ -2636,8 +2639,10 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
      * sample per pixel pair */
     const bool rgb = (p->dst_kind >= SWSC_DST_RGB24 && p->dst_kind <= SWSC_DST_ABGR) ||
                      (p->dst_kind >= SWSC_DST_RGB565 && p->dst_kind <= SWSC_DST_BGR555);
-    if (rgb && (p->chr_dst_hsub != 1 || p->chr_dst_vsub != 0 || p->full_chr || p->special || p->unscaled_lut ||
-                !p->has_chroma))
+    /* one chroma sample per pixel pair (yuv2rgb_{X,2,1} + yuv2rgb_write), or SWS_FULL_CHR_H_INT: one per pixel and the
+     * arithmetic colour step (yuv2rgb_full_{X,2,1} + yuv2rgb_write_full) */
+    if (rgb && (p->chr_dst_hsub != (p->full_chr ? 0 : 1) || p->chr_dst_vsub != 0 || p->special || p->unscaled_lut ||
+                !p->has_chroma || (p->full_chr && p->dst_kind > SWSC_DST_ABGR)))
         return 0;
     if (!rgb && p->dst_kind != SWSC_DST_PLANAR8 && p->dst_kind != SWSC_DST_NV12 && p->dst_kind != SWSC_DST_NV21 &&
         !(p->dst_kind == SWSC_DST_PLANARN && p->dst_bits >= 9 && p->dst_bits <= 14 && !p->dst_shift))
@@ -2660,6 +2665,15 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
         ret = 1;
     if (lparts == 2 || cparts == 2)
         fs4 = 8;                      /* only the eight-group variants are compiled with the second vertical record */
+    if (!ret && rgb && p->full_chr && vl->size == 1 && vc->size == 2) {
+        /* yuv2rgb_full_1 with two chroma taps (vscale.c:138-143) blends chroma without the rounding bias:
+         * flagged in bit 0 of the chroma row */
+        for (int y = 0; y < vc->len; y++) {
+            const int c0 = vc->coef[2 * y], c1 = vc->coef[2 * y + 1];
+            if (c0 + c1 == 4096 && (unsigned)c1 <= 4096u)
+                hvc[y].pos_even |= 1;
+        }
+    }
     if (!ret && rgb && vl->size == 2 && vc->size == 2) {
         /* rows the reference hands to yuv2packed2 (both filters 2-tap bilinear) round without a bias
          * (vscale.c:148-163, output.c:1861-1864): flagged in bit 0 of the even first row */
@@ -2821,7 +2835,7 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
         st->s8_hl_goff = (int *)(t + o_gl); st->s8_hc_goff = (int *)(t + o_gc);
         st->s8_hl_B = (uint32_t *)(t + o_bl); st->s8_hc_B = (uint32_t *)(t + o_bc);
     }
-    CUDA_OK(set_max_smem((const void *)pick_scale8(st->s8_fs4, rgb, mma, srck, st->s8_wide), (size_t)((int)smem)));
+    CUDA_OK(set_max_smem((const void *)pick_scale8(st->s8_fs4, rgb ? (p->full_chr ? 2 : 1) : 0, mma, srck, st->s8_wide), (size_t)((int)smem)));
     st->s8_ok = 1;
     if (getenv("SWS_B200_DEBUG"))
         fprintf(stderr, "[swscaler-b200] scale8: %s fs4=%d tile_h=%d nl_cap=%d nc_cap=%d seg_l=%d seg_c=%d slot=%d stages=%d smem=%zu\n",
@@ -2911,6 +2925,8 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.vl_n4 = st->s8_vl_n4; a.vc_n4 = st->s8_vc_n4;
     a.cy = p->rgb.cy; a.yb = p->rgb.yb; a.base_r = p->rgb.base_r; a.base_g = p->rgb.base_g; a.base_b = p->rgb.base_b;
     a.crv = p->rgb.crv; a.cgu = p->rgb.cgu; a.cgv = p->rgb.cgv; a.cbu = p->rgb.cbu;
+    a.full_chr = p->full_chr; a.y_offset = p->rgb.y_offset; a.y_coeff = p->rgb.y_coeff;
+    a.v2r = p->rgb.v2r; a.v2g = p->rgb.v2g; a.u2g = p->rgb.u2g; a.u2b = p->rgb.u2b;
     const bool rgb = (p->dst_kind >= SWSC_DST_RGB24 && p->dst_kind <= SWSC_DST_ABGR) ||
                      (p->dst_kind >= SWSC_DST_RGB565 && p->dst_kind <= SWSC_DST_BGR555);
     a.hl_pos = st->s8_hl_pos; a.hc_pos = st->s8_hc_pos;
@@ -2918,7 +2934,7 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.vl = st->s8_vl; a.vc = st->s8_vc; a.vl2 = st->s8_vl2; a.vc2 = st->s8_vc2;
     a.hl_goff = st->s8_hl_goff; a.hc_goff = st->s8_hc_goff; a.hl_B = st->s8_hl_B; a.hc_B = st->s8_hc_B;
     dim3 grid((p->dst_w + S8_TW - 1) / S8_TW, (y1 - y0 + st->s8_tile_h - 1) / st->s8_tile_h, nb_frames);
-    pick_scale8(st->s8_fs4, rgb, st->s8_mma, st->s8_srck, st->s8_wide)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
+    pick_scale8(st->s8_fs4, rgb ? (p->full_chr ? 2 : 1) : 0, st->s8_mma, st->s8_srck, st->s8_wide)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
     st->kernel_name = rgbs ? "scale_rgb_dp2a" : st->s8_srck == S8_SRC_U16 ? "scale16_dp2a" : st->s8_mma ? "scale8_mma" : "scale8_dp4a";
     CUDA_OK(cudaGetLastError());
     st->launches++;

@@ -68,6 +68,9 @@ struct Scale8Args {
     int y0, y1, tile_h;
     int nl_cap, nc_cap;
     int cy, yb, base_r, base_g, base_b, crv, cgu, cgv, cbu;   /* packed RGB output: closed-form LUT constants */
+    /* packed RGB output with full horizontal chroma (SWS_FULL_CHR_H_INT: odd widths, 4:4:4 sources): one U, V pair per
+     * pixel and the arithmetic colour step of yuv2rgb_write_full (output.c:1998-2051) */
+    int full_chr, y_offset, y_coeff, v2r, v2g, u2g, u2b;
     int vl_n4, vc_n4;        /* vertical tap groups of four in use (max over rows) */
     int seg_l, seg_c;        /* staged bytes per luma row / chroma samples per chroma row */
     int slot_bytes;          /* one ring slot: max(8 luma rows, 8 rows of both chroma planes), 128-byte multiple */
@@ -465,11 +468,14 @@ __device__ __forceinline__ void s8_hfir_uv(const unsigned char *srow, int sh, co
 /* MINB = 3: the same kernel compiled for three CTAs per SM (72 registers instead of 56) -- picked when the tile's
  * shared memory allows no more than three anyway (C4: 45.5 -> 47.5 % of the HBM peak; X1 / X2, which fit four,
  * lose 0.7 points with it and keep the 56-register build) */
-template <int FS4, bool RGB, bool MMA, int SRCK, int MINB = 0>
-__global__ void __launch_bounds__(S8_THREADS, MINB ? MINB : (SRCK != S8_SRC_U8 || (MMA && FS4 > 2)) ? 3 : (RGB || FS4 <= S8_LIGHT_FS4) ? S8_RGB_CTAS : 3)
+/* RGBK: 0 planar / semi-planar YUV output, 1 packed RGB with one chroma sample per pixel pair, 2 packed RGB with full
+ * horizontal chroma (its own instantiation: carried as a run-time branch it cost X1 10 %) */
+template <int FS4, int RGBK, bool MMA, int SRCK, int MINB = 0>
+__global__ void __launch_bounds__(S8_THREADS, MINB ? MINB : (SRCK != S8_SRC_U8 || (MMA && FS4 > 2)) ? 3 : (RGBK || FS4 <= S8_LIGHT_FS4) ? S8_RGB_CTAS : 3)
 sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_u,
                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ Scale8Args A)
 {
+    constexpr bool RGB = RGBK != 0;
     constexpr bool S16 = SRCK == S8_SRC_U16;      /* 16-bit samples straight from the ring */
     constexpr bool RGBS = SRCK == S8_SRC_RGB;     /* packed 8-bit RGB rows in the ring, converted to 14-bit Y/U/V samples per slot */
     extern __shared__ __align__(128) unsigned char s8_smem_raw[];
@@ -512,11 +518,11 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     }
     if (cy0 + lane < cy1) {
         const int2 pn = __ldg(reinterpret_cast<const int2 *>(A.vc + cy0 + lane));
-        lo_c = pn.x;
-        hi_c = pn.x + 4 * pn.y;
+        lo_c = pn.x & ~1;            /* (bit 0 of an RGB row: a rounding flag, see the V stage) */
+        hi_c = lo_c + 4 * pn.y;
         if (FS4 == 8 && A.vc2) {
             const int2 p2 = __ldg(reinterpret_cast<const int2 *>(A.vc2 + cy0 + lane));
-            hi_c = max(hi_c, p2.x + 4 * p2.y);
+            hi_c = max(hi_c, (p2.x & ~1) + 4 * p2.y);
         }
     }
     lo_l = __reduce_min_sync(0xffffffffu, lo_l);
@@ -594,6 +600,11 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     uint32_t *hb_l = reinterpret_cast<uint32_t *>(s8_smem_raw + A.stages * slot);
     uint32_t *hb_u = hb_l + S8_TW * lstride_w;
     uint32_t *hb_v = hb_u + CW * cstride_w;
+    /* full-chroma RGB output: chroma columns are stored like the luma columns of the RGB variant, even columns in
+     * slots 0..63, odd ones in 64..127, so that a lane of the V stage finds the chroma of its four pixels at the
+     * luma's conflict-free stride */
+    constexpr bool fullc = RGBK == 2;
+    auto cslot = [&](int x) { return fullc ? (x >> 1) + 64 * (x & 1) : x; };
 
     /* ring position of the pass being filtered: slot sb, parity sphase */
     int sb = 0;
@@ -730,8 +741,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                             ua = s8_range(ua, rcc.mode, rcc.coeff, rcc.offset); ub = s8_range(ub, rcc.mode, rcc.coeff, rcc.offset);
                             va = s8_range(va, rcc.mode, rcc.coeff, rcc.offset); vb = s8_range(vb, rcc.mode, rcc.coeff, rcc.offset);
                         }
-                        hb_u[xc * cstride_w + (ci >> 1)] = prmt((uint32_t)ua, (uint32_t)ub, 0x5410);
-                        hb_v[xc * cstride_w + (ci >> 1)] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
+                        hb_u[cslot(xc) * cstride_w + (ci >> 1)] = prmt((uint32_t)ua, (uint32_t)ub, 0x5410);
+                        hb_v[cslot(xc) * cstride_w + (ci >> 1)] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
                     }
                 }
             }
@@ -834,7 +845,10 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 o1 = lrow + __ldg(A.hc_goff + grp + 1);
             }
             const int c0 = 8 * ng * warp + 2 * t;
-            uint32_t *hu = hb_u + c0 * cstride_w + g, *hv = hb_v + c0 * cstride_w + g;
+            uint32_t *hu = hb_u + g, *hv = hb_v + g;
+            /* line-buffer slots (in words) of columns c0, c0 + 1, c0 + 8, c0 + 9 */
+            const int s0 = cslot(c0) * cstride_w, s1 = cslot(c0 + 1) * cstride_w;
+            const int s8 = cslot(c0 + 8) * cstride_w, s9 = cslot(c0 + 9) * cstride_w;
             int left = nc - 2 * g;
             for (int qc = 0; qc < npc; qc++) {
                 s8_wait(full_a + 8 * sb, sphase);
@@ -849,7 +863,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                     s8_mma_rows_uv<FS4>(base + o0, b0, sel, rcc, ua, ub, va, vb);
                 }
                 if (left > 0) {
-                    hu[0] = ua; hu[cstride_w] = ub; hv[0] = va; hv[cstride_w] = vb;
+                    hu[s0] = ua; hu[s1] = ub; hv[s0] = va; hv[s1] = vb;
                 }
                 if (ng == 2) {
                     if (planar) {
@@ -861,7 +875,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                         s8_mma_rows_uv<FS4>(base + o1, b1, sel, rcc, ua, ub, va, vb);
                     }
                     if (left > 0) {
-                        hu[8 * cstride_w] = ua; hu[9 * cstride_w] = ub; hv[8 * cstride_w] = va; hv[9 * cstride_w] = vb;
+                        hu[s8] = ua; hu[s9] = ub; hv[s8] = va; hv[s9] = vb;
                     }
                 }
                 hu += S8_ROWS / 2; hv += S8_ROWS / 2;
@@ -882,8 +896,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
         }
         const int seg = A.seg_c;
         const bool vfirst = A.src_layout == SWSC_SRC_NV21;
-        uint32_t *hpu = hb_u + x * cstride_w + npair * g;
-        uint32_t *hpv = hb_v + x * cstride_w + npair * g;
+        uint32_t *hpu = hb_u + cslot(x) * cstride_w + npair * g;
+        uint32_t *hpv = hb_v + cslot(x) * cstride_w + npair * g;
         const int rowbytes = planar ? seg : 2 * seg;
         const int so = 2 * npair * g * rowbytes + (S16 ? (off >> 1) * 4 : planar ? (off & ~3) : ((2 * off) & ~3));
         const int sh = S16 ? (off & 1) * 16 : planar ? (off & 3) * 8 : (off & 1) * 16;
@@ -951,6 +965,63 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 nl_ = s8_load_vrow(A.vl + y + 8);
                 nc_ = s8_load_vrow(A.vc + y + 8);
             }
+            if (fullc) {
+                /* ---- yuv2rgb_full_{X,2,1}_c_template + yuv2rgb_write_full (output.c:1998-2051,2160-2330): the sums
+                 * keep 10 fraction bits less; the 2-tap writers drop the rounding bias 1 << 9 (luma and chroma for
+                 * _2: bit 0 of the luma row; chroma only for _1 with two chroma taps: bit 0 of the chroma row) ---- */
+                const int lb = (vl.pos_even & 1) ? 0 : 1 << 9;
+                const int cb = ((vl.pos_even | vc.pos_even) & 1) ? 0 : 1 << 9;
+                const int ln4f = __shfl_sync(0xffffffffu, vl.n4, 0), cn4f = __shfl_sync(0xffffffffu, vc.n4, 0);
+                const int coff = ((vc.pos_even & ~1) - lo_c) >> 1;
+                int Yf[4], Uf[4], Vf[4];
+                s8_vsum<4>(hb_l + lane * lstride_w + (((vl.pos_even & ~1) - lo_l) >> 1), 32 * lstride_w, vl, ln4f, lb, Yf);
+                s8_vsum<4>(hb_u + lane * cstride_w + coff, 32 * cstride_w, vc, cn4f, cb - (128 << 19), Uf);
+                s8_vsum<4>(hb_v + lane * cstride_w + coff, 32 * cstride_w, vc, cn4f, cb - (128 << 19), Vf);
+                if (LONGV && A.vl2)
+                    s8_vsum_more<4>(A.vl2 + y, hb_l + lane * lstride_w, lo_l, 32 * lstride_w, Yf);
+                if (LONGV && A.vc2) {
+                    s8_vsum_more<4>(A.vc2 + y, hb_u + lane * cstride_w, lo_c, 32 * cstride_w, Uf);
+                    s8_vsum_more<4>(A.vc2 + y, hb_v + lane * cstride_w, lo_c, 32 * cstride_w, Vf);
+                }
+                __syncwarp();
+                uint32_t px[4];                 /* B | G << 8 | R << 16 of pixels 2 lane, 2 (lane + 32), 2 lane + 1, 2 (lane + 32) + 1 */
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int Yi = Yf[c] >> 10, Ui = Uf[c] >> 10, Vi = Vf[c] >> 10;
+                    const unsigned Yu = (unsigned)(Yi - A.y_offset) * (unsigned)A.y_coeff + (1u << 21);
+                    const int R = (int)(Yu + (unsigned)Vi * (unsigned)A.v2r);
+                    const int G = (int)(Yu + (unsigned)Vi * (unsigned)A.v2g + (unsigned)Ui * (unsigned)A.u2g);
+                    const int B = (int)(Yu + (unsigned)Ui * (unsigned)A.u2b);
+                    const uint32_t r = (uint32_t)min(max(R, 0), (1 << 30) - 1) >> 22, gq = (uint32_t)min(max(G, 0), (1 << 30) - 1) >> 22;
+                    const uint32_t bq = (uint32_t)min(max(B, 0), (1 << 30) - 1) >> 22;
+                    px[c] = bq | (gq << 8) | (r << 16);
+                }
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const uint32_t a = px[k], b = px[k + 2];       /* the two pixels of pair lane + 32 k */
+                    const int p = lane + 32 * k;
+                    if (bpp == 3) {
+                        uint16_t *o = reinterpret_cast<uint16_t *>(orow + 6 * p);
+                        if (kind == SWSC_DST_RGB24) {           /* R G B R G B */
+                            o[0] = (uint16_t)prmt(a, 0u, 0x4412); o[1] = (uint16_t)prmt(a, b, 0x4460); o[2] = (uint16_t)prmt(b, 0u, 0x4401);
+                        } else {                                /* B G R B G R */
+                            o[0] = (uint16_t)prmt(a, 0u, 0x4410); o[1] = (uint16_t)prmt(a, b, 0x4442); o[2] = (uint16_t)prmt(b, 0u, 0x4421);
+                        }
+                    } else {
+                        uint32_t wa, wb;
+                        if (kind == SWSC_DST_RGBA) {            /* R G B 255 */
+                            wa = prmt(a, 0xFFu, 0x4012); wb = prmt(b, 0xFFu, 0x4012);
+                        } else if (kind == SWSC_DST_BGRA) {     /* B G R 255 */
+                            wa = prmt(a, 0xFFu, 0x4210); wb = prmt(b, 0xFFu, 0x4210);
+                        } else if (kind == SWSC_DST_ARGB) {     /* 255 R G B */
+                            wa = prmt(a, 0xFFu, 0x0124); wb = prmt(b, 0xFFu, 0x0124);
+                        } else {                                /* 255 B G R */
+                            wa = prmt(a, 0xFFu, 0x2104); wb = prmt(b, 0xFFu, 0x2104);
+                        }
+                        *reinterpret_cast<uint2 *>(orow + 8 * p) = make_uint2(wa, wb);
+                    }
+                }
+            } else {
             const int bias = (vl.pos_even & 1) ? 0 : 1 << 18;
             int Y[4], U[2], V[2];
             /* this row's own tap-group counts (a leading zero tap pads odd first rows), made warp-uniform */
@@ -1018,6 +1089,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                     a0 = clamp_u8x2(a0); a1 = clamp_u8x2(a1); b0 = clamp_u8x2(b0); b1 = clamp_u8x2(b1);
                     *reinterpret_cast<uint2 *>(orow + 8 * p) = make_uint2(prmt(a0, a1, 0x6420), prmt(b0, b1, 0x6420));
                 }
+            }
             }
             __syncwarp();
             /* copy the finished row out: 16-byte stores when the destination row allows it */

@@ -194,3 +194,29 @@ def test_rgb16bpp_out_of_the_scaling_kernel(df, sf, geom, flags):
     for mode in ("noise", "extreme"):
         name = _run(case, mode=mode)
         assert name.startswith("scale"), name
+
+
+# ---- SWS_FULL_CHR_H_INT packed RGB out of the scaling kernel (odd widths, 4:4:4 sources, explicit flag) ----
+@pytest.mark.parametrize("sf", ["yuv444p", "yuv420p", "nv12", "yuv422p10le", "yuv444p12le", "bgra", "rgb24"])
+@pytest.mark.parametrize("df", ["rgb24", "bgr24", "rgba", "bgra", "argb", "abgr"])
+@pytest.mark.parametrize("geom,flags", [((322, 242, 323, 243), S.SWS_BICUBIC),                          # odd width forces it
+                                        ((322, 242, 401, 301), S.SWS_BILINEAR),                         # 2-tap rows: _2 writer
+                                        ((644, 362, 321, 181), S.SWS_LANCZOS),
+                                        ((322, 242, 322, 300), S.SWS_BILINEAR | S.SWS_FULL_CHR_H_INT),  # vertical only
+                                        ((322, 242, 400, 242), S.SWS_BICUBIC | S.SWS_FULL_CHR_H_INT),   # one vertical tap: _1 writer
+                                        ((176, 144, 352, 288), S.SWS_BICUBIC | S.SWS_FULL_CHR_H_INT)])
+def test_full_chroma_rgb_out_of_the_scaling_kernel(sf, df, geom, flags):
+    sw, sh, dw, dh = geom
+    if sf in ("bgra", "rgb24") and len(df) == 4 and sf == "bgra":
+        pytest.skip("alpha on both sides travels as a fourth line set: the general kernel")
+    case = dict(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags | BX)
+    for mode in ("noise", "extreme"):
+        name = _run(case, mode=mode)
+        assert name.startswith("scale"), name
+
+
+def test_full_chroma_vertical_chroma_offset():
+    """{4096 - a, a} two-tap chroma rows under a one-tap luma: yuv2rgb_full_1 with uvalpha != 0 (no chroma rounding bias)"""
+    case = dict(sw=322, sh=242, sf="yuv444p", dw=400, dh=242, df="rgb24", flags=S.SWS_BICUBIC | BX)
+    _run(case, ctx_kwargs=dict(chr_pos=(64, 0, 0, 0)))
+    _run(case, ctx_kwargs=dict(chr_pos=(256, 0, 0, 128)))
