@@ -113,6 +113,12 @@ def make_case(rng):
         other = rng.choice([cs, 5]) if is_rgb(case["sf"]) or is_rgb(case["df"]) or rng.random() < 0.4 else cs
         if min(case["sw"], case["sh"], case["dw"], case["dh"]) < 16:
             other = cs
+        # an unscaled cascade of an odd width without SWS_ACCURATE_RND: the reference's first stage is the yuv2rgb LUT
+        # converter, which leaves the last pixel of every row untouched -- in a buffer av_image_alloc() never
+        # initialised -- and its second stage reads it: undefined output in the last column (seed 702)
+        if (other != cs and (case["sw"] & 1) and (case["sw"], case["sh"]) == (case["dw"], case["dh"])
+                and not (case["flags"] & S.SWS_ACCURATE_RND)):
+            other = cs
         case["colorspace"] = (cs, rng.randint(0, 1), other, rng.randint(0, 1), 0, 1 << 16, 1 << 16)
     # less common options: scaler parameters, chroma siting, dither mode, picture controls
     if rng.random() < 0.1:
