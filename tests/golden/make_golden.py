@@ -168,6 +168,45 @@ def cases():
                     ctx_kwargs=dict(chr_pos=[256, 64, 128, 64])))
     out.append(dict(sw=87, sh=198, sf="yuv422p", dw=87, dh=198, df="nv12", flags=R.SWS_BICUBIC | BX,
                     ctx_kwargs=dict(chr_pos=[0, 64, 128, 128])))
+    # ---- round 2 (appended: earlier seeds stay put) ----
+    # float destinations (yuv2plane1/X_float, yuv2gbrpf32_full_X_c)
+    for df in ["grayf32le", "gbrpf32le"]:
+        for sf, g, fl in [("yuv420p", (162, 122, 200, 150), R.SWS_BICUBIC | BX), ("yuv444p10le", (162, 122, 100, 76), R.SWS_LANCZOS | BX),
+                          ("nv12", (162, 122, 162, 122), R.SWS_BICUBIC), ("yuvj420p", (53, 74, 266, 74), R.SWS_SINC | BX)]:
+            out.append(dict(sw=g[0], sh=g[1], sf=sf, dw=g[2], dh=g[3], df=df, flags=fl))
+    # the scaling kernel family: 10-/12-/16-bit sources, range conversion, 9..14-bit and dithered 8-bit writers,
+    # packed RGB sources, 17..32-tap banks, 15/16 bpp and full-chroma RGB out of it
+    for sf, df, g, fl in [("yuv420p10le", "yuv420p10le", (322, 182, 160, 90), R.SWS_BICUBIC | BX),
+                          ("yuv422p12le", "yuv420p", (322, 182, 400, 300), R.SWS_LANCZOS | BX),
+                          ("yuv444p16le", "nv12", (322, 182, 200, 100), R.SWS_BILINEAR | BX),
+                          ("yuv420p", "yuv444p12le", (322, 182, 400, 300), R.SWS_BICUBIC | BX),
+                          ("yuv420p10le", "bgra", (322, 182, 400, 300), R.SWS_BICUBIC | BX),
+                          ("bgra", "nv12", (322, 182, 160, 90), R.SWS_BICUBIC | BX),
+                          ("rgb24", "yuv420p10le", (322, 182, 400, 300), R.SWS_BILINEAR | BX),
+                          ("argb", "yuv444p", (323, 181, 200, 100), R.SWS_LANCZOS | BX),
+                          ("yuv420p", "yuv420p", (1280, 720, 160, 90), R.SWS_BICUBIC | BX),
+                          ("nv12", "rgb24", (1280, 720, 212, 120), R.SWS_BICUBIC | BX),
+                          ("yuv420p10le", "yuv420p", (960, 540, 160, 90), R.SWS_LANCZOS | BX),
+                          ("yuv420p", "rgb565le", (322, 182, 400, 300), R.SWS_LANCZOS | BX),
+                          ("rgb24", "bgr555le", (322, 182, 160, 90), R.SWS_BICUBIC | BX),
+                          ("yuv444p", "bgr24", (322, 182, 401, 301), R.SWS_BICUBIC | BX),
+                          ("yuv422p10le", "argb", (322, 182, 161, 91), R.SWS_BILINEAR | BX)]:
+        out.append(dict(sw=g[0], sh=g[1], sf=sf, dw=g[2], dh=g[3], df=df, flags=fl))
+    for rng in [(0, 1), (1, 0)]:
+        for sf, df in [("yuv420p", "yuv420p"), ("yuv420p10le", "yuv422p10le"), ("nv12", "yuv444p")]:
+            out.append(dict(sw=322, sh=182, sf=sf, dw=200, dh=120, df=df, flags=R.SWS_BICUBIC | BX,
+                            ctx_kwargs=dict(src_range=rng[0], dst_range=rng[1])))
+    # what the numpy restatement does not cover (the CPU suite skips these; the GPU suite holds the CUDA path to them):
+    # rgb48 sources, alpha through the scaler, cascades, the unscaled p010 -> nv12 copy
+    for sf, df, g, fl in [("rgb48le", "yuv420p", (162, 122, 200, 150), R.SWS_BICUBIC | BX), ("bgr48le", "yuv444p10le", (162, 122, 162, 122), R.SWS_BICUBIC | BX),
+                          ("rgb48le", "bgr48le", (163, 61, 163, 61), R.SWS_BICUBIC), ("bgr48le", "rgb24", (162, 122, 100, 76), R.SWS_BILINEAR | BX),
+                          ("rgba", "bgra", (162, 122, 200, 150), R.SWS_BICUBIC | BX), ("argb", "abgr", (163, 121, 100, 121), R.SWS_BILINEAR | BX),
+                          ("p010le", "nv12", (163, 61, 163, 61), R.SWS_BICUBIC), ("p010le", "nv12", (162, 122, 162, 122), R.SWS_POINT | BX),
+                          ("yuv420p", "yuv420p", (2048, 64, 8, 32), R.SWS_BICUBIC | BX)]:
+        out.append(dict(sw=g[0], sh=g[1], sf=sf, dw=g[2], dh=g[3], df=df, flags=fl))
+    for sf, df in [("yuv420p", "yuv420p"), ("yuv420p10le", "yuv420p10le"), ("nv12", "yuv444p16le"), ("yuv420p", "grayf32le")]:
+        out.append(dict(sw=162, sh=122, sf=sf, dw=162, dh=122, df=df, flags=R.SWS_BICUBIC | BX,
+                        colorspace=[1, 0, 5, 1, 0, 1 << 16, 1 << 16]))
     for i, c in enumerate(out):
         c.setdefault("seed", 100 + i)
         c.setdefault("mode", "extreme" if i % 7 == 3 else "noise")
