@@ -2340,7 +2340,8 @@ static int fasthi8_launch(SwsCudaState *st, const uint8_t *const src[4], const i
 typedef void (*scale8_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Scale8Args);
 static scale8_kernel_t pick_scale8(int fs4, int rgbk, bool mma, int srck, bool wide = false)
 {
-    /* rgbk: 0 planar output, 1 packed RGB with shared chroma, 2 packed RGB with full chroma.
+    /* rgbk: 0 planar output, 1 packed RGB with shared chroma, 2 packed RGB with full chroma, 3 16-bit planar output
+     * over 19-bit lines.
      * `wide`: the tile's shared memory admits at most three CTAs per SM: take the 72-register build */
     if (wide && mma && !rgbk && srck == S8_SRC_U8 && fs4 <= 2)
         return fs4 == 1 ? sws_scale8_kernel<1, 0, true, S8_SRC_U8, 3> : sws_scale8_kernel<2, 0, true, S8_SRC_U8, 3>;
@@ -2349,6 +2350,8 @@ static scale8_kernel_t pick_scale8(int fs4, int rgbk, bool mma, int srck, bool w
 #define S8_PICK_MMA(R) (fs4 == 1 ? sws_scale8_kernel<1, R, true, S8_SRC_U8> : fs4 == 2 ? sws_scale8_kernel<2, R, true, S8_SRC_U8> \
                         : sws_scale8_kernel<4, R, true, S8_SRC_U8>)
 #define S8_PICK_K(M, K) (rgbk == 2 ? S8_PICK(2, M, K) : rgbk == 1 ? S8_PICK(1, M, K) : S8_PICK(0, M, K))
+    if (rgbk == 3)              /* 19-bit lines into 16-bit planar destinations: dot-product horizontal stage only */
+        return srck == S8_SRC_U16 ? S8_PICK(3, false, S8_SRC_U16) : S8_PICK(3, false, S8_SRC_U8);
     if (srck == S8_SRC_RGB)     /* packed 8-bit RGB sources: reader stage + IDP.2A horizontal stage */
         return S8_PICK_K(false, S8_SRC_RGB);
     if (srck == S8_SRC_U16)     /* 9..16-bit planar sources: IDP.2A horizontal stage */
@@ -2623,7 +2626,11 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     const SwsCudaPlan *p = &st->plan;
     st->s8_ok = 0;
     const bool rgbs = p->src_layout == SWSC_SRC_RGB;
-    if (p->inter_bits != 15 || (p->src_layout > SWSC_SRC_NV21 && !rgbs) || p->src_alpha || p->dst_alpha)
+    /* 19-bit lines (hScale8To19_c / hScale16To19_c, swscale.c:60-97,144-159): 16-bit planar YUV destinations only */
+    const bool i19 = p->inter_bits == 19;
+    if (i19 && (p->dst_kind != SWSC_DST_PLANAR16 || p->dst_shift || rgbs))
+        return 0;
+    if ((p->inter_bits != 15 && !i19) || (p->src_layout > SWSC_SRC_NV21 && !rgbs) || p->src_alpha || p->dst_alpha)
         return 0;
     /* packed 8-bit RGB sources: samples the readers keep inside 14 bits (checked again at every launch: the matrix can
      * change), luma and chroma out of the same rows */
@@ -2644,7 +2651,7 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     if (rgb && (p->chr_dst_hsub != (p->full_chr ? 0 : 1) || p->chr_dst_vsub != 0 || p->special || p->unscaled_lut ||
                 !p->has_chroma || (p->full_chr && p->dst_kind > SWSC_DST_ABGR)))
         return 0;
-    if (!rgb && p->dst_kind != SWSC_DST_PLANAR8 && p->dst_kind != SWSC_DST_NV12 && p->dst_kind != SWSC_DST_NV21 &&
+    if (!rgb && !i19 && p->dst_kind != SWSC_DST_PLANAR8 && p->dst_kind != SWSC_DST_NV12 && p->dst_kind != SWSC_DST_NV21 &&
         !(p->dst_kind == SWSC_DST_PLANARN && p->dst_bits >= 9 && p->dst_bits <= 14 && !p->dst_shift))
         return 0;
     if (!p->has_chroma || !p->dst_has_chroma || p->special || p->unscaled_lut)
@@ -2663,7 +2670,7 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     int ret = 0, lparts = 1, cparts = 1;
     if (!hvl || !hvc || (lparts = s8_pack_v(vl, hvl, hvl + vl->len)) < 0 || (cparts = s8_pack_v(vc, hvc, hvc + vc->len)) < 0)
         ret = 1;
-    if (lparts == 2 || cparts == 2)
+    if ((lparts == 2 || cparts == 2) && !i19)
         fs4 = 8;                      /* only the eight-group variants are compiled with the second vertical record */
     if (!ret && rgb && p->full_chr && vl->size == 1 && vc->size == 2) {
         /* yuv2rgb_full_1 with two chroma taps (vscale.c:138-143) blends chroma without the rounding bias:
@@ -2695,7 +2702,7 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     const bool inter = p->src_layout != SWSC_SRC_PLANAR;
     int mma = 0, ks = 0;
     /* what the MMA variants are compiled for: no range conversion, 8-bit output, vertical banks of one record */
-    const bool plain = !p->range_mode && p->dst_kind != SWSC_DST_PLANARN && lparts == 1 && cparts == 1;
+    const bool plain = !p->range_mode && p->dst_kind != SWSC_DST_PLANARN && !i19 && lparts == 1 && cparts == 1;
     if (!ret && !s16 && !rgbs && plain && seg_l >= 0 && seg_c >= 0 &&
         !(getenv("SWS_B200_DISABLE") && strstr(getenv("SWS_B200_DISABLE"), "s8mma"))) {
         const int kl = s8_mma_ksteps(hl, S8_TW, false), kc = s8_mma_ksteps(hc, cw, inter);
@@ -2755,7 +2762,9 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
             for (int t = th_max; t >= 2; t >>= 1) {
                 const int cth = t >> p->chr_dst_vsub ? t >> p->chr_dst_vsub : 1;
                 const int nl = s8_rows_cap(hvl, hvl + vl->len, vl->len, t), nc = s8_rows_cap(hvc, hvc + vc->len, vc->len, cth);
-                const size_t lines = ((size_t)S8_TW * nl + 2 * (size_t)cw * nc) * 2 +
+                /* 15-bit lines: two rows per word; 19-bit lines: one row per word, columns nl + 1 words apart */
+                const size_t lines = (i19 ? ((size_t)S8_TW * (nl + 1) + 2 * (size_t)cw * (nc + 1)) * 4
+                                          : ((size_t)S8_TW * nl + 2 * (size_t)cw * nc) * 2) +
                                      (size_t)S8_ROWS * (seg_sy + 2 * seg_sc);     /* + the RGB readers' sample rows */
                 if (lines + 2 * (size_t)slot > budget[pass])
                     continue;
@@ -2769,7 +2778,8 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
             const int cth = th >> p->chr_dst_vsub ? th >> p->chr_dst_vsub : 1;
             nl_cap = s8_rows_cap(hvl, hvl + vl->len, vl->len, th);
             nc_cap = s8_rows_cap(hvc, hvc + vc->len, vc->len, cth);
-            const size_t lines = ((size_t)S8_TW * nl_cap + 2 * (size_t)cw * nc_cap) * 2 + (size_t)S8_ROWS * (seg_sy + 2 * seg_sc);
+            const size_t lines = (i19 ? ((size_t)S8_TW * (nl_cap + 1) + 2 * (size_t)cw * (nc_cap + 1)) * 4
+                                      : ((size_t)S8_TW * nl_cap + 2 * (size_t)cw * nc_cap) * 2) + (size_t)S8_ROWS * (seg_sy + 2 * seg_sc);
             stages = (int)((budget[best_pass] - lines) / slot);
             if (stages > st_max) stages = st_max;
             smem = lines + (size_t)stages * slot;
@@ -2835,13 +2845,13 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
         st->s8_hl_goff = (int *)(t + o_gl); st->s8_hc_goff = (int *)(t + o_gc);
         st->s8_hl_B = (uint32_t *)(t + o_bl); st->s8_hc_B = (uint32_t *)(t + o_bc);
     }
-    CUDA_OK(set_max_smem((const void *)pick_scale8(st->s8_fs4, rgb ? (p->full_chr ? 2 : 1) : 0, mma, srck, st->s8_wide), (size_t)((int)smem)));
+    CUDA_OK(set_max_smem((const void *)pick_scale8(st->s8_fs4, i19 ? 3 : rgb ? (p->full_chr ? 2 : 1) : 0, mma, srck, st->s8_wide), (size_t)((int)smem)));
     st->s8_ok = 1;
     if (getenv("SWS_B200_DEBUG"))
         fprintf(stderr, "[swscaler-b200] scale8: %s fs4=%d tile_h=%d nl_cap=%d nc_cap=%d seg_l=%d seg_c=%d slot=%d stages=%d smem=%zu\n",
-                rgbs ? "rgb" : s16 ? "dp2a16" : mma ? "mma" : "dp4a", st->s8_fs4, th, nl_cap, nc_cap, seg_l, seg_c, slot, stages, smem);
+                rgbs ? "rgb" : i19 ? "i19" : s16 ? "dp2a16" : mma ? "mma" : "dp4a", st->s8_fs4, th, nl_cap, nc_cap, seg_l, seg_c, slot, stages, smem);
     if (!st->fast_ok && !st->fast16_ok)
-        st->kernel_name = rgbs ? "scale_rgb_dp2a" : s16 ? "scale16_dp2a" : mma ? "scale8_mma" : "scale8_dp4a";
+        st->kernel_name = rgbs ? "scale_rgb_dp2a" : i19 ? (s16 ? "scale16_i19" : "scale8_i19") : s16 ? "scale16_dp2a" : mma ? "scale8_mma" : "scale8_dp4a";
     return 0;
 }
 
@@ -2929,13 +2939,18 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.v2r = p->rgb.v2r; a.v2g = p->rgb.v2g; a.u2g = p->rgb.u2g; a.u2b = p->rgb.u2b;
     const bool rgb = (p->dst_kind >= SWSC_DST_RGB24 && p->dst_kind <= SWSC_DST_ABGR) ||
                      (p->dst_kind >= SWSC_DST_RGB565 && p->dst_kind <= SWSC_DST_BGR555);
+    const bool i19 = p->inter_bits == 19;
+    a.lum_rc_offset64 = p->lum_rc_offset; a.chr_rc_offset64 = p->chr_rc_offset;
+    a.vl_coef16 = p->vl_coef; a.vc_coef16 = p->vc_coef; a.vl_pos32 = p->vl_pos; a.vc_pos32 = p->vc_pos;
+    a.vl_size = p->vl_size; a.vc_size = p->vc_size;
     a.hl_pos = st->s8_hl_pos; a.hc_pos = st->s8_hc_pos;
     a.hl_cl = st->s8_hl_cl; a.hl_ch = st->s8_hl_ch; a.hc_cl = st->s8_hc_cl; a.hc_ch = st->s8_hc_ch;
     a.vl = st->s8_vl; a.vc = st->s8_vc; a.vl2 = st->s8_vl2; a.vc2 = st->s8_vc2;
     a.hl_goff = st->s8_hl_goff; a.hc_goff = st->s8_hc_goff; a.hl_B = st->s8_hl_B; a.hc_B = st->s8_hc_B;
     dim3 grid((p->dst_w + S8_TW - 1) / S8_TW, (y1 - y0 + st->s8_tile_h - 1) / st->s8_tile_h, nb_frames);
-    pick_scale8(st->s8_fs4, rgb ? (p->full_chr ? 2 : 1) : 0, st->s8_mma, st->s8_srck, st->s8_wide)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
-    st->kernel_name = rgbs ? "scale_rgb_dp2a" : st->s8_srck == S8_SRC_U16 ? "scale16_dp2a" : st->s8_mma ? "scale8_mma" : "scale8_dp4a";
+    pick_scale8(st->s8_fs4, i19 ? 3 : rgb ? (p->full_chr ? 2 : 1) : 0, st->s8_mma, st->s8_srck, st->s8_wide)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
+    st->kernel_name = rgbs ? "scale_rgb_dp2a" : i19 ? (st->s8_srck == S8_SRC_U16 ? "scale16_i19" : "scale8_i19")
+                           : st->s8_srck == S8_SRC_U16 ? "scale16_dp2a" : st->s8_mma ? "scale8_mma" : "scale8_dp4a";
     CUDA_OK(cudaGetLastError());
     st->launches++;
     return 1;

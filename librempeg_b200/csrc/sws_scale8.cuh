@@ -84,6 +84,11 @@ struct Scale8Args {
      * as 16-bit pairs in the byte order of a pixel word, bytes per row of the luma / chroma sample buffers */
     int src_bpp, rgb_half, seg_sy, seg_sc;
     uint32_t ylo, yhi, ulo, uhi, vlo, vhi;
+    /* 19-bit lines (RGBK = 3: 16-bit planar destinations): range constants in full width, the plain vertical banks */
+    long long lum_rc_offset64, chr_rc_offset64;
+    const int16_t *vl_coef16, *vc_coef16;
+    const int32_t *vl_pos32, *vc_pos32;
+    int vl_size, vc_size;
     int out_bits;            /* planar destinations: 8, or 9..14 (16-bit little-endian samples) */
     int dither_bayer;        /* 8-bit planar output of > 8-bit sources: ff_dither_8x8_128 instead of the constant 64 */
     const int *hl_pos, *hc_pos;
@@ -236,7 +241,7 @@ __device__ __forceinline__ int dp2a_hi_ss(uint32_t a, uint32_t b, int c)
 }
 
 /* horizontal FIR of one staged row for one output column: FS4 groups of four taps */
-template <int FS4>
+template <int FS4, bool I19 = false>
 __device__ __forceinline__ int s8_hfir(const unsigned char *srow, int sh, const uint32_t (&cl)[FS4],
                                        const uint32_t (&ch)[FS4])
 {
@@ -251,7 +256,8 @@ __device__ __forceinline__ int s8_hfir(const unsigned char *srow, int sh, const 
         acc_h = dp4a_us(v, ch[k], acc_h);
         w0 = w1;
     }
-    return min(((acc_h << 8) + acc_l) >> 7, (1 << 15) - 1);
+    /* hScale8To15_c: >> 7, 15 bits; hScale8To19_c (swscale.c:144-159): >> 3, 19 bits */
+    return I19 ? min(((acc_h << 8) + acc_l) >> 3, (1 << 19) - 1) : min(((acc_h << 8) + acc_l) >> 7, (1 << 15) - 1);
 }
 
 /* lumRangeToJpeg_c / lumRangeFromJpeg_c and the chroma twins (swscale.c:163-216) on one 15-bit sample:
@@ -262,6 +268,45 @@ __device__ __forceinline__ int s8_range(int val, int mode, int coeff, int offset
     if (mode == 1)
         val = min(val, (1 << 15) - 1);
     return (int)(int16_t)val;
+}
+
+/* the 19-bit twins (lumRangeToJpeg16_c & co., swscale.c:218-255): 64-bit product, >> 18 */
+__device__ __forceinline__ int s19_range(int val, int mode, uint32_t coeff, long long offset)
+{
+    val = (int)(((long long)val * coeff + offset) >> 18);
+    if (mode == 1)
+        val = min(val, (1 << 19) - 1);
+    return val;
+}
+
+/* yuv2planeX_16_c / yuv2plane1_16_c (output.c:163-187) for NC columns of 19-bit lines (one sample per word, cstep
+ * words apart), executed by a whole warp: the row's taps sit in two registers per lane and are broadcast per tap.
+ * One tap never multiplies (a line below -2^19 must not wrap through the x 4096 of the general form). */
+template <int NC>
+__device__ __forceinline__ void s19_vrow(const uint32_t *col, int cstep, const int16_t *coef, int size, int lane,
+                                         int (&out)[NC])
+{
+    if (size == 1) {
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+            out[c] = min(max(((int)col[c * cstep] + 4) >> 3, 0), 65535);
+        return;
+    }
+    const int c0 = lane < size ? (int)__ldg(coef + lane) : 0;
+    const int c1 = lane + 32 < size ? (int)__ldg(coef + lane + 32) : 0;
+    unsigned acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+        acc[c] = (1u << 14) - 0x40000000u;
+    for (int j = 0; j < size; j++) {
+        const unsigned cj = (unsigned)__shfl_sync(0xffffffffu, j < 32 ? c0 : c1, j & 31);
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+            acc[c] += col[c * cstep + j] * cj;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+        out[c] = 0x8000 + min(max((int)acc[c] >> 15, -32768), 32767);
 }
 
 __device__ __forceinline__ int dp2a_lo_uu(uint32_t a, uint32_t b, int c)
@@ -292,7 +337,7 @@ __device__ __forceinline__ int dp2a_hi_us(uint32_t a, uint32_t b, int c)
 /* hScale16To15_c (swscale.c:99-125) of one staged row of 16-bit samples for one output column: two samples per
  * word, an odd first sample is a 16-bit funnel shift; IDP.2A against the split coefficient bytes, everything
  * modulo 2^32 like the C code's int accumulator */
-template <int FS4>
+template <int FS4, bool I19 = false>
 __device__ __forceinline__ int s16_hfir(const unsigned char *srow, int sh, int hshift, const uint32_t (&cl)[FS4],
                                         const uint32_t (&ch)[FS4])
 {
@@ -309,7 +354,7 @@ __device__ __forceinline__ int s16_hfir(const unsigned char *srow, int sh, int h
         acc_h = dp2a_hi_us(v1, ch[k], acc_h);
         w0 = w2;
     }
-    return min(((acc_h << 8) + acc_l) >> hshift, (1 << 15) - 1);
+    return min(((acc_h << 8) + acc_l) >> hshift, I19 ? (1 << 19) - 1 : (1 << 15) - 1);     /* hScale16To15_c / To19_c */
 }
 
 /* vertical FIR for NC columns (transposed 15-bit lines, cstep words apart): bias + sum of taps, before
@@ -429,7 +474,7 @@ __device__ __forceinline__ void s8_tma_prefetch(const CUtensorMap *map, int x, i
 
 /* horizontal FIR of one staged row of interleaved chroma (nv12 / nv21) for one output column: the
  * de-interleave of nv12ToUV_c (input.c:926-941) is two byte permutes per four taps */
-template <int FS4>
+template <int FS4, bool I19 = false>
 __device__ __forceinline__ void s8_hfir_uv(const unsigned char *srow, int sh, const uint32_t (&cl)[FS4],
                                            const uint32_t (&ch)[FS4], int &even, int &odd)
 {
@@ -447,8 +492,8 @@ __device__ __forceinline__ void s8_hfir_uv(const unsigned char *srow, int sh, co
         oh = dp4a_us(o, ch[k], oh);
         w0 = w2;
     }
-    even = min(((eh << 8) + el) >> 7, (1 << 15) - 1);
-    odd = min(((oh << 8) + ol) >> 7, (1 << 15) - 1);
+    even = I19 ? min(((eh << 8) + el) >> 3, (1 << 19) - 1) : min(((eh << 8) + el) >> 7, (1 << 15) - 1);
+    odd = I19 ? min(((oh << 8) + ol) >> 3, (1 << 19) - 1) : min(((oh << 8) + ol) >> 7, (1 << 15) - 1);
 }
 
 /*
@@ -475,7 +520,8 @@ __global__ void __launch_bounds__(S8_THREADS, MINB ? MINB : (SRCK != S8_SRC_U8 |
 sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_u,
                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ Scale8Args A)
 {
-    constexpr bool RGB = RGBK != 0;
+    constexpr bool RGB = RGBK == 1 || RGBK == 2;
+    constexpr bool I19 = RGBK == 3;               /* int32 lines of 19 bits, one per word, for 16-bit planar destinations */
     constexpr bool S16 = SRCK == S8_SRC_U16;      /* 16-bit samples straight from the ring */
     constexpr bool RGBS = SRCK == S8_SRC_RGB;     /* packed 8-bit RGB rows in the ring, converted to 14-bit Y/U/V samples per slot */
     extern __shared__ __align__(128) unsigned char s8_smem_raw[];
@@ -507,7 +553,20 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
 
     /* source row windows of the tile (first rows are even by construction): lane = output row */
     int lo_l = INT_MAX, hi_l = 0, lo_c = INT_MAX, hi_c = 0;
-    if (ry0 + lane < ry1) {
+    if (I19) {
+        /* plain banks: the window of a row is [pos & ~1, pos + size) (the horizontal stage works on row pairs) */
+        if (ry0 + lane < ry1) {
+            const int ps = __ldg(A.vl_pos32 + ry0 + lane);
+            lo_l = ps & ~1;
+            hi_l = ps + A.vl_size;
+        }
+        if (cy0 + lane < cy1) {
+            const int ps = __ldg(A.vc_pos32 + cy0 + lane);
+            lo_c = ps & ~1;
+            hi_c = ps + A.vc_size;
+        }
+    }
+    if (!I19 && ry0 + lane < ry1) {
         const int2 pn = __ldg(reinterpret_cast<const int2 *>(A.vl + ry0 + lane));
         lo_l = pn.x & ~1;
         hi_l = lo_l + 4 * pn.y;
@@ -516,7 +575,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             hi_l = max(hi_l, (p2.x & ~1) + 4 * p2.y);
         }
     }
-    if (cy0 + lane < cy1) {
+    if (!I19 && cy0 + lane < cy1) {
         const int2 pn = __ldg(reinterpret_cast<const int2 *>(A.vc + cy0 + lane));
         lo_c = pn.x & ~1;            /* (bit 0 of an RGB row: a rounding flag, see the V stage) */
         hi_c = lo_c + 4 * pn.y;
@@ -595,7 +654,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     uint8_t *dst2 = A.dst[2] ? A.dst[2] + f * A.dst_fstride[2] : nullptr;
     const int tw = min(S8_TW, A.dst_w - x0), th = ry1 - ry0;
     const int cw = min(CW, A.chr_dst_w - cx0);
-    const int lstride_w = A.nl_cap >> 1, cstride_w = A.nc_cap >> 1;   /* odd by construction */
+    /* words per line-buffer column: row pairs (odd by construction), or for 19-bit lines single rows + 1 (odd) */
+    const int lstride_w = I19 ? A.nl_cap + 1 : A.nl_cap >> 1, cstride_w = I19 ? A.nc_cap + 1 : A.nc_cap >> 1;
     const unsigned char *ring = s8_smem_raw;
     uint32_t *hb_l = reinterpret_cast<uint32_t *>(s8_smem_raw + A.stages * slot);
     uint32_t *hb_u = hb_l + S8_TW * lstride_w;
@@ -798,7 +858,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
         /* RGB output: even columns in slots 0..63, odd columns in 64..127, so that a lane of the V stage
          * finds both pixels of its pair at a conflict-free stride */
         const int lslot = RGB ? (x >> 1) + 64 * (x & 1) : x;
-        uint32_t *hp = hb_l + lslot * lstride_w + NP * g;
+        uint32_t *hp = hb_l + lslot * lstride_w + (I19 ? 2 : 1) * NP * g;
         int left = nl - 2 * NP * g;              /* rows of this thread's group still inside the window */
         for (int q = 0; q < npl; q++) {
             s8_wait(full_a + 8 * sb, sphase);
@@ -808,20 +868,29 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 if (2 * m < left) {
                     int va, vb;
                     if (S16) {
-                        va = s16_hfir<FS4>(sp + (2 * m) * seg, sh, A.h_shift, cl, chh);
-                        vb = s16_hfir<FS4>(sp + (2 * m + 1) * seg, sh, A.h_shift, cl, chh);
+                        va = s16_hfir<FS4, I19>(sp + (2 * m) * seg, sh, A.h_shift, cl, chh);
+                        vb = s16_hfir<FS4, I19>(sp + (2 * m + 1) * seg, sh, A.h_shift, cl, chh);
                     } else {
-                        va = s8_hfir<FS4>(sp + (2 * m) * seg, sh, cl, chh);
-                        vb = s8_hfir<FS4>(sp + (2 * m + 1) * seg, sh, cl, chh);
+                        va = s8_hfir<FS4, I19>(sp + (2 * m) * seg, sh, cl, chh);
+                        vb = s8_hfir<FS4, I19>(sp + (2 * m + 1) * seg, sh, cl, chh);
                     }
-                    if (rcl.mode) {
-                        va = s8_range(va, rcl.mode, rcl.coeff, rcl.offset);
-                        vb = s8_range(vb, rcl.mode, rcl.coeff, rcl.offset);
+                    if (I19) {
+                        if (rcl.mode) {
+                            va = s19_range(va, rcl.mode, (uint32_t)rcl.coeff, A.lum_rc_offset64);
+                            vb = s19_range(vb, rcl.mode, (uint32_t)rcl.coeff, A.lum_rc_offset64);
+                        }
+                        hp[2 * m] = (uint32_t)va;
+                        hp[2 * m + 1] = (uint32_t)vb;
+                    } else {
+                        if (rcl.mode) {
+                            va = s8_range(va, rcl.mode, rcl.coeff, rcl.offset);
+                            vb = s8_range(vb, rcl.mode, rcl.coeff, rcl.offset);
+                        }
+                        hp[m] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
                     }
-                    hp[m] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
                 }
             }
-            hp += S8_ROWS / 2;
+            hp += I19 ? S8_ROWS : S8_ROWS / 2;
             left -= S8_ROWS;
             release();
         }
@@ -896,8 +965,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
         }
         const int seg = A.seg_c;
         const bool vfirst = A.src_layout == SWSC_SRC_NV21;
-        uint32_t *hpu = hb_u + cslot(x) * cstride_w + npair * g;
-        uint32_t *hpv = hb_v + cslot(x) * cstride_w + npair * g;
+        uint32_t *hpu = hb_u + cslot(x) * cstride_w + (I19 ? 2 : 1) * npair * g;
+        uint32_t *hpv = hb_v + cslot(x) * cstride_w + (I19 ? 2 : 1) * npair * g;
         const int rowbytes = planar ? seg : 2 * seg;
         const int so = 2 * npair * g * rowbytes + (S16 ? (off >> 1) * 4 : planar ? (off & ~3) : ((2 * off) & ~3));
         const int sh = S16 ? (off & 1) * 16 : planar ? (off & 3) * 8 : (off & 1) * 16;
@@ -909,34 +978,45 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 if (2 * m < left) {
                     int ua, ub, va, vb;
                     if (S16) {               /* planar 16-bit chroma */
-                        ua = s16_hfir<FS4>(sp, sh, A.h_shift, cl, chh);
-                        ub = s16_hfir<FS4>(sp + seg, sh, A.h_shift, cl, chh);
-                        va = s16_hfir<FS4>(sp + S8_ROWS * seg, sh, A.h_shift, cl, chh);
-                        vb = s16_hfir<FS4>(sp + (S8_ROWS + 1) * seg, sh, A.h_shift, cl, chh);
+                        ua = s16_hfir<FS4, I19>(sp, sh, A.h_shift, cl, chh);
+                        ub = s16_hfir<FS4, I19>(sp + seg, sh, A.h_shift, cl, chh);
+                        va = s16_hfir<FS4, I19>(sp + S8_ROWS * seg, sh, A.h_shift, cl, chh);
+                        vb = s16_hfir<FS4, I19>(sp + (S8_ROWS + 1) * seg, sh, A.h_shift, cl, chh);
                     } else if (planar) {
-                        ua = s8_hfir<FS4>(sp, sh, cl, chh);
-                        ub = s8_hfir<FS4>(sp + seg, sh, cl, chh);
-                        va = s8_hfir<FS4>(sp + S8_ROWS * seg, sh, cl, chh);
-                        vb = s8_hfir<FS4>(sp + (S8_ROWS + 1) * seg, sh, cl, chh);
+                        ua = s8_hfir<FS4, I19>(sp, sh, cl, chh);
+                        ub = s8_hfir<FS4, I19>(sp + seg, sh, cl, chh);
+                        va = s8_hfir<FS4, I19>(sp + S8_ROWS * seg, sh, cl, chh);
+                        vb = s8_hfir<FS4, I19>(sp + (S8_ROWS + 1) * seg, sh, cl, chh);
                     } else {
-                        s8_hfir_uv<FS4>(sp, sh, cl, chh, ua, va);
-                        s8_hfir_uv<FS4>(sp + 2 * seg, sh, cl, chh, ub, vb);
+                        s8_hfir_uv<FS4, I19>(sp, sh, cl, chh, ua, va);
+                        s8_hfir_uv<FS4, I19>(sp + 2 * seg, sh, cl, chh, ub, vb);
                         if (vfirst) {
                             int t = ua; ua = va; va = t;
                             t = ub; ub = vb; vb = t;
                         }
                     }
-                    if (rcc.mode) {
-                        ua = s8_range(ua, rcc.mode, rcc.coeff, rcc.offset); ub = s8_range(ub, rcc.mode, rcc.coeff, rcc.offset);
-                        va = s8_range(va, rcc.mode, rcc.coeff, rcc.offset); vb = s8_range(vb, rcc.mode, rcc.coeff, rcc.offset);
+                    if (I19) {
+                        if (rcc.mode) {
+                            ua = s19_range(ua, rcc.mode, (uint32_t)rcc.coeff, A.chr_rc_offset64);
+                            ub = s19_range(ub, rcc.mode, (uint32_t)rcc.coeff, A.chr_rc_offset64);
+                            va = s19_range(va, rcc.mode, (uint32_t)rcc.coeff, A.chr_rc_offset64);
+                            vb = s19_range(vb, rcc.mode, (uint32_t)rcc.coeff, A.chr_rc_offset64);
+                        }
+                        hpu[2 * m] = (uint32_t)ua; hpu[2 * m + 1] = (uint32_t)ub;
+                        hpv[2 * m] = (uint32_t)va; hpv[2 * m + 1] = (uint32_t)vb;
+                    } else {
+                        if (rcc.mode) {
+                            ua = s8_range(ua, rcc.mode, rcc.coeff, rcc.offset); ub = s8_range(ub, rcc.mode, rcc.coeff, rcc.offset);
+                            va = s8_range(va, rcc.mode, rcc.coeff, rcc.offset); vb = s8_range(vb, rcc.mode, rcc.coeff, rcc.offset);
+                        }
+                        hpu[m] = prmt((uint32_t)ua, (uint32_t)ub, 0x5410);
+                        hpv[m] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
                     }
-                    hpu[m] = prmt((uint32_t)ua, (uint32_t)ub, 0x5410);
-                    hpv[m] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
                 }
                 sp += 2 * rowbytes;
             }
-            hpu += S8_ROWS / 2;
-            hpv += S8_ROWS / 2;
+            hpu += I19 ? S8_ROWS : S8_ROWS / 2;
+            hpv += I19 ? S8_ROWS : S8_ROWS / 2;
             left -= S8_ROWS;
             release();
         }
@@ -1105,6 +1185,36 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 d[i] = orow[i];
             vl = nl_;
             vc = nc_;
+        }
+        return;
+    }
+
+    if (I19) {
+        /* ============ stage V over 19-bit lines: yuv2planeX_16_c / yuv2plane1_16_c (output.c:163-187), warp = row (luma)
+         * or (plane, row) (chroma), lane = columns lane + 32 k ============ */
+        for (int ty = warp; ty < th; ty += 8) {
+            const int y = ry0 + ty;
+            const uint32_t *col = hb_l + lane * lstride_w + (__ldg(A.vl_pos32 + y) - lo_l);
+            int v[S8_TW / 32];
+            s19_vrow<S8_TW / 32>(col, 32 * lstride_w, A.vl_coef16 + (size_t)y * A.vl_size, A.vl_size, lane, v);
+            uint16_t *d = reinterpret_cast<uint16_t *>(dst0 + (size_t)y * A.dst_stride[0]) + x0 + lane;
+#pragma unroll
+            for (int c = 0; c < S8_TW / 32; c++)
+                if (lane + 32 * c < tw)
+                    d[32 * c] = (uint16_t)v[c];
+        }
+        for (int task = warp; task < 2 * ch; task += 8) {
+            const int pl = task & 1, y = cy0 + (task >> 1);
+            const uint32_t *col = (pl ? hb_v : hb_u) + lane * cstride_w + (__ldg(A.vc_pos32 + y) - lo_c);
+            uint16_t *d = reinterpret_cast<uint16_t *>((pl ? dst2 : dst1) + (size_t)y * A.dst_stride[pl ? 2 : 1]) + cx0 + lane;
+            for (int c = 0; 32 * c < CW; c += 2) {
+                int v[2];
+                s19_vrow<2>(col + 32 * c * cstride_w, 32 * cstride_w, A.vc_coef16 + (size_t)y * A.vc_size, A.vc_size, lane, v);
+                if (lane + 32 * c < cw)
+                    d[32 * c] = (uint16_t)v[0];
+                if (lane + 32 * c + 32 < cw)
+                    d[32 * (c + 1)] = (uint16_t)v[1];
+            }
         }
         return;
     }

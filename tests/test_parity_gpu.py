@@ -557,8 +557,8 @@ def test_rgb16bpp_odd_widths(df):
 def test_two_live_contexts_with_different_tiles():
     """The dynamic shared-memory limit is a property of the kernel function, not of a context: a second context
     using the same kernel with a smaller tile must not lower the limit of the first one."""
-    big = dict(sw=4096, sh=64, sf="yuv420p10le", dw=181, dh=45, df="yuv420p16le", flags=S.SWS_BICUBIC | BX)
-    small = dict(sw=64, sh=48, sf="yuv420p10le", dw=32, dh=24, df="yuv420p16le", flags=S.SWS_BICUBIC | BX)
+    big = dict(sw=4096, sh=64, sf="yuv420p10le", dw=181, dh=45, df="rgb48le", flags=S.SWS_BICUBIC | BX)
+    small = dict(sw=64, sh=48, sf="yuv420p10le", dw=32, dh=24, df="rgb48le", flags=S.SWS_BICUBIC | BX)
     ctxs, srcs = [], []
     for case in (big, small):
         ctxs.append(S.SwsContext(case["sw"], case["sh"], case["sf"], case["dw"], case["dh"], case["df"], case["flags"]))

@@ -81,6 +81,54 @@ def test_8bit_sources_to_high_depth_planar(sf, df, geom, flags):
         assert name.startswith("scale8"), name
 
 
+# ---- 16-bit planar destinations: 19-bit lines (hScale8To19_c / hScale16To19_c, swscale.c:60-97,144-159), the range
+# conversion's 16-bit twins (swscale.c:218-255) and yuv2planeX_16_c / yuv2plane1_16_c (output.c:163-187) ----
+@pytest.mark.parametrize("sf", ["yuv420p", "nv12", "nv21", "yuv422p", "yuv444p", "yuv420p10le", "yuv422p12le", "yuv444p16le",
+                                "yuv420p16le", "yuv420p9le"])
+@pytest.mark.parametrize("df", ["yuv420p16le", "yuv422p16le", "yuv444p16le"])
+@pytest.mark.parametrize("geom,flags", GEOMS)
+def test_16bit_planar_destinations(sf, df, geom, flags):
+    sw, sh, dw, dh = geom
+    case = dict(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags | BX)
+    for mode in ("noise", "extreme"):
+        name = _run(case, mode=mode)
+        if _sub(sf) == _sub(df) and sw <= 7 * dw:
+            assert name == ("scale16_i19" if "le" in sf else "scale8_i19"), name
+
+
+@pytest.mark.parametrize("sf,df", [("yuvj420p", "yuv420p16le"), ("yuv420p", "yuv444p16le"), ("yuv420p10le", "yuv420p16le"),
+                                   ("yuv444p16le", "yuv444p16le"), ("nv12", "yuv420p16le")])
+@pytest.mark.parametrize("geom,flags", GEOMS[:6])
+@pytest.mark.parametrize("ranges", [(0, 1), (1, 0)])
+def test_16bit_planar_destinations_range_conversion(sf, df, geom, flags, ranges):
+    sw, sh, dw, dh = geom
+    case = dict(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags | BX)
+    for mode in ("noise", "extreme"):
+        name = _run(case, mode=mode, ctx_kwargs=dict(src_range=ranges[0], dst_range=ranges[1]))
+        if _sub(sf) == _sub(df):
+            assert name.endswith("_i19"), name
+
+
+@pytest.mark.parametrize("flags", [S.SWS_SINC, S.SWS_LANCZOS, S.SWS_SPLINE, S.SWS_GAUSS])
+def test_16bit_planar_destinations_long_banks(flags):
+    """Banks of 17..38 taps (plain vertical banks: no second record), overshooting kernels on extreme input (lines below
+    -2^19 / above the 19-bit clip), one-tap rows."""
+    for sf, g in [("yuv420p", (1280, 720, 300, 170)), ("yuv420p10le", (642, 1000, 642, 210)), ("yuv444p16le", (900, 100, 120, 100)),
+                  ("yuv420p16le", (322, 242, 644, 242))]:
+        for mode in ("noise", "extreme"):
+            _run(dict(sw=g[0], sh=g[1], sf=sf, dw=g[2], dh=g[3], df=sf[:7] + "16le", flags=flags | BX), mode=mode)
+
+
+def test_16bit_planar_destination_slices_and_strides():
+    case = dict(sw=644, sh=366, sf="yuv420p", dw=400, dh=222, df="yuv420p16le", flags=S.SWS_BICUBIC | BX)
+    src = T.Frame("yuv420p", 644, 366, pad=16).randomize(5)
+    slices = [(y, min(64, 366 - y)) for y in range(0, 366, 64)]
+    want, _ = T.run_reference(src=src, slices=slices, dst_pad=6, **case)
+    got, name = T.run_cuda(src=src, slices=slices, dst_pad=6, **case)
+    assert T.first_diff(got.valid(), want.valid()) is None, name
+    assert name == "scale8_i19", name
+
+
 def test_high_depth_slices_and_strides():
     case = dict(sw=644, sh=366, sf="yuv420p10le", dw=400, dh=222, df="yuv420p10le", flags=S.SWS_BICUBIC | BX)
     src = T.Frame("yuv420p10le", 644, 366, pad=16).randomize(5)

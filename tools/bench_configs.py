@@ -53,6 +53,8 @@ CONFIGS = [
     ("X3 4K->1080p yuv420p10le->yuv420p10le bicubic", 3840, 2160, "yuv420p10le", 1920, 1080, "yuv420p10le", S.SWS_BICUBIC | S.BX),
     ("X4 4K->1080p yuv420p10le->yuv420p bicubic", 3840, 2160, "yuv420p10le", 1920, 1080, "yuv420p", S.SWS_BICUBIC | S.BX),
     ("X5 1080p yuvj420p->720p yuv420p bicubic (range)", 1920, 1080, "yuvj420p", 1280, 720, "yuv420p", S.SWS_BICUBIC | S.BX),
+    ("X6 4K->1080p yuv420p10le->yuv420p16le bicubic (19-bit lines)", 3840, 2160, "yuv420p10le", 1920, 1080, "yuv420p16le", S.SWS_BICUBIC | S.BX),
+    ("X7 1080p->4K yuv420p->yuv420p16le bicubic (19-bit lines)", 1920, 1080, "yuv420p", 3840, 2160, "yuv420p16le", S.SWS_BICUBIC | S.BX),
 ]
 
 
