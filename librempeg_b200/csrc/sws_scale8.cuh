@@ -1222,15 +1222,15 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     /* ================= stage V, luma: warp = row, lane = columns lane, lane+32, ... ================= */
     const int obits = GEN ? A.out_bits : 8, oshift = 27 - obits;
     const bool bayer = GEN && A.dither_bayer != 0;
+    /* Both loops below keep the destination pointer of the warp's row in registers and step it (recomputing it from the
+     * frame, row and tile indices cost 20 instructions per row), test the ragged-tile guards once, compute before they
+     * test (predicated stores instead of four reconvergence regions) and alternate between two tap records, one in use
+     * and one in flight (a single record copied at the end of every row cost 12 moves). */
     {
-        S8VRow vr;
-        if (warp < th)
-            vr = s8_load_vrow(A.vl + ry0 + warp);
-        for (int ty = warp; ty < th; ty += 8) {
-            const int y = ry0 + ty;
-            S8VRow nx;
-            if (ty + 8 < th)
-                nx = s8_load_vrow(A.vl + y + 8);        /* next row's taps are in flight while this row is filtered */
+        const bool in0 = lane < tw, in1 = lane + 32 < tw, in2 = lane + 64 < tw, in3 = lane + 96 < tw;
+        const size_t rstep = (size_t)8 * A.dst_stride[0];
+        uint8_t *drow = dst0 + (size_t)(ry0 + warp) * A.dst_stride[0] + ((size_t)(x0 + lane) << (obits == 8 ? 0 : 1));
+        auto vrow = [&](const S8VRow &vr, int y, uint8_t *dp) {
             const int n4 = __shfl_sync(0xffffffffu, vr.n4, 0);     /* this row's own group count, warp-uniform */
             const uint32_t *hp = hb_l + lane * lstride_w + ((vr.pos_even - lo_l) >> 1);
             int v[S8_TW / 32];
@@ -1238,67 +1238,93 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             if (LONGV && A.vl2)
                 s8_vsum_more<S8_TW / 32>(A.vl2 + y, hb_l + lane * lstride_w, lo_l, 32 * lstride_w, v);
             if (obits == 8) {
-                uint8_t *d = dst0 + (size_t)y * A.dst_stride[0] + x0 + lane;
                 /* lane + 32 c == lane (mod 8): one dither value per lane and row */
                 const int dz = (bayer ? c_dither_8x8_128[y & 7][lane & 7] : 64) << 12;
-#pragma unroll
-                for (int c = 0; c < S8_TW / 32; c++)
-                    if (lane + 32 * c < tw)
-                        d[32 * c] = (uint8_t)clip_u8((v[c] + dz) >> 19);
+                const int o0 = clip_u8((v[0] + dz) >> 19), o1 = clip_u8((v[1] + dz) >> 19);
+                const int o2 = clip_u8((v[2] + dz) >> 19), o3 = clip_u8((v[3] + dz) >> 19);
+                if (in0) dp[0] = (uint8_t)o0;
+                if (in1) dp[32] = (uint8_t)o1;
+                if (in2) dp[64] = (uint8_t)o2;
+                if (in3) dp[96] = (uint8_t)o3;
             } else {                                   /* yuv2planeX_10_c_template / yuv2plane1_10 (output.c:340-357) */
-                uint16_t *d = reinterpret_cast<uint16_t *>(dst0 + (size_t)y * A.dst_stride[0]) + x0 + lane;
-#pragma unroll
-                for (int c = 0; c < S8_TW / 32; c++)
-                    if (lane + 32 * c < tw)
-                        d[32 * c] = (uint16_t)clip_uintp2((v[c] + (1 << (oshift - 1))) >> oshift, obits);
+                uint16_t *d = reinterpret_cast<uint16_t *>(dp);
+                const int rnd = 1 << (oshift - 1);
+                const int o0 = clip_uintp2((v[0] + rnd) >> oshift, obits), o1 = clip_uintp2((v[1] + rnd) >> oshift, obits);
+                const int o2 = clip_uintp2((v[2] + rnd) >> oshift, obits), o3 = clip_uintp2((v[3] + rnd) >> oshift, obits);
+                if (in0) d[0] = (uint16_t)o0;
+                if (in1) d[32] = (uint16_t)o1;
+                if (in2) d[64] = (uint16_t)o2;
+                if (in3) d[96] = (uint16_t)o3;
             }
-            vr = nx;
+        };
+        S8VRow ra, rb;
+        if (warp < th)
+            ra = s8_load_vrow(A.vl + ry0 + warp);
+        for (int ty = warp; ty < th; ty += 16) {
+            const bool second = ty + 8 < th;
+            if (second)
+                rb = s8_load_vrow(A.vl + ry0 + ty + 8);     /* the next row's taps are in flight while this row is filtered */
+            vrow(ra, ry0 + ty, drow);
+            if (second) {
+                if (ty + 16 < th)
+                    ra = s8_load_vrow(A.vl + ry0 + ty + 16);
+                vrow(rb, ry0 + ty + 8, drow + rstep);
+            }
+            drow += 2 * rstep;
         }
     }
-    /* ================= stage V, chroma: task = (plane, row) ================= */
+    /* ================= stage V, chroma: task = (plane, row); 8 warps, so a warp keeps its plane ================= */
     if (ch > 0) {
         const bool semi = A.dst_kind == SWSC_DST_NV12 || A.dst_kind == SWSC_DST_NV21;
         const int first = A.dst_kind == SWSC_DST_NV21 ? 1 : 0;   /* nv12: U first */
-        S8VRow vr;
-        if (warp < 2 * ch)
-            vr = s8_load_vrow(A.vc + cy0 + (warp >> 1));
-        for (int task = warp; task < 2 * ch; task += 8) {
-            const int pl = task & 1, y = cy0 + (task >> 1);
-            S8VRow nx;
-            if (task + 8 < 2 * ch)
-                nx = s8_load_vrow(A.vc + y + 4);
+        const int pl = warp & 1;
+        const uint32_t *hb_p = pl ? hb_v : hb_u;
+        const int cstr = A.dst_stride[semi ? 1 : pl ? 2 : 1];
+        const size_t rstep = (size_t)4 * cstr;
+        uint8_t *drow = (semi ? dst1 + 2 * (cx0 + lane) + (pl ^ first)
+                              : (pl ? dst2 : dst1) + ((size_t)(cx0 + lane) << (obits == 8 ? 0 : 1))) +
+                        (size_t)(cy0 + (warp >> 1)) * cstr;
+        const int dstep = semi ? 64 : 32;
+        const int dcol = (cx0 + lane + 3 * pl) & 7;      /* chroma dither: U reads column x, V column x + 3 of the row (swscale.c:519-522, output.c:468-528) */
+        auto crow = [&](const S8VRow &vr, int y, uint8_t *dp) {
             const int n4 = __shfl_sync(0xffffffffu, vr.n4, 0);
-            const uint32_t *hp = (pl ? hb_v : hb_u) + lane * cstride_w + ((vr.pos_even - lo_c) >> 1);
-            /* chroma dither: U reads column x, V column x + 3 of the row (swscale.c:519-522, output.c:468-528) */
-            const int dz = (bayer ? c_dither_8x8_128[y & 7][(cx0 + lane + 3 * pl) & 7] : 64) << 12;
-            if (obits == 8) {
-                uint8_t *d = semi ? dst1 + (size_t)y * A.dst_stride[1] + 2 * (cx0 + lane) + (pl ^ first)
-                                  : (pl ? dst2 : dst1) + (size_t)y * A.dst_stride[pl ? 2 : 1] + cx0 + lane;
-                const int dstep = semi ? 64 : 32;
-                for (int c = 0; 32 * c < CW; c += 2) {
-                    int v[2];
-                    s8_vsum<2>(hp + 32 * c * cstride_w, 32 * cstride_w, vr, n4, 0, v);
-                    if (LONGV && A.vc2)
-                        s8_vsum_more<2>(A.vc2 + y, (pl ? hb_v : hb_u) + (lane + 32 * c) * cstride_w, lo_c, 32 * cstride_w, v);
-                    if (lane + 32 * c < cw)
-                        d[dstep * c] = (uint8_t)clip_u8((v[0] + dz) >> 19);
-                    if (lane + 32 * c + 32 < cw)
-                        d[dstep * (c + 1)] = (uint8_t)clip_u8((v[1] + dz) >> 19);
-                }
-            } else {
-                uint16_t *d = reinterpret_cast<uint16_t *>((pl ? dst2 : dst1) + (size_t)y * A.dst_stride[pl ? 2 : 1]) + cx0 + lane;
-                for (int c = 0; 32 * c < CW; c += 2) {
-                    int v[2];
-                    s8_vsum<2>(hp + 32 * c * cstride_w, 32 * cstride_w, vr, n4, 0, v);
-                    if (LONGV && A.vc2)
-                        s8_vsum_more<2>(A.vc2 + y, (pl ? hb_v : hb_u) + (lane + 32 * c) * cstride_w, lo_c, 32 * cstride_w, v);
-                    if (lane + 32 * c < cw)
-                        d[32 * c] = (uint16_t)clip_uintp2((v[0] + (1 << (oshift - 1))) >> oshift, obits);
-                    if (lane + 32 * c + 32 < cw)
-                        d[32 * (c + 1)] = (uint16_t)clip_uintp2((v[1] + (1 << (oshift - 1))) >> oshift, obits);
+            const uint32_t *hp = hb_p + lane * cstride_w + ((vr.pos_even - lo_c) >> 1);
+            const int dz = (bayer ? c_dither_8x8_128[y & 7][dcol] : 64) << 12;
+            for (int c = 0; 32 * c < CW; c += 2) {
+                int v[2];
+                s8_vsum<2>(hp + 32 * c * cstride_w, 32 * cstride_w, vr, n4, 0, v);
+                if (LONGV && A.vc2)
+                    s8_vsum_more<2>(A.vc2 + y, hb_p + (lane + 32 * c) * cstride_w, lo_c, 32 * cstride_w, v);
+                const bool i0 = lane + 32 * c < cw, i1 = lane + 32 * c + 32 < cw;
+                if (obits == 8) {
+                    const int o0 = clip_u8((v[0] + dz) >> 19), o1 = clip_u8((v[1] + dz) >> 19);
+                    if (i0) dp[dstep * c] = (uint8_t)o0;
+                    if (i1) dp[dstep * (c + 1)] = (uint8_t)o1;
+                } else {
+                    uint16_t *d = reinterpret_cast<uint16_t *>(dp);
+                    const int rnd = 1 << (oshift - 1);
+                    const int o0 = clip_uintp2((v[0] + rnd) >> oshift, obits), o1 = clip_uintp2((v[1] + rnd) >> oshift, obits);
+                    if (i0) d[32 * c] = (uint16_t)o0;
+                    if (i1) d[32 * (c + 1)] = (uint16_t)o1;
                 }
             }
-            vr = nx;
+        };
+        /* tasks warp, warp + 8, ...: rows cy0 + (warp >> 1) + 4 k */
+        S8VRow ra, rb;
+        const int r0 = warp >> 1;
+        if (r0 < ch)
+            ra = s8_load_vrow(A.vc + cy0 + r0);
+        for (int r = r0; r < ch; r += 8) {
+            const bool second = r + 4 < ch;
+            if (second)
+                rb = s8_load_vrow(A.vc + cy0 + r + 4);
+            crow(ra, cy0 + r, drow);
+            if (second) {
+                if (r + 8 < ch)
+                    ra = s8_load_vrow(A.vc + cy0 + r + 8);
+                crow(rb, cy0 + r + 4, drow + rstep);
+            }
+            drow += 2 * rstep;
         }
     }
 }

@@ -148,6 +148,35 @@ def make_case(rng):
     return case
 
 
+def fmt_class(f):
+    if f.endswith("f32le"):
+        return "f32"
+    if "48" in f:
+        return "rgb48"
+    if f.endswith(("565le", "555le")):
+        return "rgb16bpp"
+    if f in ("rgba", "bgra", "argb", "abgr"):
+        return "rgb32"
+    if f in ("rgb24", "bgr24"):
+        return "rgb24"
+    if f == "p010le":
+        return "p010"
+    if f.startswith("nv"):
+        return "nv"
+    d = T.depth_of(f)
+    return "yuv8" if d == 8 else "yuv16" if d == 16 else "yuvN"
+
+
+def case_class(case):
+    scaled = (case["sw"], case["sh"]) != (case["dw"], case["dh"])
+    extra = ""
+    if case["flags"] & S.SWS_FULL_CHR_H_INT:
+        extra += "+fullchr"
+    if case.get("colorspace") and case["colorspace"][0] != case["colorspace"][2]:
+        extra += "+matrix"
+    return "%s -> %s %s%s" % (fmt_class(case["sf"]), fmt_class(case["df"]), "scaled" if scaled else "same size", extra)
+
+
 def check_batch(case, frames=3):
     """The device-resident batched entry point (sws_cuda_scale_batch, frames strided in HBM) against the host
     path of the same context, which the caller has just compared with the reference.  Returns a diff string or None."""
@@ -197,6 +226,7 @@ def main():
     ran = skipped = bad = batches = 0
     kernels = {}
     reasons = {}
+    classes = {}
     for i in range(args.cases):
         if time.time() - t0 > args.seconds:
             break
@@ -226,6 +256,9 @@ def main():
             continue
         ran += 1
         kernels[name] = kernels.get(name, 0) + 1
+        if name in ("generic_tile", "tile15"):
+            k = name + ": " + case_class(case)
+            classes[k] = classes.get(k, 0) + 1
         diff = T.first_diff(got, want)
         if diff is not None:
             bad += 1
@@ -238,6 +271,8 @@ def main():
                 print("MISMATCH (device batch) via %s: %r\n    %s" % (name, case, bdiff), flush=True)
     print("fuzz: seed %d cases %d..%d: %d compared (+%d as device batches), %d refused, %d mismatches in %.0f s; kernels %s"
           % (args.seed, args.start, i, ran, batches, skipped, bad, time.time() - t0, dict(sorted(kernels.items()))))
+    for k, n in sorted(classes.items(), key=lambda kv: -kv[1])[:40]:
+        print("  general kernels %5d x %s" % (n, k))
     for why, n in sorted(reasons.items(), key=lambda kv: -kv[1]):
         print("  refused %5d x %s" % (n, why))
     return 1 if bad else 0
