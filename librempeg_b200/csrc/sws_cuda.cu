@@ -2356,6 +2356,8 @@ static scale8_kernel_t pick_scale8(int fs4, int rgbk, bool mma, int srck, bool w
         return S8_PICK_K(false, S8_SRC_RGB);
     if (srck == S8_SRC_U16)     /* 9..16-bit planar sources: IDP.2A horizontal stage */
         return S8_PICK_K(false, S8_SRC_U16);
+    if (srck == S8_SRC_P010)    /* p010le sources: planar / semi-planar YUV or shared-chroma packed RGB out */
+        return rgbk == 1 ? S8_PICK(1, false, S8_SRC_P010) : S8_PICK(0, false, S8_SRC_P010);
     if (mma)                    /* fs4 = K steps of the tensor-pipe horizontal stage */
         return rgbk == 2 ? S8_PICK_MMA(2) : rgbk == 1 ? S8_PICK_MMA(1) : S8_PICK_MMA(0);
     return S8_PICK_K(false, S8_SRC_U8);
@@ -2571,6 +2573,27 @@ static int s16_seg_bytes(const SwsFirBank *b, int fs4, int tile_cols)
     return worst;
 }
 
+/* interleaved 16-bit chroma (p010le), bytes per row of ONE plane (a staged row is twice that): rows start at a multiple
+ * of 8 chroma positions, a column reads 4 fs4 words (one per chroma position) from its first position */
+static int p10_seg_bytes(const SwsFirBank *b, int fs4, int tile_cols)
+{
+    int worst = 16;
+    for (int x0 = 0; x0 < b->len; x0 += tile_cols) {
+        const int x1 = x0 + tile_cols - 1 < b->len - 1 ? x0 + tile_cols - 1 : b->len - 1;
+        const int a0 = b->pos[x0] & ~7;
+        int need = 0;
+        for (int x = x0; x <= x1; x++) {
+            if (b->pos[x] < b->pos[x0])
+                return -1;
+            const int e = (b->pos[x] - a0 + 4 * fs4) * 2;
+            if (e > need) need = e;
+        }
+        need = (need + 15) & ~15;
+        if (need > worst) worst = need;
+    }
+    return worst;
+}
+
 static bool rgb420_matrix_ok(const SwsCudaPlan *p);
 static bool rgb444_matrix_ok(const SwsCudaPlan *p);
 
@@ -2639,9 +2662,13 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
         return 0;
     /* sources: 8-bit planar / nv12 / nv21, or 9..16-bit little-endian planar (hScale16To15_c) */
     const bool s16 = !rgbs && p->src_bits > 8;
-    const int srck = rgbs ? S8_SRC_RGB : s16 ? S8_SRC_U16 : S8_SRC_U8;
-    if (s16 && (p->src_layout != SWSC_SRC_PLANAR || p->src_shift || p->src_bits > 16))
+    /* p010le (p010LEToY/UV_c: the 16-bit containers >> 6, chroma interleaved U first) */
+    const bool p10 = s16 && p->src_layout == SWSC_SRC_NV12 && p->src_shift == 6 && p->src_bits == 10;
+    const int srck = rgbs ? S8_SRC_RGB : p10 ? S8_SRC_P010 : s16 ? S8_SRC_U16 : S8_SRC_U8;
+    if (s16 && !p10 && (p->src_layout != SWSC_SRC_PLANAR || p->src_shift || p->src_bits > 16))
         return 0;
+    if (p10 && (i19 || p->full_chr))
+        return 0;                     /* (compiled for the planar and the shared-chroma packed RGB writers only) */
     /* destinations: 8-bit planar / semi-planar YUV, 9..14-bit planar YUV, or packed 8-bit RGB with one chroma
      * sample per pixel pair */
     const bool rgb = (p->dst_kind >= SWSC_DST_RGB24 && p->dst_kind <= SWSC_DST_ABGR) ||
@@ -2652,7 +2679,8 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
                 !p->has_chroma || (p->full_chr && p->dst_kind > SWSC_DST_ABGR)))
         return 0;
     if (!rgb && !i19 && p->dst_kind != SWSC_DST_PLANAR8 && p->dst_kind != SWSC_DST_NV12 && p->dst_kind != SWSC_DST_NV21 &&
-        !(p->dst_kind == SWSC_DST_PLANARN && p->dst_bits >= 9 && p->dst_bits <= 14 && !p->dst_shift))
+        !(p->dst_kind == SWSC_DST_PLANARN && p->dst_bits >= 9 && p->dst_bits <= 14 && !p->dst_shift) &&
+        !(p->dst_kind == SWSC_DST_P010 && p->dst_bits == 10 && p->dst_shift == 6))
         return 0;
     if (!p->has_chroma || !p->dst_has_chroma || p->special || p->unscaled_lut)
         return 0;
@@ -2691,7 +2719,7 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
         }
     }
     int seg_l = ret ? -1 : s16 ? s16_seg_bytes(hl, fs4, S8_TW) : s8_seg_bytes(hl, fs4, S8_TW);
-    int seg_c = ret ? -1 : s16 ? s16_seg_bytes(hc, fs4, cw) : s8_seg_bytes(hc, fs4, cw);
+    int seg_c = ret ? -1 : p10 ? p10_seg_bytes(hc, fs4, cw) : s16 ? s16_seg_bytes(hc, fs4, cw) : s8_seg_bytes(hc, fs4, cw);
     int seg_sy = 0, seg_sc = 0;
     if (!ret && rgbs) {
         if (s8_rgb_segs(hl, hc, p->chr_dst_hsub, p->src_rgb_half, p->src_bpp, fs4, &seg_l, &seg_sy, &seg_sc) < 0)
@@ -2702,7 +2730,8 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     const bool inter = p->src_layout != SWSC_SRC_PLANAR;
     int mma = 0, ks = 0;
     /* what the MMA variants are compiled for: no range conversion, 8-bit output, vertical banks of one record */
-    const bool plain = !p->range_mode && p->dst_kind != SWSC_DST_PLANARN && !i19 && lparts == 1 && cparts == 1;
+    const bool plain = !p->range_mode && p->dst_kind != SWSC_DST_PLANARN && p->dst_kind != SWSC_DST_P010 && !i19 &&
+                       lparts == 1 && cparts == 1;
     if (!ret && !s16 && !rgbs && plain && seg_l >= 0 && seg_c >= 0 &&
         !(getenv("SWS_B200_DISABLE") && strstr(getenv("SWS_B200_DISABLE"), "s8mma"))) {
         const int kl = s8_mma_ksteps(hl, S8_TW, false), kc = s8_mma_ksteps(hc, cw, inter);
@@ -2728,7 +2757,7 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     }
     if (seg_l < 0 || seg_c < 0)
         ret = 1;
-    else if (seg_l > 2048 || seg_c > (s16 ? 2048 : 1024) || !get_encode_tiled())
+    else if (seg_l > 2048 || seg_c > (s16 && !p10 ? 2048 : 1024) || !get_encode_tiled())
         ret = 1;                      /* one ring-slot row is one TMA box row of at most 256 elements of 4 or 8 bytes */
     /* bytes per row of one chroma plane; interleaved rows are 2 seg_c bytes */
     const int rowc = p->src_layout == SWSC_SRC_PLANAR ? seg_c : 2 * seg_c;
@@ -2875,7 +2904,7 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     /* source planes as tensors of 4- or 8-byte elements {row elements, rows, frames}: a ring slot is one box of S8_ROWS rows */
     CUtensorMap my, mu, mv;
     const bool planar = p->src_layout == SWSC_SRC_PLANAR;
-    const int es = st->s8_elt_shift, bps = st->s8_srck == S8_SRC_U16 ? 1 : 0;
+    const int es = st->s8_elt_shift, bps = st->s8_srck == S8_SRC_U16 || st->s8_srck == S8_SRC_P010 ? 1 : 0;
     const CUtensorMapDataType edt = es == 3 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
     const uint64_t emask = (1u << es) - 1;
     const uint64_t fs_y = nb_frames > 1 ? src_fstride[0] : (uint64_t)src_stride[0] * p->src_h;
@@ -2917,7 +2946,8 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.range_mode = p->range_mode;
     a.lum_rc_coeff = (int)p->lum_rc_coeff; a.lum_rc_offset = (int)p->lum_rc_offset;
     a.chr_rc_coeff = (int)p->chr_rc_coeff; a.chr_rc_offset = (int)p->chr_rc_offset;
-    a.out_bits = p->dst_kind == SWSC_DST_PLANARN ? p->dst_bits : 8;
+    a.out_bits = p->dst_kind == SWSC_DST_PLANARN || p->dst_kind == SWSC_DST_P010 ? p->dst_bits : 8;
+    a.out_lshift = p->dst_kind == SWSC_DST_P010 ? p->dst_shift : 0;
     if (rgbs) {
         /* matrix rows as 16-bit pairs in the byte order of a pixel word (unused bytes get a zero coefficient) */
         int ky[4] = { 0, 0, 0, 0 }, ku[4] = { 0, 0, 0, 0 }, kv[4] = { 0, 0, 0, 0 };
@@ -2950,7 +2980,7 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     dim3 grid((p->dst_w + S8_TW - 1) / S8_TW, (y1 - y0 + st->s8_tile_h - 1) / st->s8_tile_h, nb_frames);
     pick_scale8(st->s8_fs4, i19 ? 3 : rgb ? (p->full_chr ? 2 : 1) : 0, st->s8_mma, st->s8_srck, st->s8_wide)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
     st->kernel_name = rgbs ? "scale_rgb_dp2a" : i19 ? (st->s8_srck == S8_SRC_U16 ? "scale16_i19" : "scale8_i19")
-                           : st->s8_srck == S8_SRC_U16 ? "scale16_dp2a" : st->s8_mma ? "scale8_mma" : "scale8_dp4a";
+                           : st->s8_srck == S8_SRC_U16 || st->s8_srck == S8_SRC_P010 ? "scale16_dp2a" : st->s8_mma ? "scale8_mma" : "scale8_dp4a";
     CUDA_OK(cudaGetLastError());
     st->launches++;
     return 1;

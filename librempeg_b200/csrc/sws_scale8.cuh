@@ -48,7 +48,7 @@
 #define S8_RGB_CTAS 4     /* CTAs per SM the packed-RGB variant is compiled for (register budget of its V + colour stage) */
 #endif
 #define S8_VF4 5         /* vertical taps: up to 5 groups of 4 (16 taps + parity pad) */
-enum { S8_SRC_U8 = 0, S8_SRC_U16 = 1, S8_SRC_RGB = 2 };
+enum { S8_SRC_U8 = 0, S8_SRC_U16 = 1, S8_SRC_RGB = 2, S8_SRC_P010 = 3 };
 
 struct S8VRow {          /* per destination row, 48 bytes */
     int pos_even;        /* first source row, rounded down to even; luma bank, RGB output: bit 0 = this row takes
@@ -90,6 +90,7 @@ struct Scale8Args {
     const int32_t *vl_pos32, *vc_pos32;
     int vl_size, vc_size;
     int out_bits;            /* planar destinations: 8, or 9..14 (16-bit little-endian samples) */
+    int out_lshift;          /* p010le destination: 10-bit samples shifted up by 6, chroma interleaved U first */
     int dither_bayer;        /* 8-bit planar output of > 8-bit sources: ff_dither_8x8_128 instead of the constant 64 */
     const int *hl_pos, *hc_pos;
     const uint32_t *hl_cl, *hl_ch, *hc_cl, *hc_ch;
@@ -337,7 +338,7 @@ __device__ __forceinline__ int dp2a_hi_us(uint32_t a, uint32_t b, int c)
 /* hScale16To15_c (swscale.c:99-125) of one staged row of 16-bit samples for one output column: two samples per
  * word, an odd first sample is a 16-bit funnel shift; IDP.2A against the split coefficient bytes, everything
  * modulo 2^32 like the C code's int accumulator */
-template <int FS4, bool I19 = false>
+template <int FS4, bool I19 = false, int SSH = 0>
 __device__ __forceinline__ int s16_hfir(const unsigned char *srow, int sh, int hshift, const uint32_t (&cl)[FS4],
                                         const uint32_t (&ch)[FS4])
 {
@@ -347,7 +348,11 @@ __device__ __forceinline__ int s16_hfir(const unsigned char *srow, int sh, int h
 #pragma unroll
     for (int k = 0; k < FS4; k++) {
         const uint32_t w1 = wp[2 * k + 1], w2 = wp[2 * k + 2];
-        const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
+        uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
+        if (SSH) {               /* p010LEToY_c (input.c): the sample is the container >> 6 */
+            v0 = (v0 >> SSH) & (0x00010001u * (0xFFFFu >> SSH));
+            v1 = (v1 >> SSH) & (0x00010001u * (0xFFFFu >> SSH));
+        }
         acc_l = dp2a_lo_uu(v0, cl[k], acc_l);
         acc_h = dp2a_lo_us(v0, ch[k], acc_h);
         acc_l = dp2a_hi_uu(v1, cl[k], acc_l);
@@ -355,6 +360,29 @@ __device__ __forceinline__ int s16_hfir(const unsigned char *srow, int sh, int h
         w0 = w2;
     }
     return min(((acc_h << 8) + acc_l) >> hshift, I19 ? (1 << 19) - 1 : (1 << 15) - 1);     /* hScale16To15_c / To19_c */
+}
+
+/* one staged row of interleaved 16-bit chroma (p010le: U in the low, V in the high half of every word; p010LEToUV_c,
+ * input.c) for one output column: sample pairs of each plane are cut out of two words with PRMT, shifted down by 6 */
+template <int FS4>
+__device__ __forceinline__ void s16_hfir_uv(const unsigned char *srow, int hshift, const uint32_t (&cl)[FS4],
+                                            const uint32_t (&ch)[FS4], int &u, int &v)
+{
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(srow);
+    int ul = 0, uh = 0, vl = 0, vh = 0;
+    constexpr uint32_t M = 0x03FF03FFu;
+#pragma unroll
+    for (int k = 0; k < FS4; k++) {
+        const uint32_t w0 = wp[4 * k], w1 = wp[4 * k + 1], w2 = wp[4 * k + 2], w3 = wp[4 * k + 3];
+        const uint32_t u0 = (prmt(w0, w1, 0x5410) >> 6) & M, u1 = (prmt(w2, w3, 0x5410) >> 6) & M;
+        const uint32_t v0 = (prmt(w0, w1, 0x7632) >> 6) & M, v1 = (prmt(w2, w3, 0x7632) >> 6) & M;
+        ul = dp2a_lo_uu(u0, cl[k], ul); uh = dp2a_lo_us(u0, ch[k], uh);
+        ul = dp2a_hi_uu(u1, cl[k], ul); uh = dp2a_hi_us(u1, ch[k], uh);
+        vl = dp2a_lo_uu(v0, cl[k], vl); vh = dp2a_lo_us(v0, ch[k], vh);
+        vl = dp2a_hi_uu(v1, cl[k], vl); vh = dp2a_hi_us(v1, ch[k], vh);
+    }
+    u = min(((uh << 8) + ul) >> hshift, (1 << 15) - 1);
+    v = min(((vh << 8) + vl) >> hshift, (1 << 15) - 1);
 }
 
 /* vertical FIR for NC columns (transposed 15-bit lines, cstep words apart): bias + sum of taps, before
@@ -522,7 +550,9 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
 {
     constexpr bool RGB = RGBK == 1 || RGBK == 2;
     constexpr bool I19 = RGBK == 3;               /* int32 lines of 19 bits, one per word, for 16-bit planar destinations */
-    constexpr bool S16 = SRCK == S8_SRC_U16;      /* 16-bit samples straight from the ring */
+    constexpr bool P10 = SRCK == S8_SRC_P010;     /* p010le: 16-bit containers >> 6, chroma interleaved U first */
+    constexpr bool S16 = SRCK == S8_SRC_U16 || P10;   /* 16-bit samples straight from the ring */
+    constexpr int SSH = P10 ? 6 : 0;
     constexpr bool RGBS = SRCK == S8_SRC_RGB;     /* packed 8-bit RGB rows in the ring, converted to 14-bit Y/U/V samples per slot */
     extern __shared__ __align__(128) unsigned char s8_smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[S8_MAX_STAGES];
@@ -637,7 +667,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                         s8_tma_load(d, &map_u, bar, cx, row, f);
                         s8_tma_load(d + S8_ROWS * A.seg_c, &map_v, bar, cx, row, f);
                     } else {
-                        s8_tma_load(d, &map_u, bar, (a0c << 1) >> A.elt_shift, row, f);   /* two bytes per sample pair */
+                        s8_tma_load(d, &map_u, bar, (a0c << (1 + A.bps)) >> A.elt_shift, row, f);   /* two samples per chroma position */
                     }
                 }
                 if (++b == A.stages) {
@@ -868,8 +898,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 if (2 * m < left) {
                     int va, vb;
                     if (S16) {
-                        va = s16_hfir<FS4, I19>(sp + (2 * m) * seg, sh, A.h_shift, cl, chh);
-                        vb = s16_hfir<FS4, I19>(sp + (2 * m + 1) * seg, sh, A.h_shift, cl, chh);
+                        va = s16_hfir<FS4, I19, SSH>(sp + (2 * m) * seg, sh, A.h_shift, cl, chh);
+                        vb = s16_hfir<FS4, I19, SSH>(sp + (2 * m + 1) * seg, sh, A.h_shift, cl, chh);
                     } else {
                         va = s8_hfir<FS4, I19>(sp + (2 * m) * seg, sh, cl, chh);
                         vb = s8_hfir<FS4, I19>(sp + (2 * m + 1) * seg, sh, cl, chh);
@@ -968,7 +998,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
         uint32_t *hpu = hb_u + cslot(x) * cstride_w + (I19 ? 2 : 1) * npair * g;
         uint32_t *hpv = hb_v + cslot(x) * cstride_w + (I19 ? 2 : 1) * npair * g;
         const int rowbytes = planar ? seg : 2 * seg;
-        const int so = 2 * npair * g * rowbytes + (S16 ? (off >> 1) * 4 : planar ? (off & ~3) : ((2 * off) & ~3));
+        const int so = 2 * npair * g * rowbytes + (P10 ? off * 4 : S16 ? (off >> 1) * 4 : planar ? (off & ~3) : ((2 * off) & ~3));
         const int sh = S16 ? (off & 1) * 16 : planar ? (off & 3) * 8 : (off & 1) * 16;
         int left = nc - 2 * npair * g;
         for (int qc = 0; qc < npc; qc++) {
@@ -977,7 +1007,10 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             for (int m = 0; m < npair; m++) {
                 if (2 * m < left) {
                     int ua, ub, va, vb;
-                    if (S16) {               /* planar 16-bit chroma */
+                    if (P10) {               /* interleaved 16-bit chroma */
+                        s16_hfir_uv<FS4>(sp, A.h_shift, cl, chh, ua, va);
+                        s16_hfir_uv<FS4>(sp + rowbytes, A.h_shift, cl, chh, ub, vb);
+                    } else if (S16) {        /* planar 16-bit chroma */
                         ua = s16_hfir<FS4, I19>(sp, sh, A.h_shift, cl, chh);
                         ub = s16_hfir<FS4, I19>(sp + seg, sh, A.h_shift, cl, chh);
                         va = s16_hfir<FS4, I19>(sp + S8_ROWS * seg, sh, A.h_shift, cl, chh);
@@ -1222,6 +1255,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     /* ================= stage V, luma: warp = row, lane = columns lane, lane+32, ... ================= */
     const int obits = GEN ? A.out_bits : 8, oshift = 27 - obits;
     const bool bayer = GEN && A.dither_bayer != 0;
+    const int olsh = GEN ? A.out_lshift : 0;       /* p010le: yuv2p010l1/lX_c, yuv2p010cX_c (output.c:538-589) */
     /* Both loops below keep the destination pointer of the warp's row in registers and step it (recomputing it from the
      * frame, row and tile indices cost 20 instructions per row), test the ragged-tile guards once, compute before they
      * test (predicated stores instead of four reconvergence regions) and alternate between two tap records, one in use
@@ -1251,10 +1285,10 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 const int rnd = 1 << (oshift - 1);
                 const int o0 = clip_uintp2((v[0] + rnd) >> oshift, obits), o1 = clip_uintp2((v[1] + rnd) >> oshift, obits);
                 const int o2 = clip_uintp2((v[2] + rnd) >> oshift, obits), o3 = clip_uintp2((v[3] + rnd) >> oshift, obits);
-                if (in0) d[0] = (uint16_t)o0;
-                if (in1) d[32] = (uint16_t)o1;
-                if (in2) d[64] = (uint16_t)o2;
-                if (in3) d[96] = (uint16_t)o3;
+                if (in0) d[0] = (uint16_t)(o0 << olsh);
+                if (in1) d[32] = (uint16_t)(o1 << olsh);
+                if (in2) d[64] = (uint16_t)(o2 << olsh);
+                if (in3) d[96] = (uint16_t)(o3 << olsh);
             }
         };
         S8VRow ra, rb;
@@ -1275,13 +1309,13 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     }
     /* ================= stage V, chroma: task = (plane, row); 8 warps, so a warp keeps its plane ================= */
     if (ch > 0) {
-        const bool semi = A.dst_kind == SWSC_DST_NV12 || A.dst_kind == SWSC_DST_NV21;
-        const int first = A.dst_kind == SWSC_DST_NV21 ? 1 : 0;   /* nv12: U first */
+        const bool semi = A.dst_kind == SWSC_DST_NV12 || A.dst_kind == SWSC_DST_NV21 || A.dst_kind == SWSC_DST_P010;
+        const int first = A.dst_kind == SWSC_DST_NV21 ? 1 : 0;   /* nv12, p010le: U first */
         const int pl = warp & 1;
         const uint32_t *hb_p = pl ? hb_v : hb_u;
         const int cstr = A.dst_stride[semi ? 1 : pl ? 2 : 1];
         const size_t rstep = (size_t)4 * cstr;
-        uint8_t *drow = (semi ? dst1 + 2 * (cx0 + lane) + (pl ^ first)
+        uint8_t *drow = (semi ? dst1 + ((2 * (cx0 + lane) + (pl ^ first)) << (obits == 8 ? 0 : 1))
                               : (pl ? dst2 : dst1) + ((size_t)(cx0 + lane) << (obits == 8 ? 0 : 1))) +
                         (size_t)(cy0 + (warp >> 1)) * cstr;
         const int dstep = semi ? 64 : 32;
@@ -1304,8 +1338,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                     uint16_t *d = reinterpret_cast<uint16_t *>(dp);
                     const int rnd = 1 << (oshift - 1);
                     const int o0 = clip_uintp2((v[0] + rnd) >> oshift, obits), o1 = clip_uintp2((v[1] + rnd) >> oshift, obits);
-                    if (i0) d[32 * c] = (uint16_t)o0;
-                    if (i1) d[32 * (c + 1)] = (uint16_t)o1;
+                    if (i0) d[dstep * c] = (uint16_t)(o0 << olsh);
+                    if (i1) d[dstep * (c + 1)] = (uint16_t)(o1 << olsh);
                 }
             }
         };

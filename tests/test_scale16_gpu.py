@@ -129,6 +129,37 @@ def test_16bit_planar_destination_slices_and_strides():
     assert name == "scale8_i19", name
 
 
+# ---- p010le on either side of the scaler: p010LEToY/UV_c readers (container >> 6, interleaved chroma) and the
+# yuv2p010l1/lX_c, yuv2p010cX_c writers (output.c:538-589) ----
+@pytest.mark.parametrize("df", ["yuv420p10le", "yuv420p", "nv12", "p010le", "yuv444p12le", "rgb24", "bgra", "yuvj420p"])
+@pytest.mark.parametrize("geom,flags", GEOMS)
+def test_p010_sources(df, geom, flags):
+    sw, sh, dw, dh = geom
+    case = dict(sw=sw, sh=sh, sf="p010le", dw=dw, dh=dh, df=df, flags=flags | BX)
+    for mode in ("noise", "extreme"):
+        name = _run(case, mode=mode)
+        if (_sub(df) == (1, 1) or df in ("rgb24", "bgra")) and sw <= 7 * dw:
+            assert name == "scale16_dp2a", name
+
+
+@pytest.mark.parametrize("sf", ["yuv420p", "nv12", "nv21", "yuv420p10le", "yuv420p16le", "yuv422p", "rgb24", "bgra", "yuvj420p"])
+@pytest.mark.parametrize("geom,flags", GEOMS[:7])
+def test_p010_destinations(sf, geom, flags):
+    sw, sh, dw, dh = geom
+    case = dict(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df="p010le", flags=flags | BX)
+    for mode in ("noise", "extreme"):
+        name = _run(case, mode=mode)
+        if _sub(sf) == (1, 1):
+            assert name.startswith("scale"), name
+
+
+def test_p010_4k_downscale_full_size():
+    case = dict(sw=3840, sh=2160, sf="p010le", dw=1920, dh=1080, df="p010le", flags=S.SWS_BICUBIC | BX)
+    assert _run(case) == "scale16_dp2a"
+    case = dict(sw=3840, sh=2160, sf="p010le", dw=1920, dh=1080, df="nv12", flags=S.SWS_BICUBIC | BX)
+    assert _run(case) == "scale16_dp2a"
+
+
 def test_high_depth_slices_and_strides():
     case = dict(sw=644, sh=366, sf="yuv420p10le", dw=400, dh=222, df="yuv420p10le", flags=S.SWS_BICUBIC | BX)
     src = T.Frame("yuv420p10le", 644, 366, pad=16).randomize(5)
