@@ -2351,7 +2351,8 @@ static scale8_kernel_t pick_scale8(int fs4, int rgbk, bool mma, int srck, bool w
                         : sws_scale8_kernel<4, R, true, S8_SRC_U8>)
 #define S8_PICK_K(M, K) (rgbk == 2 ? S8_PICK(2, M, K) : rgbk == 1 ? S8_PICK(1, M, K) : S8_PICK(0, M, K))
     if (rgbk == 3)              /* 19-bit lines into 16-bit planar destinations: dot-product horizontal stage only */
-        return srck == S8_SRC_U16 ? S8_PICK(3, false, S8_SRC_U16) : S8_PICK(3, false, S8_SRC_U8);
+        return srck == S8_SRC_U16 ? S8_PICK(3, false, S8_SRC_U16) : srck == S8_SRC_RGB ? S8_PICK(3, false, S8_SRC_RGB)
+                                                                                        : S8_PICK(3, false, S8_SRC_U8);
     if (srck == S8_SRC_RGB)     /* packed 8-bit RGB sources: reader stage + IDP.2A horizontal stage */
         return S8_PICK_K(false, S8_SRC_RGB);
     if (srck == S8_SRC_U16)     /* 9..16-bit planar sources: IDP.2A horizontal stage */
@@ -2651,13 +2652,13 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     const bool rgbs = p->src_layout == SWSC_SRC_RGB;
     /* 19-bit lines (hScale8To19_c / hScale16To19_c, swscale.c:60-97,144-159): 16-bit planar YUV destinations only */
     const bool i19 = p->inter_bits == 19;
-    if (i19 && (p->dst_kind != SWSC_DST_PLANAR16 || p->dst_shift || rgbs))
+    if (i19 && (p->dst_kind != SWSC_DST_PLANAR16 || p->dst_shift))
         return 0;
     if ((p->inter_bits != 15 && !i19) || (p->src_layout > SWSC_SRC_NV21 && !rgbs) || p->src_alpha || p->dst_alpha)
         return 0;
     /* packed 8-bit RGB sources: samples the readers keep inside 14 bits (checked again at every launch: the matrix can
      * change), luma and chroma out of the same rows */
-    if (rgbs && (p->h_shift != 13 || p->chr_src_h != p->src_h || (p->src_bpp != 3 && p->src_bpp != 4) ||
+    if (rgbs && (p->h_shift != (i19 ? 9 : 13) || p->chr_src_h != p->src_h || (p->src_bpp != 3 && p->src_bpp != 4) ||
                  !(p->src_rgb_half ? rgb420_matrix_ok(p) : rgb444_matrix_ok(p))))
         return 0;
     /* sources: 8-bit planar / nv12 / nv21, or 9..16-bit little-endian planar (hScale16To15_c) */
@@ -2880,7 +2881,7 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
         fprintf(stderr, "[swscaler-b200] scale8: %s fs4=%d tile_h=%d nl_cap=%d nc_cap=%d seg_l=%d seg_c=%d slot=%d stages=%d smem=%zu\n",
                 rgbs ? "rgb" : i19 ? "i19" : s16 ? "dp2a16" : mma ? "mma" : "dp4a", st->s8_fs4, th, nl_cap, nc_cap, seg_l, seg_c, slot, stages, smem);
     if (!st->fast_ok && !st->fast16_ok)
-        st->kernel_name = rgbs ? "scale_rgb_dp2a" : i19 ? (s16 ? "scale16_i19" : "scale8_i19") : s16 ? "scale16_dp2a" : mma ? "scale8_mma" : "scale8_dp4a";
+        st->kernel_name = rgbs ? (i19 ? "scale_rgb_i19" : "scale_rgb_dp2a") : i19 ? (s16 ? "scale16_i19" : "scale8_i19") : s16 ? "scale16_dp2a" : mma ? "scale8_mma" : "scale8_dp4a";
     return 0;
 }
 
@@ -2979,7 +2980,7 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.hl_goff = st->s8_hl_goff; a.hc_goff = st->s8_hc_goff; a.hl_B = st->s8_hl_B; a.hc_B = st->s8_hc_B;
     dim3 grid((p->dst_w + S8_TW - 1) / S8_TW, (y1 - y0 + st->s8_tile_h - 1) / st->s8_tile_h, nb_frames);
     pick_scale8(st->s8_fs4, i19 ? 3 : rgb ? (p->full_chr ? 2 : 1) : 0, st->s8_mma, st->s8_srck, st->s8_wide)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
-    st->kernel_name = rgbs ? "scale_rgb_dp2a" : i19 ? (st->s8_srck == S8_SRC_U16 ? "scale16_i19" : "scale8_i19")
+    st->kernel_name = rgbs ? (i19 ? "scale_rgb_i19" : "scale_rgb_dp2a") : i19 ? (st->s8_srck == S8_SRC_U16 ? "scale16_i19" : "scale8_i19")
                            : st->s8_srck == S8_SRC_U16 || st->s8_srck == S8_SRC_P010 ? "scale16_dp2a" : st->s8_mma ? "scale8_mma" : "scale8_dp4a";
     CUDA_OK(cudaGetLastError());
     st->launches++;

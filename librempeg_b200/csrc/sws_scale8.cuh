@@ -806,13 +806,22 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 for (int m = 0; m < S8_ROWS / 4; m++) {
                     const int r = 2 * ((S8_ROWS / 4) * gl + m), li = rbase + r - lo_l;
                     if (li >= 0 && li < nl) {
-                        int va = s16_hfir<FS4>(sp + r * A.seg_sy, shl, 13, lcl, lch);
-                        int vb = s16_hfir<FS4>(sp + (r + 1) * A.seg_sy, shl, 13, lcl, lch);
-                        if (rcl.mode) {
-                            va = s8_range(va, rcl.mode, rcl.coeff, rcl.offset);
-                            vb = s8_range(vb, rcl.mode, rcl.coeff, rcl.offset);
+                        int va = s16_hfir<FS4, I19>(sp + r * A.seg_sy, shl, I19 ? 9 : 13, lcl, lch);
+                        int vb = s16_hfir<FS4, I19>(sp + (r + 1) * A.seg_sy, shl, I19 ? 9 : 13, lcl, lch);
+                        if (I19) {
+                            if (rcl.mode) {
+                                va = s19_range(va, rcl.mode, (uint32_t)rcl.coeff, A.lum_rc_offset64);
+                                vb = s19_range(vb, rcl.mode, (uint32_t)rcl.coeff, A.lum_rc_offset64);
+                            }
+                            hb_l[lslot * lstride_w + li] = (uint32_t)va;
+                            hb_l[lslot * lstride_w + li + 1] = (uint32_t)vb;
+                        } else {
+                            if (rcl.mode) {
+                                va = s8_range(va, rcl.mode, rcl.coeff, rcl.offset);
+                                vb = s8_range(vb, rcl.mode, rcl.coeff, rcl.offset);
+                            }
+                            hb_l[lslot * lstride_w + (li >> 1)] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
                         }
-                        hb_l[lslot * lstride_w + (li >> 1)] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
                     }
                 }
             }
@@ -823,16 +832,27 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 for (int m = 0; m < npair; m++) {
                     const int r = 2 * (npair * gc + m), ci = rbase + r - lo_c;
                     if (ci >= 0 && ci < nc) {
-                        int ua = s16_hfir<FS4>(su + r * A.seg_sc, shc, 13, ccl, cch);
-                        int ub = s16_hfir<FS4>(su + (r + 1) * A.seg_sc, shc, 13, ccl, cch);
-                        int va = s16_hfir<FS4>(sv + r * A.seg_sc, shc, 13, ccl, cch);
-                        int vb = s16_hfir<FS4>(sv + (r + 1) * A.seg_sc, shc, 13, ccl, cch);
-                        if (rcc.mode) {
-                            ua = s8_range(ua, rcc.mode, rcc.coeff, rcc.offset); ub = s8_range(ub, rcc.mode, rcc.coeff, rcc.offset);
-                            va = s8_range(va, rcc.mode, rcc.coeff, rcc.offset); vb = s8_range(vb, rcc.mode, rcc.coeff, rcc.offset);
+                        int ua = s16_hfir<FS4, I19>(su + r * A.seg_sc, shc, I19 ? 9 : 13, ccl, cch);
+                        int ub = s16_hfir<FS4, I19>(su + (r + 1) * A.seg_sc, shc, I19 ? 9 : 13, ccl, cch);
+                        int va = s16_hfir<FS4, I19>(sv + r * A.seg_sc, shc, I19 ? 9 : 13, ccl, cch);
+                        int vb = s16_hfir<FS4, I19>(sv + (r + 1) * A.seg_sc, shc, I19 ? 9 : 13, ccl, cch);
+                        if (I19) {
+                            if (rcc.mode) {
+                                ua = s19_range(ua, rcc.mode, (uint32_t)rcc.coeff, A.chr_rc_offset64);
+                                ub = s19_range(ub, rcc.mode, (uint32_t)rcc.coeff, A.chr_rc_offset64);
+                                va = s19_range(va, rcc.mode, (uint32_t)rcc.coeff, A.chr_rc_offset64);
+                                vb = s19_range(vb, rcc.mode, (uint32_t)rcc.coeff, A.chr_rc_offset64);
+                            }
+                            hb_u[xc * cstride_w + ci] = (uint32_t)ua; hb_u[xc * cstride_w + ci + 1] = (uint32_t)ub;
+                            hb_v[xc * cstride_w + ci] = (uint32_t)va; hb_v[xc * cstride_w + ci + 1] = (uint32_t)vb;
+                        } else {
+                            if (rcc.mode) {
+                                ua = s8_range(ua, rcc.mode, rcc.coeff, rcc.offset); ub = s8_range(ub, rcc.mode, rcc.coeff, rcc.offset);
+                                va = s8_range(va, rcc.mode, rcc.coeff, rcc.offset); vb = s8_range(vb, rcc.mode, rcc.coeff, rcc.offset);
+                            }
+                            hb_u[cslot(xc) * cstride_w + (ci >> 1)] = prmt((uint32_t)ua, (uint32_t)ub, 0x5410);
+                            hb_v[cslot(xc) * cstride_w + (ci >> 1)] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
                         }
-                        hb_u[cslot(xc) * cstride_w + (ci >> 1)] = prmt((uint32_t)ua, (uint32_t)ub, 0x5410);
-                        hb_v[cslot(xc) * cstride_w + (ci >> 1)] = prmt((uint32_t)va, (uint32_t)vb, 0x5410);
                     }
                 }
             }

@@ -10,6 +10,14 @@ from librempeg_b200 import swscale as S
 pytestmark = pytest.mark.gpu
 BX = S.SWS_BITEXACT | S.SWS_ACCURATE_RND
 
+RGB_GEOMS_EARLY = [
+    ((640, 360, 320, 180), 4),       # SWS_BICUBIC 2:1
+    ((644, 366, 1288, 732), 4),      # 1:2 upscale, ragged tiles
+    ((322, 242, 400, 300), 2),       # SWS_BILINEAR
+    ((350, 130, 350, 260), 2),       # vertical only
+    ((642, 362, 322, 182), 0x200),   # SWS_LANCZOS
+]
+
 GEOMS = [
     ((640, 360, 320, 180), S.SWS_BICUBIC),       # 2:1, 8 taps
     ((644, 366, 1288, 732), S.SWS_BICUBIC),      # 1:2 upscale, 4 taps, ragged tiles
@@ -94,6 +102,20 @@ def test_16bit_planar_destinations(sf, df, geom, flags):
         name = _run(case, mode=mode)
         if _sub(sf) == _sub(df) and sw <= 7 * dw:
             assert name == ("scale16_i19" if "le" in sf else "scale8_i19"), name
+
+
+@pytest.mark.parametrize("sf", ["rgb24", "bgr24", "rgba", "bgra", "argb", "abgr"])
+@pytest.mark.parametrize("df", ["yuv420p16le", "yuv444p16le", "yuv422p16le"])
+@pytest.mark.parametrize("geom,flags", RGB_GEOMS_EARLY)
+def test_packed_rgb_sources_to_16bit_planar(sf, df, geom, flags):
+    sw, sh, dw, dh = geom
+    case = dict(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags | BX)
+    for mode in ("noise", "extreme"):
+        name = _run(case, mode=mode)
+        if "420" not in df:          # (a 4:2:0 destination doubles the vertical chroma ratio: its bank can exceed the kernel's taps)
+            assert name in ("scale_rgb_i19", "generic_tile"), name
+    for rng in ((0, 1), (1, 0)):
+        _run(case, ctx_kwargs=dict(src_range=rng[0], dst_range=rng[1]))
 
 
 @pytest.mark.parametrize("sf,df", [("yuvj420p", "yuv420p16le"), ("yuv420p", "yuv444p16le"), ("yuv420p10le", "yuv420p16le"),
