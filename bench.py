@@ -16,7 +16,7 @@ e2e     : Mpixels/s through the reference-facing call sws_scale() with HOST
           (page-locked) buffers -- H2D + kernel + D2H inside the timed region.
 e2e_pageable   : the same call on plain pageable numpy buffers (what av_frame_get_buffer() hands a caller).
 e2e_batch_host : sws_cuda_scale_batch_host(), several host frames in flight per device.
-configs : BASELINE.json configs[0..3] (C1..C4) and the scaler's widening rows (X1..X3, E1, E2, C3b) device-resident,
+configs : BASELINE.json configs[0..3] (C1..C4) and the scaler's widening rows (X1..X3, X6, X8, E1, E2, C3b) device-resident,
           same method as `value` (N=1 only).
 roofline: algorithmic bytes (4.5 B/pixel) / average kernel
           duration, against MEASURED_PEAKS.json hbm_gbs.
@@ -406,7 +406,7 @@ def run_b200_arm(args, rank, local_rank, world):
             tag = cfg[0].split()[0]
             # C1..C4: BASELINE.json configs[0..3]; the rest: the scaler's widening rows (up / down scaling, 10-bit
             # and packed-RGB sources) and the encode-side conversion, so that they carry driver-timed numbers too
-            if tag not in ("C1", "C2", "C3", "C4", "C3b", "X1", "X2", "X3", "E1", "E2"):
+            if tag not in ("C1", "C2", "C3", "C4", "C3b", "X1", "X2", "X3", "X6", "X8", "E1", "E2"):
                 continue
             r = BC.measure(cfg, dev, peak, steps=max(5, min(args.steps, 20)))
             configs[tag] = {"workload": r["name"], "kernel": r["kernel"], "frames_per_step": r["frames"],
