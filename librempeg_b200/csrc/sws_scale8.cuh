@@ -544,7 +544,7 @@ __device__ __forceinline__ void s8_hfir_uv(const unsigned char *srow, int sh, co
 /* RGBK: 0 planar / semi-planar YUV output, 1 packed RGB with one chroma sample per pixel pair, 2 packed RGB with full
  * horizontal chroma (its own instantiation: carried as a run-time branch it cost X1 10 %) */
 template <int FS4, int RGBK, bool MMA, int SRCK, int MINB = 0>
-__global__ void __launch_bounds__(S8_THREADS, MINB ? MINB : (SRCK != S8_SRC_U8 || (MMA && FS4 > 2)) ? 3 : (RGBK || FS4 <= S8_LIGHT_FS4) ? S8_RGB_CTAS : 3)
+__global__ void __launch_bounds__(S8_THREADS, MINB ? MINB : (SRCK != S8_SRC_U8 || (MMA && FS4 > 2) || RGBK == 3) ? 3 : (RGBK || FS4 <= S8_LIGHT_FS4) ? S8_RGB_CTAS : 3)
 sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_u,
                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ Scale8Args A)
 {
@@ -1238,6 +1238,124 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 d[i] = orow[i];
             vl = nl_;
             vc = nc_;
+        }
+        return;
+    }
+
+    if (I19 && (A.dst_kind == SWSC_DST_RGB48 || A.dst_kind == SWSC_DST_BGR48)) {
+        /* ============ stage V + colour step over 19-bit lines, rgb48le / bgr48le: yuv2rgba64_{X,2,1}_c_template
+         * (output.c:1115-1300; one chroma sample per pixel pair) and yuv2rgba64_full_{X,2,1}_c_template (:1373-1560; one per
+         * pixel), 32-bit wrap-around exactly like the C templates.  warp = row; the row's taps sit in two registers per
+         * lane and are broadcast per tap.  Rows the reference hands to the _1 writers (one luma tap, one chroma tap or a
+         * bilinear chroma pair: vscale.c:135-147) shift the line itself instead of multiplying by 4096. ============ */
+        const bool swap = A.dst_kind == SWSC_DST_BGR48;
+        const int lfs = A.vl_size, cfs = A.vc_size;
+        const unsigned yofs = (unsigned)A.y_offset, ycf = (unsigned)A.y_coeff;
+        const unsigned v2r = (unsigned)A.v2r, v2g = (unsigned)A.v2g, u2g = (unsigned)A.u2g, u2b = (unsigned)A.u2b;
+        auto px16 = [&](unsigned yu, unsigned uu, unsigned vu, int &r, int &g, int &b) {
+            yu = (yu - yofs) * ycf + (1u << 13) - (1u << 29);
+            r = clip_uintp2(((int)(vu * v2r + yu) >> 14) + (1 << 15), 16);
+            g = clip_uintp2(((int)(vu * v2g + uu * u2g + yu) >> 14) + (1 << 15), 16);
+            b = clip_uintp2(((int)(uu * u2b + yu) >> 14) + (1 << 15), 16);
+        };
+        for (int ty = warp; ty < th; ty += 8) {
+            const int y = ry0 + ty;
+            const int16_t *lf = A.vl_coef16 + (size_t)y * lfs, *cf = A.vc_coef16 + (size_t)y * cfs;
+            const int l0 = lane < lfs ? (int)__ldg(lf + lane) : 0, l1 = lane + 32 < lfs ? (int)__ldg(lf + lane + 32) : 0;
+            const int k0 = lane < cfs ? (int)__ldg(cf + lane) : 0, k1 = lane + 32 < cfs ? (int)__ldg(cf + lane + 32) : 0;
+            const int cf0 = __shfl_sync(0xffffffffu, k0, 0), cf1 = __shfl_sync(0xffffffffu, k0, 1);
+            const bool chr2 = cfs == 2 && cf0 + cf1 == 4096 && (unsigned)cf1 <= 4096u;
+            const bool one = lfs == 1 && (cfs == 1 || chr2);          /* the _1 writers */
+            const bool one_c = one && (cfs == 1 || cf1 == 0);         /* ... with uvalpha == 0: chroma from the line too */
+            const int rl = __ldg(A.vl_pos32 + y) - lo_l, rc = __ldg(A.vc_pos32 + y) - lo_c;
+            uint8_t *drow = dst0 + (size_t)y * A.dst_stride[0];
+            if (!A.full_chr) {
+                /* lane = pixel pairs lane and lane + 32: luma columns 2 lane, 2 lane + 1, 64 + 2 lane, 65 + 2 lane */
+                const uint32_t *pl = hb_l + 2 * lane * lstride_w + rl;
+                const uint32_t *pu = hb_u + lane * cstride_w + rc, *pv = hb_v + lane * cstride_w + rc;
+                unsigned Y[4] = { 0, 0, 0, 0 }, U[2] = { 0, 0 }, V[2] = { 0, 0 };
+                for (int j = 0; j < lfs; j++) {
+                    const unsigned c = (unsigned)__shfl_sync(0xffffffffu, j < 32 ? l0 : l1, j & 31);
+                    Y[0] += pl[j] * c; Y[1] += pl[lstride_w + j] * c;
+                    Y[2] += pl[64 * lstride_w + j] * c; Y[3] += pl[65 * lstride_w + j] * c;
+                }
+                for (int j = 0; j < cfs; j++) {
+                    const unsigned c = (unsigned)__shfl_sync(0xffffffffu, j < 32 ? k0 : k1, j & 31);
+                    U[0] += pu[j] * c; U[1] += pu[32 * cstride_w + j] * c;
+                    V[0] += pv[j] * c; V[1] += pv[32 * cstride_w + j] * c;
+                }
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    unsigned y1 = (unsigned)((int)(Y[2 * k] - 0x40000000u) >> 14) + 0x10000u;
+                    unsigned y2 = (unsigned)((int)(Y[2 * k + 1] - 0x40000000u) >> 14) + 0x10000u;
+                    unsigned uu = (unsigned)((int)(U[k] - (128u << 23)) >> 14), vu = (unsigned)((int)(V[k] - (128u << 23)) >> 14);
+                    if (one) {
+                        y1 = (unsigned)((int)pl[64 * k * lstride_w] >> 2);
+                        y2 = (unsigned)((int)pl[(64 * k + 1) * lstride_w] >> 2);
+                        if (one_c) {
+                            uu = (unsigned)(((int)pu[32 * k * cstride_w] - (128 << 11)) >> 2);
+                            vu = (unsigned)(((int)pv[32 * k * cstride_w] - (128 << 11)) >> 2);
+                        }
+                    }
+                    int r1, g1, b1, r2, g2, b2;
+                    px16(y1, uu, vu, r1, g1, b1);
+                    px16(y2, uu, vu, r2, g2, b2);
+                    const int xp = 2 * (lane + 32 * k);                  /* first pixel of the pair inside the tile */
+                    if (xp < tw) {
+                        uint16_t *w = reinterpret_cast<uint16_t *>(drow) + 3 * (x0 + xp);
+                        const int f1 = swap ? b1 : r1, t1 = swap ? r1 : b1, f2 = swap ? b2 : r2, t2 = swap ? r2 : b2;
+                        if (((uintptr_t)w & 3) == 0) {
+                            uint32_t *w32 = reinterpret_cast<uint32_t *>(w);
+                            w32[0] = (uint32_t)f1 | ((uint32_t)g1 << 16);
+                            w32[1] = (uint32_t)t1 | ((uint32_t)f2 << 16);
+                            w32[2] = (uint32_t)g2 | ((uint32_t)t2 << 16);
+                        } else {
+                            w[0] = (uint16_t)f1; w[1] = (uint16_t)g1; w[2] = (uint16_t)t1;
+                            w[3] = (uint16_t)f2; w[4] = (uint16_t)g2; w[5] = (uint16_t)t2;
+                        }
+                    }
+                }
+            } else {
+                /* lane = pixels lane + 32 c, every one with its own chroma sample */
+                const uint32_t *pl = hb_l + lane * lstride_w + rl;
+                const uint32_t *pu = hb_u + lane * cstride_w + rc, *pv = hb_v + lane * cstride_w + rc;
+                /* yuv2rgba64_full_1_c_template with uvalpha != 0 keeps U and V unsigned: its >> 14 is a logical shift */
+                const bool ulog = lfs == 1 && cfs == 2 && cf0 + cf1 == 4096 && cf1 > 0 && cf1 <= 4096;
+                unsigned Y[4] = { 0, 0, 0, 0 }, U[4] = { 0, 0, 0, 0 }, V[4] = { 0, 0, 0, 0 };
+                for (int j = 0; j < lfs; j++) {
+                    const unsigned c = (unsigned)__shfl_sync(0xffffffffu, j < 32 ? l0 : l1, j & 31);
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        Y[q] += pl[32 * q * lstride_w + j] * c;
+                }
+                for (int j = 0; j < cfs; j++) {
+                    const unsigned c = (unsigned)__shfl_sync(0xffffffffu, j < 32 ? k0 : k1, j & 31);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        U[q] += pu[32 * q * cstride_w + j] * c;
+                        V[q] += pv[32 * q * cstride_w + j] * c;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    unsigned yv = (unsigned)((int)(Y[q] - 0x40000000u) >> 14) + 0x10000u;
+                    unsigned uu = ulog ? (U[q] - (128u << 23)) >> 14 : (unsigned)((int)(U[q] - (128u << 23)) >> 14);
+                    unsigned vu = ulog ? (V[q] - (128u << 23)) >> 14 : (unsigned)((int)(V[q] - (128u << 23)) >> 14);
+                    if (one) {
+                        yv = (unsigned)((int)pl[32 * q * lstride_w] >> 2);
+                        if (one_c) {
+                            uu = (unsigned)(((int)pu[32 * q * cstride_w] - (128 << 11)) >> 2);
+                            vu = (unsigned)(((int)pv[32 * q * cstride_w] - (128 << 11)) >> 2);
+                        }
+                    }
+                    int r, g, b;
+                    px16(yv, uu, vu, r, g, b);
+                    if (lane + 32 * q < tw) {
+                        uint16_t *w = reinterpret_cast<uint16_t *>(drow) + 3 * (x0 + lane + 32 * q);
+                        w[0] = (uint16_t)(swap ? b : r); w[1] = (uint16_t)g; w[2] = (uint16_t)(swap ? r : b);
+                    }
+                }
+            }
         }
         return;
     }

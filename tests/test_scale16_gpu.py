@@ -141,6 +141,36 @@ def test_16bit_planar_destinations_long_banks(flags):
             _run(dict(sw=g[0], sh=g[1], sf=sf, dw=g[2], dh=g[3], df=sf[:7] + "16le", flags=flags | BX), mode=mode)
 
 
+# ---- rgb48le / bgr48le through the scaler: yuv2rgba64_{X,2,1} and yuv2rgba64_full_{X,2,1} over 19-bit lines ----
+@pytest.mark.parametrize("sf", ["yuv420p", "nv12", "yuv422p", "yuv444p", "yuv420p10le", "yuv444p12le", "yuv422p16le", "p010le",
+                                "rgb24", "bgra"])
+@pytest.mark.parametrize("df", ["rgb48le", "bgr48le"])
+@pytest.mark.parametrize("geom,flags", GEOMS[:7])
+def test_rgb48_destinations_through_the_scaler(sf, df, geom, flags):
+    sw, sh, dw, dh = geom
+    case = dict(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags | BX)
+    for mode in ("noise", "extreme"):
+        name = _run(case, mode=mode)
+        if sf not in ("p010le", "rgb24", "bgra"):    # (wide raw RGB rows and p010 sources stay on the general kernel here)
+            assert name.endswith("_i19"), name
+
+
+@pytest.mark.parametrize("sf", ["yuv420p", "yuv444p", "yuv422p10le", "yuv444p16le", "nv12"])
+@pytest.mark.parametrize("df", ["rgb48le", "bgr48le"])
+@pytest.mark.parametrize("geom", [(644, 366), (321, 243), (322, 243), (64, 48)])
+@pytest.mark.parametrize("flags", [S.SWS_BICUBIC | BX, S.SWS_BILINEAR | BX | S.SWS_FULL_CHR_H_INT, S.SWS_POINT | BX,
+                                   S.SWS_LANCZOS | S.SWS_ACCURATE_RND])
+def test_rgb48_destinations_same_size(sf, df, geom, flags):
+    """Same-size conversions outside fast420_rgb16's shapes (4:4:4 / nv12 sources, odd widths = full chroma, the _1 and _2
+    writers of one- and two-tap rows)."""
+    w, h = geom
+    for mode in ("noise", "extreme"):
+        _run(dict(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=flags), mode=mode)
+    _run(dict(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=flags), ctx_kwargs=dict(src_range=1, dst_range=0))
+    _run(dict(sw=w, sh=h, sf=sf, dw=w, dh=2 * h, df=df, flags=flags))          # vertical only: one horizontal tap
+    _run(dict(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=flags), ctx_kwargs=dict(chr_pos=(0, 64, 128, 128)))
+
+
 def test_16bit_planar_destination_slices_and_strides():
     case = dict(sw=644, sh=366, sf="yuv420p", dw=400, dh=222, df="yuv420p16le", flags=S.SWS_BICUBIC | BX)
     src = T.Frame("yuv420p", 644, 366, pad=16).randomize(5)

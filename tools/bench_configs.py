@@ -55,6 +55,8 @@ CONFIGS = [
     ("X5 1080p yuvj420p->720p yuv420p bicubic (range)", 1920, 1080, "yuvj420p", 1280, 720, "yuv420p", S.SWS_BICUBIC | S.BX),
     ("X8 4K->1080p p010le->p010le bicubic", 3840, 2160, "p010le", 1920, 1080, "p010le", S.SWS_BICUBIC | S.BX),
     ("X9 4K->1080p p010le->nv12 bicubic", 3840, 2160, "p010le", 1920, 1080, "nv12", S.SWS_BICUBIC | S.BX),
+    ("X10 4K->1080p yuv420p10le->rgb48le bicubic (19-bit lines)", 3840, 2160, "yuv420p10le", 1920, 1080, "rgb48le", S.SWS_BICUBIC | S.BX),
+    ("X11 4K yuv444p10le->rgb48le bicubic (same size, full chroma)", 3840, 2160, "yuv444p10le", 3840, 2160, "rgb48le", S.SWS_BICUBIC | S.BX),
     ("X6 4K->1080p yuv420p10le->yuv420p16le bicubic (19-bit lines)", 3840, 2160, "yuv420p10le", 1920, 1080, "yuv420p16le", S.SWS_BICUBIC | S.BX),
     ("X7 1080p->4K yuv420p->yuv420p16le bicubic (19-bit lines)", 1920, 1080, "yuv420p", 3840, 2160, "yuv420p16le", S.SWS_BICUBIC | S.BX),
 ]
