@@ -2652,7 +2652,9 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     const bool rgbs = p->src_layout == SWSC_SRC_RGB;
     /* 19-bit lines (hScale8To19_c / hScale16To19_c, swscale.c:60-97,144-159): 16-bit planar YUV destinations only */
     const bool i19 = p->inter_bits == 19;
-    const bool rgb48 = p->dst_kind == SWSC_DST_RGB48 || p->dst_kind == SWSC_DST_BGR48;
+    /* (gbrpf32le rides along: always full chroma, always the X form, float stores) */
+    const bool rgb48 = p->dst_kind == SWSC_DST_RGB48 || p->dst_kind == SWSC_DST_BGR48 ||
+                       (p->dst_kind == SWSC_DST_GBRP && p->full_chr && !p->dst_alpha);
     if (i19 && ((p->dst_kind != SWSC_DST_PLANAR16 && !rgb48) || p->dst_shift))
         return 0;
     /* rgb48le / bgr48le: yuv2rgba64_{X,2,1} (one chroma sample per pixel pair) or, with SWS_FULL_CHR_H_INT, the _full_ forms */

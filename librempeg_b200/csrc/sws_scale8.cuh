@@ -1242,13 +1242,16 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
         return;
     }
 
-    if (I19 && (A.dst_kind == SWSC_DST_RGB48 || A.dst_kind == SWSC_DST_BGR48)) {
+    if (I19 && (A.dst_kind == SWSC_DST_RGB48 || A.dst_kind == SWSC_DST_BGR48 || A.dst_kind == SWSC_DST_GBRP)) {
         /* ============ stage V + colour step over 19-bit lines, rgb48le / bgr48le: yuv2rgba64_{X,2,1}_c_template
          * (output.c:1115-1300; one chroma sample per pixel pair) and yuv2rgba64_full_{X,2,1}_c_template (:1373-1560; one per
          * pixel), 32-bit wrap-around exactly like the C templates.  warp = row; the row's taps sit in two registers per
          * lane and are broadcast per tap.  Rows the reference hands to the _1 writers (one luma tap, one chroma tap or a
          * bilinear chroma pair: vscale.c:135-147) shift the line itself instead of multiplying by 4096. ============ */
         const bool swap = A.dst_kind == SWSC_DST_BGR48;
+        /* gbrpf32le: yuv2gbrpf32_full_X_c (output.c:2536-2610) -- always the X form with the real taps, the 16-bit result
+         * times 1.0f / 65535.0f (one IEEE multiply: bit-exact), planes G, B, R */
+        const bool gbrpf = A.dst_kind == SWSC_DST_GBRP;
         const int lfs = A.vl_size, cfs = A.vc_size;
         const unsigned yofs = (unsigned)A.y_offset, ycf = (unsigned)A.y_coeff;
         const unsigned v2r = (unsigned)A.v2r, v2g = (unsigned)A.v2g, u2g = (unsigned)A.u2g, u2b = (unsigned)A.u2b;
@@ -1265,7 +1268,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             const int k0 = lane < cfs ? (int)__ldg(cf + lane) : 0, k1 = lane + 32 < cfs ? (int)__ldg(cf + lane + 32) : 0;
             const int cf0 = __shfl_sync(0xffffffffu, k0, 0), cf1 = __shfl_sync(0xffffffffu, k0, 1);
             const bool chr2 = cfs == 2 && cf0 + cf1 == 4096 && (unsigned)cf1 <= 4096u;
-            const bool one = lfs == 1 && (cfs == 1 || chr2);          /* the _1 writers */
+            const bool one = !gbrpf && lfs == 1 && (cfs == 1 || chr2);          /* the _1 writers */
             const bool one_c = one && (cfs == 1 || cf1 == 0);         /* ... with uvalpha == 0: chroma from the line too */
             const int rl = __ldg(A.vl_pos32 + y) - lo_l, rc = __ldg(A.vc_pos32 + y) - lo_c;
             uint8_t *drow = dst0 + (size_t)y * A.dst_stride[0];
@@ -1320,7 +1323,7 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 const uint32_t *pl = hb_l + lane * lstride_w + rl;
                 const uint32_t *pu = hb_u + lane * cstride_w + rc, *pv = hb_v + lane * cstride_w + rc;
                 /* yuv2rgba64_full_1_c_template with uvalpha != 0 keeps U and V unsigned: its >> 14 is a logical shift */
-                const bool ulog = lfs == 1 && cfs == 2 && cf0 + cf1 == 4096 && cf1 > 0 && cf1 <= 4096;
+                const bool ulog = !gbrpf && lfs == 1 && cfs == 2 && cf0 + cf1 == 4096 && cf1 > 0 && cf1 <= 4096;
                 unsigned Y[4] = { 0, 0, 0, 0 }, U[4] = { 0, 0, 0, 0 }, V[4] = { 0, 0, 0, 0 };
                 for (int j = 0; j < lfs; j++) {
                     const unsigned c = (unsigned)__shfl_sync(0xffffffffu, j < 32 ? l0 : l1, j & 31);
@@ -1351,8 +1354,15 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                     int r, g, b;
                     px16(yv, uu, vu, r, g, b);
                     if (lane + 32 * q < tw) {
-                        uint16_t *w = reinterpret_cast<uint16_t *>(drow) + 3 * (x0 + lane + 32 * q);
-                        w[0] = (uint16_t)(swap ? b : r); w[1] = (uint16_t)g; w[2] = (uint16_t)(swap ? r : b);
+                        if (gbrpf) {
+                            const int gx = x0 + lane + 32 * q;
+                            reinterpret_cast<float *>(drow)[gx] = __fmul_rn(1.0f / 65535.0f, (float)g);
+                            reinterpret_cast<float *>(dst1 + (size_t)y * A.dst_stride[1])[gx] = __fmul_rn(1.0f / 65535.0f, (float)b);
+                            reinterpret_cast<float *>(dst2 + (size_t)y * A.dst_stride[2])[gx] = __fmul_rn(1.0f / 65535.0f, (float)r);
+                        } else {
+                            uint16_t *w = reinterpret_cast<uint16_t *>(drow) + 3 * (x0 + lane + 32 * q);
+                            w[0] = (uint16_t)(swap ? b : r); w[1] = (uint16_t)g; w[2] = (uint16_t)(swap ? r : b);
+                        }
                     }
                 }
             }

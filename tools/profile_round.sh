@@ -29,6 +29,9 @@ cap fast_hi8 sws_fast420_hi8 "C3b 4K" 16 $((3840*2160*16))
 cap scale_rgb sws_scale8 "E2 4K" 16 $((3840*2160*16))
 cap scale16 sws_scale8 "X3 4K" 16 $((3840*2160*16))
 cap scale8_x2 sws_scale8 "X2 4K" 16 $((3840*2160*16))
+cap scale_i19 sws_scale8 "X6 4K" 16 $((3840*2160*16))
+cap scale_p010 sws_scale8 "X8 4K" 16 $((3840*2160*16))
+cap scale_rgb48 sws_scale8 "X10 4K" 16 $((3840*2160*16))
 cap copy8 sws_copy8 "U1 4K" 16 $((3840*2160*16))
 cap full444 sws_full444 "F1 4K" 16 $((3840*2160*16))
 cap rgb444 sws_rgb444 "F3 4K" 16 $((3840*2160*16))

@@ -26,11 +26,17 @@ CASES = [
     dict(sw=640, sh=360, sf="yuvj420p", dw=400, dh=224, df="yuv420p", flags=S.SWS_BICUBIC | BX),         # scale8_dp4a + range
     dict(sw=640, sh=360, sf="yuv420p10le", dw=400, dh=224, df="yuv420p10le", flags=S.SWS_BICUBIC | BX),  # scale16_dp2a
     dict(sw=640, sh=360, sf="yuv422p12le", dw=800, dh=450, df="yuv420p", flags=S.SWS_LANCZOS | BX),      # scale16_dp2a, dither
+    dict(sw=640, sh=360, sf="yuv420p", dw=400, dh=224, df="yuv420p16le", flags=S.SWS_BICUBIC | BX),      # scale8_i19 (19-bit lines)
+    dict(sw=640, sh=360, sf="yuv422p10le", dw=800, dh=450, df="yuv422p16le", flags=S.SWS_LANCZOS | BX),  # scale16_i19
+    dict(sw=640, sh=360, sf="yuv420p10le", dw=400, dh=224, df="rgb48le", flags=S.SWS_BICUBIC | BX),      # scale16_i19, rgb48 pair writer
+    dict(sw=321, sh=243, sf="yuv444p", dw=321, dh=243, df="bgr48le", flags=S.SWS_BICUBIC | BX),          # scale8_i19, rgb48 full chroma
+    dict(sw=644, sh=366, sf="bgra", dw=322, dh=182, df="yuv444p16le", flags=S.SWS_BICUBIC | BX),         # scale_rgb_i19
+    dict(sw=640, sh=360, sf="p010le", dw=400, dh=224, df="p010le", flags=S.SWS_BICUBIC | BX),            # scale16_dp2a, p010 both sides
     dict(sw=644, sh=366, sf="rgb24", dw=644, dh=366, df="yuv420p", flags=S.SWS_BICUBIC | BX),            # rgb420
     dict(sw=644, sh=366, sf="bgra", dw=322, dh=182, df="nv12", flags=S.SWS_BICUBIC | BX),                # RGB source, scaled
     dict(sw=644, sh=366, sf="yuv444p", dw=644, dh=366, df="rgb24", flags=S.SWS_BICUBIC | BX),            # full444
     dict(sw=644, sh=366, sf="rgb24", dw=644, dh=366, df="yuv444p", flags=S.SWS_BICUBIC | BX),            # rgb444
-    dict(sw=644, sh=366, sf="yuv444p", dw=400, dh=300, df="rgb48le", flags=S.SWS_BICUBIC | BX),          # generic
+    dict(sw=644, sh=366, sf="rgb48le", dw=400, dh=300, df="yuv420p", flags=S.SWS_BICUBIC | BX),          # generic (rgb48 source)
     dict(sw=644, sh=366, sf="nv12", dw=644, dh=366, df="yuv420p", flags=S.SWS_BICUBIC | BX),             # copy8
     dict(sw=644, sh=366, sf="yuv420p10le", dw=644, dh=366, df="yuv420p", flags=S.SWS_BICUBIC | BX),      # depthcopy
     dict(sw=644, sh=366, sf="rgba", dw=644, dh=366, df="bgra", flags=S.SWS_BICUBIC | BX),                # rgb_shuffle
