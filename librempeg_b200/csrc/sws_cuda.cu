@@ -2352,13 +2352,13 @@ static scale8_kernel_t pick_scale8(int fs4, int rgbk, bool mma, int srck, bool w
 #define S8_PICK_K(M, K) (rgbk == 2 ? S8_PICK(2, M, K) : rgbk == 1 ? S8_PICK(1, M, K) : S8_PICK(0, M, K))
     if (rgbk == 3)              /* 19-bit lines into 16-bit planar destinations: dot-product horizontal stage only */
         return srck == S8_SRC_U16 ? S8_PICK(3, false, S8_SRC_U16) : srck == S8_SRC_RGB ? S8_PICK(3, false, S8_SRC_RGB)
-                                                                                        : S8_PICK(3, false, S8_SRC_U8);
+               : srck == S8_SRC_P010 ? S8_PICK(3, false, S8_SRC_P010) : S8_PICK(3, false, S8_SRC_U8);
     if (srck == S8_SRC_RGB)     /* packed 8-bit RGB sources: reader stage + IDP.2A horizontal stage */
         return S8_PICK_K(false, S8_SRC_RGB);
     if (srck == S8_SRC_U16)     /* 9..16-bit planar sources: IDP.2A horizontal stage */
         return S8_PICK_K(false, S8_SRC_U16);
-    if (srck == S8_SRC_P010)    /* p010le sources: planar / semi-planar YUV or shared-chroma packed RGB out */
-        return rgbk == 1 ? S8_PICK(1, false, S8_SRC_P010) : S8_PICK(0, false, S8_SRC_P010);
+    if (srck == S8_SRC_P010)    /* p010le sources */
+        return rgbk == 3 ? S8_PICK(3, false, S8_SRC_P010) : S8_PICK_K(false, S8_SRC_P010);
     if (mma)                    /* fs4 = K steps of the tensor-pipe horizontal stage */
         return rgbk == 2 ? S8_PICK_MMA(2) : rgbk == 1 ? S8_PICK_MMA(1) : S8_PICK_MMA(0);
     return S8_PICK_K(false, S8_SRC_U8);
@@ -2675,8 +2675,6 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     const int srck = rgbs ? S8_SRC_RGB : p10 ? S8_SRC_P010 : s16 ? S8_SRC_U16 : S8_SRC_U8;
     if (s16 && !p10 && (p->src_layout != SWSC_SRC_PLANAR || p->src_shift || p->src_bits > 16))
         return 0;
-    if (p10 && (i19 || p->full_chr))
-        return 0;                     /* (compiled for the planar and the shared-chroma packed RGB writers only) */
     /* destinations: 8-bit planar / semi-planar YUV, 9..14-bit planar YUV, or packed 8-bit RGB with one chroma
      * sample per pixel pair */
     const bool rgb = (p->dst_kind >= SWSC_DST_RGB24 && p->dst_kind <= SWSC_DST_ABGR) ||
@@ -2987,7 +2985,7 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.hl_goff = st->s8_hl_goff; a.hc_goff = st->s8_hc_goff; a.hl_B = st->s8_hl_B; a.hc_B = st->s8_hc_B;
     dim3 grid((p->dst_w + S8_TW - 1) / S8_TW, (y1 - y0 + st->s8_tile_h - 1) / st->s8_tile_h, nb_frames);
     pick_scale8(st->s8_fs4, i19 ? 3 : rgb ? (p->full_chr ? 2 : 1) : 0, st->s8_mma, st->s8_srck, st->s8_wide)<<<grid, S8_THREADS, st->s8_smem, stream>>>(my, mu, mv, a);
-    st->kernel_name = rgbs ? (i19 ? "scale_rgb_i19" : "scale_rgb_dp2a") : i19 ? (st->s8_srck == S8_SRC_U16 ? "scale16_i19" : "scale8_i19")
+    st->kernel_name = rgbs ? (i19 ? "scale_rgb_i19" : "scale_rgb_dp2a") : i19 ? (st->s8_srck == S8_SRC_U16 || st->s8_srck == S8_SRC_P010 ? "scale16_i19" : "scale8_i19")
                            : st->s8_srck == S8_SRC_U16 || st->s8_srck == S8_SRC_P010 ? "scale16_dp2a" : st->s8_mma ? "scale8_mma" : "scale8_dp4a";
     CUDA_OK(cudaGetLastError());
     st->launches++;

@@ -364,7 +364,7 @@ __device__ __forceinline__ int s16_hfir(const unsigned char *srow, int sh, int h
 
 /* one staged row of interleaved 16-bit chroma (p010le: U in the low, V in the high half of every word; p010LEToUV_c,
  * input.c) for one output column: sample pairs of each plane are cut out of two words with PRMT, shifted down by 6 */
-template <int FS4>
+template <int FS4, bool I19 = false>
 __device__ __forceinline__ void s16_hfir_uv(const unsigned char *srow, int hshift, const uint32_t (&cl)[FS4],
                                             const uint32_t (&ch)[FS4], int &u, int &v)
 {
@@ -381,8 +381,8 @@ __device__ __forceinline__ void s16_hfir_uv(const unsigned char *srow, int hshif
         vl = dp2a_lo_uu(v0, cl[k], vl); vh = dp2a_lo_us(v0, ch[k], vh);
         vl = dp2a_hi_uu(v1, cl[k], vl); vh = dp2a_hi_us(v1, ch[k], vh);
     }
-    u = min(((uh << 8) + ul) >> hshift, (1 << 15) - 1);
-    v = min(((vh << 8) + vl) >> hshift, (1 << 15) - 1);
+    u = min(((uh << 8) + ul) >> hshift, I19 ? (1 << 19) - 1 : (1 << 15) - 1);
+    v = min(((vh << 8) + vl) >> hshift, I19 ? (1 << 19) - 1 : (1 << 15) - 1);
 }
 
 /* vertical FIR for NC columns (transposed 15-bit lines, cstep words apart): bias + sum of taps, before
@@ -1028,8 +1028,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
                 if (2 * m < left) {
                     int ua, ub, va, vb;
                     if (P10) {               /* interleaved 16-bit chroma */
-                        s16_hfir_uv<FS4>(sp, A.h_shift, cl, chh, ua, va);
-                        s16_hfir_uv<FS4>(sp + rowbytes, A.h_shift, cl, chh, ub, vb);
+                        s16_hfir_uv<FS4, I19>(sp, A.h_shift, cl, chh, ua, va);
+                        s16_hfir_uv<FS4, I19>(sp + rowbytes, A.h_shift, cl, chh, ub, vb);
                     } else if (S16) {        /* planar 16-bit chroma */
                         ua = s16_hfir<FS4, I19>(sp, sh, A.h_shift, cl, chh);
                         ub = s16_hfir<FS4, I19>(sp + seg, sh, A.h_shift, cl, chh);

@@ -151,7 +151,7 @@ def test_rgb48_destinations_through_the_scaler(sf, df, geom, flags):
     case = dict(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df=df, flags=flags | BX)
     for mode in ("noise", "extreme"):
         name = _run(case, mode=mode)
-        if sf not in ("p010le", "rgb24", "bgra"):    # (wide raw RGB rows and p010 sources stay on the general kernel here)
+        if sf not in ("rgb24", "bgra"):    # (wide raw RGB rows stay on the general kernel here)
             assert name.endswith("_i19"), name
 
 
@@ -183,7 +183,8 @@ def test_16bit_planar_destination_slices_and_strides():
 
 # ---- p010le on either side of the scaler: p010LEToY/UV_c readers (container >> 6, interleaved chroma) and the
 # yuv2p010l1/lX_c, yuv2p010cX_c writers (output.c:538-589) ----
-@pytest.mark.parametrize("df", ["yuv420p10le", "yuv420p", "nv12", "p010le", "yuv444p12le", "rgb24", "bgra", "yuvj420p"])
+@pytest.mark.parametrize("df", ["yuv420p10le", "yuv420p", "nv12", "p010le", "yuv444p12le", "rgb24", "bgra", "yuvj420p",
+                                "yuv420p16le", "gbrpf32le"])
 @pytest.mark.parametrize("geom,flags", GEOMS)
 def test_p010_sources(df, geom, flags):
     sw, sh, dw, dh = geom
@@ -191,7 +192,7 @@ def test_p010_sources(df, geom, flags):
     for mode in ("noise", "extreme"):
         name = _run(case, mode=mode)
         if (_sub(df) == (1, 1) or df in ("rgb24", "bgra")) and sw <= 7 * dw:
-            assert name == "scale16_dp2a", name
+            assert name == ("scale16_i19" if "16le" in df else "scale16_dp2a"), name
 
 
 @pytest.mark.parametrize("sf", ["yuv420p", "nv12", "nv21", "yuv420p10le", "yuv420p16le", "yuv422p", "rgb24", "bgra", "yuvj420p"])
