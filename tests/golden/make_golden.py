@@ -207,6 +207,41 @@ def cases():
     for sf, df in [("yuv420p", "yuv420p"), ("yuv420p10le", "yuv420p10le"), ("nv12", "yuv444p16le"), ("yuv420p", "grayf32le")]:
         out.append(dict(sw=162, sh=122, sf=sf, dw=162, dh=122, df=df, flags=R.SWS_BICUBIC | BX,
                         colorspace=[1, 0, 5, 1, 0, 1 << 16, 1 << 16]))
+    # the 19-bit lines of the scaling kernel family: 16-bit planar, rgb48 (pair and full-chroma writers, one-tap rows) and
+    # gbrpf32le destinations out of 8-bit / 10-bit / 16-bit / nv12 / p010 / packed RGB sources; p010le on both sides
+    for sf, df, g, fl in [("yuv420p", "yuv420p16le", (322, 182, 160, 90), R.SWS_BICUBIC | BX),
+                          ("nv12", "yuv444p16le", (322, 182, 400, 300), R.SWS_LANCZOS | BX),
+                          ("yuv420p10le", "yuv420p16le", (322, 182, 200, 100), R.SWS_BICUBIC | BX),
+                          ("yuv444p16le", "yuv444p16le", (322, 182, 400, 182), R.SWS_SPLINE | BX),
+                          ("yuv422p12le", "yuv422p16le", (322, 182, 322, 364), R.SWS_BILINEAR | BX),
+                          ("bgra", "yuv444p16le", (322, 182, 160, 90), R.SWS_BICUBIC | BX),
+                          ("rgb24", "yuv422p16le", (322, 182, 400, 300), R.SWS_BILINEAR | BX),
+                          ("yuv420p", "yuv420p16le", (1280, 720, 212, 120), R.SWS_LANCZOS | BX),
+                          ("yuv420p", "rgb48le", (322, 182, 160, 90), R.SWS_BICUBIC | BX),
+                          ("yuv420p10le", "bgr48le", (322, 182, 400, 300), R.SWS_LANCZOS | BX),
+                          ("yuv444p10le", "rgb48le", (322, 182, 322, 182), R.SWS_BICUBIC | BX),
+                          ("yuv444p", "bgr48le", (321, 181, 200, 100), R.SWS_BILINEAR | BX),
+                          ("nv12", "rgb48le", (322, 182, 322, 364), R.SWS_BILINEAR | BX),
+                          ("yuv422p16le", "rgb48le", (322, 182, 400, 182), R.SWS_BICUBIC | BX),
+                          ("yuv420p", "rgb48le", (323, 181, 323, 181), R.SWS_BILINEAR | BX | R.SWS_FULL_CHR_H_INT),
+                          ("bgra", "rgb48le", (322, 182, 200, 100), R.SWS_BICUBIC | BX),
+                          ("yuv420p", "gbrpf32le", (322, 182, 160, 90), R.SWS_BICUBIC | BX),
+                          ("yuv422p10le", "gbrpf32le", (322, 182, 400, 300), R.SWS_LANCZOS | BX),
+                          ("p010le", "p010le", (322, 182, 160, 90), R.SWS_BICUBIC | BX),
+                          ("p010le", "nv12", (322, 182, 400, 300), R.SWS_LANCZOS | BX),
+                          ("p010le", "yuv420p10le", (322, 182, 200, 100), R.SWS_BILINEAR | BX),
+                          ("p010le", "bgra", (322, 182, 160, 90), R.SWS_BICUBIC | BX),
+                          ("p010le", "rgb48le", (322, 182, 160, 90), R.SWS_BICUBIC | BX),
+                          ("p010le", "yuv420p16le", (322, 182, 400, 300), R.SWS_BICUBIC | BX),
+                          ("yuv420p", "p010le", (322, 182, 160, 90), R.SWS_BICUBIC | BX),
+                          ("nv12", "p010le", (322, 182, 400, 300), R.SWS_LANCZOS | BX),
+                          ("yuv420p16le", "p010le", (322, 182, 200, 100), R.SWS_BILINEAR | BX),
+                          ("rgb24", "p010le", (322, 182, 160, 90), R.SWS_BICUBIC | BX)]:
+        out.append(dict(sw=g[0], sh=g[1], sf=sf, dw=g[2], dh=g[3], df=df, flags=fl))
+    for rng in [(0, 1), (1, 0)]:
+        for sf, df in [("yuv420p", "yuv420p16le"), ("yuv420p10le", "rgb48le"), ("p010le", "p010le")]:
+            out.append(dict(sw=322, sh=182, sf=sf, dw=200, dh=120, df=df, flags=R.SWS_BICUBIC | BX,
+                            ctx_kwargs=dict(src_range=rng[0], dst_range=rng[1])))
     for i, c in enumerate(out):
         c.setdefault("seed", 100 + i)
         c.setdefault("mode", "extreme" if i % 7 == 3 else "noise")
