@@ -2655,7 +2655,9 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
     /* (gbrpf32le rides along: always full chroma, always the X form, float stores) */
     const bool rgb48 = p->dst_kind == SWSC_DST_RGB48 || p->dst_kind == SWSC_DST_BGR48 ||
                        (p->dst_kind == SWSC_DST_GBRP && p->full_chr && !p->dst_alpha);
-    if (i19 && ((p->dst_kind != SWSC_DST_PLANAR16 && !rgb48) || p->dst_shift))
+    /* grayf32le: the 16-bit luma writer with a float store, no chroma stages at all */
+    const bool grayf = p->dst_kind == SWSC_DST_PLANARF32 && !p->dst_has_chroma;
+    if (i19 && ((p->dst_kind != SWSC_DST_PLANAR16 && !rgb48 && !grayf) || p->dst_shift))
         return 0;
     /* rgb48le / bgr48le: yuv2rgba64_{X,2,1} (one chroma sample per pixel pair) or, with SWS_FULL_CHR_H_INT, the _full_ forms */
     if (rgb48 && (!i19 || p->chr_dst_hsub != (p->full_chr ? 0 : 1) || p->chr_dst_vsub != 0 || p->special || p->unscaled_lut ||
@@ -2688,7 +2690,9 @@ static int scale8_setup(SwsCudaState *st, const SwsFirBank *hl, const SwsFirBank
         !(p->dst_kind == SWSC_DST_PLANARN && p->dst_bits >= 9 && p->dst_bits <= 14 && !p->dst_shift) &&
         !(p->dst_kind == SWSC_DST_P010 && p->dst_bits == 10 && p->dst_shift == 6))
         return 0;
-    if (!p->has_chroma || !p->dst_has_chroma || p->special || p->unscaled_lut)
+    if ((!p->has_chroma || !p->dst_has_chroma) && !grayf)
+        return 0;
+    if (p->special || p->unscaled_lut)
         return 0;
     if (hl->size > 32 || hc->size > 32 || vl->size > 38 || vc->size > 38)
         return 0;                     /* horizontal: 8 tap groups of four; vertical: two records of 20 taps (39 + parity pad) */
@@ -2902,7 +2906,8 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     const bool rgbs = st->s8_srck == S8_SRC_RGB;
     if (rgbs && !(p->src_rgb_half ? rgb420_matrix_ok(p) : rgb444_matrix_ok(p)))
         return 0;                     /* sws_setColorspaceDetails() installed a matrix the 14-bit readers cannot take */
-    const int nsrc = rgbs ? 1 : p->src_layout == SWSC_SRC_PLANAR ? 3 : 2;
+    const bool luma_only = !p->dst_has_chroma;        /* grayf32le: the chroma planes are never read (nor uploaded) */
+    const int nsrc = rgbs || luma_only ? 1 : p->src_layout == SWSC_SRC_PLANAR ? 3 : 2;
     for (int i = 0; i < nsrc; i++)
         if (!src[i] || !aligned16(src[i]) || (src_stride[i] & 15) || src_stride[i] < 16 ||
             (nb_frames > 1 && (src_fstride[i] & 15)))
@@ -2922,12 +2927,12 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
                            nb_frames, src_stride[0], fs_y, st->s8_seg_l >> es, S8_ROWS)) < 0)
         return ret;
     mu = my;
-    if (!rgbs && (ret = make_map_3d(&mu, edt, src[1], (cbytes + emask) >> es, p->chr_src_h,
+    if (!rgbs && !luma_only && (ret = make_map_3d(&mu, edt, src[1], (cbytes + emask) >> es, p->chr_src_h,
                                     nb_frames, src_stride[1], fs_u, (planar ? st->s8_seg_c : 2 * st->s8_seg_c) >> es,
                                     S8_ROWS)) < 0)
         return ret;
     mv = mu;
-    if (planar && !rgbs) {
+    if (planar && !rgbs && !luma_only) {
         const uint64_t fs_v = nb_frames > 1 ? src_fstride[2] : (uint64_t)src_stride[2] * p->chr_src_h;
         if ((ret = make_map_3d(&mv, edt, src[2], (cbytes + emask) >> es, p->chr_src_h,
                                nb_frames, src_stride[2], fs_v, st->s8_seg_c >> es, S8_ROWS)) < 0)
@@ -2954,6 +2959,7 @@ static int scale8_launch(SwsCudaState *st, const uint8_t *const src[4], const in
     a.chr_rc_coeff = (int)p->chr_rc_coeff; a.chr_rc_offset = (int)p->chr_rc_offset;
     a.out_bits = p->dst_kind == SWSC_DST_PLANARN || p->dst_kind == SWSC_DST_P010 ? p->dst_bits : 8;
     a.out_lshift = p->dst_kind == SWSC_DST_P010 ? p->dst_shift : 0;
+    a.no_chroma = !p->dst_has_chroma;
     if (rgbs) {
         /* matrix rows as 16-bit pairs in the byte order of a pixel word (unused bytes get a zero coefficient) */
         int ky[4] = { 0, 0, 0, 0 }, ku[4] = { 0, 0, 0, 0 }, kv[4] = { 0, 0, 0, 0 };

@@ -90,6 +90,7 @@ struct Scale8Args {
     const int32_t *vl_pos32, *vc_pos32;
     int vl_size, vc_size;
     int out_bits;            /* planar destinations: 8, or 9..14 (16-bit little-endian samples) */
+    int no_chroma;           /* the destination has no chroma planes (grayf32le) */
     int out_lshift;          /* p010le destination: 10-bit samples shifted up by 6, chroma interleaved U first */
     int dither_bayer;        /* 8-bit planar output of > 8-bit sources: ff_dither_8x8_128 instead of the constant 64 */
     const int *hl_pos, *hc_pos;
@@ -569,7 +570,8 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     const int CW = 1 << cs;
     const int cx0 = x0 >> A.hs;
     const int cy0 = ry0 >> A.vs;
-    const int cy1 = (ry1 == A.dst_h) ? A.chr_dst_h : (ry1 >> A.vs);
+    /* (a destination without chroma planes -- grayf32le -- has no chroma rows: every chroma stage below is skipped) */
+    const int cy1 = A.no_chroma ? cy0 : (ry1 == A.dst_h) ? A.chr_dst_h : (ry1 >> A.vs);
     const int ch = cy1 - cy0;
     const int slot = A.slot_bytes;
 
@@ -1378,11 +1380,20 @@ sws_scale8_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
             const uint32_t *col = hb_l + lane * lstride_w + (__ldg(A.vl_pos32 + y) - lo_l);
             int v[S8_TW / 32];
             s19_vrow<S8_TW / 32>(col, 32 * lstride_w, A.vl_coef16 + (size_t)y * A.vl_size, A.vl_size, lane, v);
-            uint16_t *d = reinterpret_cast<uint16_t *>(dst0 + (size_t)y * A.dst_stride[0]) + x0 + lane;
+            if (A.dst_kind == SWSC_DST_PLANARF32) {
+                /* yuv2plane1_float_c / yuv2planeX_float_c (output.c:219-263): the 16-bit value times 1.0f / 65535.0f */
+                float *d = reinterpret_cast<float *>(dst0 + (size_t)y * A.dst_stride[0]) + x0 + lane;
 #pragma unroll
-            for (int c = 0; c < S8_TW / 32; c++)
-                if (lane + 32 * c < tw)
-                    d[32 * c] = (uint16_t)v[c];
+                for (int c = 0; c < S8_TW / 32; c++)
+                    if (lane + 32 * c < tw)
+                        d[32 * c] = __fmul_rn(1.0f / 65535.0f, (float)v[c]);
+            } else {
+                uint16_t *d = reinterpret_cast<uint16_t *>(dst0 + (size_t)y * A.dst_stride[0]) + x0 + lane;
+#pragma unroll
+                for (int c = 0; c < S8_TW / 32; c++)
+                    if (lane + 32 * c < tw)
+                        d[32 * c] = (uint16_t)v[c];
+            }
         }
         for (int task = warp; task < 2 * ch; task += 8) {
             const int pl = task & 1, y = cy0 + (task >> 1);

@@ -171,6 +171,19 @@ def test_rgb48_destinations_same_size(sf, df, geom, flags):
     _run(dict(sw=w, sh=h, sf=sf, dw=w, dh=h, df=df, flags=flags), ctx_kwargs=dict(chr_pos=(0, 64, 128, 128)))
 
 
+@pytest.mark.parametrize("sf", ["yuv420p", "nv12", "yuv444p10le", "yuv422p16le", "p010le", "bgra", "yuvj420p"])
+@pytest.mark.parametrize("geom,flags", GEOMS[:7])
+def test_grayf32_destination_luma_only(sf, geom, flags):
+    """grayf32le: yuv2plane1/X_float over the 19-bit luma lines; the chroma stages (and planes) are skipped."""
+    sw, sh, dw, dh = geom
+    case = dict(sw=sw, sh=sh, sf=sf, dw=dw, dh=dh, df="grayf32le", flags=flags | BX)
+    for mode in ("noise", "extreme"):
+        name = _run(case, mode=mode)
+        if sf != "bgra":
+            assert name.endswith("_i19"), name
+    _run(case, ctx_kwargs=dict(src_range=1, dst_range=0))
+
+
 def test_16bit_planar_destination_slices_and_strides():
     case = dict(sw=644, sh=366, sf="yuv420p", dw=400, dh=222, df="yuv420p16le", flags=S.SWS_BICUBIC | BX)
     src = T.Frame("yuv420p", 644, 366, pad=16).randomize(5)
