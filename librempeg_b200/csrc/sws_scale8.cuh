@@ -29,6 +29,19 @@
  * contraction is free: the host permutes B to match).  Measured: the legacy integer MMA sustains 2044 MAC /
  * clk / SM on B200, 8x the IDP.4A pipe (profiles/microbench/mma_i8_bench.cu), and the dot-product pipe is
  * left to the vertical stage.
+ *
+ * The same tile machinery serves a family of instantiations (template parameters of sws_scale8_kernel):
+ *   SRCK  S8_SRC_U8   8-bit planar / nv12 / nv21 (hScale8To15_c; MMA or IDP.4A horizontal stage)
+ *         S8_SRC_U16  9..16-bit planar (hScale16To15_c as IDP.2A over sample pairs, swscale.c:99-125)
+ *         S8_SRC_P010 p010le: containers >> 6 after the funnel shift, interleaved 16-bit chroma cut apart with PRMT
+ *         S8_SRC_RGB  packed 8-bit RGB: a reader stage per ring slot (input.c:264-345,1068-1180) feeding the 16-bit stage
+ *   RGBK  0 planar / semi-planar YUV of 8..14 bits and p010le (output.c:340-357,468-589)
+ *         1 packed 8-bit / 15-16 bpp RGB, one chroma sample per pixel pair (yuv2rgb_{X,2,1} + yuv2rgb_write)
+ *         2 packed 8-bit RGB with full horizontal chroma (yuv2rgb_full_{X,2,1} + yuv2rgb_write_full)
+ *         3 19-bit lines (hScale8To19_c / hScale16To19_c, one int32 sample per word) into 16-bit planar YUV
+ *           (yuv2planeX_16_c / yuv2plane1_16_c), rgb48le / bgr48le (yuv2rgba64[_full]_{X,2,1}), gbrpf32le
+ *           (yuv2gbrpf32_full_X_c) and grayf32le (yuv2plane1/X_float_c, luma only)
+ * with the range conversion of swscale.c:163-255 between the two FIR stages.  DESIGN.md section 4.3 has the measurements.
  */
 #pragma once
 
