@@ -48,6 +48,9 @@ FAST = [  # (sources, destinations, same size?) that the specialised kernels ser
     (["yuv444p", "yuvj444p"], RGB8, True),                                                         # full444
     (["yuv420p", "nv12", "nv21", "yuv422p", "yuv444p", "yuvj420p"],
      ["yuv420p", "nv12", "nv21", "yuv422p", "yuv444p"] + RGB8, False),                              # scale8
+    (["yuv420p", "nv12", "yuv422p", "yuv444p", "yuv420p10le", "yuv444p12le", "yuv422p16le", "p010le"] + RGB8,
+     ["yuv420p16le", "yuv422p16le", "yuv444p16le", "rgb48le", "bgr48le", "gbrpf32le", "grayf32le", "p010le"], False),  # 19-bit lines, p010
+    (["p010le"], ["yuv420p", "nv12", "yuv420p10le", "p010le", "yuv444p"] + RGB8, False),             # p010 sources
 ]
 
 
